@@ -1,0 +1,180 @@
+/*
+ * sdp_b200.h - C ABI of the B200-native Bellman backward-induction engine.
+ *
+ * This is the drop-in boundary of the hot path of pierre-haessig/stodynprog:
+ * plain pointers and sizes, no torch / numpy / C++ types.  All pointers named
+ * "device" are CUDA device pointers owned by the caller (the Python host code
+ * owns them through torch tensors and passes `tensor.data_ptr()`); `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *
+ * Conventions:
+ *   - every entry point returns 0 on success, a negative SDP_E* code otherwise,
+ *     and never throws across the ABI; `sdp_last_error()` gives the text;
+ *   - nothing is allocated, freed or retained by the library: all buffers are
+ *     caller-owned and caller-sized;
+ *   - no hidden synchronisation: work is enqueued on `stream`, the caller
+ *     synchronises; entry points are thread-safe for distinct streams;
+ *   - all arithmetic is IEEE fp64 with round-to-nearest and NO fused
+ *     multiply-add contraction, in the reference's operation order
+ *     (SURVEY.md App. A), so that cell indices / weights are bit-exact against
+ *     the reference's compiled Cython routine.
+ *
+ * The reference has no FFI of its own: its only native seam is one Cython
+ * function (stodynprog/dolointerpolation/multilinear_cython.pyx:17) and the
+ * hot loop is Python (stodynprog/stodynprog.py:466-534, :639-691, :693-775).
+ * Each entry point below cites the reference interface it replaces.
+ */
+#ifndef SDP_B200_H
+#define SDP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDP_ABI_VERSION 1
+#define SDP_MAX_D 4 /* the reference dispatches d = 1..4 (multilinear_cython.pyx:36-47) */
+
+/* error codes */
+#define SDP_OK 0
+#define SDP_EINVAL (-1)  /* bad argument (dimension, size, null pointer, alignment) */
+#define SDP_ECUDA (-2)   /* a CUDA runtime call or kernel launch failed */
+#define SDP_ENODEV (-3)  /* no CUDA device / wrong architecture */
+
+/* Rectangular state grid: what MlinInterpolator stores (stodynprog.py:261-265):
+ * smin = grid[0], smax = grid[-1], order = len(grid) per state variable.
+ * Values on the grid are C-order (`J.ravel()`, stodynprog.py:272). */
+typedef struct SdpGrid {
+    int32_t d;                /* number of state variables, 1..SDP_MAX_D */
+    int32_t order[SDP_MAX_D]; /* points per axis, each >= 2 */
+    double smin[SDP_MAX_D];
+    double smax[SDP_MAX_D];
+} SdpGrid;
+
+/* Per-state descriptor for the table build (host-built, device-read).
+ * The user's dyn/cost return arrays broadcastable to (U, W) for one state
+ * (U = flattened C-order control product, W = perturbation nodes); they are
+ * uploaded un-broadcast into a staging buffer and expanded on the device, which
+ * is what np.broadcast_arrays + astype(float) + ravel do at stodynprog.py:281-283.
+ * Slot k < d is next-state coordinate k, slot d is the stage cost g. */
+typedef struct SdpStateDesc {
+    int64_t entry_off;          /* first entry of the state's block in cell/lam tables */
+    int64_t g_off;              /* first entry of the state's block in the g table */
+    int64_t src[SDP_MAX_D + 1]; /* offset (in doubles) of each source array in staging */
+    int32_t us[SDP_MAX_D + 1];  /* source stride along the control index (0 = broadcast) */
+    int32_t ws[SDP_MAX_D + 1];  /* source stride along the perturbation index (0 = broadcast) */
+    int32_t U;                  /* admissible control combinations of this state */
+    int32_t Upad;               /* U rounded up to a multiple of 4 (16-byte aligned rows) */
+} SdpStateDesc;
+
+/* One unit of sweep work: a run of controls of one state, processed by one warp.
+ * States with more controls than the chunk size are split into several items
+ * whose partial (min, argmin) are combined by the finalize kernel. */
+typedef struct SdpItem {
+    int64_t entry_base; /* entry_off + u_begin */
+    int64_t g_base;     /* g_off + u_begin */
+    int32_t Upad;       /* row pitch of the state's block */
+    int32_t u_begin;    /* first control of the run (multiple of 4) */
+    int32_t u_count;    /* controls in the run */
+    int32_t state;      /* local state index */
+} SdpItem;
+
+/* Dense sweep tables of one shard of states (device pointers).
+ * Layout, per state block: entries [w][Upad] with the control index fastest:
+ *   cell[entry_off + w*Upad + u]            int32 flat base-cell index
+ *   lam [k*lam_plane + entry_off + w*Upad + u]   fp64 weight of state dim k
+ *   g   [g_off + u]              if g_per_w == 0 (cost does not depend on w)
+ *   g   [g_off + w*Upad + u]     if g_per_w == 1 (g_off == entry_off)
+ * Algorithmic bytes per admissible (x,u,w): 4 + 8*d + 8*(g_per_w ? 1 : 1/W). */
+typedef struct SdpTables {
+    const int32_t* cell;
+    const double* lam;
+    int64_t lam_plane;
+    const double* g;
+    int32_t g_per_w;
+    int32_t W;           /* perturbation nodes (1 for a deterministic system) */
+    int32_t expect;      /* 1: J = sum_w p_w*(g+J'); 0: deterministic, J = g+J' */
+    int32_t reserved;
+    const double* p;     /* [W] probabilities (ignored when expect == 0) */
+    const SdpItem* items;
+    int64_t n_items;
+    const int64_t* item_begin; /* [n_states+1]: items of state i are item_begin[i]..item_begin[i+1]-1 */
+    int64_t n_states;    /* states in this shard */
+} SdpTables;
+
+/* ABI / build identification. */
+int sdp_version(void);
+const char* sdp_last_error(void);
+/* Number of kernels launched by this library since load (for bench accounting). */
+int64_t sdp_launch_count(void);
+
+/* K0a - cell search on explicit points.
+ * Replaces the cell-search half of multilinear_interpolation_{1..4}d
+ * (multilinear_cython.pyx:72-79, :117-131, :177-193, :257-278).
+ * s: device [d][n]; cell: device [n]; lam: device [d][n]. */
+int sdp_cell_setup(const SdpGrid* grid, int64_t n, const double* s, int32_t* cell,
+                   double* lam, void* stream);
+
+/* K0b - table build for a chunk of states: broadcast-expand the staged
+ * dyn/cost outputs (stodynprog.py:674-677 + :281-283) and run the cell search.
+ * desc: device [n_states]; staging: device doubles; outputs as in SdpTables.
+ * Padding entries (U <= u < Upad) get cell 0, lam 0, g 0. */
+int sdp_build_tables(const SdpGrid* grid, int32_t W, int32_t g_per_w, int64_t n_states,
+                     const SdpStateDesc* desc, const double* staging, int32_t* cell,
+                     double* lam, int64_t lam_plane, double* g, int32_t max_Upad,
+                     void* stream);
+
+/* K1 - one Bellman sweep over a shard of states.
+ * Replaces the state loop of DPSolver.value_iteration (stodynprog.py:511-515)
+ * with _value_at_state_vect (:639-691): gather + nested lerp of J_prev
+ * (pyx:81-88, :133-140, :195-208, :280-300), + g, expectation over w
+ * (np.inner, :682), first-minimum argmin over the control product (:686).
+ * J_prev: device [prod(order)], the full previous value function.
+ * part_val/part_idx: device scratch [n_items].
+ * J_out: device [n_states]; argmin_out: device [n_states] flat C-order index
+ * into the state's control product. */
+int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
+              double* part_val, int32_t* part_idx, double* J_out, int32_t* argmin_out,
+              void* stream);
+
+/* K1' - fixed-policy backups (policy evaluation), `n_iter` iterations.
+ * Replaces the body of DPSolver.eval_policy (stodynprog.py:743-763).
+ * Tables are [w][n_states] planes (state index fastest):
+ *   cell[w*n_states + i], lam[k*lam_plane + w*n_states + i],
+ *   g[i] (g_per_w == 0) or g[w*n_states + i].
+ * J_a / J_b: device [n_grid] ping-pong buffers; iteration k reads one and writes
+ * states [state_begin, state_begin + n_states) of the other; on return the
+ * result is in J_a if n_iter is even, J_b if odd.
+ * rel_dp != 0: after each iteration J_ref_hist[k] = J[ref_index]; J -= that
+ * (stodynprog.py:760-762); requires the shard to be the whole grid.
+ * J_ref_hist: device [n_iter] (may be NULL when rel_dp == 0). */
+int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, const double* p,
+                    const int32_t* cell, const double* lam, int64_t lam_plane,
+                    const double* g, int64_t n_states, int64_t state_begin, int64_t n_grid,
+                    double* J_a, double* J_b, int32_t n_iter, int32_t rel_dp,
+                    int64_t ref_index, double* J_ref_hist, void* stream);
+
+/* Relative-DP normalisation: ref_out[0] = J[ref_index]; J[i] -= ref_out[0]
+ * (stodynprog.py:523-525, :760-762).  J: device [n]. */
+int sdp_rel_shift(double* J, int64_t n, int64_t ref_index, double* ref_out, void* stream);
+
+/* Sup-norm of the update, max_i |a[i] - b[i]| (NaN differences ignored), written
+ * to out[0].  New feature (the reference never computes a residual). */
+int sdp_supnorm_diff(const double* a, const double* b, int64_t n, double* out, void* stream);
+
+/* K2 - multilinear interpolation of n_v value rows at n_s points.
+ * Replaces multilinear_interpolation (multilinear_cython.pyx:17-49).
+ * values: device [n_v][prod(order)]; s: device [d][n_s]; out: device [n_v][n_s]. */
+int sdp_interp(const SdpGrid* grid, int64_t n_v, const double* values, int64_t n_s,
+               const double* s, double* out, void* stream);
+/* fp32 specialisation of the same routine (the `float` branch of the fused
+ * type `floating`, multilinear_cython.pyx:12-14,22-25). smin/smax are rounded
+ * to fp32 as the reference's float memoryviews would hold them. */
+int sdp_interp_f32(const SdpGrid* grid, int64_t n_v, const float* values, int64_t n_s,
+                   const float* s, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDP_B200_H */

@@ -1,0 +1,144 @@
+"""ctypes binding of libsdp_b200.so (C ABI declared in include/sdp_b200.h).
+
+The library is the product's only compute path.  There is NO fallback: if the
+shared object cannot be loaded, or an entry point returns an error, a
+`SdpLibraryError` is raised.  torch is used by the callers only to own device
+buffers; this module passes raw device pointers and the raw stream handle.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+SDP_MAX_D = 4
+SDP_ABI_VERSION = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libsdp_b200.so")
+
+
+class SdpLibraryError(RuntimeError):
+    """The CUDA extension is missing, stale, or one of its entry points failed."""
+
+
+class SdpGrid(ctypes.Structure):
+    _fields_ = [("d", ctypes.c_int32),
+                ("order", ctypes.c_int32 * SDP_MAX_D),
+                ("smin", ctypes.c_double * SDP_MAX_D),
+                ("smax", ctypes.c_double * SDP_MAX_D)]
+
+
+class SdpTables(ctypes.Structure):
+    _fields_ = [("cell", ctypes.c_void_p),
+                ("lam", ctypes.c_void_p),
+                ("lam_plane", ctypes.c_int64),
+                ("g", ctypes.c_void_p),
+                ("g_per_w", ctypes.c_int32),
+                ("W", ctypes.c_int32),
+                ("expect", ctypes.c_int32),
+                ("reserved", ctypes.c_int32),
+                ("p", ctypes.c_void_p),
+                ("items", ctypes.c_void_p),
+                ("n_items", ctypes.c_int64),
+                ("item_begin", ctypes.c_void_p),
+                ("n_states", ctypes.c_int64)]
+
+
+# numpy mirrors of the per-state descriptor and the work item (host-built arrays
+# uploaded verbatim; layouts must match the C structs, checked by the tests)
+STATE_DESC_DTYPE = np.dtype([("entry_off", np.int64),
+                             ("g_off", np.int64),
+                             ("src", np.int64, (SDP_MAX_D + 1,)),
+                             ("us", np.int32, (SDP_MAX_D + 1,)),
+                             ("ws", np.int32, (SDP_MAX_D + 1,)),
+                             ("U", np.int32),
+                             ("Upad", np.int32)], align=True)
+ITEM_DTYPE = np.dtype([("entry_base", np.int64),
+                       ("g_base", np.int64),
+                       ("Upad", np.int32),
+                       ("u_begin", np.int32),
+                       ("u_count", np.int32),
+                       ("state", np.int32)], align=True)
+assert STATE_DESC_DTYPE.itemsize == 104, STATE_DESC_DTYPE.itemsize
+assert ITEM_DTYPE.itemsize == 32, ITEM_DTYPE.itemsize
+
+_vp = ctypes.c_void_p
+_i32 = ctypes.c_int32
+_i64 = ctypes.c_int64
+_gp = ctypes.POINTER(SdpGrid)
+
+# name -> (restype, argtypes); every symbol include/sdp_b200.h declares
+SIGNATURES = {
+    "sdp_version": (ctypes.c_int, []),
+    "sdp_last_error": (ctypes.c_char_p, []),
+    "sdp_launch_count": (_i64, []),
+    "sdp_cell_setup": (ctypes.c_int, [_gp, _i64, _vp, _vp, _vp, _vp]),
+    "sdp_build_tables": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp,
+                                        _i32, _vp]),
+    "sdp_sweep": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sdp_policy_eval": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
+                                       _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
+    "sdp_rel_shift": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "sdp_supnorm_diff": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "sdp_interp": (ctypes.c_int, [_gp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "sdp_interp_f32": (ctypes.c_int, [_gp, _i64, _vp, _i64, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load (once) and type the shared library.  Raises SdpLibraryError."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise SdpLibraryError(
+            "CUDA extension not built: %s is missing. Run `python -m stodynprog_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU fallback." % p)
+    try:
+        lib = ctypes.CDLL(p)
+    except OSError as e:
+        raise SdpLibraryError("cannot load %s: %s" % (p, e))
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise SdpLibraryError("%s does not export %s (stale build?)" % (p, name))
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sdp_version() != SDP_ABI_VERSION:
+        raise SdpLibraryError("ABI version mismatch: library %d, binding %d"
+                              % (lib.sdp_version(), SDP_ABI_VERSION))
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(rc, what):
+    """Raise on a negative return code of an entry point."""
+    if rc != 0:
+        msg = load_library().sdp_last_error()
+        raise SdpLibraryError("%s failed (code %d): %s"
+                              % (what, rc, msg.decode("utf-8", "replace") if msg else ""))
+
+
+def make_grid(state_grid):
+    """SdpGrid from a list of 1-D grids: smin = g[0], smax = g[-1], order = len(g)
+    (what MlinInterpolator.__init__ keeps, reference stodynprog.py:261-265)."""
+    d = len(state_grid)
+    if not 1 <= d <= SDP_MAX_D:
+        raise ValueError("state dimension %d not supported by the CUDA kernels (1..%d)"
+                         % (d, SDP_MAX_D))
+    g = SdpGrid()
+    g.d = d
+    for k, ax in enumerate(state_grid):
+        g.order[k] = len(ax)
+        g.smin[k] = float(ax[0])
+        g.smax[k] = float(ax[-1])
+    return g
+
+
+def launch_count():
+    return int(load_library().sdp_launch_count())

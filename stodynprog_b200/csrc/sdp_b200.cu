@@ -1,0 +1,637 @@
+// sdp_b200.cu - hand-written sm_100a kernels + C ABI of the Bellman sweep engine.
+//
+// Hot path replaced (reference pierre-haessig/stodynprog, file:line relative to it):
+//   * cell search + gather + nested lerp of multilinear_interpolation_{1..4}d
+//     (stodynprog/dolointerpolation/multilinear_cython.pyx:54-300)
+//   * the per-state backup _value_at_state_vect (stodynprog/stodynprog.py:639-691)
+//     looped over the state grid by value_iteration (:511-515)
+//   * the policy-evaluation iteration of eval_policy (:743-763)
+//
+// This is a gather-reduce, not a contraction: no tensor cores.  The sweep kernel
+// streams the dense (cell, lambda, g) tables once from HBM with 128-bit
+// streaming loads (ld.global.cs: evict-first, no reuse), gathers the 2^d corners
+// of the previous value function through the read-only path (ld.global.nc, L1 +
+// L2 resident: J is at most a few MB), accumulates the expectation over the
+// perturbation nodes in registers in index order, and reduces (value, index)
+// lexicographically over the control run with warp shuffles - one warp per work
+// item (a state, or a run of controls of a state with many controls).
+//
+// Arithmetic contract: fp64, round-to-nearest, explicit
+// __dadd_rn/__dsub_rn/__dmul_rn/__ddiv_rn so that nvcc can never contract a
+// multiply-add into an FMA; truncating cast with x86 cvttsd2si out-of-range
+// semantics; weights are NOT clamped (linear extrapolation outside the grid).
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdlib.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <limits.h>
+#include <math.h>
+#include <atomic>
+
+#include "sdp_b200.h"
+
+// ---------------------------------------------------------------------------
+// error handling / accounting
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, const char* detail) {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+#define SDP_CUDA_CHECK(expr)                                              \
+    do {                                                                  \
+        cudaError_t _e = (expr);                                          \
+        if (_e != cudaSuccess)                                            \
+            return fail(SDP_ECUDA, #expr ": %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+#define SDP_LAUNCH_CHECK()                                                          \
+    do {                                                                            \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                         \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess)                                                      \
+            return fail(SDP_ECUDA, "kernel launch: %s", cudaGetErrorString(_e));    \
+    } while (0)
+
+extern "C" int sdp_version(void) { return SDP_ABI_VERSION; }
+extern "C" const char* sdp_last_error(void) { return g_err; }
+extern "C" int64_t sdp_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// ---------------------------------------------------------------------------
+// device-side grid description (kernel parameter, lives in constant bank)
+// ---------------------------------------------------------------------------
+template <typename T>
+struct GridT {
+    T smin[SDP_MAX_D];
+    T span[SDP_MAX_D];    // smax - smin   (pyx: `(smax[k]-smin[k])`, recomputed per point there)
+    T om1[SDP_MAX_D];     // (T)(order-1)
+    int order[SDP_MAX_D];
+    int stride[SDP_MAX_D];  // C-order strides M_k of the value array (pyx:109,164-165,235-237)
+};
+
+template <typename T>
+static int make_grid(const SdpGrid* g, GridT<T>* out, int64_t* n_grid) {
+    if (g == nullptr) return fail(SDP_EINVAL, "%s", "grid is NULL");
+    if (g->d < 1 || g->d > SDP_MAX_D) return fail(SDP_EINVAL, "%s", "grid.d must be 1..4");
+    int64_t n = 1;
+    for (int k = g->d - 1; k >= 0; --k) {
+        if (g->order[k] < 2)
+            return fail(SDP_EINVAL, "%s", "every state axis needs at least 2 grid points");
+        out->stride[k] = (int)n;
+        n *= g->order[k];
+        if (n >= (int64_t)INT_MAX) return fail(SDP_EINVAL, "%s", "grid has >= 2^31 points");
+    }
+    for (int k = 0; k < SDP_MAX_D; ++k) {
+        if (k < g->d) {
+            T lo = (T)g->smin[k], hi = (T)g->smax[k];
+            out->smin[k] = lo;
+            out->span[k] = hi - lo;
+            out->om1[k] = (T)(g->order[k] - 1);
+            out->order[k] = g->order[k];
+        } else {
+            out->smin[k] = 0; out->span[k] = 1; out->om1[k] = 1; out->order[k] = 2; out->stride[k] = 0;
+        }
+    }
+    if (n_grid) *n_grid = n;
+    return SDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// contraction-proof arithmetic
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+
+// C cast double->int as compiled for x86-64 (cvttsd2si): truncation toward zero;
+// NaN and anything whose truncation does not fit int32 give INT_MIN ("integer
+// indefinite"), which the reference then clamps to cell 0.
+__device__ __forceinline__ int x86_trunc(double t) {
+    if (!(t > -2147483649.0 && t < 2147483648.0)) return INT_MIN;
+    return __double2int_rz(t);
+}
+__device__ __forceinline__ int x86_trunc(float t) {
+    if (!(t >= -2147483648.0f && t < 2147483648.0f)) return INT_MIN;
+    return __float2int_rz(t);
+}
+
+// cell index q and barycentric weight lam along one axis (pyx:117-131):
+//   sn = (s - smin)/(smax - smin);  t = sn*(order-1)
+//   q = max(min((int)t, order-2), 0);  lam = t - q
+template <typename T>
+__device__ __forceinline__ void cell_1d(T s, T smin, T span, T om1, int order, int& q, T& lam) {
+    T sn = div_(sub_(s, smin), span);
+    T t = mul_(sn, om1);
+    int qi = x86_trunc(t);
+    qi = max(min(qi, order - 2), 0);
+    q = qi;
+    lam = sub_(t, (T)qi);
+}
+
+// nested lerp, last axis innermost (pyx:88,140,208,300):
+//   (1-l_K)*value(K+1 | corner 0) + l_K*value(K+1 | corner 1)
+template <typename T, int D, int K>
+struct Lerp {
+    __device__ __forceinline__ static T eval(const T* __restrict__ V, int base,
+                                             const int (&stride)[SDP_MAX_D], const T (&lam)[D]) {
+        T a = Lerp<T, D, K + 1>::eval(V, base, stride, lam);
+        T b = Lerp<T, D, K + 1>::eval(V, base + stride[K], stride, lam);
+        return add_(mul_(sub_((T)1, lam[K]), a), mul_(lam[K], b));
+    }
+};
+template <typename T, int D>
+struct Lerp<T, D, D> {
+    __device__ __forceinline__ static T eval(const T* __restrict__ V, int base,
+                                             const int (&)[SDP_MAX_D], const T (&)[D]) {
+        return __ldg(V + base);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// K0a: cell search on explicit points,  s [d][n] -> cell [n], lam [d][n]
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_cell_setup(GridT<double> G, int64_t n, const double* __restrict__ s,
+             int32_t* __restrict__ cell, double* __restrict__ lam) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        int q; double l;
+        cell_1d<double>(s[(int64_t)k * n + i], G.smin[k], G.span[k], G.om1[k], G.order[k], q, l);
+        base += q * G.stride[k];
+        lam[(int64_t)k * n + i] = l;
+    }
+    cell[i] = base;
+}
+
+extern "C" int sdp_cell_setup(const SdpGrid* grid, int64_t n, const double* s, int32_t* cell,
+                              double* lam, void* stream) {
+    GridT<double> G;
+    int rc = make_grid<double>(grid, &G, nullptr);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!s || !cell || !lam))) return fail(SDP_EINVAL, "%s", "sdp_cell_setup: bad arguments");
+    if (n == 0) return SDP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    switch (grid->d) {
+        case 1: k_cell_setup<1><<<blocks, 256, 0, st>>>(G, n, s, cell, lam); break;
+        case 2: k_cell_setup<2><<<blocks, 256, 0, st>>>(G, n, s, cell, lam); break;
+        case 3: k_cell_setup<3><<<blocks, 256, 0, st>>>(G, n, s, cell, lam); break;
+        default: k_cell_setup<4><<<blocks, 256, 0, st>>>(G, n, s, cell, lam); break;
+    }
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K0b: table build. One thread per (state, w, u) entry of the padded block;
+// u fastest across threads so the table writes are coalesced.
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_build_tables(GridT<double> G, int W, int g_per_w, int tiles_per_state,
+               const SdpStateDesc* __restrict__ desc, const double* __restrict__ staging,
+               int32_t* __restrict__ cell, double* __restrict__ lam, int64_t lam_plane,
+               double* __restrict__ g) {
+    const int64_t state = blockIdx.x / tiles_per_state;
+    const int tile = blockIdx.x % tiles_per_state;
+    const SdpStateDesc* ds = desc + state;
+    const int Upad = ds->Upad;
+    const int U = ds->U;
+    const int e = tile * blockDim.x + threadIdx.x;  // entry within the block: w*Upad + u
+    if (e >= W * Upad) return;
+    const int w = e / Upad;
+    const int u = e - w * Upad;
+    const int64_t off = ds->entry_off + e;
+    const bool live = u < U;
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double l = 0.0;
+        if (live) {
+            int q;
+            double sk = staging[ds->src[k] + (int64_t)u * ds->us[k] + (int64_t)w * ds->ws[k]];
+            cell_1d<double>(sk, G.smin[k], G.span[k], G.om1[k], G.order[k], q, l);
+            base += q * G.stride[k];
+        }
+        lam[(int64_t)k * lam_plane + off] = l;
+    }
+    cell[off] = base;
+    if (g_per_w || w == 0) {
+        double gv = 0.0;
+        if (live) gv = staging[ds->src[D] + (int64_t)u * ds->us[D] + (int64_t)w * ds->ws[D]];
+        g[ds->g_off + (g_per_w ? e : u)] = gv;
+    }
+}
+
+extern "C" int sdp_build_tables(const SdpGrid* grid, int32_t W, int32_t g_per_w, int64_t n_states,
+                                const SdpStateDesc* desc, const double* staging, int32_t* cell,
+                                double* lam, int64_t lam_plane, double* g, int32_t max_Upad,
+                                void* stream) {
+    GridT<double> G;
+    int rc = make_grid<double>(grid, &G, nullptr);
+    if (rc) return rc;
+    if (W < 1 || n_states < 0 || max_Upad < 0 || (max_Upad & 3))
+        return fail(SDP_EINVAL, "%s", "sdp_build_tables: bad sizes");
+    if (n_states == 0 || max_Upad == 0) return SDP_OK;
+    if (!desc || !staging || !cell || !lam || !g) return fail(SDP_EINVAL, "%s", "sdp_build_tables: NULL pointer");
+    int64_t per_state = (int64_t)W * max_Upad;
+    int tiles = (int)((per_state + 255) / 256);
+    int64_t blocks = n_states * tiles;
+    if (blocks > 0x7fffffffLL) return fail(SDP_EINVAL, "%s", "sdp_build_tables: chunk too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (grid->d) {
+        case 1: k_build_tables<1><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, tiles, desc, staging, cell, lam, lam_plane, g); break;
+        case 2: k_build_tables<2><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, tiles, desc, staging, cell, lam, lam_plane, g); break;
+        case 3: k_build_tables<3><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, tiles, desc, staging, cell, lam, lam_plane, g); break;
+        default: k_build_tables<4><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, tiles, desc, staging, cell, lam, lam_plane, g); break;
+    }
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K1: Bellman sweep
+// ---------------------------------------------------------------------------
+// numpy argmin order on (value, flat index): NaN beats everything, then the
+// smaller value, then the smaller index (first minimum wins; stodynprog.py:686,
+// SURVEY.md App. A.4).  Returns true when a is strictly preferred over b.
+__device__ __forceinline__ bool better(double av, int ai, double bv, int bi) {
+    const bool an = (av != av), bn = (bv != bv);
+    if (an | bn) return (an & bn) ? (ai < bi) : an;
+    if (av < bv) return true;
+    if (av > bv) return false;
+    return ai < bi;
+}
+
+// streamed table fragment for UPL consecutive controls of one (state, w) row
+template <int D, int UPL>
+struct Frag {
+    int cell[UPL];
+    double lam[D][UPL];
+};
+
+template <int D, int UPL>
+__device__ __forceinline__ void load_frag(Frag<D, UPL>& f, const int32_t* __restrict__ cell,
+                                          const double* __restrict__ lam, int64_t lam_plane,
+                                          int64_t off) {
+    if (UPL == 4) {
+        int4 c = __ldcs(reinterpret_cast<const int4*>(cell + off));
+        f.cell[0] = c.x; f.cell[1] = c.y; f.cell[2] = c.z; f.cell[3] = c.w;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double2* p = reinterpret_cast<const double2*>(lam + (int64_t)k * lam_plane + off);
+            double2 a = __ldcs(p);
+            double2 b = __ldcs(p + 1);
+            f.lam[k][0] = a.x; f.lam[k][1] = a.y; f.lam[k][2] = b.x; f.lam[k][3] = b.y;
+        }
+    } else {
+        int2 c = __ldcs(reinterpret_cast<const int2*>(cell + off));
+        f.cell[0] = c.x; f.cell[1] = c.y;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double2 a = __ldcs(reinterpret_cast<const double2*>(lam + (int64_t)k * lam_plane + off));
+            f.lam[k][0] = a.x; f.lam[k][1] = a.y;
+        }
+    }
+}
+
+template <int UPL>
+__device__ __forceinline__ void load_g(double (&gv)[UPL], const double* __restrict__ g, int64_t off) {
+    if (UPL == 4) {
+        const double2* p = reinterpret_cast<const double2*>(g + off);
+        double2 a = __ldcs(p), b = __ldcs(p + 1);
+        gv[0] = a.x; gv[1] = a.y; gv[2] = b.x; gv[3] = b.y;
+    } else {
+        double2 a = __ldcs(reinterpret_cast<const double2*>(g + off));
+        gv[0] = a.x; gv[1] = a.y;
+    }
+}
+
+template <int D, int UPL>
+__global__ void __launch_bounds__(256)
+k_sweep(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+        double* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+    extern __shared__ double p_sh[];
+    for (int i = threadIdx.x; i < T.W; i += blockDim.x) p_sh[i] = T.expect ? T.p[i] : 1.0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t item_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item_id >= T.n_items) return;
+    const SdpItem it = T.items[item_id];
+    const int W = T.W;
+    const int64_t pitch = it.Upad;
+
+    double best_v = CUDART_INF;
+    int best_i = INT_MAX;
+
+    // lane handles controls [u0, u0+UPL) of the run, then strides by 32*UPL
+    for (int u0 = lane * UPL; u0 < it.u_count; u0 += 32 * UPL) {
+        double acc[UPL];
+        double gv[UPL];
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) acc[j] = 0.0;
+        if (!T.g_per_w) load_g<UPL>(gv, T.g, it.g_base + u0);
+
+        Frag<D, UPL> cur, nxt;
+        load_frag<D, UPL>(cur, T.cell, T.lam, T.lam_plane, it.entry_base + u0);
+        for (int w = 0; w < W; ++w) {
+            const int64_t off_next = it.entry_base + (int64_t)(w + 1) * pitch + u0;
+            if (w + 1 < W) load_frag<D, UPL>(nxt, T.cell, T.lam, T.lam_plane, off_next);
+            if (T.g_per_w) load_g<UPL>(gv, T.g, it.g_base + (int64_t)w * pitch + u0);
+            const double pw = p_sh[w];
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) {
+                double lam[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) lam[k] = cur.lam[k][j];
+                double v = Lerp<double, D, 0>::eval(Jprev, cur.cell[j], G.stride, lam);
+                double jg = add_(gv[j], v);            // g + J_next(f(x,u,w))   stodynprog.py:677
+                if (T.expect) acc[j] = add_(acc[j], mul_(jg, pw));   // np.inner over w   :682
+                else acc[j] = jg;                      // deterministic: J = J_k_grid      :679-680
+            }
+            if (w + 1 < W) cur = nxt;
+        }
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) {
+            const int u = u0 + j;
+            if (u < it.u_count) {
+                const int idx = it.u_begin + u;
+                if (better(acc[j], idx, best_v, best_i)) { best_v = acc[j]; best_i = idx; }
+            }
+        }
+    }
+    // lexicographic (value, index) min across the warp
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best_v, s);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, s);
+        if (better(ov, oi, best_v, best_i)) { best_v = ov; best_i = oi; }
+    }
+    if (lane == 0) {
+        part_val[item_id] = best_v;
+        part_idx[item_id] = best_i;
+    }
+}
+
+// combine the partial minima of each state's items (in item order = control order)
+__global__ void __launch_bounds__(256)
+k_sweep_finalize(int64_t n_states, const int64_t* __restrict__ item_begin,
+                 const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
+                 double* __restrict__ J_out, int32_t* __restrict__ argmin_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_states) return;
+    int64_t b = item_begin[i], e = item_begin[i + 1];
+    double bv = CUDART_INF;
+    int bi = INT_MAX;
+    for (int64_t k = b; k < e; ++k) {
+        double v = part_val[k];
+        int ix = part_idx[k];
+        if (better(v, ix, bv, bi)) { bv = v; bi = ix; }
+    }
+    J_out[i] = bv;
+    argmin_out[i] = bi;
+}
+
+static int sweep_upl() {
+    static int upl = 0;
+    if (upl == 0) {
+        const char* e = getenv("SDP_UPL");
+        upl = (e && atoi(e) == 2) ? 2 : 4;
+    }
+    return upl;
+}
+
+template <int D>
+static int launch_sweep(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                        double* part_val, int32_t* part_idx, cudaStream_t st) {
+    const int warps = 8;
+    unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
+    size_t shm = (size_t)T.W * sizeof(double);
+    if (sweep_upl() == 2)
+        k_sweep<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
+    else
+        k_sweep<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
+                         double* part_val, int32_t* part_idx, double* J_out, int32_t* argmin_out,
+                         void* stream) {
+    GridT<double> G;
+    int rc = make_grid<double>(grid, &G, nullptr);
+    if (rc) return rc;
+    if (!tab) return fail(SDP_EINVAL, "%s", "sdp_sweep: tables is NULL");
+    const SdpTables& T = *tab;
+    if (T.W < 1 || T.W > 4096 || T.n_states < 0 || T.n_items < 0)
+        return fail(SDP_EINVAL, "%s", "sdp_sweep: bad sizes");
+    if (T.n_states == 0) return SDP_OK;
+    if (!T.cell || !T.lam || !T.g || !T.items || !T.item_begin || !J_prev || !part_val || !part_idx ||
+        !J_out || !argmin_out || (T.expect && !T.p))
+        return fail(SDP_EINVAL, "%s", "sdp_sweep: NULL pointer");
+    if ((T.lam_plane & 3) || ((uintptr_t)T.cell & 15) || ((uintptr_t)T.lam & 15) || ((uintptr_t)T.g & 15))
+        return fail(SDP_EINVAL, "%s", "sdp_sweep: tables must be 16-byte aligned, lam_plane % 4 == 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T.n_items > 0) {
+        if (T.n_items / 8 + 1 > 0x7fffffffLL) return fail(SDP_EINVAL, "%s", "sdp_sweep: too many items");
+        switch (grid->d) {
+            case 1: rc = launch_sweep<1>(G, T, J_prev, part_val, part_idx, st); break;
+            case 2: rc = launch_sweep<2>(G, T, J_prev, part_val, part_idx, st); break;
+            case 3: rc = launch_sweep<3>(G, T, J_prev, part_val, part_idx, st); break;
+            default: rc = launch_sweep<4>(G, T, J_prev, part_val, part_idx, st); break;
+        }
+        if (rc) return rc;
+    }
+    unsigned blocks = (unsigned)((T.n_states + 255) / 256);
+    k_sweep_finalize<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K1': fixed-policy backup. One thread per state, tables are [w][n_states]
+// planes so that adjacent threads read adjacent entries.
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_policy_eval(GridT<double> G, int W, int g_per_w, const double* __restrict__ p,
+              const int32_t* __restrict__ cell, const double* __restrict__ lam, int64_t lam_plane,
+              const double* __restrict__ g, int64_t n_states, const double* __restrict__ J_in,
+              double* __restrict__ J_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_states) return;
+    double acc = 0.0;
+    double gv = g_per_w ? 0.0 : g[i];
+    for (int w = 0; w < W; ++w) {
+        const int64_t off = (int64_t)w * n_states + i;
+        double l[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) l[k] = lam[(int64_t)k * lam_plane + off];
+        if (g_per_w) gv = g[off];
+        double v = Lerp<double, D, 0>::eval(J_in, cell[off], G.stride, l);
+        acc = add_(acc, mul_(add_(gv, v), p[w]));   // stodynprog.py:755,757
+    }
+    J_out[i] = acc;
+}
+
+__global__ void k_pick(const double* __restrict__ J, int64_t idx, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = J[idx];
+}
+__global__ void __launch_bounds__(256)
+k_sub_scalar(double* __restrict__ J, int64_t n, const double* __restrict__ ref) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) J[i] = sub_(J[i], ref[0]);
+}
+
+static int rel_shift_launch(double* J, int64_t n, int64_t ref_index, double* ref_out, cudaStream_t st) {
+    k_pick<<<1, 32, 0, st>>>(J, ref_index, ref_out);
+    SDP_LAUNCH_CHECK();
+    k_sub_scalar<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(J, n, ref_out);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+extern "C" int sdp_rel_shift(double* J, int64_t n, int64_t ref_index, double* ref_out, void* stream) {
+    if (!J || !ref_out || n <= 0 || ref_index < 0 || ref_index >= n)
+        return fail(SDP_EINVAL, "%s", "sdp_rel_shift: bad arguments");
+    return rel_shift_launch(J, n, ref_index, ref_out, (cudaStream_t)stream);
+}
+
+extern "C" int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, const double* p,
+                               const int32_t* cell, const double* lam, int64_t lam_plane,
+                               const double* g, int64_t n_states, int64_t state_begin, int64_t n_grid,
+                               double* J_a, double* J_b, int32_t n_iter, int32_t rel_dp,
+                               int64_t ref_index, double* J_ref_hist, void* stream) {
+    GridT<double> G;
+    int64_t ng = 0;
+    int rc = make_grid<double>(grid, &G, &ng);
+    if (rc) return rc;
+    if (W < 1 || n_states < 0 || n_iter < 0 || n_grid != ng || state_begin < 0 ||
+        state_begin + n_states > n_grid)
+        return fail(SDP_EINVAL, "%s", "sdp_policy_eval: bad sizes");
+    if (n_iter == 0 || n_states == 0) return SDP_OK;
+    if (!p || !cell || !lam || !g || !J_a || !J_b) return fail(SDP_EINVAL, "%s", "sdp_policy_eval: NULL pointer");
+    if (rel_dp && (!J_ref_hist || n_states != n_grid || ref_index < 0 || ref_index >= n_grid))
+        return fail(SDP_EINVAL, "%s", "sdp_policy_eval: rel_dp needs the whole grid in one shard and a J_ref_hist buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned blocks = (unsigned)((n_states + 255) / 256);
+    double* in = J_a;
+    double* out = J_b;
+    for (int it = 0; it < n_iter; ++it) {
+        double* o = out + state_begin;
+        switch (grid->d) {
+            case 1: k_policy_eval<1><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o); break;
+            case 2: k_policy_eval<2><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o); break;
+            case 3: k_policy_eval<3><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o); break;
+            default: k_policy_eval<4><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o); break;
+        }
+        SDP_LAUNCH_CHECK();
+        if (rel_dp) {
+            rc = rel_shift_launch(out, n_grid, ref_index, J_ref_hist + it, st);
+            if (rc) return rc;
+        }
+        double* t = in; in = out; out = t;
+    }
+    return SDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sup-norm of the update
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_supnorm_diff(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+               unsigned long long* __restrict__ out) {
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double d = fabs(sub_(a[i], b[i]));
+        if (d > m) m = d;  // NaN never compares greater: ignored
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        double o = __shfl_xor_sync(0xffffffffu, m, s);
+        if (o > m) m = o;
+    }
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+extern "C" int sdp_supnorm_diff(const double* a, const double* b, int64_t n, double* out, void* stream) {
+    if (!out || n < 0 || (n > 0 && (!a || !b))) return fail(SDP_EINVAL, "%s", "sdp_supnorm_diff: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SDP_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double), st));
+    if (n == 0) return SDP_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_supnorm_diff<<<(unsigned)blocks, 256, 0, st>>>(a, b, n, reinterpret_cast<unsigned long long*>(out));
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K2: general multilinear interpolation, n_v value rows x n_s points
+// ---------------------------------------------------------------------------
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+k_interp(GridT<T> G, int64_t n_grid, int64_t n_v, const T* __restrict__ values, int64_t n_s,
+         const T* __restrict__ s, T* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_s) return;
+    int base = 0;
+    T lam[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        int q;
+        cell_1d<T>(s[(int64_t)k * n_s + i], G.smin[k], G.span[k], G.om1[k], G.order[k], q, lam[k]);
+        base += q * G.stride[k];
+    }
+    for (int64_t v = 0; v < n_v; ++v)
+        out[v * n_s + i] = Lerp<T, D, 0>::eval(values + v * n_grid, base, G.stride, lam);
+}
+
+template <typename T>
+static int interp_impl(const SdpGrid* grid, int64_t n_v, const T* values, int64_t n_s, const T* s,
+                       T* out, void* stream) {
+    GridT<T> G;
+    int64_t ng = 0;
+    int rc = make_grid<T>(grid, &G, &ng);
+    if (rc) return rc;
+    if (n_v < 0 || n_s < 0) return fail(SDP_EINVAL, "%s", "sdp_interp: bad sizes");
+    if (n_v == 0 || n_s == 0) return SDP_OK;
+    if (!values || !s || !out) return fail(SDP_EINVAL, "%s", "sdp_interp: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned blocks = (unsigned)((n_s + 255) / 256);
+    switch (grid->d) {
+        case 1: k_interp<T, 1><<<blocks, 256, 0, st>>>(G, ng, n_v, values, n_s, s, out); break;
+        case 2: k_interp<T, 2><<<blocks, 256, 0, st>>>(G, ng, n_v, values, n_s, s, out); break;
+        case 3: k_interp<T, 3><<<blocks, 256, 0, st>>>(G, ng, n_v, values, n_s, s, out); break;
+        default: k_interp<T, 4><<<blocks, 256, 0, st>>>(G, ng, n_v, values, n_s, s, out); break;
+    }
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+extern "C" int sdp_interp(const SdpGrid* grid, int64_t n_v, const double* values, int64_t n_s,
+                          const double* s, double* out, void* stream) {
+    return interp_impl<double>(grid, n_v, values, n_s, s, out, stream);
+}
+extern "C" int sdp_interp_f32(const SdpGrid* grid, int64_t n_v, const float* values, int64_t n_s,
+                              const float* s, float* out, void* stream) {
+    return interp_impl<float>(grid, n_v, values, n_s, s, out, stream);
+}

@@ -1,0 +1,512 @@
+"""Device side of the solver: table residency, sweep launches, collectives.
+
+torch is plumbing here: it owns the device buffers, the stream and the
+process group.  Every compute step goes through the C ABI (`_cabi`), i.e. the
+hand-written sm_100a kernels in csrc/sdp_b200.cu.  There is no CPU path.
+
+Multi-GPU model: one process per GPU; the C-order flattened state
+grid is cut into contiguous slabs balanced by the number of admissible
+controls; each rank holds the tables of its slab only; the value function J
+(8 bytes per state) is replicated.  One exchange per sweep: all-gather of the
+new J slab (+ an all-reduce-max of the sup-norm residual when asked).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from . import tabulate as tb
+
+__all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight"]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def partition_by_weight(weights, world):
+    """Cut range(len(weights)) into `world` contiguous slabs of nearly equal
+    total weight.  Returns the world+1 boundaries (monotone, first 0, last n)."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = len(w)
+    bounds = [0]
+    if n == 0:
+        return [0] * (world + 1)
+    csum = np.cumsum(w)
+    total = csum[-1]
+    for r in range(1, world):
+        target = total * r / world
+        b = int(np.searchsorted(csum, target, side="left")) + 1
+        # pick the nearer of the two candidate cuts
+        if b - 1 > bounds[-1] and abs(csum[b - 2] - target) <= abs(csum[b - 1] - target):
+            b -= 1
+        b = min(max(b, bounds[-1]), n)
+        bounds.append(b)
+    bounds.append(n)
+    return bounds
+
+
+class Collective(object):
+    """Thin wrapper over torch.distributed for the per-sweep exchange.
+    Works with NCCL (CUDA tensors, on the current stream) and gloo (CPU tensors,
+    used by the world_size-2 host tests)."""
+
+    def __init__(self, group=None):
+        torch = _torch()
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
+        else:
+            self.world = 1
+            self.rank = 0
+        self._plans = {}
+
+    def all_gather_object(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def plan(self, bounds, device):
+        """index plan for gathering uneven contiguous slabs through one padded
+        all_gather_into_tensor"""
+        torch = _torch()
+        key = (tuple(bounds), str(device))
+        if key not in self._plans:
+            counts = np.diff(np.asarray(bounds))
+            maxc = int(counts.max()) if len(counts) else 0
+            idx = np.concatenate([r * maxc + np.arange(c) for r, c in enumerate(counts)]) \
+                if maxc > 0 else np.zeros(0, dtype=np.int64)
+            self._plans[key] = (maxc, torch.from_numpy(idx.astype(np.int64)).to(device))
+        return self._plans[key]
+
+    def all_gather_slabs(self, local, bounds, out=None):
+        """local: 1-D tensor holding this rank's slab [bounds[rank], bounds[rank+1]).
+        Returns the concatenation over ranks (length bounds[-1])."""
+        torch = _torch()
+        if self.world == 1:
+            if out is not None:
+                out.copy_(local)
+                return out
+            return local
+        maxc, index = self.plan(bounds, local.device)
+        pad_local = torch.zeros(maxc, dtype=local.dtype, device=local.device)
+        pad_local[:local.numel()] = local
+        pad_full = torch.empty(maxc * self.world, dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(pad_full, pad_local, group=self.group)
+        if out is not None:
+            torch.index_select(pad_full, 0, index, out=out)
+            return out
+        return pad_full.index_select(0, index)
+
+    def all_reduce_max(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+
+class SweepTables(object):
+    """Dense (cell, lam, g) tables of one slab of states, resident in HBM,
+    plus the host-side control discretisation needed to turn argmin indices
+    back into control values."""
+
+    def __init__(self):
+        self.grid = None           # _cabi.SdpGrid
+        self.d = 0
+        self.W = 1
+        self.expect = 1
+        self.g_per_w = 0
+        self.bounds = None         # slab boundaries over ranks (world+1)
+        self.state_begin = 0
+        self.n_states = 0
+        self.host_full = None      # HostStateTable of ALL states (replicated)
+        self.cell = self.lam = self.g = self.p = None
+        self.items = self.item_begin = None
+        self.part_val = self.part_idx = None
+        self.J_out = self.argmin = None
+        self.lam_plane = 0
+        self.n_items = 0
+        self.n_entries = 0
+        self.n_backups_local = 0   # admissible (x,u,w) triples in this slab
+        self.n_backups_total = 0
+        self.c_tables = None       # _cabi.SdpTables
+        self.setup_seconds = 0.0
+
+    @property
+    def algorithmic_bytes_per_backup(self):
+        """4 + 8 d + 8 kappa  """
+        kappa = 1.0 if self.g_per_w else 1.0 / self.W
+        return 4.0 + 8.0 * self.d + 8.0 * kappa
+
+    @property
+    def device_bytes(self):
+        n = 0
+        for t in (self.cell, self.lam, self.g, self.items, self.item_begin):
+            if t is not None:
+                n += t.numel() * t.element_size()
+        return n
+
+
+class PolicyTables(object):
+    """[w][n_states] planes for the fixed-policy backup (eval_policy)."""
+
+    def __init__(self):
+        self.grid = None
+        self.W = 1
+        self.g_per_w = 0
+        self.cell = self.lam = self.g = self.p = None
+        self.lam_plane = 0
+        self.state_begin = 0
+        self.n_states = 0
+        self.bounds = None
+
+
+class Engine(object):
+    """Owns the device, the stream, the process group and the launches."""
+
+    def __init__(self, device=None, group=None, item_chunk=None, _test_lib=None):
+        torch = _torch()
+        self.coll = Collective(group)
+        self.item_chunk = int(item_chunk) if item_chunk else 512
+        if self.item_chunk % 4:
+            raise ValueError("item_chunk must be a multiple of 4")
+        if _test_lib is not None:
+            # TEST SEAM ONLY (tests/fake_lib.py): a numpy model of the C ABI used to
+            # exercise the host logic (descriptors, items, slabs, collectives) on a
+            # machine without a GPU.  Never set by the package itself.
+            self.lib = _test_lib
+            self.device = torch.device("cpu")
+            self._cuda = False
+            return
+        self.lib = _cabi.load_library()          # raises if the extension is missing
+        if not torch.cuda.is_available():
+            raise _cabi.SdpLibraryError(
+                "no CUDA device visible: stodynprog_b200 has no CPU path "
+                "(the CPU oracle lives under oracle/ and is test infrastructure only)")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self._cuda = True
+
+    # -- helpers ----------------------------------------------------------
+    @property
+    def stream(self):
+        torch = _torch()
+        if not self._cuda:
+            return ctypes.c_void_p(0)
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ptr(self, t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+    def to_device(self, a, dtype=None):
+        torch = _torch()
+        a = np.ascontiguousarray(a)
+        if not a.flags.writeable:
+            a = a.copy()
+        t = torch.from_numpy(a)
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=False)
+
+    def sync(self):
+        if self._cuda:
+            _torch().cuda.synchronize(self.device)
+
+    # -- sweep tables -----------------------------------------------------
+    def build_sweep_tables(self, solver, t_k=None, reuse=None):
+        """Tabulate the user's callables over this rank's slab and build the dense
+        tables on the device.  `reuse`: a SweepTables whose device buffers are
+        recycled when the sizes match (time-dependent recursion)."""
+        import time
+        torch = _torch()
+        t0 = time.perf_counter()
+        sys = solver.sys
+        state_grid = [np.asarray(g, dtype=float) for g in solver.state_grid]
+        d = len(state_grid)
+        grid = _cabi.make_grid(state_grid)
+        for ax in state_grid:
+            if len(ax) < 2:
+                raise ValueError("every state variable needs at least 2 grid points "
+                                 "(the reference's interpolation reads out of bounds and "
+                                 "divides 0/0 on a 1-point axis, SURVEY.md App. A.2)")
+        n_grid = int(np.prod([len(ax) for ax in state_grid]))
+        nb_perturb = len(solver.perturb_grid)
+        if nb_perturb > 1:
+            raise NotImplementedError("multi-dimensional perturbations are not implemented "
+                                      "(neither in the reference: stodynprog.py:666,679-683)")
+        W = len(solver.perturb_grid[0]) if nb_perturb == 1 else 1
+        coll = self.coll
+        world, rank = coll.world, coll.rank
+
+        # pass 1: control boxes. Every rank scans an equal share, then the full
+        # host table is replicated (it is needed to map argmin -> control values).
+        eq = [n_grid * r // world for r in range(world + 1)]
+        mine = tb.state_tuples(state_grid, eq[rank], eq[rank + 1])
+        part = tb.scan_control_boxes(sys, solver.control_steps, mine, t_k)
+        parts = coll.all_gather_object((part.lo, part.hi, part.npts))
+        nb_control = len(sys.control)
+        host_full = tb.HostStateTable(n_grid, nb_control)
+        host_full.lo = np.concatenate([p[0] for p in parts], axis=0)
+        host_full.hi = np.concatenate([p[1] for p in parts], axis=0)
+        host_full.npts = np.concatenate([p[2] for p in parts], axis=0)
+        U_all = host_full.U.astype(np.int64)
+        if U_all.max(initial=0) >= 2 ** 31 - 4:
+            raise ValueError("more than 2^31 control combinations for one state")
+
+        # slabs balanced by admissible controls
+        bounds = partition_by_weight(U_all + 1, world) if world > 1 else [0, n_grid]
+        sb, se = bounds[rank], bounds[rank + 1]
+        n = se - sb
+        states = mine if (sb, se) == (eq[rank], eq[rank + 1]) else tb.state_tuples(state_grid, sb, se)
+        host = tb.HostStateTable(n, nb_control)
+        host.lo, host.hi, host.npts = host_full.lo[sb:se], host_full.hi[sb:se], host_full.npts[sb:se]
+        U = U_all[sb:se]
+        Upad = (U + 3) // 4 * 4
+        entry_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(W * Upad, out=entry_off[1:])
+        n_entries = int(entry_off[-1])
+        lam_plane = n_entries
+
+        T = reuse if (reuse is not None and reuse.n_entries == n_entries and reuse.W == W
+                      and reuse.d == d) else SweepTables()
+        T.grid, T.d, T.W = grid, d, W
+        T.expect = 1 if nb_perturb == 1 else 0
+        T.bounds, T.state_begin, T.n_states = bounds, sb, n
+        T.host_full = host_full
+        T.n_entries, T.lam_plane = n_entries, lam_plane
+        T.n_backups_local = int(U.sum()) * W
+        T.n_backups_total = int(U_all.sum()) * W
+        dev = self.device
+        if T.cell is None:
+            T.cell = torch.empty(max(n_entries, 4), dtype=torch.int32, device=dev)
+            T.lam = torch.empty(max(n_entries, 4) * d, dtype=torch.float64, device=dev)
+        if nb_perturb == 1:
+            T.p = self.to_device(np.asarray(solver.perturb_proba[0], dtype=float))
+        else:
+            T.p = self.to_device(np.ones(1))
+        w_grid = [np.asarray(g) for g in solver.perturb_grid]
+
+        def build(g_per_w):
+            if g_per_w:
+                g_off = entry_off
+                g_len = n_entries
+            else:
+                g_off = np.zeros(n + 1, dtype=np.int64)
+                np.cumsum(Upad, out=g_off[1:])
+                g_len = int(g_off[-1])
+            if T.g is None or T.g.numel() != max(g_len, 4):
+                T.g = torch.empty(max(g_len, 4), dtype=torch.float64, device=dev)
+            T.g_per_w = g_per_w
+
+            def flush(desc, staging, max_Upad):
+                desc_dev = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(dev)
+                stag_dev = torch.from_numpy(staging).to(dev)
+                rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, len(desc),
+                                               self._ptr(desc_dev), self._ptr(stag_dev),
+                                               self._ptr(T.cell), self._ptr(T.lam), lam_plane,
+                                               self._ptr(T.g), int(max_Upad), self.stream)
+                _cabi.check(rc, "sdp_build_tables")
+                # the staging tensors are freed by torch's caching allocator in
+                # stream order, so no synchronisation is needed here
+
+            ok = tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
+                                    g_per_w, flush)
+            return ok, g_off
+
+        ok, g_off = build(T.g_per_w if reuse is T else 0)
+        if not ok:
+            ok, g_off = build(1)
+            assert ok
+
+        # work items: one warp per run of at most `item_chunk` controls
+        chunk = self.item_chunk
+        n_it = (U + chunk - 1) // chunk
+        item_begin = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(n_it, out=item_begin[1:])
+        n_items = int(item_begin[-1])
+        st = np.repeat(np.arange(n, dtype=np.int64), n_it)
+        kk = np.arange(n_items, dtype=np.int64) - item_begin[st]
+        items = np.zeros(n_items, dtype=_cabi.ITEM_DTYPE)
+        items["u_begin"] = kk * chunk
+        items["u_count"] = np.minimum(chunk, U[st] - kk * chunk)
+        items["entry_base"] = entry_off[st] + kk * chunk
+        items["g_base"] = g_off[st] + kk * chunk
+        items["Upad"] = Upad[st]
+        items["state"] = st
+        T.n_items = n_items
+        T.items = torch.from_numpy(items.view(np.uint8).reshape(-1)).to(dev) if n_items else \
+            torch.zeros(32, dtype=torch.uint8, device=dev)
+        T.item_begin = self.to_device(item_begin)
+        T.part_val = torch.empty(max(n_items, 1), dtype=torch.float64, device=dev)
+        T.part_idx = torch.empty(max(n_items, 1), dtype=torch.int32, device=dev)
+        T.J_out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+        T.argmin = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+
+        c = _cabi.SdpTables()
+        c.cell = T.cell.data_ptr()
+        c.lam = T.lam.data_ptr()
+        c.lam_plane = lam_plane
+        c.g = T.g.data_ptr()
+        c.g_per_w = T.g_per_w
+        c.W = W
+        c.expect = T.expect
+        c.reserved = 0
+        c.p = T.p.data_ptr()
+        c.items = T.items.data_ptr()
+        c.n_items = n_items
+        c.item_begin = T.item_begin.data_ptr()
+        c.n_states = n
+        T.c_tables = c
+        self.sync()
+        T.setup_seconds = time.perf_counter() - t0
+        return T
+
+    def sweep_local(self, T, J_prev):
+        """Enqueue K1 on this rank's slab.  J_prev: device fp64 [n_grid].
+        Results land in T.J_out / T.argmin (slab-local)."""
+        rc = self.lib.sdp_sweep(ctypes.byref(T.grid), ctypes.byref(T.c_tables), self._ptr(J_prev),
+                                self._ptr(T.part_val), self._ptr(T.part_idx),
+                                self._ptr(T.J_out), self._ptr(T.argmin), self.stream)
+        _cabi.check(rc, "sdp_sweep")
+
+    def sweep(self, T, J_prev, J_new, rel_ref_index=None, ref_out=None, resid_out=None):
+        """One full Bellman sweep: K1 on the slab, all-gather of the J slab into
+        J_new (device fp64 [n_grid]), optional relative-DP shift and optional
+        sup-norm residual max|J_new - J_prev| (all-reduced)."""
+        self.sweep_local(T, J_prev)
+        n = T.n_states
+        sb = T.state_begin
+        if self.coll.world == 1:
+            J_new.copy_(T.J_out[:n])
+        else:
+            self.coll.all_gather_slabs(T.J_out[:n], T.bounds, out=J_new)
+        if rel_ref_index is not None:
+            rc = self.lib.sdp_rel_shift(self._ptr(J_new), J_new.numel(), int(rel_ref_index),
+                                        self._ptr(ref_out), self.stream)
+            _cabi.check(rc, "sdp_rel_shift")
+        if resid_out is not None:
+            a = J_new[sb:sb + n]
+            b = J_prev[sb:sb + n]
+            rc = self.lib.sdp_supnorm_diff(self._ptr(a), self._ptr(b), n, self._ptr(resid_out),
+                                           self.stream)
+            _cabi.check(rc, "sdp_supnorm_diff")
+            self.coll.all_reduce_max(resid_out)
+
+    def gather_argmin(self, T):
+        """full-grid int32 argmin (device), gathered over ranks"""
+        return self.coll.all_gather_slabs(T.argmin[:T.n_states], T.bounds)
+
+    # -- policy tables ----------------------------------------------------
+    def build_policy_tables(self, solver, pol):
+        """Evaluate dyn/cost for the fixed policy on the whole grid exactly as
+        eval_policy does (one broadcast call, stodynprog.py:731-755), expand on the
+        host to dense [d][W][N] coordinates and run the cell search (K0a) for this
+        rank's equal-count slab."""
+        torch = _torch()
+        sys = solver.sys
+        state_grid_1d = [np.asarray(g, dtype=float) for g in solver.state_grid]
+        state_dims = tuple(len(g) for g in state_grid_1d)
+        nb_state = len(state_dims)
+        nb_control = len(sys.control)
+        grid = _cabi.make_grid(state_grid_1d)
+        n_grid = int(np.prod(state_dims))
+        w_k = np.asarray(solver.perturb_grid[0])      # IndexError if deterministic, like :726
+        w_proba = np.asarray(solver.perturb_proba[0], dtype=float)
+        W = len(w_k)
+        state_grid = tuple(np.reshape(g, (1,) * i + (-1,) + (1,) * (nb_state - i))
+                           for i, g in enumerate(solver.state_grid))
+        u_k = [pol[..., i].reshape(state_dims + (1,)) for i in range(nb_control)]
+        args = state_grid + tuple(u_k) + (w_k,)
+        x_next = sys.dyn(*args, **sys.params)
+        g_k = sys.cost(*args, **sys.params)
+        full = state_dims + (W,)
+        world, rank = self.coll.world, self.coll.rank
+        bounds = [n_grid * r // world for r in range(world + 1)]
+        sb, se = bounds[rank], bounds[rank + 1]
+        n = se - sb
+
+        def dense_wn(a, allow_compact_w):
+            a = np.asarray(a)
+            if a.dtype != np.float64:
+                a = a.astype(float)
+            if a.ndim > len(full):
+                raise ValueError("dyn/cost output of rank %d does not broadcast to %s" % (a.ndim, full))
+            a = a.reshape((1,) * (len(full) - a.ndim) + a.shape)
+            if allow_compact_w and a.shape[-1] == 1:
+                flat = np.broadcast_to(a, state_dims + (1,)).reshape(n_grid)
+                return np.ascontiguousarray(flat[sb:se]), 0
+            flat = np.broadcast_to(a, full).reshape(n_grid, W)
+            return np.ascontiguousarray(flat[sb:se].T), 1     # [W][n]
+
+        P = PolicyTables()
+        P.grid, P.W, P.bounds, P.state_begin, P.n_states = grid, W, bounds, sb, n
+        coords = np.stack([dense_wn(c, False)[0].reshape(-1) for c in x_next]) if n else \
+            np.zeros((nb_state, 0))
+        g_arr, g_per_w = dense_wn(g_k, True)
+        P.g_per_w = g_per_w
+        P.lam_plane = W * n
+        s_dev = self.to_device(coords)
+        P.cell = torch.empty(max(W * n, 1), dtype=torch.int32, device=self.device)
+        P.lam = torch.empty(max(W * n, 1) * nb_state, dtype=torch.float64, device=self.device)
+        rc = self.lib.sdp_cell_setup(ctypes.byref(grid), W * n, self._ptr(s_dev), self._ptr(P.cell),
+                                     self._ptr(P.lam), self.stream)
+        _cabi.check(rc, "sdp_cell_setup")
+        P.g = self.to_device(g_arr.reshape(-1)) if n else torch.zeros(1, dtype=torch.float64, device=self.device)
+        P.p = self.to_device(w_proba)
+        return P
+
+    def policy_eval(self, P, J_a, J_b, n_iter, rel_dp, ref_index, J_ref_hist):
+        """n_iter fixed-policy backups, ping-pong between J_a and J_b (device fp64
+        [n_grid]).  Returns the tensor holding the final value function."""
+        n_grid = J_a.numel()
+        if self.coll.world == 1:
+            rc = self.lib.sdp_policy_eval(ctypes.byref(P.grid), P.W, P.g_per_w, self._ptr(P.p),
+                                          self._ptr(P.cell), self._ptr(P.lam), P.lam_plane,
+                                          self._ptr(P.g), P.n_states, 0, n_grid,
+                                          self._ptr(J_a), self._ptr(J_b), int(n_iter),
+                                          1 if rel_dp else 0, int(ref_index),
+                                          self._ptr(J_ref_hist) if rel_dp else ctypes.c_void_p(0),
+                                          self.stream)
+            _cabi.check(rc, "sdp_policy_eval")
+            return J_a if n_iter % 2 == 0 else J_b
+        cur, nxt = J_a, J_b
+        sb, n = P.state_begin, P.n_states
+        for k in range(n_iter):
+            rc = self.lib.sdp_policy_eval(ctypes.byref(P.grid), P.W, P.g_per_w, self._ptr(P.p),
+                                          self._ptr(P.cell), self._ptr(P.lam), P.lam_plane,
+                                          self._ptr(P.g), n, sb, n_grid,
+                                          self._ptr(cur), self._ptr(nxt), 1, 0, 0,
+                                          ctypes.c_void_p(0), self.stream)
+            _cabi.check(rc, "sdp_policy_eval")
+            self.coll.all_gather_slabs(nxt[sb:sb + n].clone(), P.bounds, out=nxt)
+            if rel_dp:
+                ref_ptr = ctypes.c_void_p(J_ref_hist.data_ptr() + 8 * k)
+                rc = self.lib.sdp_rel_shift(self._ptr(nxt), n_grid, int(ref_index), ref_ptr, self.stream)
+                _cabi.check(rc, "sdp_rel_shift")
+            cur, nxt = nxt, cur
+        return cur
+
+    # -- interpolation ----------------------------------------------------
+    def interp(self, grid, values, s):
+        """values: host (n_v, n_grid); s: host (d, n_s) -> host (n_v, n_s).
+        fp64 or fp32 according to values.dtype."""
+        torch = _torch()
+        f32 = values.dtype == np.float32
+        n_v, n_s = values.shape[0], s.shape[1]
+        v_dev = self.to_device(values)
+        s_dev = self.to_device(s)
+        out = torch.empty((n_v, n_s), dtype=torch.float32 if f32 else torch.float64, device=self.device)
+        fn = self.lib.sdp_interp_f32 if f32 else self.lib.sdp_interp
+        rc = fn(ctypes.byref(grid), n_v, self._ptr(v_dev), n_s, self._ptr(s_dev), self._ptr(out), self.stream)
+        _cabi.check(rc, "sdp_interp")
+        return out.cpu().numpy()

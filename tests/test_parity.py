@@ -1,0 +1,450 @@
+"""Parity of the solver (through the C ABI) against the oracle and the golden
+fixtures generated from the unmodified reference.
+
+Solver-level tests run twice: with backend "cuda" (marked gpu: the real
+libsdp_b200.so on a B200 - the parity tests proper) and with backend "model"
+(CPU suite: the same host code driving tests/fake_lib.py, a numpy model of the
+C ABI, so that descriptors, table layout, work items and the argmin -> control
+value mapping are checked without a GPU).  Raw-kernel tests are gpu-only.
+
+Bars (BASELINE.json north_star): control policies bit-exact (exact ties are
+resolved by the first-minimum rule on both sides; states where the two sides
+pick different controls are counted, and must be explainable as near-ties, i.e.
+the oracle's J at the two controls differs by <= a few ulp); J within 1e-10
+relative in fp64; integer cell indices and fp64 weights bit-exact.
+"""
+import ctypes
+import itertools
+
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err, policy_mismatch_report
+
+J_RTOL = 1e-10
+
+gpu = pytest.mark.gpu
+
+
+class _Api(object):
+    """`api` for the workload factories: the product's classes, with the solver
+    bound either to the CUDA library or to the numpy model of the C ABI."""
+
+    def __init__(self, pkg, backend):
+        self.pkg = pkg
+        self.backend = backend
+        self.SysDescription = pkg.SysDescription
+
+    def DPSolver(self, sys, **kw):
+        if self.backend == "model":
+            from fake_lib import FakeLib
+            kw["_test_lib"] = FakeLib()
+        return self.pkg.DPSolver(sys, **kw)
+
+
+@pytest.fixture(scope="module", params=[pytest.param("model"), pytest.param("cuda", marks=gpu)])
+def api(request, product):
+    """host logic is exercised twice: against the numpy model of the C ABI
+    (CPU suite) and against the real CUDA library (GPU suite)"""
+    return _Api(product, request.param)
+
+
+@pytest.fixture(scope="module")
+def cuda_api(product):
+    return _Api(product, "cuda")
+
+
+@pytest.fixture(scope="module")
+def eng(product):
+    from stodynprog_b200.engine import Engine
+    return Engine()
+
+
+def _adversarial(lo, hi, n, rng):
+    span = hi - lo
+    x = lo + span * (rng.random(n) * 1.6 - 0.3)
+    special = np.array([lo, hi, np.nextafter(hi, lo), np.nextafter(lo, hi), lo - 0.5 * span,
+                        hi + 7.3 * span, 3e9, -3e9, 1e300, -1e300, 1e6, np.inf, -np.inf, np.nan,
+                        0.0, -0.0, 5e-324, 2147483647.5 * span, -2147483648.5 * span])
+    x[:len(special)] = special
+    rng.shuffle(x)
+    return x
+
+
+# ---------------------------------------------------------------------------
+# K0: cell search, bit-exact
+# ---------------------------------------------------------------------------
+@gpu
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_cell_setup_bit_exact(eng, d):
+    import torch
+    from oracle import oracle as oc
+    from stodynprog_b200 import _cabi
+    rng = np.random.default_rng(100 + d)
+    orders = [(9,), (41, 61), (31, 61, 61), (5, 7, 6, 4)][d - 1]
+    smin = np.array([0.0, -4.0, -0.908, 1.5][:d])
+    smax = np.array([10.0, 4.0, 0.908, 2.25][:d])
+    n = 20000
+    s = np.stack([_adversarial(smin[k], smax[k], n, rng) for k in range(d)])
+    cell_o, lam_o = oc.cell_search(smin, smax, orders, s)
+    grid = _cabi.make_grid([np.linspace(smin[k], smax[k], orders[k]) for k in range(d)])
+    s_dev = eng.to_device(s)
+    cell = torch.empty(n, dtype=torch.int32, device=eng.device)
+    lam = torch.empty(d * n, dtype=torch.float64, device=eng.device)
+    rc = eng.lib.sdp_cell_setup(ctypes.byref(grid), n, eng._ptr(s_dev), eng._ptr(cell), eng._ptr(lam),
+                                eng.stream)
+    _cabi.check(rc, "sdp_cell_setup")
+    assert np.array_equal(cell.cpu().numpy(), cell_o)
+    lam_g = lam.cpu().numpy().reshape(d, n)
+    # bit-exact, NaN == NaN
+    assert np.array_equal(lam_g.view(np.int64), lam_o.view(np.int64))
+
+
+# ---------------------------------------------------------------------------
+# K2: interpolation
+# ---------------------------------------------------------------------------
+@gpu
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_interp_golden_bit_exact(product, d):
+    """against outputs of the reference's compiled Cython routine"""
+    G = golden("interp_kat.npz")
+    out = product.multilinear_interpolation(G["d%d_smin" % d], G["d%d_smax" % d], G["d%d_orders" % d],
+                                            G["d%d_values" % d], G["d%d_s" % d])
+    assert np.array_equal(out.view(np.int64), G["d%d_out" % d].view(np.int64))
+
+
+@gpu
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_interp_f32_golden(product, d):
+    G = golden("interp_kat.npz")
+    with np.errstate(over="ignore"):
+        s32 = np.ascontiguousarray(G["d%d_s" % d].astype(np.float32))
+    out = product.multilinear_interpolation(G["d%d_smin" % d].astype(np.float32),
+                                            G["d%d_smax" % d].astype(np.float32), G["d%d_orders" % d],
+                                            G["d%d_values" % d].astype(np.float32), s32)
+    assert out.dtype == np.float32
+    assert np.array_equal(out.view(np.int32), G["d%d_out_f32" % d].view(np.int32))
+
+
+@gpu
+def test_interp_1D_reference_kat(product):
+    """the reference's own known-answer test (tests/test_dolointerp.py:17-40)"""
+    smin, smax, orders = np.array([0.]), np.array([2.]), np.array([3])
+    grid = np.linspace(0., 2., 3)
+    values = np.ascontiguousarray(np.atleast_2d(grid ** 2))
+    pts = np.ascontiguousarray(np.atleast_2d(np.linspace(0., 2., 5)))
+    out = product.multilinear_interpolation(smin, smax, orders, values, pts)
+    assert np.all(np.abs(out - np.array([0, 0.5, 1, 2.5, 4])) < 1e-10)
+
+
+@gpu
+def test_MultilinearInterpolator_R2R2(product):
+    """the reference's test_R2R2 (tests/test_dolointerp.py:45-93), seeded"""
+    def f(x):
+        return np.vstack([np.sqrt(x[0, :] ** 2 + x[1, :] ** 2),
+                          np.power(x[0, :] ** 3 + x[1, :] ** 3, 1.0 / 3.0)])
+    interp = product.MultilinearInterpolator([1, 1], [2, 2], [5, 5])
+    interp.set_values(f(interp.grid))
+    corners = np.array([[1, 1], [1, 2], [2, 1], [2, 2]], dtype=float).T
+    rnd = np.random.default_rng(0).random((2, 6)) + 1
+    for pts, tol in ((corners, 1e-9), (rnd, 0.01)):
+        assert np.all(np.abs(interp(pts) - f(pts)) < tol)
+
+
+@gpu
+def test_interp_on_state_broadcast(product, port):
+    from stodynprog_b200 import workloads as wl
+    prob = wl.storage_ar1(product, n_E=11, n_P=13)
+    ora = wl.storage_ar1(port, n_E=11, n_P=13)
+    A = np.random.default_rng(3).standard_normal((11, 13))
+    f, fo = prob.solver.interp_on_state(A), ora.solver.interp_on_state(A)
+    x = np.linspace(-1, 11, 7).reshape(-1, 1)
+    y = np.linspace(-5, 5, 5)
+    assert f(x, y).shape == (7, 5)
+    assert np.array_equal(f(x, y), fo(x, y))
+    assert f(0, 0).shape == ()
+    with pytest.raises(ValueError):
+        prob.solver.interp_on_state(np.zeros((3, 3)))
+
+
+# ---------------------------------------------------------------------------
+# config #1: inventory (doc/example_inventory.rst:217-239 + reference run)
+# ---------------------------------------------------------------------------
+def test_inventory_golden(api):
+    from stodynprog_b200 import workloads as wl
+    G = golden("inventory.npz")
+    prob = wl.inventory(api)
+    J = prob.J0
+    for k in range(6):
+        J, u = prob.solver.value_iteration(J, report_time=False)
+        assert u.shape == (10, 1)
+        assert np.array_equal(u, G["pol"][k]), "policy after sweep %d" % (k + 1)
+        assert rel_err(J, G["J"][k]) <= J_RTOL
+        if k == 0:   # printed in the reference's doc
+            assert np.allclose(J, [9, 6, 3, 0, .5, 1, 1.5, 2, 2.5, 3], rtol=0, atol=1e-12)
+    assert np.array_equal(G["pol"][3][:, 0], [5, 4, 3, 2, 1, 0, 0, 0, 0, 0])
+
+
+# ---------------------------------------------------------------------------
+# config #2: deterministic time-dependent storage, bellman_recursion
+# ---------------------------------------------------------------------------
+def test_pv_storage_bellman_recursion_vs_port(api, port):
+    """short horizon, coarse control step (the model backend is slow)"""
+    from stodynprog_b200 import workloads as wl
+    prob = wl.pv_storage(api, horizon=30)
+    prob.solver.control_steps = (.01,)
+    J, pol = prob.solver.bellman_recursion(30, prob.J_fin, report_time=False)
+    ora = wl.pv_storage(port, horizon=30)
+    ora.solver.control_steps = (.01,)
+    Jo, polo = ora.solver.bellman_recursion(30, ora.J_fin)
+    assert J.shape == (30, 50) and pol.shape == (30, 50, 1)
+    n_bad, _ = policy_mismatch_report(pol, polo)
+    assert n_bad == 0
+    assert rel_err(J, Jo) <= J_RTOL
+
+
+@gpu
+def test_pv_storage_full_horizon_golden(cuda_api):
+    from stodynprog_b200 import workloads as wl
+    G = golden("pv_storage.npz")
+    prob = wl.pv_storage(cuda_api)
+    J, pol = prob.solver.bellman_recursion(prob.horizon, prob.J_fin, report_time=False)
+    n_bad, _ = policy_mismatch_report(pol, G["pol"])
+    assert n_bad == 0
+    assert rel_err(J, G["J"]) <= J_RTOL
+
+
+# ---------------------------------------------------------------------------
+# config #3: storage + AR(1) - the roofline target grid
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ar1(cuda_api):
+    from stodynprog_b200 import workloads as wl
+    return wl.storage_ar1(cuda_api)
+
+
+@gpu
+def test_storage_ar1_control_counts(ar1):
+    """notebook print_summary: [4,001 to 8,001] values, 6,342.5 on average"""
+    G = golden("storage_ar1.npz")
+    T = ar1.solver.sweep_tables()
+    assert np.array_equal(T.host_full.npts, G["control_dims"])
+    assert T.host_full.npts[:, 0].min() == 4001 and T.host_full.npts[:, 0].max() == 8001
+    assert abs(T.host_full.npts[:, 0].mean() - 6342.5) < 0.05
+    assert T.n_backups_total == 142762509
+
+
+@gpu
+def test_storage_ar1_value_iteration_golden(ar1):
+    G = golden("storage_ar1.npz")
+    J = ar1.J0
+    for k in range(3):
+        J, pol = ar1.solver.value_iteration(J, report_time=False)
+        n_bad, _ = policy_mismatch_report(pol, G["vi_pol%d" % k])
+        assert n_bad == 0, "sweep %d: %d states with a different control" % (k, n_bad)
+        assert rel_err(J, G["vi_J%d" % k]) <= J_RTOL
+
+
+@gpu
+def test_storage_ar1_eval_policy_golden(ar1):
+    G = golden("storage_ar1.npz")
+    J, J_ref = ar1.solver.eval_policy(G["pol_ini"], 50, rel_dp=True, J_ref_full=True, report_time=False)
+    assert rel_err(J_ref, G["ev_Jref_hist"]) <= J_RTOL
+    assert np.max(np.abs(J - G["ev_J"])) <= J_RTOL * np.max(np.abs(G["ev_J"]))
+
+
+@gpu
+def test_storage_ar1_policy_iteration_golden(ar1, capsys):
+    """notebook golden: 0.105724, 0.0486519, 0.0468464, 0.0468268, 0.0468268"""
+    G = golden("storage_ar1.npz")
+    (J, J_ref), pol = ar1.solver.policy_iteration(ar1.initial_policy(), 50, 4, rel_dp=True)
+    text = capsys.readouterr().out
+    costs = [l.split(':')[1].strip() for l in text.splitlines() if 'ref policy cost' in l]
+    assert costs == ['0.105724', '0.0486519', '0.0468464', '0.0468268', '0.0468268']
+    assert abs(J_ref - float(G["pi_Jref"])) <= J_RTOL * abs(float(G["pi_Jref"]))
+    n_bad, _ = policy_mismatch_report(pol, G["pi_pol"])
+    assert n_bad == 0
+    assert np.max(np.abs(J - G["pi_J"])) <= J_RTOL * np.max(np.abs(G["pi_J"]))
+
+
+@gpu
+def test_storage_ar1_random_J_vs_port(ar1, port):
+    """non-trivial J (no ties): argmin index and J against the numpy port on a
+    subset of states, plus exact agreement with the ordered-sum C oracle."""
+    from stodynprog_b200 import workloads as wl
+    ora = wl.storage_ar1(port)
+    J0 = np.random.default_rng(0).standard_normal((41, 61))
+    J, pol = ar1.solver.value_iteration(J0, report_time=False)
+    lo, hi = 1000, 1120
+    Jo, polo = ora.solver.value_iteration(J0, state_slice=(lo, hi))
+    sl = slice(lo, hi)
+    assert np.array_equal(pol.reshape(-1, 2)[sl], polo.reshape(-1, 2)[sl])
+    assert rel_err(J.reshape(-1)[sl], Jo.reshape(-1)[sl]) <= J_RTOL
+
+
+@gpu
+def test_storage_ar1_sup_norm_and_device_loop(ar1):
+    J, pol, info = ar1.solver.solve_value_iteration(max_iter=3, tol=0.0)
+    G = golden("storage_ar1.npz")
+    assert info["n_sweeps"] == 3
+    assert rel_err(J, G["vi_J2"]) <= J_RTOL
+    n_bad, _ = policy_mismatch_report(pol, G["vi_pol2"])
+    assert n_bad == 0
+    r_expected = np.max(np.abs(G["vi_J2"] - G["vi_J1"]))
+    assert abs(info["residuals"][-1] - r_expected) <= 1e-9 * r_expected
+
+
+def test_item_chunking_invariance(api):
+    """splitting a state's controls into runs must not change anything"""
+    from stodynprog_b200 import workloads as wl
+    J0 = np.random.default_rng(5).standard_normal((9, 11))
+    res = []
+    for chunk in (64, 512, 100000):
+        prob = wl.storage_ar1(api, n_E=9, n_P=11, steps=(0.01, 0.1), item_chunk=chunk)
+        res.append(prob.solver.value_iteration(J0, report_time=False))
+    for J, pol in res[1:]:
+        assert np.array_equal(J, res[0][0]) and np.array_equal(pol, res[0][1])
+
+
+# ---------------------------------------------------------------------------
+# config #4: SEAREV (3-D)
+# ---------------------------------------------------------------------------
+def _searev_small(api, **kw):
+    from stodynprog_b200 import workloads as wl
+    prob = wl.searev(api, n_E=7, n_S=11, n_A=11, **kw)
+    prob.solver.control_steps = (.01,)
+    return prob
+
+
+def test_searev_small_golden(api):
+    G = golden("searev_small.npz")
+    prob = _searev_small(api)
+    J = prob.J0
+    for k in range(2):
+        J, pol = prob.solver.value_iteration(J, report_time=False)
+        n_bad, _ = policy_mismatch_report(pol, G["vi_pol%d" % k])
+        assert n_bad == 0
+        assert rel_err(J, G["vi_J%d" % k]) <= J_RTOL
+    (Jd, Jr), pol = prob.solver.policy_iteration(prob.initial_policy(), 30, 2, rel_dp=True)
+    n_bad, _ = policy_mismatch_report(pol, G["pi_pol"])
+    assert n_bad == 0
+    assert abs(Jr - float(G["pi_Jref"])) <= J_RTOL * abs(float(G["pi_Jref"]))
+    assert np.max(np.abs(Jd - G["pi_J"])) <= J_RTOL * np.max(np.abs(G["pi_J"]))
+
+
+# ---------------------------------------------------------------------------
+# semantics: ties, NaN, deterministic branch, w-dependent cost, 4-D state
+# ---------------------------------------------------------------------------
+def _toy(api, d=1, cost_kind="plain", n_u=37, **kw):
+    """small synthetic system exercising the generic paths"""
+    import scipy.stats as stats
+    n_w = 5
+
+    def dyn(*a):
+        x, (u, w) = a[:d], a[d:]
+        return tuple(0.9 * xi + (0.3 + 0.1 * i) * u + (0.5 if i == d - 1 else 0.0) * w
+                     for i, xi in enumerate(x))
+
+    def box(*x):
+        return ((-1.0 - 0.1 * x[0], 1.0 + 0.05 * x[0]),)
+
+    def cost(*a):
+        x, (u, w) = a[:d], a[d:]
+        base = sum(xi ** 2 for xi in x) + 0.1 * u ** 2
+        if cost_kind == "w":
+            return base + 0.05 * w * u
+        if cost_kind == "flat":
+            return 0. * u + 1.0        # every control ties exactly
+        if cost_kind == "nan":
+            return np.where((u > 0.2) & (u < 0.4), np.nan, base)
+        return base
+
+    names = ['x%d' % i for i in range(d)]
+    src = "def dyn_f({0}, u, w): return dyn({0}, u, w)\n" \
+          "def cost_f({0}, u, w): return cost({0}, u, w)\n" \
+          "def box_f({0}): return box({0})\n".format(', '.join(names))
+    ns = {'dyn': dyn, 'cost': cost, 'box': box}
+    exec(src, ns)
+    sys = api.SysDescription((d, 1, 1), name='toy%d' % d)
+    sys.dyn = ns['dyn_f']
+    sys.control_box = ns['box_f']
+    sys.cost = ns['cost_f']
+    sys.perturb_laws = [stats.norm(0, 0.3)]
+    sv = api.DPSolver(sys, **kw)
+    sizes = [6, 5, 4, 3][:d]
+    args = []
+    for n in sizes:
+        args += [-1.0, 2.0, n]
+    sv.discretize_state(*args)
+    sv.discretize_perturb(-0.9, 0.9, n_w)
+    sv.control_steps = (2.0 / n_u,)
+    return sv
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+@pytest.mark.parametrize("cost_kind", ["plain", "w", "flat", "nan"])
+def test_toy_systems_vs_port(api, port, d, cost_kind):
+    sv, so = _toy(api, d, cost_kind), _toy(port, d, cost_kind)
+    shape = sv._state_grid_shape
+    J0 = np.random.default_rng(d).standard_normal(shape)
+    J, pol = sv.value_iteration(J0, report_time=False)
+    with np.errstate(invalid="ignore"):
+        Jo, polo, idxo = so.value_iteration(J0, want_index=True)
+    assert np.array_equal(pol, polo)
+    both_nan = np.isnan(J) & np.isnan(Jo)
+    assert np.array_equal(np.isnan(J), np.isnan(Jo))
+    assert rel_err(np.where(both_nan, 0, J), np.where(both_nan, 0, Jo)) <= J_RTOL
+    if cost_kind == "w":
+        assert sv.last_tables.g_per_w == 1
+    else:
+        assert sv.last_tables.g_per_w == 0
+    # policy evaluation of the greedy policy, with and without relative DP
+    if cost_kind != "nan":
+        Je = sv.eval_policy(pol, 7, report_time=False)
+        Jeo = so.eval_policy(polo, 7)
+        assert rel_err(Je, Jeo) <= J_RTOL
+        Jr, ref = sv.eval_policy(pol, 7, rel_dp=True, report_time=False)
+        Jro, refo = so.eval_policy(polo, 7, rel_dp=True)
+        assert abs(ref - refo) <= J_RTOL * abs(refo)
+        assert np.max(np.abs(Jr - Jro)) <= J_RTOL * max(np.max(np.abs(Jro)), 1e-300)
+
+
+def test_rel_dp_value_iteration(api, port):
+    sv, so = _toy(api, 2), _toy(port, 2)
+    J0 = np.zeros(sv._state_grid_shape)
+    (Jd, Jr), pol = sv.value_iteration((J0, 0.), rel_dp=True, report_time=False)
+    (Jdo, Jro), polo = so.value_iteration((J0, 0.), rel_dp=True)
+    assert np.array_equal(pol, polo)
+    assert Jd[sv._state_ref_ind] == 0.
+    assert abs(Jr - Jro) <= J_RTOL * abs(Jro)
+    assert np.max(np.abs(Jd - Jdo)) <= J_RTOL * np.max(np.abs(Jdo))
+    with pytest.raises(AssertionError):
+        sv.value_iteration((J0 + 1., 0.), rel_dp=True, report_time=False)
+    with pytest.raises(ValueError):
+        sv.value_iteration(np.zeros((2, 2)), report_time=False)
+
+
+@gpu
+def test_supnorm_kernel(eng):
+    import torch
+    from stodynprog_b200 import _cabi
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal(100003)
+    b = rng.standard_normal(100003)
+    a[17] = np.nan
+    out = torch.zeros(1, dtype=torch.float64, device=eng.device)
+    ad, bd = eng.to_device(a), eng.to_device(b)
+    rc = eng.lib.sdp_supnorm_diff(eng._ptr(ad), eng._ptr(bd), a.size, eng._ptr(out), eng.stream)
+    _cabi.check(rc, "sdp_supnorm_diff")
+    assert out.cpu().numpy()[0] == np.nanmax(np.abs(a - b))
+
+
+@gpu
+def test_abi_rejects_bad_arguments(eng):
+    from stodynprog_b200 import _cabi
+    g = _cabi.SdpGrid()
+    g.d = 7
+    rc = eng.lib.sdp_cell_setup(ctypes.byref(g), 1, None, None, None, None)
+    assert rc == -1 and b"grid.d" in eng.lib.sdp_last_error()
+    with pytest.raises(_cabi.SdpLibraryError):
+        _cabi.check(rc, "sdp_cell_setup")
