@@ -53,39 +53,62 @@ typedef struct SdpGrid {
 } SdpGrid;
 
 /* Per-state descriptor for the table build (host-built, device-read).
- * The user's dyn/cost return arrays broadcastable to (U, W) for one state
- * (U = flattened C-order control product, W = perturbation nodes); they are
- * uploaded un-broadcast into a staging buffer and expanded on the device, which
- * is what np.broadcast_arrays + astype(float) + ravel do at stodynprog.py:281-283.
- * Slot k < d is next-state coordinate k, slot d is the stage cost g. */
+ * The user's dyn/cost return arrays broadcastable to (U1, ..., Unc, W) for one
+ * state (or to (S, U1, ..., Unc, W) when the host evaluates a chunk of S states
+ * in one call); they are uploaded un-broadcast into a staging buffer and
+ * expanded on the device, which is what np.broadcast_arrays + astype(float) +
+ * ravel do at stodynprog.py:281-283.  Slot k < d is next-state coordinate k,
+ * slot d is the stage cost g.  Element (i_1..i_nc, w) of slot k of this state
+ * is staging[src[k] + sum_c i_c*cs[k][c] + w*ws[k]]; the flat control index is
+ * the C-order index over npts[0..nc) (stodynprog.py:686). */
+#define SDP_MAX_C 4 /* control variables per system supported by the table build */
 typedef struct SdpStateDesc {
-    int64_t entry_off;          /* first entry of the state's block in cell/lam tables */
-    int64_t g_off;              /* first entry of the state's block in the g table */
-    int64_t src[SDP_MAX_D + 1]; /* offset (in doubles) of each source array in staging */
-    int32_t us[SDP_MAX_D + 1];  /* source stride along the control index (0 = broadcast) */
-    int32_t ws[SDP_MAX_D + 1];  /* source stride along the perturbation index (0 = broadcast) */
-    int32_t U;                  /* admissible control combinations of this state */
-    int32_t Upad;               /* U rounded up to a multiple of 4 (16-byte aligned rows) */
+    int64_t entry_off;                  /* layout A: first entry of the state's block */
+    int64_t g_off;                      /* layout A: first entry of the state's g block */
+    int64_t src[SDP_MAX_D + 1];         /* offset (in doubles) of each source array in staging */
+    int32_t cs[SDP_MAX_D + 1][SDP_MAX_C]; /* source stride along control axis c (0 = broadcast) */
+    int32_t ws[SDP_MAX_D + 1];          /* source stride along the perturbation index (0 = broadcast) */
+    int32_t npts[SDP_MAX_C];            /* control grid dims of this state (1 for unused axes) */
+    int32_t U;                          /* admissible control combinations = prod(npts) */
+    int32_t Upad;                       /* layout A: U rounded up to a multiple of 4 */
 } SdpStateDesc;
 
-/* One unit of sweep work: a run of controls of one state, processed by one warp.
- * States with more controls than the chunk size are split into several items
+/* One unit of sweep work, processed by one warp.
+ * Layout A: a run of controls of one state (`state` = local state index).
+ * Layout B: a run of controls of one tile of 32 consecutive states
+ *           (`state` = tile index, Upad unused).
+ * Units with more controls than the chunk size are split into several items
  * whose partial (min, argmin) are combined by the finalize kernel. */
 typedef struct SdpItem {
-    int64_t entry_base; /* entry_off + u_begin */
-    int64_t g_base;     /* g_off + u_begin */
-    int32_t Upad;       /* row pitch of the state's block */
-    int32_t u_begin;    /* first control of the run (multiple of 4) */
+    int64_t entry_base; /* A: entry_off + u_begin;  B: tile_off + u_begin*W*32 */
+    int64_t g_base;     /* A: g_off + u_begin;      B: tile_g_off + u_begin*32 (or = entry_base) */
+    int32_t Upad;       /* A: row pitch of the state's block */
+    int32_t u_begin;    /* first control of the run (A: multiple of 4) */
     int32_t u_count;    /* controls in the run */
-    int32_t state;      /* local state index */
+    int32_t state;      /* A: local state index;  B: tile index */
 } SdpItem;
 
+#define SDP_LAYOUT_CONTROL_MINOR 0 /* "A": [state][w][u], lane <-> control   */
+#define SDP_LAYOUT_STATE_MINOR 1   /* "B": [tile][u][w][32 states], lane <-> state */
+
 /* Dense sweep tables of one shard of states (device pointers).
- * Layout, per state block: entries [w][Upad] with the control index fastest:
- *   cell[entry_off + w*Upad + u]            int32 flat base-cell index
+ *
+ * Layout A (control-minor), per state block: entries [w][Upad], control fastest:
+ *   cell[entry_off + w*Upad + u]                 int32 flat base-cell index
  *   lam [k*lam_plane + entry_off + w*Upad + u]   fp64 weight of state dim k
  *   g   [g_off + u]              if g_per_w == 0 (cost does not depend on w)
  *   g   [g_off + w*Upad + u]     if g_per_w == 1 (g_off == entry_off)
+ *   Best when the gathers of neighbouring controls hit the same cell (many
+ *   controls per state, fine control step): the 2^d corner loads of a warp
+ *   are broadcasts.
+ *
+ * Layout B (state-minor), per tile of 32 consecutive states, U_t = max U:
+ *   cell[tile_off + (u*W + w)*32 + lane]         lane = state - 32*tile
+ *   lam [k*lam_plane + tile_off + (u*W + w)*32 + lane]
+ *   g   [tile_g_off + u*32 + lane]  (g_per_w == 0)  or  g[tile_off + (u*W+w)*32 + lane]
+ *   Best when neighbouring states land in neighbouring cells (many states, few
+ *   controls): the corner loads of a warp are contiguous.
+ *
  * Algorithmic bytes per admissible (x,u,w): 4 + 8*d + 8*(g_per_w ? 1 : 1/W). */
 typedef struct SdpTables {
     const int32_t* cell;
@@ -95,12 +118,13 @@ typedef struct SdpTables {
     int32_t g_per_w;
     int32_t W;           /* perturbation nodes (1 for a deterministic system) */
     int32_t expect;      /* 1: J = sum_w p_w*(g+J'); 0: deterministic, J = g+J' */
-    int32_t reserved;
+    int32_t layout;      /* SDP_LAYOUT_* */
     const double* p;     /* [W] probabilities (ignored when expect == 0) */
     const SdpItem* items;
     int64_t n_items;
-    const int64_t* item_begin; /* [n_states+1]: items of state i are item_begin[i]..item_begin[i+1]-1 */
+    const int64_t* item_begin; /* A: [n_states+1], B: [n_tiles+1]: items of unit i are item_begin[i]..item_begin[i+1]-1 */
     int64_t n_states;    /* states in this shard */
+    const int32_t* U;    /* [n_states] admissible controls per state (layout B masking) */
 } SdpTables;
 
 /* ABI / build identification. */
@@ -119,11 +143,20 @@ int sdp_cell_setup(const SdpGrid* grid, int64_t n, const double* s, int32_t* cel
 /* K0b - table build for a chunk of states: broadcast-expand the staged
  * dyn/cost outputs (stodynprog.py:674-677 + :281-283) and run the cell search.
  * desc: device [n_states]; staging: device doubles; outputs as in SdpTables.
- * Padding entries (U <= u < Upad) get cell 0, lam 0, g 0. */
+ * Padding entries get cell 0, lam 0, g 0.
+ * Layout A: */
 int sdp_build_tables(const SdpGrid* grid, int32_t W, int32_t g_per_w, int64_t n_states,
                      const SdpStateDesc* desc, const double* staging, int32_t* cell,
                      double* lam, int64_t lam_plane, double* g, int32_t max_Upad,
                      void* stream);
+/* Layout B: `n_tiles` tiles of 32 states; desc[i] describes state i of the
+ * chunk (n_states <= 32*n_tiles, the last tile may be partial); tile arrays are
+ * device [n_tiles]: first entry, first g entry, U_t = max U of the tile. */
+int sdp_build_tables_tiled(const SdpGrid* grid, int32_t W, int32_t g_per_w, int64_t n_states,
+                           const SdpStateDesc* desc, const double* staging, int64_t n_tiles,
+                           const int64_t* tile_off, const int64_t* tile_g_off,
+                           const int32_t* tile_U, int32_t max_tile_U, int32_t* cell,
+                           double* lam, int64_t lam_plane, double* g, void* stream);
 
 /* K1 - one Bellman sweep over a shard of states.
  * Replaces the state loop of DPSolver.value_iteration (stodynprog.py:511-515)
@@ -131,7 +164,7 @@ int sdp_build_tables(const SdpGrid* grid, int32_t W, int32_t g_per_w, int64_t n_
  * (pyx:81-88, :133-140, :195-208, :280-300), + g, expectation over w
  * (np.inner, :682), first-minimum argmin over the control product (:686).
  * J_prev: device [prod(order)], the full previous value function.
- * part_val/part_idx: device scratch [n_items].
+ * part_val/part_idx: device scratch [n_items] (layout A) or [32*n_items] (layout B).
  * J_out: device [n_states]; argmin_out: device [n_states] flat C-order index
  * into the state's control product. */
 int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,

@@ -91,11 +91,21 @@ static int cast_int_f(float t) {
     if (!(t >= -2147483648.0f && t < 2147483648.0f)) return INT_MIN;
     return (int)t;
 }
-static float lerp_rec_f(const float* V, int base, const int* stride, const float* lam, int d, int k) {
-    if (k == d) return V[base];
-    float a = lerp_rec_f(V, base, stride, lam, d, k + 1);
-    float b = lerp_rec_f(V, base + stride[k], stride, lam, d, k + 1);
-    return (1 - lam[k]) * a + lam[k] * b;
+/* The generated C of the float specialisation writes the weights as
+ * `(1.0 - lam_k)` with a DOUBLE literal (Cython turns the pyx's `1` into 1.0),
+ * so by C's usual arithmetic conversions the `(1.0-lam)*a` terms and the sums
+ * are evaluated in double, while the innermost `lam*v` products of two floats
+ * stay float products; the result is rounded to float on the final store.
+ * Restated here with explicit types. */
+static double lerp_rec_f(const float* V, int base, const int* stride, const float* lam, int d, int k) {
+    if (k == d - 1) {
+        float v0 = V[base], v1 = V[base + stride[k]];
+        float t2 = lam[k] * v1;                       /* float * float */
+        return (1.0 - (double)lam[k]) * (double)v0 + (double)t2;
+    }
+    double a = lerp_rec_f(V, base, stride, lam, d, k + 1);
+    double b = lerp_rec_f(V, base + stride[k], stride, lam, d, k + 1);
+    return (1.0 - (double)lam[k]) * a + (double)lam[k] * b;
 }
 int oracle_interp_f32(int d, const float* smin, const float* smax, const int64_t* orders,
                       int64_t n_v, const float* values, int64_t n_s, const float* s, float* out) {
@@ -116,7 +126,7 @@ int oracle_interp_f32(int d, const float* smin, const float* smax, const int64_t
                 lam[k] = t - (float)q;
                 base += stride[k] * q;
             }
-            out[v * n_s + i] = lerp_rec_f(V, base, stride, lam, d, 0);
+            out[v * n_s + i] = (float)lerp_rec_f(V, base, stride, lam, d, 0);
         }
     }
     return 0;

@@ -11,7 +11,10 @@ import os
 import numpy as np
 
 SDP_MAX_D = 4
+SDP_MAX_C = 4
 SDP_ABI_VERSION = 1
+LAYOUT_CONTROL_MINOR = 0   # "A": [state][w][u]
+LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsdp_b200.so")
@@ -36,12 +39,13 @@ class SdpTables(ctypes.Structure):
                 ("g_per_w", ctypes.c_int32),
                 ("W", ctypes.c_int32),
                 ("expect", ctypes.c_int32),
-                ("reserved", ctypes.c_int32),
+                ("layout", ctypes.c_int32),
                 ("p", ctypes.c_void_p),
                 ("items", ctypes.c_void_p),
                 ("n_items", ctypes.c_int64),
                 ("item_begin", ctypes.c_void_p),
-                ("n_states", ctypes.c_int64)]
+                ("n_states", ctypes.c_int64),
+                ("U", ctypes.c_void_p)]
 
 
 # numpy mirrors of the per-state descriptor and the work item (host-built arrays
@@ -49,8 +53,9 @@ class SdpTables(ctypes.Structure):
 STATE_DESC_DTYPE = np.dtype([("entry_off", np.int64),
                              ("g_off", np.int64),
                              ("src", np.int64, (SDP_MAX_D + 1,)),
-                             ("us", np.int32, (SDP_MAX_D + 1,)),
+                             ("cs", np.int32, (SDP_MAX_D + 1, SDP_MAX_C)),
                              ("ws", np.int32, (SDP_MAX_D + 1,)),
+                             ("npts", np.int32, (SDP_MAX_C,)),
                              ("U", np.int32),
                              ("Upad", np.int32)], align=True)
 ITEM_DTYPE = np.dtype([("entry_base", np.int64),
@@ -59,7 +64,7 @@ ITEM_DTYPE = np.dtype([("entry_base", np.int64),
                        ("u_begin", np.int32),
                        ("u_count", np.int32),
                        ("state", np.int32)], align=True)
-assert STATE_DESC_DTYPE.itemsize == 104, STATE_DESC_DTYPE.itemsize
+assert STATE_DESC_DTYPE.itemsize == 184, STATE_DESC_DTYPE.itemsize
 assert ITEM_DTYPE.itemsize == 32, ITEM_DTYPE.itemsize
 
 _vp = ctypes.c_void_p
@@ -75,6 +80,8 @@ SIGNATURES = {
     "sdp_cell_setup": (ctypes.c_int, [_gp, _i64, _vp, _vp, _vp, _vp]),
     "sdp_build_tables": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp,
                                         _i32, _vp]),
+    "sdp_build_tables_tiled": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _vp,
+                                              _i32, _vp, _vp, _i64, _vp, _vp]),
     "sdp_sweep": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdp_policy_eval": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
                                        _vp, _vp, _i32, _i32, _i64, _vp, _vp]),

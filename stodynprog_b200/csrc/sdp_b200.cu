@@ -158,6 +158,30 @@ struct Lerp<T, D, D> {
     }
 };
 
+// fp32 specialisation of the reference's fused type: the generated C writes the
+// weights as `(1.0 - lam_k)` with a double literal, so the `(1.0-lam)*a` terms
+// and the sums are evaluated in double while the innermost `lam*v` product of
+// two floats stays a float product; one final rounding to float on the store.
+template <int D, int K>
+struct Lerp<float, D, K> {
+    __device__ __forceinline__ static double eval_d(const float* __restrict__ V, int base,
+                                                    const int (&stride)[SDP_MAX_D], const float (&lam)[D]) {
+        if (K == D - 1) {
+            float v0 = __ldg(V + base), v1 = __ldg(V + base + stride[K]);
+            float t2 = mul_(lam[K], v1);
+            return add_(mul_(sub_(1.0, (double)lam[K]), (double)v0), (double)t2);
+        } else {
+            double a = Lerp<float, D, (K + 1 < D ? K + 1 : K)>::eval_d(V, base, stride, lam);
+            double b = Lerp<float, D, (K + 1 < D ? K + 1 : K)>::eval_d(V, base + stride[K], stride, lam);
+            return add_(mul_(sub_(1.0, (double)lam[K]), a), mul_((double)lam[K], b));
+        }
+    }
+    __device__ __forceinline__ static float eval(const float* __restrict__ V, int base,
+                                                 const int (&stride)[SDP_MAX_D], const float (&lam)[D]) {
+        return __double2float_rn(eval_d(V, base, stride, lam));
+    }
+};
+
 // ---------------------------------------------------------------------------
 // K0a: cell search on explicit points,  s [d][n] -> cell [n], lam [d][n]
 // ---------------------------------------------------------------------------
@@ -198,9 +222,44 @@ extern "C" int sdp_cell_setup(const SdpGrid* grid, int64_t n, const double* s, i
 }
 
 // ---------------------------------------------------------------------------
-// K0b: table build. One thread per (state, w, u) entry of the padded block;
-// u fastest across threads so the table writes are coalesced.
+// K0b: table build.  One thread per (state, w, u) entry; the fastest thread
+// index follows the fastest table index so that the table writes are coalesced.
 // ---------------------------------------------------------------------------
+// source offset of element (flat control u, perturbation w) of slot k: the flat
+// control index is decomposed C-order over the state's control grid dims
+// (stodynprog.py:686 unravel_index), each axis with its own source stride.
+__device__ __forceinline__ int64_t src_offset(const SdpStateDesc* ds, int k, int u, int w) {
+    int64_t off = ds->src[k] + (int64_t)w * ds->ws[k];
+#pragma unroll
+    for (int c = SDP_MAX_C - 1; c >= 0; --c) {
+        const int n = ds->npts[c];
+        const int i = u % n;
+        u /= n;
+        off += (int64_t)i * ds->cs[k][c];
+    }
+    return off;
+}
+
+template <int D>
+__device__ __forceinline__ void build_entry(const GridT<double>& G, const SdpStateDesc* ds, bool live,
+                                            int u, int w, const double* __restrict__ staging,
+                                            int32_t* __restrict__ cell, double* __restrict__ lam,
+                                            int64_t lam_plane, int64_t off) {
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double l = 0.0;
+        if (live) {
+            int q;
+            double sk = staging[src_offset(ds, k, u, w)];
+            cell_1d<double>(sk, G.smin[k], G.span[k], G.om1[k], G.order[k], q, l);
+            base += q * G.stride[k];
+        }
+        lam[(int64_t)k * lam_plane + off] = l;
+    }
+    cell[off] = base;
+}
+
 template <int D>
 __global__ void __launch_bounds__(256)
 k_build_tables(GridT<double> G, int W, int g_per_w, int tiles_per_state,
@@ -218,22 +277,10 @@ k_build_tables(GridT<double> G, int W, int g_per_w, int tiles_per_state,
     const int u = e - w * Upad;
     const int64_t off = ds->entry_off + e;
     const bool live = u < U;
-    int base = 0;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        double l = 0.0;
-        if (live) {
-            int q;
-            double sk = staging[ds->src[k] + (int64_t)u * ds->us[k] + (int64_t)w * ds->ws[k]];
-            cell_1d<double>(sk, G.smin[k], G.span[k], G.om1[k], G.order[k], q, l);
-            base += q * G.stride[k];
-        }
-        lam[(int64_t)k * lam_plane + off] = l;
-    }
-    cell[off] = base;
+    build_entry<D>(G, ds, live, u, w, staging, cell, lam, lam_plane, off);
     if (g_per_w || w == 0) {
         double gv = 0.0;
-        if (live) gv = staging[ds->src[D] + (int64_t)u * ds->us[D] + (int64_t)w * ds->ws[D]];
+        if (live) gv = staging[src_offset(ds, D, u, w)];
         g[ds->g_off + (g_per_w ? e : u)] = gv;
     }
 }
@@ -259,6 +306,64 @@ extern "C" int sdp_build_tables(const SdpGrid* grid, int32_t W, int32_t g_per_w,
         case 2: k_build_tables<2><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, tiles, desc, staging, cell, lam, lam_plane, g); break;
         case 3: k_build_tables<3><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, tiles, desc, staging, cell, lam, lam_plane, g); break;
         default: k_build_tables<4><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, tiles, desc, staging, cell, lam, lam_plane, g); break;
+    }
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+// layout B: entries of a tile are [u][w][lane]; thread e -> lane = e%32, (u,w) = e/32
+template <int D>
+__global__ void __launch_bounds__(256)
+k_build_tables_tiled(GridT<double> G, int W, int g_per_w, int blocks_per_tile, int64_t n_states,
+                     const SdpStateDesc* __restrict__ desc, const double* __restrict__ staging,
+                     const int64_t* __restrict__ tile_off, const int64_t* __restrict__ tile_g_off,
+                     const int32_t* __restrict__ tile_U, int32_t* __restrict__ cell,
+                     double* __restrict__ lam, int64_t lam_plane, double* __restrict__ g) {
+    const int64_t tile = blockIdx.x / blocks_per_tile;
+    const int blk = blockIdx.x % blocks_per_tile;
+    const int Ut = tile_U[tile];
+    const int e = blk * blockDim.x + threadIdx.x;
+    if (e >= Ut * W * 32) return;
+    const int lane = e & 31;
+    const int r = e >> 5;
+    const int u = r / W;
+    const int w = r - u * W;
+    const int64_t state = tile * 32 + lane;
+    const bool in_range = state < n_states;
+    const SdpStateDesc* ds = desc + (in_range ? state : 0);
+    const bool live = in_range && u < ds->U;
+    const int64_t off = tile_off[tile] + e;
+    build_entry<D>(G, ds, live, u, w, staging, cell, lam, lam_plane, off);
+    if (g_per_w || w == 0) {
+        double gv = 0.0;
+        if (live) gv = staging[src_offset(ds, D, u, w)];
+        g[g_per_w ? off : (tile_g_off[tile] + (int64_t)u * 32 + lane)] = gv;
+    }
+}
+
+extern "C" int sdp_build_tables_tiled(const SdpGrid* grid, int32_t W, int32_t g_per_w, int64_t n_states,
+                                      const SdpStateDesc* desc, const double* staging, int64_t n_tiles,
+                                      const int64_t* tile_off, const int64_t* tile_g_off,
+                                      const int32_t* tile_U, int32_t max_tile_U, int32_t* cell,
+                                      double* lam, int64_t lam_plane, double* g, void* stream) {
+    GridT<double> G;
+    int rc = make_grid<double>(grid, &G, nullptr);
+    if (rc) return rc;
+    if (W < 1 || n_states < 0 || n_tiles < 0 || max_tile_U < 0 || n_states > 32 * n_tiles)
+        return fail(SDP_EINVAL, "%s", "sdp_build_tables_tiled: bad sizes");
+    if (n_states == 0 || max_tile_U == 0) return SDP_OK;
+    if (!desc || !staging || !tile_off || !tile_g_off || !tile_U || !cell || !lam || !g)
+        return fail(SDP_EINVAL, "%s", "sdp_build_tables_tiled: NULL pointer");
+    int64_t per_tile = (int64_t)W * max_tile_U * 32;
+    int bpt = (int)((per_tile + 255) / 256);
+    int64_t blocks = n_tiles * bpt;
+    if (blocks > 0x7fffffffLL) return fail(SDP_EINVAL, "%s", "sdp_build_tables_tiled: chunk too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (grid->d) {
+        case 1: k_build_tables_tiled<1><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, bpt, n_states, desc, staging, tile_off, tile_g_off, tile_U, cell, lam, lam_plane, g); break;
+        case 2: k_build_tables_tiled<2><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, bpt, n_states, desc, staging, tile_off, tile_g_off, tile_U, cell, lam, lam_plane, g); break;
+        case 3: k_build_tables_tiled<3><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, bpt, n_states, desc, staging, tile_off, tile_g_off, tile_U, cell, lam, lam_plane, g); break;
+        default: k_build_tables_tiled<4><<<(unsigned)blocks, 256, 0, st>>>(G, W, g_per_w, bpt, n_states, desc, staging, tile_off, tile_g_off, tile_U, cell, lam, lam_plane, g); break;
     }
     SDP_LAUNCH_CHECK();
     return SDP_OK;
@@ -408,6 +513,98 @@ k_sweep_finalize(int64_t n_states, const int64_t* __restrict__ item_begin,
     argmin_out[i] = bi;
 }
 
+// Layout B: lane <-> state of a 32-state tile; each lane walks the run of
+// controls serially (so its running minimum needs no index compare beyond the
+// NaN rule), the perturbation loop is batched WB nodes at a time to keep WB
+// independent table loads + gathers in flight per lane.
+template <int D, int WB>
+__global__ void __launch_bounds__(256)
+k_sweep_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+              double* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+    extern __shared__ double p_sh[];
+    for (int i = threadIdx.x; i < T.W; i += blockDim.x) p_sh[i] = T.expect ? T.p[i] : 1.0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t item_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item_id >= T.n_items) return;
+    const SdpItem it = T.items[item_id];
+    const int W = T.W;
+    const int64_t state = (int64_t)it.state * 32 + lane;
+    const int Us = (state < T.n_states) ? T.U[state] : 0;
+
+    double best_v = CUDART_INF;
+    int best_i = INT_MAX;
+    const int32_t* __restrict__ cellp = T.cell + it.entry_base + lane;
+    const double* __restrict__ lamp = T.lam + it.entry_base + lane;
+    const double* __restrict__ gp = T.g + it.g_base + lane;
+
+    for (int uu = 0; uu < it.u_count; ++uu) {
+        const int64_t row = (int64_t)uu * W * 32;
+        double acc = 0.0;
+        double gv = 0.0;
+        if (!T.g_per_w) gv = __ldcs(gp + (int64_t)uu * 32);
+        int w = 0;
+        for (; w + WB <= W; w += WB) {
+            int c[WB];
+            double l[WB][D];
+            double gw[WB];
+#pragma unroll
+            for (int b = 0; b < WB; ++b) {
+                const int64_t o = row + (int64_t)(w + b) * 32;
+                c[b] = __ldcs(cellp + o);
+#pragma unroll
+                for (int k = 0; k < D; ++k) l[b][k] = __ldcs(lamp + (int64_t)k * T.lam_plane + o);
+                gw[b] = T.g_per_w ? __ldcs(gp + o) : gv;
+            }
+            double v[WB];
+#pragma unroll
+            for (int b = 0; b < WB; ++b) v[b] = Lerp<double, D, 0>::eval(Jprev, c[b], G.stride, l[b]);
+#pragma unroll
+            for (int b = 0; b < WB; ++b) {
+                double jg = add_(gw[b], v[b]);
+                if (T.expect) acc = add_(acc, mul_(jg, p_sh[w + b]));
+                else acc = jg;
+            }
+        }
+        for (; w < W; ++w) {
+            const int64_t o = row + (int64_t)w * 32;
+            int c = __ldcs(cellp + o);
+            double l[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) l[k] = __ldcs(lamp + (int64_t)k * T.lam_plane + o);
+            double gw = T.g_per_w ? __ldcs(gp + o) : gv;
+            double jg = add_(gw, Lerp<double, D, 0>::eval(Jprev, c, G.stride, l));
+            if (T.expect) acc = add_(acc, mul_(jg, p_sh[w]));
+            else acc = jg;
+        }
+        const int u = it.u_begin + uu;
+        if (u < Us && better(acc, u, best_v, best_i)) { best_v = acc; best_i = u; }
+    }
+    part_val[item_id * 32 + lane] = best_v;
+    part_idx[item_id * 32 + lane] = best_i;
+}
+
+__global__ void __launch_bounds__(256)
+k_sweep_finalize_tiled(int64_t n_states, const int64_t* __restrict__ item_begin,
+                       const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
+                       double* __restrict__ J_out, int32_t* __restrict__ argmin_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_states) return;
+    const int64_t tile = i >> 5;
+    const int lane = (int)(i & 31);
+    int64_t b = item_begin[tile], e = item_begin[tile + 1];
+    double bv = CUDART_INF;
+    int bi = INT_MAX;
+    for (int64_t k = b; k < e; ++k) {
+        double v = part_val[k * 32 + lane];
+        int ix = part_idx[k * 32 + lane];
+        if (better(v, ix, bv, bi)) { bv = v; bi = ix; }
+    }
+    J_out[i] = bv;
+    argmin_out[i] = bi;
+}
+
 static int sweep_upl() {
     static int upl = 0;
     if (upl == 0) {
@@ -417,13 +614,30 @@ static int sweep_upl() {
     return upl;
 }
 
+static int sweep_wb() {
+    static int wb = 0;
+    if (wb == 0) {
+        const char* e = getenv("SDP_WB");
+        int v = e ? atoi(e) : 3;
+        wb = (v == 1 || v == 2 || v == 3 || v == 5) ? v : 3;
+    }
+    return wb;
+}
+
 template <int D>
 static int launch_sweep(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                         double* part_val, int32_t* part_idx, cudaStream_t st) {
     const int warps = 8;
     unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
     size_t shm = (size_t)T.W * sizeof(double);
-    if (sweep_upl() == 2)
+    if (T.layout == SDP_LAYOUT_STATE_MINOR) {
+        switch (sweep_wb()) {
+            case 1: k_sweep_tiled<D, 1><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+            case 2: k_sweep_tiled<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+            case 5: k_sweep_tiled<D, 5><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+            default: k_sweep_tiled<D, 3><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+        }
+    } else if (sweep_upl() == 2)
         k_sweep<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
     else
         k_sweep<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
@@ -447,6 +661,10 @@ extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double
         return fail(SDP_EINVAL, "%s", "sdp_sweep: NULL pointer");
     if ((T.lam_plane & 3) || ((uintptr_t)T.cell & 15) || ((uintptr_t)T.lam & 15) || ((uintptr_t)T.g & 15))
         return fail(SDP_EINVAL, "%s", "sdp_sweep: tables must be 16-byte aligned, lam_plane % 4 == 0");
+    if (T.layout != SDP_LAYOUT_CONTROL_MINOR && T.layout != SDP_LAYOUT_STATE_MINOR)
+        return fail(SDP_EINVAL, "%s", "sdp_sweep: unknown table layout");
+    if (T.layout == SDP_LAYOUT_STATE_MINOR && !T.U)
+        return fail(SDP_EINVAL, "%s", "sdp_sweep: layout B needs the per-state control counts");
     cudaStream_t st = (cudaStream_t)stream;
     if (T.n_items > 0) {
         if (T.n_items / 8 + 1 > 0x7fffffffLL) return fail(SDP_EINVAL, "%s", "sdp_sweep: too many items");
@@ -459,7 +677,10 @@ extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double
         if (rc) return rc;
     }
     unsigned blocks = (unsigned)((T.n_states + 255) / 256);
-    k_sweep_finalize<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
+    if (T.layout == SDP_LAYOUT_STATE_MINOR)
+        k_sweep_finalize_tiled<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
+    else
+        k_sweep_finalize<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }

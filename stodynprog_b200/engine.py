@@ -139,6 +139,9 @@ class SweepTables(object):
         self.n_backups_local = 0   # admissible (x,u,w) triples in this slab
         self.n_backups_total = 0
         self.c_tables = None       # _cabi.SdpTables
+        self.tiled = False         # layout B (state-minor) when True
+        self.U_dev = None
+        self.tabulate_mode = None
         self.setup_seconds = 0.0
 
     @property
@@ -226,7 +229,12 @@ class Engine(object):
     def build_sweep_tables(self, solver, t_k=None, reuse=None):
         """Tabulate the user's callables over this rank's slab and build the dense
         tables on the device.  `reuse`: a SweepTables whose device buffers are
-        recycled when the sizes match (time-dependent recursion)."""
+        recycled when the sizes match (time-dependent recursion).
+
+        Solver knobs read here:
+          solver.table_layout : "auto" | "control_minor" (A) | "state_minor" (B)
+          solver.tabulate     : "auto" | "per_state" | "batched"
+        """
         import time
         torch = _torch()
         t0 = time.perf_counter()
@@ -247,6 +255,7 @@ class Engine(object):
         W = len(solver.perturb_grid[0]) if nb_perturb == 1 else 1
         coll = self.coll
         world, rank = coll.world, coll.rank
+        dev = self.device
 
         # pass 1: control boxes. Every rank scans an equal share, then the full
         # host table is replicated (it is needed to map argmin -> control values).
@@ -267,88 +276,174 @@ class Engine(object):
         bounds = partition_by_weight(U_all + 1, world) if world > 1 else [0, n_grid]
         sb, se = bounds[rank], bounds[rank + 1]
         n = se - sb
-        states = mine if (sb, se) == (eq[rank], eq[rank + 1]) else tb.state_tuples(state_grid, sb, se)
         host = tb.HostStateTable(n, nb_control)
         host.lo, host.hi, host.npts = host_full.lo[sb:se], host_full.hi[sb:se], host_full.npts[sb:se]
         U = U_all[sb:se]
-        Upad = (U + 3) // 4 * 4
-        entry_off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(W * Upad, out=entry_off[1:])
-        n_entries = int(entry_off[-1])
-        lam_plane = n_entries
+
+        # table layout (see include/sdp_b200.h): lane <-> control (A) when states
+        # have many controls, lane <-> state (B) when there are many states with
+        # few controls each
+        layout = getattr(solver, "table_layout", "auto")
+        if layout == "auto":
+            mean_U = float(U.mean()) if n else 0.0
+            layout = "state_minor" if (n >= 32 * 1024 and mean_U <= 1024) else "control_minor"
+        tiled = layout == "state_minor"
+        if tiled:
+            n_tiles = (n + 31) // 32
+            Upad_t = np.zeros(n_tiles * 32, dtype=np.int64)
+            Upad_t[:n] = U
+            tile_U = Upad_t.reshape(n_tiles, 32).max(axis=1)
+            tile_off = np.zeros(n_tiles + 1, dtype=np.int64)
+            np.cumsum(tile_U * W * 32, out=tile_off[1:])
+            n_entries = int(tile_off[-1])
+            entry_off = np.zeros(n + 1, dtype=np.int64)      # unused by layout B
+            Upad = np.zeros(n, dtype=np.int64)
+        else:
+            Upad = (U + 3) // 4 * 4
+            entry_off = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(W * Upad, out=entry_off[1:])
+            n_entries = int(entry_off[-1])
+        lam_plane = (n_entries + 3) // 4 * 4
 
         T = reuse if (reuse is not None and reuse.n_entries == n_entries and reuse.W == W
-                      and reuse.d == d) else SweepTables()
+                      and reuse.d == d and reuse.tiled == tiled) else SweepTables()
         T.grid, T.d, T.W = grid, d, W
+        T.tiled = tiled
         T.expect = 1 if nb_perturb == 1 else 0
         T.bounds, T.state_begin, T.n_states = bounds, sb, n
         T.host_full = host_full
         T.n_entries, T.lam_plane = n_entries, lam_plane
         T.n_backups_local = int(U.sum()) * W
         T.n_backups_total = int(U_all.sum()) * W
-        dev = self.device
         if T.cell is None:
-            T.cell = torch.empty(max(n_entries, 4), dtype=torch.int32, device=dev)
-            T.lam = torch.empty(max(n_entries, 4) * d, dtype=torch.float64, device=dev)
+            T.cell = torch.empty(max(lam_plane, 4), dtype=torch.int32, device=dev)
+            T.lam = torch.empty(max(lam_plane, 4) * d, dtype=torch.float64, device=dev)
         if nb_perturb == 1:
             T.p = self.to_device(np.asarray(solver.perturb_proba[0], dtype=float))
         else:
             T.p = self.to_device(np.ones(1))
+        T.U_dev = self.to_device(U.astype(np.int32)) if n else torch.zeros(1, dtype=torch.int32, device=dev)
         w_grid = [np.asarray(g) for g in solver.perturb_grid]
+        mode = getattr(solver, "tabulate", "auto")
+        T.tabulate_mode = None
 
-        def build(g_per_w):
-            if g_per_w:
-                g_off = entry_off
-                g_len = n_entries
-            else:
+        def build(g_per_w, batched):
+            if tiled:
+                if g_per_w:
+                    tile_g_off = tile_off
+                else:
+                    tile_g_off = np.zeros(n_tiles + 1, dtype=np.int64)
+                    np.cumsum(tile_U * 32, out=tile_g_off[1:])
                 g_off = np.zeros(n + 1, dtype=np.int64)
-                np.cumsum(Upad, out=g_off[1:])
+                g_len = int(tile_g_off[-1])
+                tile_off_dev = self.to_device(tile_off)
+                tile_g_off_dev = self.to_device(tile_g_off)
+                tile_U_dev = self.to_device(tile_U.astype(np.int32))
+            else:
+                tile_g_off = None
+                if g_per_w:
+                    g_off = entry_off
+                else:
+                    g_off = np.zeros(n + 1, dtype=np.int64)
+                    np.cumsum(Upad, out=g_off[1:])
                 g_len = int(g_off[-1])
             if T.g is None or T.g.numel() != max(g_len, 4):
                 T.g = torch.empty(max(g_len, 4), dtype=torch.float64, device=dev)
             T.g_per_w = g_per_w
+            done = [0]      # states flushed so far (chunks arrive in order)
 
-            def flush(desc, staging, max_Upad):
+            def flush(desc, staging):
                 desc_dev = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(dev)
                 stag_dev = torch.from_numpy(staging).to(dev)
-                rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, len(desc),
-                                               self._ptr(desc_dev), self._ptr(stag_dev),
-                                               self._ptr(T.cell), self._ptr(T.lam), lam_plane,
-                                               self._ptr(T.g), int(max_Upad), self.stream)
-                _cabi.check(rc, "sdp_build_tables")
+                ns = len(desc)
+                if tiled:
+                    assert done[0] % 32 == 0
+                    t_first = done[0] // 32
+                    nt = (ns + 31) // 32
+                    rc = self.lib.sdp_build_tables_tiled(
+                        ctypes.byref(grid), W, g_per_w, ns, self._ptr(desc_dev), self._ptr(stag_dev), nt,
+                        ctypes.c_void_p(tile_off_dev.data_ptr() + 8 * t_first),
+                        ctypes.c_void_p(tile_g_off_dev.data_ptr() + 8 * t_first),
+                        ctypes.c_void_p(tile_U_dev.data_ptr() + 4 * t_first),
+                        int(tile_U[t_first:t_first + nt].max()),
+                        self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g), self.stream)
+                    _cabi.check(rc, "sdp_build_tables_tiled")
+                else:
+                    rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, ns,
+                                                   self._ptr(desc_dev), self._ptr(stag_dev),
+                                                   self._ptr(T.cell), self._ptr(T.lam), lam_plane,
+                                                   self._ptr(T.g), int(desc["Upad"].max()), self.stream)
+                    _cabi.check(rc, "sdp_build_tables")
+                done[0] += ns
                 # the staging tensors are freed by torch's caching allocator in
                 # stream order, so no synchronisation is needed here
 
-            ok = tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
-                                    g_per_w, flush)
-            return ok, g_off
+            align = 32 if tiled else 1
+            if batched:
+                tb.tabulate_states_batched(sys, state_grid, sb, se, host, w_grid, t_k, entry_off,
+                                           g_off, Upad, g_per_w, flush, align=align)
+            else:
+                states = mine if (sb, se) == (eq[rank], eq[rank + 1]) else \
+                    tb.state_tuples(state_grid, sb, se)
+                tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
+                                   g_per_w, flush, align=align)
+            return g_off, tile_g_off
 
-        ok, g_off = build(T.g_per_w if reuse is T else 0)
-        if not ok:
-            ok, g_off = build(1)
-            assert ok
+        # mode/g-layout resolution: batched evaluation is tried first in "auto"
+        # mode and abandoned if it fails or is not bit-identical to the
+        # reference's per-state calls on the sample states
+        g_per_w = T.g_per_w if reuse is T else 0
+        batched = mode in ("auto", "batched")
+        result = None
+        while result is None:
+            try:
+                result = build(g_per_w, batched)
+                T.tabulate_mode = "batched" if batched else "per_state"
+            except tb.GDependsOnW:
+                if g_per_w:
+                    raise
+                g_per_w = 1          # the cost depends on w: dense g table
+            except tb.BatchedMismatch:
+                if mode != "auto":
+                    raise
+                batched = False      # not bit-identical to per-state calls
+            except Exception:
+                if not (batched and mode == "auto"):
+                    raise
+                batched = False      # callables not vectorisable over states
+        g_off, tile_g_off = result
 
         # work items: one warp per run of at most `item_chunk` controls
         chunk = self.item_chunk
-        n_it = (U + chunk - 1) // chunk
-        item_begin = np.zeros(n + 1, dtype=np.int64)
+        if tiled:
+            units, unit_U = n_tiles, tile_U
+        else:
+            units, unit_U = n, U
+        n_it = (unit_U + chunk - 1) // chunk
+        item_begin = np.zeros(units + 1, dtype=np.int64)
         np.cumsum(n_it, out=item_begin[1:])
         n_items = int(item_begin[-1])
-        st = np.repeat(np.arange(n, dtype=np.int64), n_it)
+        st = np.repeat(np.arange(units, dtype=np.int64), n_it)
         kk = np.arange(n_items, dtype=np.int64) - item_begin[st]
         items = np.zeros(n_items, dtype=_cabi.ITEM_DTYPE)
         items["u_begin"] = kk * chunk
-        items["u_count"] = np.minimum(chunk, U[st] - kk * chunk)
-        items["entry_base"] = entry_off[st] + kk * chunk
-        items["g_base"] = g_off[st] + kk * chunk
-        items["Upad"] = Upad[st]
+        items["u_count"] = np.minimum(chunk, unit_U[st] - kk * chunk)
         items["state"] = st
+        if tiled:
+            items["entry_base"] = tile_off[st] + kk * chunk * W * 32
+            items["g_base"] = items["entry_base"] if T.g_per_w else tile_g_off[st] + kk * chunk * 32
+            items["Upad"] = 0
+        else:
+            items["entry_base"] = entry_off[st] + kk * chunk
+            items["g_base"] = g_off[st] + kk * chunk
+            items["Upad"] = Upad[st]
         T.n_items = n_items
         T.items = torch.from_numpy(items.view(np.uint8).reshape(-1)).to(dev) if n_items else \
             torch.zeros(32, dtype=torch.uint8, device=dev)
         T.item_begin = self.to_device(item_begin)
-        T.part_val = torch.empty(max(n_items, 1), dtype=torch.float64, device=dev)
-        T.part_idx = torch.empty(max(n_items, 1), dtype=torch.int32, device=dev)
+        n_part = max(n_items, 1) * (32 if tiled else 1)
+        T.part_val = torch.empty(n_part, dtype=torch.float64, device=dev)
+        T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)
         T.J_out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
         T.argmin = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
 
@@ -360,12 +455,13 @@ class Engine(object):
         c.g_per_w = T.g_per_w
         c.W = W
         c.expect = T.expect
-        c.reserved = 0
+        c.layout = _cabi.LAYOUT_STATE_MINOR if tiled else _cabi.LAYOUT_CONTROL_MINOR
         c.p = T.p.data_ptr()
         c.items = T.items.data_ptr()
         c.n_items = n_items
         c.item_begin = T.item_begin.data_ptr()
         c.n_states = n
+        c.U = T.U_dev.data_ptr()
         T.c_tables = c
         self.sync()
         T.setup_seconds = time.perf_counter() - t0

@@ -53,6 +53,9 @@ class DPSolver(object):
         self.cache_tables = bool(cache_tables)
         self._table_cache = {}
         self.last_tables = None      # SweepTables of the last sweep (bench / diagnostics)
+        # table layout and host tabulation mode (see Engine.build_sweep_tables)
+        self.table_layout = "auto"    # "auto" | "control_minor" | "state_minor"
+        self.tabulate = "auto"        # "auto" | "per_state" | "batched"
 
     # ------------------------------------------------------------------
     # discretisation (host only)
@@ -144,7 +147,8 @@ class DPSolver(object):
                 tuple(sig(g) for g in self.state_grid),
                 tuple(sig(g) for g in self.perturb_grid),
                 tuple(sig(p) for p in self.perturb_proba),
-                tuple(float(c) for c in self.control_steps))
+                tuple(float(c) for c in self.control_steps),
+                self.table_layout, self.tabulate)
 
     def clear_tables(self):
         """drop the device-resident tables (call after mutating anything the

@@ -17,7 +17,8 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["control_grid_counts", "control_axis_values", "HostStateTable", "tabulate_states"]
+__all__ = ["control_grid_counts", "control_axis_values", "HostStateTable", "tabulate_states",
+           "tabulate_states_batched", "GDependsOnW", "BatchedMismatch"]
 
 
 def _npts_for(width, step):
@@ -112,45 +113,42 @@ def _compact(a, control_dims, U, W, what):
 
 
 class _ChunkWriter(object):
-    """Accumulates staged arrays + descriptors and flushes them to the device."""
+    """Accumulates staged arrays + per-state descriptors (SdpStateDesc) and
+    flushes them to the device at chunk boundaries.  `align` = number of states
+    a flush must be a multiple of (32 for the state-minor layout)."""
 
-    def __init__(self, d, flush_fn, max_doubles):
+    def __init__(self, d, flush_fn, max_doubles, align=1):
         self.d = d
         self.flush_fn = flush_fn
         self.max_doubles = max_doubles
+        self.align = align
         self.reset()
 
     def reset(self):
         self.arrays = []
         self.n_doubles = 0
-        self.desc = []
-        self.max_Upad = 0
+        self.descs = []          # list of structured arrays
+        self.n_states = 0
 
-    def add_state(self, entry_off, g_off, U, Upad, compact):
-        """compact: list of d+1 tuples (array(Ueff,Weff), Ueff, Weff)"""
-        rec = np.zeros((), dtype=_cabi.STATE_DESC_DTYPE)
-        rec["entry_off"] = entry_off
-        rec["g_off"] = g_off
-        rec["U"] = U
-        rec["Upad"] = Upad
-        slots = list(range(self.d)) + [self.d]   # slot d holds the stage cost
-        for k, (arr, u_eff, w_eff) in zip(slots, compact):
-            rec["src"][k] = self.n_doubles
-            rec["us"][k] = w_eff if u_eff > 1 else 0
-            rec["ws"][k] = 1 if w_eff > 1 else 0
-            self.arrays.append(arr.ravel())
-            self.n_doubles += arr.size
-        self.desc.append(rec)
-        self.max_Upad = max(self.max_Upad, Upad)
-        if self.n_doubles >= self.max_doubles:
+    def add_array(self, arr):
+        """stage one array, return its offset (in doubles)"""
+        off = self.n_doubles
+        self.arrays.append(arr.reshape(-1))
+        self.n_doubles += arr.size
+        return off
+
+    def add_descs(self, recs):
+        self.descs.append(recs)
+        self.n_states += len(recs)
+        if self.n_doubles >= self.max_doubles and self.n_states % self.align == 0:
             self.flush()
 
     def flush(self):
-        if not self.desc:
+        if not self.n_states:
             return
         staging = np.concatenate(self.arrays) if self.arrays else np.zeros(1)
-        desc = np.array(self.desc, dtype=_cabi.STATE_DESC_DTYPE)
-        self.flush_fn(desc, staging, self.max_Upad)
+        desc = np.concatenate(self.descs)
+        self.flush_fn(desc, staging)
         self.reset()
 
 
@@ -174,48 +172,202 @@ def scan_control_boxes(sys, control_steps, states, t_k=None):
     return tab
 
 
-def tabulate_states(sys, states, host_tab, perturb_grid, t_k, entry_off, g_off, Upad, g_per_w,
-                    flush_fn, max_doubles=8 << 20):
-    """Second pass: call dyn/cost per state with the reference's argument
-    shapes (stodynprog.py:655-676) and stage the un-broadcast outputs.
+class GDependsOnW(Exception):
+    """the stage cost depends on the perturbation but the tables were being
+    built with one g per (state, control): restart with a dense g table"""
 
-    Returns True on success, or False if a state's cost turned out to depend on
-    the perturbation while `g_per_w` is 0 (the caller restarts in dense-g mode).
-    """
+
+def _eval_one_state(sys, x_k, host_tab, i, w_args, t_k, W):
+    """dyn/cost of one state with the reference's argument shapes
+    (stodynprog.py:655-676).  Returns [(array(Ueff,Weff), Ueff, Weff)] * (d+1)."""
     d = len(sys.state)
     nb_control = len(sys.control)
+    control_dims = tuple(int(n) for n in host_tab.npts[i])
+    U = int(np.prod(control_dims)) if nb_control else 1
+    u_grids = []
+    for c in range(nb_control):
+        ug = make_control_grid(host_tab.lo[i, c], host_tab.hi[i, c], control_dims[c])
+        # control c varies along axis c, the perturbation along the last axis
+        ug.shape = (1,) * c + (-1,) + (1,) * (nb_control - c)
+        u_grids.append(ug)
+    args = x_k + tuple(u_grids) + w_args
+    if t_k is not None:
+        args = (t_k,) + args
+    x_next = sys.dyn(*args, **sys.params)
+    g_k = sys.cost(*args, **sys.params)
+    if len(x_next) != d:
+        raise ValueError("dyn returned %d next-state components, expected %d" % (len(x_next), d))
+    compact = [_compact(c, control_dims, U, W, "dyn") for c in x_next]
+    compact.append(_compact(g_k, control_dims, U, W, "cost"))
+    # the joint broadcast of (g, x_next...) must cover the whole control grid
+    # (stodynprog.py:683 asserts J.shape == control_dims)
+    if U > 1 and not any(u_eff == U for _, u_eff, _ in compact):
+        raise AssertionError("dyn/cost outputs do not span the control grid %s" % (control_dims,))
+    return compact, control_dims, U
+
+
+def tabulate_states(sys, states, host_tab, perturb_grid, t_k, entry_off, g_off, Upad, g_per_w,
+                    flush_fn, max_doubles=8 << 20, align=1):
+    """Second pass, per-state mode: call dyn/cost once per state exactly like
+    the reference's hot loop and stage the un-broadcast outputs.
+    Raises GDependsOnW if a cost depends on w while `g_per_w` is 0."""
+    d = len(sys.state)
+    nb_control = len(sys.control)
+    if nb_control > _cabi.SDP_MAX_C:
+        raise NotImplementedError("more than %d control variables" % _cabi.SDP_MAX_C)
     W = len(perturb_grid[0]) if len(perturb_grid) > 0 else 1
-    params = sys.params
-    writer = _ChunkWriter(d, flush_fn, max_doubles)
+    writer = _ChunkWriter(d, flush_fn, max_doubles, align)
     w_args = tuple(perturb_grid)
-    for i, x_k in enumerate(states):
-        npts = host_tab.npts[i]
-        control_dims = tuple(int(n) for n in npts)
-        U = int(np.prod(control_dims)) if nb_control else 1
-        u_grids = []
-        for c in range(nb_control):
-            ug = make_control_grid(host_tab.lo[i, c], host_tab.hi[i, c], control_dims[c])
-            # control c varies along axis c, the perturbation along the last axis
-            ug.shape = (1,) * c + (-1,) + (1,) * (nb_control - c)
-            u_grids.append(ug)
-        args = x_k + tuple(u_grids) + w_args
-        if t_k is not None:
-            args = (t_k,) + args
-        x_next = sys.dyn(*args, **params)
-        g_k = sys.cost(*args, **params)
-        if len(x_next) != d:
-            raise ValueError("dyn returned %d next-state components, expected %d" % (len(x_next), d))
-        compact = [_compact(c, control_dims, U, W, "dyn") for c in x_next]
-        compact.append(_compact(g_k, control_dims, U, W, "cost"))
-        # the joint broadcast of (g, x_next...) must cover the whole control grid
-        # (stodynprog.py:683 asserts J.shape == control_dims)
-        if U > 1 and not any(u_eff == U for _, u_eff, _ in compact):
-            raise AssertionError("dyn/cost outputs do not span the control grid %s" % (control_dims,))
-        if compact[-1][2] > 1 and not g_per_w:
-            return False
-        writer.add_state(int(entry_off[i]), int(g_off[i]), U, int(Upad[i]), compact)
+    block = 1024
+    for b0 in range(0, len(states), block):
+        b1 = min(b0 + block, len(states))
+        recs = np.zeros(b1 - b0, dtype=_cabi.STATE_DESC_DTYPE)
+        recs["npts"] = 1
+        for i in range(b0, b1):
+            compact, control_dims, U = _eval_one_state(sys, states[i], host_tab, i, w_args, t_k, W)
+            if compact[-1][2] > 1 and not g_per_w:
+                raise GDependsOnW()
+            r = recs[i - b0]
+            r["U"] = U
+            r["npts"][:nb_control] = control_dims
+            # C-order strides of the flattened control index, per axis
+            tail = np.ones(nb_control + 1, dtype=np.int64)
+            for c in range(nb_control - 1, -1, -1):
+                tail[c] = tail[c + 1] * control_dims[c]
+            for k, (arr, u_eff, w_eff) in enumerate(compact):
+                r["src"][k] = writer.add_array(arr)
+                r["ws"][k] = 1 if w_eff > 1 else 0
+                if u_eff > 1:
+                    r["cs"][k][:nb_control] = w_eff * tail[1:nb_control + 1]
+        recs["entry_off"] = entry_off[b0:b1]
+        recs["g_off"] = g_off[b0:b1]
+        recs["Upad"] = Upad[b0:b1]
+        writer.add_descs(recs)
     writer.flush()
-    return True
+
+
+def _strides_or_zero(shape):
+    """element strides of a C-contiguous array of `shape`, 0 on size-1 axes"""
+    st = np.ones(len(shape), dtype=np.int64)
+    for k in range(len(shape) - 2, -1, -1):
+        st[k] = st[k + 1] * shape[k + 1]
+    return np.where(np.asarray(shape) == 1, 0, st)
+
+
+def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W):
+    """dyn/cost for a chunk of S states in ONE call: state variables enter as
+    (S,1,..,1) arrays, control c as an (S,..,n_c_max,..,1) array whose row s is
+    that state's own control grid (padded by repeating its last point), the
+    perturbation as the reference's (W,) vector.  Element-wise numpy arithmetic
+    gives the same values as the reference's per-state calls; this is verified
+    on sample states by the caller before the mode is trusted."""
+    S, nb_control = npts.shape
+    d = len(state_cols)
+    nmax = [int(npts[:, c].max()) for c in range(nb_control)]
+    full_shape = (S,) + tuple(nmax) + (W,)
+    rank = len(full_shape)
+    xs = tuple(col.reshape((S,) + (1,) * (rank - 1)) for col in state_cols)
+    us = []
+    for c in range(nb_control):
+        j = np.arange(nmax[c])[None, :]
+        n_c = npts[:, c][:, None]
+        vals = control_axis_values(lo[:, c][:, None], hi[:, c][:, None], n_c, np.minimum(j, n_c - 1))
+        us.append(vals.reshape((S,) + (1,) * c + (nmax[c],) + (1,) * (nb_control - c)))
+    args = xs + tuple(us) + w_args
+    if t_k is not None:
+        args = (t_k,) + args
+    x_next = sys.dyn(*args, **sys.params)
+    g_k = sys.cost(*args, **sys.params)
+    if len(x_next) != d:
+        raise ValueError("dyn returned %d next-state components, expected %d" % (len(x_next), d))
+    outs = []
+    for what, a in [("dyn", c) for c in x_next] + [("cost", g_k)]:
+        a = np.asarray(a)
+        if a.dtype != np.float64:
+            a = a.astype(float)
+        if a.ndim > rank:
+            raise ValueError("%s output of rank %d does not broadcast to %s" % (what, a.ndim, full_shape))
+        a = np.ascontiguousarray(a.reshape((1,) * (rank - a.ndim) + a.shape))
+        for n_a, n_f in zip(a.shape, full_shape):
+            if n_a != 1 and n_a != n_f:
+                raise ValueError("%s output shape %s does not broadcast to %s" % (what, a.shape, full_shape))
+        outs.append(a)
+    return outs, nmax
+
+
+def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid, t_k, entry_off,
+                            g_off, Upad, g_per_w, flush_fn, chunk_states=4096,
+                            max_doubles=16 << 20, align=1, verify=8):
+    """Second pass, batched mode: one dyn/cost call per chunk of states.
+    `verify` sample states of the first chunk are re-evaluated per state, the
+    reference's way, and compared bit-for-bit; a mismatch raises
+    BatchedMismatch (the caller falls back to the per-state mode)."""
+    d = len(sys.state)
+    nb_control = len(sys.control)
+    if nb_control > _cabi.SDP_MAX_C:
+        raise NotImplementedError("more than %d control variables" % _cabi.SDP_MAX_C)
+    W = len(perturb_grid[0]) if len(perturb_grid) > 0 else 1
+    w_args = tuple(perturb_grid)
+    dims = [len(g) for g in state_grid]
+    writer = _ChunkWriter(d, flush_fn, max_doubles, align)
+    n = end - begin
+    chunk_states = max(align, chunk_states // align * align)
+    checked = False
+    for b0 in range(0, n, chunk_states):
+        b1 = min(b0 + chunk_states, n)
+        S = b1 - b0
+        flat = np.arange(begin + b0, begin + b1)
+        idx = np.unravel_index(flat, dims)
+        cols = [np.asarray(state_grid[k])[idx[k]] for k in range(d)]
+        npts = host_tab.npts[b0:b1]
+        outs, nmax = _eval_state_chunk(sys, cols, host_tab.lo[b0:b1], host_tab.hi[b0:b1], npts,
+                                       w_args, t_k, W)
+        if outs[-1].shape[-1] > 1 and not g_per_w:
+            raise GDependsOnW()
+        if not checked and verify:
+            _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, min(verify, S))
+            checked = True
+        recs = np.zeros(S, dtype=_cabi.STATE_DESC_DTYPE)
+        recs["npts"] = 1
+        recs["npts"][:, :nb_control] = npts
+        recs["U"] = npts.prod(axis=1) if nb_control else 1
+        recs["entry_off"] = entry_off[b0:b1]
+        recs["g_off"] = g_off[b0:b1]
+        recs["Upad"] = Upad[b0:b1]
+        for k, a in enumerate(outs):
+            st = _strides_or_zero(a.shape)
+            base = writer.add_array(a)
+            recs["src"][:, k] = base + np.arange(S) * st[0]
+            recs["cs"][:, k, :nb_control] = st[1:1 + nb_control]
+            recs["ws"][:, k] = st[-1]
+        writer.add_descs(recs)
+    writer.flush()
+
+
+class BatchedMismatch(Exception):
+    """the user's callables do not give bit-identical results when evaluated on
+    a chunk of states at once"""
+
+
+def _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, n_check):
+    """bit-for-bit comparison of the chunk evaluation against the reference's
+    per-state evaluation on a few sample states, after full broadcast"""
+    S = len(cols[0])
+    nb_control = len(sys.control)
+    picks = np.unique(np.linspace(0, S - 1, n_check).astype(int))
+    for s in picks:
+        x_k = tuple(col[s] for col in cols)
+        compact, control_dims, U = _eval_one_state(sys, x_k, host_tab, b0 + s, w_args, t_k, W)
+        full = tuple(control_dims) + (W,)
+        for a, (ref, u_eff, w_eff) in zip(outs, compact):
+            row = a[s if a.shape[0] > 1 else 0]                     # (n1.., Weff)
+            sl = tuple(slice(0, control_dims[c] if row.shape[c] > 1 else 1)
+                       for c in range(nb_control))
+            got = np.ascontiguousarray(np.broadcast_to(row[sl], full))
+            shape = (tuple(control_dims) if u_eff > 1 else (1,) * nb_control) + (w_eff,)
+            want = np.ascontiguousarray(np.broadcast_to(ref.reshape(shape), full))
+            if not np.array_equal(got.view(np.int64), want.view(np.int64)):
+                raise BatchedMismatch()
 
 
 def state_tuples(state_grid, begin, end):

@@ -62,35 +62,52 @@ class FakeLib(object):
         self.launches += 1
         return 0
 
+    @staticmethod
+    def _src_index(r, k, U, W, nc_max=_cabi.SDP_MAX_C):
+        """(W, U) array of staging offsets of slot k for state record r"""
+        u = np.arange(U)
+        off = np.zeros(U, dtype=np.int64) + int(r["src"][k])
+        rem = u.copy()
+        for c in range(nc_max - 1, -1, -1):
+            n = int(r["npts"][c])
+            off += (rem % n) * int(r["cs"][k][c])
+            rem //= n
+        return off[None, :] + np.arange(W)[:, None] * int(r["ws"][k])
+
+    def _expand_state(self, r, d, W, stag, smin, smax, orders):
+        U = int(r["U"])
+        assert U == int(np.prod(r["npts"]))
+        coords = np.stack([stag[self._src_index(r, k, U, W)].reshape(-1) for k in range(d)])
+        c, l = oc.cell_search(smin, smax, orders, coords)
+        gsrc = stag[self._src_index(r, d, U, W)]
+        return c.reshape(W, U), l.reshape(d, W, U), gsrc
+
+    def _staging(self, D, d, W, staging):
+        top = 0
+        for r in D:
+            U = int(r["U"])
+            for k in range(d + 1):
+                top = max(top, int(self._src_index(r, k, U, W).max()) + 1)
+        return _arr(staging, top, ctypes.c_double)
+
     def sdp_build_tables(self, gref, W, g_per_w, n_states, desc, staging, cell, lam, lam_plane, g,
                          max_Upad, stream):
         d, smin, smax, orders = _grid(gref)
         D = np.frombuffer((ctypes.c_uint8 * (n_states * _cabi.STATE_DESC_DTYPE.itemsize))
                           .from_address(desc.value), dtype=_cabi.STATE_DESC_DTYPE)
-        # staging / table extents are not passed through the ABI: map generously
-        top = 0
-        for r in D:
-            for k in range(d + 1):
-                top = max(top, int(r["src"][k]) + (int(r["U"]) - 1) * int(r["us"][k])
-                          + (W - 1) * int(r["ws"][k]) + 1)
-        stag = _arr(staging, top, ctypes.c_double)
+        stag = self._staging(D, d, W, staging)
         for r in D:
             U, Upad, eo, go = int(r["U"]), int(r["Upad"]), int(r["entry_off"]), int(r["g_off"])
             assert Upad % 4 == 0 and Upad >= U and Upad <= max_Upad
-            u = np.arange(U)[None, :]
-            w = np.arange(W)[:, None]
-            coords = np.stack([stag[int(r["src"][k]) + u * int(r["us"][k]) + w * int(r["ws"][k])]
-                               .reshape(-1) for k in range(d)])
-            c, l = oc.cell_search(smin, smax, orders, coords)
+            c, l, gsrc = self._expand_state(r, d, W, stag, smin, smax, orders)
             cell_blk = _arr(cell.value + 4 * eo, W * Upad, ctypes.c_int32).reshape(W, Upad)
             cell_blk[:] = 0
-            cell_blk[:, :U] = c.reshape(W, U)
+            cell_blk[:, :U] = c
             for k in range(d):
                 lam_blk = _arr(lam.value + 8 * (k * lam_plane + eo), W * Upad,
                                ctypes.c_double).reshape(W, Upad)
                 lam_blk[:] = 0
-                lam_blk[:, :U] = l[k].reshape(W, U)
-            gsrc = stag[int(r["src"][d]) + u * int(r["us"][d]) + w * int(r["ws"][d])]
+                lam_blk[:, :U] = l[k]
             if g_per_w:
                 g_blk = _arr(g.value + 8 * go, W * Upad, ctypes.c_double).reshape(W, Upad)
                 g_blk[:] = 0
@@ -99,6 +116,48 @@ class FakeLib(object):
                 g_blk = _arr(g.value + 8 * go, Upad, ctypes.c_double)
                 g_blk[:] = 0
                 g_blk[:U] = gsrc[0]
+        self.launches += 1
+        return 0
+
+    def sdp_build_tables_tiled(self, gref, W, g_per_w, n_states, desc, staging, n_tiles, tile_off,
+                               tile_g_off, tile_U, max_tile_U, cell, lam, lam_plane, g, stream):
+        d, smin, smax, orders = _grid(gref)
+        D = np.frombuffer((ctypes.c_uint8 * (n_states * _cabi.STATE_DESC_DTYPE.itemsize))
+                          .from_address(desc.value), dtype=_cabi.STATE_DESC_DTYPE)
+        stag = self._staging(D, d, W, staging)
+        toff = _arr(tile_off, n_tiles, ctypes.c_int64)
+        tgoff = _arr(tile_g_off, n_tiles, ctypes.c_int64)
+        tU = _arr(tile_U, n_tiles, ctypes.c_int32)
+        assert n_states <= 32 * n_tiles
+        for t in range(n_tiles):
+            Ut = int(tU[t])
+            assert Ut <= max_tile_U
+            cell_blk = _arr(cell.value + 4 * int(toff[t]), Ut * W * 32, ctypes.c_int32).reshape(Ut, W, 32)
+            cell_blk[:] = 0
+            lam_blk = [_arr(lam.value + 8 * (k * lam_plane + int(toff[t])), Ut * W * 32,
+                            ctypes.c_double).reshape(Ut, W, 32) for k in range(d)]
+            for k in range(d):
+                lam_blk[k][:] = 0
+            if g_per_w:
+                g_blk = _arr(g.value + 8 * int(toff[t]), Ut * W * 32, ctypes.c_double).reshape(Ut, W, 32)
+            else:
+                g_blk = _arr(g.value + 8 * int(tgoff[t]), Ut * 32, ctypes.c_double).reshape(Ut, 32)
+            g_blk[:] = 0
+            for lane in range(32):
+                i = 32 * t + lane
+                if i >= n_states:
+                    break
+                r = D[i]
+                U = int(r["U"])
+                assert U <= Ut
+                c, l, gsrc = self._expand_state(r, d, W, stag, smin, smax, orders)
+                cell_blk[:U, :, lane] = c.T
+                for k in range(d):
+                    lam_blk[k][:U, :, lane] = l[k].T
+                if g_per_w:
+                    g_blk[:U, :, lane] = gsrc.T
+                else:
+                    g_blk[:U, lane] = gsrc[0]
         self.launches += 1
         return 0
 
@@ -111,42 +170,75 @@ class FakeLib(object):
         items = np.frombuffer((ctypes.c_uint8 * (T.n_items * _cabi.ITEM_DTYPE.itemsize))
                               .from_address(T.items), dtype=_cabi.ITEM_DTYPE)
         p = _arr(T.p, T.W, ctypes.c_double) if T.expect else np.ones(T.W)
-        pv = _arr(part_val, T.n_items, ctypes.c_double)
-        pi = _arr(part_idx, T.n_items, ctypes.c_int32)
+        tiled = T.layout == _cabi.LAYOUT_STATE_MINOR
+        width = 32 if tiled else 1
+        pv = _arr(part_val, T.n_items * width, ctypes.c_double)
+        pi = _arr(part_idx, T.n_items * width, ctypes.c_int32)
+        Us = _arr(T.U, T.n_states, ctypes.c_int32)
         W = T.W
-        for n_it, it in enumerate(items):
-            Upad, cnt = int(it["Upad"]), int(it["u_count"])
-            acc = np.zeros(cnt)
-            for w in range(W):
-                off = int(it["entry_base"]) + w * Upad
-                c = _arr(T.cell + 4 * off, cnt, ctypes.c_int32).astype(np.int64)
-                lam = [_arr(T.lam + 8 * (k * T.lam_plane + off), cnt, ctypes.c_double) for k in range(d)]
-                vals = None
-                # nested lerp, last axis innermost
-                def rec(base, k):
-                    if k == d:
-                        return J[base]
-                    a = rec(base, k + 1)
-                    b = rec(base + strides[k], k + 1)
-                    return (1 - lam[k]) * a + lam[k] * b
-                v = rec(c, 0)
-                if T.g_per_w:
-                    gv = _arr(T.g + 8 * (int(it["g_base"]) + w * Upad), cnt, ctypes.c_double)
-                else:
-                    gv = _arr(T.g + 8 * int(it["g_base"]), cnt, ctypes.c_double)
-                jg = gv + v
-                acc = acc + jg * p[w] if T.expect else jg
+
+        def lerp(c, lam):
+            def rec(base, k):
+                if k == d:
+                    return J[base]
+                a = rec(base, k + 1)
+                b = rec(base + strides[k], k + 1)
+                return (1 - lam[k]) * a + lam[k] * b
+            return rec(c, 0)
+
+        def first_min(acc):
             nan = np.isnan(acc)
-            j = int(np.argmax(nan)) if nan.any() else int(np.argmin(acc))   # first NaN, else first min
-            pv[n_it], pi[n_it] = acc[j], int(it["u_begin"]) + j
-        ib = _arr(T.item_begin, T.n_states + 1, ctypes.c_int64)
+            return int(np.argmax(nan)) if nan.any() else int(np.argmin(acc))
+
+        for n_it, it in enumerate(items):
+            cnt, ub = int(it["u_count"]), int(it["u_begin"])
+            if not tiled:
+                Upad = int(it["Upad"])
+                acc = np.zeros(cnt)
+                for w in range(W):
+                    off = int(it["entry_base"]) + w * Upad
+                    c = _arr(T.cell + 4 * off, cnt, ctypes.c_int32).astype(np.int64)
+                    lam = [_arr(T.lam + 8 * (k * T.lam_plane + off), cnt, ctypes.c_double) for k in range(d)]
+                    if T.g_per_w:
+                        gv = _arr(T.g + 8 * (int(it["g_base"]) + w * Upad), cnt, ctypes.c_double)
+                    else:
+                        gv = _arr(T.g + 8 * int(it["g_base"]), cnt, ctypes.c_double)
+                    jg = gv + lerp(c, lam)
+                    acc = acc + jg * p[w] if T.expect else jg
+                j = first_min(acc)
+                pv[n_it], pi[n_it] = acc[j], ub + j
+            else:
+                eb = int(it["entry_base"])
+                C = _arr(T.cell + 4 * eb, cnt * W * 32, ctypes.c_int32).astype(np.int64).reshape(cnt, W, 32)
+                L = [_arr(T.lam + 8 * (k * T.lam_plane + eb), cnt * W * 32, ctypes.c_double).reshape(cnt, W, 32)
+                     for k in range(d)]
+                if T.g_per_w:
+                    Gv = _arr(T.g + 8 * int(it["g_base"]), cnt * W * 32, ctypes.c_double).reshape(cnt, W, 32)
+                else:
+                    Gv = _arr(T.g + 8 * int(it["g_base"]), cnt * 32, ctypes.c_double).reshape(cnt, 1, 32)
+                acc = np.zeros((cnt, 32))
+                for w in range(W):
+                    jg = Gv[:, w if T.g_per_w else 0, :] + lerp(C[:, w, :], [l[:, w, :] for l in L])
+                    acc = acc + jg * p[w] if T.expect else jg
+                for lane in range(32):
+                    s_i = int(it["state"]) * 32 + lane
+                    n_ok = max(0, min(cnt, (int(Us[s_i]) if s_i < T.n_states else 0) - ub))
+                    if n_ok == 0:
+                        pv[n_it * 32 + lane], pi[n_it * 32 + lane] = np.inf, 2 ** 31 - 1
+                    else:
+                        j = first_min(acc[:n_ok, lane])
+                        pv[n_it * 32 + lane], pi[n_it * 32 + lane] = acc[j, lane], ub + j
+        n_units = (T.n_states + 31) // 32 if tiled else T.n_states
+        ib = _arr(T.item_begin, n_units + 1, ctypes.c_int64)
         Jo = _arr(J_out, T.n_states, ctypes.c_double)
         ao = _arr(argmin_out, T.n_states, ctypes.c_int32)
         for i in range(T.n_states):
             bv, bi = np.inf, 2 ** 31 - 1
-            for k in range(ib[i], ib[i + 1]):
-                if _better(pv[k], int(pi[k]), bv, bi):
-                    bv, bi = pv[k], int(pi[k])
+            unit, lane = (i // 32, i % 32) if tiled else (i, 0)
+            for k in range(ib[unit], ib[unit + 1]):
+                kk = k * width + lane
+                if _better(pv[kk], int(pi[kk]), bv, bi):
+                    bv, bi = pv[kk], int(pi[kk])
             Jo[i], ao[i] = bv, bi
         self.launches += 2
         return 0

@@ -28,25 +28,35 @@ gpu = pytest.mark.gpu
 
 class _Api(object):
     """`api` for the workload factories: the product's classes, with the solver
-    bound either to the CUDA library or to the numpy model of the C ABI."""
+    bound either to the CUDA library or to the numpy model of the C ABI, and
+    pinned to one table layout."""
 
-    def __init__(self, pkg, backend):
+    def __init__(self, pkg, backend, layout="auto", tabulate="auto"):
         self.pkg = pkg
         self.backend = backend
+        self.layout = layout
+        self.tabulate = tabulate
         self.SysDescription = pkg.SysDescription
 
     def DPSolver(self, sys, **kw):
         if self.backend == "model":
             from fake_lib import FakeLib
             kw["_test_lib"] = FakeLib()
-        return self.pkg.DPSolver(sys, **kw)
+        sv = self.pkg.DPSolver(sys, **kw)
+        sv.table_layout = self.layout
+        sv.tabulate = self.tabulate
+        return sv
 
 
-@pytest.fixture(scope="module", params=[pytest.param("model"), pytest.param("cuda", marks=gpu)])
+@pytest.fixture(scope="module", params=[
+    pytest.param(("model", "control_minor"), id="model-A"),
+    pytest.param(("model", "state_minor"), id="model-B"),
+    pytest.param(("cuda", "control_minor"), marks=gpu, id="cuda-A"),
+    pytest.param(("cuda", "state_minor"), marks=gpu, id="cuda-B")])
 def api(request, product):
-    """host logic is exercised twice: against the numpy model of the C ABI
-    (CPU suite) and against the real CUDA library (GPU suite)"""
-    return _Api(product, request.param)
+    """host logic is exercised against the numpy model of the C ABI (CPU suite)
+    and against the real CUDA library (GPU suite), for both table layouts"""
+    return _Api(product, *request.param)
 
 
 @pytest.fixture(scope="module")
@@ -394,10 +404,8 @@ def test_toy_systems_vs_port(api, port, d, cost_kind):
     both_nan = np.isnan(J) & np.isnan(Jo)
     assert np.array_equal(np.isnan(J), np.isnan(Jo))
     assert rel_err(np.where(both_nan, 0, J), np.where(both_nan, 0, Jo)) <= J_RTOL
-    if cost_kind == "w":
-        assert sv.last_tables.g_per_w == 1
-    else:
-        assert sv.last_tables.g_per_w == 0
+    assert sv.last_tables.g_per_w == (1 if cost_kind == "w" else 0)
+    assert sv.last_tables.tiled == (sv.table_layout == "state_minor")
     # policy evaluation of the greedy policy, with and without relative DP
     if cost_kind != "nan":
         Je = sv.eval_policy(pol, 7, report_time=False)
@@ -448,3 +456,75 @@ def test_abi_rejects_bad_arguments(eng):
     assert rc == -1 and b"grid.d" in eng.lib.sdp_last_error()
     with pytest.raises(_cabi.SdpLibraryError):
         _cabi.check(rc, "sdp_cell_setup")
+
+
+# ---------------------------------------------------------------------------
+# host tabulation: one call per chunk of states == one call per state
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
+@pytest.mark.parametrize("layout", ["control_minor", "state_minor"])
+@pytest.mark.parametrize("which", ["storage_ar1", "searev", "toy_w", "curtail"])
+def test_batched_tabulation_is_bit_identical(product, backend, layout, which):
+    from stodynprog_b200 import workloads as wl
+    tabs = []
+    for mode in ("per_state", "batched"):
+        api = _Api(product, backend, layout, mode)
+        if which == "storage_ar1":
+            sv = wl.storage_ar1(api, n_E=9, n_P=11, steps=(0.01, 0.1)).solver
+        elif which == "searev":
+            sv = _searev_small(api).solver
+        elif which == "toy_w":
+            sv = _toy(api, 3, "w")
+        else:
+            sv = _two_control_system(api)
+        T = sv.sweep_tables()
+        assert T.tabulate_mode == mode
+        tabs.append(T)
+    a, b = tabs
+    assert a.n_entries == b.n_entries and a.g_per_w == b.g_per_w
+    n = a.n_entries
+    assert np.array_equal(a.cell[:n].cpu().numpy(), b.cell[:n].cpu().numpy())
+    la = a.lam.cpu().numpy().view(np.int64).reshape(a.d, -1)[:, :n]
+    lb = b.lam.cpu().numpy().view(np.int64).reshape(b.d, -1)[:, :n]
+    assert np.array_equal(la, lb)
+    assert np.array_equal(a.g.cpu().numpy().view(np.int64), b.g.cpu().numpy().view(np.int64))
+
+
+def _two_control_system(api, **kw):
+    """storage + AR(1) with curtailment enabled: the second control's grid
+    depends on the state (U2 = [0, max(P_mis, 0)]), so the control product is
+    ragged in both axes (notebook cell 5 with curt_activ = True)."""
+    import scipy.stats as stats
+    E_rated, P_rated, p_corr = 10., 4., 0.8
+
+    def dyn_sto(E, P_mis, P_sto, P_cur, innov):
+        return (E + P_sto, p_corr * P_mis + innov)
+
+    def admissible_controls(E, P_mis):
+        return ((np.max((-E, -P_rated)), np.min((E_rated - E, P_rated))), (0, np.max((P_mis, 0))))
+
+    def cost(E, P_mis, P_sto, P_cur, innov):
+        P_dev = P_mis - P_cur - P_sto
+        return P_dev ** 2 + 0.3 * P_cur
+
+    sys = api.SysDescription((2, 2, 1), name='storage with curtailment')
+    sys.dyn = dyn_sto
+    sys.control_box = admissible_controls
+    sys.cost = cost
+    sys.perturb_laws = [stats.norm(0, 0.4)]
+    sv = api.DPSolver(sys, **kw)
+    sv.discretize_state(0, E_rated, 7, -4, 4, 9)
+    sv.discretize_perturb(-1.2, 1.2, 5)
+    sv.control_steps = (0.5, 0.25)
+    return sv
+
+
+def test_two_controls_ragged_product(api, port):
+    sv, so = _two_control_system(api), _two_control_system(port)
+    J0 = np.random.default_rng(11).standard_normal(sv._state_grid_shape)
+    J, pol = sv.value_iteration(J0, report_time=False)
+    Jo, polo = so.value_iteration(J0)
+    assert sv.last_tables.host_full.npts[:, 1].min() == 1
+    assert sv.last_tables.host_full.npts[:, 1].max() > 5
+    assert np.array_equal(pol, polo)
+    assert rel_err(J, Jo) <= J_RTOL
