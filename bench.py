@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py - Bellman backups/s of the sweep hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one full Bellman sweep (value_iteration's hot path) over the
+configured state grid.  Workload: BASELINE.json configs[4], the storage-AR1
+problem scaled to 2000 x 500 states x <=256 controls x 9 perturbation nodes
+(1 848 240 000 admissible backups per sweep, 38.6 GB of tables), sharded over
+the N GPUs (strong scaling: total work fixed).  One JSON line on stdout.
+
+  value      whole-job backups/s, tables and J resident in HBM, CUDA events on
+             the launching stream, barrier + synchronize on both sides, max over ranks
+  e2e        the same metric through the public API with HOST arrays:
+             DPSolver.value_iteration(J_host) -> (J_host, pol_host), i.e. H2D of J,
+             sweep, D2H of J and argmin, host mapping argmin -> control values
+  roofline   HBM: algorithmic bytes (4 + 8d + 8/W per backup) of the
+             streaming kernel / its own CUDA-event duration, vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's numpy/Cython loop, 1 core (the
+             reference is single-threaded), on a bounded random sample of states
+
+--impl reference times the reference's CPU path (oracle port; its interpolation
+runs through the reference's own compiled Cython routine when oracle/_ref is
+present) on bounded samples of the same workload and prints the same line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "bellman_backups_per_sec"
+UNIT = "backups/s"
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.lines = []
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_problem(api, args, **solver_kw):
+    from stodynprog_b200 import workloads as wl
+    if args.workload == "ar1":
+        return wl.storage_ar1(api, **solver_kw), "howto storage-AR1 41x61 (BASELINE configs[2])"
+    prob = wl.storage_ar1_large(api, n_E=args.n_E, n_P=args.n_P, **solver_kw)
+    name = "synthetic storage-AR1 %dx%d states x <=256 controls x 9 nodes (BASELINE configs[4])" \
+        % (args.n_E, args.n_P)
+    return prob, name
+
+
+def cpu_port_sample(args, n_states, seed=0, interp="c", J=None):
+    """time the oracle port's per-state backup (what the reference's value_iteration
+    does for each state, stodynprog.py:511-515) on `n_states` random states of the
+    workload.  Returns (backups, seconds)."""
+    from oracle.ref_port import port_api
+    prob, _ = make_problem(port_api(interp), args)
+    sv = prob.solver
+    dims = sv._state_grid_shape
+    rng = np.random.default_rng(seed)
+    if J is None:
+        J = np.random.default_rng(0).standard_normal(dims)
+    J_interp = sv.interp_on_state(J)
+    n_grid = int(np.prod(dims))
+    picks = rng.choice(n_grid, size=min(n_states, n_grid), replace=False)
+    W = len(sv.perturb_grid[0])
+    backups = 0
+    t0 = time.perf_counter()
+    for flat in picks:
+        idx = np.unravel_index(flat, dims)
+        x_k = tuple(g[i] for g, i in zip(sv.state_grid, idx))
+        _, _, _, Jall = sv.value_at_state(x_k, J_interp, None, True)
+        backups += Jall.size * W
+    return backups, time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path, bounded samples, rank 0 only"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import build as ob
+    ob.build()
+    interp = "c"
+    kind = "port"
+    try:
+        from oracle import build_ref
+        if build_ref.build() is not None:
+            from oracle.ref_loader import load_reference_cython
+            if load_reference_cython() is not None:
+                interp = "ref"
+    except Exception:
+        pass
+    _, name = make_problem(__import__("oracle.ref_port", fromlist=["port_api"]).port_api(interp), args)
+    n_sample = args.cpu_sample
+    for _ in range(args.warmup):
+        cpu_port_sample(args, max(n_sample // 10, 10), seed=99, interp=interp)
+    tot_b, tot_t = 0, 0.0
+    for k in range(args.steps):
+        b, t = cpu_port_sample(args, n_sample, seed=k, interp=interp)
+        tot_b += b
+        tot_t += t
+    value = tot_b / tot_t
+    sample = ("%d random states per step (seeded) of the %s grid, per-state numpy loop of the "
+              "reference restated in oracle/ref_port.py; interpolation through %s"
+              % (n_sample, "x".join(str(n) for n in (args.n_E, args.n_P)),
+                 "the reference's own compiled Cython routine (oracle/_ref)" if interp == "ref"
+                 else "the C restatement (oracle/sdp_oracle.c)"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import stodynprog_b200 as sdp
+    from stodynprog_b200 import _cabi
+    from stodynprog_b200 import build as product_build
+    if rank == 0:
+        product_build.build()
+    if world > 1:
+        dist.barrier()
+
+    prob, name = make_problem(sdp, args)
+    sv = prob.solver
+    if args.layout != "auto":
+        sv.table_layout = args.layout
+    if args.item_chunk:
+        sv._item_chunk = args.item_chunk
+    eng = sv.engine
+    t0 = time.perf_counter()
+    T = sv.sweep_tables()
+    setup_s = time.perf_counter() - t0
+    dims = sv._state_grid_shape
+    n_grid = int(np.prod(dims))
+
+    J_host = np.random.default_rng(0).standard_normal(dims)
+    J_prev = eng.to_device(J_host.reshape(-1))
+    J_new = torch.empty_like(J_prev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.sweep(T, J_prev, J_new)
+        J_prev, J_new = J_new, J_prev
+
+    K = args.steps
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _cabi.launch_count()
+    barrier()
+    start.record()
+    for k in range(K):
+        eng.sweep(T, J_prev, J_new, events=kev[k])
+        J_prev, J_new = J_new, J_prev
+    end.record()
+    barrier()
+    launches = _cabi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = start.elapsed_time(end)
+    k1_ms = np.array([a.elapsed_time(b) for a, b in kev])
+    t = torch.tensor([ms_total, float(np.mean(k1_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max, k1_ms_max = float(t[0]), float(t[1])
+    total_backups = T.n_backups_total
+    value = total_backups * K / (ms_total_max * 1e-3)
+
+    # roofline of the streaming kernel on this rank's slab
+    peak, peak_src = read_peaks()
+    b_alg = T.algorithmic_bytes_per_backup
+    k1_mean = float(np.mean(k1_ms))
+    achieved = T.n_backups_local * b_alg / (k1_mean * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "k_sweep_tiled" if T.tiled else "k_sweep",
+                "kernel_ms": k1_mean, "kernel_share_of_step": k1_mean * K / ms_total,
+                "algorithmic_bytes_per_backup": b_alg,
+                "algorithmic_bytes_per_launch": T.n_backups_local * b_alg,
+                "table_bytes_resident": T.device_bytes,
+                "padding_fill": T.n_backups_local / max(T.n_entries, 1)}
+
+    # end-to-end through the public API, host arrays in and out
+    n_e2e = max(3, min(K, 10))
+    J_h = J_prev.cpu().numpy().reshape(dims)
+    for _ in range(2):
+        J_h, pol_h = sv.value_iteration(J_h, report_time=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        J_h, pol_h = sv.value_iteration(J_h, report_time=False)
+    torch.cuda.synchronize()
+    e2e_local = time.perf_counter() - t0
+    te = torch.tensor([e2e_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    e2e = {"value": total_backups * n_e2e / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": 8 * n_grid, "d2h_bytes_per_step": 12 * n_grid,
+           "steps": n_e2e, "ms_per_step": 1e3 * e2e_s / n_e2e,
+           "api": "DPSolver.value_iteration(J_host) -> (J_host, pol_host)"}
+
+    setup = torch.tensor([setup_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(setup, op=dist.ReduceOp.MAX)
+
+    extra = None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import build as ob
+        ob.build()
+        b, tcpu = cpu_port_sample(args, args.cpu_sample, seed=0)
+        cpu = {"value": b / tcpu, "unit": UNIT, "cores": 1, "kind": "port",
+               "host_cpus": os.cpu_count(), "seconds": tcpu,
+               "sample": "%d random states (seeded) of the same grid, %d backups, per-state "
+                         "numpy loop of the reference restated in oracle/ref_port.py (the "
+                         "reference is single-threaded: prange compiled without OpenMP)"
+                         % (args.cpu_sample, b)}
+    if rank == 0 and world == 1 and args.workload == "large" and not args.no_extra:
+        extra = measure_config3(sdp, peak)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": ms_total_max / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "states": n_grid, "backups_per_sweep": total_backups,
+                       "state_dims": list(dims), "perturbation_nodes": T.W,
+                       "table_layout": "state_minor" if T.tiled else "control_minor",
+                       "tabulate_mode": T.tabulate_mode, "item_chunk": eng.item_chunk,
+                       "parallelism": "state slabs x%d, all-gather of J per sweep" % world,
+                       "l2": "tables streamed once per sweep (%.1f GB per GPU) >> 126 MB L2; "
+                             "no flush needed" % (T.device_bytes / 1e9),
+                       "J_init": "default_rng(0).standard_normal, then fed back sweep to sweep"},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "setup_seconds": float(setup[0]),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if extra is not None:
+            line["storage_ar1_41x61"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_config3(sdp, peak, steps=50, warmup=5):
+    """BASELINE configs[2] (the 41x61 storage-AR1 grid of the notebook, 142 762 509
+    backups per sweep): the grid the north star's 60 % roofline target is quoted on."""
+    import torch
+    from stodynprog_b200 import workloads as wl
+    prob = wl.storage_ar1(sdp)
+    sv = prob.solver
+    eng = sv.engine
+    T = sv.sweep_tables()
+    J_prev = eng.to_device(np.random.default_rng(0).standard_normal(41 * 61))
+    J_new = torch.empty_like(J_prev)
+    for _ in range(warmup):
+        eng.sweep(T, J_prev, J_new)
+        J_prev, J_new = J_new, J_prev
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(steps)]
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for k in range(steps):
+        eng.sweep(T, J_prev, J_new, events=kev[k])
+        J_prev, J_new = J_new, J_prev
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    k1 = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    b_alg = T.algorithmic_bytes_per_backup
+    ach = T.n_backups_local * b_alg / (k1 * 1e-3) / 1e9
+    return {"workload": "howto storage-AR1 41x61 x 4001..8001 controls x 9 nodes",
+            "backups_per_sweep": T.n_backups_total, "ms_per_step": ms,
+            "value": T.n_backups_total / (ms * 1e-3), "unit": UNIT,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "kernel": "k_sweep", "kernel_ms": k1,
+                         "algorithmic_bytes_per_backup": b_alg},
+            "table_layout": "state_minor" if T.tiled else "control_minor"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="large", choices=["large", "ar1"])
+    ap.add_argument("--n-E", dest="n_E", type=int, default=2000)
+    ap.add_argument("--n-P", dest="n_P", type=int, default=500)
+    ap.add_argument("--layout", default="auto", choices=["auto", "control_minor", "state_minor"])
+    ap.add_argument("--item-chunk", dest="item_chunk", type=int, default=0)
+    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=None,
+                    help="states per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.cpu_sample is None:
+        # ~200 us per state for the 2000x500 grid (<=256 controls); ~1.4 ms for the 41x61 grid
+        args.cpu_sample = (60000 if args.impl == "ours" else 8000) if args.workload == "large" else 2501
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

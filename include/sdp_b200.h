@@ -170,6 +170,13 @@ int sdp_build_tables_tiled(const SdpGrid* grid, int32_t W, int32_t g_per_w, int6
 int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
               double* part_val, int32_t* part_idx, double* J_out, int32_t* argmin_out,
               void* stream);
+/* The two launches of sdp_sweep, separately (so that a caller can bracket the
+ * streaming kernel alone with events): per-item partial minima, then the
+ * per-state combine. */
+int sdp_sweep_partials(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
+                       double* part_val, int32_t* part_idx, void* stream);
+int sdp_sweep_finalize(const SdpTables* tab, const double* part_val, const int32_t* part_idx,
+                       double* J_out, int32_t* argmin_out, void* stream);
 
 /* K1' - fixed-policy backups (policy evaluation), `n_iter` iterations.
  * Replaces the body of DPSolver.eval_policy (stodynprog.py:743-763).

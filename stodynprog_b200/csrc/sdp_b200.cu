@@ -645,37 +645,53 @@ static int launch_sweep(const GridT<double>& G, const SdpTables& T, const double
     return SDP_OK;
 }
 
-extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
-                         double* part_val, int32_t* part_idx, double* J_out, int32_t* argmin_out,
-                         void* stream) {
+static int check_tables(const SdpTables& T, const char* who) {
+    if (T.W < 1 || T.W > 4096 || T.n_states < 0 || T.n_items < 0)
+        return fail(SDP_EINVAL, "%s: bad sizes", who);
+    if (T.n_states == 0) return SDP_OK;
+    if (!T.cell || !T.lam || !T.g || !T.items || !T.item_begin || (T.expect && !T.p))
+        return fail(SDP_EINVAL, "%s: NULL pointer in tables", who);
+    if ((T.lam_plane & 3) || ((uintptr_t)T.cell & 15) || ((uintptr_t)T.lam & 15) || ((uintptr_t)T.g & 15))
+        return fail(SDP_EINVAL, "%s: tables must be 16-byte aligned, lam_plane % 4 == 0", who);
+    if (T.layout != SDP_LAYOUT_CONTROL_MINOR && T.layout != SDP_LAYOUT_STATE_MINOR)
+        return fail(SDP_EINVAL, "%s: unknown table layout", who);
+    if (T.layout == SDP_LAYOUT_STATE_MINOR && !T.U)
+        return fail(SDP_EINVAL, "%s: layout B needs the per-state control counts", who);
+    if (T.n_items / 8 + 1 > 0x7fffffffLL) return fail(SDP_EINVAL, "%s: too many items", who);
+    return SDP_OK;
+}
+
+extern "C" int sdp_sweep_partials(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
+                                  double* part_val, int32_t* part_idx, void* stream) {
     GridT<double> G;
     int rc = make_grid<double>(grid, &G, nullptr);
     if (rc) return rc;
     if (!tab) return fail(SDP_EINVAL, "%s", "sdp_sweep: tables is NULL");
     const SdpTables& T = *tab;
-    if (T.W < 1 || T.W > 4096 || T.n_states < 0 || T.n_items < 0)
-        return fail(SDP_EINVAL, "%s", "sdp_sweep: bad sizes");
-    if (T.n_states == 0) return SDP_OK;
-    if (!T.cell || !T.lam || !T.g || !T.items || !T.item_begin || !J_prev || !part_val || !part_idx ||
-        !J_out || !argmin_out || (T.expect && !T.p))
-        return fail(SDP_EINVAL, "%s", "sdp_sweep: NULL pointer");
-    if ((T.lam_plane & 3) || ((uintptr_t)T.cell & 15) || ((uintptr_t)T.lam & 15) || ((uintptr_t)T.g & 15))
-        return fail(SDP_EINVAL, "%s", "sdp_sweep: tables must be 16-byte aligned, lam_plane % 4 == 0");
-    if (T.layout != SDP_LAYOUT_CONTROL_MINOR && T.layout != SDP_LAYOUT_STATE_MINOR)
-        return fail(SDP_EINVAL, "%s", "sdp_sweep: unknown table layout");
-    if (T.layout == SDP_LAYOUT_STATE_MINOR && !T.U)
-        return fail(SDP_EINVAL, "%s", "sdp_sweep: layout B needs the per-state control counts");
+    rc = check_tables(T, "sdp_sweep");
+    if (rc) return rc;
+    if (T.n_states == 0 || T.n_items == 0) return SDP_OK;
+    if (!J_prev || !part_val || !part_idx) return fail(SDP_EINVAL, "%s", "sdp_sweep: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    if (T.n_items > 0) {
-        if (T.n_items / 8 + 1 > 0x7fffffffLL) return fail(SDP_EINVAL, "%s", "sdp_sweep: too many items");
-        switch (grid->d) {
-            case 1: rc = launch_sweep<1>(G, T, J_prev, part_val, part_idx, st); break;
-            case 2: rc = launch_sweep<2>(G, T, J_prev, part_val, part_idx, st); break;
-            case 3: rc = launch_sweep<3>(G, T, J_prev, part_val, part_idx, st); break;
-            default: rc = launch_sweep<4>(G, T, J_prev, part_val, part_idx, st); break;
-        }
-        if (rc) return rc;
+    switch (grid->d) {
+        case 1: return launch_sweep<1>(G, T, J_prev, part_val, part_idx, st);
+        case 2: return launch_sweep<2>(G, T, J_prev, part_val, part_idx, st);
+        case 3: return launch_sweep<3>(G, T, J_prev, part_val, part_idx, st);
+        default: return launch_sweep<4>(G, T, J_prev, part_val, part_idx, st);
     }
+}
+
+extern "C" int sdp_sweep_finalize(const SdpTables* tab, const double* part_val,
+                                  const int32_t* part_idx, double* J_out, int32_t* argmin_out,
+                                  void* stream) {
+    if (!tab) return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize: tables is NULL");
+    const SdpTables& T = *tab;
+    int rc = check_tables(T, "sdp_sweep_finalize");
+    if (rc) return rc;
+    if (T.n_states == 0) return SDP_OK;
+    if (!part_val || !part_idx || !J_out || !argmin_out)
+        return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
     unsigned blocks = (unsigned)((T.n_states + 255) / 256);
     if (T.layout == SDP_LAYOUT_STATE_MINOR)
         k_sweep_finalize_tiled<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
@@ -683,6 +699,14 @@ extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double
         k_sweep_finalize<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
+}
+
+extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
+                         double* part_val, int32_t* part_idx, double* J_out, int32_t* argmin_out,
+                         void* stream) {
+    int rc = sdp_sweep_partials(grid, tab, J_prev, part_val, part_idx, stream);
+    if (rc) return rc;
+    return sdp_sweep_finalize(tab, part_val, part_idx, J_out, argmin_out, stream);
 }
 
 // ---------------------------------------------------------------------------

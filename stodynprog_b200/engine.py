@@ -467,19 +467,34 @@ class Engine(object):
         T.setup_seconds = time.perf_counter() - t0
         return T
 
-    def sweep_local(self, T, J_prev):
+    def sweep_local(self, T, J_prev, events=None):
         """Enqueue K1 on this rank's slab.  J_prev: device fp64 [n_grid].
-        Results land in T.J_out / T.argmin (slab-local)."""
-        rc = self.lib.sdp_sweep(ctypes.byref(T.grid), ctypes.byref(T.c_tables), self._ptr(J_prev),
-                                self._ptr(T.part_val), self._ptr(T.part_idx),
-                                self._ptr(T.J_out), self._ptr(T.argmin), self.stream)
-        _cabi.check(rc, "sdp_sweep")
+        Results land in T.J_out / T.argmin (slab-local).  `events`: optional
+        (start, end) torch.cuda.Event pair recorded around the streaming kernel
+        alone (bench roofline)."""
+        if events is None:
+            rc = self.lib.sdp_sweep(ctypes.byref(T.grid), ctypes.byref(T.c_tables), self._ptr(J_prev),
+                                    self._ptr(T.part_val), self._ptr(T.part_idx),
+                                    self._ptr(T.J_out), self._ptr(T.argmin), self.stream)
+            _cabi.check(rc, "sdp_sweep")
+            return
+        events[0].record()
+        rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
+                                         self._ptr(J_prev), self._ptr(T.part_val),
+                                         self._ptr(T.part_idx), self.stream)
+        _cabi.check(rc, "sdp_sweep_partials")
+        events[1].record()
+        rc = self.lib.sdp_sweep_finalize(ctypes.byref(T.c_tables), self._ptr(T.part_val),
+                                         self._ptr(T.part_idx), self._ptr(T.J_out),
+                                         self._ptr(T.argmin), self.stream)
+        _cabi.check(rc, "sdp_sweep_finalize")
 
-    def sweep(self, T, J_prev, J_new, rel_ref_index=None, ref_out=None, resid_out=None):
+    def sweep(self, T, J_prev, J_new, rel_ref_index=None, ref_out=None, resid_out=None,
+              events=None):
         """One full Bellman sweep: K1 on the slab, all-gather of the J slab into
         J_new (device fp64 [n_grid]), optional relative-DP shift and optional
         sup-norm residual max|J_new - J_prev| (all-reduced)."""
-        self.sweep_local(T, J_prev)
+        self.sweep_local(T, J_prev, events)
         n = T.n_states
         sb = T.state_begin
         if self.coll.world == 1:

@@ -243,6 +243,11 @@ class FakeLib(object):
         self.launches += 2
         return 0
 
+    def sdp_sweep_partials(self, *a):
+        raise NotImplementedError("the model implements sdp_sweep as a whole")
+
+    sdp_sweep_finalize = sdp_sweep_partials
+
     def sdp_policy_eval(self, gref, W, g_per_w, p, cell, lam, lam_plane, g, n_states, state_begin,
                         n_grid, J_a, J_b, n_iter, rel_dp, ref_index, hist, stream):
         d, smin, smax, orders = _grid(gref)
