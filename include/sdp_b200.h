@@ -133,6 +133,12 @@ const char* sdp_last_error(void);
 /* Number of kernels launched by this library since load (for bench accounting). */
 int64_t sdp_launch_count(void);
 
+/* Launch tuning (developer knob; defaults are read from SDP_* environment
+ * variables): "upl" (2|4), "wb" (1|2|3|5), "tma" (0|1), "tma_rows" (4|8),
+ * "tma_stages" (2..16), "tma_warps" (1..16).  Not thread-safe against
+ * concurrent launches. */
+int sdp_set_option(const char* name, int value);
+
 /* K0a - cell search on explicit points.
  * Replaces the cell-search half of multilinear_interpolation_{1..4}d
  * (multilinear_cython.pyx:72-79, :117-131, :177-193, :257-278).
@@ -194,6 +200,15 @@ int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, const doubl
                     const double* g, int64_t n_states, int64_t state_begin, int64_t n_grid,
                     double* J_a, double* J_b, int32_t n_iter, int32_t rel_dp,
                     int64_t ref_index, double* J_ref_hist, void* stream);
+
+/* K3 - argmin index -> control values, the `u_grids[i].flatten()[ind_opt[i]]` of
+ * stodynprog.py:686-689 for every state at once.  lo/hi: device [n][nc] box
+ * bounds, npts: device [n][nc] grid sizes (what control_grids computed,
+ * stodynprog.py:445-460), argmin: device [n] flat C-order index.
+ * pol: device [n][nc], bit-identical to np.linspace(lo, hi, npts)[idx]
+ * (or the centre point (lo+hi)/2 when npts == 1). */
+int sdp_policy_values(int64_t n, int32_t nc, const double* lo, const double* hi,
+                      const int32_t* npts, const int32_t* argmin, double* pol, void* stream);
 
 /* Relative-DP normalisation: ref_out[0] = J[ref_index]; J[i] -= ref_out[0]
  * (stodynprog.py:523-525, :760-762).  J: device [n]. */

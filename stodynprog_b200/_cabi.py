@@ -77,6 +77,7 @@ SIGNATURES = {
     "sdp_version": (ctypes.c_int, []),
     "sdp_last_error": (ctypes.c_char_p, []),
     "sdp_launch_count": (_i64, []),
+    "sdp_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "sdp_cell_setup": (ctypes.c_int, [_gp, _i64, _vp, _vp, _vp, _vp]),
     "sdp_build_tables": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp,
                                         _i32, _vp]),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "sdp_sweep_finalize": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp]),
     "sdp_policy_eval": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
                                        _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
+    "sdp_policy_values": (ctypes.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdp_rel_shift": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "sdp_supnorm_diff": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "sdp_interp": (ctypes.c_int, [_gp, _i64, _vp, _i64, _vp, _vp, _vp]),

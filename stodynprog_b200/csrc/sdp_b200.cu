@@ -585,6 +585,149 @@ k_sweep_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
     part_idx[item_id * 32 + lane] = best_i;
 }
 
+// ---------------------------------------------------------------------------
+// Layout B, TMA-fed variant.  The table region of an item (tile x run of
+// controls) is one contiguous run of rows per plane (row = 32 lanes), so each
+// warp streams it through its own shared-memory ring with 1-D bulk async copies
+// (cp.async.bulk, the TMA engine; SASS UBLKCP) completing on mbarriers: the
+// HBM stream never touches the L1/LSU path, which is left to the 2^d-corner
+// gathers of J, and the prefetch depth is set by the ring, not by occupancy.
+// One elected lane re-arms a slot as soon as the warp has pulled its rows
+// into registers.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int D, int R>
+__global__ void __launch_bounds__(512)
+k_sweep_tiled_tma(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+                  double* __restrict__ part_val, int32_t* __restrict__ part_idx, int S) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = T.W;
+    const int nw = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int planes = D + (T.g_per_w ? 1 : 0);
+    const int stage_bytes = R * 128 + planes * R * 256;
+    const int p_bytes = (W * 8 + 127) & ~127;
+
+    double* p_sh = reinterpret_cast<double*>(smem_raw);
+    for (int i = threadIdx.x; i < W; i += blockDim.x) p_sh[i] = T.expect ? T.p[i] : 1.0;
+    unsigned char* ring = smem_raw + p_bytes + (size_t)warp * S * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + p_bytes + (size_t)nw * S * stage_bytes) + warp * S;
+    if (lane == 0) {
+        for (int i = 0; i < S; ++i) mbar_init(smem_u32(bars + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t item_id = (int64_t)blockIdx.x * nw + warp;
+    if (item_id >= T.n_items) return;
+    const SdpItem it = T.items[item_id];
+    const int64_t state = (int64_t)it.state * 32 + lane;
+    const int Us = (state < T.n_states) ? T.U[state] : 0;
+    const int n_rows = it.u_count * W;
+    const int n_stages = (n_rows + R - 1) / R;
+    const int32_t* gcell = T.cell + it.entry_base;
+    const double* glam = T.lam + it.entry_base;
+    const double* ggw = T.g + it.g_base;      // used as a streamed plane when g_per_w
+
+    auto issue = [&](int s) {
+        const int slot = s % S;
+        const int rows = min(R, n_rows - s * R);
+        const uint32_t bar = smem_u32(bars + slot);
+        unsigned char* dst = ring + (size_t)slot * stage_bytes;
+        mbar_expect_tx(bar, (uint32_t)(rows * (128 + planes * 256)));
+        const int64_t e0 = (int64_t)s * R * 32;
+        bulk_g2s(smem_u32(dst), gcell + e0, (uint32_t)(rows * 128), bar);
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            bulk_g2s(smem_u32(dst + R * 128 + k * R * 256), glam + (int64_t)k * T.lam_plane + e0,
+                     (uint32_t)(rows * 256), bar);
+        if (T.g_per_w)
+            bulk_g2s(smem_u32(dst + R * 128 + D * R * 256), ggw + e0, (uint32_t)(rows * 256), bar);
+    };
+
+    if (lane == 0) {
+        const int pre = min(S, n_stages);
+        for (int s = 0; s < pre; ++s) issue(s);
+    }
+
+    double best_v = CUDART_INF;
+    int best_i = INT_MAX;
+    double acc = 0.0;
+    int w = 0, uu = 0;
+    const double* __restrict__ gp = T.g + it.g_base + lane;
+    double gv = T.g_per_w ? 0.0 : __ldcs(gp);
+
+    for (int s = 0; s < n_stages; ++s) {
+        const int slot = s % S;
+        const int rows = min(R, n_rows - s * R);
+        mbar_wait(smem_u32(bars + slot), (uint32_t)((s / S) & 1));
+        const unsigned char* st = ring + (size_t)slot * stage_bytes;
+        const int32_t* cs = reinterpret_cast<const int32_t*>(st) + lane;
+        const double* ls = reinterpret_cast<const double*>(st + R * 128) + lane;
+        int c[R];
+        double l[R][D];
+        double gw[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < rows) {
+                c[r] = cs[r * 32];
+#pragma unroll
+                for (int k = 0; k < D; ++k) l[r][k] = ls[k * R * 32 + r * 32];
+                gw[r] = T.g_per_w ? ls[D * R * 32 + r * 32] : 0.0;
+            }
+        }
+        double v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r < rows) v[r] = Lerp<double, D, 0>::eval(Jprev, c[r], G.stride, l[r]);
+        __syncwarp();                       // every lane has pulled its rows out of the slot
+        if (lane == 0 && s + S < n_stages) issue(s + S);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < rows) {
+                const double jg = add_(T.g_per_w ? gw[r] : gv, v[r]);
+                if (T.expect) acc = add_(acc, mul_(jg, p_sh[w]));
+                else acc = jg;
+                if (++w == W) {
+                    const int u = it.u_begin + uu;
+                    if (u < Us && better(acc, u, best_v, best_i)) { best_v = acc; best_i = u; }
+                    w = 0;
+                    acc = 0.0;
+                    ++uu;
+                    if (!T.g_per_w && uu < it.u_count) gv = __ldcs(gp + (int64_t)uu * 32);
+                }
+            }
+        }
+    }
+    part_val[item_id * 32 + lane] = best_v;
+    part_idx[item_id * 32 + lane] = best_i;
+}
+
 __global__ void __launch_bounds__(256)
 k_sweep_finalize_tiled(int64_t n_states, const int64_t* __restrict__ item_begin,
                        const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
@@ -605,23 +748,77 @@ k_sweep_finalize_tiled(int64_t n_states, const int64_t* __restrict__ item_begin,
     argmin_out[i] = bi;
 }
 
-static int sweep_upl() {
-    static int upl = 0;
-    if (upl == 0) {
-        const char* e = getenv("SDP_UPL");
-        upl = (e && atoi(e) == 2) ? 2 : 4;
-    }
-    return upl;
+// ---------------------------------------------------------------------------
+// launch tuning.  Defaults come from the environment (SDP_UPL, SDP_WB,
+// SDP_TILED_IMPL=tma|ldg, SDP_TMA_R, SDP_TMA_S, SDP_TMA_NW) and can be changed
+// at run time through sdp_set_option() (developer tuning sweeps).
+// ---------------------------------------------------------------------------
+struct Tuning {
+    int upl;      // layout A: controls per lane per iteration (2|4)
+    int wb;       // layout B, LDG kernel: perturbation nodes batched (1|2|3|5)
+    int tma;      // layout B: 1 = TMA-fed kernel, 0 = LDG kernel
+    int R, S, NW; // TMA ring: rows per stage (4|8), stages, warps per CTA
+};
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static Tuning& tuning() {
+    static Tuning t = [] {
+        Tuning x;
+        x.upl = env_int("SDP_UPL", 4) == 2 ? 2 : 4;
+        int wb = env_int("SDP_WB", 1);
+        x.wb = (wb == 2 || wb == 3 || wb == 5) ? wb : 1;
+        const char* impl = getenv("SDP_TILED_IMPL");
+        x.tma = (impl && strcmp(impl, "ldg") == 0) ? 0 : 1;
+        x.R = env_int("SDP_TMA_R", 4) == 8 ? 8 : 4;
+        x.S = env_int("SDP_TMA_S", 4);
+        x.NW = env_int("SDP_TMA_NW", 8);
+        return x;
+    }();
+    return t;
+}
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+extern "C" int sdp_set_option(const char* name, int value) {
+    if (!name) return fail(SDP_EINVAL, "%s", "sdp_set_option: NULL name");
+    Tuning& t = tuning();
+    if (!strcmp(name, "upl")) t.upl = (value == 2) ? 2 : 4;
+    else if (!strcmp(name, "wb")) t.wb = (value == 2 || value == 3 || value == 5) ? value : 1;
+    else if (!strcmp(name, "tma")) t.tma = value ? 1 : 0;
+    else if (!strcmp(name, "tma_rows")) t.R = (value == 8) ? 8 : 4;
+    else if (!strcmp(name, "tma_stages")) t.S = value;
+    else if (!strcmp(name, "tma_warps")) t.NW = value;
+    else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
+    return SDP_OK;
 }
 
-static int sweep_wb() {
-    static int wb = 0;
-    if (wb == 0) {
-        const char* e = getenv("SDP_WB");
-        int v = e ? atoi(e) : 3;
-        wb = (v == 1 || v == 2 || v == 3 || v == 5) ? v : 3;
+template <int D, int R>
+static int launch_tiled_tma(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                            double* part_val, int32_t* part_idx, cudaStream_t st, int S, int NW,
+                            bool* launched) {
+    const int planes = D + (T.g_per_w ? 1 : 0);
+    const size_t stage_bytes = (size_t)R * 128 + (size_t)planes * R * 256;
+    const size_t p_bytes = ((size_t)T.W * 8 + 127) & ~(size_t)127;
+    size_t shm = p_bytes + (size_t)NW * S * stage_bytes + (size_t)NW * S * 8;
+    while (shm > 200 * 1024 && NW > 1) {     // shrink the CTA until the rings fit
+        NW >>= 1;
+        shm = p_bytes + (size_t)NW * S * stage_bytes + (size_t)NW * S * 8;
     }
-    return wb;
+    *launched = false;
+    if (shm > 200 * 1024) return SDP_OK;     // does not fit: caller falls back to the LDG kernel
+    static size_t attr_set[5][9] = {};
+    if (attr_set[D][R] < shm) {
+        cudaError_t e = cudaFuncSetAttribute(k_sweep_tiled_tma<D, R>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e != cudaSuccess) return fail(SDP_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set[D][R] = shm;
+    }
+    unsigned blocks = (unsigned)((T.n_items + NW - 1) / NW);
+    k_sweep_tiled_tma<D, R><<<blocks, NW * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, S);
+    *launched = true;
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
 }
 
 template <int D>
@@ -630,14 +827,23 @@ static int launch_sweep(const GridT<double>& G, const SdpTables& T, const double
     const int warps = 8;
     unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
     size_t shm = (size_t)T.W * sizeof(double);
+    const Tuning t = tuning();
     if (T.layout == SDP_LAYOUT_STATE_MINOR) {
-        switch (sweep_wb()) {
-            case 1: k_sweep_tiled<D, 1><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
-            case 2: k_sweep_tiled<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
-            case 5: k_sweep_tiled<D, 5><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
-            default: k_sweep_tiled<D, 3><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+        if (t.tma) {
+            bool launched = false;
+            const int S = clampi(t.S, 2, 16), NW = clampi(t.NW, 1, 16);
+            int rc = (t.R == 8)
+                ? launch_tiled_tma<D, 8>(G, T, Jprev, part_val, part_idx, st, S, NW, &launched)
+                : launch_tiled_tma<D, 4>(G, T, Jprev, part_val, part_idx, st, S, NW, &launched);
+            if (rc || launched) return rc;
         }
-    } else if (sweep_upl() == 2)
+        switch (t.wb) {
+            case 2: k_sweep_tiled<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+            case 3: k_sweep_tiled<D, 3><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+            case 5: k_sweep_tiled<D, 5><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+            default: k_sweep_tiled<D, 1><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+        }
+    } else if (t.upl == 2)
         k_sweep<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
     else
         k_sweep<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
@@ -793,6 +999,53 @@ extern "C" int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, 
         }
         double* t = in; in = out; out = t;
     }
+    return SDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K3: argmin index -> control values  u_grids[c].flatten()[ind_opt[c]]
+// (stodynprog.py:686-689).  The control grid of a state is np.linspace(lo, hi,
+// npts) - element i is i*step + lo with step = (hi-lo)/(npts-1) (true
+// division), (i/div)*delta + lo when step == 0, and exactly `hi` for the last
+// point - or the single centre point (lo+hi)/2 when npts == 1
+// (stodynprog.py:449-458, numpy/_core/function_base.py linspace).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_policy_values(int64_t n, int nc, const double* __restrict__ lo, const double* __restrict__ hi,
+                const int32_t* __restrict__ npts, const int32_t* __restrict__ argmin,
+                double* __restrict__ pol) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long rem = argmin[i];
+    for (int c = nc - 1; c >= 0; --c) {
+        const int m = npts[i * nc + c];
+        const int idx = (int)(rem % m);
+        rem /= m;
+        const double a = lo[i * nc + c], b = hi[i * nc + c];
+        double y;
+        if (m == 1) {
+            y = div_(add_(a, b), 2.0);
+        } else if (idx == m - 1) {
+            y = b;
+        } else {
+            const double div = (double)(m - 1);
+            const double delta = sub_(b, a);
+            const double step = div_(delta, div);
+            if (step == 0.0) y = add_(mul_(div_((double)idx, div), delta), a);
+            else y = add_(mul_((double)idx, step), a);
+        }
+        pol[i * nc + c] = y;
+    }
+}
+
+extern "C" int sdp_policy_values(int64_t n, int32_t nc, const double* lo, const double* hi,
+                                 const int32_t* npts, const int32_t* argmin, double* pol,
+                                 void* stream) {
+    if (n < 0 || nc < 0) return fail(SDP_EINVAL, "%s", "sdp_policy_values: bad sizes");
+    if (n == 0 || nc == 0) return SDP_OK;
+    if (!lo || !hi || !npts || !argmin || !pol) return fail(SDP_EINVAL, "%s", "sdp_policy_values: NULL pointer");
+    k_policy_values<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, nc, lo, hi, npts, argmin, pol);
+    SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
 

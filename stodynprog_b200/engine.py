@@ -219,6 +219,11 @@ class Engine(object):
         t = torch.from_numpy(a)
         if dtype is not None:
             t = t.to(dtype)
+        if self._cuda and t.numel() * t.element_size() >= (1 << 20):
+            # large inputs go through a pinned staging buffer (async DMA)
+            pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            pin.copy_(t)
+            return pin.to(self.device, non_blocking=True)
         return t.to(self.device, non_blocking=False)
 
     def sync(self):
@@ -323,6 +328,11 @@ class Engine(object):
         else:
             T.p = self.to_device(np.ones(1))
         T.U_dev = self.to_device(U.astype(np.int32)) if n else torch.zeros(1, dtype=torch.int32, device=dev)
+        # replicated control discretisation, for the argmin -> control value kernel
+        T.lo_dev = self.to_device(host_full.lo.reshape(-1)) if nb_control else None
+        T.hi_dev = self.to_device(host_full.hi.reshape(-1)) if nb_control else None
+        T.npts_dev = self.to_device(host_full.npts.astype(np.int32).reshape(-1)) if nb_control else None
+        T.nb_control = nb_control
         w_grid = [np.asarray(g) for g in solver.perturb_grid]
         mode = getattr(solver, "tabulate", "auto")
         T.tabulate_mode = None
@@ -516,6 +526,30 @@ class Engine(object):
     def gather_argmin(self, T):
         """full-grid int32 argmin (device), gathered over ranks"""
         return self.coll.all_gather_slabs(T.argmin[:T.n_states], T.bounds)
+
+    def policy_values(self, T, argmin_full):
+        """K3: full-grid argmin (device int32 [N]) -> control values (device fp64 [N][nc])"""
+        torch = _torch()
+        n = argmin_full.numel()
+        nc = T.nb_control
+        pol = torch.empty((n, nc), dtype=torch.float64, device=self.device)
+        if nc:
+            rc = self.lib.sdp_policy_values(n, nc, self._ptr(T.lo_dev), self._ptr(T.hi_dev),
+                                            self._ptr(T.npts_dev), self._ptr(argmin_full),
+                                            self._ptr(pol), self.stream)
+            _cabi.check(rc, "sdp_policy_values")
+        return pol
+
+    def to_host(self, *tensors):
+        """device tensors -> fresh numpy arrays (through pinned buffers, one sync)"""
+        torch = _torch()
+        if not self._cuda:
+            return [t.numpy().copy() for t in tensors]
+        outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        for o, t in zip(outs, tensors):
+            o.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return [o.numpy() for o in outs]
 
     # -- policy tables ----------------------------------------------------
     def build_policy_tables(self, solver, pol):

@@ -172,22 +172,6 @@ class DPSolver(object):
         self.last_tables = T
         return T
 
-    def _policy_from_argmin(self, T, argmin):
-        """argmin (N,) flat C-order control index -> (N, nb_control) control values
-        `u_grids[i].flatten()[ind_opt[i]]` (reference stodynprog.py:686-689)"""
-        host = T.host_full
-        nb_control = host.npts.shape[1]
-        pol = np.zeros((len(argmin), nb_control))
-        if nb_control == 0:
-            return pol
-        rem = argmin.astype(np.int64)
-        for c in reversed(range(nb_control)):
-            n_c = host.npts[:, c]
-            ind_c = rem % n_c
-            rem = rem // n_c
-            pol[:, c] = tb.control_axis_values(host.lo[:, c], host.hi[:, c], n_c, ind_c)
-        return pol
-
     def _sweep_host(self, J_next, t_k=None, rel_dp=False, tables=None):
         """one sweep with host arrays in/out. Returns (J_k, J_ref or None, pol_k, tables)"""
         import torch
@@ -203,10 +187,11 @@ class DPSolver(object):
             ref_flat = int(np.ravel_multi_index(self._state_ref_ind, state_dims))
             ref_out = torch.zeros(1, dtype=torch.float64, device=eng.device)
         eng.sweep(T, J_prev, J_new, rel_ref_index=ref_flat, ref_out=ref_out)
-        argmin = eng.gather_argmin(T)
-        J_k = J_new.cpu().numpy().reshape(state_dims)
-        J_ref = float(ref_out.cpu().numpy()[0]) if rel_dp else None
-        pol_k = self._policy_from_argmin(T, argmin.cpu().numpy()).reshape(state_dims + (nb_control,))
+        pol_dev = eng.policy_values(T, eng.gather_argmin(T))      # K3: indices -> control values
+        outs = eng.to_host(J_new, pol_dev, *([ref_out] if rel_dp else []))
+        J_k = outs[0].reshape(state_dims)
+        pol_k = outs[1].reshape(state_dims + (nb_control,))
+        J_ref = float(outs[2][0]) if rel_dp else None
         return J_k, J_ref, pol_k, T
 
     # ------------------------------------------------------------------
@@ -373,9 +358,10 @@ class DPSolver(object):
                 history.append(r)
                 if r <= tol:
                     break
-        argmin = eng.gather_argmin(T).cpu().numpy()
-        J = J_prev.cpu().numpy().reshape(state_dims)
-        pol = self._policy_from_argmin(T, argmin).reshape(state_dims + (nb_control,))
+        pol_dev = eng.policy_values(T, eng.gather_argmin(T))
+        J, pol = eng.to_host(J_prev, pol_dev)
+        J = J.reshape(state_dims)
+        pol = pol.reshape(state_dims + (nb_control,))
         info = {'n_sweeps': n_done, 'residuals': history,
                 'J_ref': float(ref_out.cpu().numpy()[0]) if rel_dp else None}
         return J, pol, info

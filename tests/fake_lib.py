@@ -280,6 +280,20 @@ class FakeLib(object):
         self.launches += n_iter
         return 0
 
+    def sdp_policy_values(self, n, nc, lo, hi, npts, argmin, pol, stream):
+        LO = _arr(lo, n * nc, ctypes.c_double).reshape(n, nc)
+        HI = _arr(hi, n * nc, ctypes.c_double).reshape(n, nc)
+        NP = _arr(npts, n * nc, ctypes.c_int32).reshape(n, nc)
+        AM = _arr(argmin, n, ctypes.c_int32).astype(np.int64)
+        out = _arr(pol, n * nc, ctypes.c_double).reshape(n, nc)
+        for i in range(n):
+            ind = np.unravel_index(AM[i], tuple(NP[i]))
+            for c in range(nc):
+                m = int(NP[i, c])
+                grid = np.array([(LO[i, c] + HI[i, c]) / 2]) if m == 1 else np.linspace(LO[i, c], HI[i, c], m)
+                out[i, c] = grid[ind[c]]
+        return 0
+
     def sdp_rel_shift(self, J, n, ref_index, ref_out, stream):
         A = _arr(J, n, ctypes.c_double)
         r = _arr(ref_out, 1, ctypes.c_double)
