@@ -769,8 +769,11 @@ static Tuning& tuning() {
         x.upl = env_int("SDP_UPL", 4) == 2 ? 2 : 4;
         int wb = env_int("SDP_WB", 1);
         x.wb = (wb == 2 || wb == 3 || wb == 5) ? wb : 1;
+        // measured on B200 (profiles/): the tiled sweep is bound by L1 wavefronts
+        // of the corner gathers, not by the HBM stream, and the LDG kernel's higher
+        // occupancy hides the gather latency better than the TMA ring does
         const char* impl = getenv("SDP_TILED_IMPL");
-        x.tma = (impl && strcmp(impl, "ldg") == 0) ? 0 : 1;
+        x.tma = (impl && strcmp(impl, "tma") == 0) ? 1 : 0;
         x.R = env_int("SDP_TMA_R", 4) == 8 ? 8 : 4;
         x.S = env_int("SDP_TMA_S", 4);
         x.NW = env_int("SDP_TMA_NW", 8);

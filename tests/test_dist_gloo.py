@@ -1,0 +1,114 @@
+"""world_size-2 tests on CPU (gloo): the sharded sweep pipeline - slab
+partition, per-rank tabulation, per-sweep all-gather of J, all-reduce-max of the
+residual, gathered argmin -> policy - driven through the numpy model of the C
+ABI, against the single-process result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir, layout):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import stodynprog_b200 as sdp
+        from stodynprog_b200 import workloads as wl
+        from fake_lib import FakeLib
+        prob = wl.storage_ar1(sdp, n_E=9, n_P=11, steps=(0.01, 0.1), _test_lib=FakeLib())
+        sv = prob.solver
+        sv.table_layout = layout
+        J0 = np.random.default_rng(0).standard_normal((9, 11))
+        J1, pol1 = sv.value_iteration(J0, report_time=False)
+        T = sv.last_tables
+        (Jd, Jr), pol2 = sv.value_iteration((J1 - J1[sv._state_ref_ind], 0.), rel_dp=True, report_time=False)
+        Je, ref = sv.eval_policy(pol1, 6, rel_dp=True, report_time=False)
+        Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=3, tol=0.0)
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), J1=J1, pol1=pol1, Jd=Jd, Jr=Jr, pol2=pol2,
+                 Je=Je, ref=ref, Js=Js, pols=pols, resid=np.array(info["residuals"]),
+                 bounds=np.array(T.bounds), n_local=T.n_states, backups=T.n_backups_local,
+                 total=T.n_backups_total)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("layout", ["control_minor", "state_minor"])
+def test_sharded_sweep_world2_matches_single_process(tmp_path, layout):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), layout), nprocs=world, join=True)
+    r = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % k)) for k in range(world)]
+
+    # single-process run of the same thing
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import stodynprog_b200 as sdp
+    from stodynprog_b200 import workloads as wl
+    from fake_lib import FakeLib
+    prob = wl.storage_ar1(sdp, n_E=9, n_P=11, steps=(0.01, 0.1), _test_lib=FakeLib())
+    sv = prob.solver
+    sv.table_layout = layout
+    J0 = np.random.default_rng(0).standard_normal((9, 11))
+    J1, pol1 = sv.value_iteration(J0, report_time=False)
+    (Jd, Jr), pol2 = sv.value_iteration((J1 - J1[sv._state_ref_ind], 0.), rel_dp=True, report_time=False)
+    Je, ref = sv.eval_policy(pol1, 6, rel_dp=True, report_time=False)
+    Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=3, tol=0.0)
+
+    for k in range(world):
+        # every rank holds the full, identical result
+        assert np.array_equal(r[k]["J1"], J1) and np.array_equal(r[k]["pol1"], pol1)
+        assert np.array_equal(r[k]["Jd"], Jd) and r[k]["Jr"] == Jr and np.array_equal(r[k]["pol2"], pol2)
+        assert np.array_equal(r[k]["Je"], Je) and r[k]["ref"] == ref
+        assert np.array_equal(r[k]["Js"], Js) and np.array_equal(r[k]["pols"], pols)
+        assert np.array_equal(r[k]["resid"], np.array(info["residuals"]))
+    # the slabs are contiguous, disjoint, cover the grid and are balanced by controls
+    b = r[0]["bounds"]
+    assert list(b) == list(r[1]["bounds"]) and b[0] == 0 and b[-1] == 99
+    assert int(r[0]["n_local"]) + int(r[1]["n_local"]) == 99
+    assert int(r[0]["backups"]) + int(r[1]["backups"]) == int(r[0]["total"])
+    assert abs(int(r[0]["backups"]) - int(r[1]["backups"])) / int(r[0]["total"]) < 0.1
+
+
+def _coll_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from stodynprog_b200.engine import Collective
+        c = Collective()
+        bounds = [0, 3, 10]
+        full = torch.arange(10, dtype=torch.float64) * 1.5
+        local = full[bounds[rank]:bounds[rank + 1]].clone()
+        got = c.all_gather_slabs(local, bounds)
+        out = torch.zeros(10, dtype=torch.float64)
+        c.all_gather_slabs(local, bounds, out=out)
+        m = c.all_reduce_max(torch.tensor([float(rank + 1)], dtype=torch.float64))
+        objs = c.all_gather_object({"rank": rank})
+        ok = bool(torch.equal(got, full) and torch.equal(out, full) and m.item() == world
+                  and [o["rank"] for o in objs] == list(range(world)))
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write(str(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_collective_uneven_slabs_world2(tmp_path):
+    mp.spawn(_coll_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for k in range(2):
+        assert open(os.path.join(str(tmp_path), "ok%d" % k)).read() == "True"

@@ -1,0 +1,305 @@
+"""Host-side API tests (CPU suite).  The SysDescription tests read like the
+reference's own (stodynprog/tests/test_stodynprog.py); the rest covers the
+solver's host logic and the C-ABI library (load + exported symbols only: no
+compute call is made without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import stodynprog_b200 as sdp
+from stodynprog_b200 import _cabi, tabulate as tb
+from stodynprog_b200.sysdesc import _zero_cost, _enforce_sig_len
+from conftest import ROOT
+
+
+# --- mirror of reference tests/test_stodynprog.py ---------------------------
+def test_zero_cost():
+    assert _zero_cost() == 0.
+    assert _zero_cost(1) == 0.
+    assert _zero_cost(1, 2) == 0.
+    assert _zero_cost(1, 2, 3) == 0.
+
+
+def test_enforce_sig_len():
+    def f0():
+        pass
+
+    def f1(x):
+        pass
+
+    def f2(x, y):
+        pass
+    arg0, arg1, arg2 = [], ['x'], ['x', 'y']
+    wp = False
+    assert _enforce_sig_len(f0, arg0, wp)
+    for f, bad in ((f0, arg1), (f0, arg2), (f1, arg0), (f1, arg2), (f2, arg1), (f2, arg0)):
+        with pytest.raises(ValueError):
+            _enforce_sig_len(f, bad, wp)
+    assert _enforce_sig_len(f1, arg1, wp)
+    assert _enforce_sig_len(f2, arg2, wp)
+    with pytest.raises(ValueError) as e:
+        _enforce_sig_len(f1, arg2, wp)
+    assert e.value.args[0] == "'f1' should accept 2 args (x, y), not 1"   # reference test :58
+
+    def f1p(x, **params):
+        pass
+    assert _enforce_sig_len(f1p, arg1, with_params=True)
+    with pytest.raises(ValueError):
+        _enforce_sig_len(f1p, arg1, with_params=False)
+    with pytest.raises(ValueError):
+        _enforce_sig_len(f1, arg1, with_params=True)
+
+
+class TestSysDescription:
+    def setup_method(self):
+        self.sys110 = sdp.SysDescription((1, 1, 0), stationnary=True, name='sys110')
+        self.sys111 = sdp.SysDescription((1, 1, 1), stationnary=True, name='sys111')
+
+    def test_attributes(self):
+        assert self.sys111.stationnary
+        assert self.sys111.stochastic
+        assert not self.sys110.stochastic
+        assert self.sys111.name == 'sys111'
+
+    def test_dyn_function(self):
+        def dyn3(my_state, my_control, my_perturb):
+            pass
+        self.sys111.dyn = dyn3
+        assert self.sys111.state == ['my_state']
+        assert self.sys111.control == ['my_control']
+        assert self.sys111.perturb == ['my_perturb']
+
+        def dyn2(x, u):
+            pass
+
+        def dyn4(x, y, u, w):
+            pass
+        with pytest.raises(ValueError):
+            self.sys111.dyn = dyn2
+        with pytest.raises(ValueError):
+            self.sys111.dyn = dyn4
+
+    def test_print_summary(self, capsys):
+        self.sys111.print_summary()
+        out = capsys.readouterr().out
+        assert 'Dynamical system "sys111" description' in out
+        assert 'stationnary, stochastic' in out
+
+    def test_time_dependent_and_params(self):
+        s = sdp.SysDescription((1, 1), stationnary=False, params={'a': 1})
+
+        def dyn(k, x, u, **p):
+            return (x + u,)
+        s.dyn = dyn
+        assert s.state == ['x'] and s.control == ['u'] and s.perturb == []
+
+        def box(k, x, **p):
+            return ((0, 1),)
+        s.control_box = box
+        with pytest.raises(ValueError):
+            s.cost = lambda k, x, u: 0      # missing **params
+        with pytest.raises(ValueError):
+            sdp.SysDescription((1,))
+
+    def test_perturb_laws(self):
+        import scipy.stats as stats
+        self.sys111.perturb_laws = [stats.norm()]
+        assert self.sys111.perturb_types == ['continuous']
+        self.sys111.perturb_laws = [stats.poisson(2)]
+        assert self.sys111.perturb_types == ['discrete']
+        with pytest.raises(ValueError):
+            self.sys111.perturb_laws = []
+        with pytest.raises(ValueError):
+            self.sys111.perturb_laws = [object()]
+
+    def test_terminal_cost(self):
+        with pytest.raises(ValueError):
+            self.sys111.terminal_cost = lambda x, y: 0
+        self.sys111.terminal_cost = lambda x: x
+        assert self.sys111.terminal_cost(3) == 3
+
+
+# --- DPSolver host logic -------------------------------------------------------
+def test_discretize_and_reference_state():
+    from stodynprog_b200 import workloads as wl
+    sv = wl.storage_ar1(sdp).solver
+    assert sv._state_grid_shape == (41, 61)
+    assert sv._state_ref_ind == (20, 30)
+    assert sv._state_ref == (sv.state_grid[0][20], sv.state_grid[1][30])
+    assert np.allclose(sum(sv.perturb_proba[0]), 1.0)
+    g = sv.state_grid_full
+    assert g[0].shape == (41, 61) and g[1][3, 7] == sv.state_grid[1][7]
+    with pytest.raises(AssertionError):
+        sv.discretize_state(0, 1, 3)
+    with pytest.raises(AssertionError):
+        sv.discretize_perturb(0, 1)
+
+
+def test_discrete_pmf_must_sum_to_one():
+    from stodynprog_b200 import workloads as wl
+    sv = wl.inventory(sdp).solver
+    assert list(sv.perturb_proba[0]) == [0.2, 0.4, 0.3, 0.1]
+    with pytest.raises(AssertionError):
+        sv.discretize_perturb(0, 2, 3)       # misses the mass at w = 3
+
+
+def test_control_grids_match_port(port):
+    from stodynprog_b200 import workloads as wl
+    import itertools
+    a = wl.storage_ar1(sdp).solver
+    b = wl.storage_ar1(port).solver
+    for x_k in itertools.islice(itertools.product(*a.state_grid), 0, 2501, 37):
+        ga, da = a.control_grids(x_k)
+        gb, db = b.control_grids(x_k)
+        assert da == db
+        for u, v in zip(ga, gb):
+            assert np.array_equal(u, v)
+    ga, da = a.control_grids((0.0, 0.0))
+    assert da == (4001, 1) and ga[1][0] == 0.0
+
+
+def test_control_axis_values_equals_linspace():
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        lo = rng.normal() * 10.0 ** rng.integers(-3, 4)
+        hi = lo + abs(rng.normal()) * 10.0 ** rng.integers(-3, 4)
+        n = int(rng.integers(2, 400))
+        ref = np.linspace(lo, hi, n)
+        idx = np.arange(n)
+        got = tb.control_axis_values(np.full(n, lo), np.full(n, hi), np.full(n, n), idx)
+        assert np.array_equal(got, ref)
+    # degenerate: zero width, and the single centre point
+    assert np.array_equal(tb.control_axis_values([1.0] * 3, [1.0] * 3, [3] * 3, [0, 1, 2]), np.linspace(1., 1., 3))
+    assert tb.control_axis_values([0.0], [0.0], [1], [0])[0] == 0.0
+    assert tb.control_axis_values([2.0], [3.0], [1], [0])[0] == 2.5
+
+
+def test_interp_on_state_errors():
+    from stodynprog_b200 import workloads as wl
+    sv = wl.storage_ar1(sdp, n_E=5, n_P=6).solver
+    with pytest.raises(ValueError) as e:
+        sv.interp_on_state(np.zeros((6, 5)))
+    assert e.value.args[0] == 'array `A` should be of shape (5, 6), not (6, 5)'
+    f = sv.interp_on_state(np.zeros((5, 6)))
+    assert f.ndim == 2 and f.values.shape == (1, 30)
+    import pickle
+    g = pickle.loads(pickle.dumps(f))           # stays picklable like the reference's
+    assert np.array_equal(g._xmax, f._xmax) and np.array_equal(g.values, f.values)
+
+
+def test_print_summary_matches_notebook(capsys):
+    """examples/howto storage-AR1.ipynb cell 8 output"""
+    from stodynprog_b200 import workloads as wl
+    sv = wl.storage_ar1(sdp).solver
+    sv.print_summary()
+    out = capsys.readouterr().out
+    assert '* state space discretized on a 41x61 points grid' in out
+    assert 'yields [4,001 to 8,001] possible values (6,342.5 on average)' in out
+    assert 'control combinations: [4,001 to 8,001] possible values (6,342.5 on average)' in out
+
+
+def test_partition_by_weight():
+    from stodynprog_b200.engine import partition_by_weight
+    w = np.array([1, 1, 1, 1, 10, 1, 1, 1, 1, 1], dtype=float)
+    b = partition_by_weight(w, 2)
+    assert b[0] == 0 and b[-1] == 10 and b == sorted(b)
+    rng = np.random.default_rng(0)
+    w = rng.integers(129, 257, size=100000).astype(float)
+    for world in (2, 4, 8):
+        b = partition_by_weight(w, world)
+        loads = [w[b[r]:b[r + 1]].sum() for r in range(world)]
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == len(w)
+        assert max(loads) / (w.sum() / world) < 1.001
+    assert partition_by_weight([], 4) == [0, 0, 0, 0, 0]
+    assert partition_by_weight([5.0], 4)[-1] == 1
+
+
+# --- the C ABI -----------------------------------------------------------------
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "sdp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_loads_and_exports_every_declared_symbol(product):
+    lib = _cabi.load_library()
+    declared = _header_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), name
+        assert name in _cabi.SIGNATURES, "binding missing for " + name
+    assert sorted(_cabi.SIGNATURES) == declared
+    assert lib.sdp_version() == _cabi.SDP_ABI_VERSION
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (sdp_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """numpy / ctypes mirrors vs the C compiler's view of include/sdp_b200.h"""
+    src = tmp_path / "layout.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "sdp_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SdpStateDesc), offsetof(SdpStateDesc, src),
+         offsetof(SdpStateDesc, cs), offsetof(SdpStateDesc, ws), offsetof(SdpStateDesc, npts),
+         offsetof(SdpStateDesc, U), offsetof(SdpStateDesc, Upad), sizeof(SdpItem));
+  printf("%zu %zu %zu %zu %zu\\n", sizeof(SdpTables), offsetof(SdpTables, p), offsetof(SdpTables, n_items),
+         offsetof(SdpTables, U), sizeof(SdpGrid));
+  return 0; }''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    l1, l2 = subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip().splitlines()
+    D = _cabi.STATE_DESC_DTYPE
+    assert [int(x) for x in l1.split()] == [D.itemsize, D.fields["src"][1], D.fields["cs"][1],
+                                            D.fields["ws"][1], D.fields["npts"][1], D.fields["U"][1],
+                                            D.fields["Upad"][1], _cabi.ITEM_DTYPE.itemsize]
+    T = _cabi.SdpTables
+    assert [int(x) for x in l2.split()] == [ctypes.sizeof(T), T.p.offset, T.n_items.offset, T.U.offset,
+                                            ctypes.sizeof(_cabi.SdpGrid)]
+
+
+def test_no_cpu_fallback(product):
+    """without a GPU the product refuses to run; without the library it says so"""
+    import torch
+    from stodynprog_b200 import workloads as wl
+    if not torch.cuda.is_available():
+        sv = wl.inventory(sdp).solver
+        with pytest.raises(_cabi.SdpLibraryError):
+            sv.value_iteration(np.zeros(10), report_time=False)
+    with pytest.raises(_cabi.SdpLibraryError):
+        _cabi.load_library("/nonexistent/libsdp_b200.so")
+
+
+def test_product_does_not_import_the_oracle():
+    """the oracle is test infrastructure: nothing under stodynprog_b200/ refers to it"""
+    pkg = os.path.join(ROOT, "stodynprog_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt and "sdp_oracle" not in txt, f
+
+
+def test_sass_has_no_fma_in_sweep_kernels(product):
+    """the parity contract forbids contraction: the sweep / policy kernels must
+    contain no DFMA (divisions in the setup kernels legitimately use it)"""
+    res = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True)
+    if res.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    fn, bad = None, {}
+    for line in res.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+        elif "DFMA" in line and fn and re.search(r"k_sweep|k_policy_eval|k_sub_scalar", fn):
+            bad[fn] = bad.get(fn, 0) + 1
+    assert not bad, bad
+    assert "UBLKCP" in res.stdout      # the TMA-fed variant is built (bulk async copies)
