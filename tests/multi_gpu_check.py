@@ -1,0 +1,68 @@
+"""Sharded-sweep parity check, to be launched with one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+        --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+
+Every rank builds the tables of its slab of the storage-AR1 grid (config #3),
+runs value_iteration / eval_policy / policy_iteration through the public API
+(NCCL all-gather of J per sweep) and compares with the golden fixtures produced
+by the unmodified reference.  Exit code 0 = parity on every rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import stodynprog_b200 as sdp
+    from stodynprog_b200 import workloads as wl
+    from conftest import golden, rel_err
+    G = golden("storage_ar1.npz")
+    layouts = ["control_minor", "state_minor"]
+    ok = True
+    for layout in layouts:
+        prob = wl.storage_ar1(sdp)
+        sv = prob.solver
+        sv.table_layout = layout
+        J = prob.J0
+        for k in range(3):
+            J, pol = sv.value_iteration(J, report_time=False)
+            bad = int(np.any(pol != G["vi_pol%d" % k], axis=-1).sum())
+            err = rel_err(J, G["vi_J%d" % k])
+            ok &= bad == 0 and err <= 1e-10
+            if rank == 0:
+                print("[%s] sweep %d: policy mismatches %d, J rel err %.2e" % (layout, k, bad, err))
+        T = sv.last_tables
+        print("[%s] rank %d slab [%d, %d) backups %d of %d" % (layout, rank, T.state_begin,
+              T.state_begin + T.n_states, T.n_backups_local, T.n_backups_total), flush=True)
+        (Jd, Jr), polp = sv.policy_iteration(prob.initial_policy(), 50, 4, rel_dp=True)
+        bad = int(np.any(polp != G["pi_pol"], axis=-1).sum())
+        errJ = float(np.max(np.abs(Jd - G["pi_J"])) / np.max(np.abs(G["pi_J"])))
+        errR = abs(Jr - float(G["pi_Jref"])) / abs(float(G["pi_Jref"]))
+        ok &= bad == 0 and errJ <= 1e-10 and errR <= 1e-10
+        if rank == 0:
+            print("[%s] policy_iteration: policy mismatches %d, J err %.2e, J_ref %.10g (err %.2e)"
+                  % (layout, bad, errJ, Jr, errR))
+        Js, pols, info = sv.solve_value_iteration(max_iter=3, tol=0.0)
+        r_expected = np.max(np.abs(G["vi_J2"] - G["vi_J1"]))
+        ok &= rel_err(Js, G["vi_J2"]) <= 1e-10 and abs(info["residuals"][-1] - r_expected) <= 1e-9 * r_expected
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_PARITY", "OK" if flag.item() == 1 else "FAILED")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

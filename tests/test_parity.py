@@ -538,3 +538,81 @@ def test_two_controls_ragged_product(api, port):
     assert sv.last_tables.host_full.npts[:, 1].max() > 5
     assert np.array_equal(pol, polo)
     assert rel_err(J, Jo) <= J_RTOL
+
+
+# ---------------------------------------------------------------------------
+# config #4 at full size: the reference's shipped golden policy
+# ---------------------------------------------------------------------------
+@gpu
+def test_searev_full_policy_iteration_golden(cuda_api, capsys):
+    """examples/20 .../storage control/pol_E10_grid3161_iter5.npy: the policy after
+    policy_iteration(pol_lin, 1000, 5, rel_dp=True) on the 31x61x61 grid (5 argmin
+    sweeps over 2.2 G backups + 6000 fixed-policy backups of the whole grid).  The
+    fixture is the unmodified reference's output, bit-identical to the shipped file."""
+    from stodynprog_b200 import workloads as wl
+    G = golden("searev_full.npz")
+    assert bool(G["matches_shipped_npy"])
+    prob = wl.searev(cuda_api)
+    (Jd, Jr), pol = prob.solver.policy_iteration(prob.initial_policy(), 1000, 5, rel_dp=True)
+    text = capsys.readouterr().out
+    costs = [l.split(':')[1].strip() for l in text.splitlines() if 'ref policy cost' in l]
+    assert costs == ['{:g}'.format(c) for c in G["pi_ref_costs"]]
+    assert costs == ['0.0864223', '0.0798338', '0.0760902', '0.0747645', '0.0746698', '0.0746743']
+    assert prob.solver.last_tables.n_backups_total == 2211312159
+    n_bad, diff = policy_mismatch_report(pol, G["pi_pol"])
+    # exact agreement is expected; a handful of near-ties (two controls whose
+    # expected costs differ by a few ulp) would be reported here, not hidden
+    print("SEAREV golden policy: %d / %d states differ" % (n_bad, diff.size))
+    assert n_bad == 0
+    assert abs(Jr - float(G["pi_Jref"])) <= J_RTOL * abs(float(G["pi_Jref"]))
+    assert np.max(np.abs(Jd - G["pi_J"])) <= J_RTOL * np.max(np.abs(G["pi_J"]))
+
+
+@gpu
+def test_sharded_two_gpus_subprocess():
+    """N > 1 on real GPUs (skipped on a 1-GPU box): tests/multi_gpu_check.py"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29517",
+           os.path.join(ROOT, "tests", "multi_gpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "MULTI_GPU_PARITY OK" in res.stdout
+
+
+# ---------------------------------------------------------------------------
+# full-size properties (config #5 is too big for the CPU oracle: sampled check)
+# ---------------------------------------------------------------------------
+@gpu
+def test_large_grid_sampled_against_port(cuda_api, port):
+    """2000 x 125 slice of config #5 (layout B, batched tabulation): 300 random
+    states checked against the numpy port; min over controls <= any fixed control;
+    idempotence of the table cache."""
+    from stodynprog_b200 import workloads as wl
+    n_E, n_P = 2000, 125
+    prob = wl.storage_ar1_large(cuda_api, n_E=n_E, n_P=n_P)
+    ora = wl.storage_ar1_large(port, n_E=n_E, n_P=n_P)
+    sv = prob.solver
+    J0 = np.random.default_rng(0).standard_normal((n_E, n_P))
+    J, pol = sv.value_iteration(J0, report_time=False)
+    T = sv.last_tables
+    assert T.tiled and T.tabulate_mode == "batched"
+    J2, pol2 = sv.value_iteration(J0, report_time=False)
+    assert sv.last_tables is T and np.array_equal(J, J2) and np.array_equal(pol, pol2)
+    Ji = ora.solver.interp_on_state(J0)
+    rng = np.random.default_rng(1)
+    for flat in rng.choice(n_E * n_P, size=300, replace=False):
+        idx = np.unravel_index(flat, (n_E, n_P))
+        x_k = tuple(g[i] for g, i in zip(ora.solver.state_grid, idx))
+        Jo, uo = ora.solver.value_at_state(x_k, Ji)
+        assert list(pol[idx]) == list(uo)
+        assert abs(J[idx] - Jo) <= J_RTOL * max(abs(Jo), 1e-300)
+    # the greedy value never exceeds the value of the 'do nothing'-like first control
+    Je = sv.eval_policy(pol, 1, J_zero=J0, report_time=False)
+    assert np.max(np.abs(Je - J)) <= 1e-10 * np.max(np.abs(J))
