@@ -66,13 +66,15 @@ if __name__ == "__main__":
         for wb in (1, 3):
             opt(lib, wb=wb)
             print("ldg wb=%d" % wb, time_sweeps(sv, T), flush=True)
-        opt(lib, tma=1)
-        for R, S, NW in itertools.product((4, 8), (2, 3, 4, 6, 8), (4, 8, 16)):
-            opt(lib, tma_rows=R, tma_stages=S, tma_warps=NW)
-            try:
+        opt(lib, tma=2)
+        for rb in (2, 4, 8):
+            opt(lib, rb=rb)
+            print("pipe rb=%d" % rb, time_sweeps(sv, T), flush=True)
+        if os.environ.get("TMA_SWEEP"):
+            opt(lib, tma=1)
+            for R, S, NW in itertools.product((4, 8), (2, 3), (1, 2, 4, 8)):
+                opt(lib, tma_rows=R, tma_stages=S, tma_warps=NW)
                 print("tma R=%d S=%d NW=%d" % (R, S, NW), time_sweeps(sv, T), flush=True)
-            except Exception as e:
-                print("tma R=%d S=%d NW=%d failed: %s" % (R, S, NW, e), flush=True)
     else:
         for upl in (4, 2):
             opt(lib, upl=upl)

@@ -586,6 +586,117 @@ k_sweep_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
 }
 
 // ---------------------------------------------------------------------------
+// Layout B, software-pipelined variant (default).  ncu on the straight LDG
+// kernel shows a pure latency problem (long-scoreboard stalls, L1/L2/DRAM all
+// below 65 % busy): the chain "table row -> corner gathers -> arithmetic" is
+// serial per warp.  Here the rows of an item (row = one (u,w) pair for the 32
+// states of the tile, contiguous in memory) are walked in groups of RB; the
+// streaming loads of group i+1 are issued before the 2^d*RB gathers of group i
+// are consumed, so every warp keeps RB rows of table traffic and RB rows of
+// gathers in flight at all times.
+// ---------------------------------------------------------------------------
+// running state of one lane (= one state of the tile) while it walks the rows
+// (u,w) of its item in order: expectation accumulator over w, minimum over u
+struct LaneWalk {
+    double best_v, acc, gv, gv_next;
+    int best_i, w, uu;
+};
+
+__device__ __forceinline__ void walk_row(LaneWalk& s, double jg, double pw, int expect, int W,
+                                         int u_begin, int u_count, int Us, bool g_per_w,
+                                         const double* __restrict__ gp) {
+    if (expect) s.acc = add_(s.acc, mul_(jg, pw));   // np.inner over w   stodynprog.py:682
+    else s.acc = jg;                                 // deterministic     :679-680
+    if (++s.w == W) {
+        const int u = u_begin + s.uu;
+        if (u < Us && better(s.acc, u, s.best_v, s.best_i)) { s.best_v = s.acc; s.best_i = u; }
+        s.w = 0;
+        s.acc = 0.0;
+        ++s.uu;
+        if (!g_per_w) {
+            s.gv = s.gv_next;
+            if (s.uu + 1 < u_count) s.gv_next = __ldcs(gp + (int64_t)(s.uu + 1) * 32);
+        }
+    }
+}
+
+template <int D, int RB>
+struct RowGroup {
+    int c[RB];
+    double l[RB][D];
+    double gw[RB];
+};
+
+// unguarded: all RB rows exist (keeps ptxas free to batch the loads)
+template <int D, int RB>
+__device__ __forceinline__ void load_rows(RowGroup<D, RB>& g, const int32_t* __restrict__ cellp,
+                                          const double* __restrict__ lamp, int64_t lam_plane,
+                                          const double* __restrict__ gwp, bool g_per_w, int row0) {
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        const int64_t o = (int64_t)(row0 + r) * 32;
+        g.c[r] = __ldcs(cellp + o);
+#pragma unroll
+        for (int k = 0; k < D; ++k) g.l[r][k] = __ldcs(lamp + (int64_t)k * lam_plane + o);
+        g.gw[r] = g_per_w ? __ldcs(gwp + o) : 0.0;
+    }
+}
+
+template <int D, int RB>
+__global__ void __launch_bounds__(256, (RB == 2 ? 3 : (RB == 4 ? 2 : 1)))
+k_sweep_tiled_pipe(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+                   double* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+    extern __shared__ double p_sh[];
+    for (int i = threadIdx.x; i < T.W; i += blockDim.x) p_sh[i] = T.expect ? T.p[i] : 1.0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t item_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item_id >= T.n_items) return;
+    const SdpItem it = T.items[item_id];
+    const int W = T.W;
+    const bool g_per_w = T.g_per_w != 0;
+    const int64_t state = (int64_t)it.state * 32 + lane;
+    const int Us = (state < T.n_states) ? T.U[state] : 0;
+    const int n_rows = it.u_count * W;
+    const int32_t* __restrict__ cellp = T.cell + it.entry_base + lane;
+    const double* __restrict__ lamp = T.lam + it.entry_base + lane;
+    const double* __restrict__ gp = T.g + it.g_base + lane;   // g rows: per u, or per (u,w)
+
+    LaneWalk s;
+    s.best_v = CUDART_INF; s.best_i = INT_MAX; s.acc = 0.0; s.w = 0; s.uu = 0;
+    s.gv = 0.0; s.gv_next = 0.0;
+    if (!g_per_w) {
+        s.gv = __ldcs(gp);
+        if (it.u_count > 1) s.gv_next = __ldcs(gp + 32);
+    }
+
+    const int n_full = n_rows / RB;
+    RowGroup<D, RB> cur, nxt;
+    if (n_full > 0) load_rows<D, RB>(cur, cellp, lamp, T.lam_plane, gp, g_per_w, 0);
+    for (int gi = 0; gi < n_full; ++gi) {
+        if (gi + 1 < n_full) load_rows<D, RB>(nxt, cellp, lamp, T.lam_plane, gp, g_per_w, (gi + 1) * RB);
+        double v[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) v[r] = Lerp<double, D, 0>::eval(Jprev, cur.c[r], G.stride, cur.l[r]);
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+            walk_row(s, add_(g_per_w ? cur.gw[r] : s.gv, v[r]), p_sh[s.w], T.expect, W, it.u_begin,
+                     it.u_count, Us, g_per_w, gp);
+        cur = nxt;
+    }
+    for (int row = n_full * RB; row < n_rows; ++row) {          // tail rows
+        RowGroup<D, 1> t;
+        load_rows<D, 1>(t, cellp, lamp, T.lam_plane, gp, g_per_w, row);
+        const double v = Lerp<double, D, 0>::eval(Jprev, t.c[0], G.stride, t.l[0]);
+        walk_row(s, add_(g_per_w ? t.gw[0] : s.gv, v), p_sh[s.w], T.expect, W, it.u_begin, it.u_count,
+                 Us, g_per_w, gp);
+    }
+    part_val[item_id * 32 + lane] = s.best_v;
+    part_idx[item_id * 32 + lane] = s.best_i;
+}
+
+// ---------------------------------------------------------------------------
 // Layout B, TMA-fed variant.  The table region of an item (tile x run of
 // controls) is one contiguous run of rows per plane (row = 32 lanes), so each
 // warp streams it through its own shared-memory ring with 1-D bulk async copies
@@ -621,7 +732,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 template <int D, int R>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 k_sweep_tiled_tma(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
                   double* __restrict__ part_val, int32_t* __restrict__ part_idx, int S) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -675,12 +786,15 @@ k_sweep_tiled_tma(GridT<double> G, SdpTables T, const double* __restrict__ Jprev
         for (int s = 0; s < pre; ++s) issue(s);
     }
 
-    double best_v = CUDART_INF;
-    int best_i = INT_MAX;
-    double acc = 0.0;
-    int w = 0, uu = 0;
+    const bool g_per_w = T.g_per_w != 0;
     const double* __restrict__ gp = T.g + it.g_base + lane;
-    double gv = T.g_per_w ? 0.0 : __ldcs(gp);
+    LaneWalk ws;
+    ws.best_v = CUDART_INF; ws.best_i = INT_MAX; ws.acc = 0.0; ws.w = 0; ws.uu = 0;
+    ws.gv = 0.0; ws.gv_next = 0.0;
+    if (!g_per_w) {
+        ws.gv = __ldcs(gp);
+        if (it.u_count > 1) ws.gv_next = __ldcs(gp + 32);
+    }
 
     for (int s = 0; s < n_stages; ++s) {
         const int slot = s % S;
@@ -689,43 +803,41 @@ k_sweep_tiled_tma(GridT<double> G, SdpTables T, const double* __restrict__ Jprev
         const unsigned char* st = ring + (size_t)slot * stage_bytes;
         const int32_t* cs = reinterpret_cast<const int32_t*>(st) + lane;
         const double* ls = reinterpret_cast<const double*>(st + R * 128) + lane;
-        int c[R];
-        double l[R][D];
-        double gw[R];
+        if (rows == R) {                     // full stage: no per-row guards
+            int c[R];
+            double l[R][D];
+            double gw[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < rows) {
+            for (int r = 0; r < R; ++r) {
                 c[r] = cs[r * 32];
 #pragma unroll
                 for (int k = 0; k < D; ++k) l[r][k] = ls[k * R * 32 + r * 32];
-                gw[r] = T.g_per_w ? ls[D * R * 32 + r * 32] : 0.0;
+                gw[r] = g_per_w ? ls[D * R * 32 + r * 32] : 0.0;
             }
-        }
-        double v[R];
+            __syncwarp();                    // every lane has pulled its rows out of the slot
+            if (lane == 0 && s + S < n_stages) issue(s + S);
+            double v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (r < rows) v[r] = Lerp<double, D, 0>::eval(Jprev, c[r], G.stride, l[r]);
-        __syncwarp();                       // every lane has pulled its rows out of the slot
-        if (lane == 0 && s + S < n_stages) issue(s + S);
+            for (int r = 0; r < R; ++r) v[r] = Lerp<double, D, 0>::eval(Jprev, c[r], G.stride, l[r]);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < rows) {
-                const double jg = add_(T.g_per_w ? gw[r] : gv, v[r]);
-                if (T.expect) acc = add_(acc, mul_(jg, p_sh[w]));
-                else acc = jg;
-                if (++w == W) {
-                    const int u = it.u_begin + uu;
-                    if (u < Us && better(acc, u, best_v, best_i)) { best_v = acc; best_i = u; }
-                    w = 0;
-                    acc = 0.0;
-                    ++uu;
-                    if (!T.g_per_w && uu < it.u_count) gv = __ldcs(gp + (int64_t)uu * 32);
-                }
+            for (int r = 0; r < R; ++r)
+                walk_row(ws, add_(g_per_w ? gw[r] : ws.gv, v[r]), p_sh[ws.w], T.expect, W, it.u_begin,
+                         it.u_count, Us, g_per_w, gp);
+        } else {                             // last, partial stage
+            for (int r = 0; r < rows; ++r) {
+                const int c = cs[r * 32];
+                double l[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) l[k] = ls[k * R * 32 + r * 32];
+                const double gw = g_per_w ? ls[D * R * 32 + r * 32] : ws.gv;
+                const double v = Lerp<double, D, 0>::eval(Jprev, c, G.stride, l);
+                walk_row(ws, add_(gw, v), p_sh[ws.w], T.expect, W, it.u_begin, it.u_count, Us,
+                         g_per_w, gp);
             }
         }
     }
-    part_val[item_id * 32 + lane] = best_v;
-    part_idx[item_id * 32 + lane] = best_i;
+    part_val[item_id * 32 + lane] = ws.best_v;
+    part_idx[item_id * 32 + lane] = ws.best_i;
 }
 
 __global__ void __launch_bounds__(256)
@@ -756,7 +868,8 @@ k_sweep_finalize_tiled(int64_t n_states, const int64_t* __restrict__ item_begin,
 struct Tuning {
     int upl;      // layout A: controls per lane per iteration (2|4)
     int wb;       // layout B, LDG kernel: perturbation nodes batched (1|2|3|5)
-    int tma;      // layout B: 1 = TMA-fed kernel, 0 = LDG kernel
+    int tma;      // layout B: 0 = straight LDG kernel, 1 = TMA-fed kernel, 2 = software-pipelined LDG kernel
+    int rb;       // layout B, pipelined kernel: rows per group (2|4|8)
     int R, S, NW; // TMA ring: rows per stage (4|8), stages, warps per CTA
 };
 static int env_int(const char* name, int dflt) {
@@ -772,11 +885,17 @@ static Tuning& tuning() {
         // measured on B200 (profiles/): the tiled sweep is bound by L1 wavefronts
         // of the corner gathers, not by the HBM stream, and the LDG kernel's higher
         // occupancy hides the gather latency better than the TMA ring does
+        // measured on B200, config #5 (profiles/r1_tuning_tiled_kernels.txt): TMA ring
+        // R=8,S=2,NW=4 85.6 % of the HBM roofline, straight LDG 78 %, pipelined LDG 71 %
         const char* impl = getenv("SDP_TILED_IMPL");
-        x.tma = (impl && strcmp(impl, "tma") == 0) ? 1 : 0;
-        x.R = env_int("SDP_TMA_R", 4) == 8 ? 8 : 4;
-        x.S = env_int("SDP_TMA_S", 4);
-        x.NW = env_int("SDP_TMA_NW", 8);
+        x.tma = 1;
+        if (impl && strcmp(impl, "pipe") == 0) x.tma = 2;
+        if (impl && strcmp(impl, "ldg") == 0) x.tma = 0;
+        int rb = env_int("SDP_RB", 4);
+        x.rb = (rb == 2 || rb == 8) ? rb : 4;
+        x.R = env_int("SDP_TMA_R", 8) == 4 ? 4 : 8;
+        x.S = env_int("SDP_TMA_S", 2);
+        x.NW = env_int("SDP_TMA_NW", 4);
         return x;
     }();
     return t;
@@ -788,7 +907,8 @@ extern "C" int sdp_set_option(const char* name, int value) {
     Tuning& t = tuning();
     if (!strcmp(name, "upl")) t.upl = (value == 2) ? 2 : 4;
     else if (!strcmp(name, "wb")) t.wb = (value == 2 || value == 3 || value == 5) ? value : 1;
-    else if (!strcmp(name, "tma")) t.tma = value ? 1 : 0;
+    else if (!strcmp(name, "tma")) t.tma = clampi(value, 0, 2);
+    else if (!strcmp(name, "rb")) t.rb = (value == 2 || value == 8) ? value : 4;
     else if (!strcmp(name, "tma_rows")) t.R = (value == 8) ? 8 : 4;
     else if (!strcmp(name, "tma_stages")) t.S = value;
     else if (!strcmp(name, "tma_warps")) t.NW = value;
@@ -832,9 +952,18 @@ static int launch_sweep(const GridT<double>& G, const SdpTables& T, const double
     size_t shm = (size_t)T.W * sizeof(double);
     const Tuning t = tuning();
     if (T.layout == SDP_LAYOUT_STATE_MINOR) {
-        if (t.tma) {
+        if (t.tma == 2) {
+            switch (t.rb) {
+                case 2: k_sweep_tiled_pipe<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+                case 8: k_sweep_tiled_pipe<D, 8><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+                default: k_sweep_tiled_pipe<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
+            }
+            SDP_LAUNCH_CHECK();
+            return SDP_OK;
+        }
+        if (t.tma == 1) {
             bool launched = false;
-            const int S = clampi(t.S, 2, 16), NW = clampi(t.NW, 1, 16);
+            const int S = clampi(t.S, 2, 16), NW = clampi(t.NW, 1, 8);
             int rc = (t.R == 8)
                 ? launch_tiled_tma<D, 8>(G, T, Jprev, part_val, part_idx, st, S, NW, &launched)
                 : launch_tiled_tma<D, 4>(G, T, Jprev, part_val, part_idx, st, S, NW, &launched);
