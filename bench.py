@@ -287,7 +287,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
     e2e = {"value": total_backups * n_e2e / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": 8 * n_grid, "d2h_bytes_per_step": 12 * n_grid,
+           "h2d_bytes_per_step": int(J_h.nbytes), "d2h_bytes_per_step": int(J_h.nbytes + pol_h.nbytes),
            "steps": n_e2e, "ms_per_step": 1e3 * e2e_s / n_e2e,
            "api": "DPSolver.value_iteration(J_host) -> (J_host, pol_host)"}
 

@@ -616,3 +616,41 @@ def test_large_grid_sampled_against_port(cuda_api, port):
     # the greedy value never exceeds the value of the 'do nothing'-like first control
     Je = sv.eval_policy(pol, 1, J_zero=J0, report_time=False)
     assert np.max(np.abs(Je - J)) <= 1e-10 * np.max(np.abs(J))
+
+
+@gpu
+def test_layout_B_kernel_variants_are_bit_identical(product):
+    """straight LDG, TMA-fed ring (several ring shapes) and software-pipelined
+    kernels of the state-minor layout, and both lane widths of layout A, must
+    produce identical J and argmin"""
+    from stodynprog_b200 import workloads as wl, _cabi
+    lib = _cabi.load_library()
+
+    def opt(**kw):
+        for k, v in kw.items():
+            _cabi.check(lib.sdp_set_option(k.encode(), int(v)), "sdp_set_option")
+    try:
+        for layout, settings in (
+                ("state_minor", [dict(tma=0, wb=1), dict(tma=0, wb=3), dict(tma=2, rb=2), dict(tma=2, rb=4),
+                                 dict(tma=2, rb=8), dict(tma=1, tma_rows=8, tma_stages=2, tma_warps=4),
+                                 dict(tma=1, tma_rows=4, tma_stages=3, tma_warps=8),
+                                 dict(tma=1, tma_rows=8, tma_stages=5, tma_warps=2)]),
+                ("control_minor", [dict(upl=4), dict(upl=2)])):
+            for which in ("ar1", "toy3w", "searev"):
+                api = _Api(product, "cuda", layout)
+                if which == "ar1":
+                    sv = wl.storage_ar1(api, n_E=40, n_P=37, steps=(0.05, 0.1), item_chunk=48).solver
+                elif which == "toy3w":
+                    sv = _toy(api, 3, "w", item_chunk=8)
+                else:
+                    sv = _searev_small(api).solver
+                J0 = np.random.default_rng(4).standard_normal(sv._state_grid_shape)
+                ref = None
+                for st in settings:
+                    opt(**st)
+                    J, pol = sv.value_iteration(J0, report_time=False)
+                    if ref is None:
+                        ref = (J, pol)
+                    assert np.array_equal(J, ref[0]) and np.array_equal(pol, ref[1]), (layout, which, st)
+    finally:
+        opt(tma=1, tma_rows=8, tma_stages=2, tma_warps=4, rb=4, wb=1, upl=4)
