@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SDP_ABI_VERSION 1
+#define SDP_ABI_VERSION 2
 #define SDP_MAX_D 4 /* the reference dispatches d = 1..4 (multilinear_cython.pyx:36-47) */
 
 /* error codes */
@@ -90,6 +90,18 @@ typedef struct SdpItem {
 
 #define SDP_LAYOUT_CONTROL_MINOR 0 /* "A": [state][w][u], lane <-> control   */
 #define SDP_LAYOUT_STATE_MINOR 1   /* "B": [tile][u][w][32 states], lane <-> state */
+/* Factored ("broadcast-compressed") variants, SURVEY.md §8(f)4: every next-state
+ * coordinate depends either on (x,u) only or on (x,w) only and the stage cost
+ * does not depend on w - true of every reference example (E_next = E + P_sto*dt,
+ * P_next = a*P + w: examples/howto storage-AR1.ipynb:143; storage_control.py:49-65).
+ * The dense (x,u,w) tables are then an outer sum of a (x,u) part and a (x,w)
+ * part, which is what np.broadcast_arrays expands at stodynprog.py:281; the
+ * factored layouts keep the two parts and the sweep kernel forms
+ * cell = cell_u + cell_w and the weight vector on the fly.  Same arithmetic,
+ * same order, bit-identical results; HBM traffic drops by about W. */
+#define SDP_LAYOUT_CONTROL_MINOR_FACTORED 2 /* "AF": u-part [state][Upad], w-part [state][W] */
+#define SDP_LAYOUT_STATE_MINOR_FACTORED 3   /* "BF": u-part [tile][u][32], w-part [tile][w][32] */
+#define SDP_FACTORED_MAX_W_REG 9 /* BF keeps the w-part of a lane in registers: W <= 9 */
 
 /* Dense sweep tables of one shard of states (device pointers).
  *
@@ -109,7 +121,18 @@ typedef struct SdpItem {
  *   Best when neighbouring states land in neighbouring cells (many states, few
  *   controls): the corner loads of a warp are contiguous.
  *
- * Algorithmic bytes per admissible (x,u,w): 4 + 8*d + 8*(g_per_w ? 1 : 1/W). */
+ * Algorithmic bytes per admissible (x,u,w): 4 + 8*d + 8*(g_per_w ? 1 : 1/W).
+ *
+ * Factored layouts (g_per_w == 0; n_u = popcount(u_mask), n_w = d - n_u, both >= 1):
+ *   u-part, entry e = entry_off + u (AF, per state, Upad entries)
+ *                   = tile_off + u*32 + lane (BF, per tile, U_t*32 entries):
+ *     cell [e]                    sum over u-type coordinates k of q_k*M_k
+ *     lam  [j*lam_plane + e]      weight of the j-th u-type coordinate (increasing k)
+ *     g    [e]                    stage cost
+ *   w-part, entry f = state*W + w (AF) = (tile*W + w)*32 + lane (BF):
+ *     cell_w[f], lam_w[j*lam_w_plane + f]   same for the w-type coordinates
+ *   Items: entry_base = g_base = first u-part entry of the run.
+ *   Actual bytes per (x,u,w): (12 + 8*n_u)/W + (4 + 8*n_w)/U(x). */
 typedef struct SdpTables {
     const int32_t* cell;
     const double* lam;
@@ -125,6 +148,12 @@ typedef struct SdpTables {
     const int64_t* item_begin; /* A: [n_states+1], B: [n_tiles+1]: items of unit i are item_begin[i]..item_begin[i+1]-1 */
     int64_t n_states;    /* states in this shard */
     const int32_t* U;    /* [n_states] admissible controls per state (layout B masking) */
+    /* factored layouts only */
+    int32_t u_mask;        /* bit k set: coordinate k depends on (x,u) only; clear: on (x,w) only */
+    int32_t reserved;
+    const int32_t* cell_w;
+    const double* lam_w;
+    int64_t lam_w_plane;
 } SdpTables;
 
 /* ABI / build identification. */
@@ -164,6 +193,25 @@ int sdp_build_tables_tiled(const SdpGrid* grid, int32_t W, int32_t g_per_w, int6
                            const int64_t* tile_off, const int64_t* tile_g_off,
                            const int32_t* tile_U, int32_t max_tile_U, int32_t* cell,
                            double* lam, int64_t lam_plane, double* g, void* stream);
+
+/* Factored layouts: the same expansion, kept as a (x,u) part and a (x,w) part.
+ * Coordinate k of entry (u) is read at w index 0 when bit k of u_mask is set,
+ * coordinate k of entry (w) at flat control index 0 otherwise; g at w index 0.
+ * The caller guarantees (and checks on the descriptors) that the staged arrays
+ * do not depend on the other index.  cell_w / lam_w point at the w-part of the
+ * chunk's first state (AF) or first tile (BF).
+ * AF: desc[i].entry_off = first u-part entry of state i, Upad entries. */
+int sdp_build_tables_factored(const SdpGrid* grid, int32_t W, int32_t u_mask, int64_t n_states,
+                              const SdpStateDesc* desc, const double* staging, int32_t* cell,
+                              double* lam, int64_t lam_plane, double* g, int32_t max_Upad,
+                              int32_t* cell_w, double* lam_w, int64_t lam_w_plane, void* stream);
+/* BF: tile_off[t] = first u-part entry of tile t of the chunk, tile_U[t] = max U. */
+int sdp_build_tables_factored_tiled(const SdpGrid* grid, int32_t W, int32_t u_mask, int64_t n_states,
+                                    const SdpStateDesc* desc, const double* staging, int64_t n_tiles,
+                                    const int64_t* tile_off, const int32_t* tile_U,
+                                    int32_t max_tile_U, int32_t* cell, double* lam,
+                                    int64_t lam_plane, double* g, int32_t* cell_w, double* lam_w,
+                                    int64_t lam_w_plane, void* stream);
 
 /* K1 - one Bellman sweep over a shard of states.
  * Replaces the state loop of DPSolver.value_iteration (stodynprog.py:511-515)

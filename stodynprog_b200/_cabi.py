@@ -12,9 +12,13 @@ import numpy as np
 
 SDP_MAX_D = 4
 SDP_MAX_C = 4
-SDP_ABI_VERSION = 1
+SDP_ABI_VERSION = 2
 LAYOUT_CONTROL_MINOR = 0   # "A": [state][w][u]
 LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
+LAYOUT_CONTROL_MINOR_FACTORED = 2   # "AF": (x,u) part [state][Upad] + (x,w) part [state][W]
+LAYOUT_STATE_MINOR_FACTORED = 3     # "BF": (x,u) part [tile][u][lane] + (x,w) part [tile][w][lane]
+FACTORED_MAX_W_REG = 9     # BF keeps a lane's w-part in registers
+FACTORED_MAX_W_SMEM = 128  # AF keeps a state's w-part in shared memory
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsdp_b200.so")
@@ -45,7 +49,12 @@ class SdpTables(ctypes.Structure):
                 ("n_items", ctypes.c_int64),
                 ("item_begin", ctypes.c_void_p),
                 ("n_states", ctypes.c_int64),
-                ("U", ctypes.c_void_p)]
+                ("U", ctypes.c_void_p),
+                ("u_mask", ctypes.c_int32),
+                ("reserved", ctypes.c_int32),
+                ("cell_w", ctypes.c_void_p),
+                ("lam_w", ctypes.c_void_p),
+                ("lam_w_plane", ctypes.c_int64)]
 
 
 # numpy mirrors of the per-state descriptor and the work item (host-built arrays
@@ -83,6 +92,10 @@ SIGNATURES = {
                                         _i32, _vp]),
     "sdp_build_tables_tiled": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _vp,
                                               _i32, _vp, _vp, _i64, _vp, _vp]),
+    "sdp_build_tables_factored": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp,
+                                                 _i32, _vp, _vp, _i64, _vp]),
+    "sdp_build_tables_factored_tiled": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _vp,
+                                                       _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "sdp_sweep": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdp_sweep_partials": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp]),
     "sdp_sweep_finalize": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp]),

@@ -369,6 +369,153 @@ extern "C" int sdp_build_tables_tiled(const SdpGrid* grid, int32_t W, int32_t g_
     return SDP_OK;
 }
 
+
+// Factored layouts: the (x,u) part and the (x,w) part of the same expansion.
+// Coordinate k of a u entry is read at w index 0, of a w entry at flat control
+// index 0 (the host has checked that the staged arrays do not depend on the
+// other index), so every value is one the dense build would also have produced.
+template <int D>
+__device__ __forceinline__ void build_part(const GridT<double>& G, const SdpStateDesc* ds, bool live,
+                                           int mask_sel, int u, int w,
+                                           const double* __restrict__ staging,
+                                           int32_t* __restrict__ cell, double* __restrict__ lam,
+                                           int64_t plane, int64_t off) {
+    int base = 0, j = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        if (!((mask_sel >> k) & 1)) continue;
+        double l = 0.0;
+        if (live) {
+            int q;
+            cell_1d<double>(staging[src_offset(ds, k, u, w)], G.smin[k], G.span[k], G.om1[k], G.order[k], q, l);
+            base += q * G.stride[k];
+        }
+        lam[(int64_t)j * plane + off] = l;
+        ++j;
+    }
+    cell[off] = base;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_build_factored(GridT<double> G, int W, int u_mask, int tiles_per_state,
+                 const SdpStateDesc* __restrict__ desc, const double* __restrict__ staging,
+                 int32_t* __restrict__ cell, double* __restrict__ lam, int64_t lam_plane,
+                 double* __restrict__ g, int32_t* __restrict__ cell_w, double* __restrict__ lam_w,
+                 int64_t lam_w_plane) {
+    const int64_t state = blockIdx.x / tiles_per_state;
+    const int tile = blockIdx.x % tiles_per_state;
+    const SdpStateDesc* ds = desc + state;
+    const int e = tile * blockDim.x + threadIdx.x;
+    const int w_mask = ~u_mask & ((1 << D) - 1);
+    if (e < ds->Upad) {
+        const bool live = e < ds->U;
+        const int64_t off = ds->entry_off + e;
+        build_part<D>(G, ds, live, u_mask, e, 0, staging, cell, lam, lam_plane, off);
+        g[off] = live ? staging[src_offset(ds, D, e, 0)] : 0.0;
+    } else {
+        const int w = e - ds->Upad;
+        if (w >= W) return;
+        build_part<D>(G, ds, true, w_mask, 0, w, staging, cell_w, lam_w, lam_w_plane, state * W + w);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_build_factored_tiled(GridT<double> G, int W, int u_mask, int blocks_per_tile, int64_t n_states,
+                       const SdpStateDesc* __restrict__ desc, const double* __restrict__ staging,
+                       const int64_t* __restrict__ tile_off, const int32_t* __restrict__ tile_U,
+                       int32_t* __restrict__ cell, double* __restrict__ lam, int64_t lam_plane,
+                       double* __restrict__ g, int32_t* __restrict__ cell_w,
+                       double* __restrict__ lam_w, int64_t lam_w_plane) {
+    const int64_t tile = blockIdx.x / blocks_per_tile;
+    const int blk = blockIdx.x % blocks_per_tile;
+    const int Ut = tile_U[tile];
+    const int e = blk * blockDim.x + threadIdx.x;
+    if (e >= (Ut + W) * 32) return;
+    const int lane = e & 31;
+    const int r = e >> 5;
+    const int64_t state = tile * 32 + lane;
+    const bool in_range = state < n_states;
+    const SdpStateDesc* ds = desc + (in_range ? state : 0);
+    const int w_mask = ~u_mask & ((1 << D) - 1);
+    if (r < Ut) {
+        const bool live = in_range && r < ds->U;
+        const int64_t off = tile_off[tile] + e;
+        build_part<D>(G, ds, live, u_mask, r, 0, staging, cell, lam, lam_plane, off);
+        g[off] = live ? staging[src_offset(ds, D, r, 0)] : 0.0;
+    } else {
+        const int w = r - Ut;
+        build_part<D>(G, ds, in_range, w_mask, 0, w, staging, cell_w, lam_w, lam_w_plane,
+                      (tile * W + w) * 32 + lane);
+    }
+}
+
+static int check_factored_args(int d, int W, int u_mask, const char* who) {
+    const int full = (1 << d) - 1;
+    if (d < 2 || d > 3) return fail(SDP_EINVAL, "%s: factored tables need 2 or 3 state variables", who);
+    if (W < 1 || u_mask <= 0 || u_mask >= full)
+        return fail(SDP_EINVAL, "%s: u_mask must select at least one and not all coordinates", who);
+    return SDP_OK;
+}
+
+extern "C" int sdp_build_tables_factored(const SdpGrid* grid, int32_t W, int32_t u_mask, int64_t n_states,
+                                         const SdpStateDesc* desc, const double* staging, int32_t* cell,
+                                         double* lam, int64_t lam_plane, double* g, int32_t max_Upad,
+                                         int32_t* cell_w, double* lam_w, int64_t lam_w_plane,
+                                         void* stream) {
+    GridT<double> G;
+    int rc = make_grid<double>(grid, &G, nullptr);
+    if (rc) return rc;
+    rc = check_factored_args(grid->d, W, u_mask, "sdp_build_tables_factored");
+    if (rc) return rc;
+    if (n_states < 0 || max_Upad < 0 || (max_Upad & 3))
+        return fail(SDP_EINVAL, "%s", "sdp_build_tables_factored: bad sizes");
+    if (n_states == 0) return SDP_OK;
+    if (!desc || !staging || !cell || !lam || !g || !cell_w || !lam_w)
+        return fail(SDP_EINVAL, "%s", "sdp_build_tables_factored: NULL pointer");
+    int tiles = (int)(((int64_t)max_Upad + W + 255) / 256);
+    int64_t blocks = n_states * tiles;
+    if (blocks > 0x7fffffffLL) return fail(SDP_EINVAL, "%s", "sdp_build_tables_factored: chunk too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grid->d == 2)
+        k_build_factored<2><<<(unsigned)blocks, 256, 0, st>>>(G, W, u_mask, tiles, desc, staging, cell, lam, lam_plane, g, cell_w, lam_w, lam_w_plane);
+    else
+        k_build_factored<3><<<(unsigned)blocks, 256, 0, st>>>(G, W, u_mask, tiles, desc, staging, cell, lam, lam_plane, g, cell_w, lam_w, lam_w_plane);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+extern "C" int sdp_build_tables_factored_tiled(const SdpGrid* grid, int32_t W, int32_t u_mask,
+                                               int64_t n_states, const SdpStateDesc* desc,
+                                               const double* staging, int64_t n_tiles,
+                                               const int64_t* tile_off, const int32_t* tile_U,
+                                               int32_t max_tile_U, int32_t* cell, double* lam,
+                                               int64_t lam_plane, double* g, int32_t* cell_w,
+                                               double* lam_w, int64_t lam_w_plane, void* stream) {
+    GridT<double> G;
+    int rc = make_grid<double>(grid, &G, nullptr);
+    if (rc) return rc;
+    rc = check_factored_args(grid->d, W, u_mask, "sdp_build_tables_factored_tiled");
+    if (rc) return rc;
+    if (n_states < 0 || n_tiles < 0 || max_tile_U < 0 || n_states > 32 * n_tiles)
+        return fail(SDP_EINVAL, "%s", "sdp_build_tables_factored_tiled: bad sizes");
+    if (n_states == 0) return SDP_OK;
+    if (!desc || !staging || !tile_off || !tile_U || !cell || !lam || !g || !cell_w || !lam_w)
+        return fail(SDP_EINVAL, "%s", "sdp_build_tables_factored_tiled: NULL pointer");
+    int64_t per_tile = ((int64_t)max_tile_U + W) * 32;
+    int bpt = (int)((per_tile + 255) / 256);
+    int64_t blocks = n_tiles * bpt;
+    if (blocks > 0x7fffffffLL) return fail(SDP_EINVAL, "%s", "sdp_build_tables_factored_tiled: chunk too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grid->d == 2)
+        k_build_factored_tiled<2><<<(unsigned)blocks, 256, 0, st>>>(G, W, u_mask, bpt, n_states, desc, staging, tile_off, tile_U, cell, lam, lam_plane, g, cell_w, lam_w, lam_w_plane);
+    else
+        k_build_factored_tiled<3><<<(unsigned)blocks, 256, 0, st>>>(G, W, u_mask, bpt, n_states, desc, staging, tile_off, tile_U, cell, lam, lam_plane, g, cell_w, lam_w, lam_w_plane);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
 // ---------------------------------------------------------------------------
 // K1: Bellman sweep
 // ---------------------------------------------------------------------------
@@ -983,6 +1130,246 @@ static int launch_sweep(const GridT<double>& G, const SdpTables& T, const double
     return SDP_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// Factored sweeps (layouts AF / BF): cell = cell_u + cell_w, the weight vector
+// is merged from the u-part and the w-part in coordinate order, so the nested
+// lerp sees exactly the operands the dense tables would have held.
+// ---------------------------------------------------------------------------
+template <int D, int MASK>
+struct Fact {
+    static constexpr int NU = ((MASK >> 0) & 1) + ((MASK >> 1) & 1) + ((MASK >> 2) & 1) + ((MASK >> 3) & 1);
+    static constexpr int NW = D - NU;
+    __device__ __forceinline__ static void merge(double (&lam)[D], const double (&lu)[NU], const double (&lw)[NW]) {
+        int ju = 0, jw = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if ((MASK >> k) & 1) lam[k] = lu[ju++];
+            else lam[k] = lw[jw++];
+        }
+    }
+};
+
+// AF: one warp per run of controls of one state, lane <-> UPL consecutive
+// controls; the state's w-part (W entries, warp-uniform) sits in shared memory.
+template <int D, int MASK, int UPL>
+__global__ void __launch_bounds__(256)
+k_sweep_fact(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+             double* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+    constexpr int NU = Fact<D, MASK>::NU, NW = Fact<D, MASK>::NW;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int W = T.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double* p_sh = reinterpret_cast<double*>(fsm);
+    double* lw_sh = p_sh + W + (size_t)warp * NW * W;                       // [NW][W] of this warp
+    int* cw_sh = reinterpret_cast<int*>(p_sh + W + (size_t)nwarps * NW * W) + warp * W;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) p_sh[i] = T.expect ? T.p[i] : 1.0;
+    __syncthreads();
+
+    const int64_t item_id = (int64_t)blockIdx.x * nwarps + warp;
+    if (item_id >= T.n_items) return;
+    const SdpItem it = T.items[item_id];
+    for (int w = lane; w < W; w += 32) {
+        const int64_t f = (int64_t)it.state * W + w;
+        cw_sh[w] = __ldg(T.cell_w + f);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) lw_sh[j * W + w] = __ldg(T.lam_w + (int64_t)j * T.lam_w_plane + f);
+    }
+    __syncwarp();
+
+    double best_v = CUDART_INF;
+    int best_i = INT_MAX;
+    for (int u0 = lane * UPL; u0 < it.u_count; u0 += 32 * UPL) {
+        const int64_t off = it.entry_base + u0;
+        int cu[UPL];
+        double lu[UPL][NU], gv[UPL], acc[UPL];
+        {
+            Frag<NU, UPL> f;
+            load_frag<NU, UPL>(f, T.cell, T.lam, T.lam_plane, off);
+            load_g<UPL>(gv, T.g, off);
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) {
+                cu[j] = f.cell[j];
+                acc[j] = 0.0;
+#pragma unroll
+                for (int k = 0; k < NU; ++k) lu[j][k] = f.lam[k][j];
+            }
+        }
+#pragma unroll 3
+        for (int w = 0; w < W; ++w) {
+            const int cw = cw_sh[w];
+            const double pw = p_sh[w];
+            double lw[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) lw[k] = lw_sh[k * W + w];
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) {
+                double lam[D];
+                Fact<D, MASK>::merge(lam, lu[j], lw);
+                const double v = Lerp<double, D, 0>::eval(Jprev, cu[j] + cw, G.stride, lam);
+                const double jg = add_(gv[j], v);
+                if (T.expect) acc[j] = add_(acc[j], mul_(jg, pw));
+                else acc[j] = jg;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) {
+            const int u = u0 + j;
+            if (u < it.u_count) {
+                const int idx = it.u_begin + u;
+                if (better(acc[j], idx, best_v, best_i)) { best_v = acc[j]; best_i = idx; }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best_v, s);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, s);
+        if (better(ov, oi, best_v, best_i)) { best_v = ov; best_i = oi; }
+    }
+    if (lane == 0) {
+        part_val[item_id] = best_v;
+        part_idx[item_id] = best_i;
+    }
+}
+
+// BF: lane <-> state of a 32-state tile; the lane's w-part (W <= 9 entries)
+// lives in registers, the u-part is streamed one control ahead.
+template <int D, int MASK>
+__global__ void __launch_bounds__(128)
+k_sweep_fact_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+                   double* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+    constexpr int NU = Fact<D, MASK>::NU, NW = Fact<D, MASK>::NW;
+    constexpr int WM = SDP_FACTORED_MAX_W_REG;
+    extern __shared__ double p_sh[];
+    for (int i = threadIdx.x; i < T.W; i += blockDim.x) p_sh[i] = T.expect ? T.p[i] : 1.0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t item_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item_id >= T.n_items) return;
+    const SdpItem it = T.items[item_id];
+    const int W = T.W;
+    const int64_t state = (int64_t)it.state * 32 + lane;
+    const int Us = (state < T.n_states) ? T.U[state] : 0;
+
+    int cw[WM];
+    double lw[WM][NW];
+#pragma unroll
+    for (int w = 0; w < WM; ++w) {
+        cw[w] = 0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) lw[w][k] = 0.0;
+        if (w < W) {
+            const int64_t f = ((int64_t)it.state * W + w) * 32 + lane;
+            cw[w] = __ldg(T.cell_w + f);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) lw[w][k] = __ldg(T.lam_w + (int64_t)k * T.lam_w_plane + f);
+        }
+    }
+
+    const int32_t* __restrict__ cup = T.cell + it.entry_base + lane;
+    const double* __restrict__ lup = T.lam + it.entry_base + lane;
+    const double* __restrict__ gp = T.g + it.g_base + lane;
+    double best_v = CUDART_INF;
+    int best_i = INT_MAX;
+
+    int c_n = __ldcs(cup);
+    double g_n = __ldcs(gp);
+    double l_n[NU];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) l_n[k] = __ldcs(lup + (int64_t)k * T.lam_plane);
+
+    for (int uu = 0; uu < it.u_count; ++uu) {
+        const int cu = c_n;
+        const double gv = g_n;
+        double lu[NU];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) lu[k] = l_n[k];
+        if (uu + 1 < it.u_count) {
+            const int64_t o = (int64_t)(uu + 1) * 32;
+            c_n = __ldcs(cup + o);
+            g_n = __ldcs(gp + o);
+#pragma unroll
+            for (int k = 0; k < NU; ++k) l_n[k] = __ldcs(lup + (int64_t)k * T.lam_plane + o);
+        }
+        double v[WM];
+#pragma unroll
+        for (int w = 0; w < WM; ++w) {
+            if (w < W) {
+                double lam[D];
+                Fact<D, MASK>::merge(lam, lu, lw[w]);
+                v[w] = Lerp<double, D, 0>::eval(Jprev, cu + cw[w], G.stride, lam);
+            }
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < WM; ++w) {
+            if (w < W) {
+                const double jg = add_(gv, v[w]);
+                if (T.expect) acc = add_(acc, mul_(jg, p_sh[w]));
+                else acc = jg;
+            }
+        }
+        const int u = it.u_begin + uu;
+        if (u < Us && better(acc, u, best_v, best_i)) { best_v = acc; best_i = u; }
+    }
+    part_val[item_id * 32 + lane] = best_v;
+    part_idx[item_id * 32 + lane] = best_i;
+}
+
+template <int D, int MASK>
+static int launch_fact_m(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                         double* part_val, int32_t* part_idx, cudaStream_t st) {
+    if (T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED) {
+        const int warps = 4;
+        unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
+        k_sweep_fact_tiled<D, MASK><<<blocks, warps * 32, (size_t)T.W * sizeof(double), st>>>(
+            G, T, Jprev, part_val, part_idx);
+    } else {
+        const int warps = 8;
+        constexpr int NW = Fact<D, MASK>::NW;
+        unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
+        size_t shm = (size_t)T.W * 8 + (size_t)warps * T.W * (8 * NW + 4);
+        if (tuning().upl == 2)
+            k_sweep_fact<D, MASK, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
+        else
+            k_sweep_fact<D, MASK, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
+    }
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+template <int D>
+static int launch_fact(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                       double* part_val, int32_t* part_idx, cudaStream_t st);
+template <>
+int launch_fact<2>(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                   double* part_val, int32_t* part_idx, cudaStream_t st) {
+    switch (T.u_mask) {
+        case 1: return launch_fact_m<2, 1>(G, T, Jprev, part_val, part_idx, st);
+        default: return launch_fact_m<2, 2>(G, T, Jprev, part_val, part_idx, st);
+    }
+}
+template <>
+int launch_fact<3>(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                   double* part_val, int32_t* part_idx, cudaStream_t st) {
+    switch (T.u_mask) {
+        case 1: return launch_fact_m<3, 1>(G, T, Jprev, part_val, part_idx, st);
+        case 2: return launch_fact_m<3, 2>(G, T, Jprev, part_val, part_idx, st);
+        case 3: return launch_fact_m<3, 3>(G, T, Jprev, part_val, part_idx, st);
+        case 4: return launch_fact_m<3, 4>(G, T, Jprev, part_val, part_idx, st);
+        case 5: return launch_fact_m<3, 5>(G, T, Jprev, part_val, part_idx, st);
+        default: return launch_fact_m<3, 6>(G, T, Jprev, part_val, part_idx, st);
+    }
+}
+
+static inline bool is_tiled(const SdpTables& T) {
+    return T.layout == SDP_LAYOUT_STATE_MINOR || T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED;
+}
+static inline bool is_factored(const SdpTables& T) {
+    return T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED || T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED;
+}
 static int check_tables(const SdpTables& T, const char* who) {
     if (T.W < 1 || T.W > 4096 || T.n_states < 0 || T.n_items < 0)
         return fail(SDP_EINVAL, "%s: bad sizes", who);
@@ -991,10 +1378,18 @@ static int check_tables(const SdpTables& T, const char* who) {
         return fail(SDP_EINVAL, "%s: NULL pointer in tables", who);
     if ((T.lam_plane & 3) || ((uintptr_t)T.cell & 15) || ((uintptr_t)T.lam & 15) || ((uintptr_t)T.g & 15))
         return fail(SDP_EINVAL, "%s: tables must be 16-byte aligned, lam_plane % 4 == 0", who);
-    if (T.layout != SDP_LAYOUT_CONTROL_MINOR && T.layout != SDP_LAYOUT_STATE_MINOR)
+    if (T.layout < SDP_LAYOUT_CONTROL_MINOR || T.layout > SDP_LAYOUT_STATE_MINOR_FACTORED)
         return fail(SDP_EINVAL, "%s: unknown table layout", who);
-    if (T.layout == SDP_LAYOUT_STATE_MINOR && !T.U)
+    if (is_tiled(T) && !T.U)
         return fail(SDP_EINVAL, "%s: layout B needs the per-state control counts", who);
+    if (is_factored(T)) {
+        if (T.g_per_w || !T.cell_w || !T.lam_w)
+            return fail(SDP_EINVAL, "%s: factored tables need g per (x,u) and a w-part", who);
+        if (T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED && T.W > SDP_FACTORED_MAX_W_REG)
+            return fail(SDP_EINVAL, "%s: layout BF supports at most 9 perturbation nodes", who);
+        if (T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED && T.W > 128)
+            return fail(SDP_EINVAL, "%s: layout AF supports at most 128 perturbation nodes", who);
+    }
     if (T.n_items / 8 + 1 > 0x7fffffffLL) return fail(SDP_EINVAL, "%s: too many items", who);
     return SDP_OK;
 }
@@ -1011,6 +1406,12 @@ extern "C" int sdp_sweep_partials(const SdpGrid* grid, const SdpTables* tab, con
     if (T.n_states == 0 || T.n_items == 0) return SDP_OK;
     if (!J_prev || !part_val || !part_idx) return fail(SDP_EINVAL, "%s", "sdp_sweep: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (is_factored(T)) {
+        rc = check_factored_args(grid->d, T.W, T.u_mask, "sdp_sweep");
+        if (rc) return rc;
+        return grid->d == 2 ? launch_fact<2>(G, T, J_prev, part_val, part_idx, st)
+                            : launch_fact<3>(G, T, J_prev, part_val, part_idx, st);
+    }
     switch (grid->d) {
         case 1: return launch_sweep<1>(G, T, J_prev, part_val, part_idx, st);
         case 2: return launch_sweep<2>(G, T, J_prev, part_val, part_idx, st);
@@ -1031,7 +1432,7 @@ extern "C" int sdp_sweep_finalize(const SdpTables* tab, const double* part_val,
         return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned blocks = (unsigned)((T.n_states + 255) / 256);
-    if (T.layout == SDP_LAYOUT_STATE_MINOR)
+    if (is_tiled(T))
         k_sweep_finalize_tiled<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
     else
         k_sweep_finalize<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);

@@ -140,6 +140,9 @@ class SweepTables(object):
         self.n_backups_total = 0
         self.c_tables = None       # _cabi.SdpTables
         self.tiled = False         # layout B (state-minor) when True
+        self.u_mask = 0            # factored layouts: coordinates of the (x,u) part; 0 = dense
+        self.cell_w = self.lam_w = None
+        self.lam_w_plane = 0
         self.U_dev = None
         self.tabulate_mode = None
         self.setup_seconds = 0.0
@@ -151,12 +154,25 @@ class SweepTables(object):
         return 4.0 + 8.0 * self.d + 8.0 * kappa
 
     @property
+    def factored(self):
+        return self.u_mask != 0
+
+    @property
+    def layout_name(self):
+        return ("state_minor" if self.tiled else "control_minor") + ("_factored" if self.u_mask else "")
+
+    @property
     def device_bytes(self):
         n = 0
-        for t in (self.cell, self.lam, self.g, self.items, self.item_begin):
+        for t in (self.cell, self.lam, self.g, self.items, self.item_begin, self.cell_w, self.lam_w):
             if t is not None:
                 n += t.numel() * t.element_size()
         return n
+
+    @property
+    def streamed_bytes_per_backup(self):
+        """bytes of table the sweep kernel actually reads per admissible (x,u,w)"""
+        return self.device_bytes / max(self.n_backups_local, 1)
 
 
 class PolicyTables(object):
@@ -237,8 +253,9 @@ class Engine(object):
         recycled when the sizes match (time-dependent recursion).
 
         Solver knobs read here:
-          solver.table_layout : "auto" | "control_minor" (A) | "state_minor" (B)
-          solver.tabulate     : "auto" | "per_state" | "batched"
+          solver.table_layout   : "auto" | "control_minor" (A) | "state_minor" (B)
+          solver.table_compress : "auto" | "off" | "on"  (factored (x,u) + (x,w) tables)
+          solver.tabulate       : "auto" | "per_state" | "batched"
         """
         import time
         torch = _torch()
@@ -293,36 +310,53 @@ class Engine(object):
             mean_U = float(U.mean()) if n else 0.0
             layout = "state_minor" if (n >= 32 * 1024 and mean_U <= 1024) else "control_minor"
         tiled = layout == "state_minor"
-        if tiled:
-            n_tiles = (n + 31) // 32
-            Upad_t = np.zeros(n_tiles * 32, dtype=np.int64)
-            Upad_t[:n] = U
-            tile_U = Upad_t.reshape(n_tiles, 32).max(axis=1)
-            tile_off = np.zeros(n_tiles + 1, dtype=np.int64)
-            np.cumsum(tile_U * W * 32, out=tile_off[1:])
-            n_entries = int(tile_off[-1])
-            entry_off = np.zeros(n + 1, dtype=np.int64)      # unused by layout B
-            Upad = np.zeros(n, dtype=np.int64)
-        else:
+        w_grid = [np.asarray(g) for g in solver.perturb_grid]
+
+        # factored ("broadcast-compressed") tables when every next-state coordinate
+        # depends on (x,u) only or on (x,w) only and g does not depend on w; probed on
+        # the slab's state with most controls, then checked on every staged chunk
+        compress = getattr(solver, "table_compress", "auto")
+        u_mask = 0
+        w_cap = _cabi.FACTORED_MAX_W_REG if tiled else _cabi.FACTORED_MAX_W_SMEM
+        if (compress != "off" and n > 0 and nb_perturb == 1 and 1 < W <= w_cap and d in (2, 3)
+                and nb_control <= _cabi.SDP_MAX_C):
+            i_probe = int(np.argmax(U))
+            x_probe = tb.state_tuples(state_grid, sb + i_probe, sb + i_probe + 1)[0]
+            u_mask = tb.probe_factor_mask(sys, x_probe, host, i_probe, w_grid, t_k) or 0
+        if compress == "on" and not u_mask:
+            raise ValueError("table_compress='on' but the system's dyn/cost do not have the "
+                             "(x,u) + (x,w) structure (or d, W are outside the supported range)")
+        if world > 1:
+            # all ranks must agree (they run the same kernels on the same layout)
+            u_mask = min(coll.all_gather_object(u_mask))
+
+        def sizes(u_mask):
+            """entry offsets of the layout: dense tables have W entries per control,
+            factored tables one"""
+            Wf = 1 if u_mask else W
+            if tiled:
+                n_tiles = (n + 31) // 32
+                Upad_t = np.zeros(n_tiles * 32, dtype=np.int64)
+                Upad_t[:n] = U
+                tile_U = Upad_t.reshape(n_tiles, 32).max(axis=1)
+                tile_off = np.zeros(n_tiles + 1, dtype=np.int64)
+                np.cumsum(tile_U * Wf * 32, out=tile_off[1:])
+                return (n_tiles, tile_U, tile_off, int(tile_off[-1]), np.zeros(n + 1, dtype=np.int64),
+                        np.zeros(n, dtype=np.int64))
             Upad = (U + 3) // 4 * 4
             entry_off = np.zeros(n + 1, dtype=np.int64)
-            np.cumsum(W * Upad, out=entry_off[1:])
-            n_entries = int(entry_off[-1])
-        lam_plane = (n_entries + 3) // 4 * 4
+            np.cumsum(Wf * Upad, out=entry_off[1:])
+            return 0, None, None, int(entry_off[-1]), entry_off, Upad
 
-        T = reuse if (reuse is not None and reuse.n_entries == n_entries and reuse.W == W
-                      and reuse.d == d and reuse.tiled == tiled) else SweepTables()
+        T = reuse if (reuse is not None and reuse.W == W and reuse.d == d and reuse.tiled == tiled) \
+            else SweepTables()
         T.grid, T.d, T.W = grid, d, W
         T.tiled = tiled
         T.expect = 1 if nb_perturb == 1 else 0
         T.bounds, T.state_begin, T.n_states = bounds, sb, n
         T.host_full = host_full
-        T.n_entries, T.lam_plane = n_entries, lam_plane
         T.n_backups_local = int(U.sum()) * W
         T.n_backups_total = int(U_all.sum()) * W
-        if T.cell is None:
-            T.cell = torch.empty(max(lam_plane, 4), dtype=torch.int32, device=dev)
-            T.lam = torch.empty(max(lam_plane, 4) * d, dtype=torch.float64, device=dev)
         if nb_perturb == 1:
             T.p = self.to_device(np.asarray(solver.perturb_proba[0], dtype=float))
         else:
@@ -333,12 +367,41 @@ class Engine(object):
         T.hi_dev = self.to_device(host_full.hi.reshape(-1)) if nb_control else None
         T.npts_dev = self.to_device(host_full.npts.astype(np.int32).reshape(-1)) if nb_control else None
         T.nb_control = nb_control
-        w_grid = [np.asarray(g) for g in solver.perturb_grid]
         mode = getattr(solver, "tabulate", "auto")
         T.tabulate_mode = None
 
-        def build(g_per_w, batched):
-            if tiled:
+        def ensure(name, numel, dtype):
+            """(re)allocate T.<name> only when the size changes (time-dependent
+            recursions rebuild same-sized tables at every instant)"""
+            t = getattr(T, name)
+            if t is None or t.numel() != numel or t.dtype != dtype:
+                setattr(T, name, None)        # release before allocating the new size
+                setattr(T, name, torch.empty(numel, dtype=dtype, device=dev))
+
+        def build(g_per_w, batched, u_mask):
+            L = {"u_mask": u_mask}
+            n_tiles, tile_U, tile_off, n_entries, entry_off, Upad = sizes(u_mask)
+            lam_plane = (n_entries + 3) // 4 * 4
+            n_u = bin(u_mask).count("1")
+            L.update(n_tiles=n_tiles, tile_U=tile_U, tile_off=tile_off, n_entries=n_entries,
+                     entry_off=entry_off, Upad=Upad, lam_plane=lam_plane)
+            ensure("cell", max(lam_plane, 4), torch.int32)
+            ensure("lam", max(lam_plane, 4) * (n_u if u_mask else d), torch.float64)
+            if u_mask:
+                n_wp = (n_tiles * 32 if tiled else n) * W
+                lam_w_plane = (n_wp + 3) // 4 * 4
+                ensure("cell_w", max(lam_w_plane, 4), torch.int32)
+                ensure("lam_w", max(lam_w_plane, 4) * (d - n_u), torch.float64)
+            else:
+                T.cell_w = T.lam_w = None
+                lam_w_plane = 0
+            L["lam_w_plane"] = lam_w_plane
+            tile_g_off = None
+            if u_mask:
+                # one g per (x,u) entry, indexed like the u-part
+                g_off, g_len = entry_off, n_entries
+                tile_g_off = tile_off
+            elif tiled:
                 if g_per_w:
                     tile_g_off = tile_off
                 else:
@@ -346,23 +409,24 @@ class Engine(object):
                     np.cumsum(tile_U * 32, out=tile_g_off[1:])
                 g_off = np.zeros(n + 1, dtype=np.int64)
                 g_len = int(tile_g_off[-1])
-                tile_off_dev = self.to_device(tile_off)
-                tile_g_off_dev = self.to_device(tile_g_off)
-                tile_U_dev = self.to_device(tile_U.astype(np.int32))
             else:
-                tile_g_off = None
                 if g_per_w:
                     g_off = entry_off
                 else:
                     g_off = np.zeros(n + 1, dtype=np.int64)
                     np.cumsum(Upad, out=g_off[1:])
                 g_len = int(g_off[-1])
-            if T.g is None or T.g.numel() != max(g_len, 4):
-                T.g = torch.empty(max(g_len, 4), dtype=torch.float64, device=dev)
-            T.g_per_w = g_per_w
+            if tiled:
+                tile_off_dev = self.to_device(tile_off)
+                tile_g_off_dev = self.to_device(tile_g_off)
+                tile_U_dev = self.to_device(tile_U.astype(np.int32))
+            L.update(g_off=g_off, tile_g_off=tile_g_off)
+            ensure("g", max(g_len, 4), torch.float64)
             done = [0]      # states flushed so far (chunks arrive in order)
 
             def flush(desc, staging):
+                if u_mask:
+                    tb.check_factorable(desc, d, u_mask)
                 desc_dev = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(dev)
                 stag_dev = torch.from_numpy(staging).to(dev)
                 ns = len(desc)
@@ -370,14 +434,32 @@ class Engine(object):
                     assert done[0] % 32 == 0
                     t_first = done[0] // 32
                     nt = (ns + 31) // 32
-                    rc = self.lib.sdp_build_tables_tiled(
-                        ctypes.byref(grid), W, g_per_w, ns, self._ptr(desc_dev), self._ptr(stag_dev), nt,
-                        ctypes.c_void_p(tile_off_dev.data_ptr() + 8 * t_first),
-                        ctypes.c_void_p(tile_g_off_dev.data_ptr() + 8 * t_first),
-                        ctypes.c_void_p(tile_U_dev.data_ptr() + 4 * t_first),
-                        int(tile_U[t_first:t_first + nt].max()),
-                        self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g), self.stream)
-                    _cabi.check(rc, "sdp_build_tables_tiled")
+                    t_off = ctypes.c_void_p(tile_off_dev.data_ptr() + 8 * t_first)
+                    t_U = ctypes.c_void_p(tile_U_dev.data_ptr() + 4 * t_first)
+                    t_Umax = int(tile_U[t_first:t_first + nt].max())
+                    if u_mask:
+                        w0 = t_first * W * 32
+                        rc = self.lib.sdp_build_tables_factored_tiled(
+                            ctypes.byref(grid), W, u_mask, ns, self._ptr(desc_dev), self._ptr(stag_dev),
+                            nt, t_off, t_U, t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane,
+                            self._ptr(T.g), ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
+                            ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
+                        _cabi.check(rc, "sdp_build_tables_factored_tiled")
+                    else:
+                        rc = self.lib.sdp_build_tables_tiled(
+                            ctypes.byref(grid), W, g_per_w, ns, self._ptr(desc_dev), self._ptr(stag_dev),
+                            nt, t_off, ctypes.c_void_p(tile_g_off_dev.data_ptr() + 8 * t_first), t_U,
+                            t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g),
+                            self.stream)
+                        _cabi.check(rc, "sdp_build_tables_tiled")
+                elif u_mask:
+                    w0 = done[0] * W
+                    rc = self.lib.sdp_build_tables_factored(
+                        ctypes.byref(grid), W, u_mask, ns, self._ptr(desc_dev), self._ptr(stag_dev),
+                        self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g),
+                        int(desc["Upad"].max()), ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
+                        ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
+                    _cabi.check(rc, "sdp_build_tables_factored")
                 else:
                     rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, ns,
                                                    self._ptr(desc_dev), self._ptr(stag_dev),
@@ -397,22 +479,32 @@ class Engine(object):
                     tb.state_tuples(state_grid, sb, se)
                 tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
                                    g_per_w, flush, align=align)
-            return g_off, tile_g_off
+            return L
 
-        # mode/g-layout resolution: batched evaluation is tried first in "auto"
+        # mode / layout resolution: batched evaluation is tried first in "auto"
         # mode and abandoned if it fails or is not bit-identical to the
-        # reference's per-state calls on the sample states
-        g_per_w = T.g_per_w if reuse is T else 0
+        # reference's per-state calls on the sample states; factored tables are
+        # abandoned for dense ones as soon as one chunk does not fit the split
+        g_per_w = T.g_per_w if (reuse is T and not u_mask) else 0
         batched = mode in ("auto", "batched")
-        result = None
-        while result is None:
+        L = None
+        while L is None:
             try:
-                result = build(g_per_w, batched)
+                L = build(g_per_w, batched, u_mask)
                 T.tabulate_mode = "batched" if batched else "per_state"
+            except tb.NotFactorable:
+                if compress == "on" or world > 1:
+                    # (with several ranks a silent per-rank fallback would desynchronise the layouts)
+                    raise ValueError("dyn/cost outputs do not keep the (x,u) + (x,w) structure "
+                                     "seen on the probe state; use solver.table_compress = 'off'")
+                u_mask = 0
             except tb.GDependsOnW:
                 if g_per_w:
                     raise
-                g_per_w = 1          # the cost depends on w: dense g table
+                if u_mask:
+                    u_mask = 0
+                else:
+                    g_per_w = 1      # the cost depends on w: dense g table
             except tb.BatchedMismatch:
                 if mode != "auto":
                     raise
@@ -421,7 +513,13 @@ class Engine(object):
                 if not (batched and mode == "auto"):
                     raise
                 batched = False      # callables not vectorisable over states
-        g_off, tile_g_off = result
+        T.u_mask = u_mask
+        T.g_per_w = g_per_w
+        n_tiles, tile_U, tile_off = L["n_tiles"], L["tile_U"], L["tile_off"]
+        entry_off, Upad, g_off, tile_g_off = L["entry_off"], L["Upad"], L["g_off"], L["tile_g_off"]
+        lam_plane = L["lam_plane"]
+        T.n_entries, T.lam_plane, T.lam_w_plane = L["n_entries"], lam_plane, L["lam_w_plane"]
+        Wf = 1 if u_mask else W     # table entries per control
 
         # work items: one warp per run of at most `item_chunk` controls
         chunk = self.item_chunk
@@ -440,8 +538,9 @@ class Engine(object):
         items["u_count"] = np.minimum(chunk, unit_U[st] - kk * chunk)
         items["state"] = st
         if tiled:
-            items["entry_base"] = tile_off[st] + kk * chunk * W * 32
-            items["g_base"] = items["entry_base"] if T.g_per_w else tile_g_off[st] + kk * chunk * 32
+            items["entry_base"] = tile_off[st] + kk * chunk * Wf * 32
+            items["g_base"] = items["entry_base"] if (T.g_per_w or u_mask) else \
+                tile_g_off[st] + kk * chunk * 32
             items["Upad"] = 0
         else:
             items["entry_base"] = entry_off[st] + kk * chunk
@@ -465,7 +564,14 @@ class Engine(object):
         c.g_per_w = T.g_per_w
         c.W = W
         c.expect = T.expect
-        c.layout = _cabi.LAYOUT_STATE_MINOR if tiled else _cabi.LAYOUT_CONTROL_MINOR
+        if u_mask:
+            c.layout = _cabi.LAYOUT_STATE_MINOR_FACTORED if tiled else _cabi.LAYOUT_CONTROL_MINOR_FACTORED
+            c.u_mask = u_mask
+            c.cell_w = T.cell_w.data_ptr()
+            c.lam_w = T.lam_w.data_ptr()
+            c.lam_w_plane = T.lam_w_plane
+        else:
+            c.layout = _cabi.LAYOUT_STATE_MINOR if tiled else _cabi.LAYOUT_CONTROL_MINOR
         c.p = T.p.data_ptr()
         c.items = T.items.data_ptr()
         c.n_items = n_items

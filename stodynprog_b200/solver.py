@@ -56,6 +56,9 @@ class DPSolver(object):
         # table layout and host tabulation mode (see Engine.build_sweep_tables)
         self.table_layout = "auto"    # "auto" | "control_minor" | "state_minor"
         self.tabulate = "auto"        # "auto" | "per_state" | "batched"
+        # "auto": keep the tables as a (x,u) part + a (x,w) part whenever dyn/cost
+        # have that structure (every reference example does); "off": always dense
+        self.table_compress = "auto"  # "auto" | "off" | "on"
 
     # ------------------------------------------------------------------
     # discretisation (host only)
@@ -148,7 +151,7 @@ class DPSolver(object):
                 tuple(sig(g) for g in self.perturb_grid),
                 tuple(sig(p) for p in self.perturb_proba),
                 tuple(float(c) for c in self.control_steps),
-                self.table_layout, self.tabulate)
+                self.table_layout, self.tabulate, self.table_compress)
 
     def clear_tables(self):
         """drop the device-resident tables (call after mutating anything the

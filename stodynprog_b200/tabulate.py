@@ -18,7 +18,8 @@ import numpy as np
 from . import _cabi
 
 __all__ = ["control_grid_counts", "control_axis_values", "HostStateTable", "tabulate_states",
-           "tabulate_states_batched", "GDependsOnW", "BatchedMismatch"]
+           "tabulate_states_batched", "GDependsOnW", "BatchedMismatch", "NotFactorable",
+           "probe_factor_mask", "check_factorable"]
 
 
 def _npts_for(width, step):
@@ -170,6 +171,56 @@ def scan_control_boxes(sys, control_steps, states, t_k=None):
         tab.hi[i] = hi
         tab.npts[i] = npts
     return tab
+
+
+class NotFactorable(Exception):
+    """a chunk of staged dyn/cost outputs does not have the (x,u) + (x,w)
+    structure the factored tables were being built for: restart dense"""
+
+
+def probe_factor_mask(sys, x_k, host_tab, i, perturb_grid, t_k):
+    """Look at what dyn/cost return for ONE state (the reference's own call,
+    stodynprog.py:674-676) and classify every next-state coordinate by the
+    axes its un-broadcast output spans: controls only, perturbation only, or
+    neither.  Returns the bit mask of the coordinates to put in the (x,u) part
+    of factored tables, or None when some coordinate spans
+    both axes, the cost depends on w, or the split would be one-sided."""
+    d = len(sys.state)
+    W = len(perturb_grid[0])
+    compact, control_dims, U = _eval_one_state(sys, x_k, host_tab, i, tuple(perturb_grid), t_k, W)
+    if compact[-1][2] > 1:
+        return None                       # g depends on w
+    mask = 0
+    free = []                             # coordinates that depend on neither u nor w
+    for k in range(d):
+        _, u_eff, w_eff = compact[k]
+        if u_eff > 1 and w_eff > 1:
+            return None
+        if u_eff > 1:
+            mask |= 1 << k
+        elif w_eff == 1:
+            free.append(k)
+    full = (1 << d) - 1
+    if mask == 0 and free:
+        mask |= 1 << free.pop(0)          # need at least one (x,u) coordinate
+    if mask == full or mask == 0:
+        return None
+    return mask
+
+
+def check_factorable(desc, d, u_mask):
+    """every state record of a chunk must agree with the split: (x,u)
+    coordinates and g have no perturbation stride, (x,w) coordinates no control
+    stride.  Raises NotFactorable otherwise."""
+    for k in range(d):
+        if (u_mask >> k) & 1:
+            ok = not np.any(desc["ws"][:, k])
+        else:
+            ok = not np.any(desc["cs"][:, k, :])
+        if not ok:
+            raise NotFactorable()
+    if np.any(desc["ws"][:, d]):
+        raise NotFactorable()
 
 
 class GDependsOnW(Exception):

@@ -161,6 +161,114 @@ class FakeLib(object):
         self.launches += 1
         return 0
 
+    # -- factored layouts: the model expands them to what the dense tables hold --
+    def _part(self, r, d, mask, stag, smin, smax, orders, strides, n, along_u):
+        """partial cell index + weights of the coordinates in `mask` for the n
+        entries along the control (along_u) or perturbation axis of state r"""
+        cell = np.zeros(n, dtype=np.int64)
+        lams = []
+        for k in range(d):
+            if not (mask >> k) & 1:
+                continue
+            if along_u:
+                idx = self._src_index(r, k, n, 1)[0]
+            else:
+                idx = self._src_index(r, k, 1, n)[:, 0]
+            full = np.zeros((d, n))
+            full[k] = stag[idx]
+            # 1-D cell search on axis k alone
+            ck, lk = oc.cell_search(smin[k:k + 1], smax[k:k + 1], orders[k:k + 1], full[k:k + 1])
+            cell += ck.astype(np.int64) * strides[k]
+            lams.append(lk[0])
+        return cell, lams
+
+    def sdp_build_tables_factored(self, gref, W, u_mask, n_states, desc, staging, cell, lam, lam_plane,
+                                  g, max_Upad, cell_w, lam_w, lam_w_plane, stream):
+        d, smin, smax, orders = _grid(gref)
+        strides = np.concatenate([np.cumprod(orders[::-1])[::-1][1:], [1]]).astype(np.int64)
+        D = np.frombuffer((ctypes.c_uint8 * (n_states * _cabi.STATE_DESC_DTYPE.itemsize))
+                          .from_address(desc.value), dtype=_cabi.STATE_DESC_DTYPE)
+        stag = self._staging(D, d, W, staging)
+        w_mask = ~u_mask & ((1 << d) - 1)
+        for i, r in enumerate(D):
+            U, Upad, eo = int(r["U"]), int(r["Upad"]), int(r["entry_off"])
+            assert Upad % 4 == 0 and U <= Upad <= max_Upad
+            cu, lu = self._part(r, d, u_mask, stag, smin, smax, orders, strides, U, True)
+            blk = _arr(cell.value + 4 * eo, Upad, ctypes.c_int32)
+            blk[:] = 0
+            blk[:U] = cu
+            for j, l in enumerate(lu):
+                blk = _arr(lam.value + 8 * (j * lam_plane + eo), Upad, ctypes.c_double)
+                blk[:] = 0
+                blk[:U] = l
+            blk = _arr(g.value + 8 * eo, Upad, ctypes.c_double)
+            blk[:] = 0
+            blk[:U] = stag[self._src_index(r, d, U, 1)[0]]
+            cw, lw = self._part(r, d, w_mask, stag, smin, smax, orders, strides, W, False)
+            _arr(cell_w.value + 4 * i * W, W, ctypes.c_int32)[:] = cw
+            for j, l in enumerate(lw):
+                _arr(lam_w.value + 8 * (j * lam_w_plane + i * W), W, ctypes.c_double)[:] = l
+        self.launches += 1
+        return 0
+
+    def sdp_build_tables_factored_tiled(self, gref, W, u_mask, n_states, desc, staging, n_tiles, tile_off,
+                                        tile_U, max_tile_U, cell, lam, lam_plane, g, cell_w, lam_w,
+                                        lam_w_plane, stream):
+        d, smin, smax, orders = _grid(gref)
+        strides = np.concatenate([np.cumprod(orders[::-1])[::-1][1:], [1]]).astype(np.int64)
+        D = np.frombuffer((ctypes.c_uint8 * (n_states * _cabi.STATE_DESC_DTYPE.itemsize))
+                          .from_address(desc.value), dtype=_cabi.STATE_DESC_DTYPE)
+        stag = self._staging(D, d, W, staging)
+        toff = _arr(tile_off, n_tiles, ctypes.c_int64)
+        tU = _arr(tile_U, n_tiles, ctypes.c_int32)
+        w_mask = ~u_mask & ((1 << d) - 1)
+        n_u = bin(u_mask).count("1")
+        for t in range(n_tiles):
+            Ut = int(tU[t])
+            assert Ut <= max_tile_U
+            cblk = _arr(cell.value + 4 * int(toff[t]), Ut * 32, ctypes.c_int32).reshape(Ut, 32)
+            lblk = [_arr(lam.value + 8 * (j * lam_plane + int(toff[t])), Ut * 32, ctypes.c_double).reshape(Ut, 32)
+                    for j in range(n_u)]
+            gblk = _arr(g.value + 8 * int(toff[t]), Ut * 32, ctypes.c_double).reshape(Ut, 32)
+            cblk[:] = 0
+            gblk[:] = 0
+            for l in lblk:
+                l[:] = 0
+            cwb = _arr(cell_w.value + 4 * t * W * 32, W * 32, ctypes.c_int32).reshape(W, 32)
+            lwb = [_arr(lam_w.value + 8 * (j * lam_w_plane + t * W * 32), W * 32, ctypes.c_double).reshape(W, 32)
+                   for j in range(d - n_u)]
+            cwb[:] = 0
+            for l in lwb:
+                l[:] = 0
+            for lane in range(32):
+                i = 32 * t + lane
+                if i >= n_states:
+                    break
+                r = D[i]
+                U = int(r["U"])
+                cu, lu = self._part(r, d, u_mask, stag, smin, smax, orders, strides, U, True)
+                cblk[:U, lane] = cu
+                for j, l in enumerate(lu):
+                    lblk[j][:U, lane] = l
+                gblk[:U, lane] = stag[self._src_index(r, d, U, 1)[0]]
+                cw, lw = self._part(r, d, w_mask, stag, smin, smax, orders, strides, W, False)
+                cwb[:, lane] = cw
+                for j, l in enumerate(lw):
+                    lwb[j][:, lane] = l
+        self.launches += 1
+        return 0
+
+    def _merge(self, T, d, lu, lw):
+        out, ju, jw = [], 0, 0
+        for k in range(d):
+            if (T.u_mask >> k) & 1:
+                out.append(lu[ju])
+                ju += 1
+            else:
+                out.append(lw[jw])
+                jw += 1
+        return out
+
     def sdp_sweep(self, gref, tref, J_prev, part_val, part_idx, J_out, argmin_out, stream):
         d, smin, smax, orders = _grid(gref)
         T = tref._obj
@@ -170,7 +278,9 @@ class FakeLib(object):
         items = np.frombuffer((ctypes.c_uint8 * (T.n_items * _cabi.ITEM_DTYPE.itemsize))
                               .from_address(T.items), dtype=_cabi.ITEM_DTYPE)
         p = _arr(T.p, T.W, ctypes.c_double) if T.expect else np.ones(T.W)
-        tiled = T.layout == _cabi.LAYOUT_STATE_MINOR
+        tiled = T.layout in (_cabi.LAYOUT_STATE_MINOR, _cabi.LAYOUT_STATE_MINOR_FACTORED)
+        factored = T.layout in (_cabi.LAYOUT_CONTROL_MINOR_FACTORED, _cabi.LAYOUT_STATE_MINOR_FACTORED)
+        n_u = bin(T.u_mask).count("1")
         width = 32 if tiled else 1
         pv = _arr(part_val, T.n_items * width, ctypes.c_double)
         pi = _arr(part_idx, T.n_items * width, ctypes.c_int32)
@@ -192,7 +302,46 @@ class FakeLib(object):
 
         for n_it, it in enumerate(items):
             cnt, ub = int(it["u_count"]), int(it["u_begin"])
-            if not tiled:
+            if factored and not tiled:
+                eb, sidx = int(it["entry_base"]), int(it["state"])
+                assert int(it["g_base"]) == eb
+                cu = _arr(T.cell + 4 * eb, cnt, ctypes.c_int32).astype(np.int64)
+                lu = [_arr(T.lam + 8 * (j * T.lam_plane + eb), cnt, ctypes.c_double) for j in range(n_u)]
+                gv = _arr(T.g + 8 * eb, cnt, ctypes.c_double)
+                acc = np.zeros(cnt)
+                for w in range(W):
+                    f = sidx * W + w
+                    cw = int(_arr(T.cell_w + 4 * f, 1, ctypes.c_int32)[0])
+                    lw = [_arr(T.lam_w + 8 * (j * T.lam_w_plane + f), 1, ctypes.c_double)[0]
+                          for j in range(d - n_u)]
+                    jg = gv + lerp(cu + cw, self._merge(T, d, lu, lw))
+                    acc = acc + jg * p[w] if T.expect else jg
+                j = first_min(acc)
+                pv[n_it], pi[n_it] = acc[j], ub + j
+            elif factored:
+                eb, tix = int(it["entry_base"]), int(it["state"])
+                assert int(it["g_base"]) == eb
+                cu = _arr(T.cell + 4 * eb, cnt * 32, ctypes.c_int32).astype(np.int64).reshape(cnt, 32)
+                lu = [_arr(T.lam + 8 * (j * T.lam_plane + eb), cnt * 32, ctypes.c_double).reshape(cnt, 32)
+                      for j in range(n_u)]
+                Gv = _arr(T.g + 8 * eb, cnt * 32, ctypes.c_double).reshape(cnt, 32)
+                acc = np.zeros((cnt, 32))
+                for w in range(W):
+                    f = (tix * W + w) * 32
+                    cw = _arr(T.cell_w + 4 * f, 32, ctypes.c_int32).astype(np.int64)[None, :]
+                    lw = [_arr(T.lam_w + 8 * (j * T.lam_w_plane + f), 32, ctypes.c_double)[None, :]
+                          for j in range(d - n_u)]
+                    jg = Gv + lerp(cu + cw, self._merge(T, d, lu, lw))
+                    acc = acc + jg * p[w] if T.expect else jg
+                for lane in range(32):
+                    s_i = tix * 32 + lane
+                    n_ok = max(0, min(cnt, (int(Us[s_i]) if s_i < T.n_states else 0) - ub))
+                    if n_ok == 0:
+                        pv[n_it * 32 + lane], pi[n_it * 32 + lane] = np.inf, 2 ** 31 - 1
+                    else:
+                        j = first_min(acc[:n_ok, lane])
+                        pv[n_it * 32 + lane], pi[n_it * 32 + lane] = acc[j, lane], ub + j
+            elif not tiled:
                 Upad = int(it["Upad"])
                 acc = np.zeros(cnt)
                 for w in range(W):

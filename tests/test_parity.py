@@ -31,11 +31,12 @@ class _Api(object):
     bound either to the CUDA library or to the numpy model of the C ABI, and
     pinned to one table layout."""
 
-    def __init__(self, pkg, backend, layout="auto", tabulate="auto"):
+    def __init__(self, pkg, backend, layout="auto", tabulate="auto", compress="auto"):
         self.pkg = pkg
         self.backend = backend
         self.layout = layout
         self.tabulate = tabulate
+        self.compress = compress
         self.SysDescription = pkg.SysDescription
 
     def DPSolver(self, sys, **kw):
@@ -45,17 +46,24 @@ class _Api(object):
         sv = self.pkg.DPSolver(sys, **kw)
         sv.table_layout = self.layout
         sv.tabulate = self.tabulate
+        sv.table_compress = self.compress
         return sv
 
 
 @pytest.fixture(scope="module", params=[
-    pytest.param(("model", "control_minor"), id="model-A"),
-    pytest.param(("model", "state_minor"), id="model-B"),
-    pytest.param(("cuda", "control_minor"), marks=gpu, id="cuda-A"),
-    pytest.param(("cuda", "state_minor"), marks=gpu, id="cuda-B")])
+    pytest.param(("model", "control_minor", "auto", "off"), id="model-A"),
+    pytest.param(("model", "state_minor", "auto", "off"), id="model-B"),
+    pytest.param(("model", "control_minor", "auto", "auto"), id="model-AF"),
+    pytest.param(("model", "state_minor", "auto", "auto"), id="model-BF"),
+    pytest.param(("cuda", "control_minor", "auto", "off"), marks=gpu, id="cuda-A"),
+    pytest.param(("cuda", "state_minor", "auto", "off"), marks=gpu, id="cuda-B"),
+    pytest.param(("cuda", "control_minor", "auto", "auto"), marks=gpu, id="cuda-AF"),
+    pytest.param(("cuda", "state_minor", "auto", "auto"), marks=gpu, id="cuda-BF")])
 def api(request, product):
     """host logic is exercised against the numpy model of the C ABI (CPU suite)
-    and against the real CUDA library (GPU suite), for both table layouts"""
+    and against the real CUDA library (GPU suite), for both table layouts, with
+    dense tables (A, B) and with factored tables wherever the system has the
+    (x,u) + (x,w) structure (AF, BF; other systems fall back to dense)"""
     return _Api(product, *request.param)
 
 
@@ -478,7 +486,7 @@ def test_batched_tabulation_is_bit_identical(product, backend, layout, which):
     from stodynprog_b200 import workloads as wl
     tabs = []
     for mode in ("per_state", "batched"):
-        api = _Api(product, backend, layout, mode)
+        api = _Api(product, backend, layout, mode, "off")
         if which == "storage_ar1":
             sv = wl.storage_ar1(api, n_E=9, n_P=11, steps=(0.01, 0.1)).solver
         elif which == "searev":
@@ -498,6 +506,166 @@ def test_batched_tabulation_is_bit_identical(product, backend, layout, which):
     lb = b.lam.cpu().numpy().view(np.int64).reshape(b.d, -1)[:, :n]
     assert np.array_equal(la, lb)
     assert np.array_equal(a.g.cpu().numpy().view(np.int64), b.g.cpu().numpy().view(np.int64))
+
+
+# ---------------------------------------------------------------------------
+# factored (x,u) + (x,w) tables: same entries, same sweep, bit for bit
+# ---------------------------------------------------------------------------
+def _separable(api, roles, n_u=23, n_w=5, **kw):
+    """synthetic system whose next-state coordinate k depends on the state and on
+    the control only (role 'u'), the perturbation only ('w') or neither ('x')"""
+    import scipy.stats as stats
+    d = len(roles)
+
+    def dyn(*a):
+        x, (u, w) = a[:d], a[d:]
+        out = []
+        for k, role in enumerate(roles):
+            if role == 'u':
+                out.append(0.8 * x[k] + (0.4 + 0.1 * k) * u)
+            elif role == 'w':
+                out.append(0.7 * x[k] + 0.3 * x[0] + (1.0 + 0.2 * k) * w)
+            else:
+                out.append(0.9 * x[k] + 0.1)
+        return tuple(out)
+
+    def box(*x):
+        return ((-1.0 - 0.1 * x[0], 1.0 + 0.05 * x[-1]),)
+
+    def cost(*a):
+        x, (u, w) = a[:d], a[d:]
+        return sum(xi ** 2 for xi in x) + 0.1 * (u - 0.2) ** 2
+
+    names = ['x%d' % i for i in range(d)]
+    src = "def dyn_f({0}, u, w): return dyn({0}, u, w)\n" \
+          "def cost_f({0}, u, w): return cost({0}, u, w)\n" \
+          "def box_f({0}): return box({0})\n".format(', '.join(names))
+    ns = {'dyn': dyn, 'cost': cost, 'box': box}
+    exec(src, ns)
+    sys = api.SysDescription((d, 1, 1), name='separable' + ''.join(roles))
+    sys.dyn = ns['dyn_f']
+    sys.control_box = ns['box_f']
+    sys.cost = ns['cost_f']
+    sys.perturb_laws = [stats.norm(0, 0.3)]
+    sv = api.DPSolver(sys, **kw)
+    args = []
+    for n in [7, 6, 5][:d]:
+        args += [-1.0, 2.0, n]
+    sv.discretize_state(*args)
+    sv.discretize_perturb(-0.9, 0.9, n_w)
+    sv.control_steps = (2.0 / n_u,)
+    return sv
+
+
+def _dense_from_factored(T):
+    """expand factored tables on the host into the dense (cell, lam[d], g) entries,
+    in the dense layout's order"""
+    W, d, n = T.W, T.d, T.n_states
+    ku = [k for k in range(d) if (T.u_mask >> k) & 1]
+    kw = [k for k in range(d) if not (T.u_mask >> k) & 1]
+    cu = T.cell.cpu().numpy().astype(np.int64)
+    lu = T.lam.cpu().numpy().reshape(len(ku), -1)
+    g = T.g.cpu().numpy()
+    cw = T.cell_w.cpu().numpy().astype(np.int64)
+    lw = T.lam_w.cpu().numpy().reshape(len(kw), -1)
+    U = T.U_dev.cpu().numpy()[:n]
+    cells, lams, gs = [], [[] for _ in range(d)], []
+    if not T.tiled:
+        Upad = (U + 3) // 4 * 4
+        eo = np.concatenate([[0], np.cumsum(Upad)])
+        for i in range(n):
+            e = slice(eo[i], eo[i] + Upad[i])
+            for w in range(W):
+                live = np.arange(Upad[i]) < U[i]
+                cells.append(np.where(live, cu[e] + cw[i * W + w], 0))
+                for j, k in enumerate(ku):
+                    lams[k].append(lu[j][e])
+                for j, k in enumerate(kw):
+                    lams[k].append(np.where(live, lw[j][i * W + w], 0.0))
+            gs.append(g[e])
+    else:
+        n_tiles = (n + 31) // 32
+        Ut = np.zeros(n_tiles * 32, dtype=np.int64)
+        Ut[:n] = U
+        Ulane = Ut.reshape(n_tiles, 32)
+        tU = Ulane.max(axis=1)
+        to = np.concatenate([[0], np.cumsum(tU * 32)])
+        for t in range(n_tiles):
+            blk = slice(to[t], to[t] + tU[t] * 32)
+            cu_t = cu[blk].reshape(tU[t], 1, 32)
+            live = np.arange(tU[t])[:, None, None] < Ulane[t][None, None, :]
+            cw_t = cw[t * W * 32:(t + 1) * W * 32].reshape(1, W, 32)
+            cells.append(np.where(live, cu_t + cw_t, 0).reshape(-1))
+            for j, k in enumerate(ku):
+                lams[k].append(np.broadcast_to(lu[j][blk].reshape(tU[t], 1, 32), (tU[t], W, 32)).reshape(-1))
+            for j, k in enumerate(kw):
+                lw_t = lw[j][t * W * 32:(t + 1) * W * 32].reshape(1, W, 32)
+                lams[k].append(np.where(live, lw_t, 0.0).reshape(-1))
+            gs.append(g[blk])
+    return (np.concatenate(cells), [np.concatenate(l) for l in lams], np.concatenate(gs))
+
+
+FACTOR_CASES = {
+    "storage_ar1": 0b01, "searev": None, "curtail": 0b01,
+    "uw": 0b01, "wu": 0b10, "uww": 0b001, "wuw": 0b010, "uuw": 0b011, "wwu": 0b100,
+    "uwu": 0b101, "wuu": 0b110, "xuw": 0b010, "xwu": 0b100,
+}
+
+
+def _factor_case(api, which):
+    from stodynprog_b200 import workloads as wl
+    if which == "storage_ar1":
+        return wl.storage_ar1(api, n_E=9, n_P=11, steps=(0.01, 0.1)).solver
+    if which == "searev":
+        return _searev_small(api).solver
+    if which == "curtail":
+        return _two_control_system(api)
+    return _separable(api, which)
+
+
+@pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
+@pytest.mark.parametrize("layout", ["control_minor", "state_minor"])
+@pytest.mark.parametrize("which", sorted(FACTOR_CASES))
+def test_factored_tables_and_sweep_equal_dense(product, backend, layout, which):
+    """the factored layouts hold exactly the entries of the dense tables (K0) and
+    the factored sweep returns bit-identical J and argmin (K1)"""
+    dense = _factor_case(_Api(product, backend, layout, "auto", "off"), which)
+    fact = _factor_case(_Api(product, backend, layout, "auto", "on"), which)
+    Td, Tf = dense.sweep_tables(), fact.sweep_tables()
+    assert not Td.factored and Tf.factored
+    if FACTOR_CASES[which] is not None:
+        assert Tf.u_mask == FACTOR_CASES[which]
+    assert Tf.layout_name == layout + "_factored"
+    cells, lams, g = _dense_from_factored(Tf)
+    n = Td.n_entries
+    assert np.array_equal(Td.cell.cpu().numpy()[:n], cells)
+    ld = Td.lam.cpu().numpy().reshape(Td.d, -1)[:, :n]
+    for k in range(Td.d):
+        assert np.array_equal(ld[k].view(np.int64), lams[k].view(np.int64)), k
+    assert np.array_equal(Td.g.cpu().numpy()[:len(g)].view(np.int64), g.view(np.int64))
+    assert Tf.device_bytes < Td.device_bytes
+    J0 = np.random.default_rng(5).standard_normal(dense._state_grid_shape)
+    for _ in range(2):
+        Jd, pold = dense.value_iteration(J0, report_time=False)
+        Jf, polf = fact.value_iteration(J0, report_time=False)
+        assert np.array_equal(Jd.view(np.int64), Jf.view(np.int64))
+        assert np.array_equal(pold, polf)
+        J0 = Jd
+
+
+def test_unfactorable_systems_fall_back_to_dense(product):
+    """a coordinate that spans controls AND perturbation, or a cost that depends
+    on w, keeps the dense tables in "auto" mode and is refused in "on" mode"""
+    for kind in ("plain", "w"):
+        sv = _toy(_Api(product, "model", "control_minor", "auto", "auto"), 2, kind)
+        assert not sv.sweep_tables().factored
+    sv = _toy(_Api(product, "model", "control_minor", "auto", "on"), 2)
+    with pytest.raises(ValueError):
+        sv.sweep_tables()
+    # deterministic and 1-D systems have nothing to factor
+    from stodynprog_b200 import workloads as wl
+    api = _Api(product, "model", "control_minor", "auto", "auto")
+    assert not wl.inventory(api).solver.sweep_tables().factored
 
 
 def _two_control_system(api, **kw):
