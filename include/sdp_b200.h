@@ -165,8 +165,9 @@ int64_t sdp_launch_count(void);
 /* Launch tuning (developer knob; defaults are read from SDP_* environment
  * variables): "upl" (2|4), "wb" (1|2|3|5), "tma" (layout-B kernel: 0 straight
  * LDG, 1 TMA-fed ring, 2 software-pipelined LDG = default), "rb" (2|4|8),
- * "tma_rows" (4|8), "tma_stages" (2..16), "tma_warps" (1..16).  Not thread-safe against
- * concurrent launches. */
+ * "tma_rows" (4|8), "tma_stages" (2..16), "tma_warps" (1..16), "hoist" (layout AF
+ * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4).
+ * Not thread-safe against concurrent launches. */
 int sdp_set_option(const char* name, int value);
 
 /* K0a - cell search on explicit points.

@@ -34,7 +34,7 @@ if __name__ == "__main__":
     todo = sys.argv[1:] or ["ar1", "large"]
     for which in todo:
         sums = {}
-        for compress in ("on", "off"):
+        for compress in os.environ.get("COMPRESS", "on,off").split(","):
             layouts = ["auto"] if which != "large" else ["state_minor"]
             for layout in layouts:
                 sv = make(which, compress, layout)

@@ -21,7 +21,8 @@ FACTORED_MAX_W_REG = 9     # BF keeps a lane's w-part in registers
 FACTORED_MAX_W_SMEM = 128  # AF keeps a state's w-part in shared memory
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libsdp_b200.so")
+# SDP_B200_LIB: developer override (kernel variants built side by side for tuning runs)
+LIB_PATH = os.environ.get("SDP_B200_LIB") or os.path.join(_HERE, "_lib", "libsdp_b200.so")
 
 
 class SdpLibraryError(RuntimeError):

@@ -44,13 +44,15 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False, extra_flags=()):
+def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile the shared library if missing or older than its sources.
-    Returns the library path."""
-    if not force and not is_stale():
+    Returns the library path.  `out`: alternative output path (tuning variants,
+    always rebuilt)."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", INCLUDE, SRC, "-o", LIB_PATH]
+    out = out or LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", INCLUDE, SRC, "-o", out]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,7 +60,7 @@ def build(force=False, verbose=False, extra_flags=()):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libsdp_b200.so (exit %d)" % res.returncode)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

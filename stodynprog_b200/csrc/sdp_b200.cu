@@ -145,8 +145,10 @@ template <typename T, int D, int K>
 struct Lerp {
     __device__ __forceinline__ static T eval(const T* __restrict__ V, int base,
                                              const int (&stride)[SDP_MAX_D], const T (&lam)[D]) {
+        // the last axis has stride 1 (make_grid): a literal lets the two corner
+        // loads share one address computation
         T a = Lerp<T, D, K + 1>::eval(V, base, stride, lam);
-        T b = Lerp<T, D, K + 1>::eval(V, base + stride[K], stride, lam);
+        T b = Lerp<T, D, K + 1>::eval(V, base + (K == D - 1 ? 1 : stride[K]), stride, lam);
         return add_(mul_(sub_((T)1, lam[K]), a), mul_(lam[K], b));
     }
 };
@@ -1018,6 +1020,8 @@ struct Tuning {
     int tma;      // layout B: 0 = straight LDG kernel, 1 = TMA-fed kernel, 2 = software-pipelined LDG kernel
     int rb;       // layout B, pipelined kernel: rows per group (2|4|8)
     int R, S, NW; // TMA ring: rows per stage (4|8), stages, warps per CTA
+    int hoist;    // layout AF, u_mask == 1: tabulate the inner interpolation per item (1) or not (0)
+    int hoist_upl; // controls per lane per iteration of the hoisted kernel (2|4)
 };
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
@@ -1043,6 +1047,8 @@ static Tuning& tuning() {
         x.R = env_int("SDP_TMA_R", 8) == 4 ? 4 : 8;
         x.S = env_int("SDP_TMA_S", 2);
         x.NW = env_int("SDP_TMA_NW", 4);
+        x.hoist = env_int("SDP_HOIST", 1) != 0;
+        x.hoist_upl = env_int("SDP_HOIST_UPL", 2) == 4 ? 4 : 2;
         return x;
     }();
     return t;
@@ -1059,6 +1065,8 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "tma_rows")) t.R = (value == 8) ? 8 : 4;
     else if (!strcmp(name, "tma_stages")) t.S = value;
     else if (!strcmp(name, "tma_warps")) t.NW = value;
+    else if (!strcmp(name, "hoist")) t.hoist = value != 0;
+    else if (!strcmp(name, "hoist_upl")) t.hoist_upl = (value == 4) ? 4 : 2;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1233,16 +1241,175 @@ k_sweep_fact(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
     }
 }
 
-// BF: lane <-> state of a 32-state tile; the lane's w-part (W <= 9 entries)
-// lives in registers, the u-part is streamed one control ahead.
-template <int D, int MASK>
-__global__ void __launch_bounds__(128)
+// BF: lane <-> state of a 32-state tile; the lane's w-part (W <= WM <= 9 entries)
+// lives in registers, the u-part is streamed one control ahead.  The w loop is
+// fully unrolled over WM slots with NO guard on the gathers (slots >= W repeat
+// slot W-1, so they hit the same lines): ncu on the guarded version showed one
+// exposed L1/L2 round trip per perturbation node (the uniform `w < W` branches
+// kept the 4*W corner loads of a control from being issued together).
+// AF with hoisted inner interpolation (u_mask == 1: coordinate 0 follows the
+// control, every other coordinate the perturbation - the structure of all the
+// reference's storage examples).  The nested lerp is
+//     (1-l0)*R(q0, w) + l0*R(q0+1, w),   R(r, w) = lerp over axes 1.. of J[r, ...]
+// and R depends on the ROW r and on w only, not on the control.  With a fine
+// control grid the controls of an item fall into a handful of rows, so the warp
+// first tabulates R for the item's row range in shared memory ((rows+1)*W inner
+// lerps, the very operations the reference does, done once instead of once per
+// control) and the per-backup work shrinks from 2^d gathers + (2^d-1) lerps to
+// two shared-memory reads + one lerp.  Items whose row range does not fit the
+// table take the generic path below.  Bit-identical by construction.
+template <int D, int UPL>
+__global__ void __launch_bounds__(256)
+k_sweep_fact_hoist(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+                   double* __restrict__ part_val, int32_t* __restrict__ part_idx, int RP) {
+    constexpr int NW = D - 1;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int W = T.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // layout: p[W] | per warp: R[W][RP+1], lw[NW][W] | per warp: cw[W]
+    double* p_sh = reinterpret_cast<double*>(fsm);
+    const int per_warp_d = W * (RP + 1) + NW * W;
+    double* R_sh = p_sh + W + (size_t)warp * per_warp_d;
+    double* lw_sh = R_sh + W * (RP + 1);
+    int* cw_sh = reinterpret_cast<int*>(p_sh + W + (size_t)nwarps * per_warp_d) + warp * W;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) p_sh[i] = T.expect ? T.p[i] : 1.0;
+    __syncthreads();
+
+    const int64_t item_id = (int64_t)blockIdx.x * nwarps + warp;
+    if (item_id >= T.n_items) return;
+    const SdpItem it = T.items[item_id];
+    for (int w = lane; w < W; w += 32) {
+        const int64_t f = (int64_t)it.state * W + w;
+        cw_sh[w] = __ldg(T.cell_w + f);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) lw_sh[j * W + w] = __ldg(T.lam_w + (int64_t)j * T.lam_w_plane + f);
+    }
+    // row range of the item's controls (cell_u = q0 * stride0)
+    int cmin = INT_MAX, cmax = INT_MIN;
+    for (int u0 = lane * 4; u0 < it.u_count; u0 += 128) {
+        const int4 c = *reinterpret_cast<const int4*>(T.cell + it.entry_base + u0);
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (u0 + j < it.u_count) { cmin = min(cmin, cc[j]); cmax = max(cmax, cc[j]); }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, s));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, s));
+    }
+    const int stride0 = G.stride[0];
+    const int r0 = cmin / stride0;
+    const int nrows = cmax / stride0 - r0 + 1;       // rows r0 .. r0+nrows-1, plus the upper corner row
+    const bool hoist = nrows <= RP;
+    __syncwarp();
+    if (hoist) {
+        const int RS = RP + 1;
+        for (int idx = lane; idx < (nrows + 1) * W; idx += 32) {
+            const int r = idx / W, w = idx - r * W;
+            double lam[D];
+            lam[0] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) lam[k + 1] = lw_sh[k * W + w];
+            R_sh[w * RS + r] = Lerp<double, D, 1>::eval(Jprev, (r0 + r) * stride0 + cw_sh[w], G.stride, lam);
+        }
+        __syncwarp();
+    }
+
+    double best_v = CUDART_INF;
+    int best_i = INT_MAX;
+    const double inv_stride0 = 1.0 / (double)stride0;
+    for (int u0 = lane * UPL; u0 < it.u_count; u0 += 32 * UPL) {
+        const int64_t off = it.entry_base + u0;
+        int cu[UPL];
+        double lu[UPL], gv[UPL], acc[UPL];
+        {
+            Frag<1, UPL> f;
+            load_frag<1, UPL>(f, T.cell, T.lam, T.lam_plane, off);
+            load_g<UPL>(gv, T.g, off);
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) { cu[j] = f.cell[j]; lu[j] = f.lam[0][j]; acc[j] = 0.0; }
+        }
+        if (hoist) {
+            const int RS = RP + 1;
+            int r[UPL];
+            double oml[UPL];
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) {
+                // q0 = cu / stride0 exactly (cu is a multiple of stride0 below 2^31)
+                int q = __double2int_rn(__dmul_rn((double)cu[j], inv_stride0)) - r0;
+                r[j] = max(0, min(q, nrows - 1));     // padding entries (cell 0) stay in range
+                oml[j] = sub_(1.0, lu[j]);
+            }
+#pragma unroll 3
+            for (int w = 0; w < W; ++w) {
+                const double pw = p_sh[w];
+                const double* Rw = R_sh + w * RS;
+#pragma unroll
+                for (int j = 0; j < UPL; ++j) {
+                    const double v = add_(mul_(oml[j], Rw[r[j]]), mul_(lu[j], Rw[r[j] + 1]));
+                    const double jg = add_(gv[j], v);
+                    if (T.expect) acc[j] = add_(acc[j], mul_(jg, pw));
+                    else acc[j] = jg;
+                }
+            }
+        } else {
+#pragma unroll 3
+            for (int w = 0; w < W; ++w) {
+                const int cw = cw_sh[w];
+                const double pw = p_sh[w];
+                double lam[UPL][D];
+#pragma unroll
+                for (int j = 0; j < UPL; ++j) {
+                    lam[j][0] = lu[j];
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) lam[j][k + 1] = lw_sh[k * W + w];
+                }
+#pragma unroll
+                for (int j = 0; j < UPL; ++j) {
+                    const double v = Lerp<double, D, 0>::eval(Jprev, cu[j] + cw, G.stride, lam[j]);
+                    const double jg = add_(gv[j], v);
+                    if (T.expect) acc[j] = add_(acc[j], mul_(jg, pw));
+                    else acc[j] = jg;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) {
+            const int u = u0 + j;
+            if (u < it.u_count) {
+                const int idx = it.u_begin + u;
+                if (better(acc[j], idx, best_v, best_i)) { best_v = acc[j]; best_i = idx; }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best_v, s);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, s);
+        if (better(ov, oi, best_v, best_i)) { best_v = ov; best_i = oi; }
+    }
+    if (lane == 0) {
+        part_val[item_id] = best_v;
+        part_idx[item_id] = best_i;
+    }
+}
+
+#ifndef SDP_BF_UB
+#define SDP_BF_UB 1      // controls per iteration of the BF kernel
+#endif
+#ifndef SDP_BF_MINB
+#define SDP_BF_MINB 1    // __launch_bounds__ min CTAs per SM of the BF kernel
+#endif
+template <int D, int MASK, int WM>
+__global__ void __launch_bounds__(128, SDP_BF_MINB)
 k_sweep_fact_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
                    double* __restrict__ part_val, int32_t* __restrict__ part_idx) {
     constexpr int NU = Fact<D, MASK>::NU, NW = Fact<D, MASK>::NW;
-    constexpr int WM = SDP_FACTORED_MAX_W_REG;
+    constexpr int UB = SDP_BF_UB;
     extern __shared__ double p_sh[];
-    for (int i = threadIdx.x; i < T.W; i += blockDim.x) p_sh[i] = T.expect ? T.p[i] : 1.0;
+    for (int i = threadIdx.x; i < WM; i += blockDim.x)
+        p_sh[i] = (i < T.W) ? (T.expect ? T.p[i] : 1.0) : 0.0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -1257,15 +1424,11 @@ k_sweep_fact_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
     double lw[WM][NW];
 #pragma unroll
     for (int w = 0; w < WM; ++w) {
-        cw[w] = 0;
+        const int ws = min(w, W - 1);
+        const int64_t f = ((int64_t)it.state * W + ws) * 32 + lane;
+        cw[w] = __ldg(T.cell_w + f);
 #pragma unroll
-        for (int k = 0; k < NW; ++k) lw[w][k] = 0.0;
-        if (w < W) {
-            const int64_t f = ((int64_t)it.state * W + w) * 32 + lane;
-            cw[w] = __ldg(T.cell_w + f);
-#pragma unroll
-            for (int k = 0; k < NW; ++k) lw[w][k] = __ldg(T.lam_w + (int64_t)k * T.lam_w_plane + f);
-        }
+        for (int k = 0; k < NW; ++k) lw[w][k] = __ldg(T.lam_w + (int64_t)k * T.lam_w_plane + f);
     }
 
     const int32_t* __restrict__ cup = T.cell + it.entry_base + lane;
@@ -1273,63 +1436,102 @@ k_sweep_fact_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
     const double* __restrict__ gp = T.g + it.g_base + lane;
     double best_v = CUDART_INF;
     int best_i = INT_MAX;
+    const int last = it.u_count - 1;
 
-    int c_n = __ldcs(cup);
-    double g_n = __ldcs(gp);
-    double l_n[NU];
+    // group of UB controls, streamed one group ahead (rows past the run repeat its last row)
+    int c_n[UB];
+    double g_n[UB], l_n[UB][NU];
 #pragma unroll
-    for (int k = 0; k < NU; ++k) l_n[k] = __ldcs(lup + (int64_t)k * T.lam_plane);
+    for (int b = 0; b < UB; ++b) {
+        const int64_t o = (int64_t)min(b, last) * 32;
+        c_n[b] = __ldcs(cup + o);
+        g_n[b] = __ldcs(gp + o);
+#pragma unroll
+        for (int k = 0; k < NU; ++k) l_n[b][k] = __ldcs(lup + (int64_t)k * T.lam_plane + o);
+    }
 
-    for (int uu = 0; uu < it.u_count; ++uu) {
-        const int cu = c_n;
-        const double gv = g_n;
-        double lu[NU];
+    for (int uu = 0; uu < it.u_count; uu += UB) {
+        int cu[UB];
+        double gv[UB], lu[UB][NU];
 #pragma unroll
-        for (int k = 0; k < NU; ++k) lu[k] = l_n[k];
-        if (uu + 1 < it.u_count) {
-            const int64_t o = (int64_t)(uu + 1) * 32;
-            c_n = __ldcs(cup + o);
-            g_n = __ldcs(gp + o);
+        for (int b = 0; b < UB; ++b) {
+            cu[b] = c_n[b];
+            gv[b] = g_n[b];
 #pragma unroll
-            for (int k = 0; k < NU; ++k) l_n[k] = __ldcs(lup + (int64_t)k * T.lam_plane + o);
+            for (int k = 0; k < NU; ++k) lu[b][k] = l_n[b][k];
         }
-        double v[WM];
+        if (uu + UB < it.u_count) {
 #pragma unroll
-        for (int w = 0; w < WM; ++w) {
-            if (w < W) {
+            for (int b = 0; b < UB; ++b) {
+                const int64_t o = (int64_t)min(uu + UB + b, last) * 32;
+                c_n[b] = __ldcs(cup + o);
+                g_n[b] = __ldcs(gp + o);
+#pragma unroll
+                for (int k = 0; k < NU; ++k) l_n[b][k] = __ldcs(lup + (int64_t)k * T.lam_plane + o);
+            }
+        }
+        double v[UB][WM];
+#pragma unroll
+        for (int b = 0; b < UB; ++b)
+#pragma unroll
+            for (int w = 0; w < WM; ++w) {
                 double lam[D];
-                Fact<D, MASK>::merge(lam, lu, lw[w]);
-                v[w] = Lerp<double, D, 0>::eval(Jprev, cu + cw[w], G.stride, lam);
+                Fact<D, MASK>::merge(lam, lu[b], lw[w]);
+                v[b][w] = Lerp<double, D, 0>::eval(Jprev, cu[b] + cw[w], G.stride, lam);
             }
-        }
-        double acc = 0.0;
 #pragma unroll
-        for (int w = 0; w < WM; ++w) {
-            if (w < W) {
-                const double jg = add_(gv, v[w]);
-                if (T.expect) acc = add_(acc, mul_(jg, p_sh[w]));
-                else acc = jg;
+        for (int b = 0; b < UB; ++b) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < WM; ++w) {
+                const double jg = add_(gv[b], v[b][w]);
+                const double nxt = T.expect ? add_(acc, mul_(jg, p_sh[w])) : jg;
+                acc = (w < W) ? nxt : acc;        // slots past W do not take part
             }
+            const int u = it.u_begin + uu + b;
+            if (uu + b <= last && u < Us && better(acc, u, best_v, best_i)) { best_v = acc; best_i = u; }
         }
-        const int u = it.u_begin + uu;
-        if (u < Us && better(acc, u, best_v, best_i)) { best_v = acc; best_i = u; }
     }
     part_val[item_id * 32 + lane] = best_v;
     part_idx[item_id * 32 + lane] = best_i;
+}
+
+template <int D, int MASK, int WM>
+static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                                double* part_val, int32_t* part_idx, cudaStream_t st) {
+    const int warps = 4;
+    unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
+    k_sweep_fact_tiled<D, MASK, WM><<<blocks, warps * 32, WM * sizeof(double), st>>>(
+        G, T, Jprev, part_val, part_idx);
 }
 
 template <int D, int MASK>
 static int launch_fact_m(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                          double* part_val, int32_t* part_idx, cudaStream_t st) {
     if (T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED) {
-        const int warps = 4;
-        unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
-        k_sweep_fact_tiled<D, MASK><<<blocks, warps * 32, (size_t)T.W * sizeof(double), st>>>(
-            G, T, Jprev, part_val, part_idx);
+        // register slots for the w-part: the smallest of 3 / 5 / 9 that holds W
+        if (T.W <= 3) launch_fact_tiled_w<D, MASK, 3>(G, T, Jprev, part_val, part_idx, st);
+        else if (T.W <= 5) launch_fact_tiled_w<D, MASK, 5>(G, T, Jprev, part_val, part_idx, st);
+        else launch_fact_tiled_w<D, MASK, SDP_FACTORED_MAX_W_REG>(G, T, Jprev, part_val, part_idx, st);
     } else {
         const int warps = 8;
         constexpr int NW = Fact<D, MASK>::NW;
         unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
+        if (MASK == 1 && tuning().hoist) {
+            // rows of the per-item inner-interpolation table that fit 44 KB of shared memory
+            const long budget = (44L * 1024 - 8L * T.W) / warps - (long)T.W * (8 * NW + 4);
+            int RP = (int)(budget / (8L * T.W)) - 1;
+            if (RP > 32) RP = 32;
+            if (RP >= 2) {
+                size_t shm = (size_t)T.W * 8 + (size_t)warps * ((size_t)T.W * (RP + 1 + NW) * 8 + (size_t)T.W * 4);
+                if (tuning().hoist_upl == 2)
+                    k_sweep_fact_hoist<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP);
+                else
+                    k_sweep_fact_hoist<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP);
+                SDP_LAUNCH_CHECK();
+                return SDP_OK;
+            }
+        }
         size_t shm = (size_t)T.W * 8 + (size_t)warps * T.W * (8 * NW + 4);
         if (tuning().upl == 2)
             k_sweep_fact<D, MASK, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);

@@ -606,7 +606,7 @@ def _dense_from_factored(T):
 
 
 FACTOR_CASES = {
-    "storage_ar1": 0b01, "searev": None, "curtail": 0b01,
+    "storage_ar1": 0b01, "searev": None, "curtail": 0b01, "coarse_controls": 0b01,
     "uw": 0b01, "wu": 0b10, "uww": 0b001, "wuw": 0b010, "uuw": 0b011, "wwu": 0b100,
     "uwu": 0b101, "wuu": 0b110, "xuw": 0b010, "xwu": 0b100,
 }
@@ -620,6 +620,10 @@ def _factor_case(api, which):
         return _searev_small(api).solver
     if which == "curtail":
         return _two_control_system(api)
+    if which == "coarse_controls":
+        # controls several state-grid rows apart: the per-item inner-interpolation
+        # table of the AF kernel does not fit and its generic path runs
+        return wl.storage_ar1(api, n_E=150, n_P=7, n_w=5, steps=(8. / 255, 0.1)).solver
     return _separable(api, which)
 
 
@@ -651,6 +655,34 @@ def test_factored_tables_and_sweep_equal_dense(product, backend, layout, which):
         assert np.array_equal(Jd.view(np.int64), Jf.view(np.int64))
         assert np.array_equal(pold, polf)
         J0 = Jd
+
+
+@gpu
+@pytest.mark.parametrize("which", ["storage_ar1", "searev", "coarse_controls", "uww"])
+def test_hoisted_inner_interpolation_is_bit_identical(product, which):
+    """AF kernel with and without the per-item table of inner interpolations"""
+    from stodynprog_b200 import _cabi
+    sv = _factor_case(_Api(product, "cuda", "control_minor", "auto", "on"), which)
+    assert sv.sweep_tables().u_mask == 1
+    lib = sv.engine.lib
+    J0 = np.random.default_rng(3).standard_normal(sv._state_grid_shape)
+    J0[0] = np.nan if which == "uww" else J0[0]
+    out = {}
+    try:
+        for hoist in (1, 0):
+            for upl in (4, 2):
+                _cabi.check(lib.sdp_set_option(b"hoist", hoist), "sdp_set_option")
+                _cabi.check(lib.sdp_set_option(b"upl", upl), "sdp_set_option")
+                _cabi.check(lib.sdp_set_option(b"hoist_upl", upl), "sdp_set_option")
+                out[hoist, upl] = sv.value_iteration(J0, report_time=False)
+    finally:
+        lib.sdp_set_option(b"hoist", 1)
+        lib.sdp_set_option(b"upl", 4)
+        lib.sdp_set_option(b"hoist_upl", 2)
+    Jr, polr = out[0, 4]
+    for key, (J, pol) in out.items():
+        assert np.array_equal(J.view(np.int64), Jr.view(np.int64)), key
+        assert np.array_equal(pol, polr, equal_nan=True), key
 
 
 def test_unfactorable_systems_fall_back_to_dense(product):
