@@ -184,6 +184,70 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def kernel_name(T):
+    """the streaming kernel the library launches for this table layout (defaults of
+    csrc/sdp_b200.cu: TMA ring R=8 for layout B, hoisted inner interpolation for AF
+    with u_mask == 1)"""
+    d = T.d
+    if T.factored:
+        if T.tiled:
+            return "k_sweep_fact_tiled<%d,%d,%d>" % (d, T.u_mask, 3 if T.W <= 3 else (5 if T.W <= 5 else 9))
+        return "k_sweep_fact_hoist<%d,2>" % d if T.u_mask == 1 else "k_sweep_fact<%d,%d,4>" % (d, T.u_mask)
+    return "k_sweep_tiled_tma<%d,8>" % d if T.tiled else "k_sweep<%d,4>" % d
+
+
+def ncu_traffic(workload, T, world):
+    """DRAM bytes per launch of the streaming kernel from the committed ncu capture
+    (profiles/r1_traffic.json; N=1 only), or None"""
+    if world != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f).get("%s/%s" % (workload, T.layout_name))
+    except Exception:
+        return None
+
+
+def time_sweeps(eng, T, J_prev, J_new, K, barrier):
+    """K timed sweeps, CUDA events on the launching stream around the whole loop and
+    around each streaming-kernel launch.  Returns (ms_total, k1_ms array, J_prev, J_new)."""
+    import torch
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for k in range(K):
+        eng.sweep(T, J_prev, J_new, events=kev[k])
+        J_prev, J_new = J_new, J_prev
+    end.record()
+    barrier()
+    return start.elapsed_time(end), np.array([a.elapsed_time(b) for a, b in kev]), J_prev, J_new
+
+
+def roofline_of(T, k1_ms, ms_total, K, peak, peak_src, traffic):
+    b_alg = T.algorithmic_bytes_per_backup
+    k1 = float(np.mean(k1_ms))
+    achieved = T.n_backups_local * b_alg / (k1 * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+         "kernel": kernel_name(T), "kernel_ms": k1, "kernel_share_of_step": k1 * K / ms_total,
+         "algorithmic_bytes_per_backup": b_alg,
+         "algorithmic_bytes_per_launch": T.n_backups_local * b_alg,
+         "table_layout": T.layout_name,
+         "table_bytes_resident": T.device_bytes,
+         "streamed_bytes_per_backup": T.streamed_bytes_per_backup,
+         "streamed_GBs": T.device_bytes / (k1 * 1e-3) / 1e9}
+    if T.factored:
+        r["note"] = ("factored (x,u)+(x,w) tables: the kernel streams %.2f B per backup instead of "
+                     "the dense layout's %.2f B, so `achieved` (dense algorithmic bytes / time, "
+                     "SURVEY.md 8d) exceeds the HBM peak; the kernel is bound by the L1 wavefronts "
+                     "of the corner gathers / the fp64 pipe, see `dense_layout` for the "
+                     "HBM-bound kernel on the same workload" % (T.streamed_bytes_per_backup, b_alg))
+    else:
+        r["padding_fill"] = T.n_backups_local / max(T.n_entries, 1)
+    return r
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -209,6 +273,7 @@ def run_ours(args):
     sv = prob.solver
     if args.layout != "auto":
         sv.table_layout = args.layout
+    sv.table_compress = args.compress
     if args.item_chunk:
         sv._item_chunk = args.item_chunk
     eng = sv.engine
@@ -219,8 +284,9 @@ def run_ours(args):
     n_grid = int(np.prod(dims))
 
     J_host = np.random.default_rng(0).standard_normal(dims)
-    J_prev = eng.to_device(J_host.reshape(-1))
-    J_new = torch.empty_like(J_prev)
+    J_prev, J_new = eng.J_pair(n_grid)
+    eng.begin_call(n_grid)
+    eng.upload_J(J_host, J_prev)
 
     def barrier():
         if world > 1:
@@ -232,24 +298,14 @@ def run_ours(args):
         J_prev, J_new = J_new, J_prev
 
     K = args.steps
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     launches0 = _cabi.launch_count()
-    barrier()
-    start.record()
-    for k in range(K):
-        eng.sweep(T, J_prev, J_new, events=kev[k])
-        J_prev, J_new = J_new, J_prev
-    end.record()
-    barrier()
+    ms_total, k1_ms, J_prev, J_new = time_sweeps(eng, T, J_prev, J_new, K, barrier)
     launches = _cabi.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = start.elapsed_time(end)
-    k1_ms = np.array([a.elapsed_time(b) for a, b in kev])
     t = torch.tensor([ms_total, float(np.mean(k1_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,21 +315,12 @@ def run_ours(args):
 
     # roofline of the streaming kernel on this rank's slab
     peak, peak_src = read_peaks()
-    b_alg = T.algorithmic_bytes_per_backup
-    k1_mean = float(np.mean(k1_ms))
-    achieved = T.n_backups_local * b_alg / (k1_mean * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "k_sweep_tiled" if T.tiled else "k_sweep",
-                "kernel_ms": k1_mean, "kernel_share_of_step": k1_mean * K / ms_total,
-                "algorithmic_bytes_per_backup": b_alg,
-                "algorithmic_bytes_per_launch": T.n_backups_local * b_alg,
-                "table_bytes_resident": T.device_bytes,
-                "padding_fill": T.n_backups_local / max(T.n_entries, 1)}
+    roofline = roofline_of(T, k1_ms, ms_total, K, peak, peak_src, ncu_traffic(args.workload, T, world))
+    J_keep = J_prev.clone()
 
     # end-to-end through the public API, host arrays in and out
     n_e2e = max(3, min(K, 10))
-    J_h = J_prev.cpu().numpy().reshape(dims)
+    J_h = J_keep.cpu().numpy().reshape(dims)
     for _ in range(2):
         J_h, pol_h = sv.value_iteration(J_h, report_time=False)
     barrier()
@@ -290,6 +337,32 @@ def run_ours(args):
            "h2d_bytes_per_step": int(J_h.nbytes), "d2h_bytes_per_step": int(J_h.nbytes + pol_h.nbytes),
            "steps": n_e2e, "ms_per_step": 1e3 * e2e_s / n_e2e,
            "api": "DPSolver.value_iteration(J_host) -> (J_host, pol_host)"}
+
+    # the same workload through the dense (x,u,w) tables: the HBM-bound kernel the
+    # roofline target is stated for
+    dense = None
+    if T.factored and not args.no_dense:
+        sv.table_compress = "off"
+        Td = sv.sweep_tables()
+        Ja, Jb = eng.J_pair(n_grid)
+        eng.begin_call(n_grid)
+        Ja.copy_(J_keep)
+        for _ in range(3):
+            eng.sweep(Td, Ja, Jb)
+            Ja, Jb = Jb, Ja
+        Kd = max(5, min(K, 10))
+        ms_d, k1_d, Ja, Jb = time_sweeps(eng, Td, Ja, Jb, Kd, barrier)
+        td = torch.tensor([ms_d], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dense = {"value": total_backups * Kd / (float(td[0]) * 1e-3), "unit": UNIT, "steps": Kd,
+                 "ms_per_step": float(td[0]) / Kd,
+                 "roofline": roofline_of(Td, k1_d, ms_d, Kd, peak, peak_src,
+                                         ncu_traffic(args.workload, Td, world))}
+        sv.table_compress = args.compress
+        del Td
+        sv.clear_tables()
+        torch.cuda.empty_cache()
 
     setup = torch.tensor([setup_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -308,7 +381,7 @@ def run_ours(args):
                          "reference is single-threaded: prange compiled without OpenMP)"
                          % (args.cpu_sample, b)}
     if rank == 0 and world == 1 and args.workload == "large" and not args.no_extra:
-        extra = measure_config3(sdp, peak)
+        extra = measure_config3(sdp, peak, peak_src)
 
     if rank == 0:
         line = {
@@ -317,15 +390,21 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "states": n_grid, "backups_per_sweep": total_backups,
                        "state_dims": list(dims), "perturbation_nodes": T.W,
-                       "table_layout": "state_minor" if T.tiled else "control_minor",
+                       "table_layout": T.layout_name,
                        "tabulate_mode": T.tabulate_mode, "item_chunk": eng.item_chunk,
-                       "parallelism": "state slabs x%d, all-gather of J per sweep" % world,
+                       "parallelism": "state slabs x%d, %s" % (
+                           world, "one rank" if world == 1 else
+                           ("J slab stored into every rank's buffer by the combine kernel over NVLink "
+                            "peer memory + flag wait" if eng.peer_exchange(n_grid) is not None
+                            else "NCCL all-gather of J per sweep")),
                        "l2": "tables streamed once per sweep (%.1f GB per GPU) >> 126 MB L2; "
                              "no flush needed" % (T.device_bytes / 1e9),
                        "J_init": "default_rng(0).standard_normal, then fed back sweep to sweep"},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "clocks": clocks, "setup_seconds": float(setup[0]),
         }
+        if dense is not None:
+            line["dense_layout"] = dense
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if extra is not None:
@@ -336,41 +415,32 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_config3(sdp, peak, steps=50, warmup=5):
+def measure_config3(sdp, peak, peak_src, steps=50, warmup=5):
     """BASELINE configs[2] (the 41x61 storage-AR1 grid of the notebook, 142 762 509
-    backups per sweep): the grid the north star's 60 % roofline target is quoted on."""
+    backups per sweep): the grid the north star's 60 % roofline target is quoted on.
+    Reported for the default (factored) tables and for the dense tables."""
     import torch
     from stodynprog_b200 import workloads as wl
-    prob = wl.storage_ar1(sdp)
-    sv = prob.solver
-    eng = sv.engine
-    T = sv.sweep_tables()
-    J_prev = eng.to_device(np.random.default_rng(0).standard_normal(41 * 61))
-    J_new = torch.empty_like(J_prev)
-    for _ in range(warmup):
-        eng.sweep(T, J_prev, J_new)
-        J_prev, J_new = J_new, J_prev
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(steps)]
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    s.record()
-    for k in range(steps):
-        eng.sweep(T, J_prev, J_new, events=kev[k])
-        J_prev, J_new = J_new, J_prev
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / steps
-    k1 = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    b_alg = T.algorithmic_bytes_per_backup
-    ach = T.n_backups_local * b_alg / (k1 * 1e-3) / 1e9
-    return {"workload": "howto storage-AR1 41x61 x 4001..8001 controls x 9 nodes",
-            "backups_per_sweep": T.n_backups_total, "ms_per_step": ms,
-            "value": T.n_backups_total / (ms * 1e-3), "unit": UNIT,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "kernel": "k_sweep", "kernel_ms": k1,
-                         "algorithmic_bytes_per_backup": b_alg},
-            "table_layout": "state_minor" if T.tiled else "control_minor"}
+    out = {"workload": "howto storage-AR1 41x61 x 4001..8001 controls x 9 nodes"}
+    for compress in ("auto", "off"):
+        prob = wl.storage_ar1(sdp)
+        sv = prob.solver
+        sv.table_compress = compress
+        eng = sv.engine
+        T = sv.sweep_tables()
+        J_prev, J_new = eng.J_pair(41 * 61)
+        eng.upload_J(np.random.default_rng(0).standard_normal(41 * 61), J_prev)
+        for _ in range(warmup):
+            eng.sweep(T, J_prev, J_new)
+            J_prev, J_new = J_new, J_prev
+        ms_total, k1_ms, J_prev, J_new = time_sweeps(eng, T, J_prev, J_new, steps,
+                                                     torch.cuda.synchronize)
+        out["backups_per_sweep"] = T.n_backups_total
+        out["default" if compress == "auto" else "dense_layout"] = {
+            "ms_per_step": ms_total / steps, "value": T.n_backups_total * steps / (ms_total * 1e-3),
+            "unit": UNIT,
+            "roofline": roofline_of(T, k1_ms, ms_total, steps, peak, peak_src, ncu_traffic("ar1", T, 1))}
+    return out
 
 
 def main():
@@ -383,6 +453,9 @@ def main():
     ap.add_argument("--n-E", dest="n_E", type=int, default=2000)
     ap.add_argument("--n-P", dest="n_P", type=int, default=500)
     ap.add_argument("--layout", default="auto", choices=["auto", "control_minor", "state_minor"])
+    ap.add_argument("--compress", default="auto", choices=["auto", "off", "on"],
+                    help="factored (x,u)+(x,w) tables (auto: whenever the system allows)")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-layout sub-measurement")
     ap.add_argument("--item-chunk", dest="item_chunk", type=int, default=0)
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=None,
                     help="states per CPU-baseline sample")

@@ -234,6 +234,34 @@ int sdp_sweep_partials(const SdpGrid* grid, const SdpTables* tab, const double* 
 int sdp_sweep_finalize(const SdpTables* tab, const double* part_val, const int32_t* part_idx,
                        double* J_out, int32_t* argmin_out, void* stream);
 
+/* Multi-GPU exchange over peer memory (NVLink 5 / NVSwitch), SURVEY.md §8e.
+ * The state grid is cut into one slab per rank; every rank keeps the whole J.
+ * Instead of an NCCL all-gather after the sweep, the per-state combine kernel
+ * stores each new J value straight into the J buffer of EVERY rank (peer-mapped
+ * pointers of a symmetric allocation), and the last CTA to finish publishes the
+ * rank's epoch in every rank's flag array; consumers wait on their local flags.
+ * All pointers are device pointers valid on the calling rank's GPU. */
+#define SDP_MAX_PEERS 8
+typedef struct SdpPeers {
+    int32_t world, rank;
+    double* J[SDP_MAX_PEERS];         /* [n_grid] destination buffer on every rank (J[rank] = local) */
+    uint64_t* flags[SDP_MAX_PEERS];   /* [world] flag array on every rank; this rank writes entry `rank` */
+    uint64_t* epoch;                  /* local: exchanges/barriers completed by this rank */
+    uint32_t* done;                   /* local: CTA completion counter, zero between launches */
+} SdpPeers;
+/* Fused per-state combine + all-gather: as sdp_sweep_finalize, but J goes to
+ * peers->J[r][state_begin + i] for every rank r; then epoch += 1 and the new
+ * epoch is released (system scope) into flags[r][rank] for every r.
+ * Every rank must issue the same sequence of finalize_p2p / barrier calls. */
+int sdp_sweep_finalize_p2p(const SdpTables* tab, const double* part_val, const int32_t* part_idx,
+                           int32_t* argmin_out, const SdpPeers* peers, int64_t state_begin,
+                           void* stream);
+/* Stream-ordered wait until every rank has published the local epoch (i.e. until
+ * the slabs written by the last sdp_sweep_finalize_p2p of all ranks have landed). */
+int sdp_p2p_wait(const SdpPeers* peers, void* stream);
+/* Stream-ordered barrier over the ranks: epoch += 1, publish, wait. */
+int sdp_p2p_barrier(const SdpPeers* peers, void* stream);
+
 /* K1' - fixed-policy backups (policy evaluation), `n_iter` iterations.
  * Replaces the body of DPSolver.eval_policy (stodynprog.py:743-763).
  * Tables are [w][n_states] planes (state index fastest):

@@ -44,7 +44,12 @@ if __name__ == "__main__":
                       % (which, compress, T.layout_name, time.perf_counter() - t0, T.n_items,
                          T.device_bytes / 1e9, T.streamed_bytes_per_backup), flush=True)
                 lib = sv.engine.lib
-                variants = [dict(upl=4), dict(upl=2)] if not T.tiled else [dict()]
+                if T.tiled:
+                    variants = [dict()]
+                elif T.factored:
+                    variants = [dict(hoist=1, hoist_upl=2), dict(hoist=1, hoist_upl=4), dict(hoist=0, upl=4)]
+                else:
+                    variants = [dict(upl=4), dict(upl=2)]
                 for v in variants:
                     opt(lib, **v)
                     r = time_sweeps(sv, T)

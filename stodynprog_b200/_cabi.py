@@ -58,6 +58,18 @@ class SdpTables(ctypes.Structure):
                 ("lam_w_plane", ctypes.c_int64)]
 
 
+SDP_MAX_PEERS = 8
+
+
+class SdpPeers(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32),
+                ("rank", ctypes.c_int32),
+                ("J", ctypes.c_void_p * SDP_MAX_PEERS),
+                ("flags", ctypes.c_void_p * SDP_MAX_PEERS),
+                ("epoch", ctypes.c_void_p),
+                ("done", ctypes.c_void_p)]
+
+
 # numpy mirrors of the per-state descriptor and the work item (host-built arrays
 # uploaded verbatim; layouts must match the C structs, checked by the tests)
 STATE_DESC_DTYPE = np.dtype([("entry_off", np.int64),
@@ -100,6 +112,10 @@ SIGNATURES = {
     "sdp_sweep": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdp_sweep_partials": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp]),
     "sdp_sweep_finalize": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp]),
+    "sdp_sweep_finalize_p2p": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp,
+                                              ctypes.POINTER(SdpPeers), _i64, _vp]),
+    "sdp_p2p_wait": (ctypes.c_int, [ctypes.POINTER(SdpPeers), _vp]),
+    "sdp_p2p_barrier": (ctypes.c_int, [ctypes.POINTER(SdpPeers), _vp]),
     "sdp_policy_eval": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
                                        _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
     "sdp_policy_values": (ctypes.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -1261,7 +1261,8 @@ k_sweep_fact(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
 template <int D, int UPL>
 __global__ void __launch_bounds__(256)
 k_sweep_fact_hoist(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
-                   double* __restrict__ part_val, int32_t* __restrict__ part_idx, int RP) {
+                   double* __restrict__ part_val, int32_t* __restrict__ part_idx, int RP,
+                   double inv_stride0) {
     constexpr int NW = D - 1;
     extern __shared__ __align__(16) unsigned char fsm[];
     const int W = T.W;
@@ -1318,7 +1319,6 @@ k_sweep_fact_hoist(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
 
     double best_v = CUDART_INF;
     int best_i = INT_MAX;
-    const double inv_stride0 = 1.0 / (double)stride0;
     for (int u0 = lane * UPL; u0 < it.u_count; u0 += 32 * UPL) {
         const int64_t off = it.entry_base + u0;
         int cu[UPL];
@@ -1524,10 +1524,11 @@ static int launch_fact_m(const GridT<double>& G, const SdpTables& T, const doubl
             if (RP > 32) RP = 32;
             if (RP >= 2) {
                 size_t shm = (size_t)T.W * 8 + (size_t)warps * ((size_t)T.W * (RP + 1 + NW) * 8 + (size_t)T.W * 4);
+                const double inv0 = 1.0 / (double)G.stride[0];   // host side: keeps fp64 division out of the kernel
                 if (tuning().hoist_upl == 2)
-                    k_sweep_fact_hoist<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP);
+                    k_sweep_fact_hoist<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0);
                 else
-                    k_sweep_fact_hoist<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP);
+                    k_sweep_fact_hoist<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0);
                 SDP_LAUNCH_CHECK();
                 return SDP_OK;
             }
@@ -1648,6 +1649,149 @@ extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double
     int rc = sdp_sweep_partials(grid, tab, J_prev, part_val, part_idx, stream);
     if (rc) return rc;
     return sdp_sweep_finalize(tab, part_val, part_idx, J_out, argmin_out, stream);
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU: fused combine + all-gather over peer memory, flag barrier
+// ---------------------------------------------------------------------------
+struct PeersDev {
+    int world, rank;
+    double* J[SDP_MAX_PEERS];
+    unsigned long long* flags[SDP_MAX_PEERS];
+    unsigned long long* epoch;
+    unsigned int* done;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// per-state combine of the partial minima; J is stored into every rank's buffer
+template <bool TILED>
+__global__ void __launch_bounds__(256)
+k_sweep_finalize_p2p(int64_t n_states, const int64_t* __restrict__ item_begin,
+                     const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
+                     int32_t* __restrict__ argmin_out, PeersDev P, int64_t state_begin) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_states) {
+        const int64_t unit = TILED ? (i >> 5) : i;
+        const int lane = TILED ? (int)(i & 31) : 0;
+        const int width = TILED ? 32 : 1;
+        double bv = CUDART_INF;
+        int bi = INT_MAX;
+        for (int64_t k = item_begin[unit]; k < item_begin[unit + 1]; ++k) {
+            const double v = part_val[k * width + lane];
+            const int ix = part_idx[k * width + lane];
+            if (better(v, ix, bv, bi)) { bv = v; bi = ix; }
+        }
+        argmin_out[i] = bi;
+#pragma unroll
+        for (int r = 0; r < SDP_MAX_PEERS; ++r)
+            if (r < P.world) P.J[r][state_begin + i] = bv;
+    }
+    // publish: every CTA fences its peer stores, the last one to finish releases the epoch
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(P.done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence();
+            *P.done = 0;
+            const unsigned long long e = *P.epoch + 1;
+            *P.epoch = e;
+            __threadfence_system();
+            for (int r = 0; r < P.world; ++r) st_release_sys(P.flags[r] + P.rank, e);
+        }
+    }
+}
+
+__global__ void k_p2p_wait(PeersDev P) {
+    const int t = threadIdx.x;
+    if (t < P.world) {
+        const unsigned long long e = *P.epoch;
+        while (ld_acquire_sys(P.flags[P.rank] + t) < e) { __nanosleep(20); }
+    }
+}
+
+__global__ void k_p2p_barrier(PeersDev P) {
+    __shared__ unsigned long long e_sh;
+    if (threadIdx.x == 0) {
+        e_sh = *P.epoch + 1;
+        *P.epoch = e_sh;
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < P.world) {
+        st_release_sys(P.flags[t] + P.rank, e_sh);
+        while (ld_acquire_sys(P.flags[P.rank] + t) < e_sh) { __nanosleep(20); }
+    }
+}
+
+static int make_peers(const SdpPeers* p, PeersDev* out, const char* who) {
+    if (!p) return fail(SDP_EINVAL, "%s: peers is NULL", who);
+    if (p->world < 1 || p->world > SDP_MAX_PEERS || p->rank < 0 || p->rank >= p->world)
+        return fail(SDP_EINVAL, "%s: bad world/rank", who);
+    if (!p->epoch || !p->done) return fail(SDP_EINVAL, "%s: NULL epoch/done counter", who);
+    out->world = p->world;
+    out->rank = p->rank;
+    for (int r = 0; r < SDP_MAX_PEERS; ++r) {
+        out->J[r] = (r < p->world) ? p->J[r] : nullptr;
+        out->flags[r] = (r < p->world) ? (unsigned long long*)p->flags[r] : nullptr;
+        if (r < p->world && !p->flags[r]) return fail(SDP_EINVAL, "%s: NULL flag array", who);
+    }
+    out->epoch = (unsigned long long*)p->epoch;
+    out->done = p->done;
+    return SDP_OK;
+}
+
+extern "C" int sdp_sweep_finalize_p2p(const SdpTables* tab, const double* part_val,
+                                      const int32_t* part_idx, int32_t* argmin_out,
+                                      const SdpPeers* peers, int64_t state_begin, void* stream) {
+    if (!tab) return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_p2p: tables is NULL");
+    const SdpTables& T = *tab;
+    int rc = check_tables(T, "sdp_sweep_finalize_p2p");
+    if (rc) return rc;
+    PeersDev P;
+    rc = make_peers(peers, &P, "sdp_sweep_finalize_p2p");
+    if (rc) return rc;
+    for (int r = 0; r < P.world; ++r)
+        if (!P.J[r]) return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_p2p: NULL J buffer");
+    if (state_begin < 0 || (T.n_states > 0 && (!part_val || !part_idx || !argmin_out)))
+        return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_p2p: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    // at least one CTA even for an empty slab: the epoch must advance on every rank
+    unsigned blocks = (unsigned)((T.n_states + 255) / 256);
+    if (blocks == 0) blocks = 1;
+    if (is_tiled(T))
+        k_sweep_finalize_p2p<true><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin);
+    else
+        k_sweep_finalize_p2p<false><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+extern "C" int sdp_p2p_wait(const SdpPeers* peers, void* stream) {
+    PeersDev P;
+    int rc = make_peers(peers, &P, "sdp_p2p_wait");
+    if (rc) return rc;
+    k_p2p_wait<<<1, 32, 0, (cudaStream_t)stream>>>(P);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+extern "C" int sdp_p2p_barrier(const SdpPeers* peers, void* stream) {
+    PeersDev P;
+    int rc = make_peers(peers, &P, "sdp_p2p_barrier");
+    if (rc) return rc;
+    k_p2p_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(P);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
 }
 
 // ---------------------------------------------------------------------------

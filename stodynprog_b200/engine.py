@@ -11,6 +11,7 @@ controls; each rank holds the tables of its slab only; the value function J
 new J slab (+ an all-reduce-max of the sup-norm residual when asked).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -114,6 +115,62 @@ class Collective(object):
             self.dist.barrier(group=self.group)
 
 
+class PeerExchange(object):
+    """Symmetric (peer-mapped) J double buffer + flag words for the fused
+    combine + all-gather of the sweep (`sdp_sweep_finalize_p2p`): every rank's
+    combine kernel stores its slab of the new J straight into every rank's
+    buffer over NVLink and publishes an epoch; consumers wait on local flags.
+
+    Buffer protocol (ping-pong): a sweep reads J[k] and writes J[1-k] on all
+    ranks; the per-sweep wait guarantees that a rank can only be one sweep ahead
+    of its peers, so the buffer it writes is never one a peer still reads.
+    `barrier()` must separate public calls (a peer may still be copying the last
+    result out of the buffer the next call will write)."""
+
+    def __init__(self, engine, n_grid):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        coll = engine.coll
+        self.engine = engine
+        self.n_grid = n_grid
+        world, rank = coll.world, coll.rank
+        if world > _cabi.SDP_MAX_PEERS:
+            raise ValueError("peer exchange supports at most %d ranks" % _cabi.SDP_MAX_PEERS)
+        group = coll.group if coll.group is not None else coll.dist.group.WORLD
+        n_pad = (n_grid + 31) // 32 * 32
+        # [J0 | J1 | flags (world u64, padded to 32 words)]
+        self.buf = symm.empty(2 * n_pad + 32, dtype=torch.float64, device=engine.device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        torch.cuda.synchronize(engine.device)
+        self.hdl.barrier()                      # zeros visible everywhere before first use
+        self.J = [self.buf[:n_grid], self.buf[n_pad:n_pad + n_grid]]
+        self.local = torch.zeros(4, dtype=torch.int64, device=engine.device)   # [epoch, done]
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.peers = []
+        for k in range(2):
+            P = _cabi.SdpPeers()
+            P.world, P.rank = world, rank
+            for r in range(world):
+                P.J[r] = ptrs[r] + 8 * k * n_pad
+                P.flags[r] = ptrs[r] + 8 * 2 * n_pad
+            P.epoch = self.local.data_ptr()
+            P.done = self.local.data_ptr() + 8
+            self.peers.append(P)
+
+    def index_of(self, t):
+        """0/1 when `t` is one of the two J buffers, else None"""
+        for k in range(2):
+            if t.data_ptr() == self.J[k].data_ptr() and t.numel() == self.n_grid:
+                return k
+        return None
+
+    def barrier(self):
+        eng = self.engine
+        rc = eng.lib.sdp_p2p_barrier(ctypes.byref(self.peers[0]), eng.stream)
+        _cabi.check(rc, "sdp_p2p_barrier")
+
+
 class SweepTables(object):
     """Dense (cell, lam, g) tables of one slab of states, resident in HBM,
     plus the host-side control discretisation needed to turn argmin indices
@@ -205,7 +262,9 @@ class Engine(object):
             self.lib = _test_lib
             self.device = torch.device("cpu")
             self._cuda = False
+            self._peer = {}
             return
+        self._peer = {}                          # n_grid -> PeerExchange | None
         self.lib = _cabi.load_library()          # raises if the extension is missing
         if not torch.cuda.is_available():
             raise _cabi.SdpLibraryError(
@@ -245,6 +304,57 @@ class Engine(object):
     def sync(self):
         if self._cuda:
             _torch().cuda.synchronize(self.device)
+
+    # -- J buffers / peer exchange ------------------------------------------
+    def peer_exchange(self, n_grid):
+        """PeerExchange for grids of n_grid points, or None (one rank, CPU test
+        seam, SDP_P2P=0, or symmetric memory not available: the NCCL all-gather
+        path is used instead)."""
+        if n_grid not in self._peer:
+            px = None
+            if self._cuda and self.coll.world > 1 and os.environ.get("SDP_P2P", "1") != "0":
+                try:
+                    px = PeerExchange(self, n_grid)
+                except Exception as e:            # no P2P / symmetric memory on this box
+                    import warnings
+                    warnings.warn("peer-memory exchange unavailable (%s: %s); using NCCL all-gather"
+                                  % (type(e).__name__, e))
+                    px = None
+                # every rank must take the same path
+                ok = self.coll.all_gather_object(px is not None)
+                if not all(ok):
+                    px = None
+            self._peer[n_grid] = px
+        return self._peer[n_grid]
+
+    def J_pair(self, n_grid):
+        """two device fp64 [n_grid] buffers to ping-pong sweeps between; with several
+        ranks they live in symmetric memory so that the sweep's combine kernel can
+        store new values directly into every rank's copy"""
+        torch = _torch()
+        px = self.peer_exchange(n_grid)
+        if px is not None:
+            return px.J[0], px.J[1]
+        return (torch.empty(n_grid, dtype=torch.float64, device=self.device),
+                torch.empty(n_grid, dtype=torch.float64, device=self.device))
+
+    def begin_call(self, n_grid):
+        """separate two public calls that reuse the symmetric J buffers"""
+        px = self._peer.get(n_grid)
+        if px is not None:
+            px.barrier()
+
+    def upload_J(self, J_host, dst):
+        """host fp64 array -> device buffer `dst` (pinned staging, async)"""
+        torch = _torch()
+        a = np.ascontiguousarray(np.asarray(J_host, dtype=np.float64).reshape(-1))
+        if self._cuda:
+            pin = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+            pin.numpy()[:] = a
+            dst.copy_(pin, non_blocking=True)
+        else:
+            dst.copy_(torch.from_numpy(a))
+        return dst
 
     # -- sweep tables -----------------------------------------------------
     def build_sweep_tables(self, solver, t_k=None, reuse=None):
@@ -610,13 +720,33 @@ class Engine(object):
         """One full Bellman sweep: K1 on the slab, all-gather of the J slab into
         J_new (device fp64 [n_grid]), optional relative-DP shift and optional
         sup-norm residual max|J_new - J_prev| (all-reduced)."""
-        self.sweep_local(T, J_prev, events)
         n = T.n_states
         sb = T.state_begin
-        if self.coll.world == 1:
-            J_new.copy_(T.J_out[:n])
+        px = self._peer.get(J_new.numel()) if self.coll.world > 1 else None
+        k_new = px.index_of(J_new) if px is not None else None
+        if k_new is not None:
+            # fused combine + all-gather: K1, then the combine kernel stores the slab
+            # into every rank's J_new over NVLink and publishes the epoch
+            if events is not None:
+                events[0].record()
+            rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
+                                             self._ptr(J_prev), self._ptr(T.part_val),
+                                             self._ptr(T.part_idx), self.stream)
+            _cabi.check(rc, "sdp_sweep_partials")
+            if events is not None:
+                events[1].record()
+            rc = self.lib.sdp_sweep_finalize_p2p(ctypes.byref(T.c_tables), self._ptr(T.part_val),
+                                                 self._ptr(T.part_idx), self._ptr(T.argmin),
+                                                 ctypes.byref(px.peers[k_new]), sb, self.stream)
+            _cabi.check(rc, "sdp_sweep_finalize_p2p")
+            rc = self.lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), self.stream)
+            _cabi.check(rc, "sdp_p2p_wait")
         else:
-            self.coll.all_gather_slabs(T.J_out[:n], T.bounds, out=J_new)
+            self.sweep_local(T, J_prev, events)
+            if self.coll.world == 1:
+                J_new.copy_(T.J_out[:n])
+            else:
+                self.coll.all_gather_slabs(T.J_out[:n], T.bounds, out=J_new)
         if rel_ref_index is not None:
             rc = self.lib.sdp_rel_shift(self._ptr(J_new), J_new.numel(), int(rel_ref_index),
                                         self._ptr(ref_out), self.stream)

@@ -182,8 +182,10 @@ class DPSolver(object):
         state_dims = tuple(len(g) for g in self.state_grid)
         nb_control = len(self.sys.control)
         T = tables if tables is not None else self.sweep_tables(t_k)
-        J_prev = eng.to_device(np.asarray(J_next, dtype=float).reshape(-1))
-        J_new = torch.empty_like(J_prev)
+        n_grid = int(np.prod(state_dims))
+        J_prev, J_new = eng.J_pair(n_grid)
+        eng.begin_call(n_grid)
+        eng.upload_J(J_next, J_prev)
         ref_out = None
         ref_flat = None
         if rel_dp:
@@ -344,8 +346,10 @@ class DPSolver(object):
         nb_control = len(self.sys.control)
         T = self.sweep_tables(None)
         J0 = np.zeros(state_dims) if J_zero is None else np.asarray(J_zero, dtype=float)
-        J_prev = eng.to_device(J0.reshape(-1))
-        J_new = torch.empty_like(J_prev)
+        n_grid = int(np.prod(state_dims))
+        J_prev, J_new = eng.J_pair(n_grid)
+        eng.begin_call(n_grid)
+        eng.upload_J(J0, J_prev)
         resid = torch.zeros(1, dtype=torch.float64, device=eng.device)
         ref_out = torch.zeros(1, dtype=torch.float64, device=eng.device) if rel_dp else None
         ref_flat = int(np.ravel_multi_index(self._state_ref_ind, state_dims)) if rel_dp else None

@@ -43,6 +43,10 @@ def main():
             if rank == 0:
                 print("[%s] sweep %d: policy mismatches %d, J rel err %.2e" % (layout, k, bad, err))
         T = sv.last_tables
+        px = sv.engine.peer_exchange(T.host_full.lo.shape[0])
+        if rank == 0:
+            print("[%s] tables %s, exchange: %s" % (layout, T.layout_name,
+                  "peer memory (fused combine + all-gather)" if px is not None else "NCCL all-gather"))
         print("[%s] rank %d slab [%d, %d) backups %d of %d" % (layout, rank, T.state_begin,
               T.state_begin + T.n_states, T.n_backups_local, T.n_backups_total), flush=True)
         (Jd, Jr), polp = sv.policy_iteration(prob.initial_policy(), 50, 4, rel_dp=True)
