@@ -391,7 +391,7 @@ def run_ours(args):
             "config": {"workload": name, "states": n_grid, "backups_per_sweep": total_backups,
                        "state_dims": list(dims), "perturbation_nodes": T.W,
                        "table_layout": T.layout_name,
-                       "tabulate_mode": T.tabulate_mode, "item_chunk": eng.item_chunk,
+                       "tabulate_mode": T.tabulate_mode, "item_chunk": T.item_chunk,
                        "parallelism": "state slabs x%d, %s" % (
                            world, "one rank" if world == 1 else
                            ("J slab stored into every rank's buffer by the combine kernel over NVLink "

@@ -1671,6 +1671,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded flag wait: a peer that died (or a call sequence that differs between the
+// ranks) must surface as a CUDA error on this rank, not as a hung GPU.
+#define SDP_P2P_TIMEOUT_NS 30000000000ULL
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long e) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < e) {
+        __nanosleep(20);
+        if (global_ns() - t0 > SDP_P2P_TIMEOUT_NS) __trap();
+    }
+}
+
 // per-state combine of the partial minima; J is stored into every rank's buffer
 template <bool TILED>
 __global__ void __launch_bounds__(256)
@@ -1714,7 +1730,7 @@ __global__ void k_p2p_wait(PeersDev P) {
     const int t = threadIdx.x;
     if (t < P.world) {
         const unsigned long long e = *P.epoch;
-        while (ld_acquire_sys(P.flags[P.rank] + t) < e) { __nanosleep(20); }
+        wait_flag(P.flags[P.rank] + t, e);
     }
 }
 
@@ -1729,7 +1745,7 @@ __global__ void k_p2p_barrier(PeersDev P) {
     const int t = threadIdx.x;
     if (t < P.world) {
         st_release_sys(P.flags[t] + P.rank, e_sh);
-        while (ld_acquire_sys(P.flags[P.rank] + t) < e_sh) { __nanosleep(20); }
+        wait_flag(P.flags[P.rank] + t, e_sh);
     }
 }
 

@@ -48,6 +48,19 @@ def partition_by_weight(weights, world):
     return bounds
 
 
+ITEMS_TARGET = 148 * 96     # work items wanted per sweep launch (about 4 waves of warps)
+
+
+def pick_item_chunk(unit_U, min_chunk, max_chunk=512, target=ITEMS_TARGET):
+    """largest power-of-two-scaled chunk in [min_chunk, max_chunk] giving at least
+    `target` work items for units with `unit_U` controls each"""
+    unit_U = np.asarray(unit_U, dtype=np.int64)
+    chunk = max_chunk
+    while chunk > min_chunk and int(((unit_U + chunk - 1) // chunk).sum()) < target:
+        chunk //= 2
+    return max(chunk, min_chunk)
+
+
 class Collective(object):
     """Thin wrapper over torch.distributed for the per-sweep exchange.
     Works with NCCL (CUDA tensors, on the current stream) and gloo (CPU tensors,
@@ -203,6 +216,7 @@ class SweepTables(object):
         self.U_dev = None
         self.tabulate_mode = None
         self.setup_seconds = 0.0
+        self.item_chunk = 0        # controls per work item used for these tables
 
     @property
     def algorithmic_bytes_per_backup(self):
@@ -252,6 +266,10 @@ class Engine(object):
     def __init__(self, device=None, group=None, item_chunk=None, _test_lib=None):
         torch = _torch()
         self.coll = Collective(group)
+        # controls per work item (one warp each).  None = adaptive: 512, halved while the
+        # slab yields fewer warps than a few waves of the machine (small grids, or
+        # one slab of a grid cut over 8 GPUs), see build_sweep_tables
+        self.item_chunk_auto = not item_chunk
         self.item_chunk = int(item_chunk) if item_chunk else 512
         if self.item_chunk % 4:
             raise ValueError("item_chunk must be a multiple of 4")
@@ -637,6 +655,12 @@ class Engine(object):
             units, unit_U = n_tiles, tile_U
         else:
             units, unit_U = n, U
+        if self.item_chunk_auto:
+            # a B200 holds 148 SMs x 16..64 resident warps; with fewer items than a few
+            # waves the sweep is latency-bound (and its tail is long), so cut the runs
+            # shorter.  Layout A walks 128 controls per warp iteration, layout B one.
+            chunk = pick_item_chunk(unit_U, 128 if not tiled else 32)
+        T.item_chunk = chunk
         n_it = (unit_U + chunk - 1) // chunk
         item_begin = np.zeros(units + 1, dtype=np.int64)
         np.cumsum(n_it, out=item_begin[1:])
