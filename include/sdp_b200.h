@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SDP_ABI_VERSION 2
+#define SDP_ABI_VERSION 3
 #define SDP_MAX_D 4 /* the reference dispatches d = 1..4 (multilinear_cython.pyx:36-47) */
 
 /* error codes */
@@ -154,6 +154,9 @@ typedef struct SdpTables {
     const int32_t* cell_w;
     const double* lam_w;
     int64_t lam_w_plane;
+    /* HOST copy of p[W] (the same values as `p`).  Required by layout BF, whose
+     * kernel takes the probabilities as launch constants; ignored otherwise. */
+    const double* p_host;
 } SdpTables;
 
 /* ABI / build identification. */

@@ -12,7 +12,7 @@ import numpy as np
 
 SDP_MAX_D = 4
 SDP_MAX_C = 4
-SDP_ABI_VERSION = 2
+SDP_ABI_VERSION = 3
 LAYOUT_CONTROL_MINOR = 0   # "A": [state][w][u]
 LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
 LAYOUT_CONTROL_MINOR_FACTORED = 2   # "AF": (x,u) part [state][Upad] + (x,w) part [state][W]
@@ -55,7 +55,8 @@ class SdpTables(ctypes.Structure):
                 ("reserved", ctypes.c_int32),
                 ("cell_w", ctypes.c_void_p),
                 ("lam_w", ctypes.c_void_p),
-                ("lam_w_plane", ctypes.c_int64)]
+                ("lam_w_plane", ctypes.c_int64),
+                ("p_host", ctypes.c_void_p)]
 
 
 SDP_MAX_PEERS = 8

@@ -1401,16 +1401,20 @@ k_sweep_fact_hoist(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
 #ifndef SDP_BF_MINB
 #define SDP_BF_MINB 1    // __launch_bounds__ min CTAs per SM of the BF kernel
 #endif
+// The probabilities enter the BF kernel as launch constants (kernel parameter =
+// constant bank, an operand of the DMUL itself): ncu showed the shared-memory
+// reads of p[w] taking 1 of the ~9.6 L1 data-pipe wavefronts per warp step of a
+// kernel that is bound by exactly that pipe.
+struct PVals {
+    double v[SDP_FACTORED_MAX_W_REG];
+};
+
 template <int D, int MASK, int WM>
 __global__ void __launch_bounds__(128, SDP_BF_MINB)
 k_sweep_fact_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
-                   double* __restrict__ part_val, int32_t* __restrict__ part_idx) {
+                   double* __restrict__ part_val, int32_t* __restrict__ part_idx, PVals PV) {
     constexpr int NU = Fact<D, MASK>::NU, NW = Fact<D, MASK>::NW;
     constexpr int UB = SDP_BF_UB;
-    extern __shared__ double p_sh[];
-    for (int i = threadIdx.x; i < WM; i += blockDim.x)
-        p_sh[i] = (i < T.W) ? (T.expect ? T.p[i] : 1.0) : 0.0;
-    __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int64_t item_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1485,7 +1489,7 @@ k_sweep_fact_tiled(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
 #pragma unroll
             for (int w = 0; w < WM; ++w) {
                 const double jg = add_(gv[b], v[b][w]);
-                const double nxt = T.expect ? add_(acc, mul_(jg, p_sh[w])) : jg;
+                const double nxt = T.expect ? add_(acc, mul_(jg, PV.v[w])) : jg;
                 acc = (w < W) ? nxt : acc;        // slots past W do not take part
             }
             const int u = it.u_begin + uu + b;
@@ -1501,8 +1505,10 @@ static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, cons
                                 double* part_val, int32_t* part_idx, cudaStream_t st) {
     const int warps = 4;
     unsigned blocks = (unsigned)((T.n_items + warps - 1) / warps);
-    k_sweep_fact_tiled<D, MASK, WM><<<blocks, warps * 32, WM * sizeof(double), st>>>(
-        G, T, Jprev, part_val, part_idx);
+    PVals pv;
+    for (int w = 0; w < SDP_FACTORED_MAX_W_REG; ++w)
+        pv.v[w] = (w < T.W) ? (T.expect ? T.p_host[w] : 1.0) : 0.0;
+    k_sweep_fact_tiled<D, MASK, WM><<<blocks, warps * 32, 0, st>>>(G, T, Jprev, part_val, part_idx, pv);
 }
 
 template <int D, int MASK>
@@ -1590,6 +1596,8 @@ static int check_tables(const SdpTables& T, const char* who) {
             return fail(SDP_EINVAL, "%s: factored tables need g per (x,u) and a w-part", who);
         if (T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED && T.W > SDP_FACTORED_MAX_W_REG)
             return fail(SDP_EINVAL, "%s: layout BF supports at most 9 perturbation nodes", who);
+        if (T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED && T.expect && !T.p_host)
+            return fail(SDP_EINVAL, "%s: layout BF needs p_host (host copy of the probabilities)", who);
         if (T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED && T.W > 128)
             return fail(SDP_EINVAL, "%s: layout AF supports at most 128 perturbation nodes", who);
     }

@@ -48,7 +48,12 @@ def partition_by_weight(weights, world):
     return bounds
 
 
-ITEMS_TARGET = 148 * 96     # work items wanted per sweep launch (about 4 waves of warps)
+# work items wanted per sweep launch.  Measured on a B200 (profiles/r1_slab_scaling.txt):
+# the streaming kernels keep their rate down to ~26 warps per SM (3 907 items of 512
+# controls: 565 G backups/s vs 626 G with 31 250) and LOSE ~10 % when the runs are cut
+# to 128 controls, so runs are only shortened when a launch would not even fill the
+# machine once (148 SMs x 16 warps).
+ITEMS_TARGET = 148 * 16
 
 
 def pick_item_chunk(unit_U, min_chunk, max_chunk=512, target=ITEMS_TARGET):
@@ -200,6 +205,7 @@ class SweepTables(object):
         self.n_states = 0
         self.host_full = None      # HostStateTable of ALL states (replicated)
         self.cell = self.lam = self.g = self.p = None
+        self.p_host = None
         self.items = self.item_begin = None
         self.part_val = self.part_idx = None
         self.J_out = self.argmin = None
@@ -410,8 +416,17 @@ class Engine(object):
         # pass 1: control boxes. Every rank scans an equal share, then the full
         # host table is replicated (it is needed to map argmin -> control values).
         eq = [n_grid * r // world for r in range(world + 1)]
-        mine = tb.state_tuples(state_grid, eq[rank], eq[rank + 1])
-        part = tb.scan_control_boxes(sys, solver.control_steps, mine, t_k)
+        mode = getattr(solver, "tabulate", "auto")
+        mine = None
+        part = None
+        if mode != "per_state":
+            # one vectorised control_box call, trusted only if sample states agree
+            # bit-for-bit with the reference's per-state calls
+            part = tb.scan_control_boxes_batched(sys, solver.control_steps, state_grid,
+                                                 eq[rank], eq[rank + 1], t_k)
+        if part is None:
+            mine = tb.state_tuples(state_grid, eq[rank], eq[rank + 1])
+            part = tb.scan_control_boxes(sys, solver.control_steps, mine, t_k)
         parts = coll.all_gather_object((part.lo, part.hi, part.npts))
         nb_control = len(sys.control)
         host_full = tb.HostStateTable(n_grid, nb_control)
@@ -485,17 +500,16 @@ class Engine(object):
         T.host_full = host_full
         T.n_backups_local = int(U.sum()) * W
         T.n_backups_total = int(U_all.sum()) * W
-        if nb_perturb == 1:
-            T.p = self.to_device(np.asarray(solver.perturb_proba[0], dtype=float))
-        else:
-            T.p = self.to_device(np.ones(1))
+        # host copy of the probabilities, kept alive with the tables (SdpTables.p_host)
+        T.p_host = np.ascontiguousarray(solver.perturb_proba[0], dtype=np.float64).copy() \
+            if nb_perturb == 1 else np.ones(1)
+        T.p = self.to_device(T.p_host)
         T.U_dev = self.to_device(U.astype(np.int32)) if n else torch.zeros(1, dtype=torch.int32, device=dev)
         # replicated control discretisation, for the argmin -> control value kernel
         T.lo_dev = self.to_device(host_full.lo.reshape(-1)) if nb_control else None
         T.hi_dev = self.to_device(host_full.hi.reshape(-1)) if nb_control else None
         T.npts_dev = self.to_device(host_full.npts.astype(np.int32).reshape(-1)) if nb_control else None
         T.nb_control = nb_control
-        mode = getattr(solver, "tabulate", "auto")
         T.tabulate_mode = None
 
         def ensure(name, numel, dtype):
@@ -603,7 +617,7 @@ class Engine(object):
                 tb.tabulate_states_batched(sys, state_grid, sb, se, host, w_grid, t_k, entry_off,
                                            g_off, Upad, g_per_w, flush, align=align)
             else:
-                states = mine if (sb, se) == (eq[rank], eq[rank + 1]) else \
+                states = mine if (mine is not None and (sb, se) == (eq[rank], eq[rank + 1])) else \
                     tb.state_tuples(state_grid, sb, se)
                 tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
                                    g_per_w, flush, align=align)
@@ -707,6 +721,7 @@ class Engine(object):
         else:
             c.layout = _cabi.LAYOUT_STATE_MINOR if tiled else _cabi.LAYOUT_CONTROL_MINOR
         c.p = T.p.data_ptr()
+        c.p_host = T.p_host.ctypes.data
         c.items = T.items.data_ptr()
         c.n_items = n_items
         c.item_begin = T.item_begin.data_ptr()

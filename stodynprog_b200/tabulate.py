@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["control_grid_counts", "control_axis_values", "HostStateTable", "tabulate_states",
+__all__ = ["scan_control_boxes", "scan_control_boxes_batched", "control_grid_counts", "control_axis_values", "HostStateTable", "tabulate_states",
            "tabulate_states_batched", "GDependsOnW", "BatchedMismatch", "NotFactorable",
            "probe_factor_mask", "check_factorable"]
 
@@ -171,6 +171,55 @@ def scan_control_boxes(sys, control_steps, states, t_k=None):
         tab.hi[i] = hi
         tab.npts[i] = npts
     return tab
+
+
+def scan_control_boxes_batched(sys, control_steps, state_grid, begin, end, t_k=None, verify=16):
+    """First pass in ONE `control_box` call for states [begin, end) of the C-order
+    grid: every state variable enters as an (S,) array.  Works for box functions
+    written with element-wise numpy (np.maximum/np.where/...); the reference's own
+    examples use `np.max((a, b))`, which does not vectorise - those raise or fail
+    the check below and the caller falls back to the per-state scan.
+
+    `verify` sample states are re-evaluated one by one, the reference's way
+    (stodynprog.py:440-460), and must agree bit-for-bit on (lo, hi, npts).
+    Returns a HostStateTable, or None when the batched call cannot be trusted."""
+    nb_control = len(sys.control)
+    S = end - begin
+    if S <= 0 or nb_control == 0:
+        return None
+    dims = [len(g) for g in state_grid]
+    idx = np.unravel_index(np.arange(begin, end), dims)
+    cols = tuple(np.asarray(state_grid[k])[idx[k]] for k in range(len(dims)))
+    args = cols if t_k is None else (t_k,) + cols
+    try:
+        with np.errstate(all="ignore"):
+            intervals = sys.control_box(*args, **sys.params)
+            if len(intervals) != nb_control or len(control_steps) != nb_control:
+                return None
+            tab = HostStateTable(S, nb_control)
+            for c, ((u_min, u_max), step) in enumerate(zip(intervals, control_steps)):
+                lo = np.asarray(u_min, dtype=float)
+                hi = np.asarray(u_max, dtype=float)
+                if lo.ndim > 1 or hi.ndim > 1 or lo.size not in (1, S) or hi.size not in (1, S):
+                    return None
+                tab.lo[:, c] = lo.reshape(-1)
+                tab.hi[:, c] = hi.reshape(-1)
+                n_interv = (tab.hi[:, c] - tab.lo[:, c]) / step
+                if not np.all(np.isfinite(n_interv)) or np.any(n_interv >= 2 ** 31):
+                    return None
+                tab.npts[:, c] = np.where(n_interv < 0.1, 1, (np.ceil(n_interv) + 1).astype(np.int64))
+    except Exception:
+        return None
+    picks = np.unique(np.linspace(0, S - 1, min(verify, S)).astype(int))
+    states = [tuple(col[i] for col in cols) for i in picks]
+    try:
+        ref = scan_control_boxes(sys, control_steps, states, t_k)
+    except Exception:
+        return None
+    same = (np.array_equal(tab.lo[picks].view(np.int64), ref.lo.view(np.int64))
+            and np.array_equal(tab.hi[picks].view(np.int64), ref.hi.view(np.int64))
+            and np.array_equal(tab.npts[picks], ref.npts))
+    return tab if same else None
 
 
 class NotFactorable(Exception):

@@ -178,6 +178,52 @@ def test_control_axis_values_equals_linspace():
     assert tb.control_axis_values([2.0], [3.0], [1], [0])[0] == 2.5
 
 
+def test_batched_control_box_scan():
+    """a box function written with element-wise numpy is scanned in one call and
+    agrees with the per-state scan; the reference's `np.max((a, b))` style does
+    not vectorise and must be rejected (the engine then scans per state)"""
+    grid = [np.linspace(0, 10, 23), np.linspace(-4, 4, 17)]
+    steps = (0.031, 0.1)
+
+    def box_vec(E, P):
+        return ((np.maximum(-E / 1.0, -4.0), np.minimum((10 - E) / 1.0, 4.0)), (0, 0))
+
+    def box_ref_style(E, P):
+        return ((np.max((-E / 1.0, -4.0)), np.min(((10 - E) / 1.0, 4.0))), (0, 0))
+
+    class S(object):
+        control = ['a', 'b']
+        params = {}
+    S.control_box = staticmethod(box_vec)
+    n = 23 * 17
+    tab = tb.scan_control_boxes_batched(S, steps, grid, 5, n - 3)
+    ref = tb.scan_control_boxes(S, steps, tb.state_tuples(grid, 5, n - 3))
+    assert tab is not None
+    assert np.array_equal(tab.lo, ref.lo) and np.array_equal(tab.hi, ref.hi)
+    assert np.array_equal(tab.npts, ref.npts) and tab.npts.max() > 100
+    S.control_box = staticmethod(box_ref_style)
+    assert tb.scan_control_boxes_batched(S, steps, grid, 0, n) is None
+
+    # a box that vectorises but to the wrong thing (a global reduction) is caught by the check
+    def box_wrong(E, P):
+        return ((np.max(-E), np.min(10 - E)), (0, 0))
+    S.control_box = staticmethod(box_wrong)
+    assert tb.scan_control_boxes_batched(S, steps, grid, 0, n) is None
+
+
+def test_pick_item_chunk():
+    from stodynprog_b200.engine import pick_item_chunk, ITEMS_TARGET
+    # plenty of units: keep the long runs
+    assert pick_item_chunk(np.full(40000, 256), 32) == 512
+    # one eighth of the large grid (a rank of an 8-GPU run) still fills the machine
+    assert pick_item_chunk(np.full(3907, 256), 32) == 512
+    # a small slab: runs are cut until there are enough warps
+    c = pick_item_chunk(np.full(600, 256), 32)
+    assert 32 <= c < 256 and ((256 + c - 1) // c) * 600 >= ITEMS_TARGET
+    # tiny problems stop at the floor
+    assert pick_item_chunk(np.full(10, 100), 128) == 128
+
+
 def test_interp_on_state_errors():
     from stodynprog_b200 import workloads as wl
     sv = wl.storage_ar1(sdp, n_E=5, n_P=6).solver
