@@ -369,15 +369,35 @@ class Engine(object):
             px.barrier()
 
     def upload_J(self, J_host, dst):
-        """host fp64 array -> device buffer `dst` (pinned staging, async)"""
+        """host fp64 array -> device buffer `dst`, asynchronously on the current stream.
+
+        The arrays this package returns live in page-locked memory (`to_host`), so
+        the usual loop `J, pol = solver.value_iteration(J)` hands back a buffer the
+        DMA engine can read directly: no staging copy.  Any other array is staged
+        through a pinned buffer in a few chunks, so that the H2D of one chunk
+        overlaps the host copy of the next.  Every public call synchronises the
+        stream before returning, so the caller's array is never read after that."""
         torch = _torch()
         a = np.ascontiguousarray(np.asarray(J_host, dtype=np.float64).reshape(-1))
-        if self._cuda:
-            pin = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
-            pin.numpy()[:] = a
-            dst.copy_(pin, non_blocking=True)
-        else:
+        if not self._cuda:
             dst.copy_(torch.from_numpy(a))
+            return dst
+        src = None
+        if a.flags.writeable:
+            t = torch.from_numpy(a)
+            if t.is_pinned():
+                src = t
+        if src is not None:
+            dst.copy_(src, non_blocking=True)
+            return dst
+        n = a.size
+        pin = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        pin_np = pin.numpy()
+        step = max((n + 3) // 4, 1 << 16)
+        for b0 in range(0, n, step):
+            b1 = min(b0 + step, n)
+            pin_np[b0:b1] = a[b0:b1]
+            dst[b0:b1].copy_(pin[b0:b1], non_blocking=True)
         return dst
 
     # -- sweep tables -----------------------------------------------------
