@@ -282,6 +282,17 @@ int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, const doubl
                     double* J_a, double* J_b, int32_t n_iter, int32_t rel_dp,
                     int64_t ref_index, double* J_ref_hist, void* stream);
 
+/* One fixed-policy backup of this rank's slab fused with the all-gather over peer
+ * memory: as one iteration of sdp_policy_eval, but the new values go to
+ * peers->J[r][state_begin + i] for every rank r and the rank's epoch is published
+ * (same protocol as sdp_sweep_finalize_p2p; follow with sdp_p2p_wait, then - under
+ * relative DP - sdp_rel_shift on the local copy, which every rank does identically).
+ * J_in: device [n_grid], the full previous value function on this rank. */
+int sdp_policy_eval_p2p(const SdpGrid* grid, int32_t W, int32_t g_per_w, const double* p,
+                        const int32_t* cell, const double* lam, int64_t lam_plane,
+                        const double* g, int64_t n_states, int64_t state_begin, int64_t n_grid,
+                        const double* J_in, const SdpPeers* peers, void* stream);
+
 /* K3 - argmin index -> control values, the `u_grids[i].flatten()[ind_opt[i]]` of
  * stodynprog.py:686-689 for every state at once.  lo/hi: device [n][nc] box
  * bounds, npts: device [n][nc] grid sizes (what control_grids computed,

@@ -1304,6 +1304,16 @@ k_sweep_fact_hoist(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
     const int nrows = cmax / stride0 - r0 + 1;       // rows r0 .. r0+nrows-1, plus the upper corner row
     const bool hoist = nrows <= RP;
     __syncwarp();
+    // The u-part is streamed one fragment ahead (ncu: 28 % of the stall samples of the
+    // single-buffered loop sat on the first use of the streamed cell); the first
+    // fragment is requested here so that its latency overlaps the table build.
+    Frag<1, UPL> f_n;
+    double g_n[UPL];
+    int u0 = lane * UPL;
+    if (u0 < it.u_count) {
+        load_frag<1, UPL>(f_n, T.cell, T.lam, T.lam_plane, it.entry_base + u0);
+        load_g<UPL>(g_n, T.g, it.entry_base + u0);
+    }
     if (hoist) {
         const int RS = RP + 1;
         for (int idx = lane; idx < (nrows + 1) * W; idx += 32) {
@@ -1319,16 +1329,15 @@ k_sweep_fact_hoist(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
 
     double best_v = CUDART_INF;
     int best_i = INT_MAX;
-    for (int u0 = lane * UPL; u0 < it.u_count; u0 += 32 * UPL) {
-        const int64_t off = it.entry_base + u0;
+    for (; u0 < it.u_count; u0 += 32 * UPL) {
         int cu[UPL];
         double lu[UPL], gv[UPL], acc[UPL];
-        {
-            Frag<1, UPL> f;
-            load_frag<1, UPL>(f, T.cell, T.lam, T.lam_plane, off);
-            load_g<UPL>(gv, T.g, off);
 #pragma unroll
-            for (int j = 0; j < UPL; ++j) { cu[j] = f.cell[j]; lu[j] = f.lam[0][j]; acc[j] = 0.0; }
+        for (int j = 0; j < UPL; ++j) { cu[j] = f_n.cell[j]; lu[j] = f_n.lam[0][j]; gv[j] = g_n[j]; acc[j] = 0.0; }
+        if (u0 + 32 * UPL < it.u_count) {
+            const int64_t off_n = it.entry_base + u0 + 32 * UPL;
+            load_frag<1, UPL>(f_n, T.cell, T.lam, T.lam_plane, off_n);
+            load_g<UPL>(g_n, T.g, off_n);
         }
         if (hoist) {
             const int RS = RP + 1;
@@ -1844,6 +1853,47 @@ k_policy_eval(GridT<double> G, int W, int g_per_w, const double* __restrict__ p,
     J_out[i] = acc;
 }
 
+// Fixed-policy backup fused with the all-gather: the new value of every state of the
+// slab goes straight into every rank's J buffer (peer-mapped pointers), the last CTA
+// publishes the epoch - the same protocol as k_sweep_finalize_p2p.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_policy_eval_p2p(GridT<double> G, int W, int g_per_w, const double* __restrict__ p,
+                  const int32_t* __restrict__ cell, const double* __restrict__ lam, int64_t lam_plane,
+                  const double* __restrict__ g, int64_t n_states, const double* __restrict__ J_in,
+                  PeersDev P, int64_t state_begin) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_states) {
+        double acc = 0.0;
+        double gv = g_per_w ? 0.0 : g[i];
+        for (int w = 0; w < W; ++w) {
+            const int64_t off = (int64_t)w * n_states + i;
+            double l[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) l[k] = lam[(int64_t)k * lam_plane + off];
+            if (g_per_w) gv = g[off];
+            double v = Lerp<double, D, 0>::eval(J_in, cell[off], G.stride, l);
+            acc = add_(acc, mul_(add_(gv, v), p[w]));   // stodynprog.py:755,757
+        }
+#pragma unroll
+        for (int r = 0; r < SDP_MAX_PEERS; ++r)
+            if (r < P.world) P.J[r][state_begin + i] = acc;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(P.done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence();
+            *P.done = 0;
+            const unsigned long long e = *P.epoch + 1;
+            *P.epoch = e;
+            __threadfence_system();
+            for (int r = 0; r < P.world; ++r) st_release_sys(P.flags[r] + P.rank, e);
+        }
+    }
+}
+
 __global__ void k_pick(const double* __restrict__ J, int64_t idx, double* __restrict__ out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = J[idx];
 }
@@ -1902,6 +1952,37 @@ extern "C" int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, 
         }
         double* t = in; in = out; out = t;
     }
+    return SDP_OK;
+}
+
+extern "C" int sdp_policy_eval_p2p(const SdpGrid* grid, int32_t W, int32_t g_per_w, const double* p,
+                                   const int32_t* cell, const double* lam, int64_t lam_plane,
+                                   const double* g, int64_t n_states, int64_t state_begin,
+                                   int64_t n_grid, const double* J_in, const SdpPeers* peers,
+                                   void* stream) {
+    GridT<double> G;
+    int64_t ng = 0;
+    int rc = make_grid<double>(grid, &G, &ng);
+    if (rc) return rc;
+    if (W < 1 || n_states < 0 || n_grid != ng || state_begin < 0 || state_begin + n_states > n_grid)
+        return fail(SDP_EINVAL, "%s", "sdp_policy_eval_p2p: bad sizes");
+    PeersDev P;
+    rc = make_peers(peers, &P, "sdp_policy_eval_p2p");
+    if (rc) return rc;
+    for (int r = 0; r < P.world; ++r)
+        if (!P.J[r]) return fail(SDP_EINVAL, "%s", "sdp_policy_eval_p2p: NULL J buffer");
+    if (!J_in || (n_states > 0 && (!p || !cell || !lam || !g)))
+        return fail(SDP_EINVAL, "%s", "sdp_policy_eval_p2p: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned blocks = (unsigned)((n_states + 255) / 256);
+    if (blocks == 0) blocks = 1;      // the epoch must advance on every rank, even for an empty slab
+    switch (grid->d) {
+        case 1: k_policy_eval_p2p<1><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin); break;
+        case 2: k_policy_eval_p2p<2><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin); break;
+        case 3: k_policy_eval_p2p<3><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin); break;
+        default: k_policy_eval_p2p<4><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin); break;
+    }
+    SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
 

@@ -287,8 +287,10 @@ class Engine(object):
             self.device = torch.device("cpu")
             self._cuda = False
             self._peer = {}
+            self._grid_cache = {}
             return
         self._peer = {}                          # n_grid -> PeerExchange | None
+        self._grid_cache = {}
         self.lib = _cabi.load_library()          # raises if the extension is missing
         if not torch.cuda.is_available():
             raise _cabi.SdpLibraryError(
@@ -511,6 +513,7 @@ class Engine(object):
             np.cumsum(Wf * Upad, out=entry_off[1:])
             return 0, None, None, int(entry_off[-1]), entry_off, Upad
 
+        prev_mode = reuse.tabulate_mode if reuse is not None else None
         T = reuse if (reuse is not None and reuse.W == W and reuse.d == d and reuse.tiled == tiled) \
             else SweepTables()
         T.grid, T.d, T.W = grid, d, W
@@ -634,8 +637,14 @@ class Engine(object):
 
             align = 32 if tiled else 1
             if batched:
+                # time-dependent recursion: the callables are the same at every instant, so
+                # the full bit-for-bit check of the batched evaluation is made at the first
+                # instant and a one-state check afterwards; unchanged control boxes reuse
+                # the chunk's control grids
                 tb.tabulate_states_batched(sys, state_grid, sb, se, host, w_grid, t_k, entry_off,
-                                           g_off, Upad, g_per_w, flush, align=align)
+                                           g_off, Upad, g_per_w, flush, align=align,
+                                           verify=1 if prev_mode == "batched" else 8,
+                                           grid_cache=self._grid_cache if t_k is not None else None)
             else:
                 states = mine if (mine is not None and (sb, se) == (eq[rank], eq[rank + 1])) else \
                     tb.state_tuples(state_grid, sb, se)
@@ -921,6 +930,25 @@ class Engine(object):
             return J_a if n_iter % 2 == 0 else J_b
         cur, nxt = J_a, J_b
         sb, n = P.state_begin, P.n_states
+        px = self._peer.get(n_grid)
+        if px is not None and px.index_of(J_a) is not None and px.index_of(J_b) is not None:
+            # fused backup + all-gather over peer memory: the kernel stores the slab's new
+            # values into every rank's buffer and publishes an epoch (no NCCL call)
+            for k in range(n_iter):
+                k_new = px.index_of(nxt)
+                rc = self.lib.sdp_policy_eval_p2p(ctypes.byref(P.grid), P.W, P.g_per_w, self._ptr(P.p),
+                                                  self._ptr(P.cell), self._ptr(P.lam), P.lam_plane,
+                                                  self._ptr(P.g), n, sb, n_grid, self._ptr(cur),
+                                                  ctypes.byref(px.peers[k_new]), self.stream)
+                _cabi.check(rc, "sdp_policy_eval_p2p")
+                rc = self.lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), self.stream)
+                _cabi.check(rc, "sdp_p2p_wait")
+                if rel_dp:
+                    ref_ptr = ctypes.c_void_p(J_ref_hist.data_ptr() + 8 * k)
+                    rc = self.lib.sdp_rel_shift(self._ptr(nxt), n_grid, int(ref_index), ref_ptr, self.stream)
+                    _cabi.check(rc, "sdp_rel_shift")
+                cur, nxt = nxt, cur
+            return cur
         for k in range(n_iter):
             rc = self.lib.sdp_policy_eval(ctypes.byref(P.grid), P.W, P.g_per_w, self._ptr(P.p),
                                           self._ptr(P.cell), self._ptr(P.lam), P.lam_plane,

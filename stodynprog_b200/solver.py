@@ -292,14 +292,17 @@ class DPSolver(object):
 
         eng = self.engine
         P = eng.build_policy_tables(self, pol)
-        J_a = eng.to_device(np.asarray(J_zero, dtype=float).reshape(-1))
-        J_b = torch.empty_like(J_a)
+        n_grid = int(np.prod(state_dims))
+        J_a, J_b = eng.J_pair(n_grid)         # symmetric (peer-mapped) buffers with several ranks
+        eng.begin_call(n_grid)
+        eng.upload_J(J_zero, J_a)
         hist = torch.zeros(max(n_iter, 1), dtype=torch.float64, device=eng.device)
         ref_flat = int(np.ravel_multi_index(ref_ind, state_dims))
         print('\rpolicy evaluation: iter. {:d}/{:d}'.format(max(n_iter - 1, 0), n_iter), end='')
         J_dev = eng.policy_eval(P, J_a, J_b, n_iter, rel_dp, ref_flat, hist)
-        J_pol = J_dev.cpu().numpy().reshape(state_dims)
-        J_ref = hist.cpu().numpy()[:n_iter] if rel_dp else None
+        outs = eng.to_host(J_dev, hist)
+        J_pol = outs[0].reshape(state_dims)
+        J_ref = outs[1][:n_iter] if rel_dp else None
 
         exec_time = (datetime.now() - t_start).total_seconds()
         if report_time:

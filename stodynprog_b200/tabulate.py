@@ -55,7 +55,8 @@ def control_axis_values(lo, hi, npts, idx):
     element-wise the same arithmetic as np.linspace (numpy/_core/function_base.py:
     y = arange(num)*step + start with step = (stop-start)/(num-1), y[-1] = stop;
     (i/div)*delta + start when step == 0) and the centre point for npts == 1.
-    Used to map argmin indices back to control VALUES (stodynprog.py:689)."""
+    Used to map argmin indices back to control VALUES (stodynprog.py:689) and to
+    lay out the control grids of a chunk of states for the batched tabulation."""
     lo = np.asarray(lo, dtype=float)
     hi = np.asarray(hi, dtype=float)
     npts = np.asarray(npts)
@@ -64,9 +65,15 @@ def control_axis_values(lo, hi, npts, idx):
     delta = hi - lo
     with np.errstate(invalid="ignore", over="ignore"):
         step = delta / div
-        y = np.where(step == 0, (idx / div) * delta, idx * step) + lo
+        y = idx * step
+        y += lo
+        flat = step == 0
+        if np.any(flat):                       # rare: degenerate or denormal-step boxes
+            y = np.where(flat, (idx / div) * delta + lo, y)
         y = np.where(idx == npts - 1, hi, y)
-        y = np.where(npts == 1, (lo + hi) / 2, y)
+        single = npts == 1
+        if np.any(single):
+            y = np.where(single, (lo + hi) / 2, y)
     return y
 
 
@@ -354,7 +361,7 @@ def _strides_or_zero(shape):
     return np.where(np.asarray(shape) == 1, 0, st)
 
 
-def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W):
+def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=None):
     """dyn/cost for a chunk of S states in ONE call: state variables enter as
     (S,1,..,1) arrays, control c as an (S,..,n_c_max,..,1) array whose row s is
     that state's own control grid (padded by repeating its last point), the
@@ -367,12 +374,26 @@ def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W):
     full_shape = (S,) + tuple(nmax) + (W,)
     rank = len(full_shape)
     xs = tuple(col.reshape((S,) + (1,) * (rank - 1)) for col in state_cols)
-    us = []
-    for c in range(nb_control):
-        j = np.arange(nmax[c])[None, :]
-        n_c = npts[:, c][:, None]
-        vals = control_axis_values(lo[:, c][:, None], hi[:, c][:, None], n_c, np.minimum(j, n_c - 1))
-        us.append(vals.reshape((S,) + (1,) * c + (nmax[c],) + (1,) * (nb_control - c)))
+    # the padded control grids of the chunk; a time-dependent recursion whose boxes do
+    # not change from one instant to the next (the common case) reuses them
+    key = None
+    us = None
+    if grid_cache is not None:
+        key = (lo.tobytes(), hi.tobytes(), npts.tobytes())
+        us = grid_cache.get(key)
+    if us is None:
+        us = []
+        for c in range(nb_control):
+            j = np.arange(nmax[c])[None, :]
+            n_c = npts[:, c][:, None]
+            vals = control_axis_values(lo[:, c][:, None], hi[:, c][:, None], n_c, np.minimum(j, n_c - 1))
+            vals = vals.reshape((S,) + (1,) * c + (nmax[c],) + (1,) * (nb_control - c))
+            vals.flags.writeable = False      # shared between calls: user code must not mutate it
+            us.append(vals)
+        if grid_cache is not None:
+            if len(grid_cache) >= 64:
+                grid_cache.clear()
+            grid_cache[key] = us
     args = xs + tuple(us) + w_args
     if t_k is not None:
         args = (t_k,) + args
@@ -397,7 +418,7 @@ def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W):
 
 def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid, t_k, entry_off,
                             g_off, Upad, g_per_w, flush_fn, chunk_states=4096,
-                            max_doubles=16 << 20, align=1, verify=8):
+                            max_doubles=16 << 20, align=1, verify=8, grid_cache=None):
     """Second pass, batched mode: one dyn/cost call per chunk of states.
     `verify` sample states of the first chunk are re-evaluated per state, the
     reference's way, and compared bit-for-bit; a mismatch raises
@@ -421,7 +442,7 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
         cols = [np.asarray(state_grid[k])[idx[k]] for k in range(d)]
         npts = host_tab.npts[b0:b1]
         outs, nmax = _eval_state_chunk(sys, cols, host_tab.lo[b0:b1], host_tab.hi[b0:b1], npts,
-                                       w_args, t_k, W)
+                                       w_args, t_k, W, grid_cache)
         if outs[-1].shape[-1] > 1 and not g_per_w:
             raise GDependsOnW()
         if not checked and verify:
