@@ -223,6 +223,8 @@ class SweepTables(object):
         self.tabulate_mode = None
         self.setup_seconds = 0.0
         self.item_chunk = 0        # controls per work item used for these tables
+        self.item_begin_host = self.unit_U_host = None
+        self.chunk_plan = None     # see Engine._chunk_plan
 
     @property
     def algorithmic_bytes_per_backup(self):
@@ -724,6 +726,9 @@ class Engine(object):
             items["g_base"] = g_off[st] + kk * chunk
             items["Upad"] = Upad[st]
         T.n_items = n_items
+        T.item_begin_host = item_begin
+        T.unit_U_host = np.asarray(unit_U, dtype=np.int64)
+        T.chunk_plan = None
         T.items = torch.from_numpy(items.view(np.uint8).reshape(-1)).to(dev) if n_items else \
             torch.zeros(32, dtype=torch.uint8, device=dev)
         T.item_begin = self.to_device(item_begin)
@@ -826,6 +831,106 @@ class Engine(object):
                                            self.stream)
             _cabi.check(rc, "sdp_supnorm_diff")
             self.coll.all_reduce_max(resid_out)
+
+    # -- one sweep with host results, D2H overlapped with compute -------------
+    OVERLAP_MIN_BACKUPS = 100 * 1000 * 1000     # below this the result copy is not worth hiding
+    OVERLAP_MIN_ITEMS = 4096
+    OVERLAP_FRACTIONS = (0.45, 0.25, 0.15, 0.10, 0.05)
+
+    def can_overlap_results(self, T):
+        return (self._cuda and self.coll.world == 1 and T.n_items >= self.OVERLAP_MIN_ITEMS
+                and T.n_backups_local >= self.OVERLAP_MIN_BACKUPS
+                and os.environ.get("SDP_OVERLAP", "1") != "0")
+
+    def _chunk_plan(self, T):
+        """cut the slab's work units (states, or tiles of 32 states) into a few runs of
+        decreasing size; each run is swept by its own launches (sub-range views of the
+        same tables: shifted item / item_begin pointers), so that its results can
+        travel to the host while the next run computes"""
+        if T.chunk_plan is not None:
+            return T.chunk_plan
+        us = 32 if T.tiled else 1
+        n_units = len(T.unit_U_host)
+        csum = np.cumsum(T.unit_U_host)
+        total = float(csum[-1])
+        cuts = [0]
+        acc = 0.0
+        for f in self.OVERLAP_FRACTIONS[:-1]:
+            acc += f
+            b = int(np.searchsorted(csum, acc * total, side="left")) + 1
+            cuts.append(min(max(b, cuts[-1]), n_units))
+        cuts.append(n_units)
+        plan = []
+        width = 32 if T.tiled else 1
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b <= a:
+                continue
+            i0, i1 = int(T.item_begin_host[a]), int(T.item_begin_host[b])
+            s0, s1 = a * us, min(b * us, T.n_states)
+            cp = _cabi.SdpTables.from_buffer_copy(T.c_tables)
+            cp.items = T.c_tables.items + _cabi.ITEM_DTYPE.itemsize * i0
+            cp.n_items = i1 - i0
+            cf = _cabi.SdpTables.from_buffer_copy(T.c_tables)
+            cf.item_begin = T.c_tables.item_begin + 8 * a
+            cf.n_states = s1 - s0
+            plan.append(dict(tab_p=cp, tab_f=cf, s0=s0, s1=s1,
+                             pv=ctypes.c_void_p(T.part_val.data_ptr() + 8 * width * i0),
+                             pi=ctypes.c_void_p(T.part_idx.data_ptr() + 4 * width * i0)))
+        T.chunk_plan = plan
+        return plan
+
+    def sweep_to_host(self, T, J_prev, J_new):
+        """One sweep of a single-rank slab, returning (J, pol) as host arrays in
+        page-locked memory.  The slab is swept in a few runs on two alternating
+        streams (so that the tail of one run is filled by the next); as soon as a run
+        is combined and its argmin mapped to control values (K3), a copy stream sends
+        that run's J and policy to the host while the following runs still compute.
+        Same kernels on sub-ranges of the same tables: bit-identical to `sweep`."""
+        torch = _torch()
+        dev = self.device
+        n, nc = T.n_states, T.nb_control
+        if not hasattr(self, "_side"):
+            self._side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+            self._copy = torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        pol = torch.empty((n, nc), dtype=torch.float64, device=dev)
+        J_pin = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        pol_pin = torch.empty((n, nc), dtype=torch.float64, pin_memory=True)
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        for k, ch in enumerate(self._chunk_plan(T)):
+            st = self._side[k % 2]
+            sp = ctypes.c_void_p(st.cuda_stream)
+            st.wait_event(ev0)
+            s0, s1 = ch["s0"], ch["s1"]
+            rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(ch["tab_p"]),
+                                             self._ptr(J_prev), ch["pv"], ch["pi"], sp)
+            _cabi.check(rc, "sdp_sweep_partials")
+            rc = self.lib.sdp_sweep_finalize(ctypes.byref(ch["tab_f"]), self._ptr(T.part_val),
+                                             self._ptr(T.part_idx),
+                                             ctypes.c_void_p(J_new.data_ptr() + 8 * s0),
+                                             ctypes.c_void_p(T.argmin.data_ptr() + 4 * s0), sp)
+            _cabi.check(rc, "sdp_sweep_finalize")
+            if nc:
+                rc = self.lib.sdp_policy_values(
+                    s1 - s0, nc, ctypes.c_void_p(T.lo_dev.data_ptr() + 8 * nc * s0),
+                    ctypes.c_void_p(T.hi_dev.data_ptr() + 8 * nc * s0),
+                    ctypes.c_void_p(T.npts_dev.data_ptr() + 4 * nc * s0),
+                    ctypes.c_void_p(T.argmin.data_ptr() + 4 * s0),
+                    ctypes.c_void_p(pol.data_ptr() + 8 * nc * s0), sp)
+                _cabi.check(rc, "sdp_policy_values")
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self._copy.wait_event(ev)
+            with torch.cuda.stream(self._copy):
+                J_pin[s0:s1].copy_(J_new[s0:s1], non_blocking=True)
+                if nc:
+                    pol_pin[s0:s1].copy_(pol[s0:s1], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(self._copy)
+        main.wait_event(done)
+        done.synchronize()
+        return J_pin.numpy(), pol_pin.numpy()
 
     def gather_argmin(self, T):
         """full-grid int32 argmin (device), gathered over ranks"""

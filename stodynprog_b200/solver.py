@@ -186,6 +186,10 @@ class DPSolver(object):
         J_prev, J_new = eng.J_pair(n_grid)
         eng.begin_call(n_grid)
         eng.upload_J(J_next, J_prev)
+        if not rel_dp and eng.can_overlap_results(T):
+            # large single-rank sweep: results stream to the host while later runs compute
+            J_k, pol_k = eng.sweep_to_host(T, J_prev, J_new)
+            return J_k.reshape(state_dims), None, pol_k.reshape(state_dims + (nb_control,)), T
         ref_out = None
         ref_flat = None
         if rel_dp:

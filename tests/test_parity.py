@@ -854,3 +854,37 @@ def test_layout_B_kernel_variants_are_bit_identical(product):
                     assert np.array_equal(J, ref[0]) and np.array_equal(pol, ref[1]), (layout, which, st)
     finally:
         opt(tma=1, tma_rows=8, tma_stages=2, tma_warps=4, rb=4, wb=1, upl=4)
+
+
+@gpu
+@pytest.mark.parametrize("layout", ["control_minor", "state_minor"])
+@pytest.mark.parametrize("compress", ["off", "auto"])
+def test_overlapped_result_copy_is_bit_identical(product, layout, compress):
+    """value_iteration's large-sweep path (runs of the slab swept on alternating streams,
+    results copied to the host while later runs compute) must return exactly what the
+    plain path returns"""
+    from stodynprog_b200 import workloads as wl
+    from stodynprog_b200.engine import Engine
+    api = _Api(product, "cuda", layout, compress=compress)
+    for prob in (wl.storage_ar1(api, n_E=40, n_P=37, steps=(0.05, 0.1), item_chunk=48),
+                 _searev_small(api)):
+        sv = prob.solver
+        J0 = np.random.default_rng(7).standard_normal(sv._state_grid_shape)
+        saved = (Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS)
+        try:
+            Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = 1 << 62, 1 << 62
+            J_a, pol_a = sv.value_iteration(J0, report_time=False)
+            assert not sv.engine.can_overlap_results(sv.last_tables)
+            Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = 0, 0
+            assert sv.engine.can_overlap_results(sv.last_tables)
+            assert len(sv.engine._chunk_plan(sv.last_tables)) >= 2
+            for _ in range(2):
+                J_b, pol_b = sv.value_iteration(J0, report_time=False)
+                assert np.array_equal(J_a, J_b) and np.array_equal(pol_a, pol_b)
+            # feeding the page-locked result back in takes the no-staging upload path
+            J_c, pol_c = sv.value_iteration(J_b, report_time=False)
+            Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = 1 << 62, 1 << 62
+            J_d, pol_d = sv.value_iteration(np.array(J_b), report_time=False)
+            assert np.array_equal(J_c, J_d) and np.array_equal(pol_c, pol_d)
+        finally:
+            Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = saved
