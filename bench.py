@@ -310,6 +310,15 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total_max, k1_ms_max = float(t[0]), float(t[1])
+    k1_per_rank = None
+    if world > 1:
+        # slab balance: every rank's mean streaming-kernel time and slab size
+        mine = torch.tensor([float(np.mean(k1_ms)), float(T.n_backups_local), float(T.n_states)],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        k1_per_rank = {"kernel_ms": [round(float(x[0]), 4) for x in allr],
+                       "backups": [int(x[1]) for x in allr], "states": [int(x[2]) for x in allr]}
     total_backups = T.n_backups_total
     value = total_backups * K / (ms_total_max * 1e-3)
 
@@ -403,6 +412,8 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "clocks": clocks, "setup_seconds": float(setup[0]),
         }
+        if k1_per_rank is not None:
+            line["slabs"] = k1_per_rank
         if dense is not None:
             line["dense_layout"] = dense
         if cpu is not None:

@@ -1704,6 +1704,29 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned 
     }
 }
 
+// Publish: every CTA fences its peer stores (system scope), the last CTA to arrive
+// bumps the rank's epoch and lanes 0..world-1 release it into the flag arrays of all
+// ranks IN PARALLEL (one st.release.sys each: a loop in one thread would pay one
+// NVLink round trip per peer, 8 in a row on a full box).  Called by all threads.
+__device__ __forceinline__ void publish_epoch(const PeersDev& P) {
+    __shared__ unsigned long long e_sh;
+    __shared__ int last_sh;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(P.done, 1u);
+        last_sh = (prev == gridDim.x - 1);
+        if (last_sh) {
+            __threadfence();
+            *P.done = 0;
+            e_sh = *P.epoch + 1;
+            *P.epoch = e_sh;
+        }
+    }
+    __syncthreads();
+    if (last_sh && threadIdx.x < P.world) st_release_sys(P.flags[threadIdx.x] + P.rank, e_sh);
+}
+
 // per-state combine of the partial minima; J is stored into every rank's buffer
 template <bool TILED>
 __global__ void __launch_bounds__(256)
@@ -1728,19 +1751,7 @@ k_sweep_finalize_p2p(int64_t n_states, const int64_t* __restrict__ item_begin,
             if (r < P.world) P.J[r][state_begin + i] = bv;
     }
     // publish: every CTA fences its peer stores, the last one to finish releases the epoch
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(P.done, 1u);
-        if (prev == gridDim.x - 1) {
-            __threadfence();
-            *P.done = 0;
-            const unsigned long long e = *P.epoch + 1;
-            *P.epoch = e;
-            __threadfence_system();
-            for (int r = 0; r < P.world; ++r) st_release_sys(P.flags[r] + P.rank, e);
-        }
-    }
+    publish_epoch(P);
 }
 
 __global__ void k_p2p_wait(PeersDev P) {
@@ -1879,19 +1890,7 @@ k_policy_eval_p2p(GridT<double> G, int W, int g_per_w, const double* __restrict_
         for (int r = 0; r < SDP_MAX_PEERS; ++r)
             if (r < P.world) P.J[r][state_begin + i] = acc;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(P.done, 1u);
-        if (prev == gridDim.x - 1) {
-            __threadfence();
-            *P.done = 0;
-            const unsigned long long e = *P.epoch + 1;
-            *P.epoch = e;
-            __threadfence_system();
-            for (int r = 0; r < P.world; ++r) st_release_sys(P.flags[r] + P.rank, e);
-        }
-    }
+    publish_epoch(P);
 }
 
 __global__ void k_pick(const double* __restrict__ J, int64_t idx, double* __restrict__ out) {
