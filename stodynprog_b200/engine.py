@@ -18,7 +18,7 @@ import numpy as np
 from . import _cabi
 from . import tabulate as tb
 
-__all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight"]
+__all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "rebalance_bounds"]
 
 
 def _torch():
@@ -53,6 +53,27 @@ def partition_by_weight(weights, world):
 # controls: 565 G backups/s vs 626 G with 31 250) and LOSE ~10 % when the runs are cut
 # to 128 controls, so runs are only shortened when a launch would not even fill the
 # machine once (148 SMs x 16 warps).
+def rebalance_bounds(U_all, bounds, times, tolerance=1.03):
+    """Re-cut contiguous slabs from measured slab times: the weight U(x)+1 of every
+    state is scaled by its slab's time per unit weight (a piecewise-constant cost
+    density), then the grid is cut into slabs of equal estimated time.  Returns the
+    new boundaries, or None if the slabs are balanced within `tolerance` (slowest /
+    mean), a time is missing, or nothing would move."""
+    t = np.asarray(times, dtype=float)
+    world = len(t)
+    old = [int(b) for b in bounds]
+    if world < 2 or not np.all(t > 0) or t.max() <= tolerance * t.mean():
+        return None
+    w = np.asarray(U_all, dtype=np.float64) + 1.0
+    for r in range(world):
+        sl = slice(old[r], old[r + 1])
+        tot = w[sl].sum()
+        if tot > 0:
+            w[sl] *= t[r] / tot
+    new = [int(b) for b in partition_by_weight(w, world)]
+    return None if new == old else new
+
+
 ITEMS_TARGET = 148 * 16
 
 
@@ -225,6 +246,7 @@ class SweepTables(object):
         self.item_chunk = 0        # controls per work item used for these tables
         self.item_begin_host = self.unit_U_host = None
         self.chunk_plan = None     # see Engine._chunk_plan
+        self.slab_times_ms = None  # measured per-rank sweep times behind a re-cut of the slabs
 
     @property
     def algorithmic_bytes_per_backup(self):
@@ -404,6 +426,43 @@ class Engine(object):
             dst[b0:b1].copy_(pin[b0:b1], non_blocking=True)
         return dst
 
+    # -- slab balance -----------------------------------------------------
+    REBALANCE_MIN_BACKUPS = 500 * 1000 * 1000    # "auto": only sweeps long enough to matter
+    REBALANCE_TOLERANCE = 1.03                   # slowest / mean slab time that is left alone
+
+    def _measured_bounds(self, T, U_all):
+        """Slab boundaries equalising the MEASURED sweep time of the ranks.
+
+        Cutting the grid by the number of admissible controls balances the backups,
+        not the time: the cost of a backup depends on where its corners fall (L1 / L2
+        hit rates differ between regions of the state space) and on the GPU (measured
+        on 8 B200s, config #5: 0.375 .. 0.454 ms for slabs of equal backup count).
+        Every rank times the streaming kernel on its slab; the per-state weights of a
+        slab are scaled by its measured time per weight and the grid is cut again.
+        Returns the new boundaries, or None when the slabs are already balanced.
+        Same data on every rank (all-gathered), so every rank takes the same decision;
+        results do not depend on the partition."""
+        torch = _torch()
+        coll = self.coll
+        n_grid = len(U_all)
+        J = torch.zeros(n_grid, dtype=torch.float64, device=self.device)
+        t_mine = 0.0
+        if T.n_states > 0 and T.n_items > 0:
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(7)]
+            for a, b in evs:
+                a.record()
+                rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
+                                                 self._ptr(J), self._ptr(T.part_val),
+                                                 self._ptr(T.part_idx), self.stream)
+                _cabi.check(rc, "sdp_sweep_partials")
+                b.record()
+            self.sync()
+            t_mine = float(np.median([a.elapsed_time(b) for a, b in evs[2:]]))
+        t = np.asarray(coll.all_gather_object(t_mine), dtype=float)
+        T.slab_times_ms = [float(x) for x in t]
+        return rebalance_bounds(U_all, T.bounds, t, self.REBALANCE_TOLERANCE)
+
     # -- sweep tables -----------------------------------------------------
     def build_sweep_tables(self, solver, t_k=None, reuse=None):
         """Tabulate the user's callables over this rank's slab and build the dense
@@ -461,307 +520,319 @@ class Engine(object):
         if U_all.max(initial=0) >= 2 ** 31 - 4:
             raise ValueError("more than 2^31 control combinations for one state")
 
-        # slabs balanced by admissible controls
-        bounds = partition_by_weight(U_all + 1, world) if world > 1 else [0, n_grid]
-        sb, se = bounds[rank], bounds[rank + 1]
-        n = se - sb
-        host = tb.HostStateTable(n, nb_control)
-        host.lo, host.hi, host.npts = host_full.lo[sb:se], host_full.hi[sb:se], host_full.npts[sb:se]
-        U = U_all[sb:se]
+        def build_for(bounds, reuse):
+            """tables of this rank's slab [bounds[rank], bounds[rank+1])"""
+            sb, se = bounds[rank], bounds[rank + 1]
+            n = se - sb
+            host = tb.HostStateTable(n, nb_control)
+            host.lo, host.hi, host.npts = host_full.lo[sb:se], host_full.hi[sb:se], host_full.npts[sb:se]
+            U = U_all[sb:se]
 
-        # table layout (see include/sdp_b200.h): lane <-> control (A) when states
-        # have many controls, lane <-> state (B) when there are many states with
-        # few controls each
-        layout = getattr(solver, "table_layout", "auto")
-        if layout == "auto":
-            mean_U = float(U.mean()) if n else 0.0
-            layout = "state_minor" if (n >= 32 * 1024 and mean_U <= 1024) else "control_minor"
-        tiled = layout == "state_minor"
-        w_grid = [np.asarray(g) for g in solver.perturb_grid]
+            # table layout (see include/sdp_b200.h): lane <-> control (A) when states
+            # have many controls, lane <-> state (B) when there are many states with
+            # few controls each
+            layout = getattr(solver, "table_layout", "auto")
+            if layout == "auto":
+                mean_U = float(U.mean()) if n else 0.0
+                layout = "state_minor" if (n >= 32 * 1024 and mean_U <= 1024) else "control_minor"
+            tiled = layout == "state_minor"
+            w_grid = [np.asarray(g) for g in solver.perturb_grid]
 
-        # factored ("broadcast-compressed") tables when every next-state coordinate
-        # depends on (x,u) only or on (x,w) only and g does not depend on w; probed on
-        # the slab's state with most controls, then checked on every staged chunk
-        compress = getattr(solver, "table_compress", "auto")
-        u_mask = 0
-        w_cap = _cabi.FACTORED_MAX_W_REG if tiled else _cabi.FACTORED_MAX_W_SMEM
-        if (compress != "off" and n > 0 and nb_perturb == 1 and 1 < W <= w_cap and d in (2, 3)
-                and nb_control <= _cabi.SDP_MAX_C):
-            i_probe = int(np.argmax(U))
-            x_probe = tb.state_tuples(state_grid, sb + i_probe, sb + i_probe + 1)[0]
-            u_mask = tb.probe_factor_mask(sys, x_probe, host, i_probe, w_grid, t_k) or 0
-        if compress == "on" and not u_mask:
-            raise ValueError("table_compress='on' but the system's dyn/cost do not have the "
-                             "(x,u) + (x,w) structure (or d, W are outside the supported range)")
-        if world > 1:
-            # all ranks must agree (they run the same kernels on the same layout)
-            u_mask = min(coll.all_gather_object(u_mask))
+            # factored ("broadcast-compressed") tables when every next-state coordinate
+            # depends on (x,u) only or on (x,w) only and g does not depend on w; probed on
+            # the slab's state with most controls, then checked on every staged chunk
+            compress = getattr(solver, "table_compress", "auto")
+            u_mask = 0
+            w_cap = _cabi.FACTORED_MAX_W_REG if tiled else _cabi.FACTORED_MAX_W_SMEM
+            if (compress != "off" and n > 0 and nb_perturb == 1 and 1 < W <= w_cap and d in (2, 3)
+                    and nb_control <= _cabi.SDP_MAX_C):
+                i_probe = int(np.argmax(U))
+                x_probe = tb.state_tuples(state_grid, sb + i_probe, sb + i_probe + 1)[0]
+                u_mask = tb.probe_factor_mask(sys, x_probe, host, i_probe, w_grid, t_k) or 0
+            if compress == "on" and not u_mask:
+                raise ValueError("table_compress='on' but the system's dyn/cost do not have the "
+                                 "(x,u) + (x,w) structure (or d, W are outside the supported range)")
+            if world > 1:
+                # all ranks must agree (they run the same kernels on the same layout)
+                u_mask = min(coll.all_gather_object(u_mask))
 
-        def sizes(u_mask):
-            """entry offsets of the layout: dense tables have W entries per control,
-            factored tables one"""
-            Wf = 1 if u_mask else W
-            if tiled:
-                n_tiles = (n + 31) // 32
-                Upad_t = np.zeros(n_tiles * 32, dtype=np.int64)
-                Upad_t[:n] = U
-                tile_U = Upad_t.reshape(n_tiles, 32).max(axis=1)
-                tile_off = np.zeros(n_tiles + 1, dtype=np.int64)
-                np.cumsum(tile_U * Wf * 32, out=tile_off[1:])
-                return (n_tiles, tile_U, tile_off, int(tile_off[-1]), np.zeros(n + 1, dtype=np.int64),
-                        np.zeros(n, dtype=np.int64))
-            Upad = (U + 3) // 4 * 4
-            entry_off = np.zeros(n + 1, dtype=np.int64)
-            np.cumsum(Wf * Upad, out=entry_off[1:])
-            return 0, None, None, int(entry_off[-1]), entry_off, Upad
-
-        prev_mode = reuse.tabulate_mode if reuse is not None else None
-        T = reuse if (reuse is not None and reuse.W == W and reuse.d == d and reuse.tiled == tiled) \
-            else SweepTables()
-        T.grid, T.d, T.W = grid, d, W
-        T.tiled = tiled
-        T.expect = 1 if nb_perturb == 1 else 0
-        T.bounds, T.state_begin, T.n_states = bounds, sb, n
-        T.host_full = host_full
-        T.n_backups_local = int(U.sum()) * W
-        T.n_backups_total = int(U_all.sum()) * W
-        # host copy of the probabilities, kept alive with the tables (SdpTables.p_host)
-        T.p_host = np.ascontiguousarray(solver.perturb_proba[0], dtype=np.float64).copy() \
-            if nb_perturb == 1 else np.ones(1)
-        T.p = self.to_device(T.p_host)
-        T.U_dev = self.to_device(U.astype(np.int32)) if n else torch.zeros(1, dtype=torch.int32, device=dev)
-        # replicated control discretisation, for the argmin -> control value kernel
-        T.lo_dev = self.to_device(host_full.lo.reshape(-1)) if nb_control else None
-        T.hi_dev = self.to_device(host_full.hi.reshape(-1)) if nb_control else None
-        T.npts_dev = self.to_device(host_full.npts.astype(np.int32).reshape(-1)) if nb_control else None
-        T.nb_control = nb_control
-        T.tabulate_mode = None
-
-        def ensure(name, numel, dtype):
-            """(re)allocate T.<name> only when the size changes (time-dependent
-            recursions rebuild same-sized tables at every instant)"""
-            t = getattr(T, name)
-            if t is None or t.numel() != numel or t.dtype != dtype:
-                setattr(T, name, None)        # release before allocating the new size
-                setattr(T, name, torch.empty(numel, dtype=dtype, device=dev))
-
-        def build(g_per_w, batched, u_mask):
-            L = {"u_mask": u_mask}
-            n_tiles, tile_U, tile_off, n_entries, entry_off, Upad = sizes(u_mask)
-            lam_plane = (n_entries + 3) // 4 * 4
-            n_u = bin(u_mask).count("1")
-            L.update(n_tiles=n_tiles, tile_U=tile_U, tile_off=tile_off, n_entries=n_entries,
-                     entry_off=entry_off, Upad=Upad, lam_plane=lam_plane)
-            ensure("cell", max(lam_plane, 4), torch.int32)
-            ensure("lam", max(lam_plane, 4) * (n_u if u_mask else d), torch.float64)
-            if u_mask:
-                n_wp = (n_tiles * 32 if tiled else n) * W
-                lam_w_plane = (n_wp + 3) // 4 * 4
-                ensure("cell_w", max(lam_w_plane, 4), torch.int32)
-                ensure("lam_w", max(lam_w_plane, 4) * (d - n_u), torch.float64)
-            else:
-                T.cell_w = T.lam_w = None
-                lam_w_plane = 0
-            L["lam_w_plane"] = lam_w_plane
-            tile_g_off = None
-            if u_mask:
-                # one g per (x,u) entry, indexed like the u-part
-                g_off, g_len = entry_off, n_entries
-                tile_g_off = tile_off
-            elif tiled:
-                if g_per_w:
-                    tile_g_off = tile_off
-                else:
-                    tile_g_off = np.zeros(n_tiles + 1, dtype=np.int64)
-                    np.cumsum(tile_U * 32, out=tile_g_off[1:])
-                g_off = np.zeros(n + 1, dtype=np.int64)
-                g_len = int(tile_g_off[-1])
-            else:
-                if g_per_w:
-                    g_off = entry_off
-                else:
-                    g_off = np.zeros(n + 1, dtype=np.int64)
-                    np.cumsum(Upad, out=g_off[1:])
-                g_len = int(g_off[-1])
-            if tiled:
-                tile_off_dev = self.to_device(tile_off)
-                tile_g_off_dev = self.to_device(tile_g_off)
-                tile_U_dev = self.to_device(tile_U.astype(np.int32))
-            L.update(g_off=g_off, tile_g_off=tile_g_off)
-            ensure("g", max(g_len, 4), torch.float64)
-            done = [0]      # states flushed so far (chunks arrive in order)
-
-            def flush(desc, staging):
-                if u_mask:
-                    tb.check_factorable(desc, d, u_mask)
-                desc_dev = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(dev)
-                stag_dev = torch.from_numpy(staging).to(dev)
-                ns = len(desc)
+            def sizes(u_mask):
+                """entry offsets of the layout: dense tables have W entries per control,
+                factored tables one"""
+                Wf = 1 if u_mask else W
                 if tiled:
-                    assert done[0] % 32 == 0
-                    t_first = done[0] // 32
-                    nt = (ns + 31) // 32
-                    t_off = ctypes.c_void_p(tile_off_dev.data_ptr() + 8 * t_first)
-                    t_U = ctypes.c_void_p(tile_U_dev.data_ptr() + 4 * t_first)
-                    t_Umax = int(tile_U[t_first:t_first + nt].max())
-                    if u_mask:
-                        w0 = t_first * W * 32
-                        rc = self.lib.sdp_build_tables_factored_tiled(
-                            ctypes.byref(grid), W, u_mask, ns, self._ptr(desc_dev), self._ptr(stag_dev),
-                            nt, t_off, t_U, t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane,
-                            self._ptr(T.g), ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
-                            ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
-                        _cabi.check(rc, "sdp_build_tables_factored_tiled")
-                    else:
-                        rc = self.lib.sdp_build_tables_tiled(
-                            ctypes.byref(grid), W, g_per_w, ns, self._ptr(desc_dev), self._ptr(stag_dev),
-                            nt, t_off, ctypes.c_void_p(tile_g_off_dev.data_ptr() + 8 * t_first), t_U,
-                            t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g),
-                            self.stream)
-                        _cabi.check(rc, "sdp_build_tables_tiled")
-                elif u_mask:
-                    w0 = done[0] * W
-                    rc = self.lib.sdp_build_tables_factored(
-                        ctypes.byref(grid), W, u_mask, ns, self._ptr(desc_dev), self._ptr(stag_dev),
-                        self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g),
-                        int(desc["Upad"].max()), ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
-                        ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
-                    _cabi.check(rc, "sdp_build_tables_factored")
-                else:
-                    rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, ns,
-                                                   self._ptr(desc_dev), self._ptr(stag_dev),
-                                                   self._ptr(T.cell), self._ptr(T.lam), lam_plane,
-                                                   self._ptr(T.g), int(desc["Upad"].max()), self.stream)
-                    _cabi.check(rc, "sdp_build_tables")
-                done[0] += ns
-                # the staging tensors are freed by torch's caching allocator in
-                # stream order, so no synchronisation is needed here
+                    n_tiles = (n + 31) // 32
+                    Upad_t = np.zeros(n_tiles * 32, dtype=np.int64)
+                    Upad_t[:n] = U
+                    tile_U = Upad_t.reshape(n_tiles, 32).max(axis=1)
+                    tile_off = np.zeros(n_tiles + 1, dtype=np.int64)
+                    np.cumsum(tile_U * Wf * 32, out=tile_off[1:])
+                    return (n_tiles, tile_U, tile_off, int(tile_off[-1]), np.zeros(n + 1, dtype=np.int64),
+                            np.zeros(n, dtype=np.int64))
+                Upad = (U + 3) // 4 * 4
+                entry_off = np.zeros(n + 1, dtype=np.int64)
+                np.cumsum(Wf * Upad, out=entry_off[1:])
+                return 0, None, None, int(entry_off[-1]), entry_off, Upad
 
-            align = 32 if tiled else 1
-            if batched:
-                # time-dependent recursion: the callables are the same at every instant, so
-                # the full bit-for-bit check of the batched evaluation is made at the first
-                # instant and a one-state check afterwards; unchanged control boxes reuse
-                # the chunk's control grids
-                tb.tabulate_states_batched(sys, state_grid, sb, se, host, w_grid, t_k, entry_off,
-                                           g_off, Upad, g_per_w, flush, align=align,
-                                           verify=1 if prev_mode == "batched" else 8,
-                                           grid_cache=self._grid_cache if t_k is not None else None)
-            else:
-                states = mine if (mine is not None and (sb, se) == (eq[rank], eq[rank + 1])) else \
-                    tb.state_tuples(state_grid, sb, se)
-                tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
-                                   g_per_w, flush, align=align)
-            return L
+            prev_mode = reuse.tabulate_mode if reuse is not None else None
+            T = reuse if (reuse is not None and reuse.W == W and reuse.d == d and reuse.tiled == tiled) \
+                else SweepTables()
+            T.grid, T.d, T.W = grid, d, W
+            T.tiled = tiled
+            T.expect = 1 if nb_perturb == 1 else 0
+            T.bounds, T.state_begin, T.n_states = bounds, sb, n
+            T.host_full = host_full
+            T.n_backups_local = int(U.sum()) * W
+            T.n_backups_total = int(U_all.sum()) * W
+            # host copy of the probabilities, kept alive with the tables (SdpTables.p_host)
+            T.p_host = np.ascontiguousarray(solver.perturb_proba[0], dtype=np.float64).copy() \
+                if nb_perturb == 1 else np.ones(1)
+            T.p = self.to_device(T.p_host)
+            T.U_dev = self.to_device(U.astype(np.int32)) if n else torch.zeros(1, dtype=torch.int32, device=dev)
+            # replicated control discretisation, for the argmin -> control value kernel
+            T.lo_dev = self.to_device(host_full.lo.reshape(-1)) if nb_control else None
+            T.hi_dev = self.to_device(host_full.hi.reshape(-1)) if nb_control else None
+            T.npts_dev = self.to_device(host_full.npts.astype(np.int32).reshape(-1)) if nb_control else None
+            T.nb_control = nb_control
+            T.tabulate_mode = None
 
-        # mode / layout resolution: batched evaluation is tried first in "auto"
-        # mode and abandoned if it fails or is not bit-identical to the
-        # reference's per-state calls on the sample states; factored tables are
-        # abandoned for dense ones as soon as one chunk does not fit the split
-        g_per_w = T.g_per_w if (reuse is T and not u_mask) else 0
-        batched = mode in ("auto", "batched")
-        L = None
-        while L is None:
-            try:
-                L = build(g_per_w, batched, u_mask)
-                T.tabulate_mode = "batched" if batched else "per_state"
-            except tb.NotFactorable:
-                if compress == "on" or world > 1:
-                    # (with several ranks a silent per-rank fallback would desynchronise the layouts)
-                    raise ValueError("dyn/cost outputs do not keep the (x,u) + (x,w) structure "
-                                     "seen on the probe state; use solver.table_compress = 'off'")
-                u_mask = 0
-            except tb.GDependsOnW:
-                if g_per_w:
-                    raise
+            def ensure(name, numel, dtype):
+                """(re)allocate T.<name> only when the size changes (time-dependent
+                recursions rebuild same-sized tables at every instant)"""
+                t = getattr(T, name)
+                if t is None or t.numel() != numel or t.dtype != dtype:
+                    setattr(T, name, None)        # release before allocating the new size
+                    setattr(T, name, torch.empty(numel, dtype=dtype, device=dev))
+
+            def build(g_per_w, batched, u_mask):
+                L = {"u_mask": u_mask}
+                n_tiles, tile_U, tile_off, n_entries, entry_off, Upad = sizes(u_mask)
+                lam_plane = (n_entries + 3) // 4 * 4
+                n_u = bin(u_mask).count("1")
+                L.update(n_tiles=n_tiles, tile_U=tile_U, tile_off=tile_off, n_entries=n_entries,
+                         entry_off=entry_off, Upad=Upad, lam_plane=lam_plane)
+                ensure("cell", max(lam_plane, 4), torch.int32)
+                ensure("lam", max(lam_plane, 4) * (n_u if u_mask else d), torch.float64)
                 if u_mask:
-                    u_mask = 0
+                    n_wp = (n_tiles * 32 if tiled else n) * W
+                    lam_w_plane = (n_wp + 3) // 4 * 4
+                    ensure("cell_w", max(lam_w_plane, 4), torch.int32)
+                    ensure("lam_w", max(lam_w_plane, 4) * (d - n_u), torch.float64)
                 else:
-                    g_per_w = 1      # the cost depends on w: dense g table
-            except tb.BatchedMismatch:
-                if mode != "auto":
-                    raise
-                batched = False      # not bit-identical to per-state calls
-            except Exception:
-                if not (batched and mode == "auto"):
-                    raise
-                batched = False      # callables not vectorisable over states
-        T.u_mask = u_mask
-        T.g_per_w = g_per_w
-        n_tiles, tile_U, tile_off = L["n_tiles"], L["tile_U"], L["tile_off"]
-        entry_off, Upad, g_off, tile_g_off = L["entry_off"], L["Upad"], L["g_off"], L["tile_g_off"]
-        lam_plane = L["lam_plane"]
-        T.n_entries, T.lam_plane, T.lam_w_plane = L["n_entries"], lam_plane, L["lam_w_plane"]
-        Wf = 1 if u_mask else W     # table entries per control
+                    T.cell_w = T.lam_w = None
+                    lam_w_plane = 0
+                L["lam_w_plane"] = lam_w_plane
+                tile_g_off = None
+                if u_mask:
+                    # one g per (x,u) entry, indexed like the u-part
+                    g_off, g_len = entry_off, n_entries
+                    tile_g_off = tile_off
+                elif tiled:
+                    if g_per_w:
+                        tile_g_off = tile_off
+                    else:
+                        tile_g_off = np.zeros(n_tiles + 1, dtype=np.int64)
+                        np.cumsum(tile_U * 32, out=tile_g_off[1:])
+                    g_off = np.zeros(n + 1, dtype=np.int64)
+                    g_len = int(tile_g_off[-1])
+                else:
+                    if g_per_w:
+                        g_off = entry_off
+                    else:
+                        g_off = np.zeros(n + 1, dtype=np.int64)
+                        np.cumsum(Upad, out=g_off[1:])
+                    g_len = int(g_off[-1])
+                if tiled:
+                    tile_off_dev = self.to_device(tile_off)
+                    tile_g_off_dev = self.to_device(tile_g_off)
+                    tile_U_dev = self.to_device(tile_U.astype(np.int32))
+                L.update(g_off=g_off, tile_g_off=tile_g_off)
+                ensure("g", max(g_len, 4), torch.float64)
+                done = [0]      # states flushed so far (chunks arrive in order)
 
-        # work items: one warp per run of at most `item_chunk` controls
-        chunk = self.item_chunk
-        if tiled:
-            units, unit_U = n_tiles, tile_U
-        else:
-            units, unit_U = n, U
-        if self.item_chunk_auto:
-            # a B200 holds 148 SMs x 16..64 resident warps; with fewer items than a few
-            # waves the sweep is latency-bound (and its tail is long), so cut the runs
-            # shorter.  Layout A walks 128 controls per warp iteration, layout B one.
-            chunk = pick_item_chunk(unit_U, 128 if not tiled else 32)
-        T.item_chunk = chunk
-        n_it = (unit_U + chunk - 1) // chunk
-        item_begin = np.zeros(units + 1, dtype=np.int64)
-        np.cumsum(n_it, out=item_begin[1:])
-        n_items = int(item_begin[-1])
-        st = np.repeat(np.arange(units, dtype=np.int64), n_it)
-        kk = np.arange(n_items, dtype=np.int64) - item_begin[st]
-        items = np.zeros(n_items, dtype=_cabi.ITEM_DTYPE)
-        items["u_begin"] = kk * chunk
-        items["u_count"] = np.minimum(chunk, unit_U[st] - kk * chunk)
-        items["state"] = st
-        if tiled:
-            items["entry_base"] = tile_off[st] + kk * chunk * Wf * 32
-            items["g_base"] = items["entry_base"] if (T.g_per_w or u_mask) else \
-                tile_g_off[st] + kk * chunk * 32
-            items["Upad"] = 0
-        else:
-            items["entry_base"] = entry_off[st] + kk * chunk
-            items["g_base"] = g_off[st] + kk * chunk
-            items["Upad"] = Upad[st]
-        T.n_items = n_items
-        T.item_begin_host = item_begin
-        T.unit_U_host = np.asarray(unit_U, dtype=np.int64)
-        T.chunk_plan = None
-        T.items = torch.from_numpy(items.view(np.uint8).reshape(-1)).to(dev) if n_items else \
-            torch.zeros(32, dtype=torch.uint8, device=dev)
-        T.item_begin = self.to_device(item_begin)
-        n_part = max(n_items, 1) * (32 if tiled else 1)
-        T.part_val = torch.empty(n_part, dtype=torch.float64, device=dev)
-        T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)
-        T.J_out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
-        T.argmin = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+                def flush(desc, staging):
+                    if u_mask:
+                        tb.check_factorable(desc, d, u_mask)
+                    desc_dev = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(dev)
+                    stag_dev = torch.from_numpy(staging).to(dev)
+                    ns = len(desc)
+                    if tiled:
+                        assert done[0] % 32 == 0
+                        t_first = done[0] // 32
+                        nt = (ns + 31) // 32
+                        t_off = ctypes.c_void_p(tile_off_dev.data_ptr() + 8 * t_first)
+                        t_U = ctypes.c_void_p(tile_U_dev.data_ptr() + 4 * t_first)
+                        t_Umax = int(tile_U[t_first:t_first + nt].max())
+                        if u_mask:
+                            w0 = t_first * W * 32
+                            rc = self.lib.sdp_build_tables_factored_tiled(
+                                ctypes.byref(grid), W, u_mask, ns, self._ptr(desc_dev), self._ptr(stag_dev),
+                                nt, t_off, t_U, t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane,
+                                self._ptr(T.g), ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
+                                ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
+                            _cabi.check(rc, "sdp_build_tables_factored_tiled")
+                        else:
+                            rc = self.lib.sdp_build_tables_tiled(
+                                ctypes.byref(grid), W, g_per_w, ns, self._ptr(desc_dev), self._ptr(stag_dev),
+                                nt, t_off, ctypes.c_void_p(tile_g_off_dev.data_ptr() + 8 * t_first), t_U,
+                                t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g),
+                                self.stream)
+                            _cabi.check(rc, "sdp_build_tables_tiled")
+                    elif u_mask:
+                        w0 = done[0] * W
+                        rc = self.lib.sdp_build_tables_factored(
+                            ctypes.byref(grid), W, u_mask, ns, self._ptr(desc_dev), self._ptr(stag_dev),
+                            self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g),
+                            int(desc["Upad"].max()), ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
+                            ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
+                        _cabi.check(rc, "sdp_build_tables_factored")
+                    else:
+                        rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, ns,
+                                                       self._ptr(desc_dev), self._ptr(stag_dev),
+                                                       self._ptr(T.cell), self._ptr(T.lam), lam_plane,
+                                                       self._ptr(T.g), int(desc["Upad"].max()), self.stream)
+                        _cabi.check(rc, "sdp_build_tables")
+                    done[0] += ns
+                    # the staging tensors are freed by torch's caching allocator in
+                    # stream order, so no synchronisation is needed here
 
-        c = _cabi.SdpTables()
-        c.cell = T.cell.data_ptr()
-        c.lam = T.lam.data_ptr()
-        c.lam_plane = lam_plane
-        c.g = T.g.data_ptr()
-        c.g_per_w = T.g_per_w
-        c.W = W
-        c.expect = T.expect
-        if u_mask:
-            c.layout = _cabi.LAYOUT_STATE_MINOR_FACTORED if tiled else _cabi.LAYOUT_CONTROL_MINOR_FACTORED
-            c.u_mask = u_mask
-            c.cell_w = T.cell_w.data_ptr()
-            c.lam_w = T.lam_w.data_ptr()
-            c.lam_w_plane = T.lam_w_plane
-        else:
-            c.layout = _cabi.LAYOUT_STATE_MINOR if tiled else _cabi.LAYOUT_CONTROL_MINOR
-        c.p = T.p.data_ptr()
-        c.p_host = T.p_host.ctypes.data
-        c.items = T.items.data_ptr()
-        c.n_items = n_items
-        c.item_begin = T.item_begin.data_ptr()
-        c.n_states = n
-        c.U = T.U_dev.data_ptr()
-        T.c_tables = c
+                align = 32 if tiled else 1
+                if batched:
+                    # time-dependent recursion: the callables are the same at every instant, so
+                    # the full bit-for-bit check of the batched evaluation is made at the first
+                    # instant and a one-state check afterwards; unchanged control boxes reuse
+                    # the chunk's control grids
+                    tb.tabulate_states_batched(sys, state_grid, sb, se, host, w_grid, t_k, entry_off,
+                                               g_off, Upad, g_per_w, flush, align=align,
+                                               verify=1 if prev_mode == "batched" else 8,
+                                               grid_cache=self._grid_cache if t_k is not None else None)
+                else:
+                    states = mine if (mine is not None and (sb, se) == (eq[rank], eq[rank + 1])) else \
+                        tb.state_tuples(state_grid, sb, se)
+                    tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
+                                       g_per_w, flush, align=align)
+                return L
+
+            # mode / layout resolution: batched evaluation is tried first in "auto"
+            # mode and abandoned if it fails or is not bit-identical to the
+            # reference's per-state calls on the sample states; factored tables are
+            # abandoned for dense ones as soon as one chunk does not fit the split
+            g_per_w = T.g_per_w if (reuse is T and not u_mask) else 0
+            batched = mode in ("auto", "batched")
+            L = None
+            while L is None:
+                try:
+                    L = build(g_per_w, batched, u_mask)
+                    T.tabulate_mode = "batched" if batched else "per_state"
+                except tb.NotFactorable:
+                    if compress == "on" or world > 1:
+                        # (with several ranks a silent per-rank fallback would desynchronise the layouts)
+                        raise ValueError("dyn/cost outputs do not keep the (x,u) + (x,w) structure "
+                                         "seen on the probe state; use solver.table_compress = 'off'")
+                    u_mask = 0
+                except tb.GDependsOnW:
+                    if g_per_w:
+                        raise
+                    if u_mask:
+                        u_mask = 0
+                    else:
+                        g_per_w = 1      # the cost depends on w: dense g table
+                except tb.BatchedMismatch:
+                    if mode != "auto":
+                        raise
+                    batched = False      # not bit-identical to per-state calls
+                except Exception:
+                    if not (batched and mode == "auto"):
+                        raise
+                    batched = False      # callables not vectorisable over states
+            T.u_mask = u_mask
+            T.g_per_w = g_per_w
+            n_tiles, tile_U, tile_off = L["n_tiles"], L["tile_U"], L["tile_off"]
+            entry_off, Upad, g_off, tile_g_off = L["entry_off"], L["Upad"], L["g_off"], L["tile_g_off"]
+            lam_plane = L["lam_plane"]
+            T.n_entries, T.lam_plane, T.lam_w_plane = L["n_entries"], lam_plane, L["lam_w_plane"]
+            Wf = 1 if u_mask else W     # table entries per control
+
+            # work items: one warp per run of at most `item_chunk` controls
+            chunk = self.item_chunk
+            if tiled:
+                units, unit_U = n_tiles, tile_U
+            else:
+                units, unit_U = n, U
+            if self.item_chunk_auto:
+                # a B200 holds 148 SMs x 16..64 resident warps; with fewer items than a few
+                # waves the sweep is latency-bound (and its tail is long), so cut the runs
+                # shorter.  Layout A walks 128 controls per warp iteration, layout B one.
+                chunk = pick_item_chunk(unit_U, 128 if not tiled else 32)
+            T.item_chunk = chunk
+            n_it = (unit_U + chunk - 1) // chunk
+            item_begin = np.zeros(units + 1, dtype=np.int64)
+            np.cumsum(n_it, out=item_begin[1:])
+            n_items = int(item_begin[-1])
+            st = np.repeat(np.arange(units, dtype=np.int64), n_it)
+            kk = np.arange(n_items, dtype=np.int64) - item_begin[st]
+            items = np.zeros(n_items, dtype=_cabi.ITEM_DTYPE)
+            items["u_begin"] = kk * chunk
+            items["u_count"] = np.minimum(chunk, unit_U[st] - kk * chunk)
+            items["state"] = st
+            if tiled:
+                items["entry_base"] = tile_off[st] + kk * chunk * Wf * 32
+                items["g_base"] = items["entry_base"] if (T.g_per_w or u_mask) else \
+                    tile_g_off[st] + kk * chunk * 32
+                items["Upad"] = 0
+            else:
+                items["entry_base"] = entry_off[st] + kk * chunk
+                items["g_base"] = g_off[st] + kk * chunk
+                items["Upad"] = Upad[st]
+            T.n_items = n_items
+            T.item_begin_host = item_begin
+            T.unit_U_host = np.asarray(unit_U, dtype=np.int64)
+            T.chunk_plan = None
+            T.items = torch.from_numpy(items.view(np.uint8).reshape(-1)).to(dev) if n_items else \
+                torch.zeros(32, dtype=torch.uint8, device=dev)
+            T.item_begin = self.to_device(item_begin)
+            n_part = max(n_items, 1) * (32 if tiled else 1)
+            T.part_val = torch.empty(n_part, dtype=torch.float64, device=dev)
+            T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)
+            T.J_out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+            T.argmin = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+
+            c = _cabi.SdpTables()
+            c.cell = T.cell.data_ptr()
+            c.lam = T.lam.data_ptr()
+            c.lam_plane = lam_plane
+            c.g = T.g.data_ptr()
+            c.g_per_w = T.g_per_w
+            c.W = W
+            c.expect = T.expect
+            if u_mask:
+                c.layout = _cabi.LAYOUT_STATE_MINOR_FACTORED if tiled else _cabi.LAYOUT_CONTROL_MINOR_FACTORED
+                c.u_mask = u_mask
+                c.cell_w = T.cell_w.data_ptr()
+                c.lam_w = T.lam_w.data_ptr()
+                c.lam_w_plane = T.lam_w_plane
+            else:
+                c.layout = _cabi.LAYOUT_STATE_MINOR if tiled else _cabi.LAYOUT_CONTROL_MINOR
+            c.p = T.p.data_ptr()
+            c.p_host = T.p_host.ctypes.data
+            c.items = T.items.data_ptr()
+            c.n_items = n_items
+            c.item_begin = T.item_begin.data_ptr()
+            c.n_states = n
+            c.U = T.U_dev.data_ptr()
+            T.c_tables = c
+            return T
+
+        # slabs balanced by admissible controls ...
+        bounds = partition_by_weight(U_all + 1, world) if world > 1 else [0, n_grid]
+        T = build_for(bounds, reuse)
+        # ... then, with several ranks, by the measured cost of a backup in each slab
+        balance = getattr(solver, "slab_balance", "auto")
+        if world > 1 and self._cuda and balance != "controls" and \
+                (balance == "measured" or T.n_backups_total >= self.REBALANCE_MIN_BACKUPS):
+            new_bounds = self._measured_bounds(T, U_all)
+            if new_bounds is not None:
+                T = build_for(new_bounds, T)
         self.sync()
         T.setup_seconds = time.perf_counter() - t0
         return T

@@ -59,6 +59,10 @@ class DPSolver(object):
         # "auto": keep the tables as a (x,u) part + a (x,w) part whenever dyn/cost
         # have that structure (every reference example does); "off": always dense
         self.table_compress = "auto"  # "auto" | "off" | "on"
+        # several ranks: cut the grid into slabs of equal admissible controls ("controls"), or
+        # re-cut once by the measured sweep time of every slab ("measured"; "auto" does so
+        # for sweeps of at least 5e8 backups)
+        self.slab_balance = "auto"    # "auto" | "controls" | "measured"
 
     # ------------------------------------------------------------------
     # discretisation (host only)
@@ -151,7 +155,7 @@ class DPSolver(object):
                 tuple(sig(g) for g in self.perturb_grid),
                 tuple(sig(p) for p in self.perturb_proba),
                 tuple(float(c) for c in self.control_steps),
-                self.table_layout, self.tabulate, self.table_compress)
+                self.table_layout, self.tabulate, self.table_compress, self.slab_balance)
 
     def clear_tables(self):
         """drop the device-resident tables (call after mutating anything the

@@ -34,6 +34,11 @@ def main():
         prob = wl.storage_ar1(sdp)
         sv = prob.solver
         sv.table_layout = layout
+        if layout == "state_minor":
+            # force the measured re-cut of the slabs (tolerance 0: any difference moves them)
+            from stodynprog_b200.engine import Engine
+            Engine.REBALANCE_TOLERANCE = 0.0
+            sv.slab_balance = "measured"
         J = prob.J0
         for k in range(3):
             J, pol = sv.value_iteration(J, report_time=False)
@@ -47,8 +52,9 @@ def main():
         if rank == 0:
             print("[%s] tables %s, exchange: %s" % (layout, T.layout_name,
                   "peer memory (fused combine + all-gather)" if px is not None else "NCCL all-gather"))
-        print("[%s] rank %d slab [%d, %d) backups %d of %d" % (layout, rank, T.state_begin,
-              T.state_begin + T.n_states, T.n_backups_local, T.n_backups_total), flush=True)
+        print("[%s] rank %d slab [%d, %d) backups %d of %d; slab times before re-cut: %s" % (
+              layout, rank, T.state_begin, T.state_begin + T.n_states, T.n_backups_local,
+              T.n_backups_total, T.slab_times_ms), flush=True)
         (Jd, Jr), polp = sv.policy_iteration(prob.initial_policy(), 50, 4, rel_dp=True)
         bad = int(np.any(polp != G["pi_pol"], axis=-1).sum())
         errJ = float(np.max(np.abs(Jd - G["pi_J"])) / np.max(np.abs(G["pi_J"])))

@@ -211,6 +211,25 @@ def test_batched_control_box_scan():
     assert tb.scan_control_boxes_batched(S, steps, grid, 0, n) is None
 
 
+def test_rebalance_bounds():
+    from stodynprog_b200.engine import rebalance_bounds, partition_by_weight
+    U = np.full(8000, 200)
+    b0 = partition_by_weight(U + 1, 4)
+    assert b0 == [0, 2000, 4000, 6000, 8000]
+    # balanced within tolerance, or a missing time: nothing moves
+    assert rebalance_bounds(U, b0, [1.0, 1.01, 0.99, 1.0]) is None
+    assert rebalance_bounds(U, b0, [1.0, 0.0, 1.0, 1.0]) is None
+    # slab 1 is 20 % slower: it shrinks, the others grow, and the estimated times equalise
+    t = np.array([1.0, 1.2, 1.0, 1.0])
+    b1 = rebalance_bounds(U, b0, t)
+    assert b1[0] == 0 and b1[-1] == 8000 and b1 == sorted(b1)
+    assert b1[2] - b1[1] < 2000 < b1[1] - b1[0]
+    density = np.repeat(t / 2000.0, 2000)
+    est = [density[b1[r]:b1[r + 1]].sum() for r in range(4)]
+    assert max(est) / min(est) < 1.002
+    assert max(est) < 1.06          # was 1.2 before the re-cut
+
+
 def test_pick_item_chunk():
     from stodynprog_b200.engine import pick_item_chunk, ITEMS_TARGET
     # plenty of units: keep the long runs
