@@ -317,7 +317,7 @@ def run_ours(args):
                             dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        k1_per_rank = {"balance": "re-cut by measured slab times" if T.slab_times_ms else "admissible controls",
+        k1_per_rank = {"balance": "re-cut by measured slab times" if T.slab_recut else "equal admissible controls",
                        "kernel_ms_before_recut": T.slab_times_ms,
                        "kernel_ms": [round(float(x[0]), 4) for x in allr],
                        "backups": [int(x[1]) for x in allr], "states": [int(x[2]) for x in allr]}

@@ -246,7 +246,8 @@ class SweepTables(object):
         self.item_chunk = 0        # controls per work item used for these tables
         self.item_begin_host = self.unit_U_host = None
         self.chunk_plan = None     # see Engine._chunk_plan
-        self.slab_times_ms = None  # measured per-rank sweep times behind a re-cut of the slabs
+        self.slab_times_ms = None  # measured per-rank sweep times (several ranks, see _measured_bounds)
+        self.slab_recut = False    # True when those times moved the slab boundaries
 
     @property
     def algorithmic_bytes_per_backup(self):
@@ -429,6 +430,7 @@ class Engine(object):
     # -- slab balance -----------------------------------------------------
     REBALANCE_MIN_BACKUPS = 500 * 1000 * 1000    # "auto": only sweeps long enough to matter
     REBALANCE_TOLERANCE = 1.03                   # slowest / mean slab time that is left alone
+    REBALANCE_SKEW = None                        # test hook (tests/multi_gpu_check.py)
 
     def _measured_bounds(self, T, U_all):
         """Slab boundaries equalising the MEASURED sweep time of the ranks.
@@ -460,6 +462,8 @@ class Engine(object):
             self.sync()
             t_mine = float(np.median([a.elapsed_time(b) for a, b in evs[2:]]))
         t = np.asarray(coll.all_gather_object(t_mine), dtype=float)
+        if self.REBALANCE_SKEW is not None:      # test hook: pretend some slabs are slower
+            t = t * np.asarray(self.REBALANCE_SKEW, dtype=float)[:len(t)]
         T.slab_times_ms = [float(x) for x in t]
         return rebalance_bounds(U_all, T.bounds, t, self.REBALANCE_TOLERANCE)
 
@@ -833,6 +837,7 @@ class Engine(object):
             new_bounds = self._measured_bounds(T, U_all)
             if new_bounds is not None:
                 T = build_for(new_bounds, T)
+                T.slab_recut = True
         self.sync()
         T.setup_seconds = time.perf_counter() - t0
         return T

@@ -38,6 +38,7 @@ def main():
             # force the measured re-cut of the slabs (tolerance 0: any difference moves them)
             from stodynprog_b200.engine import Engine
             Engine.REBALANCE_TOLERANCE = 0.0
+            Engine.REBALANCE_SKEW = [1.0 + 0.25 * (r % 2) for r in range(dist.get_world_size())]
             sv.slab_balance = "measured"
         J = prob.J0
         for k in range(3):
@@ -52,9 +53,11 @@ def main():
         if rank == 0:
             print("[%s] tables %s, exchange: %s" % (layout, T.layout_name,
                   "peer memory (fused combine + all-gather)" if px is not None else "NCCL all-gather"))
-        print("[%s] rank %d slab [%d, %d) backups %d of %d; slab times before re-cut: %s" % (
+        print("[%s] rank %d slab [%d, %d) backups %d of %d; re-cut: %s" % (
               layout, rank, T.state_begin, T.state_begin + T.n_states, T.n_backups_local,
-              T.n_backups_total, T.slab_times_ms), flush=True)
+              T.n_backups_total, T.slab_recut), flush=True)
+        if layout == "state_minor":
+            ok &= bool(T.slab_recut)
         (Jd, Jr), polp = sv.policy_iteration(prob.initial_policy(), 50, 4, rel_dp=True)
         bad = int(np.any(polp != G["pi_pol"], axis=-1).sum())
         errJ = float(np.max(np.abs(Jd - G["pi_J"])) / np.max(np.abs(G["pi_J"])))
