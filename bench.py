@@ -249,6 +249,8 @@ def roofline_of(T, k1_ms, ms_total, K, peak, peak_src, traffic):
 
 
 def run_ours(args):
+    # a rank that dies must fail the run quickly, not leave its peers spinning on flags
+    os.environ.setdefault("SDP_P2P_TIMEOUT_S", "120")
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))

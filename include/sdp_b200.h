@@ -169,7 +169,8 @@ int64_t sdp_launch_count(void);
  * variables): "upl" (2|4), "wb" (1|2|3|5), "tma" (layout-B kernel: 0 straight
  * LDG, 1 TMA-fed ring, 2 software-pipelined LDG = default), "rb" (2|4|8),
  * "tma_rows" (4|8), "tma_stages" (2..16), "tma_warps" (1..16), "hoist" (layout AF
- * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4).
+ * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4),
+ * "p2p_timeout_s" (bound of the peer-flag waits, default 600 s, then the kernel traps).
  * Not thread-safe against concurrent launches. */
 int sdp_set_option(const char* name, int value);
 
@@ -274,7 +275,9 @@ int sdp_p2p_barrier(const SdpPeers* peers, void* stream);
  * states [state_begin, state_begin + n_states) of the other; on return the
  * result is in J_a if n_iter is even, J_b if odd.
  * rel_dp != 0: after each iteration J_ref_hist[k] = J[ref_index]; J -= that
- * (stodynprog.py:760-762); requires the shard to be the whole grid.
+ * (stodynprog.py:760-762), fused into the backup kernel (every block recomputes the
+ * reference state's backup, same operations, same bits); requires the shard to be the
+ * whole grid.
  * J_ref_hist: device [n_iter] (may be NULL when rel_dp == 0). */
 int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, const double* p,
                     const int32_t* cell, const double* lam, int64_t lam_plane,
@@ -285,13 +288,18 @@ int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, const doubl
 /* One fixed-policy backup of this rank's slab fused with the all-gather over peer
  * memory: as one iteration of sdp_policy_eval, but the new values go to
  * peers->J[r][state_begin + i] for every rank r and the rank's epoch is published
- * (same protocol as sdp_sweep_finalize_p2p; follow with sdp_p2p_wait, then - under
- * relative DP - sdp_rel_shift on the local copy, which every rank does identically).
- * J_in: device [n_grid], the full previous value function on this rank. */
+ * (same protocol as sdp_sweep_finalize_p2p; follow with sdp_p2p_wait).
+ * J_in: device [n_grid], the full previous value function on this rank.
+ * Relative DP (ref_cell != NULL): every rank passes its own copy of the table entries
+ * of the reference state - ref_cell [W], ref_lam [d][W], ref_g [W] (g_per_w) or [1] -
+ * and the kernel subtracts that state's new value from everything it stores
+ * (stodynprog.py:760-762); J_ref_out[0] receives it. */
 int sdp_policy_eval_p2p(const SdpGrid* grid, int32_t W, int32_t g_per_w, const double* p,
                         const int32_t* cell, const double* lam, int64_t lam_plane,
                         const double* g, int64_t n_states, int64_t state_begin, int64_t n_grid,
-                        const double* J_in, const SdpPeers* peers, void* stream);
+                        const double* J_in, const SdpPeers* peers, const int32_t* ref_cell,
+                        const double* ref_lam, const double* ref_g, double* J_ref_out,
+                        void* stream);
 
 /* K3 - argmin index -> control values, the `u_grids[i].flatten()[ind_opt[i]]` of
  * stodynprog.py:686-689 for every state at once.  lo/hi: device [n][nc] box

@@ -120,7 +120,7 @@ SIGNATURES = {
     "sdp_policy_eval": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
                                        _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
     "sdp_policy_eval_p2p": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
-                                           _vp, ctypes.POINTER(SdpPeers), _vp]),
+                                           _vp, ctypes.POINTER(SdpPeers), _vp, _vp, _vp, _vp, _vp]),
     "sdp_policy_values": (ctypes.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdp_rel_shift": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "sdp_supnorm_diff": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -1022,7 +1022,9 @@ struct Tuning {
     int R, S, NW; // TMA ring: rows per stage (4|8), stages, warps per CTA
     int hoist;    // layout AF, u_mask == 1: tabulate the inner interpolation per item (1) or not (0)
     int hoist_upl; // controls per lane per iteration of the hoisted kernel (2|4)
+    int p2p_timeout_s; // bound of the peer-flag waits (seconds) before the kernel traps
 };
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -1049,12 +1051,11 @@ static Tuning& tuning() {
         x.NW = env_int("SDP_TMA_NW", 4);
         x.hoist = env_int("SDP_HOIST", 1) != 0;
         x.hoist_upl = env_int("SDP_HOIST_UPL", 2) == 4 ? 4 : 2;
+        x.p2p_timeout_s = clampi(env_int("SDP_P2P_TIMEOUT_S", 600), 1, 86400);
         return x;
     }();
     return t;
 }
-static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
 extern "C" int sdp_set_option(const char* name, int value) {
     if (!name) return fail(SDP_EINVAL, "%s", "sdp_set_option: NULL name");
     Tuning& t = tuning();
@@ -1067,6 +1068,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "tma_warps")) t.NW = value;
     else if (!strcmp(name, "hoist")) t.hoist = value != 0;
     else if (!strcmp(name, "hoist_upl")) t.hoist_upl = (value == 4) ? 4 : 2;
+    else if (!strcmp(name, "p2p_timeout_s")) t.p2p_timeout_s = clampi(value, 1, 86400);
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1695,12 +1697,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 // Bounded flag wait: a peer that died (or a call sequence that differs between the
 // ranks) must surface as a CUDA error on this rank, not as a hung GPU.
-#define SDP_P2P_TIMEOUT_NS 30000000000ULL
-__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long e) {
+// (default 600 s, like a collective watchdog: the ranks of an SPMD script may reach a
+// call minutes apart; `sdp_set_option("p2p_timeout_s", s)` / SDP_P2P_TIMEOUT_S change it)
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long e,
+                                          unsigned long long timeout_ns) {
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(p) < e) {
         __nanosleep(20);
-        if (global_ns() - t0 > SDP_P2P_TIMEOUT_NS) __trap();
+        if (global_ns() - t0 > timeout_ns) __trap();
     }
 }
 
@@ -1754,15 +1758,15 @@ k_sweep_finalize_p2p(int64_t n_states, const int64_t* __restrict__ item_begin,
     publish_epoch(P);
 }
 
-__global__ void k_p2p_wait(PeersDev P) {
+__global__ void k_p2p_wait(PeersDev P, unsigned long long timeout_ns) {
     const int t = threadIdx.x;
     if (t < P.world) {
         const unsigned long long e = *P.epoch;
-        wait_flag(P.flags[P.rank] + t, e);
+        wait_flag(P.flags[P.rank] + t, e, timeout_ns);
     }
 }
 
-__global__ void k_p2p_barrier(PeersDev P) {
+__global__ void k_p2p_barrier(PeersDev P, unsigned long long timeout_ns) {
     __shared__ unsigned long long e_sh;
     if (threadIdx.x == 0) {
         e_sh = *P.epoch + 1;
@@ -1773,7 +1777,7 @@ __global__ void k_p2p_barrier(PeersDev P) {
     const int t = threadIdx.x;
     if (t < P.world) {
         st_release_sys(P.flags[t] + P.rank, e_sh);
-        wait_flag(P.flags[P.rank] + t, e_sh);
+        wait_flag(P.flags[P.rank] + t, e_sh, timeout_ns);
     }
 }
 
@@ -1824,7 +1828,7 @@ extern "C" int sdp_p2p_wait(const SdpPeers* peers, void* stream) {
     PeersDev P;
     int rc = make_peers(peers, &P, "sdp_p2p_wait");
     if (rc) return rc;
-    k_p2p_wait<<<1, 32, 0, (cudaStream_t)stream>>>(P);
+    k_p2p_wait<<<1, 32, 0, (cudaStream_t)stream>>>(P, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
@@ -1833,7 +1837,7 @@ extern "C" int sdp_p2p_barrier(const SdpPeers* peers, void* stream) {
     PeersDev P;
     int rc = make_peers(peers, &P, "sdp_p2p_barrier");
     if (rc) return rc;
-    k_p2p_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(P);
+    k_p2p_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(P, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
@@ -1842,50 +1846,89 @@ extern "C" int sdp_p2p_barrier(const SdpPeers* peers, void* stream) {
 // K1': fixed-policy backup. One thread per state, tables are [w][n_states]
 // planes so that adjacent threads read adjacent entries.
 // ---------------------------------------------------------------------------
+// one fixed-policy backup: sum_w p_w * (g + J(f(x, pol(x), w)))   (stodynprog.py:755,757);
+// entry w of the state sits at index w*stride of its arrays
 template <int D>
-__global__ void __launch_bounds__(256)
-k_policy_eval(GridT<double> G, int W, int g_per_w, const double* __restrict__ p,
-              const int32_t* __restrict__ cell, const double* __restrict__ lam, int64_t lam_plane,
-              const double* __restrict__ g, int64_t n_states, const double* __restrict__ J_in,
-              double* __restrict__ J_out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_states) return;
+__device__ __forceinline__ double policy_backup(const GridT<double>& G, int W, int g_per_w,
+                                                const double* __restrict__ p,
+                                                const int32_t* __restrict__ cell,
+                                                const double* __restrict__ lam, int64_t lam_plane,
+                                                const double* __restrict__ g, int64_t stride,
+                                                const double* __restrict__ J_in) {
     double acc = 0.0;
-    double gv = g_per_w ? 0.0 : g[i];
+    double gv = g_per_w ? 0.0 : g[0];
     for (int w = 0; w < W; ++w) {
-        const int64_t off = (int64_t)w * n_states + i;
+        const int64_t off = (int64_t)w * stride;
         double l[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) l[k] = lam[(int64_t)k * lam_plane + off];
         if (g_per_w) gv = g[off];
         double v = Lerp<double, D, 0>::eval(J_in, cell[off], G.stride, l);
-        acc = add_(acc, mul_(add_(gv, v), p[w]));   // stodynprog.py:755,757
+        acc = add_(acc, mul_(add_(gv, v), p[w]));
     }
-    J_out[i] = acc;
+    return acc;
+}
+
+// the table entries of the reference state of relative DP (device pointers)
+struct RefState {
+    const int32_t* cell;
+    const double* lam;
+    int64_t lam_plane;
+    const double* g;
+    int64_t stride;
+    double* hist;       // J_ref of this iteration is written here (by block 0)
+};
+
+// Relative DP (stodynprog.py:760-762: J_ref[k] = J_pol[ref_ind]; J_pol -= J_ref[k]) is
+// fused into the backup: thread 0 of every block recomputes the backup of the reference
+// state (the same operations in the same order, hence the same bits as the thread that
+// owns that state) and the block subtracts it - one launch per iteration instead of
+// three (backup, pick, subtract) in a loop that is launch-latency bound.
+template <int D, bool REL>
+__global__ void __launch_bounds__(256)
+k_policy_eval(GridT<double> G, int W, int g_per_w, const double* __restrict__ p,
+              const int32_t* __restrict__ cell, const double* __restrict__ lam, int64_t lam_plane,
+              const double* __restrict__ g, int64_t n_states, const double* __restrict__ J_in,
+              double* __restrict__ J_out, RefState R) {
+    __shared__ double ref_sh;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    if (i < n_states)
+        acc = policy_backup<D>(G, W, g_per_w, p, cell + i, lam + i, lam_plane, g + i, n_states, J_in);
+    if (REL) {
+        if (threadIdx.x == 0) {
+            ref_sh = policy_backup<D>(G, W, g_per_w, p, R.cell, R.lam, R.lam_plane, R.g, R.stride, J_in);
+            if (blockIdx.x == 0) R.hist[0] = ref_sh;
+        }
+        __syncthreads();
+        acc = sub_(acc, ref_sh);
+    }
+    if (i < n_states) J_out[i] = acc;
 }
 
 // Fixed-policy backup fused with the all-gather: the new value of every state of the
 // slab goes straight into every rank's J buffer (peer-mapped pointers), the last CTA
 // publishes the epoch - the same protocol as k_sweep_finalize_p2p.
-template <int D>
+template <int D, bool REL>
 __global__ void __launch_bounds__(256)
 k_policy_eval_p2p(GridT<double> G, int W, int g_per_w, const double* __restrict__ p,
                   const int32_t* __restrict__ cell, const double* __restrict__ lam, int64_t lam_plane,
                   const double* __restrict__ g, int64_t n_states, const double* __restrict__ J_in,
-                  PeersDev P, int64_t state_begin) {
+                  PeersDev P, int64_t state_begin, RefState R) {
+    __shared__ double ref_sh;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_states) {
-        double acc = 0.0;
-        double gv = g_per_w ? 0.0 : g[i];
-        for (int w = 0; w < W; ++w) {
-            const int64_t off = (int64_t)w * n_states + i;
-            double l[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) l[k] = lam[(int64_t)k * lam_plane + off];
-            if (g_per_w) gv = g[off];
-            double v = Lerp<double, D, 0>::eval(J_in, cell[off], G.stride, l);
-            acc = add_(acc, mul_(add_(gv, v), p[w]));   // stodynprog.py:755,757
+    double acc = 0.0;
+    if (i < n_states)
+        acc = policy_backup<D>(G, W, g_per_w, p, cell + i, lam + i, lam_plane, g + i, n_states, J_in);
+    if (REL) {
+        if (threadIdx.x == 0) {
+            ref_sh = policy_backup<D>(G, W, g_per_w, p, R.cell, R.lam, R.lam_plane, R.g, R.stride, J_in);
+            if (blockIdx.x == 0) R.hist[0] = ref_sh;
         }
+        __syncthreads();
+        acc = sub_(acc, ref_sh);
+    }
+    if (i < n_states) {
 #pragma unroll
         for (int r = 0; r < SDP_MAX_PEERS; ++r)
             if (r < P.world) P.J[r][state_begin + i] = acc;
@@ -1936,19 +1979,31 @@ extern "C" int sdp_policy_eval(const SdpGrid* grid, int32_t W, int32_t g_per_w, 
     unsigned blocks = (unsigned)((n_states + 255) / 256);
     double* in = J_a;
     double* out = J_b;
+    RefState R = {nullptr, nullptr, 0, nullptr, 0, nullptr};
+    if (rel_dp) {
+        // the reference state belongs to this shard (whole grid): its entries are in the tables
+        const int64_t ir = ref_index - state_begin;
+        R.cell = cell + ir; R.lam = lam + ir; R.lam_plane = lam_plane; R.g = g + ir; R.stride = n_states;
+    }
     for (int it = 0; it < n_iter; ++it) {
         double* o = out + state_begin;
-        switch (grid->d) {
-            case 1: k_policy_eval<1><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o); break;
-            case 2: k_policy_eval<2><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o); break;
-            case 3: k_policy_eval<3><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o); break;
-            default: k_policy_eval<4><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o); break;
+        if (rel_dp) {
+            R.hist = J_ref_hist + it;
+            switch (grid->d) {
+                case 1: k_policy_eval<1, true><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o, R); break;
+                case 2: k_policy_eval<2, true><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o, R); break;
+                case 3: k_policy_eval<3, true><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o, R); break;
+                default: k_policy_eval<4, true><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o, R); break;
+            }
+        } else {
+            switch (grid->d) {
+                case 1: k_policy_eval<1, false><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o, R); break;
+                case 2: k_policy_eval<2, false><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o, R); break;
+                case 3: k_policy_eval<3, false><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o, R); break;
+                default: k_policy_eval<4, false><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, in, o, R); break;
+            }
         }
         SDP_LAUNCH_CHECK();
-        if (rel_dp) {
-            rc = rel_shift_launch(out, n_grid, ref_index, J_ref_hist + it, st);
-            if (rc) return rc;
-        }
         double* t = in; in = out; out = t;
     }
     return SDP_OK;
@@ -1958,7 +2013,8 @@ extern "C" int sdp_policy_eval_p2p(const SdpGrid* grid, int32_t W, int32_t g_per
                                    const int32_t* cell, const double* lam, int64_t lam_plane,
                                    const double* g, int64_t n_states, int64_t state_begin,
                                    int64_t n_grid, const double* J_in, const SdpPeers* peers,
-                                   void* stream) {
+                                   const int32_t* ref_cell, const double* ref_lam,
+                                   const double* ref_g, double* J_ref_out, void* stream) {
     GridT<double> G;
     int64_t ng = 0;
     int rc = make_grid<double>(grid, &G, &ng);
@@ -1975,11 +2031,25 @@ extern "C" int sdp_policy_eval_p2p(const SdpGrid* grid, int32_t W, int32_t g_per
     cudaStream_t st = (cudaStream_t)stream;
     unsigned blocks = (unsigned)((n_states + 255) / 256);
     if (blocks == 0) blocks = 1;      // the epoch must advance on every rank, even for an empty slab
-    switch (grid->d) {
-        case 1: k_policy_eval_p2p<1><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin); break;
-        case 2: k_policy_eval_p2p<2><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin); break;
-        case 3: k_policy_eval_p2p<3><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin); break;
-        default: k_policy_eval_p2p<4><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin); break;
+    if (ref_cell) {
+        // relative DP: every rank holds a copy of the reference state's W entries ([w], stride 1)
+        if (!ref_lam || !ref_g || !J_ref_out || !p)
+            return fail(SDP_EINVAL, "%s", "sdp_policy_eval_p2p: incomplete reference-state arguments");
+        RefState R = {ref_cell, ref_lam, (int64_t)W, ref_g, 1, J_ref_out};
+        switch (grid->d) {
+            case 1: k_policy_eval_p2p<1, true><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin, R); break;
+            case 2: k_policy_eval_p2p<2, true><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin, R); break;
+            case 3: k_policy_eval_p2p<3, true><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin, R); break;
+            default: k_policy_eval_p2p<4, true><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin, R); break;
+        }
+    } else {
+        RefState R = {nullptr, nullptr, 0, nullptr, 0, nullptr};
+        switch (grid->d) {
+            case 1: k_policy_eval_p2p<1, false><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin, R); break;
+            case 2: k_policy_eval_p2p<2, false><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin, R); break;
+            case 3: k_policy_eval_p2p<3, false><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin, R); break;
+            default: k_policy_eval_p2p<4, false><<<blocks, 256, 0, st>>>(G, W, g_per_w, p, cell, lam, lam_plane, g, n_states, J_in, P, state_begin, R); break;
+        }
     }
     SDP_LAUNCH_CHECK();
     return SDP_OK;

@@ -285,6 +285,7 @@ class PolicyTables(object):
         self.W = 1
         self.g_per_w = 0
         self.cell = self.lam = self.g = self.p = None
+        self.ref_cell = self.ref_lam = self.ref_g = None   # reference state's entries (several ranks)
         self.lam_plane = 0
         self.state_begin = 0
         self.n_states = 0
@@ -1093,7 +1094,34 @@ class Engine(object):
         _cabi.check(rc, "sdp_cell_setup")
         P.g = self.to_device(g_arr.reshape(-1)) if n else torch.zeros(1, dtype=torch.float64, device=self.device)
         P.p = self.to_device(w_proba)
+        if world > 1:
+            # every rank keeps the W table entries of relative DP's reference state (the
+            # fused backup + shift kernel recomputes that state's value in every block)
+            ref_flat = int(np.ravel_multi_index(solver._state_ref_ind, state_dims))
+            rc_coords = np.stack([np.broadcast_to(self._as_full(c, full), full).reshape(n_grid, W)[ref_flat]
+                                  for c in x_next])                       # [d][W]
+            s_ref = self.to_device(np.ascontiguousarray(rc_coords))
+            P.ref_cell = torch.empty(W, dtype=torch.int32, device=self.device)
+            P.ref_lam = torch.empty(W * nb_state, dtype=torch.float64, device=self.device)
+            rc = self.lib.sdp_cell_setup(ctypes.byref(grid), W, self._ptr(s_ref), self._ptr(P.ref_cell),
+                                         self._ptr(P.ref_lam), self.stream)
+            _cabi.check(rc, "sdp_cell_setup")
+            g_full = self._as_full(g_k, full)
+            if g_per_w:
+                P.ref_g = self.to_device(np.ascontiguousarray(
+                    np.broadcast_to(g_full, full).reshape(n_grid, W)[ref_flat]))
+            else:
+                P.ref_g = self.to_device(np.ascontiguousarray(
+                    np.broadcast_to(g_full, state_dims + (1,)).reshape(n_grid)[ref_flat:ref_flat + 1]))
         return P
+
+    @staticmethod
+    def _as_full(a, full):
+        """dyn/cost output as an fp64 array of the rank of `full` (leading axes of size 1 added)"""
+        a = np.asarray(a)
+        if a.dtype != np.float64:
+            a = a.astype(float)
+        return a.reshape((1,) * (len(full) - a.ndim) + a.shape)
 
     def policy_eval(self, P, J_a, J_b, n_iter, rel_dp, ref_index, J_ref_hist):
         """n_iter fixed-policy backups, ping-pong between J_a and J_b (device fp64
@@ -1117,17 +1145,17 @@ class Engine(object):
             # values into every rank's buffer and publishes an epoch (no NCCL call)
             for k in range(n_iter):
                 k_new = px.index_of(nxt)
-                rc = self.lib.sdp_policy_eval_p2p(ctypes.byref(P.grid), P.W, P.g_per_w, self._ptr(P.p),
-                                                  self._ptr(P.cell), self._ptr(P.lam), P.lam_plane,
-                                                  self._ptr(P.g), n, sb, n_grid, self._ptr(cur),
-                                                  ctypes.byref(px.peers[k_new]), self.stream)
+                null = ctypes.c_void_p(0)
+                rc = self.lib.sdp_policy_eval_p2p(
+                    ctypes.byref(P.grid), P.W, P.g_per_w, self._ptr(P.p), self._ptr(P.cell),
+                    self._ptr(P.lam), P.lam_plane, self._ptr(P.g), n, sb, n_grid, self._ptr(cur),
+                    ctypes.byref(px.peers[k_new]),
+                    self._ptr(P.ref_cell) if rel_dp else null, self._ptr(P.ref_lam) if rel_dp else null,
+                    self._ptr(P.ref_g) if rel_dp else null,
+                    ctypes.c_void_p(J_ref_hist.data_ptr() + 8 * k) if rel_dp else null, self.stream)
                 _cabi.check(rc, "sdp_policy_eval_p2p")
                 rc = self.lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), self.stream)
                 _cabi.check(rc, "sdp_p2p_wait")
-                if rel_dp:
-                    ref_ptr = ctypes.c_void_p(J_ref_hist.data_ptr() + 8 * k)
-                    rc = self.lib.sdp_rel_shift(self._ptr(nxt), n_grid, int(ref_index), ref_ptr, self.stream)
-                    _cabi.check(rc, "sdp_rel_shift")
                 cur, nxt = nxt, cur
             return cur
         for k in range(n_iter):

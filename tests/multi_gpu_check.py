@@ -20,6 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
+    os.environ.setdefault("SDP_P2P_TIMEOUT_S", "120")
     rank = int(os.environ["RANK"])
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
