@@ -353,6 +353,40 @@ class Engine(object):
             return pin.to(self.device, non_blocking=True)
         return t.to(self.device, non_blocking=False)
 
+    _TORCH_DTYPES = {"float64": "float64", "int32": "int32", "int64": "int64", "uint8": "uint8"}
+
+    def to_device_packed(self, arrays):
+        """Several host arrays -> ONE page-locked staging buffer -> one asynchronous
+        H2D copy; returns the device views (same shapes and dtypes).  Table builds
+        upload a dozen small arrays; one by one each is a synchronous pageable copy
+        (a stream synchronisation apiece), which dominates small or time-dependent
+        problems that rebuild their tables at every instant."""
+        torch = _torch()
+        arrs = []
+        for a in arrays:
+            a = np.ascontiguousarray(a)
+            if a.dtype.name not in self._TORCH_DTYPES:
+                a = a.view(np.uint8).reshape(-1)          # structured records travel as bytes
+            arrs.append(a)
+        if not self._cuda:
+            return [torch.from_numpy(a.copy()) for a in arrs]
+        offs, total = [], 0
+        for a in arrs:
+            total = (total + 15) // 16 * 16
+            offs.append(total)
+            total += a.nbytes
+        pin = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
+        pn = pin.numpy()
+        for a, o in zip(arrs, offs):
+            if a.nbytes:
+                pn[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+        buf = pin.to(self.device, non_blocking=True)
+        outs = []
+        for a, o in zip(arrs, offs):
+            t = buf[o:o + a.nbytes].view(getattr(torch, self._TORCH_DTYPES[a.dtype.name]))
+            outs.append(t.reshape(a.shape))
+        return outs
+
     def sync(self):
         if self._cuda:
             _torch().cuda.synchronize(self.device)
@@ -592,12 +626,15 @@ class Engine(object):
             # host copy of the probabilities, kept alive with the tables (SdpTables.p_host)
             T.p_host = np.ascontiguousarray(solver.perturb_proba[0], dtype=np.float64).copy() \
                 if nb_perturb == 1 else np.ones(1)
-            T.p = self.to_device(T.p_host)
-            T.U_dev = self.to_device(U.astype(np.int32)) if n else torch.zeros(1, dtype=torch.int32, device=dev)
+            # (one packed upload for the small per-table arrays)
+            small = [T.p_host, U.astype(np.int32) if n else np.zeros(1, dtype=np.int32)]
+            if nb_control:
+                small += [host_full.lo.reshape(-1), host_full.hi.reshape(-1),
+                          host_full.npts.astype(np.int32).reshape(-1)]
+            small = self.to_device_packed(small)
+            T.p, T.U_dev = small[0], small[1]
             # replicated control discretisation, for the argmin -> control value kernel
-            T.lo_dev = self.to_device(host_full.lo.reshape(-1)) if nb_control else None
-            T.hi_dev = self.to_device(host_full.hi.reshape(-1)) if nb_control else None
-            T.npts_dev = self.to_device(host_full.npts.astype(np.int32).reshape(-1)) if nb_control else None
+            T.lo_dev, T.hi_dev, T.npts_dev = (small[2], small[3], small[4]) if nb_control else (None, None, None)
             T.nb_control = nb_control
             T.tabulate_mode = None
 
@@ -648,9 +685,8 @@ class Engine(object):
                         np.cumsum(Upad, out=g_off[1:])
                     g_len = int(g_off[-1])
                 if tiled:
-                    tile_off_dev = self.to_device(tile_off)
-                    tile_g_off_dev = self.to_device(tile_g_off)
-                    tile_U_dev = self.to_device(tile_U.astype(np.int32))
+                    tile_off_dev, tile_g_off_dev, tile_U_dev = self.to_device_packed(
+                        [tile_off, tile_g_off, tile_U.astype(np.int32)])
                 L.update(g_off=g_off, tile_g_off=tile_g_off)
                 ensure("g", max(g_len, 4), torch.float64)
                 done = [0]      # states flushed so far (chunks arrive in order)
@@ -658,8 +694,7 @@ class Engine(object):
                 def flush(desc, staging):
                     if u_mask:
                         tb.check_factorable(desc, d, u_mask)
-                    desc_dev = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(dev)
-                    stag_dev = torch.from_numpy(staging).to(dev)
+                    desc_dev, stag_dev = self.to_device_packed([desc, staging])
                     ns = len(desc)
                     if tiled:
                         assert done[0] % 32 == 0
@@ -793,9 +828,8 @@ class Engine(object):
             T.item_begin_host = item_begin
             T.unit_U_host = np.asarray(unit_U, dtype=np.int64)
             T.chunk_plan = None
-            T.items = torch.from_numpy(items.view(np.uint8).reshape(-1)).to(dev) if n_items else \
-                torch.zeros(32, dtype=torch.uint8, device=dev)
-            T.item_begin = self.to_device(item_begin)
+            T.items, T.item_begin = self.to_device_packed(
+                [items if n_items else np.zeros(1, dtype=_cabi.ITEM_DTYPE), item_begin])
             n_part = max(n_items, 1) * (32 if tiled else 1)
             T.part_val = torch.empty(n_part, dtype=torch.float64, device=dev)
             T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)
