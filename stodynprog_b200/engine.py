@@ -314,9 +314,11 @@ class Engine(object):
             self._cuda = False
             self._peer = {}
             self._grid_cache = {}
+            self._scan_cache = None
             return
         self._peer = {}                          # n_grid -> PeerExchange | None
         self._grid_cache = {}
+        self._scan_cache = None
         self.lib = _cabi.load_library()          # raises if the extension is missing
         if not torch.cuda.is_available():
             raise _cabi.SdpLibraryError(
@@ -540,21 +542,31 @@ class Engine(object):
         eq = [n_grid * r // world for r in range(world + 1)]
         mode = getattr(solver, "tabulate", "auto")
         mine = None
-        part = None
-        if mode != "per_state":
-            # one vectorised control_box call, trusted only if sample states agree
-            # bit-for-bit with the reference's per-state calls
-            part = tb.scan_control_boxes_batched(sys, solver.control_steps, state_grid,
-                                                 eq[rank], eq[rank + 1], t_k)
-        if part is None:
-            mine = tb.state_tuples(state_grid, eq[rank], eq[rank + 1])
-            part = tb.scan_control_boxes(sys, solver.control_steps, mine, t_k)
-        parts = coll.all_gather_object((part.lo, part.hi, part.npts))
         nb_control = len(sys.control)
-        host_full = tb.HostStateTable(n_grid, nb_control)
-        host_full.lo = np.concatenate([p[0] for p in parts], axis=0)
-        host_full.hi = np.concatenate([p[1] for p in parts], axis=0)
-        host_full.npts = np.concatenate([p[2] for p in parts], axis=0)
+        # the scan is by far the longest host stage (one Python call per state): the last
+        # one is kept, so that a second layout of the same problem (dense after factored,
+        # a re-cut of the slabs) does not repeat it; DPSolver.clear_tables() drops it
+        scan_key = (t_k, id(sys.control_box), repr(sorted(sys.params.items())) if sys.params else "",
+                    tuple(float(c) for c in solver.control_steps),
+                    tuple(g.tobytes() for g in state_grid), world)
+        if self._scan_cache is not None and self._scan_cache[0] == scan_key:
+            host_full = self._scan_cache[1]
+        else:
+            part = None
+            if mode != "per_state":
+                # one vectorised control_box call, trusted only if sample states agree
+                # bit-for-bit with the reference's per-state calls
+                part = tb.scan_control_boxes_batched(sys, solver.control_steps, state_grid,
+                                                     eq[rank], eq[rank + 1], t_k)
+            if part is None:
+                mine = tb.state_tuples(state_grid, eq[rank], eq[rank + 1])
+                part = tb.scan_control_boxes(sys, solver.control_steps, mine, t_k)
+            parts = coll.all_gather_object((part.lo, part.hi, part.npts))
+            host_full = tb.HostStateTable(n_grid, nb_control)
+            host_full.lo = np.concatenate([p[0] for p in parts], axis=0)
+            host_full.hi = np.concatenate([p[1] for p in parts], axis=0)
+            host_full.npts = np.concatenate([p[2] for p in parts], axis=0)
+            self._scan_cache = (scan_key, host_full)
         U_all = host_full.U.astype(np.int64)
         if U_all.max(initial=0) >= 2 ** 31 - 4:
             raise ValueError("more than 2^31 control combinations for one state")
@@ -805,24 +817,31 @@ class Engine(object):
                 # shorter.  Layout A walks 128 controls per warp iteration, layout B one.
                 chunk = pick_item_chunk(unit_U, 128 if not tiled else 32)
             T.item_chunk = chunk
+            unit_U = np.asarray(unit_U, dtype=np.int64)
             n_it = (unit_U + chunk - 1) // chunk
+            # a unit's controls are cut into n_it runs of EQUAL length (a multiple of 4, at
+            # most `chunk`): 140 controls with chunk 128 become 72 + 68, not 128 + 12 - a
+            # short run costs a warp the same prologue (item, w-part, first row) as a long one
+            per_unit = (((unit_U + np.maximum(n_it, 1) - 1) // np.maximum(n_it, 1)) + 3) // 4 * 4
             item_begin = np.zeros(units + 1, dtype=np.int64)
             np.cumsum(n_it, out=item_begin[1:])
             n_items = int(item_begin[-1])
             st = np.repeat(np.arange(units, dtype=np.int64), n_it)
             kk = np.arange(n_items, dtype=np.int64) - item_begin[st]
+            per = per_unit[st]
             items = np.zeros(n_items, dtype=_cabi.ITEM_DTYPE)
-            items["u_begin"] = kk * chunk
-            items["u_count"] = np.minimum(chunk, unit_U[st] - kk * chunk)
+            items["u_begin"] = kk * per
+            items["u_count"] = np.minimum(per, unit_U[st] - kk * per)
             items["state"] = st
+            assert n_items == 0 or int(items["u_count"].min()) >= 1
             if tiled:
-                items["entry_base"] = tile_off[st] + kk * chunk * Wf * 32
+                items["entry_base"] = tile_off[st] + kk * per * Wf * 32
                 items["g_base"] = items["entry_base"] if (T.g_per_w or u_mask) else \
-                    tile_g_off[st] + kk * chunk * 32
+                    tile_g_off[st] + kk * per * 32
                 items["Upad"] = 0
             else:
-                items["entry_base"] = entry_off[st] + kk * chunk
-                items["g_base"] = g_off[st] + kk * chunk
+                items["entry_base"] = entry_off[st] + kk * per
+                items["g_base"] = g_off[st] + kk * per
                 items["Upad"] = Upad[st]
             T.n_items = n_items
             T.item_begin_host = item_begin
@@ -864,6 +883,12 @@ class Engine(object):
 
         # slabs balanced by admissible controls ...
         bounds = partition_by_weight(U_all + 1, world) if world > 1 else [0, n_grid]
+        override = getattr(solver, "_slab_override", None)
+        if override is not None and world == 1:
+            # developer experiments (scripts/dev_slab_chunks.py): the tables of ONE slab of
+            # the grid, as a rank of a multi-GPU run would hold them; only the streaming
+            # kernel can be run on such tables (J_out covers the slab, not the grid)
+            bounds = [int(override[0]), int(override[1])]
         T = build_for(bounds, reuse)
         # ... then, with several ranks, by the measured cost of a backup in each slab
         balance = getattr(solver, "slab_balance", "auto")

@@ -162,6 +162,9 @@ class DPSolver(object):
         user callables read from their enclosing scope)"""
         self._table_cache = {}
         self.last_tables = None
+        if self._engine is not None:
+            self._engine._scan_cache = None
+            self._engine._grid_cache = {}
 
     def sweep_tables(self, t_k=None, reuse=None):
         """device tables for the current (sys, grids, control_steps[, t_k])"""
