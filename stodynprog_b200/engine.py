@@ -48,11 +48,6 @@ def partition_by_weight(weights, world):
     return bounds
 
 
-# work items wanted per sweep launch.  Measured on a B200 (profiles/r1_slab_scaling.txt):
-# the streaming kernels keep their rate down to ~26 warps per SM (3 907 items of 512
-# controls: 565 G backups/s vs 626 G with 31 250) and LOSE ~10 % when the runs are cut
-# to 128 controls, so runs are only shortened when a launch would not even fill the
-# machine once (148 SMs x 16 warps).
 def rebalance_bounds(U_all, bounds, times, tolerance=1.03):
     """Re-cut contiguous slabs from measured slab times: the weight U(x)+1 of every
     state is scaled by its slab's time per unit weight (a piecewise-constant cost
@@ -74,7 +69,14 @@ def rebalance_bounds(U_all, bounds, times, tolerance=1.03):
     return None if new == old else new
 
 
-ITEMS_TARGET = 148 * 16
+# Work items (warps) wanted per sweep launch.  A B200 keeps 148 SMs x 12..24 warps of these
+# kernels resident, so a slab of a multi-GPU run (config #5 cut in 8: ~4 000 tiles of ~200
+# controls) is only 2-3 waves of equally long items and its time is quantised by whole waves:
+# measured per slab (profiles/r1_slab_chunks.txt) 0.373..0.449 ms with one item per tile,
+# 0.384..0.390 ms with runs of <= 64 controls (about 9 waves) - 13 % on the slowest slab,
+# which is the one the whole sweep waits for.  Runs are cut evenly (see the item table), so
+# shorter runs cost nothing measurable on a grid that is already long (2.843 vs 2.853 ms).
+ITEMS_TARGET = 148 * 96
 
 
 def pick_item_chunk(unit_U, min_chunk, max_chunk=512, target=ITEMS_TARGET):

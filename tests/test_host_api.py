@@ -234,11 +234,10 @@ def test_pick_item_chunk():
     from stodynprog_b200.engine import pick_item_chunk, ITEMS_TARGET
     # plenty of units: keep the long runs
     assert pick_item_chunk(np.full(40000, 256), 32) == 512
-    # one eighth of the large grid (a rank of an 8-GPU run) still fills the machine
-    assert pick_item_chunk(np.full(3907, 256), 32) == 512
-    # a small slab: runs are cut until there are enough warps
-    c = pick_item_chunk(np.full(600, 256), 32)
-    assert 32 <= c < 256 and ((256 + c - 1) // c) * 600 >= ITEMS_TARGET
+    # one eighth of the large grid (a rank of an 8-GPU run): runs are cut until the launch
+    # is several waves of warps long
+    c = pick_item_chunk(np.full(3907, 256), 32)
+    assert c == 64 and ((256 + c - 1) // c) * 3907 >= ITEMS_TARGET
     # tiny problems stop at the floor
     assert pick_item_chunk(np.full(10, 100), 128) == 128
 
