@@ -880,8 +880,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+#ifndef SDP_TMA_THREADS
+#define SDP_TMA_THREADS 256   // __launch_bounds__ of the TMA kernel (it is launched with NW*32 <= 256 threads)
+#endif
+#ifndef SDP_TMA_MINB
+#define SDP_TMA_MINB 1
+#endif
 template <int D, int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SDP_TMA_THREADS, SDP_TMA_MINB)
 k_sweep_tiled_tma(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
                   double* __restrict__ part_val, int32_t* __restrict__ part_idx, int S) {
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -185,6 +185,8 @@ class PeerExchange(object):
         self.hdl = symm.rendezvous(self.buf, group)
         torch.cuda.synchronize(engine.device)
         self.hdl.barrier()                      # zeros visible everywhere before first use
+        self.n_pad = n_pad
+        self._views = {}
         self.J = [self.buf[:n_grid], self.buf[n_pad:n_pad + n_grid]]
         self.local = torch.zeros(4, dtype=torch.int64, device=engine.device)   # [epoch, done]
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
@@ -198,6 +200,14 @@ class PeerExchange(object):
             P.epoch = self.local.data_ptr()
             P.done = self.local.data_ptr() + 8
             self.peers.append(P)
+
+    def peer_view(self, r, k):
+        """rank r's copy of J buffer k as a tensor on this device (peer-mapped)"""
+        import torch
+        key = (r, k)
+        if key not in self._views:
+            self._views[key] = self.hdl.get_buffer(r, (self.n_grid,), torch.float64, k * self.n_pad)
+        return self._views[key]
 
     def index_of(self, t):
         """0/1 when `t` is one of the two J buffers, else None"""
@@ -433,6 +443,23 @@ class Engine(object):
         px = self._peer.get(n_grid)
         if px is not None:
             px.barrier()
+
+    def share_J(self, J, root=0):
+        """make rank `root`'s device copy of J (one of the J_pair buffers) the copy of every
+        rank: peer-memory stores over NVLink + flag barrier, or an NCCL broadcast.
+        Collective: every rank calls it."""
+        if self.coll.world == 1:
+            return
+        px = self._peer.get(J.numel())
+        k = px.index_of(J) if px is not None else None
+        if k is None:
+            self.coll.dist.broadcast(J, src=root, group=self.coll.group)
+            return
+        if self.coll.rank == root:
+            for r in range(self.coll.world):
+                if r != root:
+                    px.peer_view(r, k).copy_(J, non_blocking=True)
+        px.barrier()
 
     def upload_J(self, J_host, dst):
         """host fp64 array -> device buffer `dst`, asynchronously on the current stream.

@@ -63,6 +63,12 @@ class DPSolver(object):
         # re-cut once by the measured sweep time of every slab ("measured"; "auto" does so
         # for sweeps of at least 5e8 backups)
         self.slab_balance = "auto"    # "auto" | "controls" | "measured"
+        # several ranks: "all" = every rank passes J_next and gets (J_k, pol_k), as an
+        # unchanged SPMD script expects; "root" = only rank 0's J_next is read (it is
+        # handed to the other ranks over NVLink) and only rank 0 gets host results, the
+        # others get None - 8 ranks pulling 24 MB each through a shared PCIe root take
+        # 2 ms, one rank 0.45 ms.  value_iteration / solve_value_iteration only.
+        self.host_results = "all"     # "all" | "root"
 
     # ------------------------------------------------------------------
     # discretisation (host only)
@@ -182,6 +188,11 @@ class DPSolver(object):
         self.last_tables = T
         return T
 
+    def _root_only(self):
+        if getattr(self, "host_results", "all") not in ("all", "root"):
+            raise ValueError("host_results must be 'all' or 'root'")
+        return self.host_results == "root" and self.engine.coll.world > 1
+
     def _sweep_host(self, J_next, t_k=None, rel_dp=False, tables=None):
         """one sweep with host arrays in/out. Returns (J_k, J_ref or None, pol_k, tables)"""
         import torch
@@ -192,7 +203,14 @@ class DPSolver(object):
         n_grid = int(np.prod(state_dims))
         J_prev, J_new = eng.J_pair(n_grid)
         eng.begin_call(n_grid)
-        eng.upload_J(J_next, J_prev)
+        root_only = self._root_only()
+        is_root = eng.coll.rank == 0
+        if root_only:
+            if is_root:
+                eng.upload_J(J_next, J_prev)
+            eng.share_J(J_prev)
+        else:
+            eng.upload_J(J_next, J_prev)
         if not rel_dp and eng.can_overlap_results(T):
             # large single-rank sweep: results stream to the host while later runs compute
             J_k, pol_k = eng.sweep_to_host(T, J_prev, J_new)
@@ -203,7 +221,10 @@ class DPSolver(object):
             ref_flat = int(np.ravel_multi_index(self._state_ref_ind, state_dims))
             ref_out = torch.zeros(1, dtype=torch.float64, device=eng.device)
         eng.sweep(T, J_prev, J_new, rel_ref_index=ref_flat, ref_out=ref_out)
-        pol_dev = eng.policy_values(T, eng.gather_argmin(T))      # K3: indices -> control values
+        argmin_full = eng.gather_argmin(T)
+        if root_only and not is_root:
+            return None, None, None, T           # results travel to rank 0's host only
+        pol_dev = eng.policy_values(T, argmin_full)               # K3: indices -> control values
         outs = eng.to_host(J_new, pol_dev, *([ref_out] if rel_dp else []))
         J_k = outs[0].reshape(state_dims)
         pol_k = outs[1].reshape(state_dims + (nb_control,))
@@ -224,16 +245,19 @@ class DPSolver(object):
         """
         t_start = datetime.now()
         ref_ind = getattr(self, '_state_ref_ind', None)
+        # host_results == "root": the other ranks' J_next is not read (it may be None)
+        ignored = self._root_only() and self.engine.coll.rank != 0
         if rel_dp:
-            J_next, J_ref = J_next
+            J_next, J_ref = J_next if J_next is not None else (None, None)
             # the cost-to-go must be a *differential* cost, zero at the reference state
-            assert J_next[ref_ind] == 0.
+            assert ignored or J_next[ref_ind] == 0.
         state_dims = tuple(len(g) for g in self.state_grid)
-        J_next = np.asarray(J_next)
-        if J_next.shape != state_dims:
-            # same check and message as interp_on_state (:413-415)
-            raise ValueError('array `A` should be of shape {:s}, not {:s}'.format(
-                str(state_dims), str(J_next.shape)))
+        if not ignored:
+            J_next = np.asarray(J_next)
+            if J_next.shape != state_dims:
+                # same check and message as interp_on_state (:413-415)
+                raise ValueError('array `A` should be of shape {:s}, not {:s}'.format(
+                    str(state_dims), str(J_next.shape)))
         if report_time:
             print('value iteration...', end='')
         t_k = None
@@ -265,6 +289,17 @@ class DPSolver(object):
         if J_fin.shape != state_dims:
             raise ValueError('array `A` should be of shape {:s}, not {:s}'.format(
                 str(state_dims), str(J_fin.shape)))
+        saved_mode, self.host_results = self.host_results, "all"   # J[k+1] feeds instant k on every rank
+        try:
+            self._recursion(t_ini, t_fin, J_fin, J, pol)
+        finally:
+            self.host_results = saved_mode
+        exec_time = (datetime.now() - t_start).total_seconds()
+        if report_time:
+            print('\rvalue iteration run in {:.2f} s'.format(exec_time))
+        return J, pol
+
+    def _recursion(self, t_ini, t_fin, J_fin, J, pol):
         tables = None
         for t_k in range(t_ini, t_fin)[::-1]:
             print('\rtk = {:3d}...'.format(t_k), end='')
@@ -274,10 +309,6 @@ class DPSolver(object):
             tables = self.engine.build_sweep_tables(self, t_k, reuse=tables)
             self.last_tables = tables
             J[k], _, pol[k], _ = self._sweep_host(J_next, t_k, False, tables=tables)
-        exec_time = (datetime.now() - t_start).total_seconds()
-        if report_time:
-            print('\rvalue iteration run in {:.2f} s'.format(exec_time))
-        return J, pol
 
     def eval_policy(self, pol, n_iter, rel_dp=False, J_zero=None,
                     report_time=True, J_ref_full=False):
@@ -331,6 +362,13 @@ class DPSolver(object):
         Returns (J_pol, pol); J_pol is a tuple (J_diff, J_ref) if `rel_dp`.
         (reference stodynprog.py:777-812)
         """
+        saved_mode, self.host_results = self.host_results, "all"   # every rank needs pol to evaluate it
+        try:
+            return self._policy_iteration(pol_init, n_val, n_pol, rel_dp)
+        finally:
+            self.host_results = saved_mode
+
+    def _policy_iteration(self, pol_init, n_val, n_pol, rel_dp):
         pol = pol_init
         J_pol = self.eval_policy(pol, n_val, rel_dp)
         if rel_dp:
@@ -363,7 +401,14 @@ class DPSolver(object):
         n_grid = int(np.prod(state_dims))
         J_prev, J_new = eng.J_pair(n_grid)
         eng.begin_call(n_grid)
-        eng.upload_J(J0, J_prev)
+        root_only = self._root_only()
+        is_root = eng.coll.rank == 0
+        if root_only:
+            if is_root:
+                eng.upload_J(J0, J_prev)
+            eng.share_J(J_prev)
+        else:
+            eng.upload_J(J0, J_prev)
         resid = torch.zeros(1, dtype=torch.float64, device=eng.device)
         ref_out = torch.zeros(1, dtype=torch.float64, device=eng.device) if rel_dp else None
         ref_flat = int(np.ravel_multi_index(self._state_ref_ind, state_dims)) if rel_dp else None
@@ -379,12 +424,15 @@ class DPSolver(object):
                 history.append(r)
                 if r <= tol:
                     break
-        pol_dev = eng.policy_values(T, eng.gather_argmin(T))
+        argmin_full = eng.gather_argmin(T)
+        info = {'n_sweeps': n_done, 'residuals': history,
+                'J_ref': float(ref_out.cpu().numpy()[0]) if rel_dp else None}
+        if root_only and not is_root:
+            return None, None, info
+        pol_dev = eng.policy_values(T, argmin_full)
         J, pol = eng.to_host(J_prev, pol_dev)
         J = J.reshape(state_dims)
         pol = pol.reshape(state_dims + (nb_control,))
-        info = {'n_sweeps': n_done, 'residuals': history,
-                'J_ref': float(ref_out.cpu().numpy()[0]) if rel_dp else None}
         return J, pol, info
 
     # ------------------------------------------------------------------

@@ -67,6 +67,23 @@ def main():
         if rank == 0:
             print("[%s] policy_iteration: policy mismatches %d, J err %.2e, J_ref %.10g (err %.2e)"
                   % (layout, bad, errJ, Jr, errR))
+        # results on rank 0 only: the other ranks pass / receive None
+        sv.host_results = "root"
+        Jr = prob.J0 if rank == 0 else None
+        for k in range(3):
+            Jr, polr = sv.value_iteration(Jr, report_time=False)
+            if rank == 0:
+                ok &= int(np.any(polr != G["vi_pol%d" % k], axis=-1).sum()) == 0
+                ok &= rel_err(Jr, G["vi_J%d" % k]) <= 1e-10
+            else:
+                ok &= Jr is None and polr is None
+        Jsr, polsr, infor = sv.solve_value_iteration(J_zero=prob.J0 if rank == 0 else None, max_iter=3, tol=0.0)
+        if rank == 0:
+            ok &= rel_err(Jsr, G["vi_J2"]) <= 1e-10
+            print("[%s] host_results='root': parity on rank 0, None elsewhere" % layout)
+        else:
+            ok &= Jsr is None
+        sv.host_results = "all"
         Js, pols, info = sv.solve_value_iteration(max_iter=3, tol=0.0)
         r_expected = np.max(np.abs(G["vi_J2"] - G["vi_J1"]))
         ok &= rel_err(Js, G["vi_J2"]) <= 1e-10 and abs(info["residuals"][-1] - r_expected) <= 1e-9 * r_expected

@@ -42,6 +42,20 @@ def _worker(rank, world, port, out_dir, layout):
         (Jd, Jr), pol2 = sv.value_iteration((J1 - J1[sv._state_ref_ind], 0.), rel_dp=True, report_time=False)
         Je, ref = sv.eval_policy(pol1, 6, rel_dp=True, report_time=False)
         Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=3, tol=0.0)
+        # host_results = "root": only rank 0's input is read, only rank 0 gets arrays
+        sv.host_results = "root"
+        Jq, polq = sv.value_iteration(J0 if rank == 0 else None, report_time=False)
+        (Jqd, Jqr), polq2 = sv.value_iteration((J1 - J1[sv._state_ref_ind], 0.) if rank == 0 else None,
+                                                rel_dp=True, report_time=False)
+        Jqs, polqs, _ = sv.solve_value_iteration(J_zero=J0 if rank == 0 else None, max_iter=3, tol=0.0)
+        if rank == 0:
+            root_ok = (np.array_equal(Jq, J1) and np.array_equal(polq, pol1) and np.array_equal(Jqd, Jd)
+                       and Jqr == Jr and np.array_equal(polq2, pol2) and np.array_equal(Jqs, Js)
+                       and np.array_equal(polqs, pols))
+        else:
+            root_ok = all(x is None for x in (Jq, polq, Jqd, Jqr, polq2, Jqs, polqs))
+        sv.host_results = "all"
+        assert root_ok, "host_results='root' mismatch on rank %d" % rank
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), J1=J1, pol1=pol1, Jd=Jd, Jr=Jr, pol2=pol2,
                  Je=Je, ref=ref, Js=Js, pols=pols, resid=np.array(info["residuals"]),
                  bounds=np.array(T.bounds), n_local=T.n_states, backups=T.n_backups_local,
