@@ -295,19 +295,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from the warm-up to the end of the e2e loop
+    # (the device-timed region alone is only K x 3 ms: too short for nvidia-smi's 100 ms period)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
     for _ in range(args.warmup):
         eng.sweep(T, J_prev, J_new)
         J_prev, J_new = J_new, J_prev
 
     K = args.steps
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     launches0 = _cabi.launch_count()
     ms_total, k1_ms, J_prev, J_new = time_sweeps(eng, T, J_prev, J_new, K, barrier)
     launches = _cabi.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total, float(np.mean(k1_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -363,6 +364,7 @@ def run_ours(args):
                          "over NVLink) and rank 0 alone downloads (J, pol)")}
 
     e2e = time_e2e("all")
+    clocks = sampler.stop() if rank == 0 else None
     e2e_all = None
     if world > 1:
         # 8 ranks pulling 24 MB each through shared PCIe roots take ~2 ms, one rank 0.45 ms
