@@ -69,6 +69,64 @@ def rebalance_bounds(U_all, bounds, times, tolerance=1.03):
     return None if new == old else new
 
 
+def make_items(unit_U, chunk, unit_off, per_entry, g_unit_off, g_per_entry, Upad):
+    """Work-item table (SdpItem records) + first item of every unit.
+
+    A unit (a state in layout A, a tile of 32 states in layout B) with unit_U controls is
+    cut into ceil(unit_U / chunk) runs of EQUAL length (a multiple of 4, at most `chunk`):
+    140 controls with chunk 128 become 72 + 68, not 128 + 12 - a short run costs a warp
+    the same prologue (item, w-part, first row) as a long one.  Control u of a unit sits
+    `u * per_entry` table entries after `unit_off[unit]` (g: `u * g_per_entry` after
+    `g_unit_off[unit]`); `Upad` is layout A's row pitch per unit (None for layout B)."""
+    unit_U = np.asarray(unit_U, dtype=np.int64)
+    units = len(unit_U)
+    n_it = (unit_U + chunk - 1) // chunk
+    per_unit = (((unit_U + np.maximum(n_it, 1) - 1) // np.maximum(n_it, 1)) + 3) // 4 * 4
+    item_begin = np.zeros(units + 1, dtype=np.int64)
+    np.cumsum(n_it, out=item_begin[1:])
+    n_items = int(item_begin[-1])
+    st = np.repeat(np.arange(units, dtype=np.int64), n_it)
+    kk = np.arange(n_items, dtype=np.int64) - item_begin[st]
+    per = per_unit[st]
+    items = np.zeros(n_items, dtype=_cabi.ITEM_DTYPE)
+    items["u_begin"] = kk * per
+    items["u_count"] = np.minimum(per, unit_U[st] - kk * per)
+    items["state"] = st
+    assert n_items == 0 or int(items["u_count"].min()) >= 1
+    items["entry_base"] = np.asarray(unit_off)[st] + kk * per * per_entry
+    items["g_base"] = np.asarray(g_unit_off)[st] + kk * per * g_per_entry
+    items["Upad"] = 0 if Upad is None else np.asarray(Upad)[st]
+    return items, item_begin
+
+
+def fill_c_tables(T):
+    """the SdpTables record (include/sdp_b200.h) of a SweepTables"""
+    c = _cabi.SdpTables()
+    c.cell = T.cell.data_ptr()
+    c.lam = T.lam.data_ptr()
+    c.lam_plane = T.lam_plane
+    c.g = T.g.data_ptr()
+    c.g_per_w = T.g_per_w
+    c.W = T.W
+    c.expect = T.expect
+    if T.u_mask:
+        c.layout = _cabi.LAYOUT_STATE_MINOR_FACTORED if T.tiled else _cabi.LAYOUT_CONTROL_MINOR_FACTORED
+        c.u_mask = T.u_mask
+        c.cell_w = T.cell_w.data_ptr()
+        c.lam_w = T.lam_w.data_ptr()
+        c.lam_w_plane = T.lam_w_plane
+    else:
+        c.layout = _cabi.LAYOUT_STATE_MINOR if T.tiled else _cabi.LAYOUT_CONTROL_MINOR
+    c.p = T.p.data_ptr()
+    c.p_host = T.p_host.ctypes.data
+    c.items = T.items.data_ptr()
+    c.n_items = T.n_items
+    c.item_begin = T.item_begin.data_ptr()
+    c.n_states = T.n_states
+    c.U = T.U_dev.data_ptr()
+    return c
+
+
 # Work items (warps) wanted per sweep launch.  A B200 keeps 148 SMs x 12..24 warps of these
 # kernels resident, so a slab of a multi-GPU run (config #5 cut in 8: ~4 000 tiles of ~200
 # controls) is only 2-3 waves of equally long items and its time is quantised by whole waves:
@@ -835,43 +893,20 @@ class Engine(object):
             Wf = 1 if u_mask else W     # table entries per control
 
             # work items: one warp per run of at most `item_chunk` controls
+            unit_U = tile_U if tiled else U
             chunk = self.item_chunk
-            if tiled:
-                units, unit_U = n_tiles, tile_U
-            else:
-                units, unit_U = n, U
             if self.item_chunk_auto:
-                # a B200 holds 148 SMs x 16..64 resident warps; with fewer items than a few
-                # waves the sweep is latency-bound (and its tail is long), so cut the runs
-                # shorter.  Layout A walks 128 controls per warp iteration, layout B one.
+                # layout A walks 128 controls per warp iteration, layout B one
                 chunk = pick_item_chunk(unit_U, 128 if not tiled else 32)
             T.item_chunk = chunk
-            unit_U = np.asarray(unit_U, dtype=np.int64)
-            n_it = (unit_U + chunk - 1) // chunk
-            # a unit's controls are cut into n_it runs of EQUAL length (a multiple of 4, at
-            # most `chunk`): 140 controls with chunk 128 become 72 + 68, not 128 + 12 - a
-            # short run costs a warp the same prologue (item, w-part, first row) as a long one
-            per_unit = (((unit_U + np.maximum(n_it, 1) - 1) // np.maximum(n_it, 1)) + 3) // 4 * 4
-            item_begin = np.zeros(units + 1, dtype=np.int64)
-            np.cumsum(n_it, out=item_begin[1:])
-            n_items = int(item_begin[-1])
-            st = np.repeat(np.arange(units, dtype=np.int64), n_it)
-            kk = np.arange(n_items, dtype=np.int64) - item_begin[st]
-            per = per_unit[st]
-            items = np.zeros(n_items, dtype=_cabi.ITEM_DTYPE)
-            items["u_begin"] = kk * per
-            items["u_count"] = np.minimum(per, unit_U[st] - kk * per)
-            items["state"] = st
-            assert n_items == 0 or int(items["u_count"].min()) >= 1
             if tiled:
-                items["entry_base"] = tile_off[st] + kk * per * Wf * 32
-                items["g_base"] = items["entry_base"] if (T.g_per_w or u_mask) else \
-                    tile_g_off[st] + kk * per * 32
-                items["Upad"] = 0
+                per_entry = Wf * 32
+                g_unit_off = tile_off if (T.g_per_w or u_mask) else tile_g_off
+                items, item_begin = make_items(unit_U, chunk, tile_off, per_entry, g_unit_off,
+                                               per_entry if (T.g_per_w or u_mask) else 32, None)
             else:
-                items["entry_base"] = entry_off[st] + kk * per
-                items["g_base"] = g_off[st] + kk * per
-                items["Upad"] = Upad[st]
+                items, item_begin = make_items(unit_U, chunk, entry_off, 1, g_off, 1, Upad)
+            n_items = len(items)
             T.n_items = n_items
             T.item_begin_host = item_begin
             T.unit_U_host = np.asarray(unit_U, dtype=np.int64)
@@ -883,31 +918,7 @@ class Engine(object):
             T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)
             T.J_out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
             T.argmin = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-
-            c = _cabi.SdpTables()
-            c.cell = T.cell.data_ptr()
-            c.lam = T.lam.data_ptr()
-            c.lam_plane = lam_plane
-            c.g = T.g.data_ptr()
-            c.g_per_w = T.g_per_w
-            c.W = W
-            c.expect = T.expect
-            if u_mask:
-                c.layout = _cabi.LAYOUT_STATE_MINOR_FACTORED if tiled else _cabi.LAYOUT_CONTROL_MINOR_FACTORED
-                c.u_mask = u_mask
-                c.cell_w = T.cell_w.data_ptr()
-                c.lam_w = T.lam_w.data_ptr()
-                c.lam_w_plane = T.lam_w_plane
-            else:
-                c.layout = _cabi.LAYOUT_STATE_MINOR if tiled else _cabi.LAYOUT_CONTROL_MINOR
-            c.p = T.p.data_ptr()
-            c.p_host = T.p_host.ctypes.data
-            c.items = T.items.data_ptr()
-            c.n_items = n_items
-            c.item_begin = T.item_begin.data_ptr()
-            c.n_states = n
-            c.U = T.U_dev.data_ptr()
-            T.c_tables = c
+            T.c_tables = fill_c_tables(T)
             return T
 
         # slabs balanced by admissible controls ...
@@ -1059,8 +1070,8 @@ class Engine(object):
             self._copy = torch.cuda.Stream(dev)
         main = torch.cuda.current_stream(dev)
         pol = torch.empty((n, nc), dtype=torch.float64, device=dev)
-        J_pin = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        pol_pin = torch.empty((n, nc), dtype=torch.float64, pin_memory=True)
+        J_pin = self.host_result_buffer((n,), torch.float64)
+        pol_pin = self.host_result_buffer((n, nc), torch.float64)
         ev0 = torch.cuda.Event()
         ev0.record(main)
         for k, ch in enumerate(self._chunk_plan(T)):
@@ -1095,7 +1106,7 @@ class Engine(object):
         done.record(self._copy)
         main.wait_event(done)
         done.synchronize()
-        return J_pin.numpy(), pol_pin.numpy()
+        return self.result_array(J_pin), self.result_array(pol_pin)
 
     def gather_argmin(self, T):
         """full-grid int32 argmin (device), gathered over ranks"""
@@ -1114,16 +1125,46 @@ class Engine(object):
             _cabi.check(rc, "sdp_policy_values")
         return pol
 
+    # Result arrays are handed to the caller as numpy views of page-locked buffers (no
+    # extra host copy, and the next call can DMA them back without staging).  Page-locked
+    # memory is a limited resource and a caller may keep every J_k of a long iteration:
+    # above this budget of LIVE result bytes new results go to ordinary pageable memory.
+    PINNED_RESULT_BUDGET = int(os.environ.get("SDP_PINNED_RESULT_BUDGET", str(4 << 30)))
+    _pinned_live = [0]
+
+    def host_result_buffer(self, shape, dtype):
+        """uninitialised host tensor for a result: page-locked while the budget lasts"""
+        torch = _torch()
+        nbytes = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+        if not self._cuda or Engine._pinned_live[0] + nbytes > self.PINNED_RESULT_BUDGET:
+            return torch.empty(shape, dtype=dtype)
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+    def result_array(self, t):
+        """numpy view of a host result tensor; a page-locked one is counted against the
+        budget until the caller drops the array (views made from it keep it alive)"""
+        import weakref
+        a = t.numpy()
+        if self._cuda and t.is_pinned():
+            nbytes = a.nbytes
+            live = Engine._pinned_live
+            live[0] += nbytes
+
+            def release(n=nbytes, live=live):
+                live[0] -= n
+            weakref.finalize(a, release)
+        return a
+
     def to_host(self, *tensors):
         """device tensors -> fresh numpy arrays (through pinned buffers, one sync)"""
         torch = _torch()
         if not self._cuda:
             return [t.numpy().copy() for t in tensors]
-        outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        outs = [self.host_result_buffer(tuple(t.shape), t.dtype) for t in tensors]
         for o, t in zip(outs, tensors):
             o.copy_(t, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return [o.numpy() for o in outs]
+        return [self.result_array(o) for o in outs]
 
     # -- policy tables ----------------------------------------------------
     def build_policy_tables(self, solver, pol):

@@ -230,6 +230,31 @@ def test_rebalance_bounds():
     assert max(est) < 1.06          # was 1.2 before the re-cut
 
 
+def test_make_items_cuts_units_into_equal_runs():
+    from stodynprog_b200.engine import make_items
+    U = np.array([140, 1, 512, 513, 129, 4, 0, 256])
+    off = np.arange(len(U)) * 100000
+    for chunk in (4, 32, 128, 512):
+        items, begin = make_items(U, chunk, off, 9 * 32, off // 2, 32, None)
+        assert begin[0] == 0 and begin[-1] == len(items)
+        for k, u in enumerate(U):
+            it = items[begin[k]:begin[k + 1]]
+            assert len(it) == -(-u // chunk)
+            if u == 0:
+                continue
+            # the runs tile [0, u) in order, none is empty, none exceeds the chunk
+            assert it["u_begin"][0] == 0 and np.all(it["u_begin"][1:] == np.cumsum(it["u_count"])[:-1])
+            assert it["u_count"].sum() == u and it["u_count"].min() >= 1 and it["u_count"].max() <= chunk
+            assert np.all(it["u_begin"] % 4 == 0)
+            # equal lengths up to the rounding to a multiple of 4
+            assert it["u_count"].max() - it["u_count"].min() <= 4 * len(it) + 3
+            assert np.all(it["state"] == k)
+            assert np.all(it["entry_base"] == off[k] + it["u_begin"].astype(np.int64) * 9 * 32)
+            assert np.all(it["g_base"] == off[k] // 2 + it["u_begin"].astype(np.int64) * 32)
+    items, _ = make_items(np.array([140]), 128, [0], 1, [0], 1, np.array([140]))
+    assert list(items["u_count"]) == [72, 68] and list(items["Upad"]) == [140, 140]
+
+
 def test_pick_item_chunk():
     from stodynprog_b200.engine import pick_item_chunk, ITEMS_TARGET
     # plenty of units: keep the long runs

@@ -886,5 +886,18 @@ def test_overlapped_result_copy_is_bit_identical(product, layout, compress):
             Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = 1 << 62, 1 << 62
             J_d, pol_d = sv.value_iteration(np.array(J_b), report_time=False)
             assert np.array_equal(J_c, J_d) and np.array_equal(pol_c, pol_d)
+            # page-locked result budget exhausted: results land in pageable memory, same values
+            import torch
+            assert torch.from_numpy(J_d).is_pinned()
+            budget = Engine.PINNED_RESULT_BUDGET
+            try:
+                Engine.PINNED_RESULT_BUDGET = 0
+                for lim in (0, 1 << 62):
+                    Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = lim, lim
+                    J_e, pol_e = sv.value_iteration(np.array(J_b), report_time=False)
+                    assert not torch.from_numpy(J_e).is_pinned()
+                    assert np.array_equal(J_e, J_d) and np.array_equal(pol_e, pol_d)
+            finally:
+                Engine.PINNED_RESULT_BUDGET = budget
         finally:
             Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = saved
