@@ -192,7 +192,10 @@ def kernel_name(T):
     if T.factored:
         if T.tiled:
             return "k_sweep_fact_tiled<%d,%d,%d>" % (d, T.u_mask, 3 if T.W <= 3 else (5 if T.W <= 5 else 9))
-        return "k_sweep_fact_hoist<%d,2>" % d if T.u_mask == 1 else "k_sweep_fact<%d,%d,4>" % (d, T.u_mask)
+        if T.u_mask == 1:
+            wm = 3 if T.W <= 3 else (5 if T.W <= 5 else 9)
+            return "k_sweep_fact_hoist_c<%d,%d>" % (d, wm) if T.W <= 9 else "k_sweep_fact_hoist<%d,2>" % d
+        return "k_sweep_fact<%d,%d,4>" % (d, T.u_mask)
     return "k_sweep_tiled_tma<%d,8>" % d if T.tiled else "k_sweep<%d,4>" % d
 
 

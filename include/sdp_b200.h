@@ -170,6 +170,7 @@ int64_t sdp_launch_count(void);
  * LDG, 1 TMA-fed ring, 2 software-pipelined LDG = default), "rb" (2|4|8),
  * "tma_rows" (4|8), "tma_stages" (2..16), "tma_warps" (1..16), "hoist" (layout AF
  * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4),
+ * "hoist_const" (0|1: constant-W variant of that kernel for W <= 9),
  * "p2p_timeout_s" (bound of the peer-flag waits, default 600 s, then the kernel traps).
  * Not thread-safe against concurrent launches. */
 int sdp_set_option(const char* name, int value);

@@ -1029,6 +1029,7 @@ struct Tuning {
     int hoist;    // layout AF, u_mask == 1: tabulate the inner interpolation per item (1) or not (0)
     int hoist_upl; // controls per lane per iteration of the hoisted kernel (2|4)
     int p2p_timeout_s; // bound of the peer-flag waits (seconds) before the kernel traps
+    int hoist_const;   // layout AF hoisted kernel: constant-W variant for W <= 9 (1) or the runtime-W kernel (0)
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static int env_int(const char* name, int dflt) {
@@ -1058,6 +1059,7 @@ static Tuning& tuning() {
         x.hoist = env_int("SDP_HOIST", 1) != 0;
         x.hoist_upl = env_int("SDP_HOIST_UPL", 2) == 4 ? 4 : 2;
         x.p2p_timeout_s = clampi(env_int("SDP_P2P_TIMEOUT_S", 600), 1, 86400);
+        x.hoist_const = env_int("SDP_HOIST_CONST", 1) != 0;
         return x;
     }();
     return t;
@@ -1075,6 +1077,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "hoist")) t.hoist = value != 0;
     else if (!strcmp(name, "hoist_upl")) t.hoist_upl = (value == 4) ? 4 : 2;
     else if (!strcmp(name, "p2p_timeout_s")) t.p2p_timeout_s = clampi(value, 1, 86400);
+    else if (!strcmp(name, "hoist_const")) t.hoist_const = value != 0;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1164,6 +1167,12 @@ struct Fact {
             else lam[k] = lw[jw++];
         }
     }
+};
+
+// probabilities as launch constants (kernel parameter = constant bank, operands of the
+// DMULs themselves; see k_sweep_fact_tiled and k_sweep_fact_hoist_c)
+struct PVals {
+    double v[SDP_FACTORED_MAX_W_REG];
 };
 
 // AF: one warp per run of controls of one state, lane <-> UPL consecutive
@@ -1412,6 +1421,170 @@ k_sweep_fact_hoist(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
     }
 }
 
+// The same hoisted sweep for W <= 9 perturbation nodes (WM = 3 | 5 | 9 unrolled slots).
+// ncu on the kernel above: 22 issued instructions per backup for 7 fp64 operations - the
+// runtime-W loop recomputes two shared-memory addresses per (control, w), reads p[w]
+// from shared memory and carries remainder loops.  Here the table is row-major
+// R[row][w] (the W values a control needs from a row are contiguous: one base address
+// per control, immediates per w), the w loop is fully unrolled with uniform guards and
+// the probabilities are launch constants.  Same operations on the same operands.
+template <int D, int WM>
+__global__ void __launch_bounds__(256)
+k_sweep_fact_hoist_c(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+                     double* __restrict__ part_val, int32_t* __restrict__ part_idx, int RP,
+                     double inv_stride0, PVals PV) {
+    constexpr int NW = D - 1;
+    constexpr int UPL = 2;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int W = T.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // per warp: R[RP+1][W], lw[NW][W] | per warp: cw[W]
+    const int per_warp_d = W * (RP + 1) + NW * W;
+    double* R_sh = reinterpret_cast<double*>(fsm) + (size_t)warp * per_warp_d;
+    double* lw_sh = R_sh + W * (RP + 1);
+    int* cw_sh = reinterpret_cast<int*>(reinterpret_cast<double*>(fsm) + (size_t)nwarps * per_warp_d) + warp * W;
+
+    const int64_t item_id = (int64_t)blockIdx.x * nwarps + warp;
+    if (item_id >= T.n_items) return;
+    const SdpItem it = T.items[item_id];
+    for (int w = lane; w < W; w += 32) {
+        const int64_t f = (int64_t)it.state * W + w;
+        cw_sh[w] = __ldg(T.cell_w + f);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) lw_sh[j * W + w] = __ldg(T.lam_w + (int64_t)j * T.lam_w_plane + f);
+    }
+    // row range of the item's controls (cell_u = q0 * stride0)
+    int cmin = INT_MAX, cmax = INT_MIN;
+    for (int u = lane * 4; u < it.u_count; u += 128) {
+        const int4 c = *reinterpret_cast<const int4*>(T.cell + it.entry_base + u);
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (u + j < it.u_count) { cmin = min(cmin, cc[j]); cmax = max(cmax, cc[j]); }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, s));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, s));
+    }
+    const int stride0 = G.stride[0];
+    const int r0 = cmin / stride0;
+    const int nrows = cmax / stride0 - r0 + 1;
+    const bool hoist = nrows <= RP;
+    __syncwarp();
+    Frag<1, UPL> f_n;
+    double g_n[UPL];
+    int u0 = lane * UPL;
+    if (u0 < it.u_count) {
+        load_frag<1, UPL>(f_n, T.cell, T.lam, T.lam_plane, it.entry_base + u0);
+        load_g<UPL>(g_n, T.g, it.entry_base + u0);
+    }
+    if (hoist) {
+        for (int idx = lane; idx < (nrows + 1) * W; idx += 32) {
+            const int r = idx / W, w = idx - r * W;
+            double lam[D];
+            lam[0] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) lam[k + 1] = lw_sh[k * W + w];
+            R_sh[idx] = Lerp<double, D, 1>::eval(Jprev, (r0 + r) * stride0 + cw_sh[w], G.stride, lam);
+        }
+        __syncwarp();
+    }
+
+    double best_v = CUDART_INF;
+    int best_i = INT_MAX;
+    for (; u0 < it.u_count; u0 += 32 * UPL) {
+        int cu[UPL];
+        double lu[UPL], gv[UPL], acc[UPL];
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) { cu[j] = f_n.cell[j]; lu[j] = f_n.lam[0][j]; gv[j] = g_n[j]; acc[j] = 0.0; }
+        if (u0 + 32 * UPL < it.u_count) {
+            const int64_t off_n = it.entry_base + u0 + 32 * UPL;
+            load_frag<1, UPL>(f_n, T.cell, T.lam, T.lam_plane, off_n);
+            load_g<UPL>(g_n, T.g, off_n);
+        }
+        if (hoist) {
+            const double* Ra[UPL];
+            const double* Rb[UPL];
+            double oml[UPL];
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) {
+                // q0 = cu / stride0 exactly (cu is a multiple of stride0 below 2^31)
+                int q = __double2int_rn(__dmul_rn((double)cu[j], inv_stride0)) - r0;
+                q = max(0, min(q, nrows - 1));        // padding entries (cell 0) stay in range
+                Ra[j] = R_sh + q * W;
+                Rb[j] = Ra[j] + W;
+                oml[j] = sub_(1.0, lu[j]);
+            }
+            if (W == WM) {
+                // all slots live: no guards, so the 2*UPL*WM shared-memory reads of a
+                // control pair are issued together
+                double v[UPL][WM];
+#pragma unroll
+                for (int w = 0; w < WM; ++w)
+#pragma unroll
+                    for (int j = 0; j < UPL; ++j)
+                        v[j][w] = add_(mul_(oml[j], Ra[j][w]), mul_(lu[j], Rb[j][w]));
+#pragma unroll
+                for (int w = 0; w < WM; ++w)
+#pragma unroll
+                    for (int j = 0; j < UPL; ++j) {
+                        const double jg = add_(gv[j], v[j][w]);
+                        if (T.expect) acc[j] = add_(acc[j], mul_(jg, PV.v[w]));
+                        else acc[j] = jg;
+                    }
+            } else {
+#pragma unroll
+                for (int w = 0; w < WM; ++w) {
+                    if (w < W) {
+#pragma unroll
+                        for (int j = 0; j < UPL; ++j) {
+                            const double v = add_(mul_(oml[j], Ra[j][w]), mul_(lu[j], Rb[j][w]));
+                            const double jg = add_(gv[j], v);
+                            if (T.expect) acc[j] = add_(acc[j], mul_(jg, PV.v[w]));
+                            else acc[j] = jg;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int w = 0; w < W; ++w) {
+                const int cw = cw_sh[w];
+                const double pw = T.expect ? __ldg(T.p + w) : 1.0;
+#pragma unroll
+                for (int j = 0; j < UPL; ++j) {
+                    double lam[D];
+                    lam[0] = lu[j];
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) lam[k + 1] = lw_sh[k * W + w];
+                    const double v = Lerp<double, D, 0>::eval(Jprev, cu[j] + cw, G.stride, lam);
+                    const double jg = add_(gv[j], v);
+                    if (T.expect) acc[j] = add_(acc[j], mul_(jg, pw));
+                    else acc[j] = jg;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) {
+            const int u = u0 + j;
+            if (u < it.u_count) {
+                const int idx = it.u_begin + u;
+                if (better(acc[j], idx, best_v, best_i)) { best_v = acc[j]; best_i = idx; }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best_v, s);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, s);
+        if (better(ov, oi, best_v, best_i)) { best_v = ov; best_i = oi; }
+    }
+    if (lane == 0) {
+        part_val[item_id] = best_v;
+        part_idx[item_id] = best_i;
+    }
+}
+
 #ifndef SDP_BF_UB
 #define SDP_BF_UB 1      // controls per iteration of the BF kernel
 #endif
@@ -1422,9 +1595,6 @@ k_sweep_fact_hoist(GridT<double> G, SdpTables T, const double* __restrict__ Jpre
 // constant bank, an operand of the DMUL itself): ncu showed the shared-memory
 // reads of p[w] taking 1 of the ~9.6 L1 data-pipe wavefronts per warp step of a
 // kernel that is bound by exactly that pipe.
-struct PVals {
-    double v[SDP_FACTORED_MAX_W_REG];
-};
 
 template <int D, int MASK, int WM>
 __global__ void __launch_bounds__(128, SDP_BF_MINB)
@@ -1545,6 +1715,22 @@ static int launch_fact_m(const GridT<double>& G, const SdpTables& T, const doubl
             const long budget = (44L * 1024 - 8L * T.W) / warps - (long)T.W * (8 * NW + 4);
             int RP = (int)(budget / (8L * T.W)) - 1;
             if (RP > 32) RP = 32;
+            if (RP >= 2 && T.W <= SDP_FACTORED_MAX_W_REG && T.p_host && tuning().hoist_const) {
+                // constant-W kernel: no p[] in shared memory (same row budget, slightly smaller block)
+                size_t shm = (size_t)warps * ((size_t)T.W * (RP + 1 + NW) * 8 + (size_t)T.W * 4);
+                const double inv0 = 1.0 / (double)G.stride[0];
+                PVals pv;
+                for (int w = 0; w < SDP_FACTORED_MAX_W_REG; ++w)
+                    pv.v[w] = (w < T.W) ? (T.expect ? T.p_host[w] : 1.0) : 0.0;
+                if (T.W <= 3)
+                    k_sweep_fact_hoist_c<D, 3><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0, pv);
+                else if (T.W <= 5)
+                    k_sweep_fact_hoist_c<D, 5><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0, pv);
+                else
+                    k_sweep_fact_hoist_c<D, 9><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0, pv);
+                SDP_LAUNCH_CHECK();
+                return SDP_OK;
+            }
             if (RP >= 2) {
                 size_t shm = (size_t)T.W * 8 + (size_t)warps * ((size_t)T.W * (RP + 1 + NW) * 8 + (size_t)T.W * 4);
                 const double inv0 = 1.0 / (double)G.stride[0];   // host side: keeps fp64 division out of the kernel

@@ -658,28 +658,37 @@ def test_factored_tables_and_sweep_equal_dense(product, backend, layout, which):
 
 
 @gpu
-@pytest.mark.parametrize("which", ["storage_ar1", "searev", "coarse_controls", "uww"])
+@pytest.mark.parametrize("which", ["storage_ar1", "searev", "coarse_controls", "uww",
+                                   "storage_ar1_w2", "storage_ar1_w4", "storage_ar1_w7"])
 def test_hoisted_inner_interpolation_is_bit_identical(product, which):
-    """AF kernel with and without the per-item table of inner interpolations"""
-    from stodynprog_b200 import _cabi
-    sv = _factor_case(_Api(product, "cuda", "control_minor", "auto", "on"), which)
+    """AF kernel with and without the per-item table of inner interpolations; the
+    constant-W kernel with all slots live (W = 3, 5, 9) and with idle slots (W = 2, 4, 7)"""
+    from stodynprog_b200 import _cabi, workloads as wl
+    api = _Api(product, "cuda", "control_minor", "auto", "on")
+    if which.startswith("storage_ar1_w"):
+        sv = wl.storage_ar1(api, n_E=9, n_P=11, n_w=int(which[-1]), steps=(0.01, 0.1)).solver
+    else:
+        sv = _factor_case(api, which)
     assert sv.sweep_tables().u_mask == 1
     lib = sv.engine.lib
     J0 = np.random.default_rng(3).standard_normal(sv._state_grid_shape)
     J0[0] = np.nan if which == "uww" else J0[0]
     out = {}
     try:
-        for hoist in (1, 0):
+        # hoist_const = 1: the constant-W kernel (W <= 9, the default); 0: the runtime-W kernel
+        for hoist, const in ((1, 1), (1, 0), (0, 0)):
             for upl in (4, 2):
                 _cabi.check(lib.sdp_set_option(b"hoist", hoist), "sdp_set_option")
+                _cabi.check(lib.sdp_set_option(b"hoist_const", const), "sdp_set_option")
                 _cabi.check(lib.sdp_set_option(b"upl", upl), "sdp_set_option")
                 _cabi.check(lib.sdp_set_option(b"hoist_upl", upl), "sdp_set_option")
-                out[hoist, upl] = sv.value_iteration(J0, report_time=False)
+                out[hoist, const, upl] = sv.value_iteration(J0, report_time=False)
     finally:
         lib.sdp_set_option(b"hoist", 1)
+        lib.sdp_set_option(b"hoist_const", 1)
         lib.sdp_set_option(b"upl", 4)
         lib.sdp_set_option(b"hoist_upl", 2)
-    Jr, polr = out[0, 4]
+    Jr, polr = out[0, 0, 4]
     for key, (J, pol) in out.items():
         assert np.array_equal(J.view(np.int64), Jr.view(np.int64)), key
         assert np.array_equal(pol, polr, equal_nan=True), key
