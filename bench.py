@@ -199,16 +199,24 @@ def kernel_name(T):
     return "k_sweep_tiled_tma<%d,8>" % d if T.tiled else "k_sweep<%d,4>" % d
 
 
-def ncu_traffic(workload, T, world):
-    """DRAM bytes per launch of the streaming kernel from the committed ncu capture
-    (profiles/r1_traffic.json; N=1 only), or None"""
+def ncu_counters(workload, T, world):
+    """what the committed `ncu --set full` capture of this workload's streaming kernel says
+    (profiles/r1_traffic.json; N=1 only): {"traffic": DRAM bytes per launch, pipe
+    utilisations, source file}, or {}"""
     if world != 1:
-        return None
+        return {}
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return json.load(f).get("%s/%s" % (workload, T.layout_name))
+            e = json.load(f).get("%s/%s" % (workload, T.layout_name))
     except Exception:
-        return None
+        return {}
+    if e is None:
+        return {}
+    return e if isinstance(e, dict) else {"traffic": e}
+
+
+def ncu_traffic(workload, T, world):
+    return ncu_counters(workload, T, world)
 
 
 def time_sweeps(eng, T, J_prev, J_new, K, barrier):
@@ -231,6 +239,8 @@ def roofline_of(T, k1_ms, ms_total, K, peak, peak_src, traffic):
     b_alg = T.algorithmic_bytes_per_backup
     k1 = float(np.mean(k1_ms))
     achieved = T.n_backups_local * b_alg / (k1 * 1e-3) / 1e9
+    ncu = traffic if isinstance(traffic, dict) else {}
+    traffic = ncu.get("traffic")
     r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
          "kernel": kernel_name(T), "kernel_ms": k1, "kernel_share_of_step": k1 * K / ms_total,
@@ -240,6 +250,8 @@ def roofline_of(T, k1_ms, ms_total, K, peak, peak_src, traffic):
          "table_bytes_resident": T.device_bytes,
          "streamed_bytes_per_backup": T.streamed_bytes_per_backup,
          "streamed_GBs": T.device_bytes / (k1 * 1e-3) / 1e9}
+    if len(ncu) > 1:
+        r["ncu"] = {k: v for k, v in ncu.items() if k != "traffic"}
     if T.factored:
         r["note"] = ("factored (x,u)+(x,w) tables: the kernel streams %.2f B per backup instead of "
                      "the dense layout's %.2f B, so `achieved` (dense algorithmic bytes / time, "

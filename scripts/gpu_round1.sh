@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $
 echo "pytest exit: $?" >> $OUT/pytest_gpu.log
 ( time timeout 600 python bench.py ) > $OUT/bench_n1.json 2> $OUT/bench_n1.err
 ( time timeout 400 python bench.py --impl reference --steps 3 --warmup 1 ) > $OUT/bench_ref.json 2> $OUT/bench_ref.err
-timeout 600 python scripts/dev_slab_scaling.py > $OUT/slab_scaling.txt 2>&1
+[ -n "${SKIP_SLAB:-}" ] || timeout 600 python scripts/dev_slab_scaling.py > $OUT/slab_scaling.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extra --no-dense \
     > $OUT/launches_bench.log 2>&1
