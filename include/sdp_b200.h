@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SDP_ABI_VERSION 3
+#define SDP_ABI_VERSION 4
 #define SDP_MAX_D 4 /* the reference dispatches d = 1..4 (multilinear_cython.pyx:36-47) */
 
 /* error codes */
@@ -102,6 +102,18 @@ typedef struct SdpItem {
 #define SDP_LAYOUT_CONTROL_MINOR_FACTORED 2 /* "AF": u-part [state][Upad], w-part [state][W] */
 #define SDP_LAYOUT_STATE_MINOR_FACTORED 3   /* "BF": u-part [tile][u][32], w-part [tile][w][32] */
 #define SDP_FACTORED_MAX_W_REG 9 /* BF keeps the w-part of a lane in registers: W <= 9 */
+/* "CF", column-shared hoist: BF tables whose tiles run along state axis 0 - tile
+ * t = c*tiles_per_col + b holds rows 32*b .. 32*b+31 of COLUMN c (the flat C-order
+ * index over the state axes 1..d-1) - for systems with u_mask == 1 whose (x,w) part
+ * does not depend on the axis-0 index (the storage examples: P_next = a*P + w does
+ * not involve E).  The inner interpolation R(row, w) over the axes 1..d-1 is then
+ * the same for all the states of a column: one CTA tabulates it once per column in
+ * shared memory ((order[0]+1)*W doubles) and every backup of the column is two
+ * shared-memory reads and one lerp instead of 2^d gathers and 2^d-1 lerps - the
+ * operations of the reference's nested formula, evaluated once instead of once per
+ * (state, control).  Bit-identical to the other layouts. */
+#define SDP_LAYOUT_COLUMN_FACTORED 4
+#define SDP_COLUMN_MAX_SMEM_BYTES (200 * 1024) /* CF: ((order[0]+1)*W + 9) * 8 must fit */
 
 /* Dense sweep tables of one shard of states (device pointers).
  *
@@ -132,7 +144,9 @@ typedef struct SdpItem {
  *   w-part, entry f = state*W + w (AF) = (tile*W + w)*32 + lane (BF):
  *     cell_w[f], lam_w[j*lam_w_plane + f]   same for the w-type coordinates
  *   Items: entry_base = g_base = first u-part entry of the run.
- *   Actual bytes per (x,u,w): (12 + 8*n_u)/W + (4 + 8*n_w)/U(x). */
+ *   Actual bytes per (x,u,w): (12 + 8*n_u)/W + (4 + 8*n_w)/U(x).
+ *
+ * Layout CF: see SDP_LAYOUT_COLUMN_FACTORED and the last fields below. */
 typedef struct SdpTables {
     const int32_t* cell;
     const double* lam;
@@ -157,6 +171,19 @@ typedef struct SdpTables {
     /* HOST copy of p[W] (the same values as `p`).  Required by layout BF, whose
      * kernel takes the probabilities as launch constants; ignored otherwise. */
     const double* p_host;
+    /* Layout CF only.  The shard is `n_states / n_cols` whole rows of axis 0 (local
+     * state i = row*n_cols + column, as in the C-order grid); units/items/u-part/w-part
+     * are those of layout BF over the column-major tiles described above, `U` is indexed
+     * by POSITION tile*32 + lane (32*n_cols*tiles_per_col entries, 0 on the padding
+     * lanes of a column's last tile); the w-part read by the sweep is that of lane 0 of
+     * the column's first tile (the caller checks that the whole column agrees).
+     * seg_begin: [n_segs + 1] item ranges - one CTA sweeps the items
+     * seg_begin[b] .. seg_begin[b+1]-1 (items are ordered by tile, hence by column) and
+     * rebuilds its shared-memory table whenever the column changes. */
+    int32_t n_cols;
+    int32_t tiles_per_col;
+    const int64_t* seg_begin;
+    int64_t n_segs;
 } SdpTables;
 
 /* ABI / build identification. */
@@ -171,6 +198,7 @@ int64_t sdp_launch_count(void);
  * "tma_rows" (4|8), "tma_stages" (2..16), "tma_warps" (1..16), "hoist" (layout AF
  * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4),
  * "hoist_const" (0|1: constant-W variant of that kernel for W <= 9),
+ * "col_threads" (layout CF: threads per CTA, 128..512), "col_ub" (controls per iteration, 1|2),
  * "p2p_timeout_s" (bound of the peer-flag waits, default 600 s, then the kernel traps).
  * Not thread-safe against concurrent launches. */
 int sdp_set_option(const char* name, int value);

@@ -12,11 +12,13 @@ import numpy as np
 
 SDP_MAX_D = 4
 SDP_MAX_C = 4
-SDP_ABI_VERSION = 3
+SDP_ABI_VERSION = 4
 LAYOUT_CONTROL_MINOR = 0   # "A": [state][w][u]
 LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
 LAYOUT_CONTROL_MINOR_FACTORED = 2   # "AF": (x,u) part [state][Upad] + (x,w) part [state][W]
 LAYOUT_STATE_MINOR_FACTORED = 3     # "BF": (x,u) part [tile][u][lane] + (x,w) part [tile][w][lane]
+LAYOUT_COLUMN_FACTORED = 4          # "CF": BF tables over column-major tiles, inner interpolation shared per column
+COLUMN_MAX_SMEM_BYTES = 200 * 1024  # CF: ((order[0]+1)*W + 9) * 8 bytes of shared memory for the column table
 FACTORED_MAX_W_REG = 9     # BF keeps a lane's w-part in registers
 FACTORED_MAX_W_SMEM = 128  # AF keeps a state's w-part in shared memory
 
@@ -56,7 +58,11 @@ class SdpTables(ctypes.Structure):
                 ("cell_w", ctypes.c_void_p),
                 ("lam_w", ctypes.c_void_p),
                 ("lam_w_plane", ctypes.c_int64),
-                ("p_host", ctypes.c_void_p)]
+                ("p_host", ctypes.c_void_p),
+                ("n_cols", ctypes.c_int32),
+                ("tiles_per_col", ctypes.c_int32),
+                ("seg_begin", ctypes.c_void_p),
+                ("n_segs", ctypes.c_int64)]
 
 
 SDP_MAX_PEERS = 8

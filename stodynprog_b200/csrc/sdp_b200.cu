@@ -995,14 +995,32 @@ k_sweep_tiled_tma(GridT<double> G, SdpTables T, const double* __restrict__ Jprev
     part_idx[item_id * 32 + lane] = ws.best_i;
 }
 
+// (tile, lane) holding local state i: 32 consecutive states per tile (layouts B / BF), or -
+// layout CF, n_cols > 0 - state i = row*n_cols + col sits in lane row%32 of tile
+// col*tiles_per_col + row/32
+__device__ __forceinline__ void tile_of_state(int64_t i, int n_cols, int tiles_per_col,
+                                              int64_t& tile, int& lane) {
+    if (n_cols > 0) {
+        const int64_t row = i / n_cols;
+        const int col = (int)(i - row * n_cols);
+        tile = (int64_t)col * tiles_per_col + (row >> 5);
+        lane = (int)(row & 31);
+    } else {
+        tile = i >> 5;
+        lane = (int)(i & 31);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_sweep_finalize_tiled(int64_t n_states, const int64_t* __restrict__ item_begin,
                        const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
-                       double* __restrict__ J_out, int32_t* __restrict__ argmin_out) {
+                       double* __restrict__ J_out, int32_t* __restrict__ argmin_out,
+                       int n_cols, int tiles_per_col) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_states) return;
-    const int64_t tile = i >> 5;
-    const int lane = (int)(i & 31);
+    int64_t tile;
+    int lane;
+    tile_of_state(i, n_cols, tiles_per_col, tile, lane);
     int64_t b = item_begin[tile], e = item_begin[tile + 1];
     double bv = CUDART_INF;
     int bi = INT_MAX;
@@ -1030,6 +1048,8 @@ struct Tuning {
     int hoist_upl; // controls per lane per iteration of the hoisted kernel (2|4)
     int p2p_timeout_s; // bound of the peer-flag waits (seconds) before the kernel traps
     int hoist_const;   // layout AF hoisted kernel: constant-W variant for W <= 9 (1) or the runtime-W kernel (0)
+    int col_threads;   // layout CF: threads per CTA (one CTA per SM: the column table fills shared memory)
+    int col_ub;        // layout CF: controls per lane per iteration (1|2)
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static int env_int(const char* name, int dflt) {
@@ -1060,6 +1080,8 @@ static Tuning& tuning() {
         x.hoist_upl = env_int("SDP_HOIST_UPL", 2) == 4 ? 4 : 2;
         x.p2p_timeout_s = clampi(env_int("SDP_P2P_TIMEOUT_S", 600), 1, 86400);
         x.hoist_const = env_int("SDP_HOIST_CONST", 1) != 0;
+        x.col_threads = clampi(env_int("SDP_COL_THREADS", 512), 128, 512) / 32 * 32;
+        x.col_ub = env_int("SDP_COL_UB", 2) == 1 ? 1 : 2;
         return x;
     }();
     return t;
@@ -1078,6 +1100,8 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "hoist_upl")) t.hoist_upl = (value == 4) ? 4 : 2;
     else if (!strcmp(name, "p2p_timeout_s")) t.p2p_timeout_s = clampi(value, 1, 86400);
     else if (!strcmp(name, "hoist_const")) t.hoist_const = value != 0;
+    else if (!strcmp(name, "col_threads")) t.col_threads = clampi(value, 128, 512) / 32 * 32;
+    else if (!strcmp(name, "col_ub")) t.col_ub = (value == 1) ? 1 : 2;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1698,6 +1722,181 @@ static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, cons
     k_sweep_fact_tiled<D, MASK, WM><<<blocks, warps * 32, 0, st>>>(G, T, Jprev, part_val, part_idx, pv);
 }
 
+// ---------------------------------------------------------------------------
+// CF: column-shared hoist (include/sdp_b200.h, SDP_LAYOUT_COLUMN_FACTORED).
+//
+// Layout BF spends 2^d gathers (32 bytes of corner values per lane through the L1
+// data pipe) and 2^d-1 lerps on every backup; ncu shows that pipe as its limiter.
+// With u_mask == 1 the nested lerp is
+//     (1-l0)*R(q0, w) + l0*R(q0+1, w),   R(r, w) = lerp over axes 1.. of J[r, ...]
+// and when the (x,w) part of a state does not depend on its axis-0 index (P_next =
+// a*P + w does not involve the storage energy), R is the same function of (r, w)
+// for ALL states of a column of the grid (fixed indices on the axes 1..d-1).  One
+// CTA therefore tabulates R for every row of the grid once per column
+// (order[0]*W inner lerps - the very operations every backup of the column would
+// repeat) and then sweeps the column's tiles, lane <-> row: a backup is two
+// shared-memory reads and one lerp.  Adjacent lanes are adjacent rows, so with W = 9
+// the 72-byte row pitch spreads a half-warp's 8-byte reads over all 32 banks.
+//
+// Work split: the item list is ordered by tile, hence by column; the host cuts it
+// into n_segs runs of equal weight, one per CTA (one CTA per SM: the table fills
+// shared memory), so a CTA meets few column changes.  Warps take the items of the
+// current column round-robin.  Partial minima have the layout of BF.
+// ---------------------------------------------------------------------------
+template <int D, int WM, int UB, bool FULL>       // FULL: W == WM, every slot live
+__global__ void __launch_bounds__(512, 1)
+k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
+                    double* __restrict__ part_val, int32_t* __restrict__ part_idx,
+                    double inv_stride0, PVals PV) {
+    constexpr int NW = D - 1;
+    extern __shared__ __align__(16) unsigned char csm[];
+    double* R_sh = reinterpret_cast<double*>(csm);      // [order[0]][W] (+ WM doubles of slack)
+    __shared__ int cw_sh[WM];
+    __shared__ double lw_sh[NW][WM];
+    const int W = T.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int rows = G.order[0];
+    const int stride0 = G.stride[0];
+
+    int64_t i = T.seg_begin[blockIdx.x];
+    const int64_t seg_end = T.seg_begin[blockIdx.x + 1];
+    while (i < seg_end) {
+        const int col = T.items[i].state / T.tiles_per_col;
+        const int64_t col_end = T.item_begin[(int64_t)(col + 1) * T.tiles_per_col];
+        const int64_t e = col_end < seg_end ? col_end : seg_end;
+        __syncthreads();                 // the previous column's readers are done with R
+        if (threadIdx.x < W) {
+            // the column's w-part: lane 0 of its first tile
+            const int64_t f = ((int64_t)col * T.tiles_per_col * W + threadIdx.x) * 32;
+            cw_sh[threadIdx.x] = __ldg(T.cell_w + f);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) lw_sh[k][threadIdx.x] = __ldg(T.lam_w + (int64_t)k * T.lam_w_plane + f);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < rows * W; idx += blockDim.x) {
+            const int r = idx / W, w = idx - r * W;
+            double lam[D];
+            lam[0] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) lam[k + 1] = lw_sh[k][w];
+            R_sh[idx] = Lerp<double, D, 1>::eval(Jprev, r * stride0 + cw_sh[w], G.stride, lam);
+        }
+        __syncthreads();
+
+        for (int64_t item_id = i + warp; item_id < e; item_id += nwarps) {
+            const SdpItem it = T.items[item_id];
+            const int Us = T.U[(int64_t)it.state * 32 + lane];      // by position; 0 on padding lanes
+            const int32_t* __restrict__ cup = T.cell + it.entry_base + lane;
+            const double* __restrict__ lup = T.lam + it.entry_base + lane;
+            const double* __restrict__ gp = T.g + it.g_base + lane;
+            double best_v = CUDART_INF;
+            int best_i = INT_MAX;
+            const int last = it.u_count - 1;
+
+            // group of UB controls, streamed one group ahead (rows past the run repeat its last row)
+            int c_n[UB];
+            double g_n[UB], l_n[UB];
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const int64_t o = (int64_t)min(b, last) * 32;
+                c_n[b] = __ldcs(cup + o);
+                g_n[b] = __ldcs(gp + o);
+                l_n[b] = __ldcs(lup + o);
+            }
+            for (int uu = 0; uu < it.u_count; uu += UB) {
+                double gv[UB], lu[UB], oml[UB];
+                const double* Ra[UB];
+#pragma unroll
+                for (int b = 0; b < UB; ++b) {
+                    gv[b] = g_n[b];
+                    lu[b] = l_n[b];
+                    oml[b] = sub_(1.0, lu[b]);
+                    // row q0 = cell_u / stride0 exactly (cell_u is a multiple of stride0 below 2^31;
+                    // padding entries hold cell 0)
+                    const int q = __double2int_rn(__dmul_rn((double)c_n[b], inv_stride0));
+                    Ra[b] = R_sh + q * W;
+                }
+                if (uu + UB < it.u_count) {
+#pragma unroll
+                    for (int b = 0; b < UB; ++b) {
+                        const int64_t o = (int64_t)min(uu + UB + b, last) * 32;
+                        c_n[b] = __ldcs(cup + o);
+                        g_n[b] = __ldcs(gp + o);
+                        l_n[b] = __ldcs(lup + o);
+                    }
+                }
+                // slots >= W read past the W live values of a row (the next row, or the slack
+                // behind the table) and are discarded below: no guards on the reads
+                double v[UB][WM];
+#pragma unroll
+                for (int b = 0; b < UB; ++b)
+#pragma unroll
+                    for (int w = 0; w < WM; ++w)
+                        v[b][w] = add_(mul_(oml[b], Ra[b][w]), mul_(lu[b], Ra[b][W + w]));
+#pragma unroll
+                for (int b = 0; b < UB; ++b) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int w = 0; w < WM; ++w) {
+                        const double jg = add_(gv[b], v[b][w]);
+                        const double nxt = T.expect ? add_(acc, mul_(jg, PV.v[w])) : jg;
+                        acc = (FULL || w < W) ? nxt : acc;   // slots past W do not take part
+                    }
+                    const int u = it.u_begin + uu + b;
+                    if (uu + b <= last && u < Us && better(acc, u, best_v, best_i)) { best_v = acc; best_i = u; }
+                }
+            }
+            part_val[item_id * 32 + lane] = best_v;
+            part_idx[item_id * 32 + lane] = best_i;
+        }
+        i = e;
+    }
+}
+
+template <int D, int WM, int UB>
+static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                                double* part_val, int32_t* part_idx, cudaStream_t st) {
+    const size_t shm = ((size_t)G.order[0] * T.W + WM) * 8;
+    if (shm > SDP_COLUMN_MAX_SMEM_BYTES)
+        return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF: the column table does not fit shared memory");
+    static size_t attr_set = 0;          // per instantiation
+    if (attr_set < shm) {
+        cudaError_t e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e != cudaSuccess) return fail(SDP_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = shm;
+    }
+    PVals pv;
+    for (int w = 0; w < SDP_FACTORED_MAX_W_REG; ++w)
+        pv.v[w] = (w < T.W) ? (T.expect ? T.p_host[w] : 1.0) : 0.0;
+    const double inv0 = 1.0 / (double)G.stride[0];
+    if (T.W == WM)
+        k_sweep_fact_column<D, WM, UB, true><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
+            G, T, Jprev, part_val, part_idx, inv0, pv);
+    else
+        k_sweep_fact_column<D, WM, UB, false><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
+            G, T, Jprev, part_val, part_idx, inv0, pv);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+template <int D>
+static int launch_fact_column(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                              double* part_val, int32_t* part_idx, cudaStream_t st) {
+    const bool ub2 = tuning().col_ub == 2;
+    if (T.W <= 3)
+        return ub2 ? launch_fact_column_k<D, 3, 2>(G, T, Jprev, part_val, part_idx, st)
+                   : launch_fact_column_k<D, 3, 1>(G, T, Jprev, part_val, part_idx, st);
+    if (T.W <= 5)
+        return ub2 ? launch_fact_column_k<D, 5, 2>(G, T, Jprev, part_val, part_idx, st)
+                   : launch_fact_column_k<D, 5, 1>(G, T, Jprev, part_val, part_idx, st);
+    return ub2 ? launch_fact_column_k<D, 9, 2>(G, T, Jprev, part_val, part_idx, st)
+               : launch_fact_column_k<D, 9, 1>(G, T, Jprev, part_val, part_idx, st);
+}
+
 template <int D, int MASK>
 static int launch_fact_m(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                          double* part_val, int32_t* part_idx, cudaStream_t st) {
@@ -1776,11 +1975,13 @@ int launch_fact<3>(const GridT<double>& G, const SdpTables& T, const double* Jpr
     }
 }
 
+static inline bool is_column(const SdpTables& T) { return T.layout == SDP_LAYOUT_COLUMN_FACTORED; }
 static inline bool is_tiled(const SdpTables& T) {
-    return T.layout == SDP_LAYOUT_STATE_MINOR || T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED;
+    return T.layout == SDP_LAYOUT_STATE_MINOR || T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED || is_column(T);
 }
 static inline bool is_factored(const SdpTables& T) {
-    return T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED || T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED;
+    return T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED || T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED ||
+           is_column(T);
 }
 static int check_tables(const SdpTables& T, const char* who) {
     if (T.W < 1 || T.W > 4096 || T.n_states < 0 || T.n_items < 0)
@@ -1790,17 +1991,26 @@ static int check_tables(const SdpTables& T, const char* who) {
         return fail(SDP_EINVAL, "%s: NULL pointer in tables", who);
     if ((T.lam_plane & 3) || ((uintptr_t)T.cell & 15) || ((uintptr_t)T.lam & 15) || ((uintptr_t)T.g & 15))
         return fail(SDP_EINVAL, "%s: tables must be 16-byte aligned, lam_plane % 4 == 0", who);
-    if (T.layout < SDP_LAYOUT_CONTROL_MINOR || T.layout > SDP_LAYOUT_STATE_MINOR_FACTORED)
+    if (T.layout < SDP_LAYOUT_CONTROL_MINOR || T.layout > SDP_LAYOUT_COLUMN_FACTORED)
         return fail(SDP_EINVAL, "%s: unknown table layout", who);
     if (is_tiled(T) && !T.U)
         return fail(SDP_EINVAL, "%s: layout B needs the per-state control counts", who);
     if (is_factored(T)) {
         if (T.g_per_w || !T.cell_w || !T.lam_w)
             return fail(SDP_EINVAL, "%s: factored tables need g per (x,u) and a w-part", who);
-        if (T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED && T.W > SDP_FACTORED_MAX_W_REG)
-            return fail(SDP_EINVAL, "%s: layout BF supports at most 9 perturbation nodes", who);
-        if (T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED && T.expect && !T.p_host)
-            return fail(SDP_EINVAL, "%s: layout BF needs p_host (host copy of the probabilities)", who);
+        if ((T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED || is_column(T)) && T.W > SDP_FACTORED_MAX_W_REG)
+            return fail(SDP_EINVAL, "%s: layouts BF / CF support at most 9 perturbation nodes", who);
+        if ((T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED || is_column(T)) && T.expect && !T.p_host)
+            return fail(SDP_EINVAL, "%s: layouts BF / CF need p_host (host copy of the probabilities)", who);
+        if (is_column(T)) {
+            if (T.u_mask != 1)
+                return fail(SDP_EINVAL, "%s: layout CF needs u_mask == 1 (axis 0 follows the control)", who);
+            if (T.n_cols < 1 || T.tiles_per_col < 1 || T.n_states % T.n_cols != 0 ||
+                (T.n_states / T.n_cols + 31) / 32 != T.tiles_per_col)
+                return fail(SDP_EINVAL, "%s: layout CF: the shard must be whole rows, 32 per tile", who);
+            if (!T.seg_begin || T.n_segs < 1 || T.n_segs > 0x7fffffffLL)
+                return fail(SDP_EINVAL, "%s: layout CF needs the CTA segments of the item list", who);
+        }
         if (T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED && T.W > 128)
             return fail(SDP_EINVAL, "%s: layout AF supports at most 128 perturbation nodes", who);
     }
@@ -1823,6 +2033,9 @@ extern "C" int sdp_sweep_partials(const SdpGrid* grid, const SdpTables* tab, con
     if (is_factored(T)) {
         rc = check_factored_args(grid->d, T.W, T.u_mask, "sdp_sweep");
         if (rc) return rc;
+        if (T.layout == SDP_LAYOUT_COLUMN_FACTORED)
+            return grid->d == 2 ? launch_fact_column<2>(G, T, J_prev, part_val, part_idx, st)
+                                : launch_fact_column<3>(G, T, J_prev, part_val, part_idx, st);
         return grid->d == 2 ? launch_fact<2>(G, T, J_prev, part_val, part_idx, st)
                             : launch_fact<3>(G, T, J_prev, part_val, part_idx, st);
     }
@@ -1847,7 +2060,8 @@ extern "C" int sdp_sweep_finalize(const SdpTables* tab, const double* part_val,
     cudaStream_t st = (cudaStream_t)stream;
     unsigned blocks = (unsigned)((T.n_states + 255) / 256);
     if (is_tiled(T))
-        k_sweep_finalize_tiled<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
+        k_sweep_finalize_tiled<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out,
+                                                       is_column(T) ? T.n_cols : 0, T.tiles_per_col);
     else
         k_sweep_finalize<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
     SDP_LAUNCH_CHECK();
@@ -1928,11 +2142,13 @@ template <bool TILED>
 __global__ void __launch_bounds__(256)
 k_sweep_finalize_p2p(int64_t n_states, const int64_t* __restrict__ item_begin,
                      const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
-                     int32_t* __restrict__ argmin_out, PeersDev P, int64_t state_begin) {
+                     int32_t* __restrict__ argmin_out, PeersDev P, int64_t state_begin,
+                     int n_cols, int tiles_per_col) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_states) {
-        const int64_t unit = TILED ? (i >> 5) : i;
-        const int lane = TILED ? (int)(i & 31) : 0;
+        int64_t unit = i;
+        int lane = 0;
+        if (TILED) tile_of_state(i, n_cols, tiles_per_col, unit, lane);
         const int width = TILED ? 32 : 1;
         double bv = CUDART_INF;
         int bi = INT_MAX;
@@ -2009,9 +2225,10 @@ extern "C" int sdp_sweep_finalize_p2p(const SdpTables* tab, const double* part_v
     unsigned blocks = (unsigned)((T.n_states + 255) / 256);
     if (blocks == 0) blocks = 1;
     if (is_tiled(T))
-        k_sweep_finalize_p2p<true><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin);
+        k_sweep_finalize_p2p<true><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin,
+                                                           is_column(T) ? T.n_cols : 0, T.tiles_per_col);
     else
-        k_sweep_finalize_p2p<false><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin);
+        k_sweep_finalize_p2p<false><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin, 0, 0);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }

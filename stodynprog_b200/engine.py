@@ -18,7 +18,12 @@ import numpy as np
 from . import _cabi
 from . import tabulate as tb
 
-__all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "rebalance_bounds"]
+__all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "rebalance_bounds",
+           "column_order", "row_aligned"]
+
+# solver.column_hoist = "auto" uses layout CF (column-shared hoist) whenever it applies iff this
+# is set; "on" / "off" on the solver override it
+COLUMN_HOIST_DEFAULT = os.environ.get("SDP_COLUMN_HOIST", "0") != "0"
 
 
 def _torch():
@@ -111,6 +116,10 @@ def fill_c_tables(T):
     c.expect = T.expect
     if T.u_mask:
         c.layout = _cabi.LAYOUT_STATE_MINOR_FACTORED if T.tiled else _cabi.LAYOUT_CONTROL_MINOR_FACTORED
+        if T.column:
+            c.layout = _cabi.LAYOUT_COLUMN_FACTORED
+            c.n_cols, c.tiles_per_col = T.n_cols, T.tiles_per_col
+            c.seg_begin, c.n_segs = T.seg_begin.data_ptr(), T.n_segs
         c.u_mask = T.u_mask
         c.cell_w = T.cell_w.data_ptr()
         c.lam_w = T.lam_w.data_ptr()
@@ -145,6 +154,40 @@ def pick_item_chunk(unit_U, min_chunk, max_chunk=512, target=ITEMS_TARGET):
     while chunk > min_chunk and int(((unit_U + chunk - 1) // chunk).sum()) < target:
         chunk //= 2
     return max(chunk, min_chunk)
+
+
+class ColumnHoistRefused(Exception):
+    """layout CF was demanded (column_hoist = 'on') for tables whose (x,w) part varies
+    along a column of the grid"""
+
+
+def column_order(n_states, n_cols):
+    """Position order of layout CF for a slab of whole rows of state axis 0.
+
+    The slab's local states are i = row*n_cols + col (C-order).  Layout CF walks them
+    column by column, every column padded to whole tiles of 32 rows: position
+    p = col*(32*tiles_per_col) + row.  Returns (order, valid, tiles_per_col):
+    order[p] = local state at position p (a padding position repeats the column's last
+    row), valid[p] = False on padding positions."""
+    n_rows = n_states // n_cols
+    assert n_rows * n_cols == n_states and n_rows >= 1
+    tiles_per_col = (n_rows + 31) // 32
+    row = np.arange(32 * tiles_per_col, dtype=np.int64)
+    valid_row = row < n_rows
+    row = np.minimum(row, n_rows - 1)
+    order = (row[None, :] * n_cols + np.arange(n_cols, dtype=np.int64)[:, None]).reshape(-1)
+    valid = np.broadcast_to(valid_row[None, :], (n_cols, len(row))).reshape(-1).copy()
+    return order, valid, tiles_per_col
+
+
+def row_aligned(bounds, n_cols):
+    """slab boundaries moved to the nearest multiple of n_cols (whole rows of axis 0),
+    kept monotone"""
+    out = [int(bounds[0])]
+    for b in bounds[1:-1]:
+        out.append(max(out[-1], int(round(float(b) / n_cols)) * n_cols))
+    out.append(int(bounds[-1]))
+    return [min(b, out[-1]) for b in out]
 
 
 class Collective(object):
@@ -316,6 +359,11 @@ class SweepTables(object):
         self.item_chunk = 0        # controls per work item used for these tables
         self.item_begin_host = self.unit_U_host = None
         self.chunk_plan = None     # see Engine._chunk_plan
+        # layout CF (column-shared hoist): BF tables over column-major tiles, see column_order()
+        self.column = False
+        self.n_cols = self.tiles_per_col = 0
+        self.seg_begin = None      # device int64 [n_segs+1]: item range of every CTA
+        self.n_segs = 0
         self.slab_times_ms = None  # measured per-rank sweep times (several ranks, see _measured_bounds)
         self.slab_recut = False    # True when those times moved the slab boundaries
 
@@ -331,6 +379,8 @@ class SweepTables(object):
 
     @property
     def layout_name(self):
+        if self.column:
+            return "column_factored"
         return ("state_minor" if self.tiled else "control_minor") + ("_factored" if self.u_mask else "")
 
     @property
@@ -658,6 +708,24 @@ class Engine(object):
         if U_all.max(initial=0) >= 2 ** 31 - 4:
             raise ValueError("more than 2^31 control combinations for one state")
 
+        # layout CF (column-shared hoist, include/sdp_b200.h): wanted by solver.column_hoist,
+        # possible when the column table fits shared memory; needs slabs of whole rows of
+        # state axis 0, a factored split with u_mask == 1 and a w-part that is the same for
+        # all the states of a column (checked on the built tables, see build_for)
+        n_rows0 = len(state_grid[0])
+        n_cols = n_grid // n_rows0
+        col_mode = getattr(solver, "column_hoist", "auto")
+        if col_mode not in ("auto", "on", "off"):
+            raise ValueError("column_hoist must be 'auto', 'on' or 'off'")
+        col_wanted = col_mode == "on" or (col_mode == "auto" and COLUMN_HOIST_DEFAULT)
+        col_candidate = bool(
+            col_wanted and d in (2, 3) and nb_perturb == 1 and 1 < W <= _cabi.FACTORED_MAX_W_REG
+            and ((n_rows0 + 1) * W + 9) * 8 <= _cabi.COLUMN_MAX_SMEM_BYTES
+            and getattr(solver, "table_layout", "auto") in ("auto", "state_minor")
+            and getattr(solver, "table_compress", "auto") != "off"
+            and n_rows0 >= 32 * world and nb_control <= _cabi.SDP_MAX_C)
+        col_refused = [False]       # set when the built w-part turns out to vary along a column
+
         def build_for(bounds, reuse):
             """tables of this rank's slab [bounds[rank], bounds[rank+1])"""
             sb, se = bounds[rank], bounds[rank + 1]
@@ -693,11 +761,37 @@ class Engine(object):
             if world > 1:
                 # all ranks must agree (they run the same kernels on the same layout)
                 u_mask = min(coll.all_gather_object(u_mask))
+            column = bool(col_candidate and not col_refused[0] and tiled and u_mask == 1 and n > 0
+                          and sb % n_cols == 0 and se % n_cols == 0)
+            if world > 1:
+                column = bool(min(coll.all_gather_object(column)))
+            if col_mode == "on" and not column:
+                raise ValueError("column_hoist='on' but layout CF does not apply: it needs the "
+                                 "state-minor layout, a factored (x,u)+(x,w) split with state axis 0 "
+                                 "alone following the control, at most 9 perturbation nodes, a w-part "
+                                 "that does not depend on axis 0, and (order[0]+1)*W*8 bytes of "
+                                 "shared memory")
+            pos = {}
 
-            def sizes(u_mask):
+            def positions(col):
+                """(n_eff, U_eff, host_eff, flat_eff, valid): the slab's states in table order -
+                C-order, or for layout CF column by column with padding (column_order)"""
+                if col not in pos:
+                    if not col:
+                        pos[col] = (n, U, host, None, None, 0)
+                    else:
+                        order, valid, tiles_per_col = column_order(n, n_cols)
+                        h = tb.HostStateTable(len(order), nb_control)
+                        h.lo, h.hi, h.npts = host.lo[order], host.hi[order], host.npts[order]
+                        pos[col] = (len(order), np.where(valid, U[order], 0), h, sb + order, valid,
+                                    tiles_per_col)
+                return pos[col]
+
+            def sizes(u_mask, col):
                 """entry offsets of the layout: dense tables have W entries per control,
                 factored tables one"""
                 Wf = 1 if u_mask else W
+                n, U = positions(col)[:2]
                 if tiled:
                     n_tiles = (n + 31) // 32
                     Upad_t = np.zeros(n_tiles * 32, dtype=np.int64)
@@ -726,14 +820,14 @@ class Engine(object):
             T.p_host = np.ascontiguousarray(solver.perturb_proba[0], dtype=np.float64).copy() \
                 if nb_perturb == 1 else np.ones(1)
             # (one packed upload for the small per-table arrays)
-            small = [T.p_host, U.astype(np.int32) if n else np.zeros(1, dtype=np.int32)]
+            small = [T.p_host]
             if nb_control:
                 small += [host_full.lo.reshape(-1), host_full.hi.reshape(-1),
                           host_full.npts.astype(np.int32).reshape(-1)]
             small = self.to_device_packed(small)
-            T.p, T.U_dev = small[0], small[1]
+            T.p = small[0]
             # replicated control discretisation, for the argmin -> control value kernel
-            T.lo_dev, T.hi_dev, T.npts_dev = (small[2], small[3], small[4]) if nb_control else (None, None, None)
+            T.lo_dev, T.hi_dev, T.npts_dev = (small[1], small[2], small[3]) if nb_control else (None, None, None)
             T.nb_control = nb_control
             T.tabulate_mode = None
 
@@ -745,9 +839,10 @@ class Engine(object):
                     setattr(T, name, None)        # release before allocating the new size
                     setattr(T, name, torch.empty(numel, dtype=dtype, device=dev))
 
-            def build(g_per_w, batched, u_mask):
+            def build(g_per_w, batched, u_mask, col):
                 L = {"u_mask": u_mask}
-                n_tiles, tile_U, tile_off, n_entries, entry_off, Upad = sizes(u_mask)
+                n, U, host, flat_eff, valid, _ = positions(col)
+                n_tiles, tile_U, tile_off, n_entries, entry_off, Upad = sizes(u_mask, col)
                 lam_plane = (n_entries + 3) // 4 * 4
                 n_u = bin(u_mask).count("1")
                 L.update(n_tiles=n_tiles, tile_U=tile_U, tile_off=tile_off, n_entries=n_entries,
@@ -844,12 +939,15 @@ class Engine(object):
                     tb.tabulate_states_batched(sys, state_grid, sb, se, host, w_grid, t_k, entry_off,
                                                g_off, Upad, g_per_w, flush, align=align,
                                                verify=1 if prev_mode == "batched" else 8,
-                                               grid_cache=self._grid_cache if t_k is not None else None)
+                                               grid_cache=self._grid_cache if t_k is not None else None,
+                                               flat_index=flat_eff, valid=valid)
                 else:
                     states = mine if (mine is not None and (sb, se) == (eq[rank], eq[rank + 1])) else \
                         tb.state_tuples(state_grid, sb, se)
+                    if col:
+                        states = [states[i] for i in flat_eff - sb]
                     tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
-                                       g_per_w, flush, align=align)
+                                       g_per_w, flush, align=align, valid=valid)
                 return L
 
             # mode / layout resolution: batched evaluation is tried first in "auto"
@@ -861,8 +959,23 @@ class Engine(object):
             L = None
             while L is None:
                 try:
-                    L = build(g_per_w, batched, u_mask)
+                    col = column and u_mask == 1
+                    built = build(g_per_w, batched, u_mask, col)
                     T.tabulate_mode = "batched" if batched else "per_state"
+                    if col:
+                        # the hoisted table is shared by a column only if the (x,w) part of its
+                        # states is the same; checked bit for bit on the built tables
+                        ok = self._column_w_part_ok(T, d, W, n_cols, positions(True)[5], positions(True)[4])
+                        if world > 1:
+                            ok = bool(min(coll.all_gather_object(ok)))
+                        if not ok:
+                            if col_mode == "on":
+                                raise ColumnHoistRefused("column_hoist='on' but the (x,w) part of the "
+                                                         "next state depends on state axis 0")
+                            col_refused[0] = True
+                            column = False
+                            built = None         # rebuild in C-order (layout BF)
+                    L = built
                 except tb.NotFactorable:
                     if compress == "on" or world > 1:
                         # (with several ranks a silent per-rank fallback would desynchronise the layouts)
@@ -880,12 +993,18 @@ class Engine(object):
                     if mode != "auto":
                         raise
                     batched = False      # not bit-identical to per-state calls
+                except ColumnHoistRefused as e:
+                    raise ValueError(str(e))
                 except Exception:
                     if not (batched and mode == "auto"):
                         raise
                     batched = False      # callables not vectorisable over states
             T.u_mask = u_mask
             T.g_per_w = g_per_w
+            col = column and u_mask == 1
+            T.column = col
+            T.n_cols, T.tiles_per_col = (n_cols, positions(True)[5]) if col else (0, 0)
+            U_eff = positions(col)[1]
             n_tiles, tile_U, tile_off = L["n_tiles"], L["tile_U"], L["tile_off"]
             entry_off, Upad, g_off, tile_g_off = L["entry_off"], L["Upad"], L["g_off"], L["tile_g_off"]
             lam_plane = L["lam_plane"]
@@ -895,9 +1014,13 @@ class Engine(object):
             # work items: one warp per run of at most `item_chunk` controls
             unit_U = tile_U if tiled else U
             chunk = self.item_chunk
+            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count if self._cuda else 148
             if self.item_chunk_auto:
-                # layout A walks 128 controls per warp iteration, layout B one
-                chunk = pick_item_chunk(unit_U, 128 if not tiled else 32)
+                # layout A walks 128 controls per warp iteration, layout B one; layout CF has one
+                # CTA per SM whose 16 warps share the items of a few column pieces: several
+                # rounds of items per piece keep the warps of a CTA level
+                chunk = pick_item_chunk(unit_U, 128 if not tiled else 32,
+                                        **({"target": sm_count * 16 * 48} if col else {}))
             T.item_chunk = chunk
             if tiled:
                 per_entry = Wf * 32
@@ -911,8 +1034,20 @@ class Engine(object):
             T.item_begin_host = item_begin
             T.unit_U_host = np.asarray(unit_U, dtype=np.int64)
             T.chunk_plan = None
-            T.items, T.item_begin = self.to_device_packed(
-                [items if n_items else np.zeros(1, dtype=_cabi.ITEM_DTYPE), item_begin])
+            up = [items if n_items else np.zeros(1, dtype=_cabi.ITEM_DTYPE), item_begin,
+                  U_eff.astype(np.int32) if len(U_eff) else np.zeros(1, dtype=np.int32)]
+            if col:
+                # one CTA per SM: the item list (ordered by tile, hence by column) is cut into
+                # runs of equal weight, so that a CTA meets few column changes
+                T.n_segs = max(1, min(sm_count * self.COLUMN_SEGS_PER_SM, n_items))
+                seg = partition_by_weight(items["u_count"].astype(np.float64) + 2.0, T.n_segs)
+                up.append(np.asarray(seg, dtype=np.int64))
+            else:
+                T.n_segs, T.seg_begin = 0, None
+            up = self.to_device_packed(up)
+            T.items, T.item_begin, T.U_dev = up[0], up[1], up[2]
+            if col:
+                T.seg_begin = up[3]
             n_part = max(n_items, 1) * (32 if tiled else 1)
             T.part_val = torch.empty(n_part, dtype=torch.float64, device=dev)
             T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)
@@ -922,7 +1057,12 @@ class Engine(object):
             return T
 
         # slabs balanced by admissible controls ...
-        bounds = partition_by_weight(U_all + 1, world) if world > 1 else [0, n_grid]
+        if world > 1 and col_candidate:
+            # whole rows of axis 0 per rank (layout CF); a row is 1/n_rows0 of the grid
+            row_w = (U_all + 1).reshape(n_rows0, n_cols).sum(axis=1)
+            bounds = [int(b) * n_cols for b in partition_by_weight(row_w, world)]
+        else:
+            bounds = partition_by_weight(U_all + 1, world) if world > 1 else [0, n_grid]
         override = getattr(solver, "_slab_override", None)
         if override is not None and world == 1:
             # developer experiments (scripts/dev_slab_chunks.py): the tables of ONE slab of
@@ -935,12 +1075,38 @@ class Engine(object):
         if world > 1 and self._cuda and balance != "controls" and \
                 (balance == "measured" or T.n_backups_total >= self.REBALANCE_MIN_BACKUPS):
             new_bounds = self._measured_bounds(T, U_all)
+            if new_bounds is not None and T.column:
+                new_bounds = row_aligned(new_bounds, n_cols)
+                if new_bounds == [int(b) for b in T.bounds]:
+                    new_bounds = None
             if new_bounds is not None:
                 T = build_for(new_bounds, T)
                 T.slab_recut = True
         self.sync()
         T.setup_seconds = time.perf_counter() - t0
         return T
+
+    COLUMN_SEGS_PER_SM = int(os.environ.get("SDP_COLUMN_SEGS_PER_SM", "1"))
+
+    def _column_w_part_ok(self, T, d, W, n_cols, tiles_per_col, valid):
+        """layout CF: True when, in every column, the (x,w) part of all real states -
+        partial cell index and weights of every perturbation node - is bit-identical to
+        that of the column's first row (the one the sweep kernel reads)"""
+        torch = _torch()
+        n_wp = n_cols * tiles_per_col * W * 32
+        live = torch.from_numpy(np.ascontiguousarray(valid.reshape(n_cols, tiles_per_col, 1, 32))).to(self.device)
+
+        def same(t):
+            v = t[:n_wp].view(n_cols, tiles_per_col, W, 32)
+            return bool(((v == v[:, :1, :, :1]) | ~live).all().item())
+
+        if not same(T.cell_w):
+            return False
+        for j in range(d - 1):
+            plane = T.lam_w[j * T.lam_w_plane:j * T.lam_w_plane + n_wp].view(torch.int64)
+            if not same(plane):
+                return False
+        return True
 
     def sweep_local(self, T, J_prev, events=None):
         """Enqueue K1 on this rank's slab.  J_prev: device fp64 [n_grid].
@@ -1014,7 +1180,7 @@ class Engine(object):
     OVERLAP_FRACTIONS = (0.45, 0.25, 0.15, 0.10, 0.05)
 
     def can_overlap_results(self, T):
-        return (self._cuda and self.coll.world == 1 and T.n_items >= self.OVERLAP_MIN_ITEMS
+        return (self._cuda and self.coll.world == 1 and not T.column and T.n_items >= self.OVERLAP_MIN_ITEMS
                 and T.n_backups_local >= self.OVERLAP_MIN_BACKUPS
                 and os.environ.get("SDP_OVERLAP", "1") != "0")
 

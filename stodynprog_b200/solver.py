@@ -59,6 +59,11 @@ class DPSolver(object):
         # "auto": keep the tables as a (x,u) part + a (x,w) part whenever dyn/cost
         # have that structure (every reference example does); "off": always dense
         self.table_compress = "auto"  # "auto" | "off" | "on"
+        # layout CF, column-shared hoist (include/sdp_b200.h): when state axis 0 alone follows
+        # the control and the (x,w) part of the next state does not depend on axis 0 (the
+        # storage examples), one CTA tabulates the inner interpolation once per column of
+        # the grid; "auto" follows SDP_COLUMN_HOIST, "on" raises if it does not apply
+        self.column_hoist = "auto"    # "auto" | "on" | "off"
         # several ranks: cut the grid into slabs of equal admissible controls ("controls"), or
         # re-cut once by the measured sweep time of every slab ("measured"; "auto" does so
         # for sweeps of at least 5e8 backups)
@@ -161,7 +166,8 @@ class DPSolver(object):
                 tuple(sig(g) for g in self.perturb_grid),
                 tuple(sig(p) for p in self.perturb_proba),
                 tuple(float(c) for c in self.control_steps),
-                self.table_layout, self.tabulate, self.table_compress, self.slab_balance)
+                self.table_layout, self.tabulate, self.table_compress, self.slab_balance,
+                getattr(self, "column_hoist", "auto"))
 
     def clear_tables(self):
         """drop the device-resident tables (call after mutating anything the

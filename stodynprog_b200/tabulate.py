@@ -314,10 +314,12 @@ def _eval_one_state(sys, x_k, host_tab, i, w_args, t_k, W):
 
 
 def tabulate_states(sys, states, host_tab, perturb_grid, t_k, entry_off, g_off, Upad, g_per_w,
-                    flush_fn, max_doubles=8 << 20, align=1):
+                    flush_fn, max_doubles=8 << 20, align=1, valid=None):
     """Second pass, per-state mode: call dyn/cost once per state exactly like
     the reference's hot loop and stage the un-broadcast outputs.
-    Raises GDependsOnW if a cost depends on w while `g_per_w` is 0."""
+    Raises GDependsOnW if a cost depends on w while `g_per_w` is 0.
+    `valid` (bool per entry of `states`, layout CF): False marks a padding position
+    that repeats a real state; its record gets U = 0 (no admissible control)."""
     d = len(sys.state)
     nb_control = len(sys.control)
     if nb_control > _cabi.SDP_MAX_C:
@@ -349,6 +351,8 @@ def tabulate_states(sys, states, host_tab, perturb_grid, t_k, entry_off, g_off, 
         recs["entry_off"] = entry_off[b0:b1]
         recs["g_off"] = g_off[b0:b1]
         recs["Upad"] = Upad[b0:b1]
+        if valid is not None:
+            recs["U"] = np.where(valid[b0:b1], recs["U"], 0)
         writer.add_descs(recs)
     writer.flush()
 
@@ -418,11 +422,17 @@ def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=
 
 def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid, t_k, entry_off,
                             g_off, Upad, g_per_w, flush_fn, chunk_states=4096,
-                            max_doubles=16 << 20, align=1, verify=8, grid_cache=None):
+                            max_doubles=16 << 20, align=1, verify=8, grid_cache=None,
+                            flat_index=None, valid=None):
     """Second pass, batched mode: one dyn/cost call per chunk of states.
     `verify` sample states of the first chunk are re-evaluated per state, the
     reference's way, and compared bit-for-bit; a mismatch raises
-    BatchedMismatch (the caller falls back to the per-state mode)."""
+    BatchedMismatch (the caller falls back to the per-state mode).
+    By default the states are [begin, end) of the C-order grid; `flat_index` gives
+    them explicitly instead (layout CF walks the grid column by column), with
+    `host_tab`, `entry_off`, ... indexed by position in that list, and `valid`
+    marking the real states (False: a padding position that repeats a real state and
+    gets U = 0)."""
     d = len(sys.state)
     nb_control = len(sys.control)
     if nb_control > _cabi.SDP_MAX_C:
@@ -431,13 +441,13 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
     w_args = tuple(perturb_grid)
     dims = [len(g) for g in state_grid]
     writer = _ChunkWriter(d, flush_fn, max_doubles, align)
-    n = end - begin
+    n = end - begin if flat_index is None else len(flat_index)
     chunk_states = max(align, chunk_states // align * align)
     checked = False
     for b0 in range(0, n, chunk_states):
         b1 = min(b0 + chunk_states, n)
         S = b1 - b0
-        flat = np.arange(begin + b0, begin + b1)
+        flat = np.arange(begin + b0, begin + b1) if flat_index is None else flat_index[b0:b1]
         idx = np.unravel_index(flat, dims)
         cols = [np.asarray(state_grid[k])[idx[k]] for k in range(d)]
         npts = host_tab.npts[b0:b1]
@@ -452,6 +462,8 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
         recs["npts"] = 1
         recs["npts"][:, :nb_control] = npts
         recs["U"] = npts.prod(axis=1) if nb_control else 1
+        if valid is not None:
+            recs["U"] = np.where(valid[b0:b1], recs["U"], 0)
         recs["entry_off"] = entry_off[b0:b1]
         recs["g_off"] = g_off[b0:b1]
         recs["Upad"] = Upad[b0:b1]

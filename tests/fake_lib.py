@@ -85,7 +85,7 @@ class FakeLib(object):
     def _staging(self, D, d, W, staging):
         top = 0
         for r in D:
-            U = int(r["U"])
+            U = max(int(r["U"]), 1)       # U = 0: a padding position of layout CF (only its w-part is read)
             for k in range(d + 1):
                 top = max(top, int(self._src_index(r, k, U, W).max()) + 1)
         return _arr(staging, top, ctypes.c_double)
@@ -278,14 +278,24 @@ class FakeLib(object):
         items = np.frombuffer((ctypes.c_uint8 * (T.n_items * _cabi.ITEM_DTYPE.itemsize))
                               .from_address(T.items), dtype=_cabi.ITEM_DTYPE)
         p = _arr(T.p, T.W, ctypes.c_double) if T.expect else np.ones(T.W)
-        tiled = T.layout in (_cabi.LAYOUT_STATE_MINOR, _cabi.LAYOUT_STATE_MINOR_FACTORED)
-        factored = T.layout in (_cabi.LAYOUT_CONTROL_MINOR_FACTORED, _cabi.LAYOUT_STATE_MINOR_FACTORED)
+        column = T.layout == _cabi.LAYOUT_COLUMN_FACTORED
+        tiled = column or T.layout in (_cabi.LAYOUT_STATE_MINOR, _cabi.LAYOUT_STATE_MINOR_FACTORED)
+        factored = column or T.layout in (_cabi.LAYOUT_CONTROL_MINOR_FACTORED, _cabi.LAYOUT_STATE_MINOR_FACTORED)
         n_u = bin(T.u_mask).count("1")
         width = 32 if tiled else 1
         pv = _arr(part_val, T.n_items * width, ctypes.c_double)
         pi = _arr(part_idx, T.n_items * width, ctypes.c_int32)
-        Us = _arr(T.U, T.n_states, ctypes.c_int32)
         W = T.W
+        n_pos = T.n_states        # entries of U: states, or (layout CF) positions incl. padding lanes
+        if column:
+            assert T.u_mask == 1 and T.n_states % T.n_cols == 0
+            assert T.tiles_per_col == (T.n_states // T.n_cols + 31) // 32
+            n_pos = T.n_cols * T.tiles_per_col * 32
+            # every CTA segment is a run of the item list; together they cover it once
+            seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
+            assert seg[0] == 0 and seg[-1] == T.n_items and np.all(np.diff(seg) >= 0)
+            assert np.all(np.diff(items["state"]) >= 0)          # ordered by tile, hence by column
+        Us = _arr(T.U, n_pos, ctypes.c_int32)
 
         def lerp(c, lam):
             def rec(base, k):
@@ -328,14 +338,21 @@ class FakeLib(object):
                 acc = np.zeros((cnt, 32))
                 for w in range(W):
                     f = (tix * W + w) * 32
-                    cw = _arr(T.cell_w + 4 * f, 32, ctypes.c_int32).astype(np.int64)[None, :]
-                    lw = [_arr(T.lam_w + 8 * (j * T.lam_w_plane + f), 32, ctypes.c_double)[None, :]
-                          for j in range(d - n_u)]
+                    if column:
+                        # the kernel reads the column's w-part at lane 0 of its first tile
+                        f0 = ((tix // T.tiles_per_col) * T.tiles_per_col * W + w) * 32
+                        cw = _arr(T.cell_w + 4 * f0, 1, ctypes.c_int32).astype(np.int64)[None, :]
+                        lw = [_arr(T.lam_w + 8 * (j * T.lam_w_plane + f0), 1, ctypes.c_double)[None, :]
+                              for j in range(d - n_u)]
+                    else:
+                        cw = _arr(T.cell_w + 4 * f, 32, ctypes.c_int32).astype(np.int64)[None, :]
+                        lw = [_arr(T.lam_w + 8 * (j * T.lam_w_plane + f), 32, ctypes.c_double)[None, :]
+                              for j in range(d - n_u)]
                     jg = Gv + lerp(cu + cw, self._merge(T, d, lu, lw))
                     acc = acc + jg * p[w] if T.expect else jg
                 for lane in range(32):
                     s_i = tix * 32 + lane
-                    n_ok = max(0, min(cnt, (int(Us[s_i]) if s_i < T.n_states else 0) - ub))
+                    n_ok = max(0, min(cnt, (int(Us[s_i]) if s_i < n_pos else 0) - ub))
                     if n_ok == 0:
                         pv[n_it * 32 + lane], pi[n_it * 32 + lane] = np.inf, 2 ** 31 - 1
                     else:
@@ -377,13 +394,16 @@ class FakeLib(object):
                     else:
                         j = first_min(acc[:n_ok, lane])
                         pv[n_it * 32 + lane], pi[n_it * 32 + lane] = acc[j, lane], ub + j
-        n_units = (T.n_states + 31) // 32 if tiled else T.n_states
+        n_units = (n_pos + 31) // 32 if tiled else T.n_states
         ib = _arr(T.item_begin, n_units + 1, ctypes.c_int64)
         Jo = _arr(J_out, T.n_states, ctypes.c_double)
         ao = _arr(argmin_out, T.n_states, ctypes.c_int32)
         for i in range(T.n_states):
             bv, bi = np.inf, 2 ** 31 - 1
             unit, lane = (i // 32, i % 32) if tiled else (i, 0)
+            if column:
+                row, c = divmod(i, T.n_cols)
+                unit, lane = c * T.tiles_per_col + row // 32, row % 32
             for k in range(ib[unit], ib[unit + 1]):
                 kk = k * width + lane
                 if _better(pv[kk], int(pi[kk]), bv, bi):

@@ -23,6 +23,20 @@ def _free_port():
     return p
 
 
+def _problem(sdp, wl, lib, layout):
+    """the sharded test problem: storage + AR(1) on a 9 x 11 grid, or - layout CF, which
+    needs slabs of whole rows of axis 0 and at least 32 rows per rank - on a 70 x 5 grid"""
+    if layout == "column":
+        prob = wl.storage_ar1(sdp, n_E=70, n_P=5, n_w=3, steps=(0.5, 0.1), _test_lib=lib)
+        prob.solver.table_layout = "state_minor"
+        prob.solver.column_hoist = "on"
+    else:
+        prob = wl.storage_ar1(sdp, n_E=9, n_P=11, steps=(0.01, 0.1), _test_lib=lib)
+        prob.solver.table_layout = layout
+    J0 = np.random.default_rng(0).standard_normal(prob.solver._state_grid_shape)
+    return prob, prob.solver, J0
+
+
 def _worker(rank, world, port, out_dir, layout):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -33,12 +47,10 @@ def _worker(rank, world, port, out_dir, layout):
         import stodynprog_b200 as sdp
         from stodynprog_b200 import workloads as wl
         from fake_lib import FakeLib
-        prob = wl.storage_ar1(sdp, n_E=9, n_P=11, steps=(0.01, 0.1), _test_lib=FakeLib())
-        sv = prob.solver
-        sv.table_layout = layout
-        J0 = np.random.default_rng(0).standard_normal((9, 11))
+        prob, sv, J0 = _problem(sdp, wl, FakeLib(), layout)
         J1, pol1 = sv.value_iteration(J0, report_time=False)
         T = sv.last_tables
+        assert T.column == (layout == "column")
         (Jd, Jr), pol2 = sv.value_iteration((J1 - J1[sv._state_ref_ind], 0.), rel_dp=True, report_time=False)
         Je, ref = sv.eval_policy(pol1, 6, rel_dp=True, report_time=False)
         Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=3, tol=0.0)
@@ -64,7 +76,7 @@ def _worker(rank, world, port, out_dir, layout):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("layout", ["control_minor", "state_minor"])
+@pytest.mark.parametrize("layout", ["control_minor", "state_minor", "column"])
 def test_sharded_sweep_world2_matches_single_process(tmp_path, layout):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), layout), nprocs=world, join=True)
@@ -75,10 +87,7 @@ def test_sharded_sweep_world2_matches_single_process(tmp_path, layout):
     import stodynprog_b200 as sdp
     from stodynprog_b200 import workloads as wl
     from fake_lib import FakeLib
-    prob = wl.storage_ar1(sdp, n_E=9, n_P=11, steps=(0.01, 0.1), _test_lib=FakeLib())
-    sv = prob.solver
-    sv.table_layout = layout
-    J0 = np.random.default_rng(0).standard_normal((9, 11))
+    prob, sv, J0 = _problem(sdp, wl, FakeLib(), layout)
     J1, pol1 = sv.value_iteration(J0, report_time=False)
     (Jd, Jr), pol2 = sv.value_iteration((J1 - J1[sv._state_ref_ind], 0.), rel_dp=True, report_time=False)
     Je, ref = sv.eval_policy(pol1, 6, rel_dp=True, report_time=False)
@@ -93,8 +102,11 @@ def test_sharded_sweep_world2_matches_single_process(tmp_path, layout):
         assert np.array_equal(r[k]["resid"], np.array(info["residuals"]))
     # the slabs are contiguous, disjoint, cover the grid and are balanced by controls
     b = r[0]["bounds"]
-    assert list(b) == list(r[1]["bounds"]) and b[0] == 0 and b[-1] == 99
-    assert int(r[0]["n_local"]) + int(r[1]["n_local"]) == 99
+    n_grid = J0.size
+    assert list(b) == list(r[1]["bounds"]) and b[0] == 0 and b[-1] == n_grid
+    assert int(r[0]["n_local"]) + int(r[1]["n_local"]) == n_grid
+    if layout == "column":
+        assert b[1] % J0.shape[1] == 0          # whole rows of axis 0 per rank
     assert int(r[0]["backups"]) + int(r[1]["backups"]) == int(r[0]["total"])
     assert abs(int(r[0]["backups"]) - int(r[1]["backups"])) / int(r[0]["total"]) < 0.1
 

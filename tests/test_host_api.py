@@ -339,8 +339,9 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SdpStateDesc), offsetof(SdpStateDesc, src),
          offsetof(SdpStateDesc, cs), offsetof(SdpStateDesc, ws), offsetof(SdpStateDesc, npts),
          offsetof(SdpStateDesc, U), offsetof(SdpStateDesc, Upad), sizeof(SdpItem));
-  printf("%zu %zu %zu %zu %zu\\n", sizeof(SdpTables), offsetof(SdpTables, p), offsetof(SdpTables, n_items),
-         offsetof(SdpTables, U), sizeof(SdpGrid));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SdpTables), offsetof(SdpTables, p), offsetof(SdpTables, n_items),
+         offsetof(SdpTables, U), sizeof(SdpGrid), offsetof(SdpTables, p_host), offsetof(SdpTables, n_cols),
+         offsetof(SdpTables, seg_begin), offsetof(SdpTables, n_segs));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
@@ -351,7 +352,32 @@ int main(void) {
                                             D.fields["Upad"][1], _cabi.ITEM_DTYPE.itemsize]
     T = _cabi.SdpTables
     assert [int(x) for x in l2.split()] == [ctypes.sizeof(T), T.p.offset, T.n_items.offset, T.U.offset,
-                                            ctypes.sizeof(_cabi.SdpGrid)]
+                                            ctypes.sizeof(_cabi.SdpGrid), T.p_host.offset, T.n_cols.offset,
+                                            T.seg_begin.offset, T.n_segs.offset]
+    hdr = open(os.path.join(ROOT, "include", "sdp_b200.h")).read()
+    for name in ("SDP_ABI_VERSION", "SDP_LAYOUT_COLUMN_FACTORED", "SDP_FACTORED_MAX_W_REG"):
+        val = int(re.search(r"#define %s (\d+)" % name, hdr).group(1))
+        assert val == getattr(_cabi, name.replace("SDP_LAYOUT_", "LAYOUT_").replace("SDP_FACTORED", "FACTORED"))
+    assert _cabi.COLUMN_MAX_SMEM_BYTES == 200 * 1024 and "SDP_COLUMN_MAX_SMEM_BYTES (200 * 1024)" in hdr
+
+
+def test_column_order_and_row_aligned_bounds():
+    """layout CF walks a slab of whole rows column by column, every column padded to
+    whole tiles of 32 rows; slab boundaries are moved to whole rows"""
+    from stodynprog_b200.engine import column_order, row_aligned
+    order, valid, tiles = column_order(70 * 5, 5)
+    assert tiles == 3 and len(order) == 5 * 96 and valid.sum() == 350
+    assert sorted(order[valid]) == list(range(350))              # every state exactly once
+    o = order.reshape(5, 96)
+    v = valid.reshape(5, 96)
+    for c in range(5):
+        assert list(o[c, :70]) == [r * 5 + c for r in range(70)]   # lane <-> row of the column
+        assert np.all(o[c, 70:] == 69 * 5 + c) and not v[c, 70:].any() and v[c, :70].all()
+    order, valid, tiles = column_order(64 * 3, 3)
+    assert tiles == 2 and valid.all() and len(order) == 192
+    assert row_aligned([0, 103, 251, 350], 5) == [0, 105, 250, 350]
+    assert row_aligned([0, 2, 3, 350], 5) == [0, 0, 5, 350]
+    assert row_aligned([0, 349, 350], 5) == [0, 350, 350]
 
 
 def test_no_cpu_fallback(product):

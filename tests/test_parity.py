@@ -694,6 +694,159 @@ def test_hoisted_inner_interpolation_is_bit_identical(product, which):
         assert np.array_equal(pol, polr, equal_nan=True), key
 
 
+# ---------------------------------------------------------------------------
+# layout CF (column-shared hoist): BF tables over column-major tiles, one inner-
+# interpolation table per column of the grid - bit-identical to layout BF
+# ---------------------------------------------------------------------------
+def _coupled_w_system(api, n0=40, **kw):
+    """u_mask == 1, but the perturbed coordinate also depends on state axis 0: the
+    (x,w) part varies along a column, so layout CF must be refused"""
+    import scipy.stats as stats
+
+    def dyn(x0, x1, u, w):
+        return (0.9 * x0 + 0.5 * u, 0.7 * x1 + 0.05 * x0 + w)
+
+    def box(x0, x1):
+        return ((-1.0, 1.0 + 0.1 * x0),)
+
+    def cost(x0, x1, u, w):
+        return x0 ** 2 + x1 ** 2 + 0.1 * u ** 2
+
+    sys = api.SysDescription((2, 1, 1), name='coupled w')
+    sys.dyn, sys.control_box, sys.cost = dyn, box, cost
+    sys.perturb_laws = [stats.norm(0, 0.3)]
+    sv = api.DPSolver(sys, **kw)
+    sv.discretize_state(-1.0, 2.0, n0, -1.0, 1.0, 5)
+    sv.discretize_perturb(-0.9, 0.9, 5)
+    sv.control_steps = (0.25,)
+    return sv
+
+
+def _column_case(api, which):
+    from stodynprog_b200 import workloads as wl
+    if which.startswith("ar1_w"):
+        # 70 rows: 3 tiles per column, the last one with 26 padding lanes; control step 0.5 =
+        # 3.5 grid rows; W = 9, 5, 3 fill the unrolled slots, W = 7, 4, 2 leave idle ones
+        return wl.storage_ar1(api, n_E=70, n_P=5, n_w=int(which[5:]), steps=(0.5, 0.1)).solver
+    if which == "ar1_exact_tiles":
+        return wl.storage_ar1(api, n_E=64, n_P=3, n_w=3, steps=(0.25, 0.1)).solver
+    if which == "searev":                       # d = 3: a column is a (speed, acceleration) pair
+        prob = wl.searev(api, n_E=33, n_S=4, n_A=3)
+        prob.solver.control_steps = (.05,)
+        return prob.solver
+    if which == "curtail":                      # two controls, ragged in both axes
+        sv = _two_control_system(api)
+        sv.discretize_state(0, 10., 35, -4, 4, 4)
+        return sv
+    raise KeyError(which)
+
+
+COLUMN_CASES = ["ar1_w9", "ar1_w7", "ar1_w5", "ar1_w4", "ar1_w3", "ar1_w2", "ar1_exact_tiles",
+                "searev", "curtail"]
+
+
+@pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
+@pytest.mark.parametrize("which", COLUMN_CASES)
+def test_column_hoist_is_bit_identical(product, backend, which):
+    """layout CF against layout BF (same factored entries, states walked column by column,
+    the inner interpolation tabulated once per column): J and policies bit for bit, NaN
+    and infinities in J included; item chunking does not matter"""
+    if backend == "model" and which in ("ar1_w7", "ar1_w5", "ar1_w4", "ar1_w2"):
+        pytest.skip("the numpy model does not depend on W; covered on the GPU")
+    ref = _column_case(_Api(product, backend, "state_minor", "auto", "on"), which)
+    ref.column_hoist = "off"
+    col = _column_case(_Api(product, backend, "state_minor", "auto", "on"), which)
+    col.column_hoist = "on"
+    J0 = np.random.default_rng(11).standard_normal(ref._state_grid_shape)
+    for sweep in range(3):
+        Jr, polr = ref.value_iteration(J0, report_time=False)
+        Jc, polc = col.value_iteration(J0, report_time=False)
+        Tr, Tc = ref.last_tables, col.last_tables
+        assert Tr.layout_name == "state_minor_factored" and Tc.layout_name == "column_factored"
+        assert Tc.n_backups_local == Tr.n_backups_local and Tc.u_mask == 1
+        assert np.array_equal(Jr.view(np.int64), Jc.view(np.int64)), sweep
+        assert np.array_equal(polr, polc, equal_nan=True), sweep
+        J0 = Jr.copy()
+        if sweep == 1:                          # special values travel through the table too
+            J0.reshape(-1)[::7] = np.nan
+            J0.reshape(-1)[3::11] = np.inf
+    if backend == "cuda":
+        # CTA size, controls per iteration and work-item length do not change a bit
+        lib = col.engine.lib
+        try:
+            for threads, ub in ((128, 1), (256, 2), (512, 1)):
+                lib.sdp_set_option(b"col_threads", threads)
+                lib.sdp_set_option(b"col_ub", ub)
+                J2, pol2 = col.value_iteration(J0, report_time=False)
+                Jr, polr = ref.value_iteration(J0, report_time=False)
+                assert np.array_equal(Jr.view(np.int64), J2.view(np.int64)), (threads, ub)
+                assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub)
+        finally:
+            lib.sdp_set_option(b"col_threads", 512)
+            lib.sdp_set_option(b"col_ub", 2)
+
+
+@pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
+def test_column_hoist_solvers_and_chunking(product, backend):
+    """the other drivers on top of layout CF: relative DP, policy iteration, the
+    device-resident loop; explicit work-item lengths"""
+    from stodynprog_b200 import workloads as wl
+    out = []
+    for colmode, chunk in (("off", None), ("on", None), ("on", 4), ("on", 512)):
+        api = _Api(product, backend, "state_minor", "auto", "on")
+        prob = wl.storage_ar1(api, n_E=40, n_P=4, n_w=5, steps=(0.5, 0.1), item_chunk=chunk)
+        sv = prob.solver
+        sv.column_hoist = colmode
+        J0 = np.random.default_rng(2).standard_normal(sv._state_grid_shape)
+        J0[sv._state_ref_ind] = 0.
+        (Jd, Jref), pol = sv.value_iteration((J0, 0.), rel_dp=True, report_time=False)
+        assert sv.last_tables.column == (colmode == "on")
+        (Jp, Jpr), polp = sv.policy_iteration(prob.initial_policy(), 5, 2, rel_dp=True)
+        Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=3, tol=0.0)
+        out.append((Jd, Jref, pol, Jp, Jpr, polp, Js, pols, np.array(info["residuals"])))
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert np.array_equal(np.asarray(a).view(np.int64), np.asarray(b).view(np.int64))
+
+
+def test_column_hoist_is_refused_when_it_does_not_apply(product):
+    """a w-part that varies along a column is detected on the built tables: "auto" falls
+    back to layout BF (same results), "on" raises; so do grids or layouts CF cannot take"""
+    import stodynprog_b200.engine as engine_mod
+    ref = _coupled_w_system(_Api(product, "model", "state_minor", "auto", "on"))
+    ref.column_hoist = "off"
+    auto = _coupled_w_system(_Api(product, "model", "state_minor", "auto", "on"))
+    saved = engine_mod.COLUMN_HOIST_DEFAULT
+    engine_mod.COLUMN_HOIST_DEFAULT = True
+    try:
+        J0 = np.random.default_rng(4).standard_normal(ref._state_grid_shape)
+        Jr, polr = ref.value_iteration(J0, report_time=False)
+        Ja, pola = auto.value_iteration(J0, report_time=False)
+        assert auto.last_tables.layout_name == "state_minor_factored"     # refused, rebuilt as BF
+        assert np.array_equal(Jr.view(np.int64), Ja.view(np.int64)) and np.array_equal(polr, pola)
+        # ... and "auto" takes it when it applies
+        ok = _column_case(_Api(product, "model", "state_minor", "auto", "on"), "ar1_exact_tiles")
+        assert ok.sweep_tables().layout_name == "column_factored"
+    finally:
+        engine_mod.COLUMN_HOIST_DEFAULT = saved
+    forced = _coupled_w_system(_Api(product, "model", "state_minor", "auto", "on"))
+    forced.column_hoist = "on"
+    with pytest.raises(ValueError):
+        forced.sweep_tables()
+    few_rows = _coupled_w_system(_Api(product, "model", "state_minor", "auto", "on"), n0=20)
+    few_rows.column_hoist = "on"
+    with pytest.raises(ValueError):
+        few_rows.sweep_tables()
+    wrong_layout = _column_case(_Api(product, "model", "control_minor", "auto", "on"), "ar1_exact_tiles")
+    wrong_layout.column_hoist = "on"
+    with pytest.raises(ValueError):
+        wrong_layout.sweep_tables()
+    bad = _column_case(_Api(product, "model", "state_minor", "auto", "on"), "ar1_exact_tiles")
+    bad.column_hoist = "sometimes"
+    with pytest.raises(ValueError):
+        bad.sweep_tables()
+
+
 def test_unfactorable_systems_fall_back_to_dense(product):
     """a coordinate that spans controls AND perturbation, or a cost that depends
     on w, keeps the dense tables in "auto" mode and is refused in "on" mode"""
