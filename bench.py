@@ -190,6 +190,9 @@ def kernel_name(T):
     with u_mask == 1)"""
     d = T.d
     if T.factored:
+        if T.column:
+            return "k_sweep_fact_column<%d,%d,2,%s>" % (d, 3 if T.W <= 3 else (5 if T.W <= 5 else 9),
+                                                        "true" if T.W in (3, 5, 9) else "false")
         if T.tiled:
             return "k_sweep_fact_tiled<%d,%d,%d>" % (d, T.u_mask, 3 if T.W <= 3 else (5 if T.W <= 5 else 9))
         if T.u_mask == 1:
@@ -252,7 +255,14 @@ def roofline_of(T, k1_ms, ms_total, K, peak, peak_src, traffic):
          "streamed_GBs": T.device_bytes / (k1 * 1e-3) / 1e9}
     if len(ncu) > 1:
         r["ncu"] = {k: v for k, v in ncu.items() if k != "traffic"}
-    if T.factored:
+    if T.column:
+        r["note"] = ("column-shared hoist over factored (x,u)+(x,w) tables: the kernel streams %.2f B "
+                     "per backup instead of the dense layout's %.2f B and reads the inner "
+                     "interpolation from a per-column table in shared memory, so `achieved` (dense "
+                     "algorithmic bytes / time, SURVEY.md 8d) exceeds the HBM peak; bound by shared-"
+                     "memory wavefronts / the fp64 pipe, see `dense_layout` for the HBM-bound kernel "
+                     "on the same workload" % (T.streamed_bytes_per_backup, b_alg))
+    elif T.factored:
         r["note"] = ("factored (x,u)+(x,w) tables: the kernel streams %.2f B per backup instead of "
                      "the dense layout's %.2f B, so `achieved` (dense algorithmic bytes / time, "
                      "SURVEY.md 8d) exceeds the HBM peak; the kernel is bound by the L1 wavefronts "
@@ -291,6 +301,7 @@ def run_ours(args):
     if args.layout != "auto":
         sv.table_layout = args.layout
     sv.table_compress = args.compress
+    sv.column_hoist = args.column_hoist
     if args.item_chunk:
         sv._item_chunk = args.item_chunk
     eng = sv.engine
@@ -393,6 +404,7 @@ def run_ours(args):
     dense = None
     if T.factored and not args.no_dense:
         sv.table_compress = "off"
+        sv.column_hoist = "off"
         Td = sv.sweep_tables()
         Ja, Jb = eng.J_pair(n_grid)
         eng.begin_call(n_grid)
@@ -410,6 +422,7 @@ def run_ours(args):
                  "roofline": roofline_of(Td, k1_d, ms_d, Kd, peak, peak_src,
                                          ncu_traffic(args.workload, Td, world))}
         sv.table_compress = args.compress
+        sv.column_hoist = args.column_hoist
         del Td
         sv.clear_tables()
         torch.cuda.empty_cache()
@@ -509,6 +522,8 @@ def main():
     ap.add_argument("--layout", default="auto", choices=["auto", "control_minor", "state_minor"])
     ap.add_argument("--compress", default="auto", choices=["auto", "off", "on"],
                     help="factored (x,u)+(x,w) tables (auto: whenever the system allows)")
+    ap.add_argument("--column-hoist", dest="column_hoist", default="auto", choices=["auto", "on", "off"],
+                    help="layout CF, one inner-interpolation table per grid column (auto: SDP_COLUMN_HOIST)")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-layout sub-measurement")
     ap.add_argument("--item-chunk", dest="item_chunk", type=int, default=0)
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=None,

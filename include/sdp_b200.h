@@ -108,12 +108,12 @@ typedef struct SdpItem {
  * does not depend on the axis-0 index (the storage examples: P_next = a*P + w does
  * not involve E).  The inner interpolation R(row, w) over the axes 1..d-1 is then
  * the same for all the states of a column: one CTA tabulates it once per column in
- * shared memory ((order[0]+1)*W doubles) and every backup of the column is two
+ * shared memory (order[0] rows of W|1 doubles) and every backup of the column is two
  * shared-memory reads and one lerp instead of 2^d gathers and 2^d-1 lerps - the
  * operations of the reference's nested formula, evaluated once instead of once per
  * (state, control).  Bit-identical to the other layouts. */
 #define SDP_LAYOUT_COLUMN_FACTORED 4
-#define SDP_COLUMN_MAX_SMEM_BYTES (200 * 1024) /* CF: ((order[0]+1)*W + 9) * 8 must fit */
+#define SDP_COLUMN_MAX_SMEM_BYTES (200 * 1024) /* CF: (order[0]*(W|1) + 9) * 8 must fit */
 
 /* Dense sweep tables of one shard of states (device pointers).
  *
@@ -199,6 +199,7 @@ int64_t sdp_launch_count(void);
  * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4),
  * "hoist_const" (0|1: constant-W variant of that kernel for W <= 9),
  * "col_threads" (layout CF: threads per CTA, 128..512), "col_ub" (controls per iteration, 1|2),
+ * "col_pf" (groups of col_ub controls in flight, 1|2),
  * "p2p_timeout_s" (bound of the peer-flag waits, default 600 s, then the kernel traps).
  * Not thread-safe against concurrent launches. */
 int sdp_set_option(const char* name, int value);

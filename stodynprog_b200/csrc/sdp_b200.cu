@@ -1050,6 +1050,7 @@ struct Tuning {
     int hoist_const;   // layout AF hoisted kernel: constant-W variant for W <= 9 (1) or the runtime-W kernel (0)
     int col_threads;   // layout CF: threads per CTA (one CTA per SM: the column table fills shared memory)
     int col_ub;        // layout CF: controls per lane per iteration (1|2)
+    int col_pf;        // layout CF: groups of col_ub controls in flight per lane (1|2)
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static int env_int(const char* name, int dflt) {
@@ -1082,6 +1083,7 @@ static Tuning& tuning() {
         x.hoist_const = env_int("SDP_HOIST_CONST", 1) != 0;
         x.col_threads = clampi(env_int("SDP_COL_THREADS", 512), 128, 512) / 32 * 32;
         x.col_ub = env_int("SDP_COL_UB", 2) == 1 ? 1 : 2;
+        x.col_pf = env_int("SDP_COL_PF", 2) == 1 ? 1 : 2;
         return x;
     }();
     return t;
@@ -1102,6 +1104,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "hoist_const")) t.hoist_const = value != 0;
     else if (!strcmp(name, "col_threads")) t.col_threads = clampi(value, 128, 512) / 32 * 32;
     else if (!strcmp(name, "col_ub")) t.col_ub = (value == 1) ? 1 : 2;
+    else if (!strcmp(name, "col_pf")) t.col_pf = (value == 1) ? 1 : 2;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1735,25 +1738,27 @@ static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, cons
 // CTA therefore tabulates R for every row of the grid once per column
 // (order[0]*W inner lerps - the very operations every backup of the column would
 // repeat) and then sweeps the column's tiles, lane <-> row: a backup is two
-// shared-memory reads and one lerp.  Adjacent lanes are adjacent rows, so with W = 9
-// the 72-byte row pitch spreads a half-warp's 8-byte reads over all 32 banks.
+// shared-memory reads and one lerp.  Adjacent lanes are adjacent rows, and the row
+// pitch is an odd number of doubles (W | 1), so a half-warp's 8-byte reads spread over
+// all 32 banks.
 //
 // Work split: the item list is ordered by tile, hence by column; the host cuts it
 // into n_segs runs of equal weight, one per CTA (one CTA per SM: the table fills
 // shared memory), so a CTA meets few column changes.  Warps take the items of the
 // current column round-robin.  Partial minima have the layout of BF.
 // ---------------------------------------------------------------------------
-template <int D, int WM, int UB, bool FULL>       // FULL: W == WM, every slot live
+template <int D, int WM, int UB, int PF, bool FULL>     // FULL: W == WM, every slot live
 __global__ void __launch_bounds__(512, 1)
 k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
                     double* __restrict__ part_val, int32_t* __restrict__ part_idx,
                     double inv_stride0, PVals PV) {
     constexpr int NW = D - 1;
     extern __shared__ __align__(16) unsigned char csm[];
-    double* R_sh = reinterpret_cast<double*>(csm);      // [order[0]][W] (+ WM doubles of slack)
+    double* R_sh = reinterpret_cast<double*>(csm);      // [order[0]][P] (+ WM doubles of slack)
     __shared__ int cw_sh[WM];
     __shared__ double lw_sh[NW][WM];
     const int W = T.W;
+    const int P = W | 1;        // odd row pitch: adjacent rows never share a bank pair
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int rows = G.order[0];
     const int stride0 = G.stride[0];
@@ -1779,7 +1784,7 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
             lam[0] = 0.0;
 #pragma unroll
             for (int k = 0; k < NW; ++k) lam[k + 1] = lw_sh[k][w];
-            R_sh[idx] = Lerp<double, D, 1>::eval(Jprev, r * stride0 + cw_sh[w], G.stride, lam);
+            R_sh[r * P + w] = Lerp<double, D, 1>::eval(Jprev, r * stride0 + cw_sh[w], G.stride, lam);
         }
         __syncthreads();
 
@@ -1793,57 +1798,69 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
             int best_i = INT_MAX;
             const int last = it.u_count - 1;
 
-            // group of UB controls, streamed one group ahead (rows past the run repeat its last row)
-            int c_n[UB];
-            double g_n[UB], l_n[UB];
+            // PF groups of UB controls are in flight: group k of the run sits in stage k % PF
+            // (rows past the run repeat its last row)
+            int c_n[PF][UB];
+            double g_n[PF][UB], l_n[PF][UB];
 #pragma unroll
-            for (int b = 0; b < UB; ++b) {
-                const int64_t o = (int64_t)min(b, last) * 32;
-                c_n[b] = __ldcs(cup + o);
-                g_n[b] = __ldcs(gp + o);
-                l_n[b] = __ldcs(lup + o);
-            }
-            for (int uu = 0; uu < it.u_count; uu += UB) {
-                double gv[UB], lu[UB], oml[UB];
-                const double* Ra[UB];
+            for (int s = 0; s < PF; ++s)
 #pragma unroll
                 for (int b = 0; b < UB; ++b) {
-                    gv[b] = g_n[b];
-                    lu[b] = l_n[b];
-                    oml[b] = sub_(1.0, lu[b]);
-                    // row q0 = cell_u / stride0 exactly (cell_u is a multiple of stride0 below 2^31;
-                    // padding entries hold cell 0)
-                    const int q = __double2int_rn(__dmul_rn((double)c_n[b], inv_stride0));
-                    Ra[b] = R_sh + q * W;
+                    const int64_t o = (int64_t)min(s * UB + b, last) * 32;
+                    c_n[s][b] = __ldcs(cup + o);
+                    g_n[s][b] = __ldcs(gp + o);
+                    l_n[s][b] = __ldcs(lup + o);
                 }
-                if (uu + UB < it.u_count) {
+            for (int uu0 = 0; uu0 < it.u_count; uu0 += UB * PF) {
 #pragma unroll
-                    for (int b = 0; b < UB; ++b) {
-                        const int64_t o = (int64_t)min(uu + UB + b, last) * 32;
-                        c_n[b] = __ldcs(cup + o);
-                        g_n[b] = __ldcs(gp + o);
-                        l_n[b] = __ldcs(lup + o);
+                for (int s = 0; s < PF; ++s) {
+                    const int uu = uu0 + s * UB;
+                    if (uu < it.u_count) {                    // warp-uniform
+                        double gv[UB], lu[UB], oml[UB];
+                        const double* Ra[UB];
+#pragma unroll
+                        for (int b = 0; b < UB; ++b) {
+                            gv[b] = g_n[s][b];
+                            lu[b] = l_n[s][b];
+                            oml[b] = sub_(1.0, lu[b]);
+                            // row q0 = cell_u / stride0 exactly (cell_u is a multiple of stride0
+                            // below 2^31; padding entries hold cell 0)
+                            const int q = __double2int_rn(__dmul_rn((double)c_n[s][b], inv_stride0));
+                            Ra[b] = R_sh + q * P;
+                        }
+                        if (uu + UB * PF < it.u_count) {
+#pragma unroll
+                            for (int b = 0; b < UB; ++b) {
+                                const int64_t o = (int64_t)min(uu + UB * PF + b, last) * 32;
+                                c_n[s][b] = __ldcs(cup + o);
+                                g_n[s][b] = __ldcs(gp + o);
+                                l_n[s][b] = __ldcs(lup + o);
+                            }
+                        }
+                        // slots >= W read past the W live values of a row (its pad, the next row,
+                        // or the slack behind the table) and are discarded below: no guards
+                        double v[UB][WM];
+#pragma unroll
+                        for (int b = 0; b < UB; ++b)
+#pragma unroll
+                            for (int w = 0; w < WM; ++w)
+                                v[b][w] = add_(mul_(oml[b], Ra[b][w]), mul_(lu[b], Ra[b][P + w]));
+#pragma unroll
+                        for (int b = 0; b < UB; ++b) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int w = 0; w < WM; ++w) {
+                                const double jg = add_(gv[b], v[b][w]);
+                                const double nxt = T.expect ? add_(acc, mul_(jg, PV.v[w])) : jg;
+                                acc = (FULL || w < W) ? nxt : acc;   // slots past W do not take part
+                            }
+                            const int u = it.u_begin + uu + b;
+                            if (uu + b <= last && u < Us && better(acc, u, best_v, best_i)) {
+                                best_v = acc;
+                                best_i = u;
+                            }
+                        }
                     }
-                }
-                // slots >= W read past the W live values of a row (the next row, or the slack
-                // behind the table) and are discarded below: no guards on the reads
-                double v[UB][WM];
-#pragma unroll
-                for (int b = 0; b < UB; ++b)
-#pragma unroll
-                    for (int w = 0; w < WM; ++w)
-                        v[b][w] = add_(mul_(oml[b], Ra[b][w]), mul_(lu[b], Ra[b][W + w]));
-#pragma unroll
-                for (int b = 0; b < UB; ++b) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int w = 0; w < WM; ++w) {
-                        const double jg = add_(gv[b], v[b][w]);
-                        const double nxt = T.expect ? add_(acc, mul_(jg, PV.v[w])) : jg;
-                        acc = (FULL || w < W) ? nxt : acc;   // slots past W do not take part
-                    }
-                    const int u = it.u_begin + uu + b;
-                    if (uu + b <= last && u < Us && better(acc, u, best_v, best_i)) { best_v = acc; best_i = u; }
                 }
             }
             part_val[item_id * 32 + lane] = best_v;
@@ -1853,18 +1870,18 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
     }
 }
 
-template <int D, int WM, int UB>
+template <int D, int WM, int UB, int PF>
 static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                                 double* part_val, int32_t* part_idx, cudaStream_t st) {
-    const size_t shm = ((size_t)G.order[0] * T.W + WM) * 8;
+    const size_t shm = ((size_t)G.order[0] * (T.W | 1) + WM) * 8;
     if (shm > SDP_COLUMN_MAX_SMEM_BYTES)
         return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF: the column table does not fit shared memory");
     static size_t attr_set = 0;          // per instantiation
     if (attr_set < shm) {
-        cudaError_t e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, true>,
+        cudaError_t e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, false>,
+            e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
         if (e != cudaSuccess) return fail(SDP_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = shm;
@@ -1874,27 +1891,32 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
         pv.v[w] = (w < T.W) ? (T.expect ? T.p_host[w] : 1.0) : 0.0;
     const double inv0 = 1.0 / (double)G.stride[0];
     if (T.W == WM)
-        k_sweep_fact_column<D, WM, UB, true><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
+        k_sweep_fact_column<D, WM, UB, PF, true><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
             G, T, Jprev, part_val, part_idx, inv0, pv);
     else
-        k_sweep_fact_column<D, WM, UB, false><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
+        k_sweep_fact_column<D, WM, UB, PF, false><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
             G, T, Jprev, part_val, part_idx, inv0, pv);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
 
+template <int D, int WM>
+static int launch_fact_column_w(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                                double* part_val, int32_t* part_idx, cudaStream_t st) {
+    const int ub = tuning().col_ub, pf = tuning().col_pf;
+    if (ub == 2)
+        return pf == 2 ? launch_fact_column_k<D, WM, 2, 2>(G, T, Jprev, part_val, part_idx, st)
+                       : launch_fact_column_k<D, WM, 2, 1>(G, T, Jprev, part_val, part_idx, st);
+    return pf == 2 ? launch_fact_column_k<D, WM, 1, 2>(G, T, Jprev, part_val, part_idx, st)
+                   : launch_fact_column_k<D, WM, 1, 1>(G, T, Jprev, part_val, part_idx, st);
+}
+
 template <int D>
 static int launch_fact_column(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                               double* part_val, int32_t* part_idx, cudaStream_t st) {
-    const bool ub2 = tuning().col_ub == 2;
-    if (T.W <= 3)
-        return ub2 ? launch_fact_column_k<D, 3, 2>(G, T, Jprev, part_val, part_idx, st)
-                   : launch_fact_column_k<D, 3, 1>(G, T, Jprev, part_val, part_idx, st);
-    if (T.W <= 5)
-        return ub2 ? launch_fact_column_k<D, 5, 2>(G, T, Jprev, part_val, part_idx, st)
-                   : launch_fact_column_k<D, 5, 1>(G, T, Jprev, part_val, part_idx, st);
-    return ub2 ? launch_fact_column_k<D, 9, 2>(G, T, Jprev, part_val, part_idx, st)
-               : launch_fact_column_k<D, 9, 1>(G, T, Jprev, part_val, part_idx, st);
+    if (T.W <= 3) return launch_fact_column_w<D, 3>(G, T, Jprev, part_val, part_idx, st);
+    if (T.W <= 5) return launch_fact_column_w<D, 5>(G, T, Jprev, part_val, part_idx, st);
+    return launch_fact_column_w<D, 9>(G, T, Jprev, part_val, part_idx, st);
 }
 
 template <int D, int MASK>

@@ -19,7 +19,7 @@ from . import _cabi
 from . import tabulate as tb
 
 __all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "rebalance_bounds",
-           "column_order", "row_aligned"]
+           "column_order", "column_segments", "row_aligned"]
 
 # solver.column_hoist = "auto" uses layout CF (column-shared hoist) whenever it applies iff this
 # is set; "on" / "off" on the solver override it
@@ -178,6 +178,17 @@ def column_order(n_states, n_cols):
     order = (row[None, :] * n_cols + np.arange(n_cols, dtype=np.int64)[:, None]).reshape(-1)
     valid = np.broadcast_to(valid_row[None, :], (n_cols, len(row))).reshape(-1).copy()
     return order, valid, tiles_per_col
+
+
+def column_segments(item_u_count, n_ctas):
+    """Layout CF: cut the item list (ordered by tile, hence by column) into at most
+    `n_ctas` contiguous runs of equal weight, one per CTA - one CTA per SM, since the
+    column table fills its shared memory - so that a CTA meets few column changes.
+    Weight of an item: its controls plus a fixed cost.  Returns int64 [n_segs + 1]."""
+    n_items = len(item_u_count)
+    n_segs = max(1, min(int(n_ctas), n_items))
+    seg = partition_by_weight(np.asarray(item_u_count, dtype=np.float64) + 2.0, n_segs)
+    return np.asarray(seg, dtype=np.int64)
 
 
 def row_aligned(bounds, n_cols):
@@ -364,6 +375,7 @@ class SweepTables(object):
         self.n_cols = self.tiles_per_col = 0
         self.seg_begin = None      # device int64 [n_segs+1]: item range of every CTA
         self.n_segs = 0
+        self.item_u_count_host = None
         self.slab_times_ms = None  # measured per-rank sweep times (several ranks, see _measured_bounds)
         self.slab_recut = False    # True when those times moved the slab boundaries
 
@@ -720,7 +732,7 @@ class Engine(object):
         col_wanted = col_mode == "on" or (col_mode == "auto" and COLUMN_HOIST_DEFAULT)
         col_candidate = bool(
             col_wanted and d in (2, 3) and nb_perturb == 1 and 1 < W <= _cabi.FACTORED_MAX_W_REG
-            and ((n_rows0 + 1) * W + 9) * 8 <= _cabi.COLUMN_MAX_SMEM_BYTES
+            and (n_rows0 * (W | 1) + 9) * 8 <= _cabi.COLUMN_MAX_SMEM_BYTES
             and getattr(solver, "table_layout", "auto") in ("auto", "state_minor")
             and getattr(solver, "table_compress", "auto") != "off"
             and n_rows0 >= 32 * world and nb_control <= _cabi.SDP_MAX_C)
@@ -769,7 +781,7 @@ class Engine(object):
                 raise ValueError("column_hoist='on' but layout CF does not apply: it needs the "
                                  "state-minor layout, a factored (x,u)+(x,w) split with state axis 0 "
                                  "alone following the control, at most 9 perturbation nodes, a w-part "
-                                 "that does not depend on axis 0, and (order[0]+1)*W*8 bytes of "
+                                 "that does not depend on axis 0, and order[0]*(W|1)*8 bytes of "
                                  "shared memory")
             pos = {}
 
@@ -1036,12 +1048,10 @@ class Engine(object):
             T.chunk_plan = None
             up = [items if n_items else np.zeros(1, dtype=_cabi.ITEM_DTYPE), item_begin,
                   U_eff.astype(np.int32) if len(U_eff) else np.zeros(1, dtype=np.int32)]
+            T.item_u_count_host = items["u_count"].copy() if col else None
             if col:
-                # one CTA per SM: the item list (ordered by tile, hence by column) is cut into
-                # runs of equal weight, so that a CTA meets few column changes
-                T.n_segs = max(1, min(sm_count * self.COLUMN_SEGS_PER_SM, n_items))
-                seg = partition_by_weight(items["u_count"].astype(np.float64) + 2.0, T.n_segs)
-                up.append(np.asarray(seg, dtype=np.int64))
+                up.append(column_segments(T.item_u_count_host, sm_count * self.COLUMN_SEGS_PER_SM))
+                T.n_segs = len(up[-1]) - 1
             else:
                 T.n_segs, T.seg_begin = 0, None
             up = self.to_device_packed(up)
@@ -1087,6 +1097,15 @@ class Engine(object):
         return T
 
     COLUMN_SEGS_PER_SM = int(os.environ.get("SDP_COLUMN_SEGS_PER_SM", "1"))
+
+    def set_column_segments(self, T, n_ctas):
+        """layout CF: re-cut the item list of built tables into `n_ctas` CTA segments
+        (developer tuning, scripts/dev_column.py)"""
+        assert T.column
+        seg = column_segments(T.item_u_count_host, n_ctas)
+        T.seg_begin = self.to_device_packed([seg])[0]
+        T.n_segs = len(seg) - 1
+        T.c_tables = fill_c_tables(T)
 
     def _column_w_part_ok(self, T, d, W, n_cols, tiles_per_col, valid):
         """layout CF: True when, in every column, the (x,w) part of all real states -

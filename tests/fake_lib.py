@@ -310,8 +310,12 @@ class FakeLib(object):
             nan = np.isnan(acc)
             return int(np.argmax(nan)) if nan.any() else int(np.argmin(acc))
 
+        if column:
+            self._column_partials(T, d, J, strides, orders, items, p, pv, pi, Us)
         for n_it, it in enumerate(items):
             cnt, ub = int(it["u_count"]), int(it["u_begin"])
+            if column:
+                continue
             if factored and not tiled:
                 eb, sidx = int(it["entry_base"]), int(it["state"])
                 assert int(it["g_base"]) == eb
@@ -411,6 +415,64 @@ class FakeLib(object):
             Jo[i], ao[i] = bv, bi
         self.launches += 2
         return 0
+
+    def _column_partials(self, T, d, J, strides, orders, items, p, pv, pi, Us):
+        """layout CF the way k_sweep_fact_column does it: one CTA per segment of the item
+        list; at every column change the table R[row][w] = inner interpolation over the axes
+        1..d-1 is rebuilt from the w-part of lane 0 of the column's first tile; a backup is
+        (1-l0)*R[q0][w] + l0*R[q0+1][w] with q0 = cell_u / stride0"""
+        W, Tc = T.W, T.tiles_per_col
+        seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
+        ib = _arr(T.item_begin, T.n_cols * Tc + 1, ctypes.c_int64)
+        rows, stride0 = int(orders[0]), int(strides[0])
+        P = W | 1
+        done = np.zeros(len(items), dtype=bool)
+        for b in range(T.n_segs):
+            i, seg_end = int(seg[b]), int(seg[b + 1])
+            while i < seg_end:
+                col = int(items[i]["state"]) // Tc
+                e = min(int(ib[(col + 1) * Tc]), seg_end)
+                R = np.full(rows * P + 9, np.nan)
+                for w in range(W):
+                    f = (col * Tc * W + w) * 32
+                    cw = int(_arr(T.cell_w + 4 * f, 1, ctypes.c_int32)[0])
+                    lw = [_arr(T.lam_w + 8 * (j * T.lam_w_plane + f), 1, ctypes.c_double)[0]
+                          for j in range(d - 1)]
+
+                    def rec(base, k):
+                        if k == d:
+                            return J[base]
+                        a = rec(base, k + 1)
+                        bb = rec(base + strides[k], k + 1)
+                        return (1 - lw[k - 1]) * a + lw[k - 1] * bb
+                    R[np.arange(rows) * P + w] = rec(np.arange(rows, dtype=np.int64) * stride0 + cw, 1)
+                for n_it in range(i, e):
+                    it = items[n_it]
+                    assert int(it["state"]) // Tc == col and not done[n_it]
+                    done[n_it] = True
+                    cnt, ub, eb, tix = int(it["u_count"]), int(it["u_begin"]), int(it["entry_base"]), int(it["state"])
+                    assert int(it["g_base"]) == eb
+                    cu = _arr(T.cell + 4 * eb, cnt * 32, ctypes.c_int32).astype(np.int64).reshape(cnt, 32)
+                    lu = _arr(T.lam + 8 * eb, cnt * 32, ctypes.c_double).reshape(cnt, 32)
+                    Gv = _arr(T.g + 8 * eb, cnt * 32, ctypes.c_double).reshape(cnt, 32)
+                    assert np.all(cu % stride0 == 0)
+                    q = cu // stride0
+                    acc = np.zeros((cnt, 32))
+                    for w in range(W):
+                        v = (1 - lu) * R[q * P + w] + lu * R[q * P + P + w]
+                        jg = Gv + v
+                        acc = acc + jg * p[w] if T.expect else jg
+                    for lane in range(32):
+                        n_ok = max(0, min(cnt, int(Us[tix * 32 + lane]) - ub))
+                        if n_ok == 0:
+                            pv[n_it * 32 + lane], pi[n_it * 32 + lane] = np.inf, 2 ** 31 - 1
+                        else:
+                            a = acc[:n_ok, lane]
+                            nan = np.isnan(a)
+                            j = int(np.argmax(nan)) if nan.any() else int(np.argmin(a))
+                            pv[n_it * 32 + lane], pi[n_it * 32 + lane] = a[j], ub + j
+                i = e
+        assert done.all()
 
     def sdp_sweep_partials(self, *a):
         raise NotImplementedError("the model implements sdp_sweep as a whole")

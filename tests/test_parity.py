@@ -774,16 +774,18 @@ def test_column_hoist_is_bit_identical(product, backend, which):
         # CTA size, controls per iteration and work-item length do not change a bit
         lib = col.engine.lib
         try:
-            for threads, ub in ((128, 1), (256, 2), (512, 1)):
+            Jr, polr = ref.value_iteration(J0, report_time=False)
+            for threads, ub, pf in ((128, 1, 1), (256, 2, 1), (512, 1, 2), (96, 2, 2)):
                 lib.sdp_set_option(b"col_threads", threads)
                 lib.sdp_set_option(b"col_ub", ub)
+                lib.sdp_set_option(b"col_pf", pf)
                 J2, pol2 = col.value_iteration(J0, report_time=False)
-                Jr, polr = ref.value_iteration(J0, report_time=False)
-                assert np.array_equal(Jr.view(np.int64), J2.view(np.int64)), (threads, ub)
-                assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub)
+                assert np.array_equal(Jr.view(np.int64), J2.view(np.int64)), (threads, ub, pf)
+                assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf)
         finally:
             lib.sdp_set_option(b"col_threads", 512)
             lib.sdp_set_option(b"col_ub", 2)
+            lib.sdp_set_option(b"col_pf", 2)
 
 
 @pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
