@@ -113,7 +113,9 @@ typedef struct SdpItem {
  * operations of the reference's nested formula, evaluated once instead of once per
  * (state, control).  Bit-identical to the other layouts. */
 #define SDP_LAYOUT_COLUMN_FACTORED 4
-#define SDP_COLUMN_MAX_SMEM_BYTES (200 * 1024) /* CF: (order[0]*(W|1) + 9) * 8 must fit */
+/* doubles per column table: order[0] rows of (W|1) doubles + 9 of slack, rounded up to even */
+#define SDP_COLUMN_PITCH(rows, W) ((((int64_t)(rows) * ((W) | 1)) + 9 + 1) & ~(int64_t)1)
+#define SDP_COLUMN_MAX_SMEM_BYTES (200 * 1024) /* CF: 8 * SDP_COLUMN_PITCH(order[0], W) must fit */
 
 /* Dense sweep tables of one shard of states (device pointers).
  *
@@ -184,6 +186,12 @@ typedef struct SdpTables {
     int32_t tiles_per_col;
     const int64_t* seg_begin;
     int64_t n_segs;
+    /* Layout CF scratch, written by every sweep: the inner-interpolation tables of all
+     * columns, [n_cols][SDP_COLUMN_PITCH(order[0], W)] doubles (caller-owned, 16-byte
+     * aligned).  A coalesced pre-pass fills it from J_prev (lanes along the columns, where
+     * the gathers of neighbouring columns are contiguous) and each CTA copies the table
+     * of its current column into shared memory. */
+    double* col_table;
 } SdpTables;
 
 /* ABI / build identification. */
@@ -199,7 +207,8 @@ int64_t sdp_launch_count(void);
  * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4),
  * "hoist_const" (0|1: constant-W variant of that kernel for W <= 9),
  * "col_threads" (layout CF: threads per CTA, 128..512), "col_ub" (controls per iteration, 1|2),
- * "col_pf" (groups of col_ub controls in flight, 1|2),
+ * "col_pf" (groups of col_ub controls in flight, 1|2), "col_prepass" (1: column tables
+ * from the coalesced pre-pass, default; 0: every CTA gathers its own from J_prev),
  * "p2p_timeout_s" (bound of the peer-flag waits, default 600 s, then the kernel traps).
  * Not thread-safe against concurrent launches. */
 int sdp_set_option(const char* name, int value);

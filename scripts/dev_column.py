@@ -72,6 +72,11 @@ def timed(T, n=10, warm=3):
 
 print("BF            :", timed(Tb), flush=True)
 sm = torch.cuda.get_device_properties(0).multi_processor_count
+for pre in (1, 0):
+    _cabi.check(lib.sdp_set_option(b"col_prepass", pre), "opt")
+    print("CF default, column tables %s:" % ("from the pre-pass" if pre else "gathered by every CTA"),
+          timed(Tc), flush=True)
+lib.sdp_set_option(b"col_prepass", 1)
 for per_sm in (1, 2, 4):
     eng.set_column_segments(Tc, sm * per_sm)
     for threads in (512, 384, 256):

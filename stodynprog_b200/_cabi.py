@@ -18,7 +18,14 @@ LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
 LAYOUT_CONTROL_MINOR_FACTORED = 2   # "AF": (x,u) part [state][Upad] + (x,w) part [state][W]
 LAYOUT_STATE_MINOR_FACTORED = 3     # "BF": (x,u) part [tile][u][lane] + (x,w) part [tile][w][lane]
 LAYOUT_COLUMN_FACTORED = 4          # "CF": BF tables over column-major tiles, inner interpolation shared per column
-COLUMN_MAX_SMEM_BYTES = 200 * 1024  # CF: (order[0]*(W|1) + 9) * 8 bytes of shared memory for the column table
+COLUMN_MAX_SMEM_BYTES = 200 * 1024  # CF: 8 * column_pitch(order[0], W) bytes of shared memory per CTA
+
+
+def column_pitch(rows, W):
+    """SDP_COLUMN_PITCH: doubles per column table of layout CF"""
+    return (rows * (W | 1) + 9 + 1) & ~1
+
+
 FACTORED_MAX_W_REG = 9     # BF keeps a lane's w-part in registers
 FACTORED_MAX_W_SMEM = 128  # AF keeps a state's w-part in shared memory
 
@@ -62,7 +69,8 @@ class SdpTables(ctypes.Structure):
                 ("n_cols", ctypes.c_int32),
                 ("tiles_per_col", ctypes.c_int32),
                 ("seg_begin", ctypes.c_void_p),
-                ("n_segs", ctypes.c_int64)]
+                ("n_segs", ctypes.c_int64),
+                ("col_table", ctypes.c_void_p)]
 
 
 SDP_MAX_PEERS = 8

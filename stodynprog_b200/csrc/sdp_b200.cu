@@ -1051,6 +1051,7 @@ struct Tuning {
     int col_threads;   // layout CF: threads per CTA (one CTA per SM: the column table fills shared memory)
     int col_ub;        // layout CF: controls per lane per iteration (1|2)
     int col_pf;        // layout CF: groups of col_ub controls in flight per lane (1|2)
+    int col_prepass;   // layout CF: column tables from the coalesced pre-pass (1) or gathered by every CTA (0)
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static int env_int(const char* name, int dflt) {
@@ -1084,6 +1085,7 @@ static Tuning& tuning() {
         x.col_threads = clampi(env_int("SDP_COL_THREADS", 512), 128, 512) / 32 * 32;
         x.col_ub = env_int("SDP_COL_UB", 2) == 1 ? 1 : 2;
         x.col_pf = env_int("SDP_COL_PF", 2) == 1 ? 1 : 2;
+        x.col_prepass = env_int("SDP_COL_PREPASS", 1) != 0;
         return x;
     }();
     return t;
@@ -1105,6 +1107,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "col_threads")) t.col_threads = clampi(value, 128, 512) / 32 * 32;
     else if (!strcmp(name, "col_ub")) t.col_ub = (value == 1) ? 1 : 2;
     else if (!strcmp(name, "col_pf")) t.col_pf = (value == 1) ? 1 : 2;
+    else if (!strcmp(name, "col_prepass")) t.col_prepass = value != 0;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1747,14 +1750,63 @@ static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, cons
 // shared memory), so a CTA meets few column changes.  Warps take the items of the
 // current column round-robin.  Partial minima have the layout of BF.
 // ---------------------------------------------------------------------------
+// Pre-pass: the inner-interpolation tables of ALL columns, R[c][r][w] at
+// col_table[c*pitch + r*P + w].  A CTA owns a tile of 32 columns x SDP_CT_ROWS rows: it
+// computes with lanes along the columns - the w-parts of neighbouring columns point at
+// neighbouring cells, so the gathers of a warp are a few lines instead of 32 - into a
+// shared-memory tile, then writes each column's run of rows contiguously.
+#define SDP_CT_ROWS 16
+template <int D>
+__global__ void __launch_bounds__(256)
+k_column_table(GridT<double> G, SdpTables T, const double* __restrict__ Jprev, int64_t pitch) {
+    constexpr int NW = D - 1;
+    constexpr int TR = SDP_CT_ROWS;
+    extern __shared__ __align__(16) unsigned char tsm[];
+    const int W = T.W;
+    const int P = W | 1;
+    const int CP = TR * P + 1;                    // odd tile pitch per column: conflict-free both ways
+    double* tile = reinterpret_cast<double*>(tsm);             // [32][CP]
+    double* lw_s = tile + 32 * CP;                             // [NW][32][W]
+    int* cw_s = reinterpret_cast<int*>(lw_s + NW * 32 * W);    // [32][W]
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * TR;
+    const int rows = G.order[0], stride0 = G.stride[0];
+    for (int k = threadIdx.x; k < 32 * W; k += blockDim.x) {
+        const int lc = k / W, w = k - lc * W;
+        const int c = min(c0 + lc, T.n_cols - 1);
+        const int64_t f = ((int64_t)c * T.tiles_per_col * W + w) * 32;     // lane 0 of the column's first tile
+        cw_s[k] = __ldg(T.cell_w + f);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) lw_s[(j * 32 + lc) * W + w] = __ldg(T.lam_w + (int64_t)j * T.lam_w_plane + f);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < TR * W * 32; k += blockDim.x) {
+        const int lc = k & 31;
+        const int rw = k >> 5;
+        const int lr = rw / W, w = rw - lr * W;
+        const int r = min(r0 + lr, rows - 1);
+        double lam[D];
+        lam[0] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) lam[j + 1] = lw_s[(j * 32 + lc) * W + w];
+        tile[lc * CP + lr * P + w] = Lerp<double, D, 1>::eval(Jprev, r * stride0 + cw_s[lc * W + w], G.stride, lam);
+    }
+    __syncthreads();
+    const int nr = min(TR, rows - r0);
+    for (int lc = threadIdx.x >> 5; lc < 32; lc += blockDim.x >> 5) {
+        if (c0 + lc >= T.n_cols) break;
+        double* dst = T.col_table + (int64_t)(c0 + lc) * pitch + (int64_t)r0 * P;
+        for (int k = threadIdx.x & 31; k < nr * P; k += 32) dst[k] = tile[lc * CP + k];
+    }
+}
+
 template <int D, int WM, int UB, int PF, bool FULL>     // FULL: W == WM, every slot live
 __global__ void __launch_bounds__(512, 1)
 k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
                     double* __restrict__ part_val, int32_t* __restrict__ part_idx,
-                    double inv_stride0, PVals PV) {
+                    double inv_stride0, PVals PV, int64_t pitch, int prepass) {
     constexpr int NW = D - 1;
     extern __shared__ __align__(16) unsigned char csm[];
-    double* R_sh = reinterpret_cast<double*>(csm);      // [order[0]][P] (+ WM doubles of slack)
+    double* R_sh = reinterpret_cast<double*>(csm);      // [order[0]][P] + slack = `pitch` doubles
     __shared__ int cw_sh[WM];
     __shared__ double lw_sh[NW][WM];
     const int W = T.W;
@@ -1770,21 +1822,29 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
         const int64_t col_end = T.item_begin[(int64_t)(col + 1) * T.tiles_per_col];
         const int64_t e = col_end < seg_end ? col_end : seg_end;
         __syncthreads();                 // the previous column's readers are done with R
-        if (threadIdx.x < W) {
-            // the column's w-part: lane 0 of its first tile
-            const int64_t f = ((int64_t)col * T.tiles_per_col * W + threadIdx.x) * 32;
-            cw_sh[threadIdx.x] = __ldg(T.cell_w + f);
+        if (prepass) {
+            // the column's table, tabulated by k_column_table: one contiguous block
+            const double2* __restrict__ src = reinterpret_cast<const double2*>(T.col_table + (int64_t)col * pitch);
+            double2* dst = reinterpret_cast<double2*>(R_sh);
+            for (int k = threadIdx.x; k < (int)(pitch >> 1); k += blockDim.x) dst[k] = src[k];
+        } else {
+            if (threadIdx.x < W) {
+                // the column's w-part: lane 0 of its first tile
+                const int64_t f = ((int64_t)col * T.tiles_per_col * W + threadIdx.x) * 32;
+                cw_sh[threadIdx.x] = __ldg(T.cell_w + f);
 #pragma unroll
-            for (int k = 0; k < NW; ++k) lw_sh[k][threadIdx.x] = __ldg(T.lam_w + (int64_t)k * T.lam_w_plane + f);
-        }
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < rows * W; idx += blockDim.x) {
-            const int r = idx / W, w = idx - r * W;
-            double lam[D];
-            lam[0] = 0.0;
+                for (int k = 0; k < NW; ++k)
+                    lw_sh[k][threadIdx.x] = __ldg(T.lam_w + (int64_t)k * T.lam_w_plane + f);
+            }
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < rows * W; idx += blockDim.x) {
+                const int r = idx / W, w = idx - r * W;
+                double lam[D];
+                lam[0] = 0.0;
 #pragma unroll
-            for (int k = 0; k < NW; ++k) lam[k + 1] = lw_sh[k][w];
-            R_sh[r * P + w] = Lerp<double, D, 1>::eval(Jprev, r * stride0 + cw_sh[w], G.stride, lam);
+                for (int k = 0; k < NW; ++k) lam[k + 1] = lw_sh[k][w];
+                R_sh[r * P + w] = Lerp<double, D, 1>::eval(Jprev, r * stride0 + cw_sh[w], G.stride, lam);
+            }
         }
         __syncthreads();
 
@@ -1873,9 +1933,19 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
 template <int D, int WM, int UB, int PF>
 static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                                 double* part_val, int32_t* part_idx, cudaStream_t st) {
-    const size_t shm = ((size_t)G.order[0] * (T.W | 1) + WM) * 8;
+    const int64_t pitch = SDP_COLUMN_PITCH(G.order[0], T.W);
+    const size_t shm = (size_t)pitch * 8;
     if (shm > SDP_COLUMN_MAX_SMEM_BYTES)
         return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF: the column table does not fit shared memory");
+    const int prepass = tuning().col_prepass;
+    if (prepass) {
+        constexpr int NW = D - 1;
+        const int P = T.W | 1;
+        const size_t tshm = (size_t)32 * (SDP_CT_ROWS * P + 1) * 8 + (size_t)NW * 32 * T.W * 8 + (size_t)32 * T.W * 4;
+        dim3 grid((unsigned)((T.n_cols + 31) / 32), (unsigned)((G.order[0] + SDP_CT_ROWS - 1) / SDP_CT_ROWS));
+        k_column_table<D><<<grid, 256, tshm, st>>>(G, T, Jprev, pitch);
+        SDP_LAUNCH_CHECK();
+    }
     static size_t attr_set = 0;          // per instantiation
     if (attr_set < shm) {
         cudaError_t e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, true>,
@@ -1892,10 +1962,10 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
     const double inv0 = 1.0 / (double)G.stride[0];
     if (T.W == WM)
         k_sweep_fact_column<D, WM, UB, PF, true><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
-            G, T, Jprev, part_val, part_idx, inv0, pv);
+            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass);
     else
         k_sweep_fact_column<D, WM, UB, PF, false><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
-            G, T, Jprev, part_val, part_idx, inv0, pv);
+            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
@@ -2032,6 +2102,8 @@ static int check_tables(const SdpTables& T, const char* who) {
                 return fail(SDP_EINVAL, "%s: layout CF: the shard must be whole rows, 32 per tile", who);
             if (!T.seg_begin || T.n_segs < 1 || T.n_segs > 0x7fffffffLL)
                 return fail(SDP_EINVAL, "%s: layout CF needs the CTA segments of the item list", who);
+            if (!T.col_table || ((uintptr_t)T.col_table & 15))
+                return fail(SDP_EINVAL, "%s: layout CF needs the 16-byte aligned column-table scratch", who);
         }
         if (T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED && T.W > 128)
             return fail(SDP_EINVAL, "%s: layout AF supports at most 128 perturbation nodes", who);

@@ -120,6 +120,7 @@ def fill_c_tables(T):
             c.layout = _cabi.LAYOUT_COLUMN_FACTORED
             c.n_cols, c.tiles_per_col = T.n_cols, T.tiles_per_col
             c.seg_begin, c.n_segs = T.seg_begin.data_ptr(), T.n_segs
+            c.col_table = T.col_table.data_ptr()
         c.u_mask = T.u_mask
         c.cell_w = T.cell_w.data_ptr()
         c.lam_w = T.lam_w.data_ptr()
@@ -376,6 +377,7 @@ class SweepTables(object):
         self.seg_begin = None      # device int64 [n_segs+1]: item range of every CTA
         self.n_segs = 0
         self.item_u_count_host = None
+        self.col_table = None      # device fp64 scratch: the column tables of the current sweep
         self.slab_times_ms = None  # measured per-rank sweep times (several ranks, see _measured_bounds)
         self.slab_recut = False    # True when those times moved the slab boundaries
 
@@ -732,7 +734,7 @@ class Engine(object):
         col_wanted = col_mode == "on" or (col_mode == "auto" and COLUMN_HOIST_DEFAULT)
         col_candidate = bool(
             col_wanted and d in (2, 3) and nb_perturb == 1 and 1 < W <= _cabi.FACTORED_MAX_W_REG
-            and (n_rows0 * (W | 1) + 9) * 8 <= _cabi.COLUMN_MAX_SMEM_BYTES
+            and 8 * _cabi.column_pitch(n_rows0, W) <= _cabi.COLUMN_MAX_SMEM_BYTES
             and getattr(solver, "table_layout", "auto") in ("auto", "state_minor")
             and getattr(solver, "table_compress", "auto") != "off"
             and n_rows0 >= 32 * world and nb_control <= _cabi.SDP_MAX_C)
@@ -1058,6 +1060,9 @@ class Engine(object):
             T.items, T.item_begin, T.U_dev = up[0], up[1], up[2]
             if col:
                 T.seg_begin = up[3]
+                ensure("col_table", n_cols * _cabi.column_pitch(n_rows0, W), torch.float64)
+            else:
+                T.col_table = None
             n_part = max(n_items, 1) * (32 if tiled else 1)
             T.part_val = torch.empty(n_part, dtype=torch.float64, device=dev)
             T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)

@@ -295,6 +295,7 @@ class FakeLib(object):
             seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
             assert seg[0] == 0 and seg[-1] == T.n_items and np.all(np.diff(seg) >= 0)
             assert np.all(np.diff(items["state"]) >= 0)          # ordered by tile, hence by column
+            assert T.col_table and T.col_table % 16 == 0         # scratch for the column tables
         Us = _arr(T.U, n_pos, ctypes.c_int32)
 
         def lerp(c, lam):

@@ -339,9 +339,10 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SdpStateDesc), offsetof(SdpStateDesc, src),
          offsetof(SdpStateDesc, cs), offsetof(SdpStateDesc, ws), offsetof(SdpStateDesc, npts),
          offsetof(SdpStateDesc, U), offsetof(SdpStateDesc, Upad), sizeof(SdpItem));
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SdpTables), offsetof(SdpTables, p), offsetof(SdpTables, n_items),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %lld\\n", sizeof(SdpTables), offsetof(SdpTables, p), offsetof(SdpTables, n_items),
          offsetof(SdpTables, U), sizeof(SdpGrid), offsetof(SdpTables, p_host), offsetof(SdpTables, n_cols),
-         offsetof(SdpTables, seg_begin), offsetof(SdpTables, n_segs));
+         offsetof(SdpTables, seg_begin), offsetof(SdpTables, n_segs), offsetof(SdpTables, col_table),
+         (long long)SDP_COLUMN_PITCH(2000, 9) * 1000 + (long long)SDP_COLUMN_PITCH(7, 4));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
@@ -353,7 +354,8 @@ int main(void) {
     T = _cabi.SdpTables
     assert [int(x) for x in l2.split()] == [ctypes.sizeof(T), T.p.offset, T.n_items.offset, T.U.offset,
                                             ctypes.sizeof(_cabi.SdpGrid), T.p_host.offset, T.n_cols.offset,
-                                            T.seg_begin.offset, T.n_segs.offset]
+                                            T.seg_begin.offset, T.n_segs.offset, T.col_table.offset,
+                                            _cabi.column_pitch(2000, 9) * 1000 + _cabi.column_pitch(7, 4)]
     hdr = open(os.path.join(ROOT, "include", "sdp_b200.h")).read()
     for name in ("SDP_ABI_VERSION", "SDP_LAYOUT_COLUMN_FACTORED", "SDP_FACTORED_MAX_W_REG"):
         val = int(re.search(r"#define %s (\d+)" % name, hdr).group(1))

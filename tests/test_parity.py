@@ -775,17 +775,20 @@ def test_column_hoist_is_bit_identical(product, backend, which):
         lib = col.engine.lib
         try:
             Jr, polr = ref.value_iteration(J0, report_time=False)
-            for threads, ub, pf in ((128, 1, 1), (256, 2, 1), (512, 1, 2), (96, 2, 2)):
+            for threads, ub, pf, pre in ((128, 1, 1, 1), (256, 2, 1, 0), (512, 1, 2, 0), (96, 2, 2, 0),
+                                         (160, 1, 2, 1)):
                 lib.sdp_set_option(b"col_threads", threads)
                 lib.sdp_set_option(b"col_ub", ub)
                 lib.sdp_set_option(b"col_pf", pf)
+                lib.sdp_set_option(b"col_prepass", pre)
                 J2, pol2 = col.value_iteration(J0, report_time=False)
-                assert np.array_equal(Jr.view(np.int64), J2.view(np.int64)), (threads, ub, pf)
-                assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf)
+                assert np.array_equal(Jr.view(np.int64), J2.view(np.int64)), (threads, ub, pf, pre)
+                assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf, pre)
         finally:
             lib.sdp_set_option(b"col_threads", 512)
             lib.sdp_set_option(b"col_ub", 2)
             lib.sdp_set_option(b"col_pf", 2)
+            lib.sdp_set_option(b"col_prepass", 1)
 
 
 @pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
