@@ -102,16 +102,21 @@ typedef struct SdpItem {
 #define SDP_LAYOUT_CONTROL_MINOR_FACTORED 2 /* "AF": u-part [state][Upad], w-part [state][W] */
 #define SDP_LAYOUT_STATE_MINOR_FACTORED 3   /* "BF": u-part [tile][u][32], w-part [tile][w][32] */
 #define SDP_FACTORED_MAX_W_REG 9 /* BF keeps the w-part of a lane in registers: W <= 9 */
-/* "CF", column-shared hoist: BF tables whose tiles run along state axis 0 - tile
- * t = c*tiles_per_col + b holds rows 32*b .. 32*b+31 of COLUMN c (the flat C-order
- * index over the state axes 1..d-1) - for systems with u_mask == 1 whose (x,w) part
- * does not depend on the axis-0 index (the storage examples: P_next = a*P + w does
- * not involve E).  The inner interpolation R(row, w) over the axes 1..d-1 is then
- * the same for all the states of a column: one CTA tabulates it once per column in
- * shared memory (order[0] rows of W|1 doubles) and every backup of the column is two
- * shared-memory reads and one lerp instead of 2^d gathers and 2^d-1 lerps - the
+/* "CF", column-shared hoist: BF tables whose tiles run along state axis 0 - a tile holds
+ * 32 consecutive rows of one COLUMN c (the flat C-order index over the state axes
+ * 1..d-1) - for systems with u_mask == 1 whose (x,w) part does not depend on the axis-0
+ * index (the storage examples: P_next = a*P + w does not involve E).  The inner
+ * interpolation R(row, w) over the axes 1..d-1 is then the same for all the states of a
+ * column: it is tabulated once per column and sweep (order[0] rows of W|1 doubles, held
+ * in shared memory by the CTA that sweeps the column) and every backup of the column is
+ * two shared-memory reads and one lerp instead of 2^d gathers and 2^d-1 lerps - the
  * operations of the reference's nested formula, evaluated once instead of once per
- * (state, control).  Bit-identical to the other layouts. */
+ * (state, control).  Bit-identical to the other layouts.
+ * Tile order: the shard's rows are cut into one or more BANDS of consecutive rows; tiles
+ * are ordered band by band, inside a band column by column, inside a column by rows
+ * (band b, rows_b rows: tile = band_first_tile[b] + c*ceil(rows_b/32) + (row - first row)/32).
+ * One band is the plain column-major order; several bands let a caller combine and copy
+ * out the results of a band (a contiguous range of states) while later bands are swept. */
 #define SDP_LAYOUT_COLUMN_FACTORED 4
 /* doubles per column table: order[0] rows of (W|1) doubles + 9 of slack, rounded up to even */
 #define SDP_COLUMN_PITCH(rows, W) ((((int64_t)(rows) * ((W) | 1)) + 9 + 1) & ~(int64_t)1)
@@ -175,23 +180,31 @@ typedef struct SdpTables {
     const double* p_host;
     /* Layout CF only.  The shard is `n_states / n_cols` whole rows of axis 0 (local
      * state i = row*n_cols + column, as in the C-order grid); units/items/u-part/w-part
-     * are those of layout BF over the column-major tiles described above, `U` is indexed
-     * by POSITION tile*32 + lane (32*n_cols*tiles_per_col entries, 0 on the padding
-     * lanes of a column's last tile); the w-part read by the sweep is that of lane 0 of
-     * the column's first tile (the caller checks that the whole column agrees).
-     * seg_begin: [n_segs + 1] item ranges - one CTA sweeps the items
-     * seg_begin[b] .. seg_begin[b+1]-1 (items are ordered by tile, hence by column) and
-     * rebuilds its shared-memory table whenever the column changes. */
+     * are those of layout BF over the tiles described above, `U` is indexed by POSITION
+     * tile*32 + lane (0 on the padding lanes of a column's last tile in a band); item.Upad
+     * holds the COLUMN of the item's tile.  The w-part read for column c is that of lane 0
+     * of tile c*tiles_per_col, its first tile in the first band (the caller checks that
+     * the whole column agrees).
+     * Streaming pass (sdp_sweep_partials): one CTA sweeps the items
+     * seg_begin[b] .. seg_begin[b+1]-1 (absolute indices into `items`; items are ordered by
+     * tile) and loads its column table whenever the column changes: run_end[i] is the end
+     * of the run of items sharing the band and column of item i.
+     * Combine pass (sdp_sweep_finalize[_p2p]): called ONCE PER BAND with a view of the
+     * band - item_begin advanced to the band's first tile, n_states / tiles_per_col those
+     * of the band, outputs advanced to the band's first state. */
     int32_t n_cols;
-    int32_t tiles_per_col;
-    const int64_t* seg_begin;
+    int32_t tiles_per_col;     /* streaming pass: of the first band; combine pass: of the band */
+    const int64_t* seg_begin;  /* [n_segs + 1] */
     int64_t n_segs;
-    /* Layout CF scratch, written by every sweep: the inner-interpolation tables of all
-     * columns, [n_cols][SDP_COLUMN_PITCH(order[0], W)] doubles (caller-owned, 16-byte
-     * aligned).  A coalesced pre-pass fills it from J_prev (lanes along the columns, where
-     * the gathers of neighbouring columns are contiguous) and each CTA copies the table
-     * of its current column into shared memory. */
+    /* scratch, written by every sweep: the inner-interpolation tables of all columns,
+     * [n_cols][SDP_COLUMN_PITCH(order[0], W)] doubles (caller-owned, 16-byte aligned).  A
+     * coalesced pre-pass (sdp_column_table, lanes along the columns, where the gathers of
+     * neighbouring columns are contiguous) fills it from J_prev and each CTA copies the
+     * table of its current column into shared memory. */
     double* col_table;
+    const int64_t* run_end;    /* [n_items] */
+    int32_t col_table_ready;   /* streaming pass: 0 = run the pre-pass first, 1 = col_table is current */
+    int32_t reserved2;
 } SdpTables;
 
 /* ABI / build identification. */
@@ -265,10 +278,13 @@ int sdp_build_tables_factored_tiled(const SdpGrid* grid, int32_t W, int32_t u_ma
  * J_prev: device [prod(order)], the full previous value function.
  * part_val/part_idx: device scratch [n_items] (layout A) or [32*n_items] (layout B).
  * J_out: device [n_states]; argmin_out: device [n_states] flat C-order index
- * into the state's control product. */
+ * into the state's control product.  (Layout CF: single-band tables only.) */
 int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
               double* part_val, int32_t* part_idx, double* J_out, int32_t* argmin_out,
               void* stream);
+/* Layout CF: the pre-pass of the streaming pass alone (fills tab->col_table from J_prev),
+ * for callers that sweep the item list in several launches with col_table_ready = 1. */
+int sdp_column_table(const SdpGrid* grid, const SdpTables* tab, const double* J_prev, void* stream);
 /* The two launches of sdp_sweep, separately (so that a caller can bracket the
  * streaming kernel alone with events): per-item partial minima, then the
  * per-state combine. */

@@ -70,7 +70,10 @@ class SdpTables(ctypes.Structure):
                 ("tiles_per_col", ctypes.c_int32),
                 ("seg_begin", ctypes.c_void_p),
                 ("n_segs", ctypes.c_int64),
-                ("col_table", ctypes.c_void_p)]
+                ("col_table", ctypes.c_void_p),
+                ("run_end", ctypes.c_void_p),
+                ("col_table_ready", ctypes.c_int32),
+                ("reserved2", ctypes.c_int32)]
 
 
 SDP_MAX_PEERS = 8
@@ -125,6 +128,7 @@ SIGNATURES = {
     "sdp_build_tables_factored_tiled": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _vp,
                                                        _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "sdp_sweep": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sdp_column_table": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp]),
     "sdp_sweep_partials": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp]),
     "sdp_sweep_finalize": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp]),
     "sdp_sweep_finalize_p2p": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp,

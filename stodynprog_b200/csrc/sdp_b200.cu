@@ -1745,8 +1745,8 @@ static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, cons
 // pitch is an odd number of doubles (W | 1), so a half-warp's 8-byte reads spread over
 // all 32 banks.
 //
-// Work split: the item list is ordered by tile, hence by column; the host cuts it
-// into n_segs runs of equal weight, one per CTA (one CTA per SM: the table fills
+// Work split: the item list is ordered by tile, i.e. by (band, column); the host cuts
+// it into n_segs runs of equal weight, one per CTA (one CTA per SM: the table fills
 // shared memory), so a CTA meets few column changes.  Warps take the items of the
 // current column round-robin.  Partial minima have the layout of BF.
 // ---------------------------------------------------------------------------
@@ -1799,6 +1799,17 @@ k_column_table(GridT<double> G, SdpTables T, const double* __restrict__ Jprev, i
     }
 }
 
+template <int D>
+static int launch_column_table(const GridT<double>& G, const SdpTables& T, const double* Jprev, cudaStream_t st) {
+    constexpr int NW = D - 1;
+    const int P = T.W | 1;
+    const size_t tshm = (size_t)32 * (SDP_CT_ROWS * P + 1) * 8 + (size_t)NW * 32 * T.W * 8 + (size_t)32 * T.W * 4;
+    dim3 grid((unsigned)((T.n_cols + 31) / 32), (unsigned)((G.order[0] + SDP_CT_ROWS - 1) / SDP_CT_ROWS));
+    k_column_table<D><<<grid, 256, tshm, st>>>(G, T, Jprev, SDP_COLUMN_PITCH(G.order[0], T.W));
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
 template <int D, int WM, int UB, int PF, bool FULL>     // FULL: W == WM, every slot live
 __global__ void __launch_bounds__(512, 1)
 k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
@@ -1818,9 +1829,9 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
     int64_t i = T.seg_begin[blockIdx.x];
     const int64_t seg_end = T.seg_begin[blockIdx.x + 1];
     while (i < seg_end) {
-        const int col = T.items[i].state / T.tiles_per_col;
-        const int64_t col_end = T.item_begin[(int64_t)(col + 1) * T.tiles_per_col];
-        const int64_t e = col_end < seg_end ? col_end : seg_end;
+        const int col = T.items[i].Upad;          // layout CF: the column of the item's tile
+        const int64_t run_end = T.run_end[i];     // end of the items of this band and column
+        const int64_t e = run_end < seg_end ? run_end : seg_end;
         __syncthreads();                 // the previous column's readers are done with R
         if (prepass) {
             // the column's table, tabulated by k_column_table: one contiguous block
@@ -1938,13 +1949,9 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
     if (shm > SDP_COLUMN_MAX_SMEM_BYTES)
         return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF: the column table does not fit shared memory");
     const int prepass = tuning().col_prepass;
-    if (prepass) {
-        constexpr int NW = D - 1;
-        const int P = T.W | 1;
-        const size_t tshm = (size_t)32 * (SDP_CT_ROWS * P + 1) * 8 + (size_t)NW * 32 * T.W * 8 + (size_t)32 * T.W * 4;
-        dim3 grid((unsigned)((T.n_cols + 31) / 32), (unsigned)((G.order[0] + SDP_CT_ROWS - 1) / SDP_CT_ROWS));
-        k_column_table<D><<<grid, 256, tshm, st>>>(G, T, Jprev, pitch);
-        SDP_LAUNCH_CHECK();
+    if (prepass && !T.col_table_ready) {
+        int rc = launch_column_table<D>(G, T, Jprev, st);
+        if (rc) return rc;
     }
     static size_t attr_set = 0;          // per instantiation
     if (attr_set < shm) {
@@ -2075,6 +2082,20 @@ static inline bool is_factored(const SdpTables& T) {
     return T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED || T.layout == SDP_LAYOUT_STATE_MINOR_FACTORED ||
            is_column(T);
 }
+// layout CF, what the streaming pass needs on top of check_tables
+static int check_column_stream(const SdpTables& T, const char* who) {
+    if (!T.seg_begin || T.n_segs < 1 || T.n_segs > 0x7fffffffLL || !T.run_end)
+        return fail(SDP_EINVAL, "%s: layout CF needs the CTA segments and column runs of the item list", who);
+    if (!T.col_table || ((uintptr_t)T.col_table & 15))
+        return fail(SDP_EINVAL, "%s: layout CF needs the 16-byte aligned column-table scratch", who);
+    return SDP_OK;
+}
+// layout CF, combine pass: the view must be one band (whole rows, 32 per tile of a column)
+static int check_column_band(const SdpTables& T, const char* who) {
+    if ((T.n_states / T.n_cols + 31) / 32 != T.tiles_per_col)
+        return fail(SDP_EINVAL, "%s: layout CF: the combine pass takes one band of rows at a time", who);
+    return SDP_OK;
+}
 static int check_tables(const SdpTables& T, const char* who) {
     if (T.W < 1 || T.W > 4096 || T.n_states < 0 || T.n_items < 0)
         return fail(SDP_EINVAL, "%s: bad sizes", who);
@@ -2097,13 +2118,8 @@ static int check_tables(const SdpTables& T, const char* who) {
         if (is_column(T)) {
             if (T.u_mask != 1)
                 return fail(SDP_EINVAL, "%s: layout CF needs u_mask == 1 (axis 0 follows the control)", who);
-            if (T.n_cols < 1 || T.tiles_per_col < 1 || T.n_states % T.n_cols != 0 ||
-                (T.n_states / T.n_cols + 31) / 32 != T.tiles_per_col)
-                return fail(SDP_EINVAL, "%s: layout CF: the shard must be whole rows, 32 per tile", who);
-            if (!T.seg_begin || T.n_segs < 1 || T.n_segs > 0x7fffffffLL)
-                return fail(SDP_EINVAL, "%s: layout CF needs the CTA segments of the item list", who);
-            if (!T.col_table || ((uintptr_t)T.col_table & 15))
-                return fail(SDP_EINVAL, "%s: layout CF needs the 16-byte aligned column-table scratch", who);
+            if (T.n_cols < 1 || T.tiles_per_col < 1 || T.n_states % T.n_cols != 0)
+                return fail(SDP_EINVAL, "%s: layout CF: the shard must be whole rows of axis 0", who);
         }
         if (T.layout == SDP_LAYOUT_CONTROL_MINOR_FACTORED && T.W > 128)
             return fail(SDP_EINVAL, "%s: layout AF supports at most 128 perturbation nodes", who);
@@ -2127,9 +2143,12 @@ extern "C" int sdp_sweep_partials(const SdpGrid* grid, const SdpTables* tab, con
     if (is_factored(T)) {
         rc = check_factored_args(grid->d, T.W, T.u_mask, "sdp_sweep");
         if (rc) return rc;
-        if (T.layout == SDP_LAYOUT_COLUMN_FACTORED)
+        if (T.layout == SDP_LAYOUT_COLUMN_FACTORED) {
+            rc = check_column_stream(T, "sdp_sweep");
+            if (rc) return rc;
             return grid->d == 2 ? launch_fact_column<2>(G, T, J_prev, part_val, part_idx, st)
                                 : launch_fact_column<3>(G, T, J_prev, part_val, part_idx, st);
+        }
         return grid->d == 2 ? launch_fact<2>(G, T, J_prev, part_val, part_idx, st)
                             : launch_fact<3>(G, T, J_prev, part_val, part_idx, st);
     }
@@ -2141,6 +2160,26 @@ extern "C" int sdp_sweep_partials(const SdpGrid* grid, const SdpTables* tab, con
     }
 }
 
+extern "C" int sdp_column_table(const SdpGrid* grid, const SdpTables* tab, const double* J_prev, void* stream) {
+    GridT<double> G;
+    int rc = make_grid<double>(grid, &G, nullptr);
+    if (rc) return rc;
+    if (!tab) return fail(SDP_EINVAL, "%s", "sdp_column_table: tables is NULL");
+    const SdpTables& T = *tab;
+    rc = check_tables(T, "sdp_column_table");
+    if (rc) return rc;
+    if (!is_column(T)) return fail(SDP_EINVAL, "%s", "sdp_column_table: the tables are not in layout CF");
+    if (T.n_states == 0 || T.n_items == 0) return SDP_OK;
+    rc = check_factored_args(grid->d, T.W, T.u_mask, "sdp_column_table");
+    if (!rc) rc = check_column_stream(T, "sdp_column_table");
+    if (rc) return rc;
+    if (!J_prev) return fail(SDP_EINVAL, "%s", "sdp_column_table: NULL pointer");
+    if (SDP_COLUMN_PITCH(G.order[0], T.W) * 8 > SDP_COLUMN_MAX_SMEM_BYTES)
+        return fail(SDP_EINVAL, "%s", "sdp_column_table: the column table does not fit shared memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    return grid->d == 2 ? launch_column_table<2>(G, T, J_prev, st) : launch_column_table<3>(G, T, J_prev, st);
+}
+
 extern "C" int sdp_sweep_finalize(const SdpTables* tab, const double* part_val,
                                   const int32_t* part_idx, double* J_out, int32_t* argmin_out,
                                   void* stream) {
@@ -2149,6 +2188,7 @@ extern "C" int sdp_sweep_finalize(const SdpTables* tab, const double* part_val,
     int rc = check_tables(T, "sdp_sweep_finalize");
     if (rc) return rc;
     if (T.n_states == 0) return SDP_OK;
+    if (is_column(T) && (rc = check_column_band(T, "sdp_sweep_finalize"))) return rc;
     if (!part_val || !part_idx || !J_out || !argmin_out)
         return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -2307,6 +2347,7 @@ extern "C" int sdp_sweep_finalize_p2p(const SdpTables* tab, const double* part_v
     const SdpTables& T = *tab;
     int rc = check_tables(T, "sdp_sweep_finalize_p2p");
     if (rc) return rc;
+    if (is_column(T) && T.n_states > 0 && (rc = check_column_band(T, "sdp_sweep_finalize_p2p"))) return rc;
     PeersDev P;
     rc = make_peers(peers, &P, "sdp_sweep_finalize_p2p");
     if (rc) return rc;

@@ -121,6 +121,8 @@ def fill_c_tables(T):
             c.n_cols, c.tiles_per_col = T.n_cols, T.tiles_per_col
             c.seg_begin, c.n_segs = T.seg_begin.data_ptr(), T.n_segs
             c.col_table = T.col_table.data_ptr()
+            c.run_end = T.run_end.data_ptr()
+            c.col_table_ready = 0
         c.u_mask = T.u_mask
         c.cell_w = T.cell_w.data_ptr()
         c.lam_w = T.lam_w.data_ptr()
@@ -162,23 +164,48 @@ class ColumnHoistRefused(Exception):
     along a column of the grid"""
 
 
-def column_order(n_states, n_cols):
+def column_order(n_states, n_cols, band_rows=None):
     """Position order of layout CF for a slab of whole rows of state axis 0.
 
     The slab's local states are i = row*n_cols + col (C-order).  Layout CF walks them
-    column by column, every column padded to whole tiles of 32 rows: position
-    p = col*(32*tiles_per_col) + row.  Returns (order, valid, tiles_per_col):
-    order[p] = local state at position p (a padding position repeats the column's last
-    row), valid[p] = False on padding positions."""
+    band by band (`band_rows`: row boundaries [0, ..., n_rows]; default one band), inside a
+    band column by column, every column of a band padded to whole tiles of 32 rows.
+    Returns (order, valid, band_tiles, band_tile_begin, tile_col):
+      order[p]  local state at position p (a padding position repeats the last row of
+                its column in the band), valid[p] False on padding positions;
+      band_tiles[b] tiles per column in band b; band_tile_begin[b] its first tile;
+      tile_col[t] the column of tile t."""
     n_rows = n_states // n_cols
     assert n_rows * n_cols == n_states and n_rows >= 1
-    tiles_per_col = (n_rows + 31) // 32
-    row = np.arange(32 * tiles_per_col, dtype=np.int64)
-    valid_row = row < n_rows
-    row = np.minimum(row, n_rows - 1)
-    order = (row[None, :] * n_cols + np.arange(n_cols, dtype=np.int64)[:, None]).reshape(-1)
-    valid = np.broadcast_to(valid_row[None, :], (n_cols, len(row))).reshape(-1).copy()
-    return order, valid, tiles_per_col
+    if band_rows is None:
+        band_rows = [0, n_rows]
+    band_rows = [int(r) for r in band_rows]
+    assert band_rows[0] == 0 and band_rows[-1] == n_rows and all(a < b for a, b in zip(band_rows, band_rows[1:]))
+    cols = np.arange(n_cols, dtype=np.int64)
+    orders, valids, band_tiles, band_tile_begin, tile_col = [], [], [], [0], []
+    for r0, r1 in zip(band_rows[:-1], band_rows[1:]):
+        tpc = (r1 - r0 + 31) // 32
+        row = r0 + np.arange(32 * tpc, dtype=np.int64)
+        valid_row = row < r1
+        row = np.minimum(row, r1 - 1)
+        orders.append((row[None, :] * n_cols + cols[:, None]).reshape(-1))
+        valids.append(np.broadcast_to(valid_row[None, :], (n_cols, len(row))).reshape(-1))
+        band_tiles.append(tpc)
+        band_tile_begin.append(band_tile_begin[-1] + n_cols * tpc)
+        tile_col.append(np.repeat(cols, tpc))
+    return (np.concatenate(orders), np.concatenate(valids), band_tiles, band_tile_begin,
+            np.concatenate(tile_col))
+
+
+def item_run_ends(run_key):
+    """run_end[i] = index one past the last item of the run of equal consecutive keys
+    containing item i (layout CF: the items of one band and column)"""
+    key = np.asarray(run_key)
+    n = len(key)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    ends = np.concatenate([np.flatnonzero(key[1:] != key[:-1]) + 1, [n]]).astype(np.int64)
+    return ends[np.searchsorted(ends, np.arange(n), side="right")]
 
 
 def column_segments(item_u_count, n_ctas):
@@ -378,6 +405,10 @@ class SweepTables(object):
         self.n_segs = 0
         self.item_u_count_host = None
         self.col_table = None      # device fp64 scratch: the column tables of the current sweep
+        self.run_end = None        # device int64 [n_items]: end of every item's (band, column) run
+        self.bands = None          # dict(rows, tiles, tile_begin, tile_col), see column_order
+        self.band_views = None     # per band: (SdpTables view for the combine pass, first state, states)
+        self.sm_count = 148
         self.slab_times_ms = None  # measured per-rank sweep times (several ranks, see _measured_bounds)
         self.slab_recut = False    # True when those times moved the slab boundaries
 
@@ -788,17 +819,20 @@ class Engine(object):
             pos = {}
 
             def positions(col):
-                """(n_eff, U_eff, host_eff, flat_eff, valid): the slab's states in table order -
-                C-order, or for layout CF column by column with padding (column_order)"""
+                """(n_eff, U_eff, host_eff, flat_eff, valid, bands): the slab's states in table
+                order - C-order, or for layout CF band by band, column by column, with padding
+                (column_order)"""
                 if col not in pos:
                     if not col:
-                        pos[col] = (n, U, host, None, None, 0)
+                        pos[col] = (n, U, host, None, None, None)
                     else:
-                        order, valid, tiles_per_col = column_order(n, n_cols)
+                        bands = self._column_bands(U.reshape(n // n_cols, n_cols).sum(axis=1), W)
+                        order, valid, band_tiles, band_tile_begin, tile_col = column_order(n, n_cols, bands)
                         h = tb.HostStateTable(len(order), nb_control)
                         h.lo, h.hi, h.npts = host.lo[order], host.hi[order], host.npts[order]
                         pos[col] = (len(order), np.where(valid, U[order], 0), h, sb + order, valid,
-                                    tiles_per_col)
+                                    dict(rows=bands, tiles=band_tiles, tile_begin=band_tile_begin,
+                                         tile_col=tile_col))
                 return pos[col]
 
             def sizes(u_mask, col):
@@ -979,7 +1013,8 @@ class Engine(object):
                     if col:
                         # the hoisted table is shared by a column only if the (x,w) part of its
                         # states is the same; checked bit for bit on the built tables
-                        ok = self._column_w_part_ok(T, d, W, n_cols, positions(True)[5], positions(True)[4])
+                        ok = self._column_w_part_ok(T, W, n_cols, positions(True)[5], positions(True)[4],
+                                                    built["lam_w_plane"])
                         if world > 1:
                             ok = bool(min(coll.all_gather_object(ok)))
                         if not ok:
@@ -1017,7 +1052,8 @@ class Engine(object):
             T.g_per_w = g_per_w
             col = column and u_mask == 1
             T.column = col
-            T.n_cols, T.tiles_per_col = (n_cols, positions(True)[5]) if col else (0, 0)
+            T.bands = positions(True)[5] if col else None
+            T.n_cols, T.tiles_per_col = (n_cols, T.bands["tiles"][0]) if col else (0, 0)
             U_eff = positions(col)[1]
             n_tiles, tile_U, tile_off = L["n_tiles"], L["tile_U"], L["tile_off"]
             entry_off, Upad, g_off, tile_g_off = L["entry_off"], L["Upad"], L["g_off"], L["tile_g_off"]
@@ -1039,8 +1075,10 @@ class Engine(object):
             if tiled:
                 per_entry = Wf * 32
                 g_unit_off = tile_off if (T.g_per_w or u_mask) else tile_g_off
+                # (layout CF: the Upad field of an item carries the column of its tile)
                 items, item_begin = make_items(unit_U, chunk, tile_off, per_entry, g_unit_off,
-                                               per_entry if (T.g_per_w or u_mask) else 32, None)
+                                               per_entry if (T.g_per_w or u_mask) else 32,
+                                               T.bands["tile_col"] if col else None)
             else:
                 items, item_begin = make_items(unit_U, chunk, entry_off, 1, g_off, 1, Upad)
             n_items = len(items)
@@ -1052,17 +1090,23 @@ class Engine(object):
                   U_eff.astype(np.int32) if len(U_eff) else np.zeros(1, dtype=np.int32)]
             T.item_u_count_host = items["u_count"].copy() if col else None
             if col:
+                T.sm_count = sm_count
                 up.append(column_segments(T.item_u_count_host, sm_count * self.COLUMN_SEGS_PER_SM))
                 T.n_segs = len(up[-1]) - 1
+                # items of one band and column are consecutive (tiles are ordered that way)
+                tile_band = np.repeat(np.arange(len(T.bands["tiles"])), np.diff(T.bands["tile_begin"]))
+                st_of_item = items["state"].astype(np.int64)
+                up.append(item_run_ends(tile_band[st_of_item] * n_cols + T.bands["tile_col"][st_of_item]))
             else:
-                T.n_segs, T.seg_begin = 0, None
+                T.n_segs, T.seg_begin, T.run_end = 0, None, None
             up = self.to_device_packed(up)
             T.items, T.item_begin, T.U_dev = up[0], up[1], up[2]
             if col:
-                T.seg_begin = up[3]
+                T.seg_begin, T.run_end = up[3], up[4]
                 ensure("col_table", n_cols * _cabi.column_pitch(n_rows0, W), torch.float64)
             else:
                 T.col_table = None
+            T.band_views = None
             n_part = max(n_items, 1) * (32 if tiled else 1)
             T.part_val = torch.empty(n_part, dtype=torch.float64, device=dev)
             T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)
@@ -1111,48 +1155,110 @@ class Engine(object):
         T.seg_begin = self.to_device_packed([seg])[0]
         T.n_segs = len(seg) - 1
         T.c_tables = fill_c_tables(T)
+        T.band_views = T.chunk_plan = None
 
-    def _column_w_part_ok(self, T, d, W, n_cols, tiles_per_col, valid):
+    def _column_w_part_ok(self, T, W, n_cols, bands, valid, lam_w_plane):
         """layout CF: True when, in every column, the (x,w) part of all real states -
         partial cell index and weights of every perturbation node - is bit-identical to
-        that of the column's first row (the one the sweep kernel reads)"""
+        that of the column's first row (lane 0 of its first tile in the first band, the
+        one the sweep kernels read)"""
         torch = _torch()
-        n_wp = n_cols * tiles_per_col * W * 32
-        live = torch.from_numpy(np.ascontiguousarray(valid.reshape(n_cols, tiles_per_col, 1, 32))).to(self.device)
-
-        def same(t):
-            v = t[:n_wp].view(n_cols, tiles_per_col, W, 32)
-            return bool(((v == v[:, :1, :, :1]) | ~live).all().item())
-
-        if not same(T.cell_w):
-            return False
-        for j in range(d - 1):
-            plane = T.lam_w[j * T.lam_w_plane:j * T.lam_w_plane + n_wp].view(torch.int64)
-            if not same(plane):
-                return False
+        live_all = torch.from_numpy(np.ascontiguousarray(valid)).to(self.device)
+        planes = [T.cell_w] + [T.lam_w[j * lam_w_plane:(j + 1) * lam_w_plane].view(torch.int64)
+                               for j in range(T.d - 1)]
+        for t in planes:
+            ref = None
+            for tpc, t0, t1 in zip(bands["tiles"], bands["tile_begin"][:-1], bands["tile_begin"][1:]):
+                v = t[t0 * W * 32:t1 * W * 32].view(n_cols, tpc, W, 32)
+                if ref is None:
+                    ref = v[:, :1, :, :1]
+                live = live_all[t0 * 32:t1 * 32].view(n_cols, tpc, 1, 32)
+                if not bool(((v == ref) | ~live).all().item()):
+                    return False
         return True
+
+    # layout CF on one rank: the rows are cut into bands of decreasing size so that the
+    # results of a band can travel to the host while the next bands are swept (sweep_to_host)
+    COLUMN_BANDS = os.environ.get("SDP_COLUMN_BANDS", "1")       # "auto" | number of bands
+
+    def _column_bands(self, row_weight, W):
+        """row boundaries of the bands of layout CF for a slab whose rows weigh `row_weight`
+        (admissible controls per row)"""
+        n_rows = len(row_weight)
+        mode = self.COLUMN_BANDS
+        one = [0, n_rows]
+        if self.coll.world > 1:
+            return one               # the fused combine + exchange publishes one epoch per sweep
+        if mode == "auto":
+            big = (self._cuda and self.coll.world == 1
+                   and float(np.sum(row_weight)) * W >= self.OVERLAP_MIN_BACKUPS
+                   and os.environ.get("SDP_OVERLAP", "1") != "0")
+            fractions = self.OVERLAP_FRACTIONS if big else (1.0,)
+        else:
+            k = max(1, int(mode))
+            fractions = self.OVERLAP_FRACTIONS[:k - 1] + (1.0,) if k <= len(self.OVERLAP_FRACTIONS) \
+                else tuple([1.0 / k] * k)
+        if len(fractions) == 1 or n_rows < 64 * len(fractions):
+            return one
+        csum = np.cumsum(np.asarray(row_weight, dtype=np.float64))
+        cuts, acc = [0], 0.0
+        for f in fractions[:-1]:
+            acc += f
+            r = int(np.searchsorted(csum, acc * csum[-1], side="left")) + 1
+            r = (r + 31) // 32 * 32                  # whole tiles: no padding lanes inside the slab
+            if cuts[-1] < r < n_rows:
+                cuts.append(r)
+        return cuts + [n_rows]
+
+    def _band_views(self, T):
+        """layout CF: per band (SdpTables view for the combine pass, first state, states)"""
+        if T.band_views is None:
+            views = []
+            B = T.bands
+            for b, tpc in enumerate(B["tiles"]):
+                v = _cabi.SdpTables.from_buffer_copy(T.c_tables)
+                v.item_begin = T.c_tables.item_begin + 8 * int(B["tile_begin"][b])
+                s0, s1 = int(B["rows"][b]) * T.n_cols, int(B["rows"][b + 1]) * T.n_cols
+                v.n_states = s1 - s0
+                v.tiles_per_col = int(tpc)
+                views.append((v, s0, s1 - s0))
+            T.band_views = views
+        return T.band_views
+
+    def _finalize(self, T, J_out, argmin, stream=None):
+        """the combine pass: one launch, or for layout CF one per band"""
+        stream = self.stream if stream is None else stream
+        if not T.column:
+            rc = self.lib.sdp_sweep_finalize(ctypes.byref(T.c_tables), self._ptr(T.part_val),
+                                             self._ptr(T.part_idx), self._ptr(J_out), self._ptr(argmin), stream)
+            _cabi.check(rc, "sdp_sweep_finalize")
+            return
+        for v, s0, ns in self._band_views(T):
+            rc = self.lib.sdp_sweep_finalize(ctypes.byref(v), self._ptr(T.part_val), self._ptr(T.part_idx),
+                                             ctypes.c_void_p(J_out.data_ptr() + 8 * s0),
+                                             ctypes.c_void_p(argmin.data_ptr() + 4 * s0), stream)
+            _cabi.check(rc, "sdp_sweep_finalize")
 
     def sweep_local(self, T, J_prev, events=None):
         """Enqueue K1 on this rank's slab.  J_prev: device fp64 [n_grid].
         Results land in T.J_out / T.argmin (slab-local).  `events`: optional
         (start, end) torch.cuda.Event pair recorded around the streaming kernel
         alone (bench roofline)."""
-        if events is None:
+        if events is None and not T.column:
             rc = self.lib.sdp_sweep(ctypes.byref(T.grid), ctypes.byref(T.c_tables), self._ptr(J_prev),
                                     self._ptr(T.part_val), self._ptr(T.part_idx),
                                     self._ptr(T.J_out), self._ptr(T.argmin), self.stream)
             _cabi.check(rc, "sdp_sweep")
             return
-        events[0].record()
+        if events is not None:
+            events[0].record()
         rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
                                          self._ptr(J_prev), self._ptr(T.part_val),
                                          self._ptr(T.part_idx), self.stream)
         _cabi.check(rc, "sdp_sweep_partials")
-        events[1].record()
-        rc = self.lib.sdp_sweep_finalize(ctypes.byref(T.c_tables), self._ptr(T.part_val),
-                                         self._ptr(T.part_idx), self._ptr(T.J_out),
-                                         self._ptr(T.argmin), self.stream)
-        _cabi.check(rc, "sdp_sweep_finalize")
+        if events is not None:
+            events[1].record()
+        self._finalize(T, T.J_out, T.argmin)
 
     def sweep(self, T, J_prev, J_new, rel_ref_index=None, ref_out=None, resid_out=None,
               events=None):
@@ -1204,7 +1310,9 @@ class Engine(object):
     OVERLAP_FRACTIONS = (0.45, 0.25, 0.15, 0.10, 0.05)
 
     def can_overlap_results(self, T):
-        return (self._cuda and self.coll.world == 1 and not T.column and T.n_items >= self.OVERLAP_MIN_ITEMS
+        if T.column and len(T.bands["tiles"]) < 2:
+            return False             # layout CF streams its results band by band
+        return (self._cuda and self.coll.world == 1 and T.n_items >= self.OVERLAP_MIN_ITEMS
                 and T.n_backups_local >= self.OVERLAP_MIN_BACKUPS
                 and os.environ.get("SDP_OVERLAP", "1") != "0")
 
@@ -1215,6 +1323,22 @@ class Engine(object):
         travel to the host while the next run computes"""
         if T.chunk_plan is not None:
             return T.chunk_plan
+        if T.column:
+            # one run per band: its own CTA segments over the band's items (absolute item
+            # indices, the column tables are tabulated once before the first run)
+            plan = []
+            tb0 = T.bands["tile_begin"]
+            for b, (view, s0, ns) in enumerate(self._band_views(T)):
+                i0, i1 = int(T.item_begin_host[tb0[b]]), int(T.item_begin_host[tb0[b + 1]])
+                seg = i0 + column_segments(T.item_u_count_host[i0:i1], T.sm_count * self.COLUMN_SEGS_PER_SM)
+                seg_dev = self.to_device_packed([seg])[0]
+                cp = _cabi.SdpTables.from_buffer_copy(T.c_tables)
+                cp.seg_begin, cp.n_segs, cp.col_table_ready = seg_dev.data_ptr(), len(seg) - 1, 1
+                plan.append(dict(tab_p=cp, tab_f=view, s0=s0, s1=s0 + ns, keep=seg_dev,
+                                 pv=ctypes.c_void_p(T.part_val.data_ptr()),
+                                 pi=ctypes.c_void_p(T.part_idx.data_ptr())))
+            T.chunk_plan = plan
+            return plan
         us = 32 if T.tiled else 1
         n_units = len(T.unit_U_host)
         csum = np.cumsum(T.unit_U_host)
@@ -1262,6 +1386,10 @@ class Engine(object):
         pol = torch.empty((n, nc), dtype=torch.float64, device=dev)
         J_pin = self.host_result_buffer((n,), torch.float64)
         pol_pin = self.host_result_buffer((n, nc), torch.float64)
+        if T.column:
+            rc = self.lib.sdp_column_table(ctypes.byref(T.grid), ctypes.byref(T.c_tables), self._ptr(J_prev),
+                                           self.stream)
+            _cabi.check(rc, "sdp_column_table")
         ev0 = torch.cuda.Event()
         ev0.record(main)
         for k, ch in enumerate(self._chunk_plan(T)):

@@ -270,6 +270,17 @@ class FakeLib(object):
         return out
 
     def sdp_sweep(self, gref, tref, J_prev, part_val, part_idx, J_out, argmin_out, stream):
+        self.sdp_sweep_partials(gref, tref, J_prev, part_val, part_idx, stream)
+        return self.sdp_sweep_finalize(tref, part_val, part_idx, J_out, argmin_out, stream)
+
+    def sdp_column_table(self, gref, tref, J_prev, stream):
+        T = tref._obj
+        assert T.layout == _cabi.LAYOUT_COLUMN_FACTORED and T.col_table and T.run_end and T.seg_begin
+        self.col_table_J = _arr(J_prev, int(np.prod(_grid(gref)[3])), ctypes.c_double).copy()
+        self.launches += 1
+        return 0
+
+    def sdp_sweep_partials(self, gref, tref, J_prev, part_val, part_idx, stream):
         d, smin, smax, orders = _grid(gref)
         T = tref._obj
         n_grid = int(np.prod(orders))
@@ -289,13 +300,15 @@ class FakeLib(object):
         n_pos = T.n_states        # entries of U: states, or (layout CF) positions incl. padding lanes
         if column:
             assert T.u_mask == 1 and T.n_states % T.n_cols == 0
-            assert T.tiles_per_col == (T.n_states // T.n_cols + 31) // 32
-            n_pos = T.n_cols * T.tiles_per_col * 32
-            # every CTA segment is a run of the item list; together they cover it once
+            n_pos = (int(items["state"].max()) + 1) * 32 if len(items) else 0
+            # every CTA segment is a run of the item list (this launch may cover only a part of it)
             seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
-            assert seg[0] == 0 and seg[-1] == T.n_items and np.all(np.diff(seg) >= 0)
-            assert np.all(np.diff(items["state"]) >= 0)          # ordered by tile, hence by column
+            assert 0 <= seg[0] and seg[-1] <= T.n_items and np.all(np.diff(seg) >= 0)
+            assert np.all(np.diff(items["state"]) >= 0)          # ordered by tile
             assert T.col_table and T.col_table % 16 == 0         # scratch for the column tables
+            if T.col_table_ready:
+                # the caller ran the pre-pass (sdp_column_table) on this J
+                assert np.array_equal(self.col_table_J.view(np.int64), J.view(np.int64))
         Us = _arr(T.U, n_pos, ctypes.c_int32)
 
         def lerp(c, lam):
@@ -399,8 +412,23 @@ class FakeLib(object):
                     else:
                         j = first_min(acc[:n_ok, lane])
                         pv[n_it * 32 + lane], pi[n_it * 32 + lane] = acc[j, lane], ub + j
-        n_units = (n_pos + 31) // 32 if tiled else T.n_states
+        self.launches += 1
+        return 0
+
+    def sdp_sweep_finalize(self, tref, part_val, part_idx, J_out, argmin_out, stream):
+        T = tref._obj
+        column = T.layout == _cabi.LAYOUT_COLUMN_FACTORED
+        tiled = column or T.layout in (_cabi.LAYOUT_STATE_MINOR, _cabi.LAYOUT_STATE_MINOR_FACTORED)
+        width = 32 if tiled else 1
+        n_units = (T.n_states + 31) // 32 if tiled else T.n_states
+        if column:
+            # one band of whole rows: n_states, tiles_per_col and item_begin are the band's
+            assert T.n_states % T.n_cols == 0 and T.tiles_per_col == (T.n_states // T.n_cols + 31) // 32
+            n_units = T.n_cols * T.tiles_per_col
         ib = _arr(T.item_begin, n_units + 1, ctypes.c_int64)
+        top = int(ib[-1]) * width
+        pv = _arr(part_val, top, ctypes.c_double)
+        pi = _arr(part_idx, top, ctypes.c_int32)
         Jo = _arr(J_out, T.n_states, ctypes.c_double)
         ao = _arr(argmin_out, T.n_states, ctypes.c_int32)
         for i in range(T.n_states):
@@ -414,7 +442,7 @@ class FakeLib(object):
                 if _better(pv[kk], int(pi[kk]), bv, bi):
                     bv, bi = pv[kk], int(pi[kk])
             Jo[i], ao[i] = bv, bi
-        self.launches += 2
+        self.launches += 1
         return 0
 
     def _column_partials(self, T, d, J, strides, orders, items, p, pv, pi, Us):
@@ -422,17 +450,17 @@ class FakeLib(object):
         list; at every column change the table R[row][w] = inner interpolation over the axes
         1..d-1 is rebuilt from the w-part of lane 0 of the column's first tile; a backup is
         (1-l0)*R[q0][w] + l0*R[q0+1][w] with q0 = cell_u / stride0"""
-        W, Tc = T.W, T.tiles_per_col
+        W, Tc = T.W, T.tiles_per_col          # (tiles per column of the FIRST band)
         seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
-        ib = _arr(T.item_begin, T.n_cols * Tc + 1, ctypes.c_int64)
+        run_end = _arr(T.run_end, T.n_items, ctypes.c_int64)
         rows, stride0 = int(orders[0]), int(strides[0])
         P = W | 1
         done = np.zeros(len(items), dtype=bool)
         for b in range(T.n_segs):
             i, seg_end = int(seg[b]), int(seg[b + 1])
             while i < seg_end:
-                col = int(items[i]["state"]) // Tc
-                e = min(int(ib[(col + 1) * Tc]), seg_end)
+                col = int(items[i]["Upad"])       # layout CF: the column of the item's tile
+                e = min(int(run_end[i]), seg_end)
                 R = np.full(rows * P + 9, np.nan)
                 for w in range(W):
                     f = (col * Tc * W + w) * 32
@@ -449,7 +477,7 @@ class FakeLib(object):
                     R[np.arange(rows) * P + w] = rec(np.arange(rows, dtype=np.int64) * stride0 + cw, 1)
                 for n_it in range(i, e):
                     it = items[n_it]
-                    assert int(it["state"]) // Tc == col and not done[n_it]
+                    assert int(it["Upad"]) == col and not done[n_it]
                     done[n_it] = True
                     cnt, ub, eb, tix = int(it["u_count"]), int(it["u_begin"]), int(it["entry_base"]), int(it["state"])
                     assert int(it["g_base"]) == eb
@@ -473,12 +501,7 @@ class FakeLib(object):
                             j = int(np.argmax(nan)) if nan.any() else int(np.argmin(a))
                             pv[n_it * 32 + lane], pi[n_it * 32 + lane] = a[j], ub + j
                 i = e
-        assert done.all()
-
-    def sdp_sweep_partials(self, *a):
-        raise NotImplementedError("the model implements sdp_sweep as a whole")
-
-    sdp_sweep_finalize = sdp_sweep_partials
+        assert done[int(seg[0]):int(seg[-1])].all()
 
     def sdp_policy_eval(self, gref, W, g_per_w, p, cell, lam, lam_plane, g, n_states, state_begin,
                         n_grid, J_a, J_b, n_iter, rel_dp, ref_index, hist, stream):

@@ -364,19 +364,35 @@ int main(void) {
 
 
 def test_column_order_and_row_aligned_bounds():
-    """layout CF walks a slab of whole rows column by column, every column padded to
-    whole tiles of 32 rows; slab boundaries are moved to whole rows"""
-    from stodynprog_b200.engine import column_order, row_aligned
-    order, valid, tiles = column_order(70 * 5, 5)
-    assert tiles == 3 and len(order) == 5 * 96 and valid.sum() == 350
+    """layout CF walks a slab of whole rows band by band, column by column, every column
+    of a band padded to whole tiles of 32 rows; slab boundaries are moved to whole rows"""
+    from stodynprog_b200.engine import column_order, row_aligned, item_run_ends, column_segments
+    order, valid, tiles, tile_begin, tile_col = column_order(70 * 5, 5)
+    assert tiles == [3] and tile_begin == [0, 15] and len(order) == 5 * 96 and valid.sum() == 350
     assert sorted(order[valid]) == list(range(350))              # every state exactly once
+    assert list(tile_col) == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4]
     o = order.reshape(5, 96)
     v = valid.reshape(5, 96)
     for c in range(5):
         assert list(o[c, :70]) == [r * 5 + c for r in range(70)]   # lane <-> row of the column
         assert np.all(o[c, 70:] == 69 * 5 + c) and not v[c, 70:].any() and v[c, :70].all()
-    order, valid, tiles = column_order(64 * 3, 3)
-    assert tiles == 2 and valid.all() and len(order) == 192
+    order, valid, tiles, tile_begin, tile_col = column_order(64 * 3, 3)
+    assert tiles == [2] and valid.all() and len(order) == 192
+    # two bands: rows 0..39 (2 tiles per column, 24 padding lanes) and 40..69 (1 tile, 2 padding lanes)
+    order, valid, tiles, tile_begin, tile_col = column_order(70 * 5, 5, [0, 40, 70])
+    assert tiles == [2, 1] and tile_begin == [0, 10, 15] and len(order) == 32 * 15
+    assert sorted(order[valid]) == list(range(350))
+    assert list(tile_col) == [0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 0, 1, 2, 3, 4]
+    assert list(order[:40]) == [r * 5 for r in range(40)] and not valid[40:64].any()
+    band1 = order[320:].reshape(5, 32)
+    assert list(band1[2, :30]) == [r * 5 + 2 for r in range(40, 70)]
+    with pytest.raises(AssertionError):
+        column_order(70 * 5, 5, [0, 40, 60])
+    assert list(item_run_ends([3, 3, 3, 4, 9, 9])) == [3, 3, 3, 4, 6, 6]
+    assert list(item_run_ends([])) == [] and list(item_run_ends([7])) == [1]
+    seg = column_segments(np.array([10, 10, 10, 10, 30, 10]), 3)
+    assert seg[0] == 0 and seg[-1] == 6 and len(seg) == 4 and np.all(np.diff(seg) >= 0)
+    assert list(column_segments(np.array([5, 5]), 148)) == [0, 1, 2]
     assert row_aligned([0, 103, 251, 350], 5) == [0, 105, 250, 350]
     assert row_aligned([0, 2, 3, 350], 5) == [0, 0, 5, 350]
     assert row_aligned([0, 349, 350], 5) == [0, 350, 350]

@@ -814,6 +814,38 @@ def test_column_hoist_solvers_and_chunking(product, backend):
             assert np.array_equal(np.asarray(a).view(np.int64), np.asarray(b).view(np.int64))
 
 
+@pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
+@pytest.mark.parametrize("which", ["ar1_w3_tall", "searev_tall"])
+def test_column_hoist_row_bands(product, backend, which, monkeypatch):
+    """layout CF with the rows cut into several bands (tiles ordered band by band, one
+    combine launch per band): same J and policies, bit for bit, as one band and as BF"""
+    from stodynprog_b200 import workloads as wl
+    from stodynprog_b200.engine import Engine
+    out = {}
+    for bands in ("off", "1", "3", "5"):
+        monkeypatch.setattr(Engine, "COLUMN_BANDS", "1" if bands == "off" else bands)
+        api = _Api(product, backend, "state_minor", "auto", "on")
+        if which == "ar1_w3_tall":
+            sv = wl.storage_ar1(api, n_E=330, n_P=3, n_w=3, steps=(2.0, 0.1)).solver
+        else:
+            prob = wl.searev(api, n_E=330, n_S=3, n_A=2)
+            prob.solver.control_steps = (.2,)
+            sv = prob.solver
+        sv.column_hoist = "off" if bands == "off" else "on"
+        J0 = np.random.default_rng(8).standard_normal(sv._state_grid_shape)
+        J1, pol1 = sv.value_iteration(J0, report_time=False)
+        T = sv.last_tables
+        if bands != "off":
+            assert T.column and len(T.bands["tiles"]) == int(bands)
+            assert T.bands["rows"][0] == 0 and T.bands["rows"][-1] == sv._state_grid_shape[0]
+            assert all(r % 32 == 0 for r in T.bands["rows"][:-1])
+        J2, pol2 = sv.value_iteration(J1, report_time=False)
+        out[bands] = (J1, pol1, J2, pol2)
+    for bands, res in out.items():
+        for a, b in zip(out["off"], res):
+            assert np.array_equal(a.view(np.int64), b.view(np.int64)), bands
+
+
 def test_column_hoist_is_refused_when_it_does_not_apply(product):
     """a w-part that varies along a column is detected on the built tables: "auto" falls
     back to layout BF (same results), "on" raises; so do grids or layouts CF cannot take"""
@@ -1068,3 +1100,38 @@ def test_overlapped_result_copy_is_bit_identical(product, layout, compress):
                 Engine.PINNED_RESULT_BUDGET = budget
         finally:
             Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = saved
+
+
+@gpu
+@pytest.mark.parametrize("bands", ["3", "5"])
+def test_column_hoist_overlapped_result_copy(product, bands, monkeypatch):
+    """layout CF, large-sweep path of value_iteration: the column tables are tabulated
+    once, every band is swept by its own launch (its own CTA segments over the band's
+    items) on alternating streams, combined and copied to the host while the next bands
+    compute - same J and policies as the plain path and as layout BF"""
+    from stodynprog_b200 import workloads as wl
+    from stodynprog_b200.engine import Engine
+    monkeypatch.setattr(Engine, "COLUMN_BANDS", bands)
+    res = {}
+    for colmode in ("off", "on"):
+        api = _Api(product, "cuda", "state_minor", "auto", "on")
+        sv = wl.storage_ar1(api, n_E=400, n_P=7, n_w=9, steps=(0.5, 0.1)).solver
+        sv.column_hoist = colmode
+        J0 = np.random.default_rng(9).standard_normal(sv._state_grid_shape)
+        monkeypatch.setattr(Engine, "OVERLAP_MIN_BACKUPS", 1 << 62)
+        monkeypatch.setattr(Engine, "OVERLAP_MIN_ITEMS", 1 << 62)
+        J_a, pol_a = sv.value_iteration(J0, report_time=False)
+        T = sv.last_tables
+        assert not sv.engine.can_overlap_results(T) and T.column == (colmode == "on")
+        monkeypatch.setattr(Engine, "OVERLAP_MIN_BACKUPS", 0)
+        monkeypatch.setattr(Engine, "OVERLAP_MIN_ITEMS", 0)
+        assert sv.engine.can_overlap_results(T)
+        if T.column:
+            assert len(T.bands["tiles"]) == int(bands) == len(sv.engine._chunk_plan(T))
+        for _ in range(3):
+            J_b, pol_b = sv.value_iteration(J0, report_time=False)
+            assert np.array_equal(J_a, J_b) and np.array_equal(pol_a, pol_b)
+        J_c, pol_c = sv.value_iteration(J_b, report_time=False)       # page-locked input, second sweep
+        res[colmode] = (J_a, pol_a, J_c, pol_c)
+    for a, b in zip(res["off"], res["on"]):
+        assert np.array_equal(a.view(np.int64), b.view(np.int64))
