@@ -635,6 +635,7 @@ def test_factored_tables_and_sweep_equal_dense(product, backend, layout, which):
     the factored sweep returns bit-identical J and argmin (K1)"""
     dense = _factor_case(_Api(product, backend, layout, "auto", "off"), which)
     fact = _factor_case(_Api(product, backend, layout, "auto", "on"), which)
+    fact.column_hoist = "off"         # (layout CF reorders the tiles; it has its own tests)
     Td, Tf = dense.sweep_tables(), fact.sweep_tables()
     assert not Td.factored and Tf.factored
     if FACTOR_CASES[which] is not None:
@@ -1068,6 +1069,7 @@ def test_overlapped_result_copy_is_bit_identical(product, layout, compress):
     for prob in (wl.storage_ar1(api, n_E=40, n_P=37, steps=(0.05, 0.1), item_chunk=48),
                  _searev_small(api)):
         sv = prob.solver
+        sv.column_hoist = "off"       # (layout CF streams its results band by band: own test)
         J0 = np.random.default_rng(7).standard_normal(sv._state_grid_shape)
         saved = (Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS)
         try:
