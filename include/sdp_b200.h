@@ -219,9 +219,10 @@ int64_t sdp_launch_count(void);
  * "tma_rows" (4|8), "tma_stages" (2..16), "tma_warps" (1..16), "hoist" (layout AF
  * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4),
  * "hoist_const" (0|1: constant-W variant of that kernel for W <= 9),
- * "col_threads" (layout CF: threads per CTA, 128..512), "col_ub" (controls per iteration, 1|2),
- * "col_pf" (groups of col_ub controls in flight, 1|2), "col_prepass" (1: column tables
- * from the coalesced pre-pass, default; 0: every CTA gathers its own from J_prev),
+ * "col_threads" (layout CF: threads per CTA, 128..768), "col_ub" (controls per iteration, 1|2),
+ * "col_pf" (groups of col_ub controls in flight, 1|2), "col_prepass" (column tables
+ * from the coalesced pre-pass, copied into shared memory by the TMA engine = 2, default, or by
+ * vector loads = 1; 0: every CTA gathers its own from J_prev),
  * "p2p_timeout_s" (bound of the peer-flag waits, default 600 s, then the kernel traps).
  * Not thread-safe against concurrent launches. */
 int sdp_set_option(const char* name, int value);

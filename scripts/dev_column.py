@@ -81,6 +81,7 @@ def e2e(n=8):
         1e3 * dt, T.n_backups_total / dt / 1e9, eng.can_overlap_results(T)), J_h, pol_h
 
 
+quick = bool(os.environ.get("COLUMN_QUICK"))
 Tc = build("on", "1")
 ref = {}
 for n in (1, 3):
@@ -88,15 +89,15 @@ for n in (1, 3):
 print("CF 1 band     :", timed(Tc), flush=True)
 msg, Jc_h, polc_h = e2e()
 print("CF 1 band     :", msg, flush=True)
-for pre in (0, 1):
+for pre in (0, 1, 2):
     _cabi.check(lib.sdp_set_option(b"col_prepass", pre), "opt")
-    print("CF 1 band, column tables %s:" % ("from the pre-pass" if pre else "gathered by every CTA"),
-          timed(Tc), flush=True)
+    print("CF 1 band, column tables %s:" % ("gathered by every CTA", "pre-pass + vector-load copy",
+                                            "pre-pass + TMA bulk copy")[pre], timed(Tc), flush=True)
 sm = torch.cuda.get_device_properties(0).multi_processor_count
-for per_sm in (1, 2, 4):
+for per_sm in ((1,) if quick else (1, 2)):
     eng.set_column_segments(Tc, sm * per_sm)
-    for threads in (512, 384, 256):
-        for ub, pf in ((2, 2), (2, 1), (1, 2), (1, 1)):
+    for threads in (512, 576, 640, 704, 768):
+        for ub, pf in ((2, 2), (2, 1), (1, 2)):
             _cabi.check(lib.sdp_set_option(b"col_threads", threads), "opt")
             _cabi.check(lib.sdp_set_option(b"col_ub", ub), "opt")
             _cabi.check(lib.sdp_set_option(b"col_pf", pf), "opt")
@@ -121,13 +122,17 @@ print("e2e results CF == BF:", np.array_equal(Jc_h.view(np.int64), Jb_h.view(np.
       np.array_equal(polc_h, polb_h), flush=True)
 del Tb
 
-T5 = build("on", "auto")
-print("CF bands %s:" % (T5.bands["rows"],), timed(T5), flush=True)
-J5, a5 = sweeps(T5, 3)
-print("CF banded vs CF 1 band after 3 sweeps: J %s argmin %s"
-      % (bool(torch.equal(J5.view(torch.int64), ref[3][0].view(torch.int64))), bool(torch.equal(a5, ref[3][1]))),
-      flush=True)
-msg, J5_h, pol5_h = e2e()
-print("CF banded     :", msg, flush=True)
-print("e2e results CF banded == BF:", np.array_equal(J5_h.view(np.int64), Jb_h.view(np.int64)),
-      np.array_equal(pol5_h, polb_h), flush=True)
+for bands in ("auto", "3", "2"):
+    T5 = build("on", bands)
+    for threads in (512, 640):
+        _cabi.check(lib.sdp_set_option(b"col_threads", threads), "opt")
+        print("CF bands %s threads=%d:" % (T5.bands["rows"], threads), timed(T5), flush=True)
+        J5, a5 = sweeps(T5, 3)
+        print("   vs CF 1 band after 3 sweeps: J %s argmin %s"
+              % (bool(torch.equal(J5.view(torch.int64), ref[3][0].view(torch.int64))),
+                 bool(torch.equal(a5, ref[3][1]))), flush=True)
+        msg, J5_h, pol5_h = e2e()
+        print("   ", msg, "; results == BF:", np.array_equal(J5_h.view(np.int64), Jb_h.view(np.int64)),
+              np.array_equal(pol5_h, polb_h), flush=True)
+    lib.sdp_set_option(b"col_threads", 512)
+    del T5

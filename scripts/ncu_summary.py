@@ -22,6 +22,13 @@ WANT = [
     'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__grid_size',
     'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'sm__maximum_warps_per_active_cycle_pct',
     'launch__waves_per_multiprocessor', 'smsp__cycles_active.avg',
+    'launch__shared_mem_per_block_static', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum', 'smsp__inst_executed_op_shared_ld.sum',
+    'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.sum',
+    'sm__inst_executed_pipe_alu.sum', 'sm__inst_executed_pipe_fmaheavy.sum',
+    'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'smsp__inst_executed_pipe_uniform.sum', 'sm__inst_executed_pipe_cbu.sum',
 ]
 
 rows = list(csv.reader(sys.stdin))

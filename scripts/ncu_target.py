@@ -1,6 +1,6 @@
 """target for ncu captures: build one workload and run a few sweeps.
     python scripts/ncu_target.py {ar1|large|searev} {on|off} [n_sweeps]
-env: N_E (large), SEAREV_N_E, LAYOUT"""
+env: N_E (large), SEAREV_N_E, LAYOUT, COLUMN (on|off|auto: layout CF)"""
 import os
 import sys
 
@@ -15,6 +15,7 @@ from dev_factored import make  # noqa: E402
 which, compress = sys.argv[1], sys.argv[2]
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 sv = make(which, compress, os.environ.get("LAYOUT", "state_minor" if which == "large" else "auto"))
+sv.column_hoist = os.environ.get("COLUMN", "auto")
 T = sv.sweep_tables()
 eng = sv.engine
 J_prev = eng.to_device(np.random.default_rng(0).standard_normal(int(np.prod(sv._state_grid_shape))))

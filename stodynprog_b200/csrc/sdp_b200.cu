@@ -1051,7 +1051,7 @@ struct Tuning {
     int col_threads;   // layout CF: threads per CTA (one CTA per SM: the column table fills shared memory)
     int col_ub;        // layout CF: controls per lane per iteration (1|2)
     int col_pf;        // layout CF: groups of col_ub controls in flight per lane (1|2)
-    int col_prepass;   // layout CF: column tables from the coalesced pre-pass (1) or gathered by every CTA (0)
+    int col_prepass;   // layout CF: column tables from the coalesced pre-pass, copied by vector loads (1) or by the TMA engine (2); 0: gathered by every CTA
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static int env_int(const char* name, int dflt) {
@@ -1082,10 +1082,10 @@ static Tuning& tuning() {
         x.hoist_upl = env_int("SDP_HOIST_UPL", 2) == 4 ? 4 : 2;
         x.p2p_timeout_s = clampi(env_int("SDP_P2P_TIMEOUT_S", 600), 1, 86400);
         x.hoist_const = env_int("SDP_HOIST_CONST", 1) != 0;
-        x.col_threads = clampi(env_int("SDP_COL_THREADS", 512), 128, 512) / 32 * 32;
+        x.col_threads = clampi(env_int("SDP_COL_THREADS", 512), 128, 768) / 32 * 32;
         x.col_ub = env_int("SDP_COL_UB", 2) == 1 ? 1 : 2;
         x.col_pf = env_int("SDP_COL_PF", 2) == 1 ? 1 : 2;
-        x.col_prepass = env_int("SDP_COL_PREPASS", 1) != 0;
+        x.col_prepass = clampi(env_int("SDP_COL_PREPASS", 2), 0, 2);
         return x;
     }();
     return t;
@@ -1104,10 +1104,10 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "hoist_upl")) t.hoist_upl = (value == 4) ? 4 : 2;
     else if (!strcmp(name, "p2p_timeout_s")) t.p2p_timeout_s = clampi(value, 1, 86400);
     else if (!strcmp(name, "hoist_const")) t.hoist_const = value != 0;
-    else if (!strcmp(name, "col_threads")) t.col_threads = clampi(value, 128, 512) / 32 * 32;
+    else if (!strcmp(name, "col_threads")) t.col_threads = clampi(value, 128, 768) / 32 * 32;
     else if (!strcmp(name, "col_ub")) t.col_ub = (value == 1) ? 1 : 2;
     else if (!strcmp(name, "col_pf")) t.col_pf = (value == 1) ? 1 : 2;
-    else if (!strcmp(name, "col_prepass")) t.col_prepass = value != 0;
+    else if (!strcmp(name, "col_prepass")) t.col_prepass = clampi(value, 0, 2);
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1810,16 +1810,26 @@ static int launch_column_table(const GridT<double>& G, const SdpTables& T, const
     return SDP_OK;
 }
 
-template <int D, int WM, int UB, int PF, bool FULL>     // FULL: W == WM, every slot live
-__global__ void __launch_bounds__(512, 1)
+// MAXT: launch bound (512 threads leave 128 registers per thread, 640 leave 102, 768 leave 85).
+// prepass: 0 = the CTA gathers its table from J_prev, 1 = copies it from col_table with
+// vector loads, 2 = with one bulk asynchronous copy (TMA engine, SASS UBLKCP) on an mbarrier.
+template <int D, int WM, int UB, int PF, bool FULL, int MAXT>     // FULL: W == WM, every slot live
+__global__ void __launch_bounds__(MAXT, 1)
 k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
                     double* __restrict__ part_val, int32_t* __restrict__ part_idx,
                     double inv_stride0, PVals PV, int64_t pitch, int prepass) {
     constexpr int NW = D - 1;
-    extern __shared__ __align__(16) unsigned char csm[];
+    extern __shared__ __align__(128) unsigned char csm[];
     double* R_sh = reinterpret_cast<double*>(csm);      // [order[0]][P] + slack = `pitch` doubles
     __shared__ int cw_sh[WM];
     __shared__ double lw_sh[NW][WM];
+    __shared__ __align__(8) uint64_t tbar;              // completion of the bulk copy of a table
+    uint32_t tphase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&tbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const int W = T.W;
     const int P = W | 1;        // odd row pitch: adjacent rows never share a bank pair
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -1833,11 +1843,32 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
         const int64_t run_end = T.run_end[i];     // end of the items of this band and column
         const int64_t e = run_end < seg_end ? run_end : seg_end;
         __syncthreads();                 // the previous column's readers are done with R
-        if (prepass) {
-            // the column's table, tabulated by k_column_table: one contiguous block
+        if (prepass == 2) {
+            // the column's table, tabulated by k_column_table, is one contiguous block: one
+            // thread hands it to the TMA engine in <= 32 KB pieces, everybody waits on the barrier
+            if (threadIdx.x == 0) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(T.col_table + (int64_t)col * pitch);
+                const uint32_t bytes = (uint32_t)(pitch * 8);
+                const uint32_t bar = smem_u32(&tbar);
+                mbar_expect_tx(bar, bytes);
+                for (uint32_t o = 0; o < bytes; o += 32768u)
+                    bulk_g2s(smem_u32(csm + o), src + o, min(32768u, bytes - o), bar);
+            }
+            mbar_wait(smem_u32(&tbar), tphase);
+            tphase ^= 1u;
+        } else if (prepass) {
             const double2* __restrict__ src = reinterpret_cast<const double2*>(T.col_table + (int64_t)col * pitch);
             double2* dst = reinterpret_cast<double2*>(R_sh);
-            for (int k = threadIdx.x; k < (int)(pitch >> 1); k += blockDim.x) dst[k] = src[k];
+            const int n2 = (int)(pitch >> 1);
+            int k = threadIdx.x;
+            for (; k + 7 * (int)blockDim.x < n2; k += 8 * blockDim.x) {     // 8 independent loads in flight
+                double2 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = src[k + j * blockDim.x];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[k + j * blockDim.x] = v[j];
+            }
+            for (; k < n2; k += blockDim.x) dst[k] = src[k];
         } else {
             if (threadIdx.x < W) {
                 // the column's w-part: lane 0 of its first tile
@@ -1941,9 +1972,9 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
     }
 }
 
-template <int D, int WM, int UB, int PF>
+template <int D, int WM, int UB, int PF, int MAXT>
 static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, const double* Jprev,
-                                double* part_val, int32_t* part_idx, cudaStream_t st) {
+                                double* part_val, int32_t* part_idx, cudaStream_t st, int threads) {
     const int64_t pitch = SDP_COLUMN_PITCH(G.order[0], T.W);
     const size_t shm = (size_t)pitch * 8;
     if (shm > SDP_COLUMN_MAX_SMEM_BYTES)
@@ -1955,10 +1986,10 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
     }
     static size_t attr_set = 0;          // per instantiation
     if (attr_set < shm) {
-        cudaError_t e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, true>,
+        cudaError_t e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, true, MAXT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, false>,
+            e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, false, MAXT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
         if (e != cudaSuccess) return fail(SDP_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = shm;
@@ -1968,10 +1999,10 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
         pv.v[w] = (w < T.W) ? (T.expect ? T.p_host[w] : 1.0) : 0.0;
     const double inv0 = 1.0 / (double)G.stride[0];
     if (T.W == WM)
-        k_sweep_fact_column<D, WM, UB, PF, true><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
+        k_sweep_fact_column<D, WM, UB, PF, true, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
             G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass);
     else
-        k_sweep_fact_column<D, WM, UB, PF, false><<<(unsigned)T.n_segs, tuning().col_threads, shm, st>>>(
+        k_sweep_fact_column<D, WM, UB, PF, false, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
             G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
@@ -1980,12 +2011,20 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
 template <int D, int WM>
 static int launch_fact_column_w(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                                 double* part_val, int32_t* part_idx, cudaStream_t st) {
-    const int ub = tuning().col_ub, pf = tuning().col_pf;
+    const int ub = tuning().col_ub, pf = tuning().col_pf, threads = tuning().col_threads;
+    if (threads > 640) {       // 85 registers per thread
+        if (ub == 2) return launch_fact_column_k<D, WM, 2, 1, 768>(G, T, Jprev, part_val, part_idx, st, threads);
+        return pf == 2 ? launch_fact_column_k<D, WM, 1, 2, 768>(G, T, Jprev, part_val, part_idx, st, threads)
+                       : launch_fact_column_k<D, WM, 1, 1, 768>(G, T, Jprev, part_val, part_idx, st, threads);
+    }
+    if (threads > 512)
+        return pf == 2 ? launch_fact_column_k<D, WM, 2, 2, 640>(G, T, Jprev, part_val, part_idx, st, threads)
+                       : launch_fact_column_k<D, WM, 2, 1, 640>(G, T, Jprev, part_val, part_idx, st, threads);
     if (ub == 2)
-        return pf == 2 ? launch_fact_column_k<D, WM, 2, 2>(G, T, Jprev, part_val, part_idx, st)
-                       : launch_fact_column_k<D, WM, 2, 1>(G, T, Jprev, part_val, part_idx, st);
-    return pf == 2 ? launch_fact_column_k<D, WM, 1, 2>(G, T, Jprev, part_val, part_idx, st)
-                   : launch_fact_column_k<D, WM, 1, 1>(G, T, Jprev, part_val, part_idx, st);
+        return pf == 2 ? launch_fact_column_k<D, WM, 2, 2, 512>(G, T, Jprev, part_val, part_idx, st, threads)
+                       : launch_fact_column_k<D, WM, 2, 1, 512>(G, T, Jprev, part_val, part_idx, st, threads);
+    return pf == 2 ? launch_fact_column_k<D, WM, 1, 2, 512>(G, T, Jprev, part_val, part_idx, st, threads)
+                   : launch_fact_column_k<D, WM, 1, 1, 512>(G, T, Jprev, part_val, part_idx, st, threads);
 }
 
 template <int D>

@@ -746,6 +746,16 @@ COLUMN_CASES = ["ar1_w9", "ar1_w7", "ar1_w5", "ar1_w4", "ar1_w3", "ar1_w2", "ar1
                 "searev", "curtail"]
 
 
+def _same_bits(a, b):
+    """bit-identical, except that any NaN matches any NaN: which of two NaN operands (or
+    which sign of a generated NaN) an fp64 instruction returns depends on the operand order
+    the compiler picked for a commutative operation, not on the algorithm - and numpy's
+    argmin (stodynprog.py:686) does not tell NaNs apart either"""
+    a, b = np.asarray(a), np.asarray(b)
+    na, nb = np.isnan(a), np.isnan(b)
+    return bool(np.array_equal(na, nb) and np.array_equal(a[~na].view(np.int64), b[~nb].view(np.int64)))
+
+
 @pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
 @pytest.mark.parametrize("which", COLUMN_CASES)
 def test_column_hoist_is_bit_identical(product, backend, which):
@@ -765,7 +775,7 @@ def test_column_hoist_is_bit_identical(product, backend, which):
         Tr, Tc = ref.last_tables, col.last_tables
         assert Tr.layout_name == "state_minor_factored" and Tc.layout_name == "column_factored"
         assert Tc.n_backups_local == Tr.n_backups_local and Tc.u_mask == 1
-        assert np.array_equal(Jr.view(np.int64), Jc.view(np.int64)), sweep
+        assert _same_bits(Jr, Jc), sweep
         assert np.array_equal(polr, polc, equal_nan=True), sweep
         J0 = Jr.copy()
         if sweep == 1:                          # special values travel through the table too
@@ -776,20 +786,21 @@ def test_column_hoist_is_bit_identical(product, backend, which):
         lib = col.engine.lib
         try:
             Jr, polr = ref.value_iteration(J0, report_time=False)
-            for threads, ub, pf, pre in ((128, 1, 1, 1), (256, 2, 1, 0), (512, 1, 2, 0), (96, 2, 2, 0),
-                                         (160, 1, 2, 1)):
+            for threads, ub, pf, pre in ((128, 1, 1, 1), (256, 2, 1, 0), (512, 1, 2, 0), (96, 2, 2, 2),
+                                         (160, 1, 2, 1), (640, 2, 1, 2), (640, 2, 2, 1), (768, 2, 1, 2),
+                                         (768, 1, 2, 0), (704, 1, 1, 2)):
                 lib.sdp_set_option(b"col_threads", threads)
                 lib.sdp_set_option(b"col_ub", ub)
                 lib.sdp_set_option(b"col_pf", pf)
                 lib.sdp_set_option(b"col_prepass", pre)
                 J2, pol2 = col.value_iteration(J0, report_time=False)
-                assert np.array_equal(Jr.view(np.int64), J2.view(np.int64)), (threads, ub, pf, pre)
+                assert _same_bits(Jr, J2), (threads, ub, pf, pre)
                 assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf, pre)
         finally:
             lib.sdp_set_option(b"col_threads", 512)
             lib.sdp_set_option(b"col_ub", 2)
             lib.sdp_set_option(b"col_pf", 2)
-            lib.sdp_set_option(b"col_prepass", 1)
+            lib.sdp_set_option(b"col_prepass", 2)
 
 
 @pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
