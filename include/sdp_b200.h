@@ -220,7 +220,8 @@ int64_t sdp_launch_count(void);
  * with u_mask == 1: per-item table of inner interpolations, 0|1), "hoist_upl" (2|4),
  * "hoist_const" (0|1: constant-W variant of that kernel for W <= 9),
  * "col_threads" (layout CF: threads per CTA, 128..768), "col_ub" (controls per iteration, 1|2),
- * "col_pf" (groups of col_ub controls in flight, 1|2), "col_prepass" (column tables
+ * "col_pf" (groups of col_ub controls in flight, 1|2), "col_dynamic" (0|1: the warps of a CTA
+ * take the items of a column round-robin / first come first served), "col_prepass" (column tables
  * from the coalesced pre-pass, copied into shared memory by the TMA engine = 2, default, or by
  * vector loads = 1; 0: every CTA gathers its own from J_prev),
  * "p2p_timeout_s" (bound of the peer-flag waits, default 600 s, then the kernel traps).

@@ -1051,6 +1051,7 @@ struct Tuning {
     int col_threads;   // layout CF: threads per CTA (one CTA per SM: the column table fills shared memory)
     int col_ub;        // layout CF: controls per lane per iteration (1|2)
     int col_pf;        // layout CF: groups of col_ub controls in flight per lane (1|2)
+    int col_dynamic;   // layout CF: warps take the items of a column first come first served (1) or round-robin (0)
     int col_prepass;   // layout CF: column tables from the coalesced pre-pass, copied by vector loads (1) or by the TMA engine (2); 0: gathered by every CTA
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -1086,6 +1087,7 @@ static Tuning& tuning() {
         x.col_ub = env_int("SDP_COL_UB", 2) == 1 ? 1 : 2;
         x.col_pf = env_int("SDP_COL_PF", 2) == 1 ? 1 : 2;
         x.col_prepass = clampi(env_int("SDP_COL_PREPASS", 2), 0, 2);
+        x.col_dynamic = env_int("SDP_COL_DYNAMIC", 0) != 0;
         return x;
     }();
     return t;
@@ -1108,6 +1110,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "col_ub")) t.col_ub = (value == 1) ? 1 : 2;
     else if (!strcmp(name, "col_pf")) t.col_pf = (value == 1) ? 1 : 2;
     else if (!strcmp(name, "col_prepass")) t.col_prepass = clampi(value, 0, 2);
+    else if (!strcmp(name, "col_dynamic")) t.col_dynamic = value != 0;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1817,9 +1820,10 @@ template <int D, int WM, int UB, int PF, bool FULL, int MAXT>     // FULL: W == 
 __global__ void __launch_bounds__(MAXT, 1)
 k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jprev,
                     double* __restrict__ part_val, int32_t* __restrict__ part_idx,
-                    double inv_stride0, PVals PV, int64_t pitch, int prepass) {
+                    double inv_stride0, PVals PV, int64_t pitch, int prepass, int dynamic) {
     constexpr int NW = D - 1;
     extern __shared__ __align__(128) unsigned char csm[];
+    __shared__ int next_item;                           // dynamic hand-out of the items of a column
     double* R_sh = reinterpret_cast<double*>(csm);      // [order[0]][P] + slack = `pitch` doubles
     __shared__ int cw_sh[WM];
     __shared__ double lw_sh[NW][WM];
@@ -1843,6 +1847,7 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
         const int64_t run_end = T.run_end[i];     // end of the items of this band and column
         const int64_t e = run_end < seg_end ? run_end : seg_end;
         __syncthreads();                 // the previous column's readers are done with R
+        if (threadIdx.x == 0) next_item = 0;
         if (prepass == 2) {
             // the column's table, tabulated by k_column_table, is one contiguous block: one
             // thread hands it to the TMA engine in <= 32 KB pieces, everybody waits on the barrier
@@ -1890,7 +1895,16 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
         }
         __syncthreads();
 
-        for (int64_t item_id = i + warp; item_id < e; item_id += nwarps) {
+        // the warps share the items of the column: round-robin, or (dynamic) first come first
+        // served - the items differ in length and a column piece may hold only a few of them
+        for (int round = 0;; ++round) {
+            int k = round * nwarps + warp;
+            if (dynamic) {
+                if (lane == 0) k = atomicAdd(&next_item, 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+            }
+            const int64_t item_id = i + k;
+            if (item_id >= e) break;
             const SdpItem it = T.items[item_id];
             const int Us = T.U[(int64_t)it.state * 32 + lane];      // by position; 0 on padding lanes
             const int32_t* __restrict__ cup = T.cell + it.entry_base + lane;
@@ -2000,10 +2014,10 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
     const double inv0 = 1.0 / (double)G.stride[0];
     if (T.W == WM)
         k_sweep_fact_column<D, WM, UB, PF, true, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
-            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass);
+            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, tuning().col_dynamic);
     else
         k_sweep_fact_column<D, WM, UB, PF, false, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
-            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass);
+            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, tuning().col_dynamic);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }

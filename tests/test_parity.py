@@ -793,6 +793,7 @@ def test_column_hoist_is_bit_identical(product, backend, which):
                 lib.sdp_set_option(b"col_ub", ub)
                 lib.sdp_set_option(b"col_pf", pf)
                 lib.sdp_set_option(b"col_prepass", pre)
+                lib.sdp_set_option(b"col_dynamic", (threads // 32) % 2)
                 J2, pol2 = col.value_iteration(J0, report_time=False)
                 assert _same_bits(Jr, J2), (threads, ub, pf, pre)
                 assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf, pre)
@@ -801,6 +802,7 @@ def test_column_hoist_is_bit_identical(product, backend, which):
             lib.sdp_set_option(b"col_ub", 2)
             lib.sdp_set_option(b"col_pf", 2)
             lib.sdp_set_option(b"col_prepass", 2)
+            lib.sdp_set_option(b"col_dynamic", 0)
 
 
 @pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
