@@ -191,8 +191,8 @@ def kernel_name(T):
     d = T.d
     if T.factored:
         if T.column:
-            return "k_sweep_fact_column<%d,%d,2,%s>" % (d, 3 if T.W <= 3 else (5 if T.W <= 5 else 9),
-                                                        "true" if T.W in (3, 5, 9) else "false")
+            return "k_column_table<%d> + k_sweep_fact_column<%d,%d,2,2,%s,640>" % (
+                d, d, 3 if T.W <= 3 else (5 if T.W <= 5 else 9), "true" if T.W in (3, 5, 9) else "false")
         if T.tiled:
             return "k_sweep_fact_tiled<%d,%d,%d>" % (d, T.u_mask, 3 if T.W <= 3 else (5 if T.W <= 5 else 9))
         if T.u_mask == 1:

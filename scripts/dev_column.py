@@ -103,7 +103,7 @@ for per_sm in ((1,) if quick else (1, 2)):
             _cabi.check(lib.sdp_set_option(b"col_pf", pf), "opt")
             print("CF segs/SM=%d threads=%d ub=%d pf=%d:" % (per_sm, threads, ub, pf), timed(Tc, n=6, warm=2),
                   flush=True)
-lib.sdp_set_option(b"col_threads", 512)
+lib.sdp_set_option(b"col_threads", 640)
 lib.sdp_set_option(b"col_ub", 2)
 lib.sdp_set_option(b"col_pf", 2)
 del Tc
@@ -134,5 +134,5 @@ for bands in ("auto", "3", "2"):
         msg, J5_h, pol5_h = e2e()
         print("   ", msg, "; results == BF:", np.array_equal(J5_h.view(np.int64), Jb_h.view(np.int64)),
               np.array_equal(pol5_h, polb_h), flush=True)
-    lib.sdp_set_option(b"col_threads", 512)
+    lib.sdp_set_option(b"col_threads", 640)
     del T5

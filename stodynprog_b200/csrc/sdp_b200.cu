@@ -1083,7 +1083,9 @@ static Tuning& tuning() {
         x.hoist_upl = env_int("SDP_HOIST_UPL", 2) == 4 ? 4 : 2;
         x.p2p_timeout_s = clampi(env_int("SDP_P2P_TIMEOUT_S", 600), 1, 86400);
         x.hoist_const = env_int("SDP_HOIST_CONST", 1) != 0;
-        x.col_threads = clampi(env_int("SDP_COL_THREADS", 512), 128, 768) / 32 * 32;
+        // measured on config #5 (profiles/r1_column_tuning.txt): 512 threads 1.30 ms per sweep,
+        // 640 (5 warps per scheduler, 96 registers) 1.24 ms, 704 1.38 ms, 768 1.22-1.26 ms
+        x.col_threads = clampi(env_int("SDP_COL_THREADS", 640), 128, 768) / 32 * 32;
         x.col_ub = env_int("SDP_COL_UB", 2) == 1 ? 1 : 2;
         x.col_pf = env_int("SDP_COL_PF", 2) == 1 ? 1 : 2;
         x.col_prepass = clampi(env_int("SDP_COL_PREPASS", 2), 0, 2);

@@ -21,9 +21,10 @@ from . import tabulate as tb
 __all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "rebalance_bounds",
            "column_order", "column_segments", "row_aligned"]
 
-# solver.column_hoist = "auto" uses layout CF (column-shared hoist) whenever it applies iff this
-# is set; "on" / "off" on the solver override it
-COLUMN_HOIST_DEFAULT = os.environ.get("SDP_COLUMN_HOIST", "0") != "0"
+# solver.column_hoist = "auto" uses layout CF (column-shared hoist) whenever it applies unless
+# SDP_COLUMN_HOIST=0; "on" / "off" on the solver override it.  Measured on config #5, one B200
+# (profiles/r1_column_tuning.txt): 1.21 ms per sweep against 2.83 ms for layout BF.
+COLUMN_HOIST_DEFAULT = os.environ.get("SDP_COLUMN_HOIST", "1") != "0"
 
 
 def _torch():
@@ -1131,8 +1132,10 @@ class Engine(object):
         T = build_for(bounds, reuse)
         # ... then, with several ranks, by the measured cost of a backup in each slab
         balance = getattr(solver, "slab_balance", "auto")
+        # (layout CF cuts whole rows of axis 0 and keeps the cut by admissible controls unless
+        # the measured re-cut is asked for explicitly)
         if world > 1 and self._cuda and balance != "controls" and \
-                (balance == "measured" or T.n_backups_total >= self.REBALANCE_MIN_BACKUPS):
+                (balance == "measured" or (T.n_backups_total >= self.REBALANCE_MIN_BACKUPS and not T.column)):
             new_bounds = self._measured_bounds(T, U_all)
             if new_bounds is not None and T.column:
                 new_bounds = row_aligned(new_bounds, n_cols)
@@ -1179,7 +1182,12 @@ class Engine(object):
 
     # layout CF on one rank: the rows are cut into bands of decreasing size so that the
     # results of a band can travel to the host while the next bands are swept (sweep_to_host)
-    COLUMN_BANDS = os.environ.get("SDP_COLUMN_BANDS", "1")       # "auto" | number of bands
+    # Measured on config #5 (profiles/r1_column_tuning.txt), ms per device-resident sweep /
+    # ms per value_iteration call with host arrays: 1 band 1.21 / 1.93, 3 bands (45 / 25 /
+    # 30 % of the controls) 1.29 / 1.75, 5 bands (45 / 25 / 15 / 10 / 5 %) 1.75 / 1.72 - a
+    # small band gives a CTA only a round or two of items per column table.
+    COLUMN_BANDS = os.environ.get("SDP_COLUMN_BANDS", "auto")    # "auto" | number of bands
+    COLUMN_BAND_FRACTIONS = (0.45, 0.25, 0.30)
 
     def _column_bands(self, row_weight, W):
         """row boundaries of the bands of layout CF for a slab whose rows weigh `row_weight`
@@ -1193,7 +1201,7 @@ class Engine(object):
             big = (self._cuda and self.coll.world == 1
                    and float(np.sum(row_weight)) * W >= self.OVERLAP_MIN_BACKUPS
                    and os.environ.get("SDP_OVERLAP", "1") != "0")
-            fractions = self.OVERLAP_FRACTIONS if big else (1.0,)
+            fractions = self.COLUMN_BAND_FRACTIONS if big else (1.0,)
         else:
             k = max(1, int(mode))
             fractions = self.OVERLAP_FRACTIONS[:k - 1] + (1.0,) if k <= len(self.OVERLAP_FRACTIONS) \

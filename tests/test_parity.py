@@ -798,7 +798,7 @@ def test_column_hoist_is_bit_identical(product, backend, which):
                 assert _same_bits(Jr, J2), (threads, ub, pf, pre)
                 assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf, pre)
         finally:
-            lib.sdp_set_option(b"col_threads", 512)
+            lib.sdp_set_option(b"col_threads", 640)
             lib.sdp_set_option(b"col_ub", 2)
             lib.sdp_set_option(b"col_pf", 2)
             lib.sdp_set_option(b"col_prepass", 2)
