@@ -454,6 +454,7 @@ def run_ours(args):
             "config": {"workload": name, "states": n_grid, "backups_per_sweep": total_backups,
                        "state_dims": list(dims), "perturbation_nodes": T.W,
                        "table_layout": T.layout_name,
+                       "row_bands": (T.bands["rows"] if T.column else None),
                        "tabulate_mode": T.tabulate_mode, "item_chunk": T.item_chunk,
                        "parallelism": "state slabs x%d, %s" % (
                            world, "one rank" if world == 1 else
