@@ -860,6 +860,80 @@ def test_column_hoist_row_bands(product, backend, which, monkeypatch):
             assert np.array_equal(a.view(np.int64), b.view(np.int64)), bands
 
 
+def test_column_hoist_band_launch_plan(product, monkeypatch):
+    """the launch sequence of value_iteration's large-sweep path for layout CF, replayed on
+    the numpy model: pre-pass once, then per row band one streaming launch over the band's
+    own CTA segments (col_table_ready = 1) and one combine launch on the band's view - the
+    union must equal the one-launch sweep"""
+    import ctypes
+    import torch
+    from stodynprog_b200 import workloads as wl
+    from stodynprog_b200.engine import Engine
+    monkeypatch.setattr(Engine, "COLUMN_BANDS", "3")
+    api = _Api(product, "model", "state_minor", "auto", "on")
+    sv = wl.storage_ar1(api, n_E=330, n_P=3, n_w=3, steps=(2.0, 0.1)).solver
+    sv.column_hoist = "on"
+    T = sv.sweep_tables()
+    eng = sv.engine
+    assert T.column and len(T.bands["tiles"]) == 3 and not eng.can_overlap_results(T)   # (no GPU here)
+    n_grid = 330 * 3
+    J = torch.from_numpy(np.random.default_rng(3).standard_normal(n_grid))
+    J_ref = torch.empty(n_grid, dtype=torch.float64)
+    eng.sweep(T, J, J_ref)
+    argmin_ref = T.argmin[:n_grid].clone()
+    plan = eng._chunk_plan(T)
+    assert len(plan) == 3 and plan is eng._chunk_plan(T)
+    assert [ch["s0"] for ch in plan] == [r * 3 for r in T.bands["rows"][:-1]]
+    assert [ch["s1"] for ch in plan] == [r * 3 for r in T.bands["rows"][1:]]
+    T.part_val.fill_(float("nan"))
+    T.argmin.fill_(-7)
+    J_new = torch.full((n_grid,), float("nan"), dtype=torch.float64)
+    lib = eng.lib
+    assert lib.sdp_column_table(ctypes.byref(T.grid), ctypes.byref(T.c_tables), eng._ptr(J), eng.stream) == 0
+    tb0 = T.bands["tile_begin"]
+    for b, ch in enumerate(plan):
+        seg = ch["keep"].numpy()
+        i0, i1 = int(T.item_begin_host[tb0[b]]), int(T.item_begin_host[tb0[b + 1]])
+        assert seg[0] == i0 and seg[-1] == i1 and np.all(np.diff(seg) >= 0) and i1 > i0
+        assert ch["tab_p"].col_table_ready == 1 and ch["tab_p"].n_segs == len(seg) - 1
+        assert ch["tab_f"].n_states == ch["s1"] - ch["s0"] and ch["tab_f"].tiles_per_col == T.bands["tiles"][b]
+        assert lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(ch["tab_p"]), eng._ptr(J), ch["pv"],
+                                      ch["pi"], eng.stream) == 0
+        assert lib.sdp_sweep_finalize(ctypes.byref(ch["tab_f"]), eng._ptr(T.part_val), eng._ptr(T.part_idx),
+                                      ctypes.c_void_p(J_new.data_ptr() + 8 * ch["s0"]),
+                                      ctypes.c_void_p(T.argmin.data_ptr() + 4 * ch["s0"]), eng.stream) == 0
+    assert torch.equal(J_new.view(torch.int64), J_ref.view(torch.int64))
+    assert torch.equal(T.argmin[:n_grid], argmin_ref)
+    # re-cutting the CTA segments invalidates the cached plan and band views
+    eng.set_column_segments(T, 7)
+    assert T.n_segs == 7 and T.chunk_plan is None and T.band_views is None
+    J_again = torch.empty(n_grid, dtype=torch.float64)
+    eng.sweep(T, J, J_again)
+    assert torch.equal(J_again.view(torch.int64), J_ref.view(torch.int64))
+
+
+def test_column_bands_choice(product, monkeypatch):
+    """row bands of layout CF: none on several ranks or small slabs, whole tiles of 32 rows,
+    cut by the controls of the rows"""
+    from stodynprog_b200.engine import Engine
+    from fake_lib import FakeLib
+    eng = Engine(_test_lib=FakeLib())
+    w = np.full(2000, 205.0)
+    monkeypatch.setattr(Engine, "COLUMN_BANDS", "1")
+    assert eng._column_bands(w, 9) == [0, 2000]
+    monkeypatch.setattr(Engine, "COLUMN_BANDS", "auto")
+    assert eng._column_bands(w, 9) == [0, 2000]            # no GPU: nothing to overlap
+    monkeypatch.setattr(Engine, "COLUMN_BANDS", "3")
+    assert eng._column_bands(w, 9) == [0, 928, 1408, 2000]
+    assert eng._column_bands(np.r_[np.full(1000, 100.0), np.full(1000, 300.0)], 9) == [0, 1280, 1600, 2000]
+    monkeypatch.setattr(Engine, "COLUMN_BANDS", "5")
+    b = eng._column_bands(w, 9)
+    assert len(b) == 6 and all(x % 32 == 0 for x in b[:-1]) and b[-1] == 2000
+    assert eng._column_bands(np.full(100, 205.0), 9) == [0, 100]      # too few rows for 5 bands
+    eng.coll.world = 2
+    assert eng._column_bands(w, 9) == [0, 2000]            # one epoch per sweep and rank
+
+
 def test_column_hoist_is_refused_when_it_does_not_apply(product):
     """a w-part that varies along a column is detected on the built tables: "auto" falls
     back to layout BF (same results), "on" raises; so do grids or layouts CF cannot take"""
