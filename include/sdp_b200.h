@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SDP_ABI_VERSION 4
+#define SDP_ABI_VERSION 5
 #define SDP_MAX_D 4 /* the reference dispatches d = 1..4 (multilinear_cython.pyx:36-47) */
 
 /* error codes */
@@ -317,6 +317,13 @@ typedef struct SdpPeers {
 int sdp_sweep_finalize_p2p(const SdpTables* tab, const double* part_val, const int32_t* part_idx,
                            int32_t* argmin_out, const SdpPeers* peers, int64_t state_begin,
                            void* stream);
+/* The same for a shard made of whole COLUMNS of the grid (layout CF, one band, n_cols local
+ * columns): local state i = row*n_cols + lc is grid state row*glob_cols + col_begin + lc, and
+ * that is where its J goes in every rank's buffer.  (Sharding by columns keeps the cost of the
+ * column tables - pre-pass and loads - proportional to the shard.) */
+int sdp_sweep_finalize_p2p_cols(const SdpTables* tab, const double* part_val, const int32_t* part_idx,
+                                int32_t* argmin_out, const SdpPeers* peers, int64_t glob_cols,
+                                int64_t col_begin, void* stream);
 /* Stream-ordered wait until every rank has published the local epoch (i.e. until
  * the slabs written by the last sdp_sweep_finalize_p2p of all ranks have landed). */
 int sdp_p2p_wait(const SdpPeers* peers, void* stream);

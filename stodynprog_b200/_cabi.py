@@ -12,7 +12,7 @@ import numpy as np
 
 SDP_MAX_D = 4
 SDP_MAX_C = 4
-SDP_ABI_VERSION = 4
+SDP_ABI_VERSION = 5
 LAYOUT_CONTROL_MINOR = 0   # "A": [state][w][u]
 LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
 LAYOUT_CONTROL_MINOR_FACTORED = 2   # "AF": (x,u) part [state][Upad] + (x,w) part [state][W]
@@ -133,6 +133,8 @@ SIGNATURES = {
     "sdp_sweep_finalize": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _vp]),
     "sdp_sweep_finalize_p2p": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp,
                                               ctypes.POINTER(SdpPeers), _i64, _vp]),
+    "sdp_sweep_finalize_p2p_cols": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp,
+                                                   ctypes.POINTER(SdpPeers), _i64, _i64, _vp]),
     "sdp_p2p_wait": (ctypes.c_int, [ctypes.POINTER(SdpPeers), _vp]),
     "sdp_p2p_barrier": (ctypes.c_int, [ctypes.POINTER(SdpPeers), _vp]),
     "sdp_policy_eval": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,

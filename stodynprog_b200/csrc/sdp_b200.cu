@@ -2355,6 +2355,36 @@ k_sweep_finalize_p2p(int64_t n_states, const int64_t* __restrict__ item_begin,
     publish_epoch(P);
 }
 
+// the same combine for a shard of whole COLUMNS of the grid (layout CF, one band): local
+// state i = row*n_cols + lc is grid state row*glob_cols + col_begin + lc, so a warp stores
+// runs of consecutive values of one row into every rank's buffer
+__global__ void __launch_bounds__(256)
+k_sweep_finalize_p2p_cols(int64_t n_states, const int64_t* __restrict__ item_begin,
+                          const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
+                          int32_t* __restrict__ argmin_out, PeersDev P, int n_cols, int tiles_per_col,
+                          int64_t glob_cols, int64_t col_begin) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_states) {
+        int64_t unit;
+        int lane;
+        tile_of_state(i, n_cols, tiles_per_col, unit, lane);
+        double bv = CUDART_INF;
+        int bi = INT_MAX;
+        for (int64_t k = item_begin[unit]; k < item_begin[unit + 1]; ++k) {
+            const double v = part_val[k * 32 + lane];
+            const int ix = part_idx[k * 32 + lane];
+            if (better(v, ix, bv, bi)) { bv = v; bi = ix; }
+        }
+        argmin_out[i] = bi;
+        const int64_t row = i / n_cols;
+        const int64_t g = row * glob_cols + col_begin + (i - row * n_cols);
+#pragma unroll
+        for (int r = 0; r < SDP_MAX_PEERS; ++r)
+            if (r < P.world) P.J[r][g] = bv;
+    }
+    publish_epoch(P);
+}
+
 __global__ void k_p2p_wait(PeersDev P, unsigned long long timeout_ns) {
     const int t = threadIdx.x;
     if (t < P.world) {
@@ -2419,6 +2449,33 @@ extern "C" int sdp_sweep_finalize_p2p(const SdpTables* tab, const double* part_v
                                                            is_column(T) ? T.n_cols : 0, T.tiles_per_col);
     else
         k_sweep_finalize_p2p<false><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin, 0, 0);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+extern "C" int sdp_sweep_finalize_p2p_cols(const SdpTables* tab, const double* part_val,
+                                           const int32_t* part_idx, int32_t* argmin_out,
+                                           const SdpPeers* peers, int64_t glob_cols, int64_t col_begin,
+                                           void* stream) {
+    if (!tab) return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_p2p_cols: tables is NULL");
+    const SdpTables& T = *tab;
+    int rc = check_tables(T, "sdp_sweep_finalize_p2p_cols");
+    if (rc) return rc;
+    if (!is_column(T)) return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_p2p_cols: the tables are not in layout CF");
+    if (T.n_states > 0 && (rc = check_column_band(T, "sdp_sweep_finalize_p2p_cols"))) return rc;
+    PeersDev P;
+    rc = make_peers(peers, &P, "sdp_sweep_finalize_p2p_cols");
+    if (rc) return rc;
+    for (int r = 0; r < P.world; ++r)
+        if (!P.J[r]) return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_p2p_cols: NULL J buffer");
+    if (col_begin < 0 || glob_cols < col_begin + T.n_cols ||
+        (T.n_states > 0 && (!part_val || !part_idx || !argmin_out)))
+        return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_p2p_cols: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned blocks = (unsigned)((T.n_states + 255) / 256);
+    if (blocks == 0) blocks = 1;       // the epoch must advance on every rank
+    k_sweep_finalize_p2p_cols<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P,
+                                                      T.n_cols, T.tiles_per_col, glob_cols, col_begin);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }

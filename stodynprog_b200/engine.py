@@ -25,6 +25,9 @@ __all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "reba
 # SDP_COLUMN_HOIST=0; "on" / "off" on the solver override it.  Measured on config #5, one B200
 # (profiles/r1_column_tuning.txt): 1.21 ms per sweep against 2.83 ms for layout BF.
 COLUMN_HOIST_DEFAULT = os.environ.get("SDP_COLUMN_HOIST", "1") != "0"
+# solver.slab_axis = "auto": how a grid in layout CF is cut over several ranks ("rows" |
+# "columns"); by columns is the better cut on paper but has not run on GPUs yet
+SLAB_AXIS_DEFAULT = os.environ.get("SDP_SLAB_AXIS", "rows")
 
 
 def _torch():
@@ -287,6 +290,27 @@ class Collective(object):
             return out
         return pad_full.index_select(0, index)
 
+    def all_gather_indexed(self, local, maxc, index, out=None):
+        """all-gather of unequal 1-D pieces followed by one index_select: element g of the
+        result is element index[g] of the rank-major padded concatenation (rank r's piece at
+        [r*maxc, r*maxc + len)).  Used when the pieces are not contiguous slabs of the
+        result (grid sharded by columns)."""
+        torch = _torch()
+        if self.world == 1:
+            res = local.index_select(0, index)
+            if out is not None:
+                out.copy_(res)
+                return out
+            return res
+        pad_local = torch.zeros(maxc, dtype=local.dtype, device=local.device)
+        pad_local[:local.numel()] = local
+        pad_full = torch.empty(maxc * self.world, dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(pad_full, pad_local, group=self.group)
+        if out is not None:
+            torch.index_select(pad_full, 0, index, out=out)
+            return out
+        return pad_full.index_select(0, index)
+
     def all_reduce_max(self, t):
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
@@ -410,6 +434,11 @@ class SweepTables(object):
         self.bands = None          # dict(rows, tiles, tile_begin, tile_col), see column_order
         self.band_views = None     # per band: (SdpTables view for the combine pass, first state, states)
         self.sm_count = 148
+        # grid sharded by COLUMNS (layout CF, solver.slab_axis = "columns"): this rank holds the
+        # columns [col_bounds[rank], col_bounds[rank+1]) of every row; local state row*n_cols + lc
+        self.col_bounds = None
+        self.gather_index = None   # device int64 [n_grid]: see Collective.all_gather_indexed
+        self.gather_maxc = 0
         self.slab_times_ms = None  # measured per-rank sweep times (several ranks, see _measured_bounds)
         self.slab_recut = False    # True when those times moved the slab boundaries
 
@@ -771,14 +800,37 @@ class Engine(object):
             and getattr(solver, "table_compress", "auto") != "off"
             and n_rows0 >= 32 * world and nb_control <= _cabi.SDP_MAX_C)
         col_refused = [False]       # set when the built w-part turns out to vary along a column
+        # several ranks: slabs of whole rows of axis 0 ("rows"), or - layout CF only - whole
+        # columns ("columns": every rank then tabulates and loads the tables of its own columns
+        # only, so the per-column costs divide by the number of ranks)
+        slab_axis = getattr(solver, "slab_axis", "auto")
+        if slab_axis not in ("auto", "rows", "columns"):
+            raise ValueError("slab_axis must be 'auto', 'rows' or 'columns'")
+        if slab_axis == "auto":
+            slab_axis = SLAB_AXIS_DEFAULT
+        by_columns = world > 1 and slab_axis == "columns"
+        if by_columns and not (col_candidate and n_cols >= world):
+            raise ValueError("slab_axis='columns' needs layout CF (column_hoist) and at least one "
+                             "grid column per rank")
 
         def build_for(bounds, reuse):
-            """tables of this rank's slab [bounds[rank], bounds[rank+1])"""
-            sb, se = bounds[rank], bounds[rank + 1]
-            n = se - sb
+            """tables of this rank's slab: states [bounds[rank], bounds[rank+1]) of the C-order
+            grid, or (by_columns) the columns [bounds[rank], bounds[rank+1]) of every row"""
+            if by_columns:
+                c0, c1 = bounds[rank], bounds[rank + 1]
+                # local state row*(c1-c0) + lc  <->  grid state row*n_cols + c0 + lc
+                glob = (np.arange(n_rows0, dtype=np.int64)[:, None] * n_cols
+                        + np.arange(c0, c1, dtype=np.int64)[None, :]).reshape(-1)
+                sb, se, n = 0, n_grid, len(glob)
+                n_cols_loc = c1 - c0
+            else:
+                sb, se = bounds[rank], bounds[rank + 1]
+                n = se - sb
+                glob = slice(sb, se)
+                n_cols_loc = n_cols
             host = tb.HostStateTable(n, nb_control)
-            host.lo, host.hi, host.npts = host_full.lo[sb:se], host_full.hi[sb:se], host_full.npts[sb:se]
-            U = U_all[sb:se]
+            host.lo, host.hi, host.npts = host_full.lo[glob], host_full.hi[glob], host_full.npts[glob]
+            U = U_all[glob]
 
             # table layout (see include/sdp_b200.h): lane <-> control (A) when states
             # have many controls, lane <-> state (B) when there are many states with
@@ -808,9 +860,11 @@ class Engine(object):
                 # all ranks must agree (they run the same kernels on the same layout)
                 u_mask = min(coll.all_gather_object(u_mask))
             column = bool(col_candidate and not col_refused[0] and tiled and u_mask == 1 and n > 0
-                          and sb % n_cols == 0 and se % n_cols == 0)
+                          and (by_columns or (sb % n_cols == 0 and se % n_cols == 0)))
             if world > 1:
                 column = bool(min(coll.all_gather_object(column)))
+            if by_columns and not column:
+                raise ValueError("slab_axis='columns' but layout CF does not apply to these tables")
             if col_mode == "on" and not column:
                 raise ValueError("column_hoist='on' but layout CF does not apply: it needs the "
                                  "state-minor layout, a factored (x,u)+(x,w) split with state axis 0 "
@@ -827,11 +881,12 @@ class Engine(object):
                     if not col:
                         pos[col] = (n, U, host, None, None, None)
                     else:
-                        bands = self._column_bands(U.reshape(n // n_cols, n_cols).sum(axis=1), W)
-                        order, valid, band_tiles, band_tile_begin, tile_col = column_order(n, n_cols, bands)
+                        bands = self._column_bands(U.reshape(n // n_cols_loc, n_cols_loc).sum(axis=1), W)
+                        order, valid, band_tiles, band_tile_begin, tile_col = column_order(n, n_cols_loc, bands)
                         h = tb.HostStateTable(len(order), nb_control)
                         h.lo, h.hi, h.npts = host.lo[order], host.hi[order], host.npts[order]
-                        pos[col] = (len(order), np.where(valid, U[order], 0), h, sb + order, valid,
+                        flat = glob[order] if by_columns else sb + order
+                        pos[col] = (len(order), np.where(valid, U[order], 0), h, flat, valid,
                                     dict(rows=bands, tiles=band_tiles, tile_begin=band_tile_begin,
                                          tile_col=tile_col))
                 return pos[col]
@@ -862,6 +917,18 @@ class Engine(object):
             T.tiled = tiled
             T.expect = 1 if nb_perturb == 1 else 0
             T.bounds, T.state_begin, T.n_states = bounds, sb, n
+            T.col_bounds = None
+            if by_columns:
+                # the exchange goes by grid position, not by slab: T.bounds stays None
+                T.bounds, T.state_begin, T.col_bounds = None, 0, [int(b) for b in bounds]
+                widths = np.diff(np.asarray(bounds, dtype=np.int64))
+                T.gather_maxc = int(widths.max()) * n_rows0
+                cols = np.arange(n_cols, dtype=np.int64)
+                owner = np.searchsorted(np.asarray(bounds[1:], dtype=np.int64), cols, side="right")
+                lc = cols - np.asarray(bounds, dtype=np.int64)[owner]
+                rows = np.arange(n_rows0, dtype=np.int64)[:, None]
+                idx = owner[None, :] * T.gather_maxc + rows * widths[owner][None, :] + lc[None, :]
+                T.gather_index = self.to_device(idx.reshape(-1))
             T.host_full = host_full
             T.n_backups_local = int(U.sum()) * W
             T.n_backups_total = int(U_all.sum()) * W
@@ -994,7 +1061,7 @@ class Engine(object):
                     states = mine if (mine is not None and (sb, se) == (eq[rank], eq[rank + 1])) else \
                         tb.state_tuples(state_grid, sb, se)
                     if col:
-                        states = [states[i] for i in flat_eff - sb]
+                        states = [states[i] for i in flat_eff - sb]      # (by_columns: sb = 0, all states)
                     tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
                                        g_per_w, flush, align=align, valid=valid)
                 return L
@@ -1014,12 +1081,12 @@ class Engine(object):
                     if col:
                         # the hoisted table is shared by a column only if the (x,w) part of its
                         # states is the same; checked bit for bit on the built tables
-                        ok = self._column_w_part_ok(T, W, n_cols, positions(True)[5], positions(True)[4],
+                        ok = self._column_w_part_ok(T, W, n_cols_loc, positions(True)[5], positions(True)[4],
                                                     built["lam_w_plane"])
                         if world > 1:
                             ok = bool(min(coll.all_gather_object(ok)))
                         if not ok:
-                            if col_mode == "on":
+                            if col_mode == "on" or by_columns:
                                 raise ColumnHoistRefused("column_hoist='on' but the (x,w) part of the "
                                                          "next state depends on state axis 0")
                             col_refused[0] = True
@@ -1054,7 +1121,7 @@ class Engine(object):
             col = column and u_mask == 1
             T.column = col
             T.bands = positions(True)[5] if col else None
-            T.n_cols, T.tiles_per_col = (n_cols, T.bands["tiles"][0]) if col else (0, 0)
+            T.n_cols, T.tiles_per_col = (n_cols_loc, T.bands["tiles"][0]) if col else (0, 0)
             U_eff = positions(col)[1]
             n_tiles, tile_U, tile_off = L["n_tiles"], L["tile_U"], L["tile_off"]
             entry_off, Upad, g_off, tile_g_off = L["entry_off"], L["Upad"], L["g_off"], L["tile_g_off"]
@@ -1097,14 +1164,14 @@ class Engine(object):
                 # items of one band and column are consecutive (tiles are ordered that way)
                 tile_band = np.repeat(np.arange(len(T.bands["tiles"])), np.diff(T.bands["tile_begin"]))
                 st_of_item = items["state"].astype(np.int64)
-                up.append(item_run_ends(tile_band[st_of_item] * n_cols + T.bands["tile_col"][st_of_item]))
+                up.append(item_run_ends(tile_band[st_of_item] * n_cols_loc + T.bands["tile_col"][st_of_item]))
             else:
                 T.n_segs, T.seg_begin, T.run_end = 0, None, None
             up = self.to_device_packed(up)
             T.items, T.item_begin, T.U_dev = up[0], up[1], up[2]
             if col:
                 T.seg_begin, T.run_end = up[3], up[4]
-                ensure("col_table", n_cols * _cabi.column_pitch(n_rows0, W), torch.float64)
+                ensure("col_table", n_cols_loc * _cabi.column_pitch(n_rows0, W), torch.float64)
             else:
                 T.col_table = None
             T.band_views = None
@@ -1117,7 +1184,11 @@ class Engine(object):
             return T
 
         # slabs balanced by admissible controls ...
-        if world > 1 and col_candidate:
+        if by_columns:
+            # whole columns per rank, cut by the admissible controls of the columns
+            col_w = (U_all + 1).reshape(n_rows0, n_cols).sum(axis=0)
+            bounds = [int(b) for b in partition_by_weight(col_w, world)]
+        elif world > 1 and col_candidate:
             # whole rows of axis 0 per rank (layout CF); a row is 1/n_rows0 of the grid
             row_w = (U_all + 1).reshape(n_rows0, n_cols).sum(axis=1)
             bounds = [int(b) * n_cols for b in partition_by_weight(row_w, world)]
@@ -1134,7 +1205,7 @@ class Engine(object):
         balance = getattr(solver, "slab_balance", "auto")
         # (layout CF cuts whole rows of axis 0 and keeps the cut by admissible controls unless
         # the measured re-cut is asked for explicitly)
-        if world > 1 and self._cuda and balance != "controls" and \
+        if world > 1 and self._cuda and balance != "controls" and not by_columns and \
                 (balance == "measured" or (T.n_backups_total >= self.REBALANCE_MIN_BACKUPS and not T.column)):
             new_bounds = self._measured_bounds(T, U_all)
             if new_bounds is not None and T.column:
@@ -1288,16 +1359,24 @@ class Engine(object):
             _cabi.check(rc, "sdp_sweep_partials")
             if events is not None:
                 events[1].record()
-            rc = self.lib.sdp_sweep_finalize_p2p(ctypes.byref(T.c_tables), self._ptr(T.part_val),
-                                                 self._ptr(T.part_idx), self._ptr(T.argmin),
-                                                 ctypes.byref(px.peers[k_new]), sb, self.stream)
-            _cabi.check(rc, "sdp_sweep_finalize_p2p")
+            if T.col_bounds is not None:
+                rc = self.lib.sdp_sweep_finalize_p2p_cols(
+                    ctypes.byref(T.c_tables), self._ptr(T.part_val), self._ptr(T.part_idx), self._ptr(T.argmin),
+                    ctypes.byref(px.peers[k_new]), T.col_bounds[-1], T.col_bounds[self.coll.rank], self.stream)
+                _cabi.check(rc, "sdp_sweep_finalize_p2p_cols")
+            else:
+                rc = self.lib.sdp_sweep_finalize_p2p(ctypes.byref(T.c_tables), self._ptr(T.part_val),
+                                                     self._ptr(T.part_idx), self._ptr(T.argmin),
+                                                     ctypes.byref(px.peers[k_new]), sb, self.stream)
+                _cabi.check(rc, "sdp_sweep_finalize_p2p")
             rc = self.lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), self.stream)
             _cabi.check(rc, "sdp_p2p_wait")
         else:
             self.sweep_local(T, J_prev, events)
             if self.coll.world == 1:
                 J_new.copy_(T.J_out[:n])
+            elif T.col_bounds is not None:
+                self.coll.all_gather_indexed(T.J_out[:n], T.gather_maxc, T.gather_index, out=J_new)
             else:
                 self.coll.all_gather_slabs(T.J_out[:n], T.bounds, out=J_new)
         if rel_ref_index is not None:
@@ -1305,6 +1384,11 @@ class Engine(object):
                                         self._ptr(ref_out), self.stream)
             _cabi.check(rc, "sdp_rel_shift")
         if resid_out is not None:
+            if T.col_bounds is not None:
+                # every rank holds all of J: any partition of the grid does for the residual
+                world, rank, n_grid = self.coll.world, self.coll.rank, J_new.numel()
+                sb = n_grid * rank // world
+                n = n_grid * (rank + 1) // world - sb
             a = J_new[sb:sb + n]
             b = J_prev[sb:sb + n]
             rc = self.lib.sdp_supnorm_diff(self._ptr(a), self._ptr(b), n, self._ptr(resid_out),
@@ -1436,6 +1520,8 @@ class Engine(object):
 
     def gather_argmin(self, T):
         """full-grid int32 argmin (device), gathered over ranks"""
+        if T.col_bounds is not None:
+            return self.coll.all_gather_indexed(T.argmin[:T.n_states], T.gather_maxc, T.gather_index)
         return self.coll.all_gather_slabs(T.argmin[:T.n_states], T.bounds)
 
     def policy_values(self, T, argmin_full):

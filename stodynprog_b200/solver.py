@@ -64,6 +64,10 @@ class DPSolver(object):
         # storage examples), one CTA tabulates the inner interpolation once per column of
         # the grid; "auto" follows SDP_COLUMN_HOIST, "on" raises if it does not apply
         self.column_hoist = "auto"    # "auto" | "on" | "off"
+        # several ranks, layout CF: cut the grid into slabs of whole rows of axis 0 ("rows") or
+        # into whole columns ("columns": the per-column costs then divide by the number of
+        # ranks; not run on GPUs yet, hence not what "auto" picks - SDP_SLAB_AXIS)
+        self.slab_axis = "auto"       # "auto" | "rows" | "columns"
         # several ranks: cut the grid into slabs of equal admissible controls ("controls"), or
         # re-cut once by the measured sweep time of every slab ("measured"; "auto" does so
         # for sweeps of at least 5e8 backups)
@@ -167,7 +171,7 @@ class DPSolver(object):
                 tuple(sig(p) for p in self.perturb_proba),
                 tuple(float(c) for c in self.control_steps),
                 self.table_layout, self.tabulate, self.table_compress, self.slab_balance,
-                getattr(self, "column_hoist", "auto"))
+                getattr(self, "column_hoist", "auto"), getattr(self, "slab_axis", "auto"))
 
     def clear_tables(self):
         """drop the device-resident tables (call after mutating anything the

@@ -26,10 +26,12 @@ def _free_port():
 def _problem(sdp, wl, lib, layout):
     """the sharded test problem: storage + AR(1) on a 9 x 11 grid, or - layout CF, which
     needs slabs of whole rows of axis 0 and at least 32 rows per rank - on a 70 x 5 grid"""
-    if layout == "column":
+    if layout.startswith("column"):
         prob = wl.storage_ar1(sdp, n_E=70, n_P=5, n_w=3, steps=(0.5, 0.1), _test_lib=lib)
         prob.solver.table_layout = "state_minor"
         prob.solver.column_hoist = "on"
+        if layout == "column_by_columns":       # the grid cut into whole columns instead of rows
+            prob.solver.slab_axis = "columns"
     else:
         prob = wl.storage_ar1(sdp, n_E=9, n_P=11, steps=(0.01, 0.1), _test_lib=lib)
         prob.solver.table_layout = layout
@@ -50,7 +52,8 @@ def _worker(rank, world, port, out_dir, layout):
         prob, sv, J0 = _problem(sdp, wl, FakeLib(), layout)
         J1, pol1 = sv.value_iteration(J0, report_time=False)
         T = sv.last_tables
-        assert T.column == (layout == "column")
+        assert T.column == layout.startswith("column")
+        assert (T.col_bounds is not None) == (layout == "column_by_columns")
         (Jd, Jr), pol2 = sv.value_iteration((J1 - J1[sv._state_ref_ind], 0.), rel_dp=True, report_time=False)
         Je, ref = sv.eval_policy(pol1, 6, rel_dp=True, report_time=False)
         Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=3, tol=0.0)
@@ -70,13 +73,14 @@ def _worker(rank, world, port, out_dir, layout):
         assert root_ok, "host_results='root' mismatch on rank %d" % rank
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), J1=J1, pol1=pol1, Jd=Jd, Jr=Jr, pol2=pol2,
                  Je=Je, ref=ref, Js=Js, pols=pols, resid=np.array(info["residuals"]),
-                 bounds=np.array(T.bounds), n_local=T.n_states, backups=T.n_backups_local,
+                 bounds=np.array(T.bounds if T.bounds is not None else T.col_bounds), n_local=T.n_states,
+                 backups=T.n_backups_local,
                  total=T.n_backups_total)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("layout", ["control_minor", "state_minor", "column"])
+@pytest.mark.parametrize("layout", ["control_minor", "state_minor", "column", "column_by_columns"])
 def test_sharded_sweep_world2_matches_single_process(tmp_path, layout):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), layout), nprocs=world, join=True)
@@ -103,6 +107,12 @@ def test_sharded_sweep_world2_matches_single_process(tmp_path, layout):
     # the slabs are contiguous, disjoint, cover the grid and are balanced by controls
     b = r[0]["bounds"]
     n_grid = J0.size
+    if layout == "column_by_columns":
+        # the ranks hold whole columns: 2 + 3 of the 5, every row of them
+        assert list(b) == list(r[1]["bounds"]) and b[0] == 0 and b[-1] == J0.shape[1] and 0 < b[1] < 5
+        assert int(r[0]["n_local"]) == b[1] * J0.shape[0] and int(r[1]["n_local"]) == (5 - b[1]) * J0.shape[0]
+        assert int(r[0]["backups"]) + int(r[1]["backups"]) == int(r[0]["total"])
+        return
     assert list(b) == list(r[1]["bounds"]) and b[0] == 0 and b[-1] == n_grid
     assert int(r[0]["n_local"]) + int(r[1]["n_local"]) == n_grid
     if layout == "column":
