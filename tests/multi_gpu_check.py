@@ -19,6 +19,47 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def check_column_layout(sdp, wl, rank):
+    """layout CF (one inner-interpolation table per grid column) over several ranks, the
+    grid cut into whole rows and into whole columns, against the oracle port on the host"""
+    from conftest import rel_err
+    from oracle.ref_port import port_api
+    world = dist.get_world_size()
+    n_E, n_P = 32 * world + 8, 2 * world + 3
+    kw = dict(n_E=n_E, n_P=n_P, n_w=9, steps=(0.5, 0.1))
+    ora = wl.storage_ar1(port_api(), **kw).solver
+    J0 = np.random.default_rng(5).standard_normal((n_E, n_P))
+    want = []
+    J = J0
+    for k in range(2):
+        J, pol = ora.value_iteration(J)
+        want.append((J, pol))
+    ok = True
+    for axis in ("rows", "columns"):
+        sv = wl.storage_ar1(sdp, **kw).solver
+        sv.table_layout = "state_minor"
+        sv.column_hoist = "on"
+        sv.slab_axis = axis
+        J = J0
+        for k in range(2):
+            J, pol = sv.value_iteration(J, report_time=False)
+            bad = int(np.any(pol != want[k][1], axis=-1).sum())
+            err = rel_err(J, want[k][0])
+            ok &= bad == 0 and err <= 1e-10
+            if rank == 0:
+                print("[column_factored, slabs of %s] sweep %d: policy mismatches %d, J rel err %.2e"
+                      % (axis, k, bad, err))
+        T = sv.last_tables
+        ok &= T.column and (T.col_bounds is not None) == (axis == "columns")
+        Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=2, tol=0.0)
+        r_expected = np.max(np.abs(want[1][0] - want[0][0]))
+        ok &= rel_err(Js, want[1][0]) <= 1e-10 and abs(info["residuals"][-1] - r_expected) <= 1e-9 * r_expected
+        print("[column_factored, slabs of %s] rank %d: %d states, %s" % (
+              axis, rank, T.n_states, "columns %s" % T.col_bounds if T.col_bounds else "bounds %s" % T.bounds),
+              flush=True)
+    return bool(ok)
+
+
 def main():
     os.environ.setdefault("SDP_P2P_TIMEOUT_S", "120")
     rank = int(os.environ["RANK"])
@@ -87,6 +128,7 @@ def main():
         Js, pols, info = sv.solve_value_iteration(max_iter=3, tol=0.0)
         r_expected = np.max(np.abs(G["vi_J2"] - G["vi_J1"]))
         ok &= rel_err(Js, G["vi_J2"]) <= 1e-10 and abs(info["residuals"][-1] - r_expected) <= 1e-9 * r_expected
+    ok &= check_column_layout(sdp, wl, rank)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
