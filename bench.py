@@ -255,6 +255,15 @@ def roofline_of(T, k1_ms, ms_total, K, peak, peak_src, traffic):
          "streamed_GBs": T.device_bytes / (k1 * 1e-3) / 1e9}
     if len(ncu) > 1:
         r["ncu"] = {k: v for k, v in ncu.items() if k != "traffic"}
+        # the pipe the committed ncu capture shows closest to its peak: what actually bounds the
+        # kernel when `frac` (dense algorithmic bytes over the HBM peak) is not the binding ratio
+        pipes = {"l1_data_pipe_pct": "L1 / shared-memory data pipe (wavefronts)", "fp64_pipe_pct": "fp64 pipe",
+                 "dram_pct": "HBM", "l1_pct": "L1", "l2_pct": "L2"}
+        seen = [(float(ncu[k]), name) for k, name in pipes.items() if k in ncu]
+        if seen:
+            top = max(seen)
+            r["limiter"] = {"unit": top[1], "frac_of_peak": round(top[0] / 100.0, 3),
+                            "source": ncu.get("source")}
     if T.column:
         r["note"] = ("column-shared hoist over factored (x,u)+(x,w) tables: the kernel streams %.2f B "
                      "per backup instead of the dense layout's %.2f B and reads the inner "
