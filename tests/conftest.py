@@ -47,3 +47,16 @@ def policy_mismatch_report(pol_a, pol_b):
     """number of states whose control values differ at all"""
     diff = np.any(pol_a != pol_b, axis=-1)
     return int(diff.sum()), diff
+
+
+def _golden_cases():
+    """tests/golden/make_golden_cases.py as a module (problem factories of the fixtures)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "golden_cases", os.path.join(ROOT, "tests", "golden", "make_golden_cases.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+sys.modules.setdefault("golden_cases", _golden_cases())

@@ -18,6 +18,10 @@ Fixtures and the reference code path that produced them:
                      policy_iteration(pol_ini, 50, 4, rel_dp=True) (:693-812)
   searev_small.npz   config #4 callables on a 7x11x11 grid, control step .01: value_iteration x2,
                      policy_iteration(pol_lin, 30, 2, rel_dp=True)
+  column_cases.npz   grids with >= 32 rows of state axis 0, which the column-shared layout (CF)
+                     takes: storage-AR1 on 70 x 5 (control step 0.5): 3 x value_iteration from 0,
+                     one from a random J, policy_iteration(pol_ini, 10, 2, rel_dp=True);
+                     SEAREV on 33 x 4 x 3 (control step .05): 2 x value_iteration
   searev_full.npz    config #4 as shipped: policy_iteration(pol_lin, 1000, 5, rel_dp=True)
                      (== examples/20 .../storage control/pol_E10_grid3161_iter5.npy), ~15 min
 """
@@ -35,6 +39,8 @@ sys.path.insert(0, ROOT)
 
 from oracle.ref_loader import load_reference, load_reference_cython  # noqa: E402
 from stodynprog_b200 import workloads as wl  # noqa: E402
+sys.path.insert(0, HERE)
+from make_golden_cases import column_cases  # noqa: E402
 
 
 def quiet(fn, *a, **k):
@@ -185,12 +191,40 @@ def make_searev_full(ref):
          matches_shipped_npy=np.array(same))
 
 
+def make_column_cases(ref):
+    ar1, sea = column_cases(ref)
+    out = {}
+    sv = ar1.solver
+    J = ar1.J0
+    for k in range(3):
+        (J, u), _ = quiet(sv.value_iteration, J)
+        out['ar1_vi_J%d' % k] = J.copy()
+        out['ar1_vi_pol%d' % k] = u.copy()
+    J_rand = np.random.default_rng(70).standard_normal(sv._state_grid_shape)
+    (J, u), _ = quiet(sv.value_iteration, J_rand)
+    out['ar1_J_rand'], out['ar1_vr_J'], out['ar1_vr_pol'] = J_rand, J, u
+    pol_ini = ar1.initial_policy()
+    ((Jd, Jr), pol), text = quiet(sv.policy_iteration, pol_ini, 10, 2, rel_dp=True)
+    out['ar1_pi_J'], out['ar1_pi_Jref'], out['ar1_pi_pol'] = Jd, np.array(Jr), pol
+    out['ar1_pi_ref_costs'] = ref_costs(text)
+    sv = sea.solver
+    J = sea.J0
+    for k in range(2):
+        (J, u), _ = quiet(sv.value_iteration, J)
+        out['sea_vi_J%d' % k] = J.copy()
+        out['sea_vi_pol%d' % k] = u.copy()
+    save('column_cases.npz', **out)
+
+
 if __name__ == '__main__':
     ref = load_reference()
     assert ref is not None, 'the reference is not available here'
     if '--searev-full' in sys.argv:
         make_searev_full(ref)
+    elif '--column-cases' in sys.argv:
+        make_column_cases(ref)
     else:
+        make_column_cases(ref)
         make_interp_kat(ref)
         make_inventory(ref)
         make_pv(ref)

@@ -31,12 +31,13 @@ class _Api(object):
     bound either to the CUDA library or to the numpy model of the C ABI, and
     pinned to one table layout."""
 
-    def __init__(self, pkg, backend, layout="auto", tabulate="auto", compress="auto"):
+    def __init__(self, pkg, backend, layout="auto", tabulate="auto", compress="auto", column="auto"):
         self.pkg = pkg
         self.backend = backend
         self.layout = layout
         self.tabulate = tabulate
         self.compress = compress
+        self.column = column
         self.SysDescription = pkg.SysDescription
 
     def DPSolver(self, sys, **kw):
@@ -47,6 +48,7 @@ class _Api(object):
         sv.table_layout = self.layout
         sv.tabulate = self.tabulate
         sv.table_compress = self.compress
+        sv.column_hoist = self.column
         return sv
 
 
@@ -54,16 +56,20 @@ class _Api(object):
     pytest.param(("model", "control_minor", "auto", "off"), id="model-A"),
     pytest.param(("model", "state_minor", "auto", "off"), id="model-B"),
     pytest.param(("model", "control_minor", "auto", "auto"), id="model-AF"),
-    pytest.param(("model", "state_minor", "auto", "auto"), id="model-BF"),
+    pytest.param(("model", "state_minor", "auto", "auto", "off"), id="model-BF"),
+    pytest.param(("model", "state_minor", "auto", "auto", "auto"), id="model-CF"),
     pytest.param(("cuda", "control_minor", "auto", "off"), marks=gpu, id="cuda-A"),
     pytest.param(("cuda", "state_minor", "auto", "off"), marks=gpu, id="cuda-B"),
     pytest.param(("cuda", "control_minor", "auto", "auto"), marks=gpu, id="cuda-AF"),
-    pytest.param(("cuda", "state_minor", "auto", "auto"), marks=gpu, id="cuda-BF")])
+    pytest.param(("cuda", "state_minor", "auto", "auto", "off"), marks=gpu, id="cuda-BF"),
+    pytest.param(("cuda", "state_minor", "auto", "auto", "auto"), marks=gpu, id="cuda-CF")])
 def api(request, product):
     """host logic is exercised against the numpy model of the C ABI (CPU suite)
     and against the real CUDA library (GPU suite), for both table layouts, with
     dense tables (A, B) and with factored tables wherever the system has the
-    (x,u) + (x,w) structure (AF, BF; other systems fall back to dense)"""
+    (x,u) + (x,w) structure (AF, BF; other systems fall back to dense), and with the
+    column-shared hoist on top of BF wherever it applies (CF: the storage-AR1 problems,
+    whose 41 rows of axis 0 make two tiles per column)"""
     return _Api(product, *request.param)
 
 
@@ -826,6 +832,40 @@ def test_column_hoist_solvers_and_chunking(product, backend):
     for other in out[1:]:
         for a, b in zip(out[0], other):
             assert np.array_equal(np.asarray(a).view(np.int64), np.asarray(b).view(np.int64))
+
+
+@pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
+@pytest.mark.parametrize("colmode", ["on", "off"])
+def test_column_cases_golden(product, backend, colmode, capsys):
+    """fixtures generated from the unmodified reference on grids that layout CF takes
+    (tests/golden/column_cases.npz): value iteration from 0 and from a random J, policy
+    iteration with relative DP (2-D storage-AR1, 70 x 5) and value iteration on a 3-D SEAREV
+    grid (33 x 4 x 3) - through layout CF and, for comparison, through layout BF"""
+    from golden_cases import column_cases
+    G = golden("column_cases.npz")
+    ar1, sea = column_cases(_Api(product, backend, "state_minor", "auto", "on", colmode))
+    want_layout = "column_factored" if colmode == "on" else "state_minor_factored"
+    J = ar1.J0
+    for k in range(3):
+        J, pol = ar1.solver.value_iteration(J, report_time=False)
+        assert ar1.solver.last_tables.layout_name == want_layout
+        n_bad, _ = policy_mismatch_report(pol, G["ar1_vi_pol%d" % k])
+        assert n_bad == 0 and rel_err(J, G["ar1_vi_J%d" % k]) <= J_RTOL, k
+    J, pol = ar1.solver.value_iteration(G["ar1_J_rand"], report_time=False)
+    n_bad, _ = policy_mismatch_report(pol, G["ar1_vr_pol"])
+    assert n_bad == 0 and rel_err(J, G["ar1_vr_J"]) <= J_RTOL
+    (Jd, Jr), pol = ar1.solver.policy_iteration(ar1.initial_policy(), 10, 2, rel_dp=True)
+    n_bad, _ = policy_mismatch_report(pol, G["ar1_pi_pol"])
+    assert n_bad == 0 and abs(Jr - float(G["ar1_pi_Jref"])) <= J_RTOL * abs(float(G["ar1_pi_Jref"]))
+    assert np.max(np.abs(Jd - G["ar1_pi_J"])) <= J_RTOL * np.max(np.abs(G["ar1_pi_J"]))
+    printed = [float(l.split(':')[1]) for l in capsys.readouterr().out.splitlines() if 'ref policy cost' in l]
+    assert ['{:g}'.format(c) for c in printed] == ['{:g}'.format(c) for c in G["ar1_pi_ref_costs"]]
+    J = sea.J0
+    for k in range(2):
+        J, pol = sea.solver.value_iteration(J, report_time=False)
+        assert sea.solver.last_tables.layout_name == want_layout
+        n_bad, _ = policy_mismatch_report(pol, G["sea_vi_pol%d" % k])
+        assert n_bad == 0 and rel_err(J, G["sea_vi_J%d" % k]) <= J_RTOL, k
 
 
 @pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
