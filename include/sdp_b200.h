@@ -285,7 +285,10 @@ int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
               double* part_val, int32_t* part_idx, double* J_out, int32_t* argmin_out,
               void* stream);
 /* Layout CF: the pre-pass of the streaming pass alone (fills tab->col_table from J_prev),
- * for callers that sweep the item list in several launches with col_table_ready = 1. */
+ * for callers that sweep the item list in several launches with col_table_ready = 1.
+ * Part of K1: it evaluates, once per grid column and perturbation node, the inner levels of
+ * the nested lerp of multilinear_interpolation_{2,3}d (multilinear_cython.pyx:133-140,
+ * :195-208) that `J_next_interp(*x_next)` (stodynprog.py:677) repeats for every control. */
 int sdp_column_table(const SdpGrid* grid, const SdpTables* tab, const double* J_prev, void* stream);
 /* The two launches of sdp_sweep, separately (so that a caller can bracket the
  * streaming kernel alone with events): per-item partial minima, then the
