@@ -717,6 +717,10 @@ class Engine(object):
         return rebalance_bounds(U_all, T.bounds, t, self.REBALANCE_TOLERANCE)
 
     # -- sweep tables -----------------------------------------------------
+    # host cores for the per-state control_box scan of large grids (one rank; forked workers)
+    SCAN_PROCS = int(os.environ.get("SDP_SCAN_PROCS", str(min(8, os.cpu_count() or 1))))
+    SCAN_PARALLEL_MIN_STATES = 200 * 1000
+
     def build_sweep_tables(self, solver, t_k=None, reuse=None):
         """Tabulate the user's callables over this rank's slab and build the dense
         tables on the device.  `reuse`: a SweepTables whose device buffers are
@@ -770,6 +774,11 @@ class Engine(object):
                 # bit-for-bit with the reference's per-state calls
                 part = tb.scan_control_boxes_batched(sys, solver.control_steps, state_grid,
                                                      eq[rank], eq[rank + 1], t_k)
+            if part is None and world == 1 and self.SCAN_PROCS > 1 and n_grid >= self.SCAN_PARALLEL_MIN_STATES:
+                # box functions that do not vectorise (np.max((a, b)) on scalars, as in the
+                # reference's examples): one call per state, on several host cores
+                part = tb.scan_control_boxes_parallel(sys, solver.control_steps, state_grid,
+                                                      eq[rank], eq[rank + 1], t_k, self.SCAN_PROCS)
             if part is None:
                 mine = tb.state_tuples(state_grid, eq[rank], eq[rank + 1])
                 part = tb.scan_control_boxes(sys, solver.control_steps, mine, t_k)

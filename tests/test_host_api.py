@@ -398,6 +398,45 @@ def test_column_order_and_row_aligned_bounds():
     assert row_aligned([0, 349, 350], 5) == [0, 350, 350]
 
 
+def test_parallel_control_box_scan(monkeypatch):
+    """the per-state control_box scan on forked workers: same boxes and grid sizes, bit for
+    bit; None (serial scan takes over) when a worker fails; used by the table build of large
+    single-rank grids"""
+    from stodynprog_b200 import tabulate as tb, workloads as wl
+    from stodynprog_b200.engine import Engine
+    from fake_lib import FakeLib
+    sv = wl.storage_ar1(sdp, n_E=23, n_P=7, steps=(0.3, 0.1), _test_lib=FakeLib()).solver
+    n = 23 * 7
+    serial = tb.scan_control_boxes(sv.sys, sv.control_steps, tb.state_tuples(sv.state_grid, 5, n - 3))
+    par = tb.scan_control_boxes_parallel(sv.sys, sv.control_steps, sv.state_grid, 5, n - 3, None, procs=3)
+    assert par is not None
+    assert np.array_equal(par.lo.view(np.int64), serial.lo.view(np.int64))
+    assert np.array_equal(par.hi.view(np.int64), serial.hi.view(np.int64))
+    assert np.array_equal(par.npts, serial.npts)
+    assert tb.state_tuples_at(sv.state_grid, 17, 60) == tb.state_tuples(sv.state_grid, 17, 60)
+    assert tb.scan_control_boxes_parallel(sv.sys, sv.control_steps, sv.state_grid, 0, n, None, procs=1) is None
+
+    def bad_box(E, P_mis):
+        raise RuntimeError("box function failing in a worker")
+    good = sv.sys.control_box
+    sv.sys._control_box = bad_box            # (bypasses the signature check of the setter)
+    try:
+        assert tb.scan_control_boxes_parallel(sv.sys, sv.control_steps, sv.state_grid, 0, n, None, procs=2) is None
+    finally:
+        sv.sys._control_box = good
+    # the table build takes the parallel scan above its size threshold: same tables
+    J0 = np.random.default_rng(0).standard_normal((23, 7))
+    J_a, pol_a = sv.value_iteration(J0, report_time=False)
+    calls = []
+    real = tb.scan_control_boxes_parallel
+    monkeypatch.setattr(tb, "scan_control_boxes_parallel", lambda *a, **k: calls.append(1) or real(*a, **k))
+    monkeypatch.setattr(Engine, "SCAN_PARALLEL_MIN_STATES", 10)
+    monkeypatch.setattr(Engine, "SCAN_PROCS", 2)
+    sv2 = wl.storage_ar1(sdp, n_E=23, n_P=7, steps=(0.3, 0.1), _test_lib=FakeLib()).solver
+    J_b, pol_b = sv2.value_iteration(J0, report_time=False)
+    assert calls and np.array_equal(J_a, J_b) and np.array_equal(pol_a, pol_b)
+
+
 def test_no_cpu_fallback(product):
     """without a GPU the product refuses to run; without the library it says so"""
     import torch
