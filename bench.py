@@ -103,6 +103,16 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(name, dims, W):
+    """the `config` object: the workload, stated identically by both arms"""
+    return {"workload": name, "states": int(np.prod(dims)), "state_dims": [int(n) for n in dims],
+            "perturbation_nodes": int(W),
+            "J_init": "default_rng(0).standard_normal on the grid",
+            "l2": "GPU arm: every sweep streams its shard of the tables once (4.3 GB on one GPU, "
+                  "0.54 GB per GPU on eight; 126 MB of L2), so nothing is flushed between timed "
+                  "sweeps; CPU arm: not applicable"}
+
+
 def make_problem(api, args, **solver_kw):
     from stodynprog_b200 import workloads as wl
     if args.workload == "ar1":
@@ -138,44 +148,124 @@ def cpu_port_sample(args, n_states, seed=0, interp="c", J=None):
     return backups, time.perf_counter() - t0
 
 
+def port_sample_check(args, J_in, results, n_states, seed=1234):
+    """Parity of this run's own results, outside the timed region: `n_states` seeded random
+    states of the workload's grid are backed up by the oracle port (the reference's per-state
+    loop, stodynprog.py:639-691) from the same J_in, and compared with every (label, J_out,
+    pol) in `results`.  Returns the `verified` object of the bench line."""
+    from oracle import build as ob
+    ob.build()
+    from oracle.ref_port import port_api
+    prob, _ = make_problem(port_api("c"), args)
+    sv = prob.solver
+    dims = sv._state_grid_shape
+    J_interp = sv.interp_on_state(np.asarray(J_in).reshape(dims))
+    n_grid = int(np.prod(dims))
+    picks = np.random.default_rng(seed).choice(n_grid, size=min(n_states, n_grid), replace=False)
+    out = {"states": int(len(picks)), "policy_mismatch": 0, "J_rel": 0.0, "paths": {},
+           "checker": "oracle/ref_port.py (per-state numpy loop of the reference) on seeded random "
+                      "states of the same grid, same J_next"}
+    want_J = np.empty(len(picks))
+    want_pol = np.empty((len(picks), len(sv.sys.control)))
+    for n, flat in enumerate(picks):
+        idx = np.unravel_index(flat, dims)
+        x_k = tuple(g[i] for g, i in zip(sv.state_grid, idx))
+        want_J[n], want_pol[n] = sv.value_at_state(x_k, J_interp)
+    scale = np.maximum(np.abs(want_J), 1e-300)
+    for label, J_out, pol in results:
+        got_J = np.asarray(J_out).reshape(-1)[picks]
+        got_pol = np.asarray(pol).reshape(n_grid, -1)[picks]
+        bad = int(np.any(got_pol != want_pol, axis=1).sum())
+        err = float(np.max(np.abs(got_J - want_J) / scale))
+        out["paths"][label] = {"policy_mismatch": bad, "J_rel": err}
+        out["policy_mismatch"] += bad
+        out["J_rel"] = max(out["J_rel"], err)
+    out["ok"] = bool(out["policy_mismatch"] == 0 and out["J_rel"] <= 1e-10)
+    return out
+
+
+def reference_sample(args, solver, n_states, seed, J=None):
+    """time `n_states` seeded random states of the workload through the per-state backup of
+    `solver` - the UNMODIFIED reference's DPSolver._value_at_state_vect (stodynprog.py:639-691,
+    what its value_iteration calls for each state, :511-515) or the oracle port's restatement.
+    Returns (backups, seconds)."""
+    dims = solver._state_grid_shape
+    n_grid = int(np.prod(dims))
+    if J is None:
+        J = np.random.default_rng(0).standard_normal(dims)
+    J_interp = solver.interp_on_state(J)
+    picks = np.random.default_rng(seed).choice(n_grid, size=min(n_states, n_grid), replace=False)
+    W = len(solver.perturb_grid[0])
+    stock = hasattr(solver, "_value_at_state_vect")
+    states = []
+    backups = 0
+    for flat in picks:                       # (control counts are taken outside the timed loop)
+        idx = np.unravel_index(flat, dims)
+        x_k = tuple(g[i] for g, i in zip(solver.state_grid, idx))
+        states.append(x_k)
+        backups += int(np.prod(solver.control_grids(x_k)[1])) * W
+    fn = solver._value_at_state_vect if stock else solver.value_at_state
+    t0 = time.perf_counter()
+    for x_k in states:
+        fn(x_k, J_interp)
+    return backups, time.perf_counter() - t0
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path, bounded samples, rank 0 only"""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host
+    cores, bounded samples, rank 0 only.  The stock package (its .py files staged verbatim under
+    the git-ignored oracle/_ref/py by __graft_entry__.build(), its Cython routine compiled from
+    its own source into oracle/_ref) when present - kind "reference"; else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import contextlib
+    import io
     from oracle import build as ob
     ob.build()
-    interp = "c"
-    kind = "port"
+    kind, solver, how = "port", None, None
     try:
         from oracle import build_ref
-        if build_ref.build() is not None:
-            from oracle.ref_loader import load_reference_cython
-            if load_reference_cython() is not None:
-                interp = "ref"
-    except Exception:
-        pass
-    _, name = make_problem(__import__("oracle.ref_port", fromlist=["port_api"]).port_api(interp), args)
+        build_ref.build()
+        build_ref.stage_reference_python()
+        from oracle.ref_loader import load_reference
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = load_reference()
+        if ref is not None:
+            prob, name = make_problem(ref, args)
+            solver = prob.solver
+            kind = "reference"
+            how = ("the unmodified reference (stodynprog.DPSolver._value_at_state_vect, "
+                   "stodynprog.py:639-691, with its own compiled Cython interpolation)")
+    except Exception as e:
+        sys.stderr.write("stock reference unavailable (%s: %s); timing the oracle port\n"
+                         % (type(e).__name__, e))
+        solver = None
+    if solver is None:
+        from oracle.ref_port import port_api
+        prob, name = make_problem(port_api("c"), args)
+        solver = prob.solver
+        how = "the oracle port of the reference's per-state loop (oracle/ref_port.py + sdp_oracle.c)"
     n_sample = args.cpu_sample
     for _ in range(args.warmup):
-        cpu_port_sample(args, max(n_sample // 10, 10), seed=99, interp=interp)
+        reference_sample(args, solver, max(n_sample // 10, 10), seed=99)
     tot_b, tot_t = 0, 0.0
     for k in range(args.steps):
-        b, t = cpu_port_sample(args, n_sample, seed=k, interp=interp)
+        b, t = reference_sample(args, solver, n_sample, seed=k)
         tot_b += b
         tot_t += t
     value = tot_b / tot_t
-    sample = ("%d random states per step (seeded) of the %s grid, per-state numpy loop of the "
-              "reference restated in oracle/ref_port.py; interpolation through %s"
-              % (n_sample, "x".join(str(n) for n in (args.n_E, args.n_P)),
-                 "the reference's own compiled Cython routine (oracle/_ref)" if interp == "ref"
-                 else "the C restatement (oracle/sdp_oracle.c)"))
+    sample = ("%d seeded random states per step of the same %s grid (a full sweep is %d states, "
+              "~200 s on one core) through %s; 1 core: the reference is single-threaded (its prange "
+              "is compiled without OpenMP, setup.py:21)"
+              % (n_sample, "x".join(str(n) for n in solver._state_grid_shape),
+                 int(np.prod(solver._state_grid_shape)), how))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "sample": sample},
+        "config": workload_config(name, solver._state_grid_shape, len(solver.perturb_grid[0])),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -184,42 +274,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def kernel_name(T):
-    """the streaming kernel the library launches for this table layout (defaults of
-    csrc/sdp_b200.cu: TMA ring R=8 for layout B, hoisted inner interpolation for AF
-    with u_mask == 1)"""
-    d = T.d
-    if T.factored:
-        if T.column:
-            return "k_column_table<%d> + k_sweep_fact_column<%d,%d,2,2,%s,640>" % (
-                d, d, 3 if T.W <= 3 else (5 if T.W <= 5 else 9), "true" if T.W in (3, 5, 9) else "false")
-        if T.tiled:
-            return "k_sweep_fact_tiled<%d,%d,%d>" % (d, T.u_mask, 3 if T.W <= 3 else (5 if T.W <= 5 else 9))
-        if T.u_mask == 1:
-            wm = 3 if T.W <= 3 else (5 if T.W <= 5 else 9)
-            return "k_sweep_fact_hoist_c<%d,%d>" % (d, wm) if T.W <= 9 else "k_sweep_fact_hoist<%d,2>" % d
-        return "k_sweep_fact<%d,%d,4>" % (d, T.u_mask)
-    return "k_sweep_tiled_tma<%d,8>" % d if T.tiled else "k_sweep<%d,4>" % d
-
-
-def ncu_counters(workload, T, world):
-    """what the committed `ncu --set full` capture of this workload's streaming kernel says
-    (profiles/r1_traffic.json; N=1 only): {"traffic": DRAM bytes per launch, pipe
-    utilisations, source file}, or {}"""
-    if world != 1:
-        return {}
+def ncu_capture(kernel, n_states):
+    """the committed `ncu --set full` capture of this very kernel instantiation on a shard of this
+    very size (profiles/r2_traffic.json), or {}: DRAM bytes per launch and pipe utilisations are
+    properties of one (kernel, problem) pair and are attached to nothing else"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            e = json.load(f).get("%s/%s" % (workload, T.layout_name))
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            entries = json.load(f).get("captures", [])
     except Exception:
         return {}
-    if e is None:
-        return {}
-    return e if isinstance(e, dict) else {"traffic": e}
-
-
-def ncu_traffic(workload, T, world):
-    return ncu_counters(workload, T, world)
+    base = kernel.split(" [")[0]
+    for e in entries:
+        if e.get("kernel") == base and int(e.get("n_states", -1)) == int(n_states):
+            return dict(e, provenance="committed ncu capture (not measured in this run)")
+    return {}
 
 
 def time_sweeps(eng, T, J_prev, J_new, K, barrier):
@@ -235,50 +303,66 @@ def time_sweeps(eng, T, J_prev, J_new, K, barrier):
         J_prev, J_new = J_new, J_prev
     end.record()
     barrier()
-    return start.elapsed_time(end), np.array([a.elapsed_time(b) for a, b in kev]), J_prev, J_new
+    from stodynprog_b200 import _cabi
+    return (start.elapsed_time(end), np.array([a.elapsed_time(b) for a, b in kev]), J_prev, J_new,
+            _cabi.last_kernel())
 
 
-def roofline_of(T, k1_ms, ms_total, K, peak, peak_src, traffic):
+SMEM_BYTES_PER_CLK_PER_SM = 128       # B200 shared-memory data path (B300_MICROARCH.md)
+
+
+def roofline_of(T, kernel, k1_ms, ms_total, K, peak, peak_src, sm_count, sm_mhz):
+    """roofline object of the streaming kernel `kernel` (the library's own name for what it
+    launched).  `frac` is a UTILISATION of the unit that bounds the kernel:
+      dense tables (layouts A / B)   HBM: the 4 + 8d + 8/W algorithmic bytes per backup (= what the
+                                     kernel streams) over the measured copy bandwidth
+      factored tables (AF / BF)      HBM, on the bytes of the compressed tables (each read once per
+                                     sweep); the dense-equivalent rate is reported beside it
+      layout CF                      shared memory: 16 B per backup (two 8-byte reads of the column
+                                     table) over 128 B/clk/SM x SMs x the SM clock of this run
+    """
     b_alg = T.algorithmic_bytes_per_backup
     k1 = float(np.mean(k1_ms))
-    achieved = T.n_backups_local * b_alg / (k1 * 1e-3) / 1e9
-    ncu = traffic if isinstance(traffic, dict) else {}
-    traffic = ncu.get("traffic")
-    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-         "kernel": kernel_name(T), "kernel_ms": k1, "kernel_share_of_step": k1 * K / ms_total,
-         "algorithmic_bytes_per_backup": b_alg,
-         "algorithmic_bytes_per_launch": T.n_backups_local * b_alg,
-         "table_layout": T.layout_name,
-         "table_bytes_resident": T.device_bytes,
-         "streamed_bytes_per_backup": T.streamed_bytes_per_backup,
-         "streamed_GBs": T.device_bytes / (k1 * 1e-3) / 1e9}
-    if len(ncu) > 1:
-        r["ncu"] = {k: v for k, v in ncu.items() if k != "traffic"}
-        # the pipe the committed ncu capture shows closest to its peak: what actually bounds the
-        # kernel when `frac` (dense algorithmic bytes over the HBM peak) is not the binding ratio
-        pipes = {"l1_data_pipe_pct": "L1 / shared-memory data pipe (wavefronts)", "fp64_pipe_pct": "fp64 pipe",
-                 "dram_pct": "HBM", "l1_pct": "L1", "l2_pct": "L2"}
-        seen = [(float(ncu[k]), name) for k, name in pipes.items() if k in ncu]
-        if seen:
-            top = max(seen)
-            r["limiter"] = {"unit": top[1], "frac_of_peak": round(top[0] / 100.0, 3),
-                            "source": ncu.get("source")}
+    dense_rate = T.n_backups_local * b_alg / (k1 * 1e-3) / 1e9
+    streamed_rate = T.device_bytes / (k1 * 1e-3) / 1e9
+    cap = ncu_capture(kernel, T.n_states)
+    r = {"kernel": kernel, "kernel_ms": k1, "kernel_share_of_step": k1 * K / ms_total,
+         "table_layout": T.layout_name, "table_bytes_resident": T.device_bytes,
+         "traffic": cap.get("traffic")}
+    hbm = {"achieved": streamed_rate, "peak": peak, "unit": "GB/s", "frac": streamed_rate / peak,
+           "peak_source": peak_src, "bytes_per_backup": T.streamed_bytes_per_backup,
+           "what": "bytes of table the kernel reads per sweep (each once) / kernel time"}
     if T.column:
-        r["note"] = ("column-shared hoist over factored (x,u)+(x,w) tables: the kernel streams %.2f B "
-                     "per backup instead of the dense layout's %.2f B and reads the inner "
-                     "interpolation from a per-column table in shared memory, so `achieved` (dense "
-                     "algorithmic bytes / time, SURVEY.md 8d) exceeds the HBM peak; bound by shared-"
-                     "memory wavefronts / the fp64 pipe, see `dense_layout` for the HBM-bound kernel "
-                     "on the same workload" % (T.streamed_bytes_per_backup, b_alg))
-    elif T.factored:
-        r["note"] = ("factored (x,u)+(x,w) tables: the kernel streams %.2f B per backup instead of "
-                     "the dense layout's %.2f B, so `achieved` (dense algorithmic bytes / time, "
-                     "SURVEY.md 8d) exceeds the HBM peak; the kernel is bound by the L1 wavefronts "
-                     "of the corner gathers / the fp64 pipe, see `dense_layout` for the "
-                     "HBM-bound kernel on the same workload" % (T.streamed_bytes_per_backup, b_alg))
+        smem_peak = SMEM_BYTES_PER_CLK_PER_SM * sm_count * sm_mhz * 1e6 / 1e9
+        smem_rate = T.n_backups_local * 16.0 / (k1 * 1e-3) / 1e9
+        r.update({"bound": "smem", "achieved": smem_rate, "peak": smem_peak, "unit": "GB/s",
+                  "frac": smem_rate / smem_peak,
+                  "peak_source": "%d B/clk/SM x %d SMs x %.0f MHz (SM clock sampled in this run)"
+                                 % (SMEM_BYTES_PER_CLK_PER_SM, sm_count, sm_mhz),
+                  "algorithmic_bytes_per_backup": 16.0,
+                  "algorithmic_bytes_per_launch": T.n_backups_local * 16.0,
+                  "hbm": hbm})
     else:
-        r["padding_fill"] = T.n_backups_local / max(T.n_entries, 1)
+        r.update({"bound": "hbm", "achieved": streamed_rate, "peak": peak, "unit": "GB/s",
+                  "frac": streamed_rate / peak, "peak_source": peak_src,
+                  "algorithmic_bytes_per_backup": T.streamed_bytes_per_backup if T.factored else b_alg,
+                  "algorithmic_bytes_per_launch": float(T.device_bytes) if T.factored
+                  else T.n_backups_local * b_alg})
+        if not T.factored:
+            # (padding of the dense layouts counts against the fraction: streamed >= algorithmic)
+            r["achieved"] = dense_rate
+            r["frac"] = dense_rate / peak
+            r["padding_fill"] = T.n_backups_local / max(T.n_entries, 1)
+            r["streamed_GBs"] = streamed_rate
+    if T.factored:
+        r["dense_equivalent"] = {
+            "achieved": dense_rate, "unit": "GB/s", "over_hbm_peak": dense_rate / peak,
+            "bytes_per_backup": b_alg,
+            "what": "SURVEY.md 8d figure: the dense (x,u,w) layout's 4 + 8d + 8/W bytes per backup x "
+                    "backups / kernel time - NOT a utilisation: the compressed tables never stream "
+                    "those bytes (see `dense_layout` for the kernel that does)"}
+    if cap:
+        r["ncu"] = {k: v for k, v in cap.items() if k not in ("traffic", "kernel", "n_states")}
     return r
 
 
@@ -342,7 +426,7 @@ def run_ours(args):
 
     K = args.steps
     launches0 = _cabi.launch_count()
-    ms_total, k1_ms, J_prev, J_new = time_sweeps(eng, T, J_prev, J_new, K, barrier)
+    ms_total, k1_ms, J_prev, J_new, kernel = time_sweeps(eng, T, J_prev, J_new, K, barrier)
     launches = _cabi.launch_count() - launches0
     t = torch.tensor([ms_total, float(np.mean(k1_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -362,9 +446,7 @@ def run_ours(args):
     total_backups = T.n_backups_total
     value = total_backups * K / (ms_total_max * 1e-3)
 
-    # roofline of the streaming kernel on this rank's slab
     peak, peak_src = read_peaks()
-    roofline = roofline_of(T, k1_ms, ms_total, K, peak, peak_src, ncu_traffic(args.workload, T, world))
     J_keep = J_prev.clone()
 
     # end-to-end through the public API, host arrays in and out
@@ -400,6 +482,11 @@ def run_ours(args):
 
     e2e = time_e2e("all")
     clocks = sampler.stop() if rank == 0 else None
+    # roofline of the streaming kernel on this rank's shard (rank 0's is printed)
+    props = torch.cuda.get_device_properties(local_rank)
+    sm_count = props.multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or getattr(props, "clock_rate", 1965000) / 1e3
+    roofline = roofline_of(T, kernel, k1_ms, ms_total, K, peak, peak_src, sm_count, sm_mhz)
     e2e_all = None
     if world > 1:
         # 8 ranks pulling 24 MB each through shared PCIe roots take ~2 ms, one rank 0.45 ms
@@ -407,6 +494,26 @@ def run_ours(args):
         e2e_all = e2e
         e2e = time_e2e("root")
         sv.host_results = "all"
+
+    # parity of THIS run, outside the timed regions: one more sweep from J_keep through the
+    # device-resident path that was timed (Engine.sweep + exchange) and one through the public
+    # API (the e2e path), both compared with the oracle port on seeded random states
+    verified = None
+    if args.verify_states > 0:
+        Ja, Jb = eng.J_pair(n_grid)
+        eng.begin_call(n_grid)
+        Ja.copy_(J_keep)
+        eng.sweep(T, Ja, Jb)
+        pol_dev = eng.policy_values(T, eng.gather_argmin(T))
+        J_dev_out, pol_dev_out = eng.to_host(Jb, pol_dev)
+        J_in_host = J_keep.cpu().numpy().reshape(dims)
+        sv.host_results = "all"
+        J_api_out, pol_api_out = sv.value_iteration(J_in_host.copy(), report_time=False)
+        if rank == 0:
+            verified = port_sample_check(args, J_in_host, [
+                ("Engine.sweep (device-resident, timed path)", J_dev_out, pol_dev_out),
+                ("DPSolver.value_iteration (e2e path)", J_api_out, pol_api_out)], args.verify_states)
+        barrier()
 
     # the same workload through the dense (x,u,w) tables: the HBM-bound kernel the
     # roofline target is stated for
@@ -422,14 +529,13 @@ def run_ours(args):
             eng.sweep(Td, Ja, Jb)
             Ja, Jb = Jb, Ja
         Kd = max(5, min(K, 10))
-        ms_d, k1_d, Ja, Jb = time_sweeps(eng, Td, Ja, Jb, Kd, barrier)
+        ms_d, k1_d, Ja, Jb, kernel_d = time_sweeps(eng, Td, Ja, Jb, Kd, barrier)
         td = torch.tensor([ms_d], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dense = {"value": total_backups * Kd / (float(td[0]) * 1e-3), "unit": UNIT, "steps": Kd,
                  "ms_per_step": float(td[0]) / Kd,
-                 "roofline": roofline_of(Td, k1_d, ms_d, Kd, peak, peak_src,
-                                         ncu_traffic(args.workload, Td, world))}
+                 "roofline": roofline_of(Td, kernel_d, k1_d, ms_d, Kd, peak, peak_src, sm_count, sm_mhz)}
         sv.table_compress = args.compress
         sv.column_hoist = args.column_hoist
         del Td
@@ -453,29 +559,29 @@ def run_ours(args):
                          "reference is single-threaded: prange compiled without OpenMP)"
                          % (args.cpu_sample, b)}
     if rank == 0 and world == 1 and args.workload == "large" and not args.no_extra:
-        extra = measure_config3(sdp, peak, peak_src)
+        extra = measure_config3(sdp, peak, peak_src, sm_count, sm_mhz)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms_total_max / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "states": n_grid, "backups_per_sweep": total_backups,
-                       "state_dims": list(dims), "perturbation_nodes": T.W,
-                       "table_layout": T.layout_name,
-                       "row_bands": (T.bands["rows"] if T.column else None),
-                       "tabulate_mode": T.tabulate_mode, "item_chunk": T.item_chunk,
-                       "parallelism": "state slabs x%d, %s" % (
-                           world, "one rank" if world == 1 else
-                           ("J slab stored into every rank's buffer by the combine kernel over NVLink "
-                            "peer memory + flag wait" if eng.peer_exchange(n_grid) is not None
-                            else "NCCL all-gather of J per sweep")),
-                       "l2": "tables streamed once per sweep (%.1f GB per GPU) >> 126 MB L2; "
-                             "no flush needed" % (T.device_bytes / 1e9),
-                       "J_init": "default_rng(0).standard_normal, then fed back sweep to sweep"},
+            "config": workload_config(name, dims, T.W),
+            "plan": {"backups_per_sweep": total_backups, "table_layout": T.layout_name,
+                     "row_bands": (T.bands["rows"] if T.column else None),
+                     "shard_axis": (None if world == 1 else "columns" if T.col_bounds is not None else "rows"),
+                     "tabulate_mode": T.tabulate_mode, "item_chunk": T.item_chunk,
+                     "table_gb_per_gpu": T.device_bytes / 1e9,
+                     "parallelism": "state shards x%d, %s" % (
+                         world, "one rank" if world == 1 else
+                         ("J shard stored into every rank's buffer by the combine kernel over NVLink "
+                          "peer memory + flag wait" if eng.peer_exchange(n_grid) is not None
+                          else "NCCL all-gather of J per sweep"))},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "clocks": clocks, "setup_seconds": float(setup[0]),
         }
+        if verified is not None:
+            line["verified"] = verified
         if e2e_all is not None:
             line["e2e_all_ranks"] = e2e_all
         if k1_per_rank is not None:
@@ -492,7 +598,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_config3(sdp, peak, peak_src, steps=50, warmup=5):
+def measure_config3(sdp, peak, peak_src, sm_count, sm_mhz, steps=50, warmup=5):
     """BASELINE configs[2] (the 41x61 storage-AR1 grid of the notebook, 142 762 509
     backups per sweep): the grid the north star's 60 % roofline target is quoted on.
     Reported for the default (factored) tables and for the dense tables."""
@@ -510,13 +616,13 @@ def measure_config3(sdp, peak, peak_src, steps=50, warmup=5):
         for _ in range(warmup):
             eng.sweep(T, J_prev, J_new)
             J_prev, J_new = J_new, J_prev
-        ms_total, k1_ms, J_prev, J_new = time_sweeps(eng, T, J_prev, J_new, steps,
-                                                     torch.cuda.synchronize)
+        ms_total, k1_ms, J_prev, J_new, kernel = time_sweeps(eng, T, J_prev, J_new, steps,
+                                                             torch.cuda.synchronize)
         out["backups_per_sweep"] = T.n_backups_total
         out["default" if compress == "auto" else "dense_layout"] = {
             "ms_per_step": ms_total / steps, "value": T.n_backups_total * steps / (ms_total * 1e-3),
             "unit": UNIT,
-            "roofline": roofline_of(T, k1_ms, ms_total, steps, peak, peak_src, ncu_traffic("ar1", T, 1))}
+            "roofline": roofline_of(T, kernel, k1_ms, ms_total, steps, peak, peak_src, sm_count, sm_mhz)}
     return out
 
 
@@ -539,6 +645,8 @@ def main():
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=None,
                     help="states per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify-states", dest="verify_states", type=int, default=1000,
+                    help="states of the final sweep checked against the oracle port (0: skip)")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SDP_ABI_VERSION 5
+#define SDP_ABI_VERSION 6
 #define SDP_MAX_D 4 /* the reference dispatches d = 1..4 (multilinear_cython.pyx:36-47) */
 
 /* error codes */
@@ -212,6 +212,10 @@ int sdp_version(void);
 const char* sdp_last_error(void);
 /* Number of kernels launched by this library since load (for bench accounting). */
 int64_t sdp_launch_count(void);
+/* Name (template arguments, CTA shape) of the streaming kernel that the calling thread's last
+ * sdp_sweep / sdp_sweep_partials launched: what a bench line or a profile summary must call
+ * it.  Valid until that thread's next launch. */
+const char* sdp_last_kernel(void);
 
 /* Launch tuning (developer knob; defaults are read from SDP_* environment
  * variables): "upl" (2|4), "wb" (1|2|3|5), "tma" (layout-B kernel: 0 straight

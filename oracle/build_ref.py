@@ -54,6 +54,32 @@ def build(force=False, verbose=False):
     return so
 
 
+PY_STAGE = os.path.join(OUT_DIR, "py")      # oracle/_ref/py/stodynprog/*.py (git-ignored)
+
+
+def stage_reference_python(force=False):
+    """Build artefact for the GPU box: the reference's own Python package, copied VERBATIM from
+    where it lies (/root/reference/stodynprog/**/*.py) into the git-ignored oracle/_ref/py/, next
+    to its compiled routine.  It never enters the repository's history; it travels with the
+    snapshot so that `bench.py --impl reference` can time the unmodified
+    DPSolver._value_at_state_vect (stodynprog.py:639-691) on the GPU box's host cores, where
+    /root/reference does not exist.  Returns the directory to put on sys.path, or None."""
+    src = os.path.join(REF_ROOT, "stodynprog")
+    dst = os.path.join(PY_STAGE, "stodynprog")
+    if os.path.exists(os.path.join(dst, "stodynprog.py")) and not force:
+        return PY_STAGE
+    if not os.path.exists(os.path.join(src, "stodynprog.py")):
+        return None
+    for base, dirs, files in os.walk(src):
+        rel = os.path.relpath(base, src)
+        for f in files:
+            if f.endswith(".py"):
+                os.makedirs(os.path.join(dst, rel), exist_ok=True)
+                shutil.copyfile(os.path.join(base, f), os.path.join(dst, rel, f))
+    return PY_STAGE
+
+
 if __name__ == "__main__":
+    print("oracle/_ref/py:", stage_reference_python(force="--force" in sys.argv))
     p = build(force="--force" in sys.argv, verbose=True)
     print("oracle/_ref:", p)

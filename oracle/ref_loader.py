@@ -4,8 +4,10 @@ TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py to generate the
 committed golden fixtures, and by the (container-only) cross-check tests.  The
 reference tree is never copied or modified: its Python package is imported from
 where it lies (/root/reference) and its Cython routine is the object compiled by
-oracle/build_ref.py.  On the GPU box /root/reference does not exist and
-`load_reference()` returns None.
+oracle/build_ref.py.  On the GPU box /root/reference does not exist: there the
+package is imported from the verbatim, git-ignored copy that `__graft_entry__.build()` stages
+under oracle/_ref/py (build_ref.stage_reference_python) - for `bench.py --impl reference` only;
+without it `load_reference()` returns None.
 
 Three shims are needed on py3.12 / numpy 2.x; they are
 applied to the *environment*, not to the reference's files:
@@ -27,8 +29,20 @@ REF_ROOT = os.environ.get("STODYNPROG_REFERENCE", "/root/reference")
 _cache = {}
 
 
+def _package_root():
+    """directory holding the reference's `stodynprog` package: the read-only reference tree in
+    the build container, else the verbatim copy staged by build_ref.stage_reference_python()
+    (git-ignored oracle/_ref/py, the only form in which it reaches the GPU box)"""
+    if os.path.exists(os.path.join(REF_ROOT, "stodynprog", "stodynprog.py")):
+        return REF_ROOT
+    from . import build_ref
+    if os.path.exists(os.path.join(build_ref.PY_STAGE, "stodynprog", "stodynprog.py")):
+        return build_ref.PY_STAGE
+    return None
+
+
 def reference_available():
-    return os.path.exists(os.path.join(REF_ROOT, "stodynprog", "stodynprog.py"))
+    return _package_root() is not None
 
 
 def _apply_shims():
@@ -87,8 +101,9 @@ def load_reference():
     cy = load_reference_cython()
     # the compiled routine lives outside the (read-only) reference tree:
     sys.modules["stodynprog.dolointerpolation.multilinear_cython"] = cy
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    root = _package_root()
+    if root not in sys.path:
+        sys.path.insert(0, root)
     # the reference package's __init__ does `from stodynprog import tests`
     # which needs nose: give it an inert stub.
     if "nose" not in sys.modules:

@@ -12,7 +12,7 @@ import numpy as np
 
 SDP_MAX_D = 4
 SDP_MAX_C = 4
-SDP_ABI_VERSION = 5
+SDP_ABI_VERSION = 6
 LAYOUT_CONTROL_MINOR = 0   # "A": [state][w][u]
 LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
 LAYOUT_CONTROL_MINOR_FACTORED = 2   # "AF": (x,u) part [state][Upad] + (x,w) part [state][W]
@@ -117,6 +117,7 @@ SIGNATURES = {
     "sdp_version": (ctypes.c_int, []),
     "sdp_last_error": (ctypes.c_char_p, []),
     "sdp_launch_count": (_i64, []),
+    "sdp_last_kernel": (ctypes.c_char_p, []),
     "sdp_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "sdp_cell_setup": (ctypes.c_int, [_gp, _i64, _vp, _vp, _vp, _vp]),
     "sdp_build_tables": (ctypes.c_int, [_gp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp,
@@ -206,3 +207,9 @@ def make_grid(state_grid):
 
 def launch_count():
     return int(load_library().sdp_launch_count())
+
+
+def last_kernel():
+    """the streaming kernel this thread's last sweep launched, as the library names it"""
+    name = load_library().sdp_last_kernel()
+    return name.decode("utf-8", "replace") if name else ""

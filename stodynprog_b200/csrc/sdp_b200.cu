@@ -23,6 +23,7 @@
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <stdarg.h>
 #include <stdlib.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -62,6 +63,17 @@ static int fail(int code, const char* fmt, const char* detail) {
 extern "C" int sdp_version(void) { return SDP_ABI_VERSION; }
 extern "C" const char* sdp_last_error(void) { return g_err; }
 extern "C" int64_t sdp_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// name (template arguments, CTA shape) of the streaming kernel the calling thread's last
+// sdp_sweep_partials launched: what a bench line or a profile summary should call it
+static thread_local char g_last_kernel[192] = "";
+static void note_kernel(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_kernel, sizeof(g_last_kernel), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* sdp_last_kernel(void) { return g_last_kernel; }
 
 // ---------------------------------------------------------------------------
 // device-side grid description (kernel parameter, lives in constant bank)
@@ -1140,6 +1152,7 @@ static int launch_tiled_tma(const GridT<double>& G, const SdpTables& T, const do
     }
     unsigned blocks = (unsigned)((T.n_items + NW - 1) / NW);
     k_sweep_tiled_tma<D, R><<<blocks, NW * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, S);
+    note_kernel("k_sweep_tiled_tma<%d,%d> [%d stages, %d threads]", D, R, S, NW * 32);
     *launched = true;
     SDP_LAUNCH_CHECK();
     return SDP_OK;
@@ -1159,6 +1172,7 @@ static int launch_sweep(const GridT<double>& G, const SdpTables& T, const double
                 case 8: k_sweep_tiled_pipe<D, 8><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
                 default: k_sweep_tiled_pipe<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
             }
+            note_kernel("k_sweep_tiled_pipe<%d,%d>", D, (t.rb == 2 || t.rb == 8) ? t.rb : 4);
             SDP_LAUNCH_CHECK();
             return SDP_OK;
         }
@@ -1176,10 +1190,14 @@ static int launch_sweep(const GridT<double>& G, const SdpTables& T, const double
             case 5: k_sweep_tiled<D, 5><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
             default: k_sweep_tiled<D, 1><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx); break;
         }
-    } else if (t.upl == 2)
+        note_kernel("k_sweep_tiled<%d,%d>", D, (t.wb == 2 || t.wb == 3 || t.wb == 5) ? t.wb : 1);
+    } else if (t.upl == 2) {
         k_sweep<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
-    else
+        note_kernel("k_sweep<%d,2>", D);
+    } else {
         k_sweep<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
+        note_kernel("k_sweep<%d,4>", D);
+    }
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
@@ -1731,6 +1749,7 @@ static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, cons
     for (int w = 0; w < SDP_FACTORED_MAX_W_REG; ++w)
         pv.v[w] = (w < T.W) ? (T.expect ? T.p_host[w] : 1.0) : 0.0;
     k_sweep_fact_tiled<D, MASK, WM><<<blocks, warps * 32, 0, st>>>(G, T, Jprev, part_val, part_idx, pv);
+    note_kernel("k_sweep_fact_tiled<%d,%d,%d>", D, MASK, WM);
 }
 
 // ---------------------------------------------------------------------------
@@ -2020,6 +2039,9 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
     else
         k_sweep_fact_column<D, WM, UB, PF, false, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
             G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, tuning().col_dynamic);
+    note_kernel("%sk_sweep_fact_column<%d,%d,%d,%d,%s,%d> [%d CTAs x %d threads]",
+                (prepass && !T.col_table_ready) ? "k_column_table + " : "", D, WM, UB, PF,
+                T.W == WM ? "true" : "false", MAXT, (int)T.n_segs, threads);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
@@ -2081,6 +2103,7 @@ static int launch_fact_m(const GridT<double>& G, const SdpTables& T, const doubl
                     k_sweep_fact_hoist_c<D, 5><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0, pv);
                 else
                     k_sweep_fact_hoist_c<D, 9><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0, pv);
+                note_kernel("k_sweep_fact_hoist_c<%d,%d>", D, T.W <= 3 ? 3 : (T.W <= 5 ? 5 : 9));
                 SDP_LAUNCH_CHECK();
                 return SDP_OK;
             }
@@ -2091,6 +2114,7 @@ static int launch_fact_m(const GridT<double>& G, const SdpTables& T, const doubl
                     k_sweep_fact_hoist<D, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0);
                 else
                     k_sweep_fact_hoist<D, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx, RP, inv0);
+                note_kernel("k_sweep_fact_hoist<%d,%d>", D, tuning().hoist_upl == 2 ? 2 : 4);
                 SDP_LAUNCH_CHECK();
                 return SDP_OK;
             }
@@ -2100,6 +2124,7 @@ static int launch_fact_m(const GridT<double>& G, const SdpTables& T, const doubl
             k_sweep_fact<D, MASK, 2><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
         else
             k_sweep_fact<D, MASK, 4><<<blocks, warps * 32, shm, st>>>(G, T, Jprev, part_val, part_idx);
+        note_kernel("k_sweep_fact<%d,%d,%d>", D, MASK, tuning().upl == 2 ? 2 : 4);
     }
     SDP_LAUNCH_CHECK();
     return SDP_OK;

@@ -818,6 +818,11 @@ class Engine(object):
         if slab_axis == "auto":
             slab_axis = SLAB_AXIS_DEFAULT
         by_columns = world > 1 and slab_axis == "columns"
+        # developer experiments (scripts/dev_shard_emulation.py): the tables of ONE column shard
+        # [c0, c1) of the grid on a single rank, as a rank of a multi-GPU run would hold them
+        col_override = getattr(solver, "_col_override", None) if world == 1 else None
+        if col_override is not None:
+            by_columns = True
         if by_columns and not (col_candidate and n_cols >= world):
             raise ValueError("slab_axis='columns' needs layout CF (column_hoist) and at least one "
                              "grid column per rank")
@@ -860,7 +865,9 @@ class Engine(object):
             if (compress != "off" and n > 0 and nb_perturb == 1 and 1 < W <= w_cap and d in (2, 3)
                     and nb_control <= _cabi.SDP_MAX_C):
                 i_probe = int(np.argmax(U))
-                x_probe = tb.state_tuples(state_grid, sb + i_probe, sb + i_probe + 1)[0]
+                # (host row i_probe is grid state glob[i_probe] when the shard is whole columns)
+                g_probe = int(glob[i_probe]) if by_columns else sb + i_probe
+                x_probe = tb.state_tuples_at(state_grid, g_probe, g_probe + 1)[0]
                 u_mask = tb.probe_factor_mask(sys, x_probe, host, i_probe, w_grid, t_k) or 0
             if compress == "on" and not u_mask:
                 raise ValueError("table_compress='on' but the system's dyn/cost do not have the "
@@ -927,7 +934,9 @@ class Engine(object):
             T.expect = 1 if nb_perturb == 1 else 0
             T.bounds, T.state_begin, T.n_states = bounds, sb, n
             T.col_bounds = None
-            if by_columns:
+            if by_columns and col_override is not None:
+                T.bounds, T.state_begin, T.col_bounds = None, 0, [int(b) for b in bounds]
+            elif by_columns:
                 # the exchange goes by grid position, not by slab: T.bounds stays None
                 T.bounds, T.state_begin, T.col_bounds = None, 0, [int(b) for b in bounds]
                 widths = np.diff(np.asarray(bounds, dtype=np.int64))
@@ -1193,7 +1202,9 @@ class Engine(object):
             return T
 
         # slabs balanced by admissible controls ...
-        if by_columns:
+        if col_override is not None:
+            bounds = [int(col_override[0]), int(col_override[1])]
+        elif by_columns:
             # whole columns per rank, cut by the admissible controls of the columns
             col_w = (U_all + 1).reshape(n_rows0, n_cols).sum(axis=0)
             bounds = [int(b) for b in partition_by_weight(col_w, world)]

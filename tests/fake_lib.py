@@ -53,6 +53,9 @@ class FakeLib(object):
     def sdp_launch_count(self):
         return self.launches
 
+    def sdp_last_kernel(self):
+        return b"fake_lib (numpy model of the ABI)"
+
     def sdp_cell_setup(self, gref, n, s, cell, lam, stream):
         d, smin, smax, orders = _grid(gref)
         S = _arr(s, d * n, ctypes.c_double).reshape(d, n)
