@@ -1,0 +1,80 @@
+"""developer experiment (torchrun, one process per GPU): where a sharded sweep of config #5 spends
+its time on every rank - streaming kernel (pre-pass + column sweep), fused combine + peer stores +
+epoch, flag wait - from CUDA events between the launches of Engine.sweep's peer-memory path.
+    torchrun --nproc-per-node N scripts/dev_exchange_breakdown.py [K]"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+os.environ.setdefault("SDP_P2P_TIMEOUT_S", "60")
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+import stodynprog_b200 as sdp  # noqa: E402
+from stodynprog_b200 import workloads as wl, _cabi  # noqa: E402
+
+sv = wl.storage_ar1_large(sdp).solver
+eng = sv.engine
+T = sv.sweep_tables()
+n_grid = int(np.prod(sv._state_grid_shape))
+J_prev, J_new = eng.J_pair(n_grid)
+eng.begin_call(n_grid)
+eng.upload_J(np.random.default_rng(0).standard_normal(n_grid), J_prev)
+px = eng._peer[n_grid]
+assert px is not None, "needs the peer-memory exchange"
+st = eng.torch_stream
+lib = eng.lib
+
+
+def one(J_prev, J_new, ev):
+    k_new = px.index_of(J_new)
+    ev[0].record(st)
+    _cabi.check(lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables), eng._ptr(J_prev),
+                                       eng._ptr(T.part_val), eng._ptr(T.part_idx), eng.stream), "partials")
+    ev[1].record(st)
+    if T.col_bounds is not None:
+        rc = lib.sdp_sweep_finalize_p2p_cols(ctypes.byref(T.c_tables), eng._ptr(T.part_val), eng._ptr(T.part_idx),
+                                             eng._ptr(T.argmin), ctypes.byref(px.peers[k_new]),
+                                             T.col_bounds[-1], T.col_bounds[rank], eng.stream)
+    else:
+        rc = lib.sdp_sweep_finalize_p2p(ctypes.byref(T.c_tables), eng._ptr(T.part_val), eng._ptr(T.part_idx),
+                                        eng._ptr(T.argmin), ctypes.byref(px.peers[k_new]), T.state_begin,
+                                        eng.stream)
+    _cabi.check(rc, "finalize_p2p")
+    ev[2].record(st)
+    _cabi.check(lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), eng.stream), "wait")
+    ev[3].record(st)
+
+
+evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+for _ in range(5):
+    one(J_prev, J_new, evs[0])
+    J_prev, J_new = J_new, J_prev
+dist.barrier()
+torch.cuda.synchronize()
+for k in range(K):
+    one(J_prev, J_new, evs[k])
+    J_prev, J_new = J_new, J_prev
+torch.cuda.synchronize()
+seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in evs[3:]])
+gap = np.array([evs[k][3].elapsed_time(evs[k + 1][0]) for k in range(3, K - 1)])
+tot = evs[3][0].elapsed_time(evs[K - 1][3]) / (K - 3)
+mine = torch.tensor(list(seg.mean(axis=0)) + [gap.mean(), tot], dtype=torch.float64, device="cuda")
+allr = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+dist.all_gather(allr, mine)
+if rank == 0:
+    print("shards of %s, %d ranks, %s; ms per sweep" % ("columns" if T.col_bounds is not None else "rows",
+                                                      dist.get_world_size(), _cabi.last_kernel()))
+    print("rank  kernel  combine+stores+epoch  wait  gap   step")
+    for r, x in enumerate(allr):
+        print("%4d  %.4f  %.4f                %.4f %.4f %.4f" % ((r,) + tuple(float(v) for v in x)))
+dist.barrier()
+dist.destroy_process_group()

@@ -38,7 +38,7 @@ for STEP in "$@"; do
       cat $OUT/${TAG}_bench_reference.json ;;
     check)
       PORT=$((PORT+1))
-      ( time SDP_CHECK_COLUMN_AXIS=1 timeout 600 $TR --master-port $PORT tests/multi_gpu_check.py ) > $OUT/${TAG}_multi_gpu_check_n$N.log 2>&1
+      ( time SDP_CHECK_COLUMN_AXIS=1 SDP_CHECK_BENCH_GRID=1 timeout 600 $TR --master-port $PORT tests/multi_gpu_check.py ) > $OUT/${TAG}_multi_gpu_check_n$N.log 2>&1
       echo "exit: $?" >> $OUT/${TAG}_multi_gpu_check_n$N.log
       grep -v "^\[W\|Warning" $OUT/${TAG}_multi_gpu_check_n$N.log | tail -30 ;;
     emu)

@@ -25,9 +25,12 @@ __all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "reba
 # SDP_COLUMN_HOIST=0; "on" / "off" on the solver override it.  Measured on config #5, one B200
 # (profiles/r1_column_tuning.txt): 1.21 ms per sweep against 2.83 ms for layout BF.
 COLUMN_HOIST_DEFAULT = os.environ.get("SDP_COLUMN_HOIST", "1") != "0"
-# solver.slab_axis = "auto": how a grid in layout CF is cut over several ranks ("rows" |
-# "columns"); by columns is the better cut on paper but has not run on GPUs yet
-SLAB_AXIS_DEFAULT = os.environ.get("SDP_SLAB_AXIS", "rows")
+# solver.slab_axis = "auto": how a grid in layout CF is cut over several ranks ("auto" | "rows" |
+# "columns").  By columns every rank tabulates and loads the tables of its own columns only;
+# measured on config #5 (profiles/r2_shard_emulation.txt, one rank's streaming kernel): 0.179 ms
+# against 0.233 ms per sweep for 1/8 of the grid, 0.61 against 0.65 ms for 1/2.  "auto" cuts
+# by columns whenever layout CF applies and every rank gets at least 4 columns.
+SLAB_AXIS_DEFAULT = os.environ.get("SDP_SLAB_AXIS", "auto")
 
 
 def _torch():
@@ -163,6 +166,11 @@ def pick_item_chunk(unit_U, min_chunk, max_chunk=512, target=ITEMS_TARGET):
     return max(chunk, min_chunk)
 
 
+class _ColumnsNotApplicable(Exception):
+    """the cut by columns was chosen by "auto" but layout CF turned out not to apply to the
+    built tables: build_sweep_tables starts again with slabs of rows"""
+
+
 class ColumnHoistRefused(Exception):
     """layout CF was demanded (column_hoist = 'on') for tables whose (x,w) part varies
     along a column of the grid"""
@@ -231,6 +239,34 @@ def row_aligned(bounds, n_cols):
         out.append(max(out[-1], int(round(float(b) / n_cols)) * n_cols))
     out.append(int(bounds[-1]))
     return [min(b, out[-1]) for b in out]
+
+
+class _DeviceBoundLib(object):
+    """The C ABI launches on the calling thread's CURRENT device (it takes raw pointers and a
+    stream, and never calls cudaSetDevice).  An Engine made for `device` must therefore make that
+    device current around every entry point, or DPSolver(sys, device='cuda:1') would launch on
+    GPU 0 against GPU 1 pointers.  `torch.cuda.device` is a no-op when the device is already
+    current (one C++ call)."""
+
+    def __init__(self, lib, device):
+        self._lib = lib
+        self._guard = _torch().cuda.device(device)
+        self._wrapped = {}
+
+    def __getattr__(self, name):
+        fn = self._wrapped.get(name)
+        if fn is None:
+            raw = getattr(self._lib, name)
+            if not name.startswith("sdp_") or name in ("sdp_version", "sdp_last_error", "sdp_launch_count",
+                                                       "sdp_last_kernel", "sdp_set_option"):
+                return raw
+            guard = self._guard
+
+            def fn(*args):
+                with guard:
+                    return raw(*args)
+            self._wrapped[name] = fn
+        return fn
 
 
 class Collective(object):
@@ -522,7 +558,10 @@ class Engine(object):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self._cuda = True
+        self.lib = _DeviceBoundLib(self.lib, self.device)
 
     # -- helpers ----------------------------------------------------------
     @property
@@ -531,6 +570,11 @@ class Engine(object):
         if not self._cuda:
             return ctypes.c_void_p(0)
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def torch_stream(self):
+        """the launching stream (torch's current stream of THIS engine's device)"""
+        return _torch().cuda.current_stream(self.device)
 
     def _ptr(self, t):
         return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
@@ -702,12 +746,12 @@ class Engine(object):
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                    for _ in range(7)]
             for a, b in evs:
-                a.record()
+                a.record(self.torch_stream)
                 rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
                                                  self._ptr(J), self._ptr(T.part_val),
                                                  self._ptr(T.part_idx), self.stream)
                 _cabi.check(rc, "sdp_sweep_partials")
-                b.record()
+                b.record(self.torch_stream)
             self.sync()
             t_mine = float(np.median([a.elapsed_time(b) for a, b in evs[2:]]))
         t = np.asarray(coll.all_gather_object(t_mine), dtype=float)
@@ -717,11 +761,23 @@ class Engine(object):
         return rebalance_bounds(U_all, T.bounds, t, self.REBALANCE_TOLERANCE)
 
     # -- sweep tables -----------------------------------------------------
-    # host cores for the per-state control_box scan of large grids (one rank; forked workers)
-    SCAN_PROCS = int(os.environ.get("SDP_SCAN_PROCS", str(min(8, os.cpu_count() or 1))))
+    # host cores for the per-state control_box scan of large grids (one rank; forked workers).
+    # Opt-in (SDP_SCAN_PROCS=8): forking a process that holds a CUDA context and BLAS threads is
+    # only safe for plain-numpy box functions; the scans above cover the common cases without it
+    SCAN_PROCS = int(os.environ.get("SDP_SCAN_PROCS", "1"))
     SCAN_PARALLEL_MIN_STATES = 200 * 1000
 
     def build_sweep_tables(self, solver, t_k=None, reuse=None):
+        """Tabulate the user's callables over this rank's shard and build the tables on the
+        device (see _build_sweep_tables).  With several ranks and slab_axis "auto" the grid is
+        cut by columns when layout CF is expected to apply; if the built tables refuse it (same
+        decision on every rank), the build starts again with slabs of rows."""
+        try:
+            return self._build_sweep_tables(solver, t_k, reuse, None)
+        except _ColumnsNotApplicable:
+            return self._build_sweep_tables(solver, t_k, None, "rows")
+
+    def _build_sweep_tables(self, solver, t_k, reuse, forced_axis):
         """Tabulate the user's callables over this rank's slab and build the dense
         tables on the device.  `reuse`: a SweepTables whose device buffers are
         recycled when the sizes match (time-dependent recursion).
@@ -765,14 +821,29 @@ class Engine(object):
         scan_key = (t_k, id(sys.control_box), repr(sorted(sys.params.items())) if sys.params else "",
                     tuple(float(c) for c in solver.control_steps),
                     tuple(g.tobytes() for g in state_grid), world)
+        host_full = None
         if self._scan_cache is not None and self._scan_cache[0] == scan_key:
             host_full = self._scan_cache[1]
-        else:
+            # the box function may read globals / closure cells that changed since the scan
+            # (the reference calls it afresh in every sweep): re-check three states
+            probe = sorted({0, n_grid // 2, n_grid - 1})
+            now = tb.scan_control_boxes(sys, solver.control_steps,
+                                        [tb.state_tuples_at(state_grid, i, i + 1)[0] for i in probe], t_k)
+            if not (np.array_equal(now.lo.view(np.int64), host_full.lo[probe].view(np.int64))
+                    and np.array_equal(now.hi.view(np.int64), host_full.hi[probe].view(np.int64))
+                    and np.array_equal(now.npts, host_full.npts[probe])):
+                host_full = None
+        if host_full is None:
             part = None
             if mode != "per_state":
                 # one vectorised control_box call, trusted only if sample states agree
                 # bit-for-bit with the reference's per-state calls
                 part = tb.scan_control_boxes_batched(sys, solver.control_steps, state_grid,
+                                                     eq[rank], eq[rank + 1], t_k)
+            if part is None and mode != "per_state":
+                # box functions that read only some of the state variables (the storage
+                # examples): one call per distinct box, checked on sample states
+                part = tb.scan_control_boxes_by_axes(sys, solver.control_steps, state_grid,
                                                      eq[rank], eq[rank + 1], t_k)
             if part is None and world == 1 and self.SCAN_PROCS > 1 and n_grid >= self.SCAN_PARALLEL_MIN_STATES:
                 # box functions that do not vectorise (np.max((a, b)) on scalars, as in the
@@ -817,6 +888,11 @@ class Engine(object):
             raise ValueError("slab_axis must be 'auto', 'rows' or 'columns'")
         if slab_axis == "auto":
             slab_axis = SLAB_AXIS_DEFAULT
+        axis_auto = slab_axis == "auto" or forced_axis is not None
+        if forced_axis is not None:
+            slab_axis = forced_axis
+        elif slab_axis == "auto":
+            slab_axis = "columns" if (col_candidate and n_cols >= 4 * world) else "rows"
         by_columns = world > 1 and slab_axis == "columns"
         # developer experiments (scripts/dev_shard_emulation.py): the tables of ONE column shard
         # [c0, c1) of the grid on a single rank, as a rank of a multi-GPU run would hold them
@@ -880,6 +956,8 @@ class Engine(object):
             if world > 1:
                 column = bool(min(coll.all_gather_object(column)))
             if by_columns and not column:
+                if axis_auto:
+                    raise _ColumnsNotApplicable()
                 raise ValueError("slab_axis='columns' but layout CF does not apply to these tables")
             if col_mode == "on" and not column:
                 raise ValueError("column_hoist='on' but layout CF does not apply: it needs the "
@@ -1104,6 +1182,8 @@ class Engine(object):
                         if world > 1:
                             ok = bool(min(coll.all_gather_object(ok)))
                         if not ok:
+                            if by_columns and axis_auto and col_mode != "on":
+                                raise _ColumnsNotApplicable()
                             if col_mode == "on" or by_columns:
                                 raise ColumnHoistRefused("column_hoist='on' but the (x,w) part of the "
                                                          "next state depends on state axis 0")
@@ -1130,6 +1210,8 @@ class Engine(object):
                     batched = False      # not bit-identical to per-state calls
                 except ColumnHoistRefused as e:
                     raise ValueError(str(e))
+                except _ColumnsNotApplicable:
+                    raise
                 except Exception:
                     if not (batched and mode == "auto"):
                         raise
@@ -1350,13 +1432,13 @@ class Engine(object):
             _cabi.check(rc, "sdp_sweep")
             return
         if events is not None:
-            events[0].record()
+            events[0].record(self.torch_stream)
         rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
                                          self._ptr(J_prev), self._ptr(T.part_val),
                                          self._ptr(T.part_idx), self.stream)
         _cabi.check(rc, "sdp_sweep_partials")
         if events is not None:
-            events[1].record()
+            events[1].record(self.torch_stream)
         self._finalize(T, T.J_out, T.argmin)
 
     def sweep(self, T, J_prev, J_new, rel_ref_index=None, ref_out=None, resid_out=None,
@@ -1372,13 +1454,13 @@ class Engine(object):
             # fused combine + all-gather: K1, then the combine kernel stores the slab
             # into every rank's J_new over NVLink and publishes the epoch
             if events is not None:
-                events[0].record()
+                events[0].record(self.torch_stream)
             rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
                                              self._ptr(J_prev), self._ptr(T.part_val),
                                              self._ptr(T.part_idx), self.stream)
             _cabi.check(rc, "sdp_sweep_partials")
             if events is not None:
-                events[1].record()
+                events[1].record(self.torch_stream)
             if T.col_bounds is not None:
                 rc = self.lib.sdp_sweep_finalize_p2p_cols(
                     ctypes.byref(T.c_tables), self._ptr(T.part_val), self._ptr(T.part_idx), self._ptr(T.argmin),
@@ -1481,7 +1563,7 @@ class Engine(object):
         T.chunk_plan = plan
         return plan
 
-    def sweep_to_host(self, T, J_prev, J_new):
+    def sweep_to_host(self, T, J_prev, J_new, while_waiting=None):
         """One sweep of a single-rank slab, returning (J, pol) as host arrays in
         page-locked memory.  The slab is swept in a few runs on two alternating
         streams (so that the tail of one run is filled by the next); as soon as a run
@@ -1535,6 +1617,8 @@ class Engine(object):
         done = torch.cuda.Event()
         done.record(self._copy)
         main.wait_event(done)
+        if while_waiting is not None:
+            while_waiting()          # host work hidden behind the sweep (the GPU is busy)
         done.synchronize()
         return self.result_array(J_pin), self.result_array(pol_pin)
 
@@ -1587,14 +1671,19 @@ class Engine(object):
             weakref.finalize(a, release)
         return a
 
-    def to_host(self, *tensors):
-        """device tensors -> fresh numpy arrays (through pinned buffers, one sync)"""
+    def to_host(self, *tensors, while_waiting=None):
+        """device tensors -> fresh numpy arrays (through pinned buffers, one sync);
+        `while_waiting()` runs on the host between the enqueue and the synchronisation"""
         torch = _torch()
         if not self._cuda:
+            if while_waiting is not None:
+                while_waiting()
             return [t.numpy().copy() for t in tensors]
         outs = [self.host_result_buffer(tuple(t.shape), t.dtype) for t in tensors]
         for o, t in zip(outs, tensors):
             o.copy_(t, non_blocking=True)
+        if while_waiting is not None:
+            while_waiting()
         torch.cuda.current_stream(self.device).synchronize()
         return [self.result_array(o) for o in outs]
 

@@ -66,7 +66,8 @@ class DPSolver(object):
         self.column_hoist = "auto"    # "auto" | "on" | "off"
         # several ranks, layout CF: cut the grid into slabs of whole rows of axis 0 ("rows") or
         # into whole columns ("columns": the per-column costs then divide by the number of
-        # ranks; not run on GPUs yet, hence not what "auto" picks - SDP_SLAB_AXIS)
+        # ranks); "auto" (SDP_SLAB_AXIS) takes columns wherever layout CF applies and every rank
+        # gets at least 4 of them
         self.slab_axis = "auto"       # "auto" | "rows" | "columns"
         # several ranks: cut the grid into slabs of equal admissible controls ("controls"), or
         # re-cut once by the measured sweep time of every slab ("measured"; "auto" does so
@@ -182,18 +183,53 @@ class DPSolver(object):
             self._engine._scan_cache = None
             self._engine._grid_cache = {}
 
-    def sweep_tables(self, t_k=None, reuse=None):
-        """device tables for the current (sys, grids, control_steps[, t_k])"""
+    def _probe_fingerprint(self, t_k=None):
+        """What the user's control_box / dyn / cost return TODAY on three probe states (first,
+        middle, last of the grid), as bytes.  The reference calls them afresh in every sweep
+        (stodynprog.py:440,674,676), so callables that read module globals or closure cells - its
+        own doc/example_inventory.py cost reads (h, p, c) - see changes made between two calls;
+        cached tables are only reused while this fingerprint is unchanged."""
+        sys = self.sys
+        grids = [np.asarray(g, dtype=float) for g in self.state_grid]
+        dims = [len(g) for g in grids]
+        w_args = tuple(self.perturb_grid)
+        W = len(self.perturb_grid[0]) if len(self.perturb_grid) else 1
+        out = []
+        for idx in ([0] * len(dims), [n // 2 for n in dims], [n - 1 for n in dims]):
+            x_k = tuple(g[i] for g, i in zip(grids, idx))
+            tab = tb.scan_control_boxes(sys, self.control_steps, [x_k], t_k)
+            out += [tab.lo.tobytes(), tab.hi.tobytes(), tab.npts.tobytes()]
+            compact, _, _ = tb._eval_one_state(sys, x_k, tab, 0, w_args, t_k, W)
+            out += [a.tobytes() for a, _, _ in compact]
+        return b"".join(out)
+
+    def _cached_tables(self, t_k):
+        return self._table_cache.get(self._cache_key(t_k)) if self.cache_tables else None
+
+    def _tables_still_valid(self, T, t_k=None):
+        """False when the callables no longer give what the cached tables `T` were built from
+        (same answer on every rank: the probe states are grid states, not shard states)"""
+        fp = getattr(T, "probe_fingerprint", None)
+        return fp is None or fp == self._probe_fingerprint(t_k)
+
+    def sweep_tables(self, t_k=None, reuse=None, validate=True):
+        """device tables for the current (sys, grids, control_steps[, t_k]); cached stationary
+        tables are re-validated against the callables (`_probe_fingerprint`) unless the caller
+        does that itself while the GPU works (`_sweep_host`)"""
         if not self.cache_tables:
             T = self.engine.build_sweep_tables(self, t_k, reuse=reuse)
             self.last_tables = T
             return T
         key = self._cache_key(t_k)
         T = self._table_cache.get(key)
+        if T is not None and validate and not self._tables_still_valid(T, t_k):
+            self.clear_tables()
+            T = None
         if T is None:
             T = self.engine.build_sweep_tables(self, t_k, reuse=reuse)
             if t_k is None:
                 # stationary tables are reused across sweeps / policy iterations
+                T.probe_fingerprint = self._probe_fingerprint(t_k)
                 self._table_cache = {key: T}
         self.last_tables = T
         return T
@@ -209,7 +245,16 @@ class DPSolver(object):
         eng = self.engine
         state_dims = tuple(len(g) for g in self.state_grid)
         nb_control = len(self.sys.control)
-        T = tables if tables is not None else self.sweep_tables(t_k)
+        # cached tables are launched at once and checked against the callables WHILE the GPU
+        # sweeps (the host would only wait); a stale cache costs one wasted sweep, then a rebuild
+        cached = tables is None and self._cached_tables(t_k) is not None
+        T = tables if tables is not None else self.sweep_tables(t_k, validate=False)
+        stale = []
+
+        def check_cache():
+            if cached and not stale and not self._tables_still_valid(T, t_k):
+                stale.append(True)
+
         n_grid = int(np.prod(state_dims))
         J_prev, J_new = eng.J_pair(n_grid)
         eng.begin_call(n_grid)
@@ -223,7 +268,10 @@ class DPSolver(object):
             eng.upload_J(J_next, J_prev)
         if not rel_dp and eng.can_overlap_results(T):
             # large single-rank sweep: results stream to the host while later runs compute
-            J_k, pol_k = eng.sweep_to_host(T, J_prev, J_new)
+            J_k, pol_k = eng.sweep_to_host(T, J_prev, J_new, while_waiting=check_cache)
+            if stale:
+                self.clear_tables()
+                return self._sweep_host(J_next, t_k, rel_dp)
             return J_k.reshape(state_dims), None, pol_k.reshape(state_dims + (nb_control,)), T
         ref_out = None
         ref_flat = None
@@ -233,9 +281,16 @@ class DPSolver(object):
         eng.sweep(T, J_prev, J_new, rel_ref_index=ref_flat, ref_out=ref_out)
         argmin_full = eng.gather_argmin(T)
         if root_only and not is_root:
+            check_cache()
+            if stale:
+                self.clear_tables()
+                return self._sweep_host(J_next, t_k, rel_dp)
             return None, None, None, T           # results travel to rank 0's host only
         pol_dev = eng.policy_values(T, argmin_full)               # K3: indices -> control values
-        outs = eng.to_host(J_new, pol_dev, *([ref_out] if rel_dp else []))
+        outs = eng.to_host(J_new, pol_dev, *([ref_out] if rel_dp else []), while_waiting=check_cache)
+        if stale:
+            self.clear_tables()
+            return self._sweep_host(J_next, t_k, rel_dp)
         J_k = outs[0].reshape(state_dims)
         pol_k = outs[1].reshape(state_dims + (nb_control,))
         J_ref = float(outs[2][0]) if rel_dp else None

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["scan_control_boxes", "scan_control_boxes_batched", "scan_control_boxes_parallel", "state_tuples_at", "control_grid_counts", "control_axis_values", "HostStateTable", "tabulate_states",
+__all__ = ["scan_control_boxes", "scan_control_boxes_batched", "scan_control_boxes_by_axes", "scan_control_boxes_parallel", "state_tuples_at", "control_grid_counts", "control_axis_values", "HostStateTable", "tabulate_states",
            "tabulate_states_batched", "GDependsOnW", "BatchedMismatch", "NotFactorable",
            "probe_factor_mask", "check_factorable"]
 
@@ -205,20 +205,36 @@ def scan_control_boxes_parallel(sys, control_steps, state_grid, begin, end, t_k=
     serially, which also reproduces any exception of the user's control_box in place)."""
     global _SCAN_JOB
     import multiprocessing as mp
+    import os
+    import time
+    import warnings
     n = end - begin
+    try:
+        procs = min(procs, len(os.sched_getaffinity(0)))     # cores this process may use
+    except AttributeError:
+        pass
     if procs < 2 or n < 2 * procs or "fork" not in mp.get_all_start_methods():
         return None
     n_chunks = procs * 4
     cuts = [begin + n * k // n_chunks for k in range(n_chunks + 1)]
     chunks = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
     if timeout is None:
-        timeout = 30.0 + 5e-5 * n          # five times the ~10 us per state seen on the examples
+        # ten times what a timed serial sample predicts for the workers' share
+        k = min(n, 256)
+        t0 = time.perf_counter()
+        try:
+            scan_control_boxes(sys, control_steps, state_tuples_at(state_grid, begin, begin + k), t_k)
+        except Exception:
+            return None      # (the serial scan reproduces the user's exception in place)
+        timeout = 10.0 + 10.0 * (time.perf_counter() - t0) / k * n / procs
     _SCAN_JOB = (sys, control_steps, state_grid, t_k)
     pool = None
     try:
         pool = mp.get_context("fork").Pool(procs)
         parts = pool.map_async(_scan_chunk, chunks).get(timeout=timeout)
-    except Exception:
+    except Exception as e:
+        warnings.warn("parallel control_box scan failed (%s: %s); scanning serially"
+                      % (type(e).__name__, e))
         return None
     finally:
         _SCAN_JOB = None
@@ -229,6 +245,81 @@ def scan_control_boxes_parallel(sys, control_steps, state_grid, begin, end, t_k=
     tab.hi = np.concatenate([p[1] for p in parts], axis=0)
     tab.npts = np.concatenate([p[2] for p in parts], axis=0)
     return tab
+
+
+def scan_control_boxes_by_axes(sys, control_steps, state_grid, begin, end, t_k=None,
+                               verify_min=2048, verify_frac=1.0 / 128, seed=0):
+    """First pass for box functions that read only SOME of the state variables - the rule in the
+    reference's examples: the admissible storage power depends on the stored energy alone
+    (examples/howto storage-AR1.ipynb:214, storage_control.py:67-79), so the 10^6 states of
+    config #5 hold 2 000 distinct boxes - without vectorising the user's function (the examples'
+    `np.max((a, b))` on scalars cannot take arrays).
+
+    1. Hypothesis: from the middle state of the grid, each state axis is moved alone through up
+       to 9 of its values; an axis whose moves never change the box (bit for bit) is taken as
+       ignored.
+    2. `control_box` is called the reference's way (stodynprog.py:440), once per point of the
+       product of the axes that are NOT ignored, the ignored ones held at their middle value.
+    3. The table is broadcast to the states [begin, end) of the C-order grid and CHECKED: at
+       least `verify_min` (and `verify_frac` of the) states, seeded random plus the first and
+       last, are re-evaluated one by one with their own coordinates and must give the same
+       (lo, hi, npts) bit for bit - the trust level of the batched dyn/cost evaluation.
+    Returns a HostStateTable, or None when no axis can be dropped, the saving is below 4x, or
+    the check fails (the caller then scans every state)."""
+    nb_control = len(sys.control)
+    dims = [len(g) for g in state_grid]
+    d = len(dims)
+    n = end - begin
+    if n < 4096 or nb_control == 0 or d < 2:
+        return None
+    grids = [np.asarray(g) for g in state_grid]
+    mid = [m // 2 for m in dims]
+
+    def box_at(idx):
+        x_k = tuple(grids[k][i] for k, i in enumerate(idx))
+        return scan_control_boxes(sys, control_steps, [x_k], t_k)
+
+    def same(a, b):
+        return (np.array_equal(a.lo.view(np.int64), b.lo.view(np.int64))
+                and np.array_equal(a.hi.view(np.int64), b.hi.view(np.int64))
+                and np.array_equal(a.npts, b.npts))
+
+    try:
+        base = box_at(mid)
+        used = []
+        for k in range(d):
+            moves = np.unique(np.linspace(0, dims[k] - 1, min(9, dims[k])).astype(int))
+            if any(not same(base, box_at(mid[:k] + [int(i)] + mid[k + 1:])) for i in moves):
+                used.append(k)
+        n_sub = int(np.prod([dims[k] for k in used])) if used else 1
+        if len(used) == d or n_sub * 4 > n:
+            return None
+        # the boxes over the product of the axes the function reads
+        sub_dims = [dims[k] for k in used]
+        sub_states = []
+        for sub in itertools.product(*[range(m) for m in sub_dims]):
+            idx = list(mid)
+            for k, i in zip(used, sub):
+                idx[k] = i
+            sub_states.append(tuple(grids[k][i] for k, i in enumerate(idx)))
+        sub_tab = scan_control_boxes(sys, control_steps, sub_states, t_k)
+        full_idx = np.unravel_index(np.arange(begin, end), dims)
+        sub_flat = np.ravel_multi_index([full_idx[k] for k in used], sub_dims) if used \
+            else np.zeros(n, dtype=np.int64)
+        tab = HostStateTable(n, nb_control)
+        tab.lo, tab.hi, tab.npts = sub_tab.lo[sub_flat], sub_tab.hi[sub_flat], sub_tab.npts[sub_flat]
+        # check on states evaluated with their own coordinates
+        n_check = min(n, max(verify_min, int(n * verify_frac)))
+        picks = np.random.default_rng(seed).choice(n, size=n_check, replace=False)
+        picks = np.unique(np.concatenate([picks, [0, n - 1]]))
+        states = [tuple(grids[k][full_idx[k][i]] for k in range(d)) for i in picks]
+        ref = scan_control_boxes(sys, control_steps, states, t_k)
+    except Exception:
+        return None          # (the per-state scan reproduces the user's exception in place)
+    ok = (np.array_equal(tab.lo[picks].view(np.int64), ref.lo.view(np.int64))
+          and np.array_equal(tab.hi[picks].view(np.int64), ref.hi.view(np.int64))
+          and np.array_equal(tab.npts[picks], ref.npts))
+    return tab if ok else None
 
 
 def scan_control_boxes_batched(sys, control_steps, state_grid, begin, end, t_k=None, verify=16):
@@ -476,7 +567,7 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
                             max_doubles=16 << 20, align=1, verify=8, grid_cache=None,
                             flat_index=None, valid=None):
     """Second pass, batched mode: one dyn/cost call per chunk of states.
-    `verify` sample states of the first chunk are re-evaluated per state, the
+    `verify` sample states of EVERY chunk are re-evaluated per state, the
     reference's way, and compared bit-for-bit; a mismatch raises
     BatchedMismatch (the caller falls back to the per-state mode).
     By default the states are [begin, end) of the C-order grid; `flat_index` gives
@@ -494,7 +585,6 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
     writer = _ChunkWriter(d, flush_fn, max_doubles, align)
     n = end - begin if flat_index is None else len(flat_index)
     chunk_states = max(align, chunk_states // align * align)
-    checked = False
     for b0 in range(0, n, chunk_states):
         b1 = min(b0 + chunk_states, n)
         S = b1 - b0
@@ -506,9 +596,11 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
                                        w_args, t_k, W, grid_cache)
         if outs[-1].shape[-1] > 1 and not g_per_w:
             raise GDependsOnW()
-        if not checked and verify:
-            _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, min(verify, S))
-            checked = True
+        if verify:
+            # every chunk is another region of the state space, where the branches of a user's
+            # np.where / clipping may differ: each is checked on its own sample states
+            _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, min(verify, S),
+                          None if valid is None else valid[b0:b1])
         recs = np.zeros(S, dtype=_cabi.STATE_DESC_DTYPE)
         recs["npts"] = 1
         recs["npts"][:, :nb_control] = npts
@@ -533,12 +625,14 @@ class BatchedMismatch(Exception):
     a chunk of states at once"""
 
 
-def _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, n_check):
+def _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, n_check, valid=None):
     """bit-for-bit comparison of the chunk evaluation against the reference's
     per-state evaluation on a few sample states, after full broadcast"""
     S = len(cols[0])
     nb_control = len(sys.control)
     picks = np.unique(np.linspace(0, S - 1, n_check).astype(int))
+    if valid is not None:
+        picks = picks[np.asarray(valid)[picks]]      # (padding positions repeat a real state)
     for s in picks:
         x_k = tuple(col[s] for col in cols)
         compact, control_dims, U = _eval_one_state(sys, x_k, host_tab, b0 + s, w_args, t_k, W)

@@ -62,6 +62,44 @@ def check_column_layout(sdp, wl, rank):
     return bool(ok)
 
 
+def check_bench_grid(sdp, wl, rank, n_check=300):
+    """the bench workload itself (config #5, 2000 x 500 states x <= 256 controls x 9 nodes) on all
+    ranks, cut into rows and into columns: value_iteration from a random J and the device-resident
+    loop, `n_check` seeded random states against the oracle port (stodynprog.py:639-691)"""
+    from oracle.ref_port import port_api
+    ora = wl.storage_ar1_large(port_api()).solver
+    dims = ora._state_grid_shape
+    n_grid = int(np.prod(dims))
+    J0 = np.random.default_rng(11).standard_normal(dims)
+    picks = np.random.default_rng(12).choice(n_grid, size=n_check, replace=False)
+    want_J = np.empty(n_check)
+    want_pol = np.empty((n_check, 2))
+    if rank == 0:
+        Ji = ora.interp_on_state(J0)
+        for n, flat in enumerate(picks):
+            idx = np.unravel_index(flat, dims)
+            x_k = tuple(g[i] for g, i in zip(ora.state_grid, idx))
+            want_J[n], want_pol[n] = ora.value_at_state(x_k, Ji)
+    ok = True
+    for axis in ("rows", "columns"):
+        sv = wl.storage_ar1_large(sdp).solver
+        sv.slab_axis = axis
+        J, pol = sv.value_iteration(J0, report_time=False)
+        Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=1)
+        T = sv.last_tables
+        ok &= T.column and (T.col_bounds is not None) == (axis == "columns")
+        if rank == 0:
+            for label, Jx, px in (("value_iteration", J, pol), ("solve_value_iteration", Js, pols)):
+                bad = int(np.any(px.reshape(n_grid, 2)[picks] != want_pol, axis=1).sum())
+                err = float(np.max(np.abs(Jx.reshape(-1)[picks] - want_J) / np.maximum(np.abs(want_J), 1e-300)))
+                ok &= bad == 0 and err <= 1e-10
+                print("[bench grid 2000x500, %s, shards of %s] %d sampled states: policy mismatches %d, "
+                      "J rel err %.2e" % (label, axis, n_check, bad, err), flush=True)
+        del sv, T
+        torch.cuda.empty_cache()
+    return bool(ok)
+
+
 def main():
     os.environ.setdefault("SDP_P2P_TIMEOUT_S", "120")
     rank = int(os.environ["RANK"])
@@ -131,6 +169,8 @@ def main():
         r_expected = np.max(np.abs(G["vi_J2"] - G["vi_J1"]))
         ok &= rel_err(Js, G["vi_J2"]) <= 1e-10 and abs(info["residuals"][-1] - r_expected) <= 1e-9 * r_expected
     ok &= check_column_layout(sdp, wl, rank)
+    if os.environ.get("SDP_CHECK_BENCH_GRID"):
+        ok &= check_bench_grid(sdp, wl, rank)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

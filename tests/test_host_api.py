@@ -437,6 +437,112 @@ def test_parallel_control_box_scan(monkeypatch):
     assert calls and np.array_equal(J_a, J_b) and np.array_equal(pol_a, pol_b)
 
 
+def test_control_box_scan_by_axes():
+    """box functions that ignore some state variables (np.max((a, b)) on scalars: not
+    vectorisable) are scanned once per distinct box and checked on sample states: same table,
+    bit for bit; a box that reads every axis, or one whose dependence hides from the probe but not
+    from the check, gives None (per-state scan)"""
+    from stodynprog_b200 import workloads as wl
+    from fake_lib import FakeLib
+    sv = wl.storage_ar1(sdp, n_E=90, n_P=70, steps=(0.3, 0.1), _test_lib=FakeLib()).solver
+    n = 90 * 70
+    calls = [0]
+    good = sv.sys.control_box
+
+    def counting(E, P_mis):
+        calls[0] += 1
+        return good(E, P_mis)
+    sv.sys._control_box = counting
+    fast = tb.scan_control_boxes_by_axes(sv.sys, sv.control_steps, sv.state_grid, 100, n - 50)
+    n_calls = calls[0]
+    sv.sys._control_box = good
+    serial = tb.scan_control_boxes(sv.sys, sv.control_steps, tb.state_tuples(sv.state_grid, 100, n - 50))
+    assert fast is not None and n_calls < n // 2
+    assert np.array_equal(fast.lo.view(np.int64), serial.lo.view(np.int64))
+    assert np.array_equal(fast.hi.view(np.int64), serial.hi.view(np.int64))
+    assert np.array_equal(fast.npts, serial.npts)
+
+    def both_axes(E, P_mis):
+        return ((-E - 1., P_mis + 10.), (0, 0))
+    sv.sys._control_box = both_axes
+    assert tb.scan_control_boxes_by_axes(sv.sys, sv.control_steps, sv.state_grid, 0, n) is None
+
+    def hidden(E, P_mis):           # depends on P_mis only in a corner the axis probe does not visit
+        lo, hi = good(E, P_mis)[0]
+        return ((lo, hi + (1.0 if (E > 9.9 and P_mis > 3.9) else 0.0)), (0, 0))
+    sv.sys._control_box = hidden
+    assert tb.scan_control_boxes_by_axes(sv.sys, sv.control_steps, sv.state_grid, 0, n) is None
+    sv.sys._control_box = good
+
+
+def test_batched_tabulation_checks_every_chunk():
+    """a cost that is not element-wise over the state axis in ONE region of the state space only
+    must be caught although the first chunk verifies: the batched mode is abandoned"""
+    from stodynprog_b200 import workloads as wl
+    from fake_lib import FakeLib
+    prob = wl.storage_ar1(sdp, n_E=64, n_P=8, steps=(0.5, 0.1), _test_lib=FakeLib())
+    sv = prob.solver
+    good = sv.sys.cost
+
+    def sneaky(E, P_mis, P_sto, P_cur, innov):
+        g = good(E, P_mis, P_sto, P_cur, innov)
+        if np.ndim(E) > 0 and np.max(E) > 9.:       # chunks holding the top of the E range only
+            g = g + 1e-3 * np.mean(E)               # depends on the whole chunk
+        return g
+    sv.sys._cost = sneaky
+    seen = []
+    real = tb.tabulate_states_batched
+
+    def small_chunks(*a, **k):
+        k["chunk_states"] = 128
+        try:
+            return real(*a, **k)
+        except tb.BatchedMismatch:
+            seen.append("mismatch")
+            raise
+    tb.tabulate_states_batched = small_chunks
+    try:
+        T = sv.sweep_tables()
+    finally:
+        tb.tabulate_states_batched = real
+    assert seen and T.tabulate_mode == "per_state"
+
+
+def test_cached_tables_follow_the_callables(port):
+    """The reference calls dyn / cost / control_box afresh in every sweep, so a change of a
+    global or closure variable they read takes effect at once (its doc/example_inventory.py cost
+    reads h, p, c).  Cached tables are re-validated on probe states and rebuilt."""
+    from stodynprog_b200 import workloads as wl
+    from fake_lib import FakeLib
+    price = [1.0]
+
+    def build(api, **kw):
+        prob = wl.inventory(api, **kw)
+        base = prob.sys.cost
+        prob.sys.cost = lambda x, u, w: base(x, u, w) * price[0]
+        return prob.solver
+    sv, ora = build(sdp, _test_lib=FakeLib()), build(port)
+    J0 = np.zeros(10)
+    for p_now in (1.0, 1.0, 2.5, 2.5):
+        price[0] = p_now
+        J, pol = sv.value_iteration(J0, report_time=False)
+        Jo, polo = ora.value_iteration(J0)
+        assert np.array_equal(pol, polo) and np.allclose(J, Jo, rtol=1e-12, atol=0)
+        Js, pols, _ = sv.solve_value_iteration(J_zero=J0, max_iter=1)
+        assert np.array_equal(pols, polo)
+    # the control-box scan is re-checked too
+    cap = [10]
+    sv2, ora2 = wl.inventory(sdp, _test_lib=FakeLib()).solver, wl.inventory(port).solver
+    for s_ in (sv2, ora2):
+        s_.sys._control_box = lambda x: ((0, cap[0]),)
+    sv2.cache_tables = False
+    for c_now in (10, 4):
+        cap[0] = c_now
+        J, pol = sv2.value_iteration(J0 - np.arange(10.), report_time=False)
+        Jo, polo = ora2.value_iteration(J0 - np.arange(10.))
+        assert np.array_equal(pol, polo) and np.allclose(J, Jo, rtol=1e-12, atol=0)
+
+
 def test_no_cpu_fallback(product):
     """without a GPU the product refuses to run; without the library it says so"""
     import torch
