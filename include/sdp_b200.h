@@ -334,6 +334,13 @@ int sdp_sweep_finalize_p2p_cols(const SdpTables* tab, const double* part_val, co
 /* Stream-ordered wait until every rank has published the local epoch (i.e. until
  * the slabs written by the last sdp_sweep_finalize_p2p of all ranks have landed). */
 int sdp_p2p_wait(const SdpPeers* peers, void* stream);
+/* sdp_p2p_wait(wait_for) followed by sdp_sweep_partials(...), with the wait folded into the first
+ * kernel that reads J_prev where the layout has one that can carry it (layout CF: every CTA of
+ * the column-table pre-pass starts with the flag wait) - one launch less per sweep of a
+ * device-resident iteration.  Same results as the two calls. */
+int sdp_sweep_partials_after(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
+                             double* part_val, int32_t* part_idx, const SdpPeers* wait_for,
+                             void* stream);
 /* Stream-ordered barrier over the ranks: epoch += 1, publish, wait. */
 int sdp_p2p_barrier(const SdpPeers* peers, void* stream);
 

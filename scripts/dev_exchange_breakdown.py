@@ -34,11 +34,21 @@ st = eng.torch_stream
 lib = eng.lib
 
 
+FOLD = os.environ.get("FOLD", "0") == "1"     # the wait rides in the next sweep's pre-pass
+pending = [None]
+
+
 def one(J_prev, J_new, ev):
     k_new = px.index_of(J_new)
     ev[0].record(st)
-    _cabi.check(lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables), eng._ptr(J_prev),
-                                       eng._ptr(T.part_val), eng._ptr(T.part_idx), eng.stream), "partials")
+    if pending[0] is not None:
+        _cabi.check(lib.sdp_sweep_partials_after(ctypes.byref(T.grid), ctypes.byref(T.c_tables), eng._ptr(J_prev),
+                                                 eng._ptr(T.part_val), eng._ptr(T.part_idx),
+                                                 ctypes.byref(pending[0]), eng.stream), "partials_after")
+        pending[0] = None
+    else:
+        _cabi.check(lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables), eng._ptr(J_prev),
+                                           eng._ptr(T.part_val), eng._ptr(T.part_idx), eng.stream), "partials")
     ev[1].record(st)
     if T.col_bounds is not None:
         rc = lib.sdp_sweep_finalize_p2p_cols(ctypes.byref(T.c_tables), eng._ptr(T.part_val), eng._ptr(T.part_idx),
@@ -50,7 +60,10 @@ def one(J_prev, J_new, ev):
                                         eng.stream)
     _cabi.check(rc, "finalize_p2p")
     ev[2].record(st)
-    _cabi.check(lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), eng.stream), "wait")
+    if FOLD:
+        pending[0] = px.peers[k_new]
+    else:
+        _cabi.check(lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), eng.stream), "wait")
     ev[3].record(st)
 
 
@@ -63,6 +76,8 @@ torch.cuda.synchronize()
 for k in range(K):
     one(J_prev, J_new, evs[k])
     J_prev, J_new = J_new, J_prev
+if pending[0] is not None:
+    _cabi.check(lib.sdp_p2p_wait(ctypes.byref(pending[0]), eng.stream), "wait")
 torch.cuda.synchronize()
 seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in evs[3:]])
 gap = np.array([evs[k][3].elapsed_time(evs[k + 1][0]) for k in range(3, K - 1)])
@@ -71,8 +86,8 @@ mine = torch.tensor(list(seg.mean(axis=0)) + [gap.mean(), tot], dtype=torch.floa
 allr = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
 dist.all_gather(allr, mine)
 if rank == 0:
-    print("shards of %s, %d ranks, %s; ms per sweep" % ("columns" if T.col_bounds is not None else "rows",
-                                                      dist.get_world_size(), _cabi.last_kernel()))
+    print("shards of %s, %d ranks, %s; wait folded into the pre-pass: %s; ms per sweep" % ("columns" if T.col_bounds is not None else "rows",
+                                                      dist.get_world_size(), _cabi.last_kernel(), FOLD))
     print("rank  kernel  combine+stores+epoch  wait  gap   step")
     for r, x in enumerate(allr):
         print("%4d  %.4f  %.4f                %.4f %.4f %.4f" % ((r,) + tuple(float(v) for v in x)))

@@ -1774,18 +1774,67 @@ static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, cons
 // shared memory), so a CTA meets few column changes.  Warps take the items of the
 // current column round-robin.  Partial minima have the layout of BF.
 // ---------------------------------------------------------------------------
+// Peer-memory exchange state (see "Multi-GPU" below); declared here because the pre-pass of
+// layout CF can start with the flag wait of the previous sweep's exchange.
+struct PeersDev {
+    int world, rank;
+    double* J[SDP_MAX_PEERS];
+    unsigned long long* flags[SDP_MAX_PEERS];
+    unsigned long long* epoch;
+    unsigned int* done;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded flag wait: a peer that died (or a call sequence that differs between the
+// ranks) must surface as a CUDA error on this rank, not as a hung GPU.
+// (default 600 s, like a collective watchdog: the ranks of an SPMD script may reach a
+// call minutes apart; `sdp_set_option("p2p_timeout_s", s)` / SDP_P2P_TIMEOUT_S change it)
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long e,
+                                          unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < e) {
+        __nanosleep(20);
+        if (global_ns() - t0 > timeout_ns) __trap();
+    }
+}
+
 // Pre-pass: the inner-interpolation tables of ALL columns, R[c][r][w] at
 // col_table[c*pitch + r*P + w].  A CTA owns a tile of 32 columns x SDP_CT_ROWS rows: it
 // computes with lanes along the columns - the w-parts of neighbouring columns point at
 // neighbouring cells, so the gathers of a warp are a few lines instead of 32 - into a
 // shared-memory tile, then writes each column's run of rows contiguously.
+// set by sdp_sweep_partials_after for the duration of the call: the exchange whose flag wait
+// the first kernel that reads J_prev must perform (consumed by launch_column_table)
+static thread_local const PeersDev* g_wait_peers = nullptr;
+
 #define SDP_CT_ROWS 16
-template <int D>
+// `WAIT`: every CTA first waits (lanes 0..world-1, ld.acquire.sys on the local flags) until all
+// ranks have published the current epoch, i.e. until the J slabs of the previous sweep have
+// landed - the stream-ordered sdp_p2p_wait folded into the first kernel that reads J.
+template <int D, bool WAIT>
 __global__ void __launch_bounds__(256)
-k_column_table(GridT<double> G, SdpTables T, const double* __restrict__ Jprev, int64_t pitch) {
+k_column_table(GridT<double> G, SdpTables T, const double* __restrict__ Jprev, int64_t pitch,
+               PeersDev PW, unsigned long long timeout_ns) {
     constexpr int NW = D - 1;
     constexpr int TR = SDP_CT_ROWS;
     extern __shared__ __align__(16) unsigned char tsm[];
+    if (WAIT) {
+        if (threadIdx.x < PW.world) wait_flag(PW.flags[PW.rank] + threadIdx.x, *PW.epoch, timeout_ns);
+        __syncthreads();
+    }
     const int W = T.W;
     const int P = W | 1;
     const int CP = TR * P + 1;                    // odd tile pitch per column: conflict-free both ways
@@ -1829,7 +1878,18 @@ static int launch_column_table(const GridT<double>& G, const SdpTables& T, const
     const int P = T.W | 1;
     const size_t tshm = (size_t)32 * (SDP_CT_ROWS * P + 1) * 8 + (size_t)NW * 32 * T.W * 8 + (size_t)32 * T.W * 4;
     dim3 grid((unsigned)((T.n_cols + 31) / 32), (unsigned)((G.order[0] + SDP_CT_ROWS - 1) / SDP_CT_ROWS));
-    k_column_table<D><<<grid, 256, tshm, st>>>(G, T, Jprev, SDP_COLUMN_PITCH(G.order[0], T.W));
+    const int64_t pitch = SDP_COLUMN_PITCH(G.order[0], T.W);
+    if (g_wait_peers) {
+        // the flag wait of the previous exchange rides in this kernel (sdp_sweep_partials_after)
+        const PeersDev P2 = *g_wait_peers;
+        g_wait_peers = nullptr;
+        k_column_table<D, true><<<grid, 256, tshm, st>>>(
+            G, T, Jprev, pitch, P2, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL);
+    } else {
+        PeersDev none;
+        memset(&none, 0, sizeof(none));
+        k_column_table<D, false><<<grid, 256, tshm, st>>>(G, T, Jprev, pitch, none, 0ULL);
+    }
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
@@ -2260,6 +2320,10 @@ extern "C" int sdp_column_table(const SdpGrid* grid, const SdpTables* tab, const
     return grid->d == 2 ? launch_column_table<2>(G, T, J_prev, st) : launch_column_table<3>(G, T, J_prev, st);
 }
 
+// (layout CF: the transposing combine kernel lives with the peer-memory code below)
+static void launch_combine_column_local(const SdpTables& T, const double* part_val, const int32_t* part_idx,
+                                        double* J_out, int32_t* argmin_out, cudaStream_t st);
+
 extern "C" int sdp_sweep_finalize(const SdpTables* tab, const double* part_val,
                                   const int32_t* part_idx, double* J_out, int32_t* argmin_out,
                                   void* stream) {
@@ -2273,9 +2337,11 @@ extern "C" int sdp_sweep_finalize(const SdpTables* tab, const double* part_val,
         return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned blocks = (unsigned)((T.n_states + 255) / 256);
-    if (is_tiled(T))
+    if (is_column(T))
+        launch_combine_column_local(T, part_val, part_idx, J_out, argmin_out, st);
+    else if (is_tiled(T))
         k_sweep_finalize_tiled<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out,
-                                                       is_column(T) ? T.n_cols : 0, T.tiles_per_col);
+                                                       0, T.tiles_per_col);
     else
         k_sweep_finalize<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, J_out, argmin_out);
     SDP_LAUNCH_CHECK();
@@ -2293,41 +2359,6 @@ extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double
 // ---------------------------------------------------------------------------
 // Multi-GPU: fused combine + all-gather over peer memory, flag barrier
 // ---------------------------------------------------------------------------
-struct PeersDev {
-    int world, rank;
-    double* J[SDP_MAX_PEERS];
-    unsigned long long* flags[SDP_MAX_PEERS];
-    unsigned long long* epoch;
-    unsigned int* done;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// Bounded flag wait: a peer that died (or a call sequence that differs between the
-// ranks) must surface as a CUDA error on this rank, not as a hung GPU.
-// (default 600 s, like a collective watchdog: the ranks of an SPMD script may reach a
-// call minutes apart; `sdp_set_option("p2p_timeout_s", s)` / SDP_P2P_TIMEOUT_S change it)
-__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long e,
-                                          unsigned long long timeout_ns) {
-    const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(p) < e) {
-        __nanosleep(20);
-        if (global_ns() - t0 > timeout_ns) __trap();
-    }
-}
-
 // Publish: every CTA fences its peer stores (system scope), the last CTA to arrive
 // bumps the rank's epoch and lanes 0..world-1 release it into the flag arrays of all
 // ranks IN PARALLEL (one st.release.sys each: a loop in one thread would pay one
@@ -2380,36 +2411,6 @@ k_sweep_finalize_p2p(int64_t n_states, const int64_t* __restrict__ item_begin,
     publish_epoch(P);
 }
 
-// the same combine for a shard of whole COLUMNS of the grid (layout CF, one band): local
-// state i = row*n_cols + lc is grid state row*glob_cols + col_begin + lc, so a warp stores
-// runs of consecutive values of one row into every rank's buffer
-__global__ void __launch_bounds__(256)
-k_sweep_finalize_p2p_cols(int64_t n_states, const int64_t* __restrict__ item_begin,
-                          const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
-                          int32_t* __restrict__ argmin_out, PeersDev P, int n_cols, int tiles_per_col,
-                          int64_t glob_cols, int64_t col_begin) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_states) {
-        int64_t unit;
-        int lane;
-        tile_of_state(i, n_cols, tiles_per_col, unit, lane);
-        double bv = CUDART_INF;
-        int bi = INT_MAX;
-        for (int64_t k = item_begin[unit]; k < item_begin[unit + 1]; ++k) {
-            const double v = part_val[k * 32 + lane];
-            const int ix = part_idx[k * 32 + lane];
-            if (better(v, ix, bv, bi)) { bv = v; bi = ix; }
-        }
-        argmin_out[i] = bi;
-        const int64_t row = i / n_cols;
-        const int64_t g = row * glob_cols + col_begin + (i - row * n_cols);
-#pragma unroll
-        for (int r = 0; r < SDP_MAX_PEERS; ++r)
-            if (r < P.world) P.J[r][g] = bv;
-    }
-    publish_epoch(P);
-}
-
 __global__ void k_p2p_wait(PeersDev P, unsigned long long timeout_ns) {
     const int t = threadIdx.x;
     if (t < P.world) {
@@ -2431,6 +2432,79 @@ __global__ void k_p2p_barrier(PeersDev P, unsigned long long timeout_ns) {
         st_release_sys(P.flags[t] + P.rank, e_sh);
         wait_flag(P.flags[P.rank] + t, e_sh, timeout_ns);
     }
+}
+
+// Layout CF combine, both sides coalesced.  The partial minima of a tile are 32 lanes = 32
+// consecutive ROWS of one column, the value function is C-order (columns fastest): a thread
+// per state in grid order (k_sweep_finalize_tiled) reads every partial from another cache
+// line - measured 35 us per sweep for the 125 000 states of one rank of eight, five times the
+// peer stores themselves.  Here a CTA owns 32 rows x 32 columns of a band: warp w combines
+// the items of column c0 + w (lanes = rows: one contiguous 256-byte read per item), the block
+// transposes through shared memory, then warp w stores row r0 + w (lanes = columns: 256
+// contiguous bytes into the local buffer, or into every rank's buffer over NVLink).
+// State (row, col) of the band goes to J[j_offset + row * j_pitch + col] and to
+// argmin_out[row * n_cols + col].  P.world == 0: local store into J_out, no epoch.
+__global__ void __launch_bounds__(1024)
+k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
+                 const int64_t* __restrict__ item_begin, const double* __restrict__ part_val,
+                 const int32_t* __restrict__ part_idx, double* __restrict__ J_out,
+                 int32_t* __restrict__ argmin_out, PeersDev P, int64_t j_offset, int64_t j_pitch) {
+    __shared__ double v_sh[32][33];
+    __shared__ int i_sh[32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ty = blockIdx.x / col_blocks;                 // tile (32 rows) of the band
+    const int c0 = (blockIdx.x - ty * col_blocks) * 32;
+    if (n_rows > 0) {
+        const int c = c0 + warp;
+        if (c < n_cols) {
+            const int64_t tile = (int64_t)c * tiles_per_col + ty;
+            double bv = CUDART_INF;
+            int bi = INT_MAX;
+            for (int64_t k = item_begin[tile]; k < item_begin[tile + 1]; ++k) {
+                const double v = part_val[k * 32 + lane];
+                const int ix = part_idx[k * 32 + lane];
+                if (better(v, ix, bv, bi)) { bv = v; bi = ix; }
+            }
+            v_sh[lane][warp] = bv;
+            i_sh[lane][warp] = bi;
+        }
+    }
+    __syncthreads();
+    if (n_rows > 0) {
+        const int r = ty * 32 + warp, c = c0 + lane;
+        if (r < n_rows && c < n_cols) {
+            const double bv = v_sh[warp][lane];
+            argmin_out[(int64_t)r * n_cols + c] = i_sh[warp][lane];
+            const int64_t g = j_offset + (int64_t)r * j_pitch + c;
+            if (P.world == 0) {
+                J_out[g] = bv;
+            } else {
+#pragma unroll
+                for (int q = 0; q < SDP_MAX_PEERS; ++q)
+                    if (q < P.world) P.J[q][g] = bv;
+            }
+        }
+    }
+    if (P.world > 0) publish_epoch(P);
+}
+
+// launch of the above for one band of layout CF
+static void launch_combine_column(const SdpTables& T, const double* part_val, const int32_t* part_idx,
+                                  double* J_out, int32_t* argmin_out, const PeersDev& P,
+                                  int64_t j_offset, int64_t j_pitch, cudaStream_t st) {
+    const int n_rows = T.n_cols > 0 ? (int)(T.n_states / T.n_cols) : 0;
+    const int col_blocks = T.n_cols > 0 ? (T.n_cols + 31) / 32 : 1;
+    unsigned blocks = (unsigned)col_blocks * (unsigned)((n_rows + 31) / 32);
+    if (blocks == 0) blocks = 1;       // (an empty shard still publishes its epoch)
+    k_combine_column<<<blocks, 1024, 0, st>>>(n_rows, T.n_cols, T.tiles_per_col, col_blocks, T.item_begin,
+                                              part_val, part_idx, J_out, argmin_out, P, j_offset, j_pitch);
+}
+
+static void launch_combine_column_local(const SdpTables& T, const double* part_val, const int32_t* part_idx,
+                                        double* J_out, int32_t* argmin_out, cudaStream_t st) {
+    PeersDev none;
+    memset(&none, 0, sizeof(none));
+    launch_combine_column(T, part_val, part_idx, J_out, argmin_out, none, 0, T.n_cols, st);
 }
 
 static int make_peers(const SdpPeers* p, PeersDev* out, const char* who) {
@@ -2469,9 +2543,11 @@ extern "C" int sdp_sweep_finalize_p2p(const SdpTables* tab, const double* part_v
     // at least one CTA even for an empty slab: the epoch must advance on every rank
     unsigned blocks = (unsigned)((T.n_states + 255) / 256);
     if (blocks == 0) blocks = 1;
-    if (is_tiled(T))
+    if (is_column(T) && T.n_states > 0)
+        launch_combine_column(T, part_val, part_idx, nullptr, argmin_out, P, state_begin, T.n_cols, st);
+    else if (is_tiled(T))
         k_sweep_finalize_p2p<true><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin,
-                                                           is_column(T) ? T.n_cols : 0, T.tiles_per_col);
+                                                           0, T.tiles_per_col);
     else
         k_sweep_finalize_p2p<false><<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P, state_begin, 0, 0);
     SDP_LAUNCH_CHECK();
@@ -2497,10 +2573,8 @@ extern "C" int sdp_sweep_finalize_p2p_cols(const SdpTables* tab, const double* p
         (T.n_states > 0 && (!part_val || !part_idx || !argmin_out)))
         return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_p2p_cols: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned blocks = (unsigned)((T.n_states + 255) / 256);
-    if (blocks == 0) blocks = 1;       // the epoch must advance on every rank
-    k_sweep_finalize_p2p_cols<<<blocks, 256, 0, st>>>(T.n_states, T.item_begin, part_val, part_idx, argmin_out, P,
-                                                      T.n_cols, T.tiles_per_col, glob_cols, col_begin);
+    // (an empty shard still launches one CTA: the epoch must advance on every rank)
+    launch_combine_column(T, part_val, part_idx, nullptr, argmin_out, P, col_begin, glob_cols, st);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
 }
@@ -2512,6 +2586,29 @@ extern "C" int sdp_p2p_wait(const SdpPeers* peers, void* stream) {
     k_p2p_wait<<<1, 32, 0, (cudaStream_t)stream>>>(P, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL);
     SDP_LAUNCH_CHECK();
     return SDP_OK;
+}
+
+extern "C" int sdp_sweep_partials_after(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
+                                        double* part_val, int32_t* part_idx, const SdpPeers* wait_for,
+                                        void* stream) {
+    PeersDev P;
+    int rc = make_peers(wait_for, &P, "sdp_sweep_partials_after");
+    if (rc) return rc;
+    const bool fold = tab && tab->layout == SDP_LAYOUT_COLUMN_FACTORED && tuning().col_prepass &&
+                      !tab->col_table_ready && tab->n_states > 0 && tab->n_items > 0;
+    if (!fold) {
+        // no kernel of this layout can carry the wait: a separate launch, as sdp_p2p_wait
+        k_p2p_wait<<<1, 32, 0, (cudaStream_t)stream>>>(P, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL);
+        SDP_LAUNCH_CHECK();
+        return sdp_sweep_partials(grid, tab, J_prev, part_val, part_idx, stream);
+    }
+    g_wait_peers = &P;
+    rc = sdp_sweep_partials(grid, tab, J_prev, part_val, part_idx, stream);
+    if (g_wait_peers) {           // an argument check failed before the pre-pass was launched
+        g_wait_peers = nullptr;
+        if (!rc) rc = fail(SDP_EINVAL, "%s", "sdp_sweep_partials_after: the wait was not enqueued");
+    }
+    return rc;
 }
 
 extern "C" int sdp_p2p_barrier(const SdpPeers* peers, void* stream) {

@@ -667,6 +667,7 @@ class Engine(object):
 
     def begin_call(self, n_grid):
         """separate two public calls that reuse the symmetric J buffers"""
+        self.flush_exchange()
         px = self._peer.get(n_grid)
         if px is not None:
             px.barrier()
@@ -677,6 +678,7 @@ class Engine(object):
         Collective: every rank calls it."""
         if self.coll.world == 1:
             return
+        self.flush_exchange()
         px = self._peer.get(J.numel())
         k = px.index_of(J) if px is not None else None
         if k is None:
@@ -1441,24 +1443,52 @@ class Engine(object):
             events[1].record(self.torch_stream)
         self._finalize(T, T.J_out, T.argmin)
 
+    # Device-resident iterations (solve_value_iteration, the bench loop) may leave the flag wait
+    # of a sweep's exchange to the NEXT sweep, whose first kernel then starts with it
+    # (sdp_sweep_partials_after): one launch less per sweep.  Every other consumer of J calls
+    # flush_exchange() first.  SDP_FOLD_WAIT=0 keeps the separate sdp_p2p_wait launch.
+    FOLD_WAIT = os.environ.get("SDP_FOLD_WAIT", "1") != "0"
+    _pending_wait = None
+
+    def flush_exchange(self):
+        """enqueue the flag wait a sweep(..., defer_wait=True) left pending"""
+        pend, self._pending_wait = self._pending_wait, None
+        if pend is not None:
+            rc = self.lib.sdp_p2p_wait(ctypes.byref(pend), self.stream)
+            _cabi.check(rc, "sdp_p2p_wait")
+
     def sweep(self, T, J_prev, J_new, rel_ref_index=None, ref_out=None, resid_out=None,
-              events=None):
+              events=None, defer_wait=False):
         """One full Bellman sweep: K1 on the slab, all-gather of the J slab into
         J_new (device fp64 [n_grid]), optional relative-DP shift and optional
-        sup-norm residual max|J_new - J_prev| (all-reduced)."""
+        sup-norm residual max|J_new - J_prev| (all-reduced).
+        `defer_wait`: the caller's next use of J_new is another sweep (or it calls
+        flush_exchange() itself): the arrival of the peers' slabs is then awaited by that
+        sweep's first kernel."""
         n = T.n_states
         sb = T.state_begin
         px = self._peer.get(J_new.numel()) if self.coll.world > 1 else None
         k_new = px.index_of(J_new) if px is not None else None
+        pend, self._pending_wait = self._pending_wait, None
+        if k_new is None and pend is not None:
+            self._pending_wait = pend
+            self.flush_exchange()
+            pend = None
         if k_new is not None:
             # fused combine + all-gather: K1, then the combine kernel stores the slab
             # into every rank's J_new over NVLink and publishes the epoch
             if events is not None:
                 events[0].record(self.torch_stream)
-            rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
-                                             self._ptr(J_prev), self._ptr(T.part_val),
-                                             self._ptr(T.part_idx), self.stream)
-            _cabi.check(rc, "sdp_sweep_partials")
+            if pend is not None:
+                rc = self.lib.sdp_sweep_partials_after(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
+                                                       self._ptr(J_prev), self._ptr(T.part_val),
+                                                       self._ptr(T.part_idx), ctypes.byref(pend), self.stream)
+                _cabi.check(rc, "sdp_sweep_partials_after")
+            else:
+                rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(T.c_tables),
+                                                 self._ptr(J_prev), self._ptr(T.part_val),
+                                                 self._ptr(T.part_idx), self.stream)
+                _cabi.check(rc, "sdp_sweep_partials")
             if events is not None:
                 events[1].record(self.torch_stream)
             if T.col_bounds is not None:
@@ -1471,8 +1501,11 @@ class Engine(object):
                                                      self._ptr(T.part_idx), self._ptr(T.argmin),
                                                      ctypes.byref(px.peers[k_new]), sb, self.stream)
                 _cabi.check(rc, "sdp_sweep_finalize_p2p")
-            rc = self.lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), self.stream)
-            _cabi.check(rc, "sdp_p2p_wait")
+            if defer_wait and self.FOLD_WAIT and rel_ref_index is None and resid_out is None:
+                self._pending_wait = px.peers[k_new]
+            else:
+                rc = self.lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), self.stream)
+                _cabi.check(rc, "sdp_p2p_wait")
         else:
             self.sweep_local(T, J_prev, events)
             if self.coll.world == 1:
@@ -1675,6 +1708,7 @@ class Engine(object):
         """device tensors -> fresh numpy arrays (through pinned buffers, one sync);
         `while_waiting()` runs on the host between the enqueue and the synchronisation"""
         torch = _torch()
+        self.flush_exchange()
         if not self._cuda:
             if while_waiting is not None:
                 while_waiting()
@@ -1777,6 +1811,7 @@ class Engine(object):
         """n_iter fixed-policy backups, ping-pong between J_a and J_b (device fp64
         [n_grid]).  Returns the tensor holding the final value function."""
         n_grid = J_a.numel()
+        self.flush_exchange()
         if self.coll.world == 1:
             rc = self.lib.sdp_policy_eval(ctypes.byref(P.grid), P.W, P.g_per_w, self._ptr(P.p),
                                           self._ptr(P.cell), self._ptr(P.lam), P.lam_plane,

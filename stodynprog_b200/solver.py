@@ -480,8 +480,10 @@ class DPSolver(object):
         history = []
         n_done = 0
         for k in range(max_iter):
+            # (between two sweeps the arrival of the peers' slabs is awaited by the next sweep's
+            # first kernel; relative DP and the residual read J right away and wait themselves)
             eng.sweep(T, J_prev, J_new, rel_ref_index=ref_flat, ref_out=ref_out,
-                      resid_out=resid if tol is not None else None)
+                      resid_out=resid if tol is not None else None, defer_wait=k + 1 < max_iter)
             J_prev, J_new = J_new, J_prev
             n_done += 1
             if tol is not None and (k + 1) % check_every == 0:
@@ -489,6 +491,7 @@ class DPSolver(object):
                 history.append(r)
                 if r <= tol:
                     break
+        eng.flush_exchange()
         argmin_full = eng.gather_argmin(T)
         info = {'n_sweeps': n_done, 'residuals': history,
                 'J_ref': float(ref_out.cpu().numpy()[0]) if rel_dp else None}

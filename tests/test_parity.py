@@ -1146,6 +1146,82 @@ def test_large_grid_sampled_against_port(cuda_api, port):
 
 
 @gpu
+def test_device_argument_is_honoured(product, port):
+    """DPSolver(sys, device='cuda:1') while device 0 is current: buffers AND launches go to
+    GPU 1 (the C ABI launches on the current device, so the engine makes its device current
+    around every entry point); the caller's current device is left alone"""
+    import torch
+    from stodynprog_b200 import workloads as wl
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    kw = dict(n_E=9, n_P=11, steps=(0.01, 0.1))
+    sv = wl.storage_ar1(product, device="cuda:1", **kw).solver
+    ora = wl.storage_ar1(port, **kw).solver
+    J = np.random.default_rng(0).standard_normal((9, 11))
+    for _ in range(2):
+        Jg, polg = sv.value_iteration(J, report_time=False)
+        Jo, polo = ora.value_iteration(J)
+        assert policy_mismatch_report(polg, polo)[0] == 0 and rel_err(Jg, Jo) <= J_RTOL
+        J = Jo
+    assert sv.last_tables.cell.device.index == 1 and torch.cuda.current_device() == 0
+    pol0 = wl.storage_ar1(product, **kw).initial_policy()
+    assert rel_err(sv.eval_policy(pol0, 5, report_time=False), ora.eval_policy(pol0, 5)) <= J_RTOL
+
+
+@gpu
+def test_config5_full_size_against_port(cuda_api, port):
+    """BASELINE configs[4] at FULL size - 2000 x 500 states x 129..256 controls x 9 nodes,
+    1 848 240 000 backups per sweep - through the default tables (layout CF, three row bands):
+    `value_iteration` (results streamed band by band, Engine.sweep_to_host) and the
+    device-resident loop (Engine.sweep), 1 000 seeded random states against the oracle port
+    (stodynprog.py:639-691): policies exact, J within 1e-10."""
+    from stodynprog_b200 import workloads as wl
+    prob = wl.storage_ar1_large(cuda_api)
+    ora = wl.storage_ar1_large(port).solver
+    sv = prob.solver
+    dims = sv._state_grid_shape
+    assert dims == (2000, 500)
+    J0 = np.random.default_rng(3).standard_normal(dims)
+    J, pol = sv.value_iteration(J0, report_time=False)
+    T = sv.last_tables
+    assert T.layout_name == "column_factored" and len(T.bands["tiles"]) == 3
+    assert T.n_backups_total == 1848240000
+    Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=1)
+    assert np.array_equal(J.view(np.int64), Js.view(np.int64)) and np.array_equal(pol, pols)
+    Ji = ora.interp_on_state(J0)
+    n_bad, worst = 0, 0.0
+    for flat in np.random.default_rng(4).choice(J0.size, size=1000, replace=False):
+        idx = np.unravel_index(flat, dims)
+        x_k = tuple(g[i] for g, i in zip(ora.state_grid, idx))
+        Jo, uo = ora.value_at_state(x_k, Ji)
+        n_bad += list(pol[idx]) != list(uo)
+        worst = max(worst, abs(J[idx] - Jo) / max(abs(Jo), 1e-300))
+    assert n_bad == 0 and worst <= J_RTOL, (n_bad, worst)
+
+
+@gpu
+@pytest.mark.parametrize("n_w", [3, 4, 5, 9])
+def test_column_layout_against_port_by_W(cuda_api, port, n_w):
+    """layout CF against the oracle port on every state, for the node counts that take the
+    3-, 5- and 9-slot instantiations of the column kernel exactly (FULL) and partly (W = 4:
+    slot masking)"""
+    from stodynprog_b200 import workloads as wl
+    kw = dict(n_E=70, n_P=6, n_w=n_w, steps=(0.3, 0.1))
+    sv = wl.storage_ar1(cuda_api, **kw).solver
+    sv.table_layout, sv.column_hoist = "state_minor", "on"
+    ora = wl.storage_ar1(port, **kw).solver
+    J = np.random.default_rng(n_w).standard_normal((70, 6))
+    for sweep in range(2):
+        Jg, polg = sv.value_iteration(J, report_time=False)
+        assert sv.last_tables.layout_name == "column_factored"
+        Jo, polo = ora.value_iteration(J)
+        assert policy_mismatch_report(polg, polo)[0] == 0
+        assert rel_err(Jg, Jo) <= J_RTOL
+        J = Jo
+
+
+@gpu
 def test_layout_B_kernel_variants_are_bit_identical(product):
     """straight LDG, TMA-fed ring (several ring shapes) and software-pipelined
     kernels of the state-minor layout, and both lane widths of layout A, must
