@@ -602,6 +602,72 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_pv(args):
+    """--workload pv: BASELINE configs[1], the time-dependent deterministic storage problem
+    (examples/01 .../pv_storage_control.py: 50 states x 1 001..2 001 controls, T = 240 instants,
+    17 894 880 backups per recursion).  A step = one whole bellman_recursion(T, J_fin).
+      value  backups/s of the recursion proper: tables of all instants resident, the T sweeps
+             enqueued back to back, one copy of (J, pol) to the host (Engine.recursion_fast)
+      e2e    backups/s of the public call DPSolver.bellman_recursion(T, J_fin) -> (J, pol),
+             INCLUDING the host tabulation of the user's callables for all instants
+      cpu_baseline  the same recursion through the oracle port / the stock reference, 1 core"""
+    import contextlib
+    import io
+    import torch
+    import stodynprog_b200 as sdp
+    from stodynprog_b200 import workloads as wl, _cabi
+    from stodynprog_b200 import build as product_build
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(0)
+    product_build.build()
+    prob = wl.pv_storage(sdp)
+    sv = prob.solver
+    name = "examples/01 deterministic PV storage: 50 states x 1001..2001 controls x T=240 (BASELINE configs[1])"
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    for _ in range(max(args.warmup, 1)):
+        with quiet:
+            J, pol = sv.bellman_recursion(prob.horizon, prob.J_fin)
+    backups = sv.last_tables.n_backups_total * prob.horizon
+    launches0 = _cabi.launch_count()
+    walls, sweeps, tabs = [], [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        with quiet:
+            J, pol = sv.bellman_recursion(prob.horizon, prob.J_fin)
+        walls.append(time.perf_counter() - t0)
+        info = sv.last_recursion or {}
+        sweeps.append(info.get("sweeps_s", float("nan")))
+        tabs.append(info.get("tabulate_s", float("nan")) + info.get("upload_build_s", float("nan")))
+    launches = _cabi.launch_count() - launches0
+    from oracle import build as ob
+    ob.build()
+    from oracle.ref_port import port_api
+    ora = wl.pv_storage(port_api())
+    t0 = time.perf_counter()
+    Jo, polo = ora.solver.bellman_recursion(ora.horizon, ora.J_fin)
+    t_cpu = time.perf_counter() - t0
+    bad = int(np.any(pol != polo, axis=-1).sum())
+    err = float(np.max(np.abs(J - Jo) / np.maximum(np.abs(Jo), 1e-300)))
+    line = {
+        "metric": METRIC, "value": backups / float(np.mean(sweeps)), "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(sweeps)),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "states": 50, "instants": int(prob.horizon), "backups_per_recursion": backups},
+        "e2e": {"value": backups / float(np.mean(walls)), "unit": UNIT, "ms_per_step": 1e3 * float(np.mean(walls)),
+                "h2d_bytes_per_step": int(8 * (sv.last_tables.g.numel() * prob.horizon + 50)),
+                "d2h_bytes_per_step": int(8 * 2 * 50 * prob.horizon),
+                "api": "DPSolver.bellman_recursion(T, J_fin) -> (J, pol), user callables tabulated inside",
+                "tabulate_upload_ms": 1e3 * float(np.mean(tabs)), "sweeps_and_copy_ms": 1e3 * float(np.mean(sweeps))},
+        "gpu_launches": int(launches), "recursion_path": "fast" if sv.last_recursion else "per_instant",
+        "verified": {"states": int(Jo.size), "policy_mismatch": bad, "J_rel": err, "ok": bool(bad == 0 and err <= 1e-10),
+                     "checker": "oracle/ref_port.py, the whole recursion"},
+        "cpu_baseline": {"value": backups / t_cpu, "unit": UNIT, "cores": 1, "kind": "port", "seconds": t_cpu,
+                         "sample": "the whole T=240 recursion through oracle/ref_port.py"},
+    }
+    print(json.dumps(line))
+
+
 def measure_config3(sdp, peak, peak_src, sm_count, sm_mhz, steps=50, warmup=5):
     """BASELINE configs[2] (the 41x61 storage-AR1 grid of the notebook, 142 762 509
     backups per sweep): the grid the north star's 60 % roofline target is quoted on.
@@ -636,7 +702,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="large", choices=["large", "ar1"])
+    ap.add_argument("--workload", default="large", choices=["large", "ar1", "pv"])
     ap.add_argument("--n-E", dest="n_E", type=int, default=2000)
     ap.add_argument("--n-P", dest="n_P", type=int, default=500)
     ap.add_argument("--layout", default="auto", choices=["auto", "control_minor", "state_minor"])
@@ -658,7 +724,9 @@ def main():
     if args.cpu_sample is None:
         # ~200 us per state for the 2000x500 grid (<=256 controls); ~1.4 ms for the 41x61 grid
         args.cpu_sample = (60000 if args.impl == "ours" else 8000) if args.workload == "large" else 2501
-    if args.impl == "reference":
+    if args.workload == "pv" and args.impl == "ours":
+        run_pv(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

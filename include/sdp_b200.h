@@ -407,6 +407,18 @@ int sdp_interp(const SdpGrid* grid, int64_t n_v, const double* values, int64_t n
 int sdp_interp_f32(const SdpGrid* grid, int64_t n_v, const float* values, int64_t n_s,
                    const float* s, float* out, void* stream);
 
+/* K2 for a handful of points, on the HOST: values, s and out are host pointers, nothing touches
+ * the GPU.  Same operations in the same order as sdp_interp / sdp_interp_f32 (bit-identical
+ * results).  For the one-point-at-a-time calls of the reference's simulation loops
+ * (examples/20 Searev storage control/storage_control.py:217,246 evaluate
+ * `interp_on_state(pol)(x)` per time step), where a launch plus two PCIe crossings per point
+ * would make the drop-in slower than multilinear_cython.pyx:17-49 itself.  Not a fallback: the
+ * Python front-end uses it below a point-count threshold only, and the library is still required. */
+int sdp_interp_host(const SdpGrid* grid, int64_t n_v, const double* values, int64_t n_s,
+                    const double* s, double* out);
+int sdp_interp_host_f32(const SdpGrid* grid, int64_t n_v, const float* values, int64_t n_s,
+                        const float* s, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,14 +121,35 @@ class PortSolver(object):
             dims.append(npts)
         return grids, tuple(dims)
 
+    def _perturb_product(self):
+        """Several perturbations - a TODO of the reference (stodynprog.py:614,666,679-683,728), so
+        there is no reference behaviour to restate; the convention defined here (and documented
+        in DESIGN.md) is the natural extension of its one-perturbation code: grid j enters dyn /
+        cost on its own axis behind the controls, shape (1,)*j + (W_j,) + (1,)*(m-1-j); the
+        joint law is the product of the (independent) marginals; the expectation is np.inner
+        over the C-order flattened product grid.  Returns (w_args, w_shape, p_flat)."""
+        m = len(self.perturb_grid)
+        w_shape = tuple(len(g) for g in self.perturb_grid)
+        w_args = tuple(np.asarray(g).reshape((1,) * j + (-1,) + (1,) * (m - 1 - j))
+                       for j, g in enumerate(self.perturb_grid))
+        p = np.ones(1)
+        for q in self.perturb_proba:
+            p = np.multiply.outer(p, np.asarray(q, dtype=float)).reshape(-1)
+        return w_args, w_shape, p
+
     # stodynprog.py:639-691
     def value_at_state(self, x_k, J_interp, t_k=None, want_index=False):
         u_grids, control_dims = self.control_grids(x_k, t_k)
         nc = len(u_grids)
-        for i in range(nc):
-            u_grids[i].shape = (1,) * i + (-1,) + (1,) * (nc - i)
         nb_perturb = len(self.perturb_grid)
-        args = x_k + tuple(u_grids) + tuple(self.perturb_grid)
+        n_w_axes = max(nb_perturb, 1)
+        for i in range(nc):
+            u_grids[i].shape = (1,) * i + (-1,) + (1,) * (nc - 1 - i + n_w_axes)
+        if nb_perturb >= 2:
+            w_args, w_shape, p_flat = self._perturb_product()
+        else:
+            w_args = tuple(self.perturb_grid)
+        args = x_k + tuple(u_grids) + w_args
         if t_k is not None:
             args = (t_k,) + args
         x_next = self.sys.dyn(*args, **self.sys.params)
@@ -139,6 +160,9 @@ class PortSolver(object):
         elif nb_perturb == 1:
             J = np.inner(J_grid, self.perturb_proba[0])
             assert J.shape == control_dims
+        else:
+            J_grid = np.broadcast_to(J_grid, control_dims + w_shape).reshape(control_dims + (-1,))
+            J = np.inner(J_grid, p_flat)
         flat = J.argmin()
         ind = np.unravel_index(flat, control_dims)
         u_opt = [u_grids[i].flatten()[ind[i]] for i in range(nc)]
@@ -202,15 +226,22 @@ class PortSolver(object):
         nc = len(self.sys.control)
         assert pol.shape == dims + (nc,)
         w_k, w_proba = self.perturb_grid[0], self.perturb_proba[0]
-        sg = tuple(np.reshape(self.state_grid[i], (1,) * i + (-1,) + (1,) * (ns - i))
+        m = len(self.perturb_grid)
+        w_args, w_shape = (w_k,), (len(w_k),)
+        if m >= 2:
+            w_args, w_shape, w_proba = self._perturb_product()
+        sg = tuple(np.reshape(self.state_grid[i], (1,) * i + (-1,) + (1,) * (ns - 1 - i + m))
                    for i in range(ns))
         for k in range(n_iter):
             J_interp = self.interp_on_state(J_pol)
-            u_k = [pol[..., i].reshape(dims + (1,)) for i in range(nc)]
-            args = sg + tuple(u_k) + (w_k,)
+            u_k = [pol[..., i].reshape(dims + (1,) * m) for i in range(nc)]
+            args = sg + tuple(u_k) + w_args
             x_next = self.sys.dyn(*args, **self.sys.params)
             g = self.sys.cost(*args, **self.sys.params)
-            J_pol = np.inner(g + J_interp(*x_next), w_proba)
+            J_grid = g + J_interp(*x_next)
+            if m >= 2:
+                J_grid = np.broadcast_to(J_grid, dims + w_shape).reshape(dims + (-1,))
+            J_pol = np.inner(J_grid, w_proba)
             if rel_dp:
                 J_ref[k] = J_pol[ref_ind]
                 J_pol -= J_ref[k]

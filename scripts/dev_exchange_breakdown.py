@@ -91,5 +91,46 @@ if rank == 0:
     print("rank  kernel  combine+stores+epoch  wait  gap   step")
     for r, x in enumerate(allr):
         print("%4d  %.4f  %.4f                %.4f %.4f %.4f" % ((r,) + tuple(float(v) for v in x)))
+# where the combine + exchange launch spends its time: the same combine with local stores only
+# (sdp_sweep_finalize), then the fused launch with parts of the exchange switched off (timing
+# only: `dbg_exchange` gives wrong results)
+def time_fn(fn, reps=20):
+    e = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in e:
+        a.record(st)
+        fn()
+        b.record(st)
+    torch.cuda.synchronize()
+    return float(np.median([a.elapsed_time(b) for a, b in e[3:]]))
+
+
+def fused():
+    k_new = px.index_of(J_new)
+    if T.col_bounds is not None:
+        rc = lib.sdp_sweep_finalize_p2p_cols(ctypes.byref(T.c_tables), eng._ptr(T.part_val), eng._ptr(T.part_idx),
+                                             eng._ptr(T.argmin), ctypes.byref(px.peers[k_new]),
+                                             T.col_bounds[-1], T.col_bounds[rank], eng.stream)
+    else:
+        rc = lib.sdp_sweep_finalize_p2p(ctypes.byref(T.c_tables), eng._ptr(T.part_val), eng._ptr(T.part_idx),
+                                        eng._ptr(T.argmin), ctypes.byref(px.peers[k_new]), T.state_begin, eng.stream)
+    _cabi.check(rc, "finalize_p2p")
+    _cabi.check(lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), eng.stream), "wait")
+
+
+def local():
+    _cabi.check(lib.sdp_sweep_finalize(ctypes.byref(T.c_tables), eng._ptr(T.part_val), eng._ptr(T.part_idx),
+                                       eng._ptr(T.J_out), eng._ptr(T.argmin), eng.stream), "finalize")
+
+
+res = {"local combine": time_fn(local)}
+for name, dbg in (("fused + wait", 0), ("  no remote stores", 1), ("  no system fence", 2), ("  relaxed flag stores", 4),
+                  ("  none of the three", 7)):
+    dist.barrier()
+    lib.sdp_set_option(b"dbg_exchange", dbg)
+    res[name] = time_fn(fused)
+lib.sdp_set_option(b"dbg_exchange", 0)
+if rank == 0:
+    for k, v in res.items():
+        print("%-24s %.4f ms" % (k, v))
 dist.barrier()
 dist.destroy_process_group()

@@ -16,11 +16,19 @@ from stodynprog_b200 import workloads as wl, _cabi  # noqa: E402
 from stodynprog_b200.engine import Engine, partition_by_weight  # noqa: E402
 
 Ns = [int(a) for a in sys.argv[1:]] or [8]
+# OPTS="col_dynamic=1,col_threads=768": library options; CHUNK=16: controls per work item
+for kv in filter(None, os.environ.get("OPTS", "").split(",")):
+    k, v = kv.split("=")
+    _cabi.check(_cabi.load_library().sdp_set_option(k.encode(), int(v)), "sdp_set_option")
+AXES = os.environ.get("AXES", "rows,columns").split(",")
 Engine.COLUMN_BANDS = "1"          # a rank of a multi-GPU run sweeps one band
 
 prob = wl.storage_ar1_large(sdp)
 sv = prob.solver
+if os.environ.get("CHUNK"):
+    sv._item_chunk = int(os.environ["CHUNK"])
 eng = sv.engine
+print("OPTS=%s CHUNK=%s" % (os.environ.get("OPTS", ""), os.environ.get("CHUNK", "auto")))
 T = eng.build_sweep_tables(sv)                 # the scan happens here, once
 U_all = T.host_full.U.astype(np.int64)
 n_rows, n_cols = sv._state_grid_shape
@@ -49,6 +57,8 @@ for N in Ns:
     col_w = (U_all + 1).reshape(n_rows, n_cols).sum(axis=0)
     cb = [int(b) for b in partition_by_weight(col_w, N)]
     for axis, bounds in (("rows", rb), ("columns", cb)):
+        if axis not in AXES:
+            continue
         ts = []
         for r in range(N):
             sv._slab_override = sv._col_override = None

@@ -53,11 +53,17 @@ for STEP in "$@"; do
           --log-file $OUT/${TAG}_launches_$W.csv python scripts/ncu_target.py $W on 3 >> $OUT/${TAG}_ncu_$W.log 2>&1
       tail -40 $OUT/${TAG}_ncu_$W.txt ;;
     sanitize)
-      for TOOL in memcheck racecheck; do
-        ( time timeout 900 compute-sanitizer --tool $TOOL --error-exitcode 9 python scripts/sanitizer_target.py ) \
-            > $OUT/${TAG}_sanitizer_$TOOL.log 2>&1
-        echo "exit: $?" >> $OUT/${TAG}_sanitizer_$TOOL.log
-        tail -8 $OUT/${TAG}_sanitizer_$TOOL.log
+      for TOOL in ${SAN_TOOLS:-memcheck racecheck}; do
+        L=$OUT/${TAG}_sanitizer_${TOOL}_n$N.log
+        if [ "$N" -gt 1 ]; then
+          PORT=$((PORT+1))
+          ( time timeout 1200 compute-sanitizer --tool $TOOL --target-processes all --error-exitcode 9 \
+              $TR --master-port $PORT scripts/sanitizer_target.py ) > $L 2>&1
+        else
+          ( time timeout 1200 compute-sanitizer --tool $TOOL --error-exitcode 9 python scripts/sanitizer_target.py ) > $L 2>&1
+        fi
+        echo "exit: $?" >> $L
+        grep -v "Warning\|warn" $L | tail -25
       done ;;
     py)
       S=${ARGS%% *}; A=""; [ "$ARGS" != "$S" ] && A=${ARGS#* }

@@ -149,6 +149,8 @@ SIGNATURES = {
     "sdp_supnorm_diff": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "sdp_interp": (ctypes.c_int, [_gp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "sdp_interp_f32": (ctypes.c_int, [_gp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "sdp_interp_host": (ctypes.c_int, [_gp, _i64, _vp, _i64, _vp, _vp]),
+    "sdp_interp_host_f32": (ctypes.c_int, [_gp, _i64, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

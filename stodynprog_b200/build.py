@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "--fmad=false",          # never contract a*b+c: parity contract, SURVEY.md App. A
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",   # (host pass: sdp_interp_host)
     "-cudart", "static",
 ]
 

@@ -1065,6 +1065,7 @@ struct Tuning {
     int col_pf;        // layout CF: groups of col_ub controls in flight per lane (1|2)
     int col_dynamic;   // layout CF: warps take the items of a column first come first served (1) or round-robin (0)
     int col_prepass;   // layout CF: column tables from the coalesced pre-pass, copied by vector loads (1) or by the TMA engine (2); 0: gathered by every CTA
+    int dbg_exchange;  // TIMING EXPERIMENTS ONLY (wrong results): 1 = no stores to remote ranks, 2 = no system fence, 4 = relaxed flag stores
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static int env_int(const char* name, int dflt) {
@@ -1097,11 +1098,15 @@ static Tuning& tuning() {
         x.hoist_const = env_int("SDP_HOIST_CONST", 1) != 0;
         // measured on config #5 (profiles/r1_column_tuning.txt): 512 threads 1.30 ms per sweep,
         // 640 (5 warps per scheduler, 96 registers) 1.24 ms, 704 1.38 ms, 768 1.22-1.26 ms
-        x.col_threads = clampi(env_int("SDP_COL_THREADS", 640), 128, 768) / 32 * 32;
+        // round 2 (profiles/r2_emu_variants.txt, one band / one shard of eight): 640 threads round-robin
+        // 1.180 / 0.1788 ms, 640 first-come-first-served 1.168 / 0.1729, 768 round-robin 1.158 / 0.1746,
+        // 768 first-come-first-served 1.148 / 0.1726 -> 768 threads, items handed out dynamically
+        x.col_threads = clampi(env_int("SDP_COL_THREADS", 768), 128, 768) / 32 * 32;
         x.col_ub = env_int("SDP_COL_UB", 2) == 1 ? 1 : 2;
         x.col_pf = env_int("SDP_COL_PF", 2) == 1 ? 1 : 2;
         x.col_prepass = clampi(env_int("SDP_COL_PREPASS", 2), 0, 2);
-        x.col_dynamic = env_int("SDP_COL_DYNAMIC", 0) != 0;
+        x.col_dynamic = env_int("SDP_COL_DYNAMIC", 1) != 0;
+        x.dbg_exchange = 0;
         return x;
     }();
     return t;
@@ -1125,6 +1130,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "col_pf")) t.col_pf = (value == 1) ? 1 : 2;
     else if (!strcmp(name, "col_prepass")) t.col_prepass = clampi(value, 0, 2);
     else if (!strcmp(name, "col_dynamic")) t.col_dynamic = value != 0;
+    else if (!strcmp(name, "dbg_exchange")) t.dbg_exchange = value;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -2363,12 +2369,17 @@ extern "C" int sdp_sweep(const SdpGrid* grid, const SdpTables* tab, const double
 // bumps the rank's epoch and lanes 0..world-1 release it into the flag arrays of all
 // ranks IN PARALLEL (one st.release.sys each: a loop in one thread would pay one
 // NVLink round trip per peer, 8 in a row on a full box).  Called by all threads.
-__device__ __forceinline__ void publish_epoch(const PeersDev& P) {
+__device__ __forceinline__ void publish_epoch(const PeersDev& P, int dbg = 0) {
     __shared__ unsigned long long e_sh;
     __shared__ int last_sh;
-    __threadfence_system();
+    // ONE system-scope fence per CTA, by the thread that signals, after the CTA barrier: the
+    // barrier orders the peer stores of all the CTA's threads before it and the fence is
+    // cumulative (the pattern of a grid-wide barrier).  A fence in every thread was measured at
+    // 33 us per launch on 2 and on 8 GPUs alike (the MEMBAR.SYS of the 32 warps of a CTA take
+    // turns), four times the stores themselves.
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (!(dbg & 2)) __threadfence_system();
         const unsigned int prev = atomicAdd(P.done, 1u);
         last_sh = (prev == gridDim.x - 1);
         if (last_sh) {
@@ -2379,7 +2390,10 @@ __device__ __forceinline__ void publish_epoch(const PeersDev& P) {
         }
     }
     __syncthreads();
-    if (last_sh && threadIdx.x < P.world) st_release_sys(P.flags[threadIdx.x] + P.rank, e_sh);
+    if (last_sh && threadIdx.x < P.world) {
+        if (dbg & 4) *(volatile unsigned long long*)(P.flags[threadIdx.x] + P.rank) = e_sh;
+        else st_release_sys(P.flags[threadIdx.x] + P.rank, e_sh);
+    }
 }
 
 // per-state combine of the partial minima; J is stored into every rank's buffer
@@ -2448,7 +2462,7 @@ __global__ void __launch_bounds__(1024)
 k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
                  const int64_t* __restrict__ item_begin, const double* __restrict__ part_val,
                  const int32_t* __restrict__ part_idx, double* __restrict__ J_out,
-                 int32_t* __restrict__ argmin_out, PeersDev P, int64_t j_offset, int64_t j_pitch) {
+                 int32_t* __restrict__ argmin_out, PeersDev P, int64_t j_offset, int64_t j_pitch, int dbg) {
     __shared__ double v_sh[32][33];
     __shared__ int i_sh[32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2481,11 +2495,11 @@ k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
             } else {
 #pragma unroll
                 for (int q = 0; q < SDP_MAX_PEERS; ++q)
-                    if (q < P.world) P.J[q][g] = bv;
+                    if (q < P.world && (!(dbg & 1) || q == P.rank)) P.J[q][g] = bv;
             }
         }
     }
-    if (P.world > 0) publish_epoch(P);
+    if (P.world > 0) publish_epoch(P, dbg);
 }
 
 // launch of the above for one band of layout CF
@@ -2497,7 +2511,8 @@ static void launch_combine_column(const SdpTables& T, const double* part_val, co
     unsigned blocks = (unsigned)col_blocks * (unsigned)((n_rows + 31) / 32);
     if (blocks == 0) blocks = 1;       // (an empty shard still publishes its epoch)
     k_combine_column<<<blocks, 1024, 0, st>>>(n_rows, T.n_cols, T.tiles_per_col, col_blocks, T.item_begin,
-                                              part_val, part_idx, J_out, argmin_out, P, j_offset, j_pitch);
+                                              part_val, part_idx, J_out, argmin_out, P, j_offset, j_pitch,
+                                              tuning().dbg_exchange);
 }
 
 static void launch_combine_column_local(const SdpTables& T, const double* part_val, const int32_t* part_idx,
@@ -2954,6 +2969,84 @@ static int interp_impl(const SdpGrid* grid, int64_t n_v, const T* values, int64_
     }
     SDP_LAUNCH_CHECK();
     return SDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K2 on the host, for a handful of points.  The reference's simulation loops call the policy
+// interpolant one scalar point at a time (examples/20 .../storage_control.py:217,246): through
+// the GPU that is two PCIe crossings and a launch per point.  Same arithmetic as k_interp,
+// operation for operation (x86 cvttsd2si cast semantics, true division, no contraction: the
+// host pass is compiled with -ffp-contract=off), so both paths return the same bits.
+// ---------------------------------------------------------------------------
+static inline int host_trunc(double t) {
+    if (!(t > -2147483649.0 && t < 2147483648.0)) return INT_MIN;
+    return (int)t;
+}
+static inline int host_trunc(float t) {
+    if (!(t >= -2147483648.0f && t < 2147483648.0f)) return INT_MIN;
+    return (int)t;
+}
+static double host_lerp(const double* V, int base, const int* stride, const double* lam, int D, int K) {
+    if (K == D) return V[base];
+    const double a = host_lerp(V, base, stride, lam, D, K + 1);
+    const double b = host_lerp(V, base + (K == D - 1 ? 1 : stride[K]), stride, lam, D, K + 1);
+    const double oml = 1.0 - lam[K];
+    const double x = oml * a, y = lam[K] * b;
+    return x + y;
+}
+// fp32: the generated C of the reference evaluates (1.0 - lam)*a and the sums in double, the
+// innermost lam*v product in float, one rounding to float at the end (see Lerp<float,...>)
+static double host_lerp_f(const float* V, int base, const int* stride, const float* lam, int D, int K) {
+    if (K == D - 1) {
+        const float v0 = V[base], v1 = V[base + stride[K]];
+        const float t2 = lam[K] * v1;
+        const double x = (1.0 - (double)lam[K]) * (double)v0;
+        return x + (double)t2;
+    }
+    const double a = host_lerp_f(V, base, stride, lam, D, K + 1);
+    const double b = host_lerp_f(V, base + stride[K], stride, lam, D, K + 1);
+    const double x = (1.0 - (double)lam[K]) * a, y = (double)lam[K] * b;
+    return x + y;
+}
+template <typename T>
+static int interp_host_impl(const SdpGrid* grid, int64_t n_v, const T* values, int64_t n_s, const T* s, T* out) {
+    GridT<T> G;
+    int64_t ng = 0;
+    int rc = make_grid<T>(grid, &G, &ng);
+    if (rc) return rc;
+    if (n_v < 0 || n_s < 0) return fail(SDP_EINVAL, "%s", "sdp_interp_host: bad sizes");
+    if (n_v == 0 || n_s == 0) return SDP_OK;
+    if (!values || !s || !out) return fail(SDP_EINVAL, "%s", "sdp_interp_host: NULL pointer");
+    const int D = grid->d;
+    for (int64_t i = 0; i < n_s; ++i) {
+        int base = 0;
+        T lam[SDP_MAX_D];
+        for (int k = 0; k < D; ++k) {
+            const T d0 = s[(int64_t)k * n_s + i] - G.smin[k];
+            const T sn = d0 / G.span[k];
+            const T t = sn * G.om1[k];
+            int q = host_trunc(t);
+            q = q < G.order[k] - 2 ? q : G.order[k] - 2;
+            q = q > 0 ? q : 0;
+            lam[k] = t - (T)q;
+            base += q * G.stride[k];
+        }
+        for (int64_t v = 0; v < n_v; ++v) {
+            if (sizeof(T) == 8)
+                out[v * n_s + i] = (T)host_lerp((const double*)(values + v * ng), base, G.stride, (const double*)lam, D, 0);
+            else
+                out[v * n_s + i] = (T)(float)host_lerp_f((const float*)(values + v * ng), base, G.stride, (const float*)lam, D, 0);
+        }
+    }
+    return SDP_OK;
+}
+extern "C" int sdp_interp_host(const SdpGrid* grid, int64_t n_v, const double* values, int64_t n_s,
+                               const double* s, double* out) {
+    return interp_host_impl<double>(grid, n_v, values, n_s, s, out);
+}
+extern "C" int sdp_interp_host_f32(const SdpGrid* grid, int64_t n_v, const float* values, int64_t n_s,
+                                   const float* s, float* out) {
+    return interp_host_impl<float>(grid, n_v, values, n_s, s, out);
 }
 
 extern "C" int sdp_interp(const SdpGrid* grid, int64_t n_v, const double* values, int64_t n_s,

@@ -802,11 +802,12 @@ class Engine(object):
                                  "(the reference's interpolation reads out of bounds and "
                                  "divides 0/0 on a 1-point axis, SURVEY.md App. A.2)")
         n_grid = int(np.prod([len(ax) for ax in state_grid]))
+        # several perturbations (a TODO of the reference, stodynprog.py:666,679-683): their product
+        # grid is flattened in C order into one axis of W nodes (tabulate.perturb_layout)
         nb_perturb = len(solver.perturb_grid)
-        if nb_perturb > 1:
-            raise NotImplementedError("multi-dimensional perturbations are not implemented "
-                                      "(neither in the reference: stodynprog.py:666,679-683)")
-        W = len(solver.perturb_grid[0]) if nb_perturb == 1 else 1
+        W = tb.perturb_layout(solver.perturb_grid)[2]
+        if W > 4096:
+            raise ValueError("the product perturbation grid has %d nodes; at most 4096 are supported" % W)
         coll = self.coll
         world, rank = coll.world, coll.rank
         dev = self.device
@@ -876,7 +877,7 @@ class Engine(object):
             raise ValueError("column_hoist must be 'auto', 'on' or 'off'")
         col_wanted = col_mode == "on" or (col_mode == "auto" and COLUMN_HOIST_DEFAULT)
         col_candidate = bool(
-            col_wanted and d in (2, 3) and nb_perturb == 1 and 1 < W <= _cabi.FACTORED_MAX_W_REG
+            col_wanted and d in (2, 3) and nb_perturb >= 1 and 1 < W <= _cabi.FACTORED_MAX_W_REG
             and 8 * _cabi.column_pitch(n_rows0, W) <= _cabi.COLUMN_MAX_SMEM_BYTES
             and getattr(solver, "table_layout", "auto") in ("auto", "state_minor")
             and getattr(solver, "table_compress", "auto") != "off"
@@ -940,7 +941,7 @@ class Engine(object):
             compress = getattr(solver, "table_compress", "auto")
             u_mask = 0
             w_cap = _cabi.FACTORED_MAX_W_REG if tiled else _cabi.FACTORED_MAX_W_SMEM
-            if (compress != "off" and n > 0 and nb_perturb == 1 and 1 < W <= w_cap and d in (2, 3)
+            if (compress != "off" and n > 0 and nb_perturb >= 1 and 1 < W <= w_cap and d in (2, 3)
                     and nb_control <= _cabi.SDP_MAX_C):
                 i_probe = int(np.argmax(U))
                 # (host row i_probe is grid state glob[i_probe] when the shard is whole columns)
@@ -1011,7 +1012,7 @@ class Engine(object):
                 else SweepTables()
             T.grid, T.d, T.W = grid, d, W
             T.tiled = tiled
-            T.expect = 1 if nb_perturb == 1 else 0
+            T.expect = 1 if nb_perturb >= 1 else 0
             T.bounds, T.state_begin, T.n_states = bounds, sb, n
             T.col_bounds = None
             if by_columns and col_override is not None:
@@ -1031,8 +1032,7 @@ class Engine(object):
             T.n_backups_local = int(U.sum()) * W
             T.n_backups_total = int(U_all.sum()) * W
             # host copy of the probabilities, kept alive with the tables (SdpTables.p_host)
-            T.p_host = np.ascontiguousarray(solver.perturb_proba[0], dtype=np.float64).copy() \
-                if nb_perturb == 1 else np.ones(1)
+            T.p_host = tb.joint_proba(solver.perturb_proba) if nb_perturb >= 1 else np.ones(1)
             # (one packed upload for the small per-table arrays)
             small = [T.p_host]
             if nb_control:
@@ -1052,6 +1052,9 @@ class Engine(object):
                 if t is None or t.numel() != numel or t.dtype != dtype:
                     setattr(T, name, None)        # release before allocating the new size
                     setattr(T, name, torch.empty(numel, dtype=dtype, device=dev))
+
+            keep_staging = bool(getattr(solver, "_keep_staging", False))
+            flushes, chunk_record = [], []
 
             def build(g_per_w, batched, u_mask, col):
                 L = {"u_mask": u_mask}
@@ -1098,48 +1101,63 @@ class Engine(object):
                 L.update(g_off=g_off, tile_g_off=tile_g_off)
                 ensure("g", max(g_len, 4), torch.float64)
                 done = [0]      # states flushed so far (chunks arrive in order)
+                del flushes[:], chunk_record[:]
 
                 def flush(desc, staging):
                     if u_mask:
                         tb.check_factorable(desc, d, u_mask)
                     desc_dev, stag_dev = self.to_device_packed([desc, staging])
                     ns = len(desc)
+                    first = done[0]
                     if tiled:
-                        assert done[0] % 32 == 0
-                        t_first = done[0] // 32
+                        assert first % 32 == 0
+                        t_first = first // 32
                         nt = (ns + 31) // 32
                         t_off = ctypes.c_void_p(tile_off_dev.data_ptr() + 8 * t_first)
                         t_U = ctypes.c_void_p(tile_U_dev.data_ptr() + 4 * t_first)
                         t_Umax = int(tile_U[t_first:t_first + nt].max())
-                        if u_mask:
+                    max_Upad = int(desc["Upad"].max()) if not tiled else 0
+
+                    def launch(desc_ptr, stag_ptr, g_ptr):
+                        """K0 on this chunk: `desc_ptr` / `stag_ptr` the chunk's descriptors and
+                        staged outputs, `g_ptr` the stage-cost table to fill (a recursion whose
+                        dynamics ignore the instant calls it again per instant with the
+                        descriptors pointing at that instant's cost)"""
+                        if tiled and u_mask:
                             w0 = t_first * W * 32
                             rc = self.lib.sdp_build_tables_factored_tiled(
-                                ctypes.byref(grid), W, u_mask, ns, self._ptr(desc_dev), self._ptr(stag_dev),
+                                ctypes.byref(grid), W, u_mask, ns, desc_ptr, stag_ptr,
                                 nt, t_off, t_U, t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane,
-                                self._ptr(T.g), ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
+                                g_ptr, ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
                                 ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
                             _cabi.check(rc, "sdp_build_tables_factored_tiled")
-                        else:
+                        elif tiled:
                             rc = self.lib.sdp_build_tables_tiled(
-                                ctypes.byref(grid), W, g_per_w, ns, self._ptr(desc_dev), self._ptr(stag_dev),
+                                ctypes.byref(grid), W, g_per_w, ns, desc_ptr, stag_ptr,
                                 nt, t_off, ctypes.c_void_p(tile_g_off_dev.data_ptr() + 8 * t_first), t_U,
-                                t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g),
+                                t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane, g_ptr,
                                 self.stream)
                             _cabi.check(rc, "sdp_build_tables_tiled")
-                    elif u_mask:
-                        w0 = done[0] * W
-                        rc = self.lib.sdp_build_tables_factored(
-                            ctypes.byref(grid), W, u_mask, ns, self._ptr(desc_dev), self._ptr(stag_dev),
-                            self._ptr(T.cell), self._ptr(T.lam), lam_plane, self._ptr(T.g),
-                            int(desc["Upad"].max()), ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
-                            ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
-                        _cabi.check(rc, "sdp_build_tables_factored")
-                    else:
-                        rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, ns,
-                                                       self._ptr(desc_dev), self._ptr(stag_dev),
-                                                       self._ptr(T.cell), self._ptr(T.lam), lam_plane,
-                                                       self._ptr(T.g), int(desc["Upad"].max()), self.stream)
-                        _cabi.check(rc, "sdp_build_tables")
+                        elif u_mask:
+                            w0 = first * W
+                            rc = self.lib.sdp_build_tables_factored(
+                                ctypes.byref(grid), W, u_mask, ns, desc_ptr, stag_ptr,
+                                self._ptr(T.cell), self._ptr(T.lam), lam_plane, g_ptr,
+                                max_Upad, ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
+                                ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
+                            _cabi.check(rc, "sdp_build_tables_factored")
+                        else:
+                            rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, ns,
+                                                           desc_ptr, stag_ptr,
+                                                           self._ptr(T.cell), self._ptr(T.lam), lam_plane,
+                                                           g_ptr, max_Upad, self.stream)
+                            _cabi.check(rc, "sdp_build_tables")
+
+                    launch(self._ptr(desc_dev), self._ptr(stag_dev), self._ptr(T.g))
+                    # (`keep`: the device arrays the launch closure points into)
+                    flushes.append(dict(desc=desc, n_staging=len(staging), stag_dev=stag_dev, launch=launch,
+                                        first=first, keep=(desc_dev, tile_off_dev, tile_g_off_dev, tile_U_dev)
+                                        if tiled else (desc_dev,)) if keep_staging else None)
                     done[0] += ns
                     # the staging tensors are freed by torch's caching allocator in
                     # stream order, so no synchronisation is needed here
@@ -1154,7 +1172,8 @@ class Engine(object):
                                                g_off, Upad, g_per_w, flush, align=align,
                                                verify=1 if prev_mode == "batched" else 8,
                                                grid_cache=self._grid_cache if t_k is not None else None,
-                                               flat_index=flat_eff, valid=valid)
+                                               flat_index=flat_eff, valid=valid,
+                                               record=chunk_record if keep_staging else None)
                 else:
                     states = mine if (mine is not None and (sb, se) == (eq[rank], eq[rank + 1])) else \
                         tb.state_tuples(state_grid, sb, se)
@@ -1283,6 +1302,11 @@ class Engine(object):
             T.J_out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
             T.argmin = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             T.c_tables = fill_c_tables(T)
+            # (kept for Engine.recursion_fast: one chunk, one flush, batched evaluation)
+            T.build_record = None
+            if keep_staging and T.tabulate_mode == "batched" and len(flushes) == 1 and len(chunk_record) == 1 \
+                    and not col:
+                T.build_record = dict(flushes[0], host=host, w_grid=w_grid, **chunk_record[0])
             return T
 
         # slabs balanced by admissible controls ...
@@ -1721,6 +1745,148 @@ class Engine(object):
         torch.cuda.current_stream(self.device).synchronize()
         return [self.result_array(o) for o in outs]
 
+    # -- time-dependent recursion, fast path ----------------------------------
+    RECURSION_MAX_G_BYTES = 8 << 30      # per-instant stage-cost tables kept resident
+
+    def recursion_fast(self, solver, t_ini, t_fin, J_fin, J_out, pol_out):
+        """bellman_recursion (stodynprog.py:536-591) for systems whose dynamics and admissible
+        controls do not depend on the instant, only the stage cost does - the reference's
+        time-dependent examples (examples/01 .../pv_storage_control.py:43-65: the PV production
+        enters the cost alone).  The cell / weight tables are then the same at every instant:
+        they are built once, the cost is tabulated for all instants up front, the T sweeps
+        are enqueued back to back with J and the policy staying on the device, and one copy
+        brings (J, pol) of all instants to the host.
+
+        Nothing is assumed: the box scan and the batched dyn evaluation of the first, middle
+        and last instant are compared bit for bit, and at every instant dyn / control_box of
+        one sample state (another one each time) are compared with the tables and the batched
+        cost is checked on sample states against the reference's per-state call.  Any
+        difference -> returns None and the caller takes the per-instant path.
+        Returns a dict of timings on success."""
+        import time
+        torch = _torch()
+        t0 = time.perf_counter()
+        sys = solver.sys
+        if self.coll.world > 1 or t_fin - t_ini < 3:
+            return None
+        t_base = t_fin - 1
+        solver._keep_staging = True
+        try:
+            T = self.build_sweep_tables(solver, t_base)
+        finally:
+            solver._keep_staging = False
+        rec = getattr(T, "build_record", None)
+        if rec is None or T.n_states != len(rec["desc"]):
+            return None
+        d, nc, W = T.d, T.nb_control, T.W
+        host, cols, outs0 = rec["host"], rec["cols"], rec["outs"]
+        S = T.n_states
+        g0 = outs0[-1]
+        n_T = t_fin - t_ini
+        g_len = T.g.numel()
+        if n_T * g_len * 8 > self.RECURSION_MAX_G_BYTES:
+            return None
+        state_grid = [np.asarray(g, dtype=float) for g in solver.state_grid]
+        w_args, w_shape, _ = tb.perturb_layout(rec["w_grid"])
+        state_of = lambda i: tuple(c[i] for c in cols)            # noqa: E731
+
+        def same_bits(a, b):
+            return a.shape == b.shape and np.array_equal(a.view(np.int64), b.view(np.int64))
+
+        # 1. dyn / control_box at the first and the middle instant against the last one
+        for t_chk in sorted({t_ini, (t_ini + t_fin) // 2}):
+            if t_chk == t_base:
+                continue
+            box = tb.scan_control_boxes(sys, solver.control_steps, [state_of(i) for i in range(S)], t_chk)
+            if not (same_bits(box.lo, host.lo) and same_bits(box.hi, host.hi) and np.array_equal(box.npts, host.npts)):
+                return None
+            dyn_t, _ = tb._eval_state_chunk(sys, cols, host.lo, host.hi, host.npts, w_args, t_chk, W,
+                                            self._grid_cache, w_shape, only="dyn")
+            if not all(same_bits(a, b) for a, b in zip(dyn_t, outs0[:d])):
+                return None
+
+        # 2. the stage cost of every instant (one batched call each), checked on sample states
+        g_src = np.empty((n_T,) + g0.shape)
+        k_base = t_base - t_ini
+        g_src[k_base] = g0
+        for k in range(n_T):
+            t_k = t_ini + k
+            if t_k == t_base:
+                continue
+            i_chk = (7 * k) % S
+            x_chk = state_of(i_chk)
+            box = tb.scan_control_boxes(sys, solver.control_steps, [x_chk], t_k)
+            if not (same_bits(box.lo[0], host.lo[i_chk]) and same_bits(box.hi[0], host.hi[i_chk])
+                    and np.array_equal(box.npts[0], host.npts[i_chk])):
+                return None
+            (g_t,), nmax = tb._eval_state_chunk(sys, cols, host.lo, host.hi, host.npts, w_args, t_k, W,
+                                                self._grid_cache, w_shape, only="cost")
+            if g_t.shape != g0.shape:
+                return None
+            full = tuple(int(n) for n in host.npts[i_chk]) + (W,)
+            for i_s, what in ((i_chk, None), ((i_chk + S // 2) % S, "cost")):
+                compact, cdims, U = tb._eval_one_state(sys, state_of(i_s), host, i_s, w_args, t_k, W, w_shape,
+                                                       only=what)
+                cdims = tuple(cdims)
+                pairs = [(g_t, compact[-1])] if what == "cost" else \
+                    list(zip(list(outs0[:d]) + [g_t], compact))
+                for a, (ref, u_eff, w_eff) in pairs:
+                    row = a[i_s if a.shape[0] > 1 else 0]
+                    sl = tuple(slice(0, cdims[c] if row.shape[c] > 1 else 1) for c in range(nc))
+                    shape = (cdims if u_eff > 1 else (1,) * nc) + (w_eff,)
+                    fullb = cdims + (W,)
+                    got = np.ascontiguousarray(np.broadcast_to(row[sl], fullb))
+                    want = np.ascontiguousarray(np.broadcast_to(ref.reshape(shape), fullb))
+                    if not same_bits(got, want):
+                        return None
+            g_src[k] = g_t
+        t_tab = time.perf_counter()
+
+        # 3. device: staging of instant t_base + the cost of all instants behind it; per-instant
+        # descriptors differ only in where the cost is read
+        n_stag = rec["n_staging"]
+        g_size = g0.size
+        stag_all = torch.empty(n_stag + n_T * g_size, dtype=torch.float64, device=self.device)
+        stag_all[:n_stag].copy_(rec["stag_dev"])
+        stag_all[n_stag:].copy_(self.to_device(g_src.reshape(-1)))
+        desc_all = np.repeat(rec["desc"][None, :], n_T, axis=0)
+        shift = n_stag + np.arange(n_T, dtype=np.int64) * g_size - rec["g_base"]
+        desc_all["src"][:, :, d] += shift[:, None]
+        desc_dev = self.to_device_packed([desc_all.reshape(-1)])[0]
+        desc_bytes = desc_all.dtype.itemsize * S
+        g_all = torch.empty((n_T, g_len), dtype=torch.float64, device=self.device)
+        for k in range(n_T):
+            rec["launch"](ctypes.c_void_p(desc_dev.data_ptr() + k * desc_bytes), self._ptr(stag_all),
+                          ctypes.c_void_p(g_all.data_ptr() + 8 * k * g_len))
+
+        # 4. the T sweeps back to back, J and the policy on the device
+        n_grid = S
+        J_all = torch.empty((n_T + 1, n_grid), dtype=torch.float64, device=self.device)
+        J_all[n_T].copy_(self.to_device(np.ascontiguousarray(np.asarray(J_fin, dtype=np.float64).reshape(-1))))
+        arg_all = torch.empty((n_T, n_grid), dtype=torch.int32, device=self.device)
+        pol_all = torch.empty((n_T, n_grid, max(nc, 1)), dtype=torch.float64, device=self.device)
+        self.sync()
+        t_up = time.perf_counter()
+        for k in range(n_T - 1, -1, -1):
+            v = _cabi.SdpTables.from_buffer_copy(T.c_tables)
+            v.g = g_all.data_ptr() + 8 * k * g_len
+            rc = self.lib.sdp_sweep(ctypes.byref(T.grid), ctypes.byref(v), self._ptr(J_all[k + 1]),
+                                    self._ptr(T.part_val), self._ptr(T.part_idx), self._ptr(J_all[k]),
+                                    self._ptr(arg_all[k]), self.stream)
+            _cabi.check(rc, "sdp_sweep")
+            if nc:
+                rc = self.lib.sdp_policy_values(n_grid, nc, self._ptr(T.lo_dev), self._ptr(T.hi_dev),
+                                                self._ptr(T.npts_dev), self._ptr(arg_all[k]),
+                                                self._ptr(pol_all[k]), self.stream)
+                _cabi.check(rc, "sdp_policy_values")
+        J_h, pol_h = self.to_host(J_all[:n_T], pol_all)
+        t_end = time.perf_counter()
+        J_out[...] = J_h.reshape(J_out.shape)
+        if nc:
+            pol_out[...] = pol_h.reshape(pol_out.shape)
+        return {"tabulate_s": t_tab - t0, "upload_build_s": t_up - t_tab, "sweeps_s": t_end - t_up,
+                "instants": n_T, "tables": T}
+
     # -- policy tables ----------------------------------------------------
     def build_policy_tables(self, solver, pol):
         """Evaluate dyn/cost for the fixed policy on the whole grid exactly as
@@ -1735,15 +1901,21 @@ class Engine(object):
         nb_control = len(sys.control)
         grid = _cabi.make_grid(state_grid_1d)
         n_grid = int(np.prod(state_dims))
-        w_k = np.asarray(solver.perturb_grid[0])      # IndexError if deterministic, like :726
-        w_proba = np.asarray(solver.perturb_proba[0], dtype=float)
-        W = len(w_k)
-        state_grid = tuple(np.reshape(g, (1,) * i + (-1,) + (1,) * (nb_state - i))
+        solver.perturb_grid[0]                        # IndexError if deterministic, like :726
+        w_args, w_shape, W = tb.perturb_layout(solver.perturb_grid)
+        w_proba = tb.joint_proba(solver.perturb_proba)
+        n_w_axes = len(w_shape)
+        state_grid = tuple(np.reshape(g, (1,) * i + (-1,) + (1,) * (nb_state - 1 - i + n_w_axes))
                            for i, g in enumerate(solver.state_grid))
-        u_k = [pol[..., i].reshape(state_dims + (1,)) for i in range(nb_control)]
-        args = state_grid + tuple(u_k) + (w_k,)
+        u_k = [pol[..., i].reshape(state_dims + (1,) * n_w_axes) for i in range(nb_control)]
+        args = state_grid + tuple(u_k) + w_args
         x_next = sys.dyn(*args, **sys.params)
         g_k = sys.cost(*args, **sys.params)
+        if n_w_axes > 1:
+            # one trailing axis: the C-order flattened product of the perturbation axes
+            x_next = tuple(tb._fold_w(self._as_full(c, state_dims + w_shape), nb_state, w_shape, "dyn")
+                           for c in x_next)
+            g_k = tb._fold_w(self._as_full(g_k, state_dims + w_shape), nb_state, w_shape, "cost")
         full = state_dims + (W,)
         world, rank = self.coll.world, self.coll.rank
         bounds = [n_grid * r // world for r in range(world + 1)]

@@ -9,11 +9,23 @@
   API vendored by the reference (dolointerpolation/multilinear_cython.pyx:17-49,
   dolointerpolation/multilinear.py:15-91).
 
-All evaluations run on the GPU; there is no CPU path in this package.
+Batches are evaluated on the GPU (K2).  Calls with at most `HOST_MAX_POINTS` points - the
+reference's simulation loops evaluate the policy interpolant one scalar point per time step
+(examples/20 Searev storage control/storage_control.py:217,246) - go to the library's host
+routine `sdp_interp_host` instead: same operations in the same order, bit-identical results,
+no launch and no PCIe crossing.  It is a latency path of the same native library, not a
+fallback: without the CUDA extension or without a GPU the package raises.
 """
+import ctypes
+import os
+
 import numpy as np
 
 from . import _cabi
+
+# a GPU call costs ~100 us of copies, launch and synchronisation: what the host routine needs
+# for a few thousand points
+HOST_MAX_POINTS = int(os.environ.get("SDP_INTERP_HOST_MAX_POINTS", "2048"))
 
 __all__ = ["MlinInterpolator", "multilinear_interpolation", "MultilinearInterpolator", "mlinspace"]
 
@@ -59,8 +71,18 @@ def multilinear_interpolation(smin, smax, orders, values, s, engine=None):
         g.order[k] = orders[k]
         g.smin[k] = float(smin[k])
         g.smax[k] = float(smax[k])
-    eng = engine or _default_engine()
-    return eng.interp(g, np.ascontiguousarray(values), np.ascontiguousarray(s))
+    eng = engine or _default_engine()          # (raises without the extension or without a GPU)
+    values = np.ascontiguousarray(values)
+    s = np.ascontiguousarray(s)
+    n_v, n_s = values.shape[0], s.shape[1]
+    if n_v * n_s <= HOST_MAX_POINTS and getattr(eng, "_cuda", False):
+        out = np.empty((n_v, n_s), dtype=dtype)
+        fn = eng.lib.sdp_interp_host_f32 if dtype == np.float32 else eng.lib.sdp_interp_host
+        rc = fn(ctypes.byref(g), n_v, values.ctypes.data_as(ctypes.c_void_p), n_s,
+                s.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+        _cabi.check(rc, "sdp_interp_host")
+        return out
+    return eng.interp(g, values, s)
 
 
 class MlinInterpolator(object):

@@ -79,6 +79,10 @@ class DPSolver(object):
         # others get None - 8 ranks pulling 24 MB each through a shared PCIe root take
         # 2 ms, one rank 0.45 ms.  value_iteration / solve_value_iteration only.
         self.host_results = "all"     # "all" | "root"
+        # bellman_recursion: "auto" tabulates all instants up front and runs the sweeps back to
+        # back when only the stage cost depends on the instant; "per_instant" never does
+        self.recursion_mode = "auto"  # "auto" | "per_instant"
+        self.last_recursion = None    # timings of the last fast recursion (diagnostics)
 
     # ------------------------------------------------------------------
     # discretisation (host only)
@@ -192,14 +196,13 @@ class DPSolver(object):
         sys = self.sys
         grids = [np.asarray(g, dtype=float) for g in self.state_grid]
         dims = [len(g) for g in grids]
-        w_args = tuple(self.perturb_grid)
-        W = len(self.perturb_grid[0]) if len(self.perturb_grid) else 1
+        w_args, w_shape, W = tb.perturb_layout(self.perturb_grid)
         out = []
         for idx in ([0] * len(dims), [n // 2 for n in dims], [n - 1 for n in dims]):
             x_k = tuple(g[i] for g, i in zip(grids, idx))
             tab = tb.scan_control_boxes(sys, self.control_steps, [x_k], t_k)
             out += [tab.lo.tobytes(), tab.hi.tobytes(), tab.npts.tobytes()]
-            compact, _, _ = tb._eval_one_state(sys, x_k, tab, 0, w_args, t_k, W)
+            compact, _, _ = tb._eval_one_state(sys, x_k, tab, 0, w_args, t_k, W, w_shape)
             out += [a.tobytes() for a, _, _ in compact]
         return b"".join(out)
 
@@ -365,6 +368,16 @@ class DPSolver(object):
         return J, pol
 
     def _recursion(self, t_ini, t_fin, J_fin, J, pol):
+        # systems whose dynamics and admissible controls ignore the instant (checked, not
+        # assumed): one table build, the cost of all instants tabulated up front, the sweeps
+        # enqueued back to back (Engine.recursion_fast); anything else: instant by instant
+        self.last_recursion = None
+        if getattr(self, "recursion_mode", "auto") != "per_instant":
+            info = self.engine.recursion_fast(self, t_ini, t_fin, J_fin, J, pol)
+            if info is not None:
+                self.last_tables = info.pop("tables")
+                self.last_recursion = info
+                return
         tables = None
         for t_k in range(t_ini, t_fin)[::-1]:
             print('\rtk = {:3d}...'.format(t_k), end='')

@@ -19,7 +19,7 @@ from . import _cabi
 
 __all__ = ["scan_control_boxes", "scan_control_boxes_batched", "scan_control_boxes_by_axes", "scan_control_boxes_parallel", "state_tuples_at", "control_grid_counts", "control_axis_values", "HostStateTable", "tabulate_states",
            "tabulate_states_batched", "GDependsOnW", "BatchedMismatch", "NotFactorable",
-           "probe_factor_mask", "check_factorable"]
+           "probe_factor_mask", "check_factorable", "perturb_layout", "joint_proba"]
 
 
 def _npts_for(width, step):
@@ -90,7 +90,59 @@ class HostStateTable(object):
         return self.npts.prod(axis=1)
 
 
-def _compact(a, control_dims, U, W, what):
+def perturb_layout(perturb_grid):
+    """(w_args, w_shape, W) of a solver's perturbation grids.
+
+    One perturbation: its grid goes to dyn/cost as the reference passes it, a (W,) vector on the
+    last axis (stodynprog.py:667-672).  Several perturbations - which the reference leaves as a
+    TODO (stodynprog.py:614,666,679-683,728) - each get an axis of their own behind the control
+    axes: grid j is passed with shape (1,)*j + (W_j,) + (1,)*(m-1-j), the outputs broadcast to
+    controls + (W_1, .., W_m), and the product grid is flattened in C order into ONE axis of
+    W = W_1*..*W_m nodes whose probabilities are the products of the marginals
+    (`joint_proba`; the laws of a SysDescription are independent).  The expectation is then the
+    reference's np.inner over that axis, nodes summed in C order of the product."""
+    m = len(perturb_grid)
+    if m == 0:
+        return (), (), 1
+    grids = [np.asarray(g) for g in perturb_grid]
+    w_shape = tuple(len(g) for g in grids)
+    if m == 1:
+        return (grids[0],), w_shape, w_shape[0]
+    w_args = tuple(g.reshape((1,) * j + (-1,) + (1,) * (m - 1 - j)) for j, g in enumerate(grids))
+    return w_args, w_shape, int(np.prod(w_shape))
+
+
+def joint_proba(perturb_proba):
+    """probabilities of the flattened product grid of `perturb_layout` (C order)"""
+    p = np.ones(1)
+    for q in perturb_proba:
+        p = np.multiply.outer(p, np.asarray(q, dtype=float)).reshape(-1)
+    return np.ascontiguousarray(p)
+
+
+def _fold_w(a, lead, w_shape, what):
+    """output of dyn/cost with `lead` leading axes (controls, or states + controls) followed by
+    one axis per perturbation -> the same with ONE trailing axis: the C-order flattened product of
+    the perturbation axes, or size 1 when the output spans none of them"""
+    m = len(w_shape)
+    if m <= 1:
+        return a
+    if a.ndim > lead + m:
+        raise ValueError("%s returned an array of rank %d; expected something broadcastable to "
+                         "%d leading axes + the perturbation grid %s" % (what, a.ndim, lead, w_shape))
+    a = a.reshape((1,) * (lead + m - a.ndim) + a.shape)
+    tail = a.shape[lead:]
+    for n_a, n_w in zip(tail, w_shape):
+        if n_a != 1 and n_a != n_w:
+            raise ValueError("%s output shape %s does not broadcast to the perturbation grid %s"
+                             % (what, a.shape, w_shape))
+    if all(n_a == 1 for n_a in tail):
+        return a.reshape(a.shape[:lead] + (1,))
+    a = np.broadcast_to(a, a.shape[:lead] + tuple(w_shape))
+    return a.reshape(a.shape[:lead] + (-1,))
+
+
+def _compact(a, control_dims, U, W, what, w_shape=()):
     """Reduce one dyn/cost output to a C-contiguous (Ueff, Weff) fp64 array with
     Ueff in {1,U}, Weff in {1,W}: the un-broadcast form of what
     MlinInterpolator.__call__ would expand (stodynprog.py:281-283:
@@ -98,6 +150,7 @@ def _compact(a, control_dims, U, W, what):
     a = np.asarray(a)
     if a.dtype != np.float64:
         a = a.astype(float)
+    a = _fold_w(a, len(control_dims), w_shape, what)
     nb = len(control_dims) + 1
     if a.ndim > nb:
         raise ValueError("%s returned an array of rank %d; expected something broadcastable "
@@ -384,8 +437,8 @@ def probe_factor_mask(sys, x_k, host_tab, i, perturb_grid, t_k):
     of factored tables, or None when some coordinate spans
     both axes, the cost depends on w, or the split would be one-sided."""
     d = len(sys.state)
-    W = len(perturb_grid[0])
-    compact, control_dims, U = _eval_one_state(sys, x_k, host_tab, i, tuple(perturb_grid), t_k, W)
+    w_args, w_shape, W = perturb_layout(perturb_grid)
+    compact, control_dims, U = _eval_one_state(sys, x_k, host_tab, i, w_args, t_k, W, w_shape)
     if compact[-1][2] > 1:
         return None                       # g depends on w
     mask = 0
@@ -426,28 +479,34 @@ class GDependsOnW(Exception):
     built with one g per (state, control): restart with a dense g table"""
 
 
-def _eval_one_state(sys, x_k, host_tab, i, w_args, t_k, W):
+def _eval_one_state(sys, x_k, host_tab, i, w_args, t_k, W, w_shape=(), only=None):
     """dyn/cost of one state with the reference's argument shapes
-    (stodynprog.py:655-676).  Returns [(array(Ueff,Weff), Ueff, Weff)] * (d+1)."""
+    (stodynprog.py:655-676).  Returns [(array(Ueff,Weff), Ueff, Weff)] * (d+1).
+    `w_args`, `W`, `w_shape`: see perturb_layout."""
     d = len(sys.state)
     nb_control = len(sys.control)
     control_dims = tuple(int(n) for n in host_tab.npts[i])
     U = int(np.prod(control_dims)) if nb_control else 1
+    n_w_axes = max(len(w_shape), 1)
     u_grids = []
     for c in range(nb_control):
         ug = make_control_grid(host_tab.lo[i, c], host_tab.hi[i, c], control_dims[c])
-        # control c varies along axis c, the perturbation along the last axis
-        ug.shape = (1,) * c + (-1,) + (1,) * (nb_control - c)
+        # control c varies along axis c, the perturbation(s) along the last axis (axes)
+        ug.shape = (1,) * c + (-1,) + (1,) * (nb_control - 1 - c + n_w_axes)
         u_grids.append(ug)
     args = x_k + tuple(u_grids) + w_args
     if t_k is not None:
         args = (t_k,) + args
+    if only == "cost":          # (see _eval_state_chunk)
+        return [_compact(sys.cost(*args, **sys.params), control_dims, U, W, "cost", w_shape)], control_dims, U
     x_next = sys.dyn(*args, **sys.params)
-    g_k = sys.cost(*args, **sys.params)
     if len(x_next) != d:
         raise ValueError("dyn returned %d next-state components, expected %d" % (len(x_next), d))
-    compact = [_compact(c, control_dims, U, W, "dyn") for c in x_next]
-    compact.append(_compact(g_k, control_dims, U, W, "cost"))
+    compact = [_compact(c, control_dims, U, W, "dyn", w_shape) for c in x_next]
+    if only == "dyn":
+        return compact, control_dims, U
+    g_k = sys.cost(*args, **sys.params)
+    compact.append(_compact(g_k, control_dims, U, W, "cost", w_shape))
     # the joint broadcast of (g, x_next...) must cover the whole control grid
     # (stodynprog.py:683 asserts J.shape == control_dims)
     if U > 1 and not any(u_eff == U for _, u_eff, _ in compact):
@@ -466,16 +525,15 @@ def tabulate_states(sys, states, host_tab, perturb_grid, t_k, entry_off, g_off, 
     nb_control = len(sys.control)
     if nb_control > _cabi.SDP_MAX_C:
         raise NotImplementedError("more than %d control variables" % _cabi.SDP_MAX_C)
-    W = len(perturb_grid[0]) if len(perturb_grid) > 0 else 1
+    w_args, w_shape, W = perturb_layout(perturb_grid)
     writer = _ChunkWriter(d, flush_fn, max_doubles, align)
-    w_args = tuple(perturb_grid)
     block = 1024
     for b0 in range(0, len(states), block):
         b1 = min(b0 + block, len(states))
         recs = np.zeros(b1 - b0, dtype=_cabi.STATE_DESC_DTYPE)
         recs["npts"] = 1
         for i in range(b0, b1):
-            compact, control_dims, U = _eval_one_state(sys, states[i], host_tab, i, w_args, t_k, W)
+            compact, control_dims, U = _eval_one_state(sys, states[i], host_tab, i, w_args, t_k, W, w_shape)
             if compact[-1][2] > 1 and not g_per_w:
                 raise GDependsOnW()
             r = recs[i - b0]
@@ -507,7 +565,8 @@ def _strides_or_zero(shape):
     return np.where(np.asarray(shape) == 1, 0, st)
 
 
-def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=None):
+def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=None, w_shape=(),
+                      only=None):
     """dyn/cost for a chunk of S states in ONE call: state variables enter as
     (S,1,..,1) arrays, control c as an (S,..,n_c_max,..,1) array whose row s is
     that state's own control grid (padded by repeating its last point), the
@@ -519,13 +578,15 @@ def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=
     nmax = [int(npts[:, c].max()) for c in range(nb_control)]
     full_shape = (S,) + tuple(nmax) + (W,)
     rank = len(full_shape)
-    xs = tuple(col.reshape((S,) + (1,) * (rank - 1)) for col in state_cols)
+    n_w_axes = max(len(w_shape), 1)
+    rank_in = 1 + nb_control + n_w_axes         # rank of the arguments (one axis per perturbation)
+    xs = tuple(col.reshape((S,) + (1,) * (rank_in - 1)) for col in state_cols)
     # the padded control grids of the chunk; a time-dependent recursion whose boxes do
     # not change from one instant to the next (the common case) reuses them
     key = None
     us = None
     if grid_cache is not None:
-        key = (lo.tobytes(), hi.tobytes(), npts.tobytes())
+        key = (lo.tobytes(), hi.tobytes(), npts.tobytes(), n_w_axes)
         us = grid_cache.get(key)
     if us is None:
         us = []
@@ -533,7 +594,7 @@ def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=
             j = np.arange(nmax[c])[None, :]
             n_c = npts[:, c][:, None]
             vals = control_axis_values(lo[:, c][:, None], hi[:, c][:, None], n_c, np.minimum(j, n_c - 1))
-            vals = vals.reshape((S,) + (1,) * c + (nmax[c],) + (1,) * (nb_control - c))
+            vals = vals.reshape((S,) + (1,) * c + (nmax[c],) + (1,) * (nb_control - 1 - c + n_w_axes))
             vals.flags.writeable = False      # shared between calls: user code must not mutate it
             us.append(vals)
         if grid_cache is not None:
@@ -543,15 +604,22 @@ def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=
     args = xs + tuple(us) + w_args
     if t_k is not None:
         args = (t_k,) + args
-    x_next = sys.dyn(*args, **sys.params)
-    g_k = sys.cost(*args, **sys.params)
-    if len(x_next) != d:
-        raise ValueError("dyn returned %d next-state components, expected %d" % (len(x_next), d))
+    # `only`: "cost" / "dyn" evaluate one of the two callables (time-dependent recursions whose
+    # dynamics do not depend on the instant re-evaluate the cost alone)
+    pairs = []
+    if only != "cost":
+        x_next = sys.dyn(*args, **sys.params)
+        if len(x_next) != d:
+            raise ValueError("dyn returned %d next-state components, expected %d" % (len(x_next), d))
+        pairs += [("dyn", c) for c in x_next]
+    if only != "dyn":
+        pairs.append(("cost", sys.cost(*args, **sys.params)))
     outs = []
-    for what, a in [("dyn", c) for c in x_next] + [("cost", g_k)]:
+    for what, a in pairs:
         a = np.asarray(a)
         if a.dtype != np.float64:
             a = a.astype(float)
+        a = _fold_w(a, 1 + nb_control, w_shape, what)
         if a.ndim > rank:
             raise ValueError("%s output of rank %d does not broadcast to %s" % (what, a.ndim, full_shape))
         a = np.ascontiguousarray(a.reshape((1,) * (rank - a.ndim) + a.shape))
@@ -565,7 +633,7 @@ def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=
 def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid, t_k, entry_off,
                             g_off, Upad, g_per_w, flush_fn, chunk_states=4096,
                             max_doubles=16 << 20, align=1, verify=8, grid_cache=None,
-                            flat_index=None, valid=None):
+                            flat_index=None, valid=None, record=None):
     """Second pass, batched mode: one dyn/cost call per chunk of states.
     `verify` sample states of EVERY chunk are re-evaluated per state, the
     reference's way, and compared bit-for-bit; a mismatch raises
@@ -579,8 +647,7 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
     nb_control = len(sys.control)
     if nb_control > _cabi.SDP_MAX_C:
         raise NotImplementedError("more than %d control variables" % _cabi.SDP_MAX_C)
-    W = len(perturb_grid[0]) if len(perturb_grid) > 0 else 1
-    w_args = tuple(perturb_grid)
+    w_args, w_shape, W = perturb_layout(perturb_grid)
     dims = [len(g) for g in state_grid]
     writer = _ChunkWriter(d, flush_fn, max_doubles, align)
     n = end - begin if flat_index is None else len(flat_index)
@@ -593,14 +660,14 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
         cols = [np.asarray(state_grid[k])[idx[k]] for k in range(d)]
         npts = host_tab.npts[b0:b1]
         outs, nmax = _eval_state_chunk(sys, cols, host_tab.lo[b0:b1], host_tab.hi[b0:b1], npts,
-                                       w_args, t_k, W, grid_cache)
+                                       w_args, t_k, W, grid_cache, w_shape)
         if outs[-1].shape[-1] > 1 and not g_per_w:
             raise GDependsOnW()
         if verify:
             # every chunk is another region of the state space, where the branches of a user's
             # np.where / clipping may differ: each is checked on its own sample states
             _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, min(verify, S),
-                          None if valid is None else valid[b0:b1])
+                          None if valid is None else valid[b0:b1], w_shape)
         recs = np.zeros(S, dtype=_cabi.STATE_DESC_DTYPE)
         recs["npts"] = 1
         recs["npts"][:, :nb_control] = npts
@@ -616,6 +683,11 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
             recs["src"][:, k] = base + np.arange(S) * st[0]
             recs["cs"][:, k, :nb_control] = st[1:1 + nb_control]
             recs["ws"][:, k] = st[-1]
+        if record is not None:
+            # what a recursion whose dynamics ignore the instant needs to re-tabulate the cost
+            # alone (Engine.recursion_fast): the chunk's state columns and un-broadcast outputs,
+            # and where the cost sits in the staging buffer
+            record.append(dict(cols=cols, outs=outs, g_base=int(base), b0=b0, b1=b1))
         writer.add_descs(recs)
     writer.flush()
 
@@ -625,7 +697,7 @@ class BatchedMismatch(Exception):
     a chunk of states at once"""
 
 
-def _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, n_check, valid=None):
+def _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, n_check, valid=None, w_shape=()):
     """bit-for-bit comparison of the chunk evaluation against the reference's
     per-state evaluation on a few sample states, after full broadcast"""
     S = len(cols[0])
@@ -635,7 +707,7 @@ def _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, n_check, valid=
         picks = picks[np.asarray(valid)[picks]]      # (padding positions repeat a real state)
     for s in picks:
         x_k = tuple(col[s] for col in cols)
-        compact, control_dims, U = _eval_one_state(sys, x_k, host_tab, b0 + s, w_args, t_k, W)
+        compact, control_dims, U = _eval_one_state(sys, x_k, host_tab, b0 + s, w_args, t_k, W, w_shape)
         full = tuple(control_dims) + (W,)
         for a, (ref, u_eff, w_eff) in zip(outs, compact):
             row = a[s if a.shape[0] > 1 else 0]                     # (n1.., Weff)

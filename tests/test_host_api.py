@@ -13,7 +13,7 @@ import pytest
 import stodynprog_b200 as sdp
 from stodynprog_b200 import _cabi, tabulate as tb
 from stodynprog_b200.sysdesc import _zero_cost, _enforce_sig_len
-from conftest import ROOT
+from conftest import ROOT, golden
 
 
 # --- mirror of reference tests/test_stodynprog.py ---------------------------
@@ -541,6 +541,31 @@ def test_cached_tables_follow_the_callables(port):
         J, pol = sv2.value_iteration(J0 - np.arange(10.), report_time=False)
         Jo, polo = ora2.value_iteration(J0 - np.arange(10.))
         assert np.array_equal(pol, polo) and np.allclose(J, Jo, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+def test_host_interpolation_routine_is_bit_exact(product, d):
+    """sdp_interp_host / sdp_interp_host_f32 (the latency path for a handful of points: host
+    pointers, no launch) against the outputs of the reference's own compiled Cython routine on
+    the adversarial fixture points (outside the grid, +-3e9, +-1e300, +-inf, NaN), fp64 and fp32"""
+    G = golden("interp_kat.npz")
+    lib = _cabi.load_library()
+    smin, smax, orders = G["d%d_smin" % d], G["d%d_smax" % d], G["d%d_orders" % d]
+    g = _cabi.SdpGrid()
+    g.d = d
+    for k in range(d):
+        g.order[k], g.smin[k], g.smax[k] = int(orders[k]), float(smin[k]), float(smax[k])
+    for dtype, fn, want in ((np.float64, lib.sdp_interp_host, G["d%d_out" % d]),
+                            (np.float32, lib.sdp_interp_host_f32, G["d%d_out_f32" % d])):
+        values = np.ascontiguousarray(G["d%d_values" % d], dtype=dtype)
+        s = np.ascontiguousarray(G["d%d_s" % d], dtype=dtype)
+        out = np.empty((values.shape[0], s.shape[1]), dtype=dtype)
+        rc = fn(ctypes.byref(g), values.shape[0], values.ctypes.data_as(ctypes.c_void_p), s.shape[1],
+                s.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        bits = np.int64 if dtype == np.float64 else np.int32
+        same = (out.view(bits) == want.view(bits)) | (np.isnan(out) & np.isnan(want))
+        assert same.all(), (dtype, int((~same).sum()))
 
 
 def test_no_cpu_fallback(product):

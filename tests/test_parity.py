@@ -237,6 +237,45 @@ def test_pv_storage_bellman_recursion_vs_port(api, port):
     assert rel_err(J, Jo) <= J_RTOL
 
 
+def test_recursion_fast_path_and_its_refusals(api, port):
+    """bellman_recursion: when only the stage cost depends on the instant the tables are built
+    once and the sweeps run back to back (Engine.recursion_fast) - same J and policies, bit for
+    bit, as the instant-by-instant path; dynamics or admissible controls that do depend on
+    the instant are detected and take the instant-by-instant path (and match the port)"""
+    from stodynprog_b200 import workloads as wl
+    out = {}
+    for mode in ("auto", "per_instant"):
+        prob = wl.pv_storage(api, horizon=12)
+        sv = prob.solver
+        sv.control_steps = (.02,)
+        sv.recursion_mode = mode
+        out[mode] = sv.bellman_recursion(12, prob.J_fin, report_time=False)
+        assert (sv.last_recursion is not None) == (mode == "auto")
+        if mode == "auto":
+            assert sv.last_recursion["instants"] == 12
+    assert _same_bits(out["auto"][0], out["per_instant"][0]) and np.array_equal(out["auto"][1], out["per_instant"][1])
+
+    def variant(a, what):
+        prob = wl.pv_storage(a, horizon=12)
+        sv, sysd = prob.solver, prob.sys
+        sv.control_steps = (.02,)
+        dyn0, box0 = sysd.dyn, sysd.control_box
+        if what == "dyn":          # a self-discharge that sets in half-way
+            sysd._dyn = lambda k, E, P: (dyn0(k, E, P)[0] - 0.01 * E * (k >= 6),)
+        else:                       # the rated power shrinks with the instant
+            def box(k, E):
+                (lo, hi), = box0(k, E)
+                return ((lo * (1 - 0.02 * k), hi),)
+            sysd._control_box = box
+        return prob
+    for what in ("dyn", "box"):
+        prob, ora = variant(api, what), variant(port, what)
+        J, pol = prob.solver.bellman_recursion(12, prob.J_fin, report_time=False)
+        assert prob.solver.last_recursion is None
+        Jo, polo = ora.solver.bellman_recursion(12, ora.J_fin)
+        assert policy_mismatch_report(pol, polo)[0] == 0 and rel_err(J, Jo) <= J_RTOL
+
+
 @gpu
 def test_pv_storage_full_horizon_golden(cuda_api):
     from stodynprog_b200 import workloads as wl
@@ -439,6 +478,99 @@ def test_toy_systems_vs_port(api, port, d, cost_kind):
         Jro, refo = so.eval_policy(polo, 7, rel_dp=True)
         assert abs(ref - refo) <= J_RTOL * abs(refo)
         assert np.max(np.abs(Jr - Jro)) <= J_RTOL * max(np.max(np.abs(Jro)), 1e-300)
+
+
+def _two_perturbations(api, kind, n0=6, **kw):
+    """2 states, 1 control, TWO perturbations (a continuous one on 3 nodes, a discrete one on 2):
+    `kind` "mixed": a coordinate and the cost depend on control AND perturbations (dense tables);
+    "split": E-like coordinate follows the control, the other the perturbations (factored)"""
+    import scipy.stats as stats
+
+    def dyn(x0, x1, u, w1, w2):
+        if kind == "mixed":
+            return (0.9 * x0 + 0.4 * u + 0.3 * w1, 0.8 * x1 + 0.2 * u * w2 + 0.1 * w1)
+        return (x0 + 0.5 * u, 0.8 * x1 + 0.3 * w1 + 0.25 * w2)
+
+    def box(x0, x1):
+        return ((-1.0 - 0.1 * x0, 1.0 + 0.05 * x0),)
+
+    def cost(x0, x1, u, w1, w2):
+        base = x0 ** 2 + 0.5 * x1 ** 2 + 0.1 * u ** 2
+        return base + 0.05 * w1 * u - 0.02 * w2 if kind == "mixed" else base
+
+    sys = api.SysDescription((2, 1, 2), name='two perturbations')
+    sys.dyn, sys.control_box, sys.cost = dyn, box, cost
+    sys.perturb_laws = [stats.norm(0, 0.5), stats.rv_discrete(values=([0, 1], [0.3, 0.7])).freeze()]
+    sv = api.DPSolver(sys, **kw)
+    sv.discretize_state(-1.0, 2.0, n0, -1.0, 1.5, 5)
+    sv.discretize_perturb(-0.9, 0.9, 3, 0, 1, 2)
+    sv.control_steps = (2.0 / 23,)
+    return sv
+
+
+def test_two_perturbations_port_against_brute_force(port):
+    """the oracle port's convention for several perturbations (the reference has a TODO there,
+    stodynprog.py:614,666,679-683) pinned against explicit loops: for every control, the sum
+    over (w1, w2) in C order of p1[i]*p2[j] * (g + J(f(x, u, w1_i, w2_j)))"""
+    from oracle import oracle as oc
+    for kind in ("mixed", "split"):
+        so = _two_perturbations(port, kind)
+        sysd = so.sys
+        J0 = np.random.default_rng(5).standard_normal(so._state_grid_shape)
+        Jo, polo = so.value_iteration(J0)
+        smin = np.array([g[0] for g in so.state_grid])
+        smax = np.array([g[-1] for g in so.state_grid])
+        orders = np.array([len(g) for g in so.state_grid], dtype=np.int64)
+        vals = np.ascontiguousarray(J0.reshape(1, -1))
+        (w1, w2), (p1, p2) = so.perturb_grid, so.perturb_proba
+        for i0, x0 in enumerate(so.state_grid[0]):
+            for i1, x1 in enumerate(so.state_grid[1]):
+                (ug,), _ = so.control_grids((x0, x1))
+                best, best_u = None, None
+                for u in ug:
+                    acc = 0.0
+                    for a, wa in enumerate(w1):
+                        for b, wb in enumerate(w2):
+                            xn = sysd.dyn(x0, x1, u, wa, wb)
+                            pt = np.array([[float(xn[0])], [float(xn[1])]])
+                            v = float(oc.interp(smin, smax, orders, vals, pt)[0, 0])
+                            acc += (sysd.cost(x0, x1, u, wa, wb) + v) * (p1[a] * p2[b])
+                    if best is None or acc < best:
+                        best, best_u = acc, u
+                assert abs(Jo[i0, i1] - best) <= 1e-12 * max(abs(best), 1.0)
+                assert polo[i0, i1, 0] == best_u
+
+
+@pytest.mark.parametrize("kind", ["mixed", "split"])
+def test_two_perturbations_vs_port(api, port, kind):
+    """value iteration, policy evaluation and policy iteration with a product perturbation grid
+    (3 x 2 nodes flattened to W = 6) against the oracle port"""
+    sv, so = _two_perturbations(api, kind), _two_perturbations(port, kind)
+    J0 = np.random.default_rng(6).standard_normal(sv._state_grid_shape)
+    J, pol = sv.value_iteration(J0, report_time=False)
+    Jo, polo = so.value_iteration(J0)
+    T = sv.last_tables
+    assert T.W == 6 and T.expect == 1
+    assert bool(T.u_mask) == (kind == "split" and sv.table_compress != "off")
+    assert np.array_equal(pol, polo) and rel_err(J, Jo) <= J_RTOL
+    Je, ref = sv.eval_policy(pol, 6, rel_dp=True, report_time=False)
+    Jeo, refo = so.eval_policy(polo, 6, rel_dp=True)
+    assert abs(ref - refo) <= J_RTOL * abs(refo) and np.max(np.abs(Je - Jeo)) <= J_RTOL * np.max(np.abs(Jeo))
+    (Jp, Jr), polp = sv.policy_iteration(pol, 4, 2, rel_dp=True)
+    (Jpo, Jro), polpo = so.policy_iteration(polo, 4, 2, rel_dp=True)
+    assert np.array_equal(polp, polpo) and abs(Jr - Jro) <= J_RTOL * abs(Jro)
+
+
+@pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
+def test_two_perturbations_column_layout(product, port, backend):
+    """the product perturbation grid through layout CF (40 rows of axis 0, W = 6 <= 9 slots)"""
+    api = _Api(product, backend, "state_minor", "auto", "on", "on")
+    sv, so = _two_perturbations(api, "split", n0=40), _two_perturbations(port, "split", n0=40)
+    J0 = np.random.default_rng(7).standard_normal(sv._state_grid_shape)
+    J, pol = sv.value_iteration(J0, report_time=False)
+    Jo, polo = so.value_iteration(J0)
+    assert sv.last_tables.layout_name == "column_factored"
+    assert np.array_equal(pol, polo) and rel_err(J, Jo) <= J_RTOL
 
 
 def test_rel_dp_value_iteration(api, port):
@@ -804,11 +936,11 @@ def test_column_hoist_is_bit_identical(product, backend, which):
                 assert _same_bits(Jr, J2), (threads, ub, pf, pre)
                 assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf, pre)
         finally:
-            lib.sdp_set_option(b"col_threads", 640)
+            lib.sdp_set_option(b"col_threads", 768)
             lib.sdp_set_option(b"col_ub", 2)
             lib.sdp_set_option(b"col_pf", 2)
             lib.sdp_set_option(b"col_prepass", 2)
-            lib.sdp_set_option(b"col_dynamic", 0)
+            lib.sdp_set_option(b"col_dynamic", 1)
 
 
 @pytest.mark.parametrize("backend", [pytest.param("model"), pytest.param("cuda", marks=gpu)])
