@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SDP_ABI_VERSION 6
+#define SDP_ABI_VERSION 7
 #define SDP_MAX_D 4 /* the reference dispatches d = 1..4 (multilinear_cython.pyx:36-47) */
 
 /* error codes */
@@ -204,7 +204,15 @@ typedef struct SdpTables {
     double* col_table;
     const int64_t* run_end;    /* [n_items] */
     int32_t col_table_ready;   /* streaming pass: 0 = run the pre-pass first, 1 = col_table is current */
-    int32_t reserved2;
+    /* streaming pass, optional launch shape: low 16 bits = threads per CTA (0: library default),
+     * bit 16 = hand the items of a run out round-robin instead of first come first served */
+    int32_t col_launch_hint;
+    /* streaming pass, optional [n_items]: the ORDER in which the item list is walked - seg_begin and
+     * run_end then refer to positions p of this order, position p being item item_order[p], and a
+     * run is a stretch of positions whose items share a column (any bands).  NULL: positions are
+     * item indices.  Lets a device-resident sweep visit the bands of a column back to back (one
+     * table load per column) while the tables stay ordered band by band for the combine. */
+    const int64_t* item_order;
 } SdpTables;
 
 /* ABI / build identification. */
@@ -316,6 +324,10 @@ typedef struct SdpPeers {
     uint64_t* flags[SDP_MAX_PEERS];   /* [world] flag array on every rank; this rank writes entry `rank` */
     uint64_t* epoch;                  /* local: exchanges/barriers completed by this rank */
     uint32_t* done;                   /* local: CTA completion counter, zero between launches */
+    /* optional (all NULL: off): [n_grid] int32 argmin buffer on every rank.  The fused combine then
+     * stores each state's argmin next to its J on every rank, so that every rank holds the whole
+     * policy and the host results can be mapped and copied out by all ranks in parallel. */
+    int32_t* A[SDP_MAX_PEERS];
 } SdpPeers;
 /* Fused per-state combine + all-gather: as sdp_sweep_finalize, but J goes to
  * peers->J[r][state_begin + i] for every rank r; then epoch += 1 and the new

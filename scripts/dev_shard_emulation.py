@@ -15,13 +15,13 @@ import stodynprog_b200 as sdp  # noqa: E402
 from stodynprog_b200 import workloads as wl, _cabi  # noqa: E402
 from stodynprog_b200.engine import Engine, partition_by_weight  # noqa: E402
 
-Ns = [int(a) for a in sys.argv[1:]] or [8]
+Ns = [int(a) for a in sys.argv[1:] if int(a) > 1] if len(sys.argv) > 1 else [8]
 # OPTS="col_dynamic=1,col_threads=768": library options; CHUNK=16: controls per work item
 for kv in filter(None, os.environ.get("OPTS", "").split(",")):
     k, v = kv.split("=")
     _cabi.check(_cabi.load_library().sdp_set_option(k.encode(), int(v)), "sdp_set_option")
 AXES = os.environ.get("AXES", "rows,columns").split(",")
-Engine.COLUMN_BANDS = "1"          # a rank of a multi-GPU run sweeps one band
+Engine.COLUMN_BANDS = os.environ.get("BANDS", "1")    # (a rank of a multi-GPU run sweeps one band)
 
 prob = wl.storage_ar1_large(sdp)
 sv = prob.solver
@@ -49,7 +49,7 @@ def time_partials(T, reps=12):
 
 
 t1 = time_partials(T)
-print("N=1 (one band): %.4f ms, layout %s, items %d, chunk %d" % (t1, T.layout_name, T.n_items, T.item_chunk), flush=True)
+print("N=1 (bands %s): %.4f ms, layout %s, items %d, chunk %d" % (T.bands["rows"], t1, T.layout_name, T.n_items, T.item_chunk), flush=True)
 del T
 for N in Ns:
     row_w = (U_all + 1).reshape(n_rows, n_cols).sum(axis=1)

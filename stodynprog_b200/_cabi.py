@@ -12,7 +12,7 @@ import numpy as np
 
 SDP_MAX_D = 4
 SDP_MAX_C = 4
-SDP_ABI_VERSION = 6
+SDP_ABI_VERSION = 7
 LAYOUT_CONTROL_MINOR = 0   # "A": [state][w][u]
 LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
 LAYOUT_CONTROL_MINOR_FACTORED = 2   # "AF": (x,u) part [state][Upad] + (x,w) part [state][W]
@@ -73,7 +73,8 @@ class SdpTables(ctypes.Structure):
                 ("col_table", ctypes.c_void_p),
                 ("run_end", ctypes.c_void_p),
                 ("col_table_ready", ctypes.c_int32),
-                ("reserved2", ctypes.c_int32)]
+                ("col_launch_hint", ctypes.c_int32),
+                ("item_order", ctypes.c_void_p)]
 
 
 SDP_MAX_PEERS = 8
@@ -85,7 +86,8 @@ class SdpPeers(ctypes.Structure):
                 ("J", ctypes.c_void_p * SDP_MAX_PEERS),
                 ("flags", ctypes.c_void_p * SDP_MAX_PEERS),
                 ("epoch", ctypes.c_void_p),
-                ("done", ctypes.c_void_p)]
+                ("done", ctypes.c_void_p),
+                ("A", ctypes.c_void_p * SDP_MAX_PEERS)]
 
 
 # numpy mirrors of the per-state descriptor and the work item (host-built arrays

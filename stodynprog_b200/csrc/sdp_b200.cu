@@ -1785,6 +1785,7 @@ static void launch_fact_tiled_w(const GridT<double>& G, const SdpTables& T, cons
 struct PeersDev {
     int world, rank;
     double* J[SDP_MAX_PEERS];
+    int32_t* A[SDP_MAX_PEERS];      // optional: every rank's full-grid argmin buffer (NULL: none)
     unsigned long long* flags[SDP_MAX_PEERS];
     unsigned long long* epoch;
     unsigned int* done;
@@ -1930,8 +1931,10 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
     int64_t i = T.seg_begin[blockIdx.x];
     const int64_t seg_end = T.seg_begin[blockIdx.x + 1];
     while (i < seg_end) {
-        const int col = T.items[i].Upad;          // layout CF: the column of the item's tile
-        const int64_t run_end = T.run_end[i];     // end of the items of this band and column
+        // (positions i index the item list directly, or through T.item_order: the bands of a
+        // column back to back, so that a device-resident sweep loads each column's table once)
+        const int col = T.items[T.item_order ? T.item_order[i] : i].Upad;     // the column of the item's tile
+        const int64_t run_end = T.run_end[i];     // end of the run of positions sharing this table
         const int64_t e = run_end < seg_end ? run_end : seg_end;
         __syncthreads();                 // the previous column's readers are done with R
         if (threadIdx.x == 0) next_item = 0;
@@ -1990,8 +1993,9 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
                 if (lane == 0) k = atomicAdd(&next_item, 1);
                 k = __shfl_sync(0xffffffffu, k, 0);
             }
-            const int64_t item_id = i + k;
-            if (item_id >= e) break;
+            const int64_t pos = i + k;
+            if (pos >= e) break;
+            const int64_t item_id = T.item_order ? T.item_order[pos] : pos;
             const SdpItem it = T.items[item_id];
             const int Us = T.U[(int64_t)it.state * 32 + lane];      // by position; 0 on padding lanes
             const int32_t* __restrict__ cup = T.cell + it.entry_base + lane;
@@ -2099,12 +2103,13 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
     for (int w = 0; w < SDP_FACTORED_MAX_W_REG; ++w)
         pv.v[w] = (w < T.W) ? (T.expect ? T.p_host[w] : 1.0) : 0.0;
     const double inv0 = 1.0 / (double)G.stride[0];
+    const int dynamic = (T.col_launch_hint & 0xffff) ? !((T.col_launch_hint >> 16) & 1) : tuning().col_dynamic;
     if (T.W == WM)
         k_sweep_fact_column<D, WM, UB, PF, true, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
-            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, tuning().col_dynamic);
+            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, dynamic);
     else
         k_sweep_fact_column<D, WM, UB, PF, false, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
-            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, tuning().col_dynamic);
+            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, dynamic);
     note_kernel("%sk_sweep_fact_column<%d,%d,%d,%d,%s,%d> [%d CTAs x %d threads]",
                 (prepass && !T.col_table_ready) ? "k_column_table + " : "", D, WM, UB, PF,
                 T.W == WM ? "true" : "false", MAXT, (int)T.n_segs, threads);
@@ -2115,7 +2120,12 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
 template <int D, int WM>
 static int launch_fact_column_w(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                                 double* part_val, int32_t* part_idx, cudaStream_t st) {
-    const int ub = tuning().col_ub, pf = tuning().col_pf, threads = tuning().col_threads;
+    // T.col_launch_hint (low 16 bits: threads per CTA, bit 16: hand the items out round-robin):
+    // the caller's knowledge of the launch - many short column pieces per CTA (a band of rows)
+    // run best with 640 threads round-robin, long ones with 768 and first come first served
+    const int hint_threads = T.col_launch_hint & 0xffff;
+    const int ub = tuning().col_ub, pf = tuning().col_pf;
+    const int threads = hint_threads ? clampi(hint_threads, 128, 768) / 32 * 32 : tuning().col_threads;
     if (threads > 640) {       // 85 registers per thread
         if (ub == 2) return launch_fact_column_k<D, WM, 2, 1, 768>(G, T, Jprev, part_val, part_idx, st, threads);
         return pf == 2 ? launch_fact_column_k<D, WM, 1, 2, 768>(G, T, Jprev, part_val, part_idx, st, threads)
@@ -2420,6 +2430,11 @@ k_sweep_finalize_p2p(int64_t n_states, const int64_t* __restrict__ item_begin,
 #pragma unroll
         for (int r = 0; r < SDP_MAX_PEERS; ++r)
             if (r < P.world) P.J[r][state_begin + i] = bv;
+        if (P.A[0]) {
+#pragma unroll
+            for (int r = 0; r < SDP_MAX_PEERS; ++r)
+                if (r < P.world) P.A[r][state_begin + i] = bi;
+        }
     }
     // publish: every CTA fences its peer stores, the last one to finish releases the epoch
     publish_epoch(P);
@@ -2496,6 +2511,14 @@ k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
 #pragma unroll
                 for (int q = 0; q < SDP_MAX_PEERS; ++q)
                     if (q < P.world && (!(dbg & 1) || q == P.rank)) P.J[q][g] = bv;
+                if (P.A[0]) {
+                    // the argmin travels with J: every rank then holds the whole policy and can
+                    // map and copy out any part of it (results fanned out over all PCIe links)
+                    const int bi = i_sh[warp][lane];
+#pragma unroll
+                    for (int q = 0; q < SDP_MAX_PEERS; ++q)
+                        if (q < P.world && (!(dbg & 1) || q == P.rank)) P.A[q][g] = bi;
+                }
             }
         }
     }
@@ -2531,6 +2554,7 @@ static int make_peers(const SdpPeers* p, PeersDev* out, const char* who) {
     out->rank = p->rank;
     for (int r = 0; r < SDP_MAX_PEERS; ++r) {
         out->J[r] = (r < p->world) ? p->J[r] : nullptr;
+        out->A[r] = (r < p->world) ? p->A[r] : nullptr;
         out->flags[r] = (r < p->world) ? (unsigned long long*)p->flags[r] : nullptr;
         if (r < p->world && !p->flags[r]) return fail(SDP_EINVAL, "%s: NULL flag array", who);
     }

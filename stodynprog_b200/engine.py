@@ -128,8 +128,13 @@ def fill_c_tables(T):
             c.n_cols, c.tiles_per_col = T.n_cols, T.tiles_per_col
             c.seg_begin, c.n_segs = T.seg_begin.data_ptr(), T.n_segs
             c.col_table = T.col_table.data_ptr()
-            c.run_end = T.run_end.data_ptr()
             c.col_table_ready = 0
+            if T.item_order is not None:
+                # several bands: the whole-list launch walks the bands of a column back to back
+                c.item_order = T.item_order.data_ptr()
+                c.run_end = T.run_end_ord.data_ptr()
+            else:
+                c.run_end = T.run_end.data_ptr()
         c.u_mask = T.u_mask
         c.cell_w = T.cell_w.data_ptr()
         c.lam_w = T.lam_w.data_ptr()
@@ -390,6 +395,14 @@ class PeerExchange(object):
         self._views = {}
         self.J = [self.buf[:n_grid], self.buf[n_pad:n_pad + n_grid]]
         self.local = torch.zeros(4, dtype=torch.int64, device=engine.device)   # [epoch, done]
+        # every rank's full-grid argmin, filled by the peers' combine kernels like J (SdpPeers.A)
+        self.abuf = symm.empty(n_pad, dtype=torch.int32, device=engine.device)
+        self.abuf.zero_()
+        self.ahdl = symm.rendezvous(self.abuf, group)
+        torch.cuda.synchronize(engine.device)
+        self.ahdl.barrier()
+        self.argmin = self.abuf[:n_grid]
+        aptrs = [int(p) for p in self.ahdl.buffer_ptrs]
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.peers = []
         for k in range(2):
@@ -398,6 +411,7 @@ class PeerExchange(object):
             for r in range(world):
                 P.J[r] = ptrs[r] + 8 * k * n_pad
                 P.flags[r] = ptrs[r] + 8 * 2 * n_pad
+                P.A[r] = aptrs[r]
             P.epoch = self.local.data_ptr()
             P.done = self.local.data_ptr() + 8
             self.peers.append(P)
@@ -467,6 +481,8 @@ class SweepTables(object):
         self.item_u_count_host = None
         self.col_table = None      # device fp64 scratch: the column tables of the current sweep
         self.run_end = None        # device int64 [n_items]: end of every item's (band, column) run
+        self.item_order = None     # several bands: device int64 [n_items], items column by column (all bands)
+        self.run_end_ord = None    # ... and the end of every position's column run in that order
         self.bands = None          # dict(rows, tiles, tile_begin, tile_col), see column_order
         self.band_views = None     # per band: (SdpTables view for the combine pass, first state, states)
         self.sm_count = 148
@@ -653,6 +669,98 @@ class Engine(object):
                     px = None
             self._peer[n_grid] = px
         return self._peer[n_grid]
+
+    def host_share(self, n_grid, nc):
+        """HostShare for results of [n_grid] states x nc controls, or None: one rank, no peer
+        exchange (the argmin must travel with J), SDP_HOST_SHARE=0, or shared memory /
+        cudaHostRegister not available - same answer on every rank"""
+        key = ("host_share", n_grid, nc)
+        if key not in self._peer:
+            hs = None
+            if (self.coll.world > 1 and self.peer_exchange(n_grid) is not None
+                    and os.environ.get("SDP_HOST_SHARE", "1") != "0"):
+                from .hostshare import HostShare
+                err = None
+                try:
+                    hs = HostShare(self.coll, n_grid, nc, self._cuda)
+                except Exception as e:          # every rank must still take part in the vote below
+                    err = e
+                ok = self.coll.all_gather_object(hs is not None)
+                if not all(ok):
+                    if err is not None:
+                        import warnings
+                        warnings.warn("shared host results unavailable (%s: %s)" % (type(err).__name__, err))
+                    hs = None
+            self._peer[key] = hs
+        return self._peer[key]
+
+    def sweep_shared(self, hs, T, J_next, rel_ref_index=None, want_results=True, while_waiting=None):
+        """One sweep with host arrays in and out through the shared page-locked segment `hs`:
+        every rank uploads 1/N of J_next and hands it to its peers over NVLink, sweeps its shard
+        (the combine kernel stores J AND the argmin into every rank's buffers), maps 1/N of the
+        policy to control values and copies 1/N of (J, pol) into the shared result slot over its
+        own PCIe link.  Returns (J, pol, J_ref) as views of the slot (None, None, J_ref when
+        `want_results` is False), or None when no slot is free (the caller takes the private-
+        copy path; same decision on every rank)."""
+        torch = _torch()
+        world, rank = self.coll.world, self.coll.rank
+        n_grid, nc = hs.n_grid, hs.nc
+        px = self.peer_exchange(n_grid)
+        # 1. where is the input, which slot takes the output (rank 0's array decides)
+        src = -2
+        if rank == 0:
+            src = hs.slot_of(J_next)
+            if src is None:
+                hs.stage_J().numpy()[:] = np.asarray(J_next, dtype=np.float64).reshape(-1)
+                src = -1
+        hs.publish(0, src if rank == 0 else 0)
+        hs.publish(1, hs.live_mask())
+        hs.barrier()
+        src = hs.read(0, 0)
+        live = 0
+        for r in range(world):
+            live |= hs.read(r, 1)
+        out = next((s_ for s_ in range(hs.n_slots) if s_ != src and not (live >> s_) & 1), None)
+        if out is None:
+            return None
+        J_src = hs.stage_J() if src < 0 else hs.slot_J(src)
+        # 2. upload 1/N, hand it to the peers
+        J_prev, J_new = self.J_pair(n_grid)
+        self.begin_call(n_grid)
+        a, b = n_grid * rank // world, n_grid * (rank + 1) // world
+        k = px.index_of(J_prev)
+        J_prev[a:b].copy_(J_src[a:b], non_blocking=True)
+        for r in range(world):
+            if r != rank:
+                px.peer_view(r, k)[a:b].copy_(J_prev[a:b], non_blocking=True)
+        px.barrier()
+        # 3. the sweep; J_new and the argmin are complete on every rank after the flag wait
+        ref_out = torch.zeros(1, dtype=torch.float64, device=self.device) if rel_ref_index is not None else None
+        self.sweep(T, J_prev, J_new, rel_ref_index=rel_ref_index, ref_out=ref_out)
+        # 4. 1/N of the results -> the shared slot
+        pol = torch.empty((b - a, max(nc, 1)), dtype=torch.float64, device=self.device)
+        if nc and b > a:
+            rc = self.lib.sdp_policy_values(
+                b - a, nc, ctypes.c_void_p(T.lo_dev.data_ptr() + 8 * nc * a),
+                ctypes.c_void_p(T.hi_dev.data_ptr() + 8 * nc * a),
+                ctypes.c_void_p(T.npts_dev.data_ptr() + 4 * nc * a),
+                ctypes.c_void_p(px.argmin.data_ptr() + 4 * a), self._ptr(pol), self.stream)
+            _cabi.check(rc, "sdp_policy_values")
+        hs.slot_J(out)[a:b].copy_(J_new[a:b], non_blocking=True)
+        if nc:
+            hs.slot_pol(out)[a * nc:b * nc].copy_(pol.view(-1)[:(b - a) * nc], non_blocking=True)
+        ref_host = None
+        if ref_out is not None:
+            ref_host = self.host_result_buffer((1,), torch.float64)
+            ref_host.copy_(ref_out, non_blocking=True)
+        if while_waiting is not None:
+            while_waiting()
+        self.torch_stream.synchronize() if self._cuda else None
+        hs.barrier()
+        J_ref = float(ref_host[0]) if ref_host is not None else None
+        if not want_results:
+            return None, None, J_ref
+        return hs, out, J_ref
 
     def J_pair(self, n_grid):
         """two device fp64 [n_grid] buffers to ping-pong sweeps between; with several
@@ -1278,20 +1386,33 @@ class Engine(object):
             up = [items if n_items else np.zeros(1, dtype=_cabi.ITEM_DTYPE), item_begin,
                   U_eff.astype(np.int32) if len(U_eff) else np.zeros(1, dtype=np.int32)]
             T.item_u_count_host = items["u_count"].copy() if col else None
+            T.item_order = T.run_end_ord = None
             if col:
                 T.sm_count = sm_count
-                up.append(column_segments(T.item_u_count_host, sm_count * self.COLUMN_SEGS_PER_SM))
-                T.n_segs = len(up[-1]) - 1
                 # items of one band and column are consecutive (tiles are ordered that way)
-                tile_band = np.repeat(np.arange(len(T.bands["tiles"])), np.diff(T.bands["tile_begin"]))
+                n_bands = len(T.bands["tiles"])
+                tile_band = np.repeat(np.arange(n_bands), np.diff(T.bands["tile_begin"]))
                 st_of_item = items["state"].astype(np.int64)
-                up.append(item_run_ends(tile_band[st_of_item] * n_cols_loc + T.bands["tile_col"][st_of_item]))
+                item_col = T.bands["tile_col"][st_of_item]
+                weights = T.item_u_count_host
+                if n_bands > 1:
+                    # the launch over the whole list (device-resident sweeps) walks the items column
+                    # by column, the bands of a column back to back: one table load per column
+                    order = np.argsort(item_col * n_bands + tile_band[st_of_item], kind="stable").astype(np.int64)
+                    weights = weights[order]
+                up.append(column_segments(weights, sm_count * self.COLUMN_SEGS_PER_SM))
+                T.n_segs = len(up[-1]) - 1
+                up.append(item_run_ends(tile_band[st_of_item] * n_cols_loc + item_col))
+                if n_bands > 1:
+                    up += [order, item_run_ends(item_col[order])]
             else:
                 T.n_segs, T.seg_begin, T.run_end = 0, None, None
             up = self.to_device_packed(up)
             T.items, T.item_begin, T.U_dev = up[0], up[1], up[2]
             if col:
                 T.seg_begin, T.run_end = up[3], up[4]
+                if len(up) > 5:
+                    T.item_order, T.run_end_ord = up[5], up[6]
                 ensure("col_table", n_cols_loc * _cabi.column_pitch(n_rows0, W), torch.float64)
             else:
                 T.col_table = None
@@ -1348,12 +1469,20 @@ class Engine(object):
         return T
 
     COLUMN_SEGS_PER_SM = int(os.environ.get("SDP_COLUMN_SEGS_PER_SM", "1"))
+    # launch shape of a band's sweep (SdpTables.col_launch_hint): 640 threads, round-robin - measured
+    # on config #5 with ~10 column pieces per CTA (profiles/r2_emu_variants_bands.txt): 1.256 ms
+    # against 1.346 ms for the 768-thread first-come-first-served shape that is best (1.146 against
+    # 1.180 ms) when a CTA meets 3-4 long pieces
+    BAND_LAUNCH_HINT = 640 | (1 << 16)
 
     def set_column_segments(self, T, n_ctas):
         """layout CF: re-cut the item list of built tables into `n_ctas` CTA segments
         (developer tuning, scripts/dev_column.py)"""
         assert T.column
-        seg = column_segments(T.item_u_count_host, n_ctas)
+        w = T.item_u_count_host
+        if T.item_order is not None:
+            w = w[T.item_order.cpu().numpy()]
+        seg = column_segments(w, n_ctas)
         T.seg_begin = self.to_device_packed([seg])[0]
         T.n_segs = len(seg) - 1
         T.c_tables = fill_c_tables(T)
@@ -1585,6 +1714,9 @@ class Engine(object):
                 seg_dev = self.to_device_packed([seg])[0]
                 cp = _cabi.SdpTables.from_buffer_copy(T.c_tables)
                 cp.seg_begin, cp.n_segs, cp.col_table_ready = seg_dev.data_ptr(), len(seg) - 1, 1
+                # a band is walked in the list's own order: many short column pieces per CTA
+                cp.item_order, cp.run_end = 0, T.run_end.data_ptr()
+                cp.col_launch_hint = self.BAND_LAUNCH_HINT
                 plan.append(dict(tab_p=cp, tab_f=view, s0=s0, s1=s0 + ns, keep=seg_dev,
                                  pv=ctypes.c_void_p(T.part_val.data_ptr()),
                                  pi=ctypes.c_void_p(T.part_idx.data_ptr())))
@@ -1745,6 +1877,18 @@ class Engine(object):
         torch.cuda.current_stream(self.device).synchronize()
         return [self.result_array(o) for o in outs]
 
+    def _pinned_scratch(self, n_doubles):
+        """page-locked fp64 scratch of at least `n_doubles`, kept on the engine (allocating and
+        pinning 100+ MB costs as much as copying it); None without CUDA"""
+        if not self._cuda:
+            return None
+        torch = _torch()
+        buf = getattr(self, "_pin_scratch", None)
+        if buf is None or buf.numel() < n_doubles:
+            self._pin_scratch = None
+            buf = self._pin_scratch = torch.empty(n_doubles, dtype=torch.float64, pin_memory=True)
+        return buf
+
     # -- time-dependent recursion, fast path ----------------------------------
     RECURSION_MAX_G_BYTES = 8 << 30      # per-instant stage-cost tables kept resident
 
@@ -1806,7 +1950,9 @@ class Engine(object):
                 return None
 
         # 2. the stage cost of every instant (one batched call each), checked on sample states
-        g_src = np.empty((n_T,) + g0.shape)
+        # (filled in place in page-locked memory kept between recursions: one asynchronous upload)
+        g_pin = self._pinned_scratch(n_T * g0.size)
+        g_src = (g_pin.numpy() if g_pin is not None else np.empty(n_T * g0.size)).reshape((n_T,) + g0.shape)
         k_base = t_base - t_ini
         g_src[k_base] = g0
         for k in range(n_T):
@@ -1848,7 +1994,10 @@ class Engine(object):
         g_size = g0.size
         stag_all = torch.empty(n_stag + n_T * g_size, dtype=torch.float64, device=self.device)
         stag_all[:n_stag].copy_(rec["stag_dev"])
-        stag_all[n_stag:].copy_(self.to_device(g_src.reshape(-1)))
+        if g_pin is not None:
+            stag_all[n_stag:].copy_(g_pin[:n_T * g_size], non_blocking=True)
+        else:
+            stag_all[n_stag:].copy_(self.to_device(g_src.reshape(-1)))
         desc_all = np.repeat(rec["desc"][None, :], n_T, axis=0)
         shift = n_stag + np.arange(n_T, dtype=np.int64) * g_size - rec["g_base"]
         desc_all["src"][:, :, d] += shift[:, None]

@@ -259,10 +259,28 @@ class DPSolver(object):
                 stale.append(True)
 
         n_grid = int(np.prod(state_dims))
-        J_prev, J_new = eng.J_pair(n_grid)
-        eng.begin_call(n_grid)
         root_only = self._root_only()
         is_root = eng.coll.rank == 0
+        hs = eng.host_share(n_grid, nb_control) if eng.coll.world > 1 else None
+        if hs is not None:
+            # several ranks: inputs and results through page-locked memory shared by the ranks,
+            # 1/N of each over every rank's own PCIe link (hostshare.py)
+            ref_flat = int(np.ravel_multi_index(self._state_ref_ind, state_dims)) if rel_dp else None
+            got = eng.sweep_shared(hs, T, J_next, rel_ref_index=ref_flat,
+                                   want_results=not (root_only and not is_root), while_waiting=check_cache)
+            if stale:
+                self.clear_tables()
+                return self._sweep_host(J_next, t_k, rel_dp)
+            if got is not None:
+                if got[0] is None:
+                    return None, None, None, T
+                hs_, slot, J_ref = got
+                # rank 0 may write into what it gets (the next call reads ITS array); the other
+                # ranks share the same pages and get read-only views
+                J_k, pol_k = hs_.hand_out(slot, state_dims, state_dims + (nb_control,), writable=is_root)
+                return J_k, J_ref, pol_k, T
+        J_prev, J_new = eng.J_pair(n_grid)
+        eng.begin_call(n_grid)
         if root_only:
             if is_root:
                 eng.upload_J(J_next, J_prev)

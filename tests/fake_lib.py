@@ -308,6 +308,9 @@ class FakeLib(object):
             seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
             assert 0 <= seg[0] and seg[-1] <= T.n_items and np.all(np.diff(seg) >= 0)
             assert np.all(np.diff(items["state"]) >= 0)          # ordered by tile
+            if T.item_order:
+                # an explicit walking order: a permutation of the item list
+                assert sorted(_arr(T.item_order, T.n_items, ctypes.c_int64)) == list(range(T.n_items))
             assert T.col_table and T.col_table % 16 == 0         # scratch for the column tables
             if T.col_table_ready:
                 # the caller ran the pre-pass (sdp_column_table) on this J
@@ -456,13 +459,15 @@ class FakeLib(object):
         W, Tc = T.W, T.tiles_per_col          # (tiles per column of the FIRST band)
         seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
         run_end = _arr(T.run_end, T.n_items, ctypes.c_int64)
+        # positions -> items (SdpTables.item_order), identity when absent
+        order = _arr(T.item_order, T.n_items, ctypes.c_int64) if T.item_order else np.arange(T.n_items)
         rows, stride0 = int(orders[0]), int(strides[0])
         P = W | 1
         done = np.zeros(len(items), dtype=bool)
         for b in range(T.n_segs):
             i, seg_end = int(seg[b]), int(seg[b + 1])
             while i < seg_end:
-                col = int(items[i]["Upad"])       # layout CF: the column of the item's tile
+                col = int(items[order[i]]["Upad"])       # layout CF: the column of the item's tile
                 e = min(int(run_end[i]), seg_end)
                 R = np.full(rows * P + 9, np.nan)
                 for w in range(W):
@@ -478,7 +483,7 @@ class FakeLib(object):
                         bb = rec(base + strides[k], k + 1)
                         return (1 - lw[k - 1]) * a + lw[k - 1] * bb
                     R[np.arange(rows) * P + w] = rec(np.arange(rows, dtype=np.int64) * stride0 + cw, 1)
-                for n_it in range(i, e):
+                for n_it in (int(order[pos]) for pos in range(i, e)):
                     it = items[n_it]
                     assert int(it["Upad"]) == col and not done[n_it]
                     done[n_it] = True

@@ -62,6 +62,44 @@ def check_column_layout(sdp, wl, rank):
     return bool(ok)
 
 
+def check_shared_results(sdp, wl, rank):
+    """host results through the shared page-locked segment (hostshare.py): every array handed
+    out keeps its values while it is alive - five sweeps whose results are all KEPT (the ring has
+    three slots: the later calls must fall back to private copies, not overwrite), then a loop
+    that drops them (slots recycled); rank 0's arrays are writable, the others' read-only"""
+    from conftest import rel_err
+    from oracle.ref_port import port_api
+    from stodynprog_b200.hostshare import SlotArray
+    kw = dict(steps=(0.05, 0.1))
+    sv, so = wl.storage_ar1(sdp, **kw).solver, wl.storage_ar1(port_api(), **kw).solver
+    J0 = np.random.default_rng(21).standard_normal(sv._state_grid_shape)
+    want, J = [], J0
+    for k in range(7):
+        J, pol = so.value_iteration(J)
+        want.append((J, pol))
+    ok, kept, J, shared = True, [], J0, 0
+    for k in range(5):
+        J, pol = sv.value_iteration(J, report_time=False)
+        kept.append((J, pol))
+        shared += isinstance(J, SlotArray)
+    for k, (Jk, polk) in enumerate(kept):
+        ok &= np.array_equal(polk, want[k][1]) and rel_err(Jk, want[k][0]) <= 1e-10
+    ok &= 1 <= shared < 5
+    if isinstance(kept[0][0], SlotArray):
+        ok &= kept[0][0].flags.writeable == (rank == 0)
+    del kept, pol
+    for k in range(5, 7):
+        J, pol = sv.value_iteration(J, report_time=False)
+        ok &= isinstance(J, SlotArray) and np.array_equal(pol, want[k][1]) and rel_err(J, want[k][0]) <= 1e-10
+    (Jd, Jr), pol = sv.value_iteration((want[6][0] - want[6][0][sv._state_ref_ind], 0.), rel_dp=True, report_time=False)
+    (Jdo, Jro), polo = so.value_iteration((want[6][0] - want[6][0][so._state_ref_ind], 0.), rel_dp=True)
+    ok &= np.array_equal(pol, polo) and abs(Jr - Jro) <= 1e-10 * abs(Jro) and np.max(np.abs(Jd - Jdo)) <= 1e-10 * np.max(np.abs(Jdo))
+    if rank == 0:
+        print("[shared host results] %d of 5 kept sweeps in shared slots, values intact, recycled afterwards: %s"
+              % (shared, "OK" if ok else "FAILED"), flush=True)
+    return bool(ok)
+
+
 def check_bench_grid(sdp, wl, rank, n_check=300):
     """the bench workload itself (config #5, 2000 x 500 states x <= 256 controls x 9 nodes) on all
     ranks, cut into rows and into columns: value_iteration from a random J and the device-resident
@@ -169,6 +207,7 @@ def main():
         r_expected = np.max(np.abs(G["vi_J2"] - G["vi_J1"]))
         ok &= rel_err(Js, G["vi_J2"]) <= 1e-10 and abs(info["residuals"][-1] - r_expected) <= 1e-9 * r_expected
     ok &= check_column_layout(sdp, wl, rank)
+    ok &= check_shared_results(sdp, wl, rank)
     if os.environ.get("SDP_CHECK_BENCH_GRID"):
         ok &= check_bench_grid(sdp, wl, rank)
     flag = torch.tensor([1 if ok else 0], device="cuda")

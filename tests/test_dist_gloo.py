@@ -148,3 +148,48 @@ def test_collective_uneven_slabs_world2(tmp_path):
     mp.spawn(_coll_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     for k in range(2):
         assert open(os.path.join(str(tmp_path), "ok%d" % k)).read() == "True"
+
+
+def _share_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from stodynprog_b200.engine import Collective
+        from stodynprog_b200.hostshare import HostShare
+        hs = HostShare(Collective(), n_grid=12, nc=2, cuda=False)      # (no cudaHostRegister on CPU)
+        ok = True
+        # the segment is one piece of memory: what a rank writes into its part of a slot, the
+        # others read after the flag barrier
+        a, b = 12 * rank // world, 12 * (rank + 1) // world
+        hs.slot_J(1).numpy()[a:b] = 100 * rank + np.arange(a, b)
+        hs.slot_pol(1).numpy()[2 * a:2 * b] = -rank
+        hs.publish(0, 7 + rank)
+        hs.barrier()
+        want = np.concatenate([100 * r + np.arange(12 * r // world, 12 * (r + 1) // world) for r in range(world)])
+        ok &= np.array_equal(hs.slot_J(1).numpy(), want)
+        ok &= [hs.read(r, 0) for r in range(world)] == [7 + r for r in range(world)]
+        # arrays handed out keep their slot busy until they die; views of them count
+        J, pol = hs.hand_out(1, (3, 4), (3, 4, 2), writable=rank == 0)
+        ok &= hs.slot_of(J) == 1 and hs.slot_of(np.zeros(12)) is None and hs.live_mask() == 2
+        ok &= J.flags.writeable == (rank == 0) and np.array_equal(J.reshape(-1), want)
+        row = J[1]
+        del J, pol
+        ok &= hs.live_mask() == 2
+        del row
+        ok &= hs.live_mask() == 0
+        for _ in range(50):
+            hs.barrier()
+        open(os.path.join(out_dir, "share%d" % rank), "w").write(str(bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_host_share_world2(tmp_path):
+    """the shared page-locked result segment (hostshare.py) without a GPU: mapping, flag barrier,
+    control words, slot liveness"""
+    mp.spawn(_share_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for k in range(2):
+        assert open(os.path.join(str(tmp_path), "share%d" % k)).read() == "True"
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("sdp_b200_")]
