@@ -1654,12 +1654,14 @@ class Engine(object):
                                                      self._ptr(T.part_idx), self._ptr(T.argmin),
                                                      ctypes.byref(px.peers[k_new]), sb, self.stream)
                 _cabi.check(rc, "sdp_sweep_finalize_p2p")
+            self._argmin_in_px = True
             if defer_wait and self.FOLD_WAIT and rel_ref_index is None and resid_out is None:
                 self._pending_wait = px.peers[k_new]
             else:
                 rc = self.lib.sdp_p2p_wait(ctypes.byref(px.peers[k_new]), self.stream)
                 _cabi.check(rc, "sdp_p2p_wait")
         else:
+            self._argmin_in_px = False
             self.sweep_local(T, J_prev, events)
             if self.coll.world == 1:
                 J_new.copy_(T.J_out[:n])
@@ -1812,7 +1814,14 @@ class Engine(object):
         return self.result_array(J_pin), self.result_array(pol_pin)
 
     def gather_argmin(self, T):
-        """full-grid int32 argmin (device), gathered over ranks"""
+        """full-grid int32 argmin (device) of the last sweep.  With the peer-memory exchange every
+        rank already holds it (the combine kernel stores the argmin next to J, SdpPeers.A): valid
+        until the next sweep; otherwise gathered over the ranks"""
+        if self.coll.world > 1 and T.host_full is not None:
+            px = self._peer.get(int(T.host_full.lo.shape[0]))
+            if px is not None and getattr(self, "_argmin_in_px", False):
+                self.flush_exchange()
+                return px.argmin
         if T.col_bounds is not None:
             return self.coll.all_gather_indexed(T.argmin[:T.n_states], T.gather_maxc, T.gather_index)
         return self.coll.all_gather_slabs(T.argmin[:T.n_states], T.bounds)

@@ -73,27 +73,61 @@ def check_shared_results(sdp, wl, rank):
     kw = dict(steps=(0.05, 0.1))
     sv, so = wl.storage_ar1(sdp, **kw).solver, wl.storage_ar1(port_api(), **kw).solver
     J0 = np.random.default_rng(21).standard_normal(sv._state_grid_shape)
-    want, J = [], J0
-    for k in range(7):
-        J, pol = so.value_iteration(J)
-        want.append((J, pol))
-    ok, kept, J, shared = True, [], J0, 0
+    kept, J, shared, fails = [], J0, 0, []
+
+    def same_policy(J_in, pol_gpu, pol_port, what):
+        """policies equal, or - counted and printed - different only where the port's own values
+        of the two controls are tied to the last bits (the order of the expectation sum differs
+        between np.inner and the kernel: north_star's 'exact ties counted and reported')"""
+        bad = np.argwhere(np.any(pol_gpu != pol_port, axis=-1))
+        if len(bad) == 0:
+            return True
+        Ji = so.interp_on_state(np.array(J_in))
+        worst = 0.0
+        for idx in bad:
+            x_k = tuple(g[i] for g, i in zip(so.state_grid, idx))
+            grids, dims = so.control_grids(x_k)
+            _, _, flat, Jall = so.value_at_state(x_k, Ji, None, True)
+            u_idx = tuple(int(np.argmin(np.abs(grids[c] - pol_gpu[tuple(idx)][c]))) for c in range(len(grids)))
+            gap = abs(float(Jall[u_idx]) - float(Jall.reshape(-1)[flat])) / max(abs(float(Jall.reshape(-1)[flat])), 1e-300)
+            worst = max(worst, gap)
+        if rank == 0:
+            print("[shared host results] %s: %d states with another control, tied within %.1e (relative)"
+                  % (what, len(bad), worst), flush=True)
+        return worst <= 1e-13
+
+    def need(cond, what):
+        if not cond:
+            fails.append(what)
     for k in range(5):
         J, pol = sv.value_iteration(J, report_time=False)
         kept.append((J, pol))
         shared += isinstance(J, SlotArray)
+    # (every sweep is checked against the port fed with the SAME input array, so that a
+    # near-tie cannot be broken differently because of a last-bit difference in J)
+    want = [so.value_iteration(np.array(J0 if k == 0 else kept[k - 1][0])) for k in range(5)]
     for k, (Jk, polk) in enumerate(kept):
-        ok &= np.array_equal(polk, want[k][1]) and rel_err(Jk, want[k][0]) <= 1e-10
-    ok &= 1 <= shared < 5
+        need(same_policy(J0 if k == 0 else kept[k - 1][0], polk, want[k][1], "kept sweep %d" % k), "kept policy %d" % k)
+        need(rel_err(Jk, want[k][0]) <= 1e-10, "kept J %d (%.2e)" % (k, rel_err(Jk, want[k][0])))
+    need(1 <= shared < 5, "%d of 5 kept results in shared slots" % shared)
     if isinstance(kept[0][0], SlotArray):
-        ok &= kept[0][0].flags.writeable == (rank == 0)
-    del kept, pol
+        need(kept[0][0].flags.writeable == (rank == 0), "writeable flag")
+    del kept, pol, Jk, polk
     for k in range(5, 7):
+        J_in = np.array(J)
+        Jo, polo = so.value_iteration(J_in.copy())
         J, pol = sv.value_iteration(J, report_time=False)
-        ok &= isinstance(J, SlotArray) and np.array_equal(pol, want[k][1]) and rel_err(J, want[k][0]) <= 1e-10
-    (Jd, Jr), pol = sv.value_iteration((want[6][0] - want[6][0][sv._state_ref_ind], 0.), rel_dp=True, report_time=False)
-    (Jdo, Jro), polo = so.value_iteration((want[6][0] - want[6][0][so._state_ref_ind], 0.), rel_dp=True)
-    ok &= np.array_equal(pol, polo) and abs(Jr - Jro) <= 1e-10 * abs(Jro) and np.max(np.abs(Jd - Jdo)) <= 1e-10 * np.max(np.abs(Jdo))
+        need(isinstance(J, SlotArray), "recycled slot %d" % k)
+        need(same_policy(J_in, pol, polo, "sweep %d" % k) and rel_err(J, Jo) <= 1e-10, "values after recycling %d" % k)
+    J_in = np.array(J) - J[sv._state_ref_ind]
+    (Jd, Jr), pol = sv.value_iteration((J_in, 0.), rel_dp=True, report_time=False)
+    (Jdo, Jro), polo = so.value_iteration((J_in.copy(), 0.), rel_dp=True)
+    need(same_policy(J_in, pol, polo, "relative DP"), "relative DP policy")
+    need(abs(Jr - Jro) <= 1e-10 * abs(Jro), "relative DP J_ref %r vs %r" % (Jr, Jro))
+    need(np.max(np.abs(Jd - Jdo)) <= 1e-10 * np.max(np.abs(Jdo)), "relative DP J")
+    ok = not fails
+    if fails:
+        print("[shared host results] rank %d: %s" % (rank, "; ".join(fails)), flush=True)
     if rank == 0:
         print("[shared host results] %d of 5 kept sweeps in shared slots, values intact, recycled afterwards: %s"
               % (shared, "OK" if ok else "FAILED"), flush=True)
