@@ -301,7 +301,8 @@ def time_sweeps(eng, T, J_prev, J_new, K, barrier):
     for k in range(K):
         # a device-resident iteration: between two sweeps the arrival of the peers' J slabs is
         # awaited by the next sweep's first kernel; the last wait is inside the timed region
-        eng.sweep(T, J_prev, J_new, events=kev[k], defer_wait=True)
+        # (the policy of an intermediate sweep is read by nobody: only the last one sends its argmin)
+        eng.sweep(T, J_prev, J_new, events=kev[k], defer_wait=True, want_argmin=(k == K - 1))
         J_prev, J_new = J_new, J_prev
     eng.flush_exchange()
     end.record()

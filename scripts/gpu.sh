@@ -45,13 +45,24 @@ for STEP in "$@"; do
       ( time timeout 900 python scripts/dev_shard_emulation.py $(echo ${ARGS:-8} | tr ',' ' ') ) > $OUT/${TAG}_shard_emulation.txt 2>&1
       cat $OUT/${TAG}_shard_emulation.txt ;;
     ncu)
-      W=${ARGS:-large}
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -c 3 -f \
-          -o $OUT/${TAG}_ncu_$W python scripts/ncu_target.py $W on 3 > $OUT/${TAG}_ncu_$W.log 2>&1
+      # ncu:NAME[:ENV=V,ENV=V]  NAME in large (default tables of config #5), shard8 (one rank of eight),
+      # largedense, ar1, ar1dense.  Full-set capture of every kernel of one sweep + a launch list.
+      W=${ARGS%% *}; W=${W:-large}
+      case $W in
+        large)      TGT="large on 3";  ENVS="" ;;
+        large1band) TGT="large on 3";  ENVS="BANDS=1" ;;
+        shard8)     TGT="large on 3";  ENVS="COL_SHARD=3/8" ;;
+        largedense) TGT="large off 3"; ENVS="" ;;
+        ar1)        TGT="ar1 on 3";    ENVS="" ;;
+        ar1dense)   TGT="ar1 off 3";   ENVS="" ;;
+      esac
+      env $ENVS timeout 900 ncu --set full --clock-control none --import-source on \
+          -k regex:'k_sweep|k_column_table|k_combine' --launch-skip ${NCU_SKIP:-6} -c ${NCU_COUNT:-6} -f \
+          -o $OUT/${TAG}_ncu_$W python scripts/ncu_target.py $TGT > $OUT/${TAG}_ncu_$W.log 2>&1
       ncu -i $OUT/${TAG}_ncu_$W.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/${TAG}_ncu_$W.txt
-      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-          --log-file $OUT/${TAG}_launches_$W.csv python scripts/ncu_target.py $W on 3 >> $OUT/${TAG}_ncu_$W.log 2>&1
-      tail -40 $OUT/${TAG}_ncu_$W.txt ;;
+      env $ENVS timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+          --log-file $OUT/${TAG}_launches_$W.csv python scripts/ncu_target.py $TGT >> $OUT/${TAG}_ncu_$W.log 2>&1
+      grep "== kernel\|gpu__time_duration\|dram__bytes_read.sum \|wavefronts.avg.pct\|fp64_cycles_active.avg.pct_of_peak_sustained_elapsed\|issue_active" $OUT/${TAG}_ncu_$W.txt | head -40 ;;
     sanitize)
       for TOOL in ${SAN_TOOLS:-memcheck racecheck}; do
         L=$OUT/${TAG}_sanitizer_${TOOL}_n$N.log

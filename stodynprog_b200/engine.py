@@ -405,16 +405,18 @@ class PeerExchange(object):
         aptrs = [int(p) for p in self.ahdl.buffer_ptrs]
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.peers = []
-        for k in range(2):
-            P = _cabi.SdpPeers()
-            P.world, P.rank = world, rank
-            for r in range(world):
-                P.J[r] = ptrs[r] + 8 * k * n_pad
-                P.flags[r] = ptrs[r] + 8 * 2 * n_pad
-                P.A[r] = aptrs[r]
-            P.epoch = self.local.data_ptr()
-            P.done = self.local.data_ptr() + 8
-            self.peers.append(P)
+        self.peers_J_only = []      # the same exchanges without the argmin (sweeps of a device-resident loop)
+        for with_argmin in (True, False):
+            for k in range(2):
+                P = _cabi.SdpPeers()
+                P.world, P.rank = world, rank
+                for r in range(world):
+                    P.J[r] = ptrs[r] + 8 * k * n_pad
+                    P.flags[r] = ptrs[r] + 8 * 2 * n_pad
+                    P.A[r] = aptrs[r] if with_argmin else None
+                P.epoch = self.local.data_ptr()
+                P.done = self.local.data_ptr() + 8
+                (self.peers if with_argmin else self.peers_J_only).append(P)
 
     def peer_view(self, r, k):
         """rank r's copy of J buffer k as a tensor on this device (peer-mapped)"""
@@ -1611,13 +1613,16 @@ class Engine(object):
             _cabi.check(rc, "sdp_p2p_wait")
 
     def sweep(self, T, J_prev, J_new, rel_ref_index=None, ref_out=None, resid_out=None,
-              events=None, defer_wait=False):
+              events=None, defer_wait=False, want_argmin=True):
         """One full Bellman sweep: K1 on the slab, all-gather of the J slab into
         J_new (device fp64 [n_grid]), optional relative-DP shift and optional
         sup-norm residual max|J_new - J_prev| (all-reduced).
         `defer_wait`: the caller's next use of J_new is another sweep (or it calls
         flush_exchange() itself): the arrival of the peers' slabs is then awaited by that
-        sweep's first kernel."""
+        sweep's first kernel.
+        `want_argmin` False: an intermediate sweep of a device-resident loop, whose policy
+        nobody reads - the combine kernel then sends J alone to the peers (the shard's own
+        argmin is still written; gather_argmin falls back to collecting those)."""
         n = T.n_states
         sb = T.state_begin
         px = self._peer.get(J_new.numel()) if self.coll.world > 1 else None
@@ -1644,17 +1649,18 @@ class Engine(object):
                 _cabi.check(rc, "sdp_sweep_partials")
             if events is not None:
                 events[1].record(self.torch_stream)
+            P_out = px.peers[k_new] if want_argmin else px.peers_J_only[k_new]
             if T.col_bounds is not None:
                 rc = self.lib.sdp_sweep_finalize_p2p_cols(
                     ctypes.byref(T.c_tables), self._ptr(T.part_val), self._ptr(T.part_idx), self._ptr(T.argmin),
-                    ctypes.byref(px.peers[k_new]), T.col_bounds[-1], T.col_bounds[self.coll.rank], self.stream)
+                    ctypes.byref(P_out), T.col_bounds[-1], T.col_bounds[self.coll.rank], self.stream)
                 _cabi.check(rc, "sdp_sweep_finalize_p2p_cols")
             else:
                 rc = self.lib.sdp_sweep_finalize_p2p(ctypes.byref(T.c_tables), self._ptr(T.part_val),
                                                      self._ptr(T.part_idx), self._ptr(T.argmin),
-                                                     ctypes.byref(px.peers[k_new]), sb, self.stream)
+                                                     ctypes.byref(P_out), sb, self.stream)
                 _cabi.check(rc, "sdp_sweep_finalize_p2p")
-            self._argmin_in_px = True
+            self._argmin_in_px = bool(want_argmin)
             if defer_wait and self.FOLD_WAIT and rel_ref_index is None and resid_out is None:
                 self._pending_wait = px.peers[k_new]
             else:

@@ -514,7 +514,8 @@ class DPSolver(object):
             # (between two sweeps the arrival of the peers' slabs is awaited by the next sweep's
             # first kernel; relative DP and the residual read J right away and wait themselves)
             eng.sweep(T, J_prev, J_new, rel_ref_index=ref_flat, ref_out=ref_out,
-                      resid_out=resid if tol is not None else None, defer_wait=k + 1 < max_iter)
+                      resid_out=resid if tol is not None else None, defer_wait=k + 1 < max_iter,
+                      want_argmin=(tol is not None or k + 1 == max_iter))
             J_prev, J_new = J_new, J_prev
             n_done += 1
             if tol is not None and (k + 1) % check_every == 0:
