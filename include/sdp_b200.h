@@ -120,7 +120,8 @@ typedef struct SdpItem {
 #define SDP_LAYOUT_COLUMN_FACTORED 4
 /* doubles per column table: order[0] rows of (W|1) doubles + 9 of slack, rounded up to even */
 #define SDP_COLUMN_PITCH(rows, W) ((((int64_t)(rows) * ((W) | 1)) + 9 + 1) & ~(int64_t)1)
-#define SDP_COLUMN_MAX_SMEM_BYTES (200 * 1024) /* CF: 8 * SDP_COLUMN_PITCH(order[0], W) must fit */
+#define SDP_COLUMN_PITCH2(rows, W) ((((int64_t)(rows) * ((W) | 1)) + ((rows) >> 1) + 10 + 1) & ~(int64_t)1) /* col_pairs */
+#define SDP_COLUMN_MAX_SMEM_BYTES (200 * 1024) /* CF: 8 * SDP_COLUMN_PITCH[2](order[0], W) must fit */
 
 /* Dense sweep tables of one shard of states (device pointers).
  *
@@ -171,7 +172,7 @@ typedef struct SdpTables {
     const int32_t* U;    /* [n_states] admissible controls per state (layout B masking) */
     /* factored layouts only */
     int32_t u_mask;        /* bit k set: coordinate k depends on (x,u) only; clear: on (x,w) only */
-    int32_t reserved;
+    int32_t col_pairs;     /* layout CF: 1 = two rows per lane (see pos_row below), 0 = one */
     const int32_t* cell_w;
     const double* lam_w;
     int64_t lam_w_plane;
@@ -213,6 +214,19 @@ typedef struct SdpTables {
      * item indices.  Lets a device-resident sweep visit the bands of a column back to back (one
      * table load per column) while the tables stay ordered band by band for the combine. */
     const int64_t* item_order;
+    /* Layout CF with col_pairs = 1 ("two rows per lane").  A lane of the streaming pass then owns
+     * the positions 2j, 2j+1 of a tile: two rows of the column that are neighbours on axis 0, so
+     * that the table rows their backups read overlap - R[q], R[q+1] and R[q'], R[q'+1] with
+     * q' in {q, q+1} - and 3 shared-memory reads serve 2 backups (anything else is handled, with
+     * a 4th read).  Positions are no longer rows: the caller pairs rows as it sees fit (rows
+     * with the same control grid size) and pads, `pos_row[p]` = row of the band held by position
+     * p of EVERY column, -1 on padding; tiles per column is even, the two tiles of a pair are
+     * cut into the same runs of controls, and the streaming pass walks `item_order` (required),
+     * which lists the items of the FIRST tile of every pair only: item.g_base of such an item is
+     * the index of the same run in the second tile.  The column tables are swizzled: row q at
+     * q*(W|1) + (q >> 1), SDP_COLUMN_PITCH2 doubles per column.
+     * Combine pass: pos_row advanced to the band's first position. */
+    const int32_t* pos_row;
 } SdpTables;
 
 /* ABI / build identification. */

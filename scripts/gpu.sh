@@ -57,7 +57,7 @@ for STEP in "$@"; do
         ar1dense)   TGT="ar1 off 3";   ENVS="" ;;
       esac
       env $ENVS timeout 900 ncu --set full --clock-control none --import-source on \
-          -k regex:'k_sweep|k_column_table|k_combine' --launch-skip ${NCU_SKIP:-6} -c ${NCU_COUNT:-6} -f \
+          -k regex:'k_sweep|k_column_table|k_combine' --launch-skip ${NCU_SKIP:-2} -c ${NCU_COUNT:-4} -f \
           -o $OUT/${TAG}_ncu_$W python scripts/ncu_target.py $TGT > $OUT/${TAG}_ncu_$W.log 2>&1
       ncu -i $OUT/${TAG}_ncu_$W.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/${TAG}_ncu_$W.txt
       env $ENVS timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \

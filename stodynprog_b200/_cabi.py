@@ -21,8 +21,10 @@ LAYOUT_COLUMN_FACTORED = 4          # "CF": BF tables over column-major tiles, i
 COLUMN_MAX_SMEM_BYTES = 200 * 1024  # CF: 8 * column_pitch(order[0], W) bytes of shared memory per CTA
 
 
-def column_pitch(rows, W):
-    """SDP_COLUMN_PITCH: doubles per column table of layout CF"""
+def column_pitch(rows, W, pairs=False):
+    """SDP_COLUMN_PITCH / SDP_COLUMN_PITCH2: doubles per column table of layout CF"""
+    if pairs:
+        return (rows * (W | 1) + (rows >> 1) + 10 + 1) & ~1
     return (rows * (W | 1) + 9 + 1) & ~1
 
 
@@ -61,7 +63,7 @@ class SdpTables(ctypes.Structure):
                 ("n_states", ctypes.c_int64),
                 ("U", ctypes.c_void_p),
                 ("u_mask", ctypes.c_int32),
-                ("reserved", ctypes.c_int32),
+                ("col_pairs", ctypes.c_int32),
                 ("cell_w", ctypes.c_void_p),
                 ("lam_w", ctypes.c_void_p),
                 ("lam_w_plane", ctypes.c_int64),
@@ -74,7 +76,8 @@ class SdpTables(ctypes.Structure):
                 ("run_end", ctypes.c_void_p),
                 ("col_table_ready", ctypes.c_int32),
                 ("col_launch_hint", ctypes.c_int32),
-                ("item_order", ctypes.c_void_p)]
+                ("item_order", ctypes.c_void_p),
+                ("pos_row", ctypes.c_void_p)]
 
 
 SDP_MAX_PEERS = 8

@@ -1874,8 +1874,17 @@ k_column_table(GridT<double> G, SdpTables T, const double* __restrict__ Jprev, i
     const int nr = min(TR, rows - r0);
     for (int lc = threadIdx.x >> 5; lc < 32; lc += blockDim.x >> 5) {
         if (c0 + lc >= T.n_cols) break;
-        double* dst = T.col_table + (int64_t)(c0 + lc) * pitch + (int64_t)r0 * P;
-        for (int k = threadIdx.x & 31; k < nr * P; k += 32) dst[k] = tile[lc * CP + k];
+        if (T.col_pairs) {
+            // two rows per lane: row q at q*P + (q >> 1) (see k_sweep_fact_column2)
+            double* dstc = T.col_table + (int64_t)(c0 + lc) * pitch;
+            for (int k = threadIdx.x & 31; k < nr * P; k += 32) {
+                const int lr = k / P, w = k - lr * P, r = r0 + lr;
+                dstc[r * P + (r >> 1) + w] = tile[lc * CP + k];
+            }
+        } else {
+            double* dst = T.col_table + (int64_t)(c0 + lc) * pitch + (int64_t)r0 * P;
+            for (int k = threadIdx.x & 31; k < nr * P; k += 32) dst[k] = tile[lc * CP + k];
+        }
     }
 }
 
@@ -1885,7 +1894,7 @@ static int launch_column_table(const GridT<double>& G, const SdpTables& T, const
     const int P = T.W | 1;
     const size_t tshm = (size_t)32 * (SDP_CT_ROWS * P + 1) * 8 + (size_t)NW * 32 * T.W * 8 + (size_t)32 * T.W * 4;
     dim3 grid((unsigned)((T.n_cols + 31) / 32), (unsigned)((G.order[0] + SDP_CT_ROWS - 1) / SDP_CT_ROWS));
-    const int64_t pitch = SDP_COLUMN_PITCH(G.order[0], T.W);
+    const int64_t pitch = T.col_pairs ? SDP_COLUMN_PITCH2(G.order[0], T.W) : SDP_COLUMN_PITCH(G.order[0], T.W);
     if (g_wait_peers) {
         // the flag wait of the previous exchange rides in this kernel (sdp_sweep_partials_after)
         const PeersDev P2 = *g_wait_peers;
@@ -2117,6 +2126,213 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
     return SDP_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Layout CF, two rows per lane (SdpTables.col_pairs).  ncu on k_sweep_fact_column: shared-memory
+// wavefronts at 88 % of the pipe - 16 bytes of table per backup, R[q][w] and R[q+1][w] - with the
+// fp64 pipe at 61 %.  Two rows of a column that are neighbours on axis 0 and have the same
+// control grid land, for the same control, in the same or in neighbouring table rows
+// (E' = E + P*dt: q' - q in {0, 1}), so a lane that owns both reads R[q], R[q+1], R[q'+1]: 3
+// reads for 2 backups, 12 bytes per backup.  Lane l of a warp owns the positions 2j, 2j+1
+// (j = l & 15) of the first (l < 16) or the second tile of a PAIR of tiles of the column; the
+// u-part streams as int2 / double2.  Any other q' - q costs the warp a 4th read for that control.
+// The table is swizzled, row q at q*P + (q >> 1): a lane step of two rows is then an odd number
+// of doubles (2P + 1) and a half-warp's 8-byte reads still cover all 32 banks.
+// Same operations per backup, in the same order, as every other layout: bit-identical.
+// ---------------------------------------------------------------------------
+template <int D, int WM, bool FULL, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+k_sweep_fact_column2(GridT<double> G, SdpTables T, double* __restrict__ part_val,
+                     int32_t* __restrict__ part_idx, double inv_stride0, PVals PV, int64_t pitch, int dynamic) {
+    extern __shared__ __align__(128) unsigned char csm[];
+    __shared__ int next_item;
+    __shared__ __align__(8) uint64_t tbar;
+    double* R_sh = reinterpret_cast<double*>(csm);
+    uint32_t tphase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&tbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int W = T.W;
+    const int P = W | 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int half = lane >> 4, j2 = (lane & 15) * 2;
+
+    int64_t i = T.seg_begin[blockIdx.x];
+    const int64_t seg_end = T.seg_begin[blockIdx.x + 1];
+    while (i < seg_end) {
+        const int col = T.items[T.item_order[i]].Upad;
+        const int64_t run_end = T.run_end[i];
+        const int64_t e = run_end < seg_end ? run_end : seg_end;
+        __syncthreads();                 // the previous column's readers are done with R
+        if (threadIdx.x == 0) {
+            next_item = 0;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(T.col_table + (int64_t)col * pitch);
+            const uint32_t bytes = (uint32_t)(pitch * 8);
+            const uint32_t bar = smem_u32(&tbar);
+            mbar_expect_tx(bar, bytes);
+            for (uint32_t o = 0; o < bytes; o += 32768u)
+                bulk_g2s(smem_u32(csm + o), src + o, min(32768u, bytes - o), bar);
+        }
+        mbar_wait(smem_u32(&tbar), tphase);
+        tphase ^= 1u;
+        __syncthreads();
+
+        for (int round = 0;; ++round) {
+            int k = round * nwarps + warp;
+            if (dynamic) {
+                if (lane == 0) k = atomicAdd(&next_item, 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+            }
+            const int64_t pos = i + k;
+            if (pos >= e) break;
+            const int64_t idA = T.item_order[pos];
+            const SdpItem itA = T.items[idA];
+            const int64_t idB = itA.g_base;           // the same run of controls in the pair's second tile
+            const bool live = !half || idB >= 0;
+            const int64_t my_id = (half && idB >= 0) ? idB : idA;
+            int64_t ebase = itA.entry_base;
+            int tile = itA.state;
+            if (half && idB >= 0) {
+                ebase = T.items[idB].entry_base;
+                tile = T.items[idB].state;
+            }
+            int Us0 = 0, Us1 = 0;
+            if (live) {
+                const int2 uu = *reinterpret_cast<const int2*>(T.U + (int64_t)tile * 32 + j2);
+                Us0 = uu.x;
+                Us1 = uu.y;
+            }
+            // control u of the tile: entries ebase + u*32 + position
+            const int2* __restrict__ cup = reinterpret_cast<const int2*>(T.cell + ebase + j2);
+            const double2* __restrict__ lup = reinterpret_cast<const double2*>(T.lam + ebase + j2);
+            const double2* __restrict__ gp = reinterpret_cast<const double2*>(T.g + ebase + j2);
+            const int cnt = itA.u_count, last = cnt - 1;
+            double bv0 = CUDART_INF, bv1 = CUDART_INF;
+            int bi0 = INT_MAX, bi1 = INT_MAX;
+
+            int2 c_n[2];
+            double2 l_n[2], g_n[2];
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int o = min(s2, last) * 16;
+                c_n[s2] = __ldcs(cup + o);
+                l_n[s2] = __ldcs(lup + o);
+                g_n[s2] = __ldcs(gp + o);
+            }
+            for (int uu0 = 0; uu0 < cnt; uu0 += 2) {
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int uu = uu0 + s2;
+                    if (uu < cnt) {                         // warp-uniform
+                        const int2 c = c_n[s2];
+                        const double2 l = l_n[s2], g = g_n[s2];
+                        if (uu + 2 < cnt) {
+                            const int o = min(uu + 2, last) * 16;
+                            c_n[s2] = __ldcs(cup + o);
+                            l_n[s2] = __ldcs(lup + o);
+                            g_n[s2] = __ldcs(gp + o);
+                        }
+                        const int qa = __double2int_rn(__dmul_rn((double)c.x, inv_stride0));
+                        const int qb = __double2int_rn(__dmul_rn((double)c.y, inv_stride0));
+                        const int dq = qb - qa;
+                        const double* __restrict__ Ra0 = R_sh + qa * P + (qa >> 1);
+                        const double* __restrict__ Ra1 = R_sh + (qa + 1) * P + ((qa + 1) >> 1);
+                        const double* __restrict__ Rb1 = R_sh + (qb + 1) * P + ((qb + 1) >> 1);
+                        const double oma = sub_(1.0, l.x), omb = sub_(1.0, l.y);
+                        double acc0 = 0.0, acc1 = 0.0;
+                        if (__any_sync(0xffffffffu, (unsigned)dq > 1u)) {
+                            // rows that are no neighbours in the table: four reads
+                            const double* __restrict__ Rb0 = R_sh + qb * P + (qb >> 1);
+#pragma unroll
+                            for (int w = 0; w < WM; ++w) {
+                                const double va = add_(mul_(oma, Ra0[w]), mul_(l.x, Ra1[w]));
+                                const double vb = add_(mul_(omb, Rb0[w]), mul_(l.y, Rb1[w]));
+                                const double ja = add_(g.x, va), jb = add_(g.y, vb);
+                                const double na = T.expect ? add_(acc0, mul_(ja, PV.v[w])) : ja;
+                                const double nb = T.expect ? add_(acc1, mul_(jb, PV.v[w])) : jb;
+                                acc0 = (FULL || w < W) ? na : acc0;
+                                acc1 = (FULL || w < W) ? nb : acc1;
+                            }
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < WM; ++w) {
+                                const double x0 = Ra0[w], x1 = Ra1[w], x2 = Rb1[w];
+                                const double y0 = dq ? x1 : x0;           // R[qb][w]
+                                const double va = add_(mul_(oma, x0), mul_(l.x, x1));
+                                const double vb = add_(mul_(omb, y0), mul_(l.y, x2));
+                                const double ja = add_(g.x, va), jb = add_(g.y, vb);
+                                const double na = T.expect ? add_(acc0, mul_(ja, PV.v[w])) : ja;
+                                const double nb = T.expect ? add_(acc1, mul_(jb, PV.v[w])) : jb;
+                                acc0 = (FULL || w < W) ? na : acc0;
+                                acc1 = (FULL || w < W) ? nb : acc1;
+                            }
+                        }
+                        const int u = itA.u_begin + uu;
+                        if (u < Us0 && better(acc0, u, bv0, bi0)) { bv0 = acc0; bi0 = u; }
+                        if (u < Us1 && better(acc1, u, bv1, bi1)) { bv1 = acc1; bi1 = u; }
+                    }
+                }
+            }
+            if (live) {
+                *reinterpret_cast<double2*>(part_val + my_id * 32 + j2) = make_double2(bv0, bv1);
+                *reinterpret_cast<int2*>(part_idx + my_id * 32 + j2) = make_int2(bi0, bi1);
+            }
+        }
+        i = e;
+    }
+}
+
+template <int D, int WM, int MAXT>
+static int launch_fact_column2_k(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                                 double* part_val, int32_t* part_idx, cudaStream_t st, int threads) {
+    const int64_t pitch = SDP_COLUMN_PITCH2(G.order[0], T.W);
+    const size_t shm = (size_t)pitch * 8;
+    if (shm > SDP_COLUMN_MAX_SMEM_BYTES)
+        return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF: the column table does not fit shared memory");
+    if (!T.item_order || !T.pos_row)
+        return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF with col_pairs needs item_order and pos_row");
+    if (!T.col_table_ready) {
+        int rc = launch_column_table<D>(G, T, Jprev, st);
+        if (rc) return rc;
+    }
+    static size_t attr_set = 0;          // per instantiation
+    if (attr_set < shm) {
+        cudaError_t e = cudaFuncSetAttribute(k_sweep_fact_column2<D, WM, true, MAXT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_sweep_fact_column2<D, WM, false, MAXT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e != cudaSuccess) return fail(SDP_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = shm;
+    }
+    PVals pv;
+    for (int w = 0; w < SDP_FACTORED_MAX_W_REG; ++w)
+        pv.v[w] = (w < T.W) ? (T.expect ? T.p_host[w] : 1.0) : 0.0;
+    const double inv0 = 1.0 / (double)G.stride[0];
+    const int dynamic = (T.col_launch_hint & 0xffff) ? !((T.col_launch_hint >> 16) & 1) : tuning().col_dynamic;
+    if (T.W == WM)
+        k_sweep_fact_column2<D, WM, true, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
+            G, T, part_val, part_idx, inv0, pv, pitch, dynamic);
+    else
+        k_sweep_fact_column2<D, WM, false, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
+            G, T, part_val, part_idx, inv0, pv, pitch, dynamic);
+    note_kernel("%sk_sweep_fact_column2<%d,%d,%s,%d> [%d CTAs x %d threads]",
+                !T.col_table_ready ? "k_column_table + " : "", D, WM, T.W == WM ? "true" : "false", MAXT,
+                (int)T.n_segs, threads);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+template <int D, int WM>
+static int launch_fact_column2_w(const GridT<double>& G, const SdpTables& T, const double* Jprev,
+                                 double* part_val, int32_t* part_idx, cudaStream_t st) {
+    const int hint_threads = T.col_launch_hint & 0xffff;
+    const int threads = hint_threads ? clampi(hint_threads, 128, 768) / 32 * 32 : tuning().col_threads;
+    if (threads > 640) return launch_fact_column2_k<D, WM, 768>(G, T, Jprev, part_val, part_idx, st, threads);
+    return launch_fact_column2_k<D, WM, 640>(G, T, Jprev, part_val, part_idx, st, threads);
+}
+
 template <int D, int WM>
 static int launch_fact_column_w(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                                 double* part_val, int32_t* part_idx, cudaStream_t st) {
@@ -2144,6 +2360,13 @@ static int launch_fact_column_w(const GridT<double>& G, const SdpTables& T, cons
 template <int D>
 static int launch_fact_column(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                               double* part_val, int32_t* part_idx, cudaStream_t st) {
+    if (T.col_pairs) {
+        if (tuning().col_prepass != 2)
+            return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF with col_pairs needs col_prepass = 2");
+        if (T.W <= 3) return launch_fact_column2_w<D, 3>(G, T, Jprev, part_val, part_idx, st);
+        if (T.W <= 5) return launch_fact_column2_w<D, 5>(G, T, Jprev, part_val, part_idx, st);
+        return launch_fact_column2_w<D, 9>(G, T, Jprev, part_val, part_idx, st);
+    }
     if (T.W <= 3) return launch_fact_column_w<D, 3>(G, T, Jprev, part_val, part_idx, st);
     if (T.W <= 5) return launch_fact_column_w<D, 5>(G, T, Jprev, part_val, part_idx, st);
     return launch_fact_column_w<D, 9>(G, T, Jprev, part_val, part_idx, st);
@@ -2248,7 +2471,8 @@ static int check_column_stream(const SdpTables& T, const char* who) {
 }
 // layout CF, combine pass: the view must be one band (whole rows, 32 per tile of a column)
 static int check_column_band(const SdpTables& T, const char* who) {
-    if ((T.n_states / T.n_cols + 31) / 32 != T.tiles_per_col)
+    if (T.pos_row ? (T.n_states / T.n_cols > (int64_t)T.tiles_per_col * 32)
+                  : ((T.n_states / T.n_cols + 31) / 32 != T.tiles_per_col))
         return fail(SDP_EINVAL, "%s: layout CF: the combine pass takes one band of rows at a time", who);
     return SDP_OK;
 }
@@ -2330,7 +2554,7 @@ extern "C" int sdp_column_table(const SdpGrid* grid, const SdpTables* tab, const
     if (!rc) rc = check_column_stream(T, "sdp_column_table");
     if (rc) return rc;
     if (!J_prev) return fail(SDP_EINVAL, "%s", "sdp_column_table: NULL pointer");
-    if (SDP_COLUMN_PITCH(G.order[0], T.W) * 8 > SDP_COLUMN_MAX_SMEM_BYTES)
+    if ((T.col_pairs ? SDP_COLUMN_PITCH2(G.order[0], T.W) : SDP_COLUMN_PITCH(G.order[0], T.W)) * 8 > SDP_COLUMN_MAX_SMEM_BYTES)
         return fail(SDP_EINVAL, "%s", "sdp_column_table: the column table does not fit shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     return grid->d == 2 ? launch_column_table<2>(G, T, J_prev, st) : launch_column_table<3>(G, T, J_prev, st);
@@ -2477,7 +2701,8 @@ __global__ void __launch_bounds__(1024)
 k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
                  const int64_t* __restrict__ item_begin, const double* __restrict__ part_val,
                  const int32_t* __restrict__ part_idx, double* __restrict__ J_out,
-                 int32_t* __restrict__ argmin_out, PeersDev P, int64_t j_offset, int64_t j_pitch, int dbg) {
+                 int32_t* __restrict__ argmin_out, PeersDev P, int64_t j_offset, int64_t j_pitch, int dbg,
+                 const int32_t* __restrict__ pos_row) {
     __shared__ double v_sh[32][33];
     __shared__ int i_sh[32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2500,8 +2725,9 @@ k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
     }
     __syncthreads();
     if (n_rows > 0) {
-        const int r = ty * 32 + warp, c = c0 + lane;
-        if (r < n_rows && c < n_cols) {
+        // (two rows per lane: position ty*32 + warp of the column holds row pos_row[...], -1 = padding)
+        const int r = pos_row ? pos_row[ty * 32 + warp] : ty * 32 + warp, c = c0 + lane;
+        if (r >= 0 && r < n_rows && c < n_cols) {
             const double bv = v_sh[warp][lane];
             argmin_out[(int64_t)r * n_cols + c] = i_sh[warp][lane];
             const int64_t g = j_offset + (int64_t)r * j_pitch + c;
@@ -2531,11 +2757,11 @@ static void launch_combine_column(const SdpTables& T, const double* part_val, co
                                   int64_t j_offset, int64_t j_pitch, cudaStream_t st) {
     const int n_rows = T.n_cols > 0 ? (int)(T.n_states / T.n_cols) : 0;
     const int col_blocks = T.n_cols > 0 ? (T.n_cols + 31) / 32 : 1;
-    unsigned blocks = (unsigned)col_blocks * (unsigned)((n_rows + 31) / 32);
-    if (blocks == 0) blocks = 1;       // (an empty shard still publishes its epoch)
+    unsigned blocks = (unsigned)col_blocks * (unsigned)(T.pos_row ? T.tiles_per_col : (n_rows + 31) / 32);
+    if (blocks == 0 || n_rows == 0) blocks = 1;       // (an empty shard still publishes its epoch)
     k_combine_column<<<blocks, 1024, 0, st>>>(n_rows, T.n_cols, T.tiles_per_col, col_blocks, T.item_begin,
                                               part_val, part_idx, J_out, argmin_out, P, j_offset, j_pitch,
-                                              tuning().dbg_exchange);
+                                              tuning().dbg_exchange, T.pos_row);
 }
 
 static void launch_combine_column_local(const SdpTables& T, const double* part_val, const int32_t* part_idx,

@@ -31,6 +31,8 @@ COLUMN_HOIST_DEFAULT = os.environ.get("SDP_COLUMN_HOIST", "1") != "0"
 # against 0.233 ms per sweep for 1/8 of the grid, 0.61 against 0.65 ms for 1/2.  "auto" cuts
 # by columns whenever layout CF applies and every rank gets at least 4 columns.
 SLAB_AXIS_DEFAULT = os.environ.get("SDP_SLAB_AXIS", "auto")
+# solver.column_pairs = "auto": layout CF with two rows per lane (3 shared-memory reads for 2 backups)
+COLUMN_PAIRS_DEFAULT = os.environ.get("SDP_COLUMN_PAIRS", "1") != "0"
 
 
 def _torch():
@@ -135,6 +137,9 @@ def fill_c_tables(T):
                 c.run_end = T.run_end_ord.data_ptr()
             else:
                 c.run_end = T.run_end.data_ptr()
+            if getattr(T, "pairs", False):
+                c.col_pairs = 1
+                c.pos_row = T.pos_row.data_ptr()
         c.u_mask = T.u_mask
         c.cell_w = T.cell_w.data_ptr()
         c.lam_w = T.lam_w.data_ptr()
@@ -181,17 +186,37 @@ class ColumnHoistRefused(Exception):
     along a column of the grid"""
 
 
-def column_order(n_states, n_cols, band_rows=None):
+def pair_positions(r0, r1, pair_ok):
+    """Positions of the rows [r0, r1) of a band for the two-rows-per-lane sweep: rows r, r+1 with
+    pair_ok[r] share a lane (positions 2j, 2j+1), any other row gets a lane of its own with a
+    padding position (-1) beside it; padded with -1 to a multiple of 64 (whole pairs of tiles).
+    Returns the int64 array position -> row."""
+    out = []
+    r = r0
+    while r < r1:
+        if r + 1 < r1 and pair_ok[r]:
+            out += [r, r + 1]
+            r += 2
+        else:
+            out += [r, -1]
+            r += 1
+    out += [-1] * (-len(out) % 64)
+    return np.asarray(out, dtype=np.int64)
+
+
+def column_order(n_states, n_cols, band_rows=None, pair_ok=None):
     """Position order of layout CF for a slab of whole rows of state axis 0.
 
     The slab's local states are i = row*n_cols + col (C-order).  Layout CF walks them
     band by band (`band_rows`: row boundaries [0, ..., n_rows]; default one band), inside a
     band column by column, every column of a band padded to whole tiles of 32 rows.
-    Returns (order, valid, band_tiles, band_tile_begin, tile_col):
+    Returns (order, valid, band_tiles, band_tile_begin, tile_col, pos_row):
       order[p]  local state at position p (a padding position repeats the last row of
                 its column in the band), valid[p] False on padding positions;
       band_tiles[b] tiles per column in band b; band_tile_begin[b] its first tile;
-      tile_col[t] the column of tile t."""
+      tile_col[t] the column of tile t;
+      pos_row   None, or - `pair_ok` given: two rows per lane, see pair_positions - per band the
+                int64 array position (of every column) -> row of the band (row - r0), -1 = padding."""
     n_rows = n_states // n_cols
     assert n_rows * n_cols == n_states and n_rows >= 1
     if band_rows is None:
@@ -199,19 +224,27 @@ def column_order(n_states, n_cols, band_rows=None):
     band_rows = [int(r) for r in band_rows]
     assert band_rows[0] == 0 and band_rows[-1] == n_rows and all(a < b for a, b in zip(band_rows, band_rows[1:]))
     cols = np.arange(n_cols, dtype=np.int64)
-    orders, valids, band_tiles, band_tile_begin, tile_col = [], [], [], [0], []
+    orders, valids, band_tiles, band_tile_begin, tile_col, pos_row = [], [], [], [0], [], []
     for r0, r1 in zip(band_rows[:-1], band_rows[1:]):
-        tpc = (r1 - r0 + 31) // 32
-        row = r0 + np.arange(32 * tpc, dtype=np.int64)
-        valid_row = row < r1
-        row = np.minimum(row, r1 - 1)
+        if pair_ok is None:
+            tpc = (r1 - r0 + 31) // 32
+            row = r0 + np.arange(32 * tpc, dtype=np.int64)
+            valid_row = row < r1
+            row = np.minimum(row, r1 - 1)
+        else:
+            pr = pair_positions(r0, r1, pair_ok)
+            tpc = len(pr) // 32
+            valid_row = pr >= 0
+            # (a padding position repeats the nearest real row before it: any real state does)
+            row = np.maximum.accumulate(np.where(valid_row, pr, r0))
+            pos_row.append(np.where(valid_row, pr - r0, -1))
         orders.append((row[None, :] * n_cols + cols[:, None]).reshape(-1))
         valids.append(np.broadcast_to(valid_row[None, :], (n_cols, len(row))).reshape(-1))
         band_tiles.append(tpc)
         band_tile_begin.append(band_tile_begin[-1] + n_cols * tpc)
         tile_col.append(np.repeat(cols, tpc))
     return (np.concatenate(orders), np.concatenate(valids), band_tiles, band_tile_begin,
-            np.concatenate(tile_col))
+            np.concatenate(tile_col), pos_row if pair_ok is not None else None)
 
 
 def item_run_ends(run_key):
@@ -483,6 +516,8 @@ class SweepTables(object):
         self.item_u_count_host = None
         self.col_table = None      # device fp64 scratch: the column tables of the current sweep
         self.run_end = None        # device int64 [n_items]: end of every item's (band, column) run
+        self.pairs = False         # layout CF with two rows per lane (SdpTables.col_pairs)
+        self.pos_row = self.work_dev = self.work_host = None
         self.item_order = None     # several bands: device int64 [n_items], items column by column (all bands)
         self.run_end_ord = None    # ... and the end of every position's column run in that order
         self.bands = None          # dict(rows, tiles, tile_begin, tile_col), see column_order
@@ -993,6 +1028,12 @@ class Engine(object):
             and getattr(solver, "table_compress", "auto") != "off"
             and n_rows0 >= 32 * world and nb_control <= _cabi.SDP_MAX_C)
         col_refused = [False]       # set when the built w-part turns out to vary along a column
+        # layout CF with two rows per lane (SdpTables.col_pairs): solver.column_pairs / SDP_COLUMN_PAIRS
+        pair_mode = getattr(solver, "column_pairs", "auto")
+        if pair_mode not in ("auto", "on", "off"):
+            raise ValueError("column_pairs must be 'auto', 'on' or 'off'")
+        pairs = bool(col_candidate and (pair_mode == "on" or (pair_mode == "auto" and COLUMN_PAIRS_DEFAULT))
+                     and 8 * _cabi.column_pitch(n_rows0, W, pairs=True) <= _cabi.COLUMN_MAX_SMEM_BYTES)
         # several ranks: slabs of whole rows of axis 0 ("rows"), or - layout CF only - whole
         # columns ("columns": every rank then tabulates and loads the tables of its own columns
         # only, so the per-column costs divide by the number of ranks)
@@ -1089,13 +1130,21 @@ class Engine(object):
                         pos[col] = (n, U, host, None, None, None)
                     else:
                         bands = self._column_bands(U.reshape(n // n_cols_loc, n_cols_loc).sum(axis=1), W)
-                        order, valid, band_tiles, band_tile_begin, tile_col = column_order(n, n_cols_loc, bands)
+                        pair_ok = None
+                        if pairs:
+                            # rows that may share a lane: neighbours on axis 0 with the same control
+                            # grid sizes in every column (their backups then read overlapping table
+                            # rows); a speed hint only - the kernel handles any pair
+                            npts_rc = host.npts.reshape(n // n_cols_loc, n_cols_loc * max(nb_control, 1))
+                            pair_ok = np.all(npts_rc[1:] == npts_rc[:-1], axis=1)
+                        order, valid, band_tiles, band_tile_begin, tile_col, pos_row = \
+                            column_order(n, n_cols_loc, bands, pair_ok)
                         h = tb.HostStateTable(len(order), nb_control)
                         h.lo, h.hi, h.npts = host.lo[order], host.hi[order], host.npts[order]
                         flat = glob[order] if by_columns else sb + order
                         pos[col] = (len(order), np.where(valid, U[order], 0), h, flat, valid,
                                     dict(rows=bands, tiles=band_tiles, tile_begin=band_tile_begin,
-                                         tile_col=tile_col))
+                                         tile_col=tile_col, pos_row=pos_row))
                 return pos[col]
 
             def sizes(u_mask, col):
@@ -1108,6 +1157,9 @@ class Engine(object):
                     Upad_t = np.zeros(n_tiles * 32, dtype=np.int64)
                     Upad_t[:n] = U
                     tile_U = Upad_t.reshape(n_tiles, 32).max(axis=1)
+                    if col and pairs:
+                        # the two tiles of a pair are swept by one warp: same number of controls
+                        tile_U = np.repeat(tile_U.reshape(-1, 2).max(axis=1), 2)
                     tile_off = np.zeros(n_tiles + 1, dtype=np.int64)
                     np.cumsum(tile_U * Wf * 32, out=tile_off[1:])
                     return (n_tiles, tile_U, tile_off, int(tile_off[-1]), np.zeros(n + 1, dtype=np.int64),
@@ -1388,7 +1440,9 @@ class Engine(object):
             up = [items if n_items else np.zeros(1, dtype=_cabi.ITEM_DTYPE), item_begin,
                   U_eff.astype(np.int32) if len(U_eff) else np.zeros(1, dtype=np.int32)]
             T.item_u_count_host = items["u_count"].copy() if col else None
-            T.item_order = T.run_end_ord = None
+            T.item_order = T.run_end_ord = T.pos_row = None
+            T.pairs = bool(col and pairs)
+            T.work_host = None
             if col:
                 T.sm_count = sm_count
                 # items of one band and column are consecutive (tiles are ordered that way)
@@ -1396,26 +1450,44 @@ class Engine(object):
                 tile_band = np.repeat(np.arange(n_bands), np.diff(T.bands["tile_begin"]))
                 st_of_item = items["state"].astype(np.int64)
                 item_col = T.bands["tile_col"][st_of_item]
-                weights = T.item_u_count_host
-                if n_bands > 1:
-                    # the launch over the whole list (device-resident sweeps) walks the items column
+                # the WORK list: what a warp takes - every item, or (two rows per lane) the items of
+                # the first tile of every pair, each carrying the index of the same run of controls
+                # in the second tile (item.g_base; the two tiles are cut alike)
+                work = np.arange(n_items, dtype=np.int64)
+                if T.pairs:
+                    n_it = np.diff(item_begin)[st_of_item]
+                    first = (st_of_item % 2) == 0        # (tiles per column and band are even)
+                    items["g_base"] = np.where(first, work + n_it, -1)
+                    work = work[first]
+                T.work_host = work
+                w_band, w_col, w_cnt = tile_band[st_of_item][work], item_col[work], T.item_u_count_host[work]
+                if n_bands > 1 or T.pairs:
+                    # the launch over the whole list (device-resident sweeps) walks the work column
                     # by column, the bands of a column back to back: one table load per column
-                    order = np.argsort(item_col * n_bands + tile_band[st_of_item], kind="stable").astype(np.int64)
-                    weights = weights[order]
-                up.append(column_segments(weights, sm_count * self.COLUMN_SEGS_PER_SM))
-                T.n_segs = len(up[-1]) - 1
-                up.append(item_run_ends(tile_band[st_of_item] * n_cols_loc + item_col))
-                if n_bands > 1:
-                    up += [order, item_run_ends(item_col[order])]
+                    by_col = np.argsort(w_col * n_bands + w_band, kind="stable")
+                    order = work[by_col]
+                    up.append(column_segments(w_cnt[by_col], sm_count * self.COLUMN_SEGS_PER_SM))
+                    up.append(item_run_ends(w_band * n_cols_loc + w_col))      # (natural order, per band)
+                    up += [order, item_run_ends(w_col[by_col])]
+                else:
+                    up.append(column_segments(w_cnt, sm_count * self.COLUMN_SEGS_PER_SM))
+                    up.append(item_run_ends(w_band * n_cols_loc + w_col))
+                T.n_segs = len(up[3]) - 1
+                if T.pairs:
+                    up += [work, np.concatenate(T.bands["pos_row"]).astype(np.int32)]
+                up[0] = items            # (g_base now holds the partners)
             else:
                 T.n_segs, T.seg_begin, T.run_end = 0, None, None
             up = self.to_device_packed(up)
             T.items, T.item_begin, T.U_dev = up[0], up[1], up[2]
             if col:
                 T.seg_begin, T.run_end = up[3], up[4]
-                if len(up) > 5:
+                if n_bands > 1 or T.pairs:
                     T.item_order, T.run_end_ord = up[5], up[6]
-                ensure("col_table", n_cols_loc * _cabi.column_pitch(n_rows0, W), torch.float64)
+                T.work_dev = None
+                if T.pairs:
+                    T.work_dev, T.pos_row = up[-2], up[-1]
+                ensure("col_table", n_cols_loc * _cabi.column_pitch(n_rows0, W, T.pairs), torch.float64)
             else:
                 T.col_table = None
             T.band_views = None
@@ -1481,9 +1553,9 @@ class Engine(object):
         """layout CF: re-cut the item list of built tables into `n_ctas` CTA segments
         (developer tuning, scripts/dev_column.py)"""
         assert T.column
-        w = T.item_u_count_host
+        w = T.item_u_count_host[T.work_host]
         if T.item_order is not None:
-            w = w[T.item_order.cpu().numpy()]
+            w = T.item_u_count_host[T.item_order.cpu().numpy()]
         seg = column_segments(w, n_ctas)
         T.seg_begin = self.to_device_packed([seg])[0]
         T.n_segs = len(seg) - 1
@@ -1559,6 +1631,8 @@ class Engine(object):
                 s0, s1 = int(B["rows"][b]) * T.n_cols, int(B["rows"][b + 1]) * T.n_cols
                 v.n_states = s1 - s0
                 v.tiles_per_col = int(tpc)
+                if getattr(T, "pairs", False):
+                    v.pos_row = T.pos_row.data_ptr() + 4 * 32 * int(sum(B["tiles"][:b]))
                 views.append((v, s0, s1 - s0))
             T.band_views = views
         return T.band_views
@@ -1717,13 +1791,17 @@ class Engine(object):
             plan = []
             tb0 = T.bands["tile_begin"]
             for b, (view, s0, ns) in enumerate(self._band_views(T)):
-                i0, i1 = int(T.item_begin_host[tb0[b]]), int(T.item_begin_host[tb0[b + 1]])
-                seg = i0 + column_segments(T.item_u_count_host[i0:i1], T.sm_count * self.COLUMN_SEGS_PER_SM)
+                # (positions of the work list - every item, or with two rows per lane the items
+                # of the first tile of every pair - that belong to the band)
+                i0, i1 = (int(np.searchsorted(T.work_host, T.item_begin_host[tb0[k]])) for k in (b, b + 1))
+                seg = i0 + column_segments(T.item_u_count_host[T.work_host[i0:i1]],
+                                           T.sm_count * self.COLUMN_SEGS_PER_SM)
                 seg_dev = self.to_device_packed([seg])[0]
                 cp = _cabi.SdpTables.from_buffer_copy(T.c_tables)
                 cp.seg_begin, cp.n_segs, cp.col_table_ready = seg_dev.data_ptr(), len(seg) - 1, 1
                 # a band is walked in the list's own order: many short column pieces per CTA
-                cp.item_order, cp.run_end = 0, T.run_end.data_ptr()
+                cp.item_order = T.work_dev.data_ptr() if T.work_dev is not None else 0
+                cp.run_end = T.run_end.data_ptr()
                 cp.col_launch_hint = self.BAND_LAUNCH_HINT
                 plan.append(dict(tab_p=cp, tab_f=view, s0=s0, s1=s0 + ns, keep=seg_dev,
                                  pv=ctypes.c_void_p(T.part_val.data_ptr()),

@@ -64,6 +64,10 @@ class DPSolver(object):
         # storage examples), one CTA tabulates the inner interpolation once per column of
         # the grid; "auto" follows SDP_COLUMN_HOIST, "on" raises if it does not apply
         self.column_hoist = "auto"    # "auto" | "on" | "off"
+        # layout CF: a lane of the sweep owns two neighbouring rows of a column, whose backups
+        # read overlapping rows of the column table (3 shared-memory reads for 2 backups);
+        # "auto" follows SDP_COLUMN_PAIRS
+        self.column_pairs = "auto"    # "auto" | "on" | "off"
         # several ranks, layout CF: cut the grid into slabs of whole rows of axis 0 ("rows") or
         # into whole columns ("columns": the per-column costs then divide by the number of
         # ranks); "auto" (SDP_SLAB_AXIS) takes columns wherever layout CF applies and every rank
@@ -176,7 +180,8 @@ class DPSolver(object):
                 tuple(sig(p) for p in self.perturb_proba),
                 tuple(float(c) for c in self.control_steps),
                 self.table_layout, self.tabulate, self.table_compress, self.slab_balance,
-                getattr(self, "column_hoist", "auto"), getattr(self, "slab_axis", "auto"))
+                getattr(self, "column_hoist", "auto"), getattr(self, "slab_axis", "auto"),
+                getattr(self, "column_pairs", "auto"))
 
     def clear_tables(self):
         """drop the device-resident tables (call after mutating anything the

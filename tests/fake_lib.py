@@ -308,9 +308,8 @@ class FakeLib(object):
             seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
             assert 0 <= seg[0] and seg[-1] <= T.n_items and np.all(np.diff(seg) >= 0)
             assert np.all(np.diff(items["state"]) >= 0)          # ordered by tile
-            if T.item_order:
-                # an explicit walking order: a permutation of the item list
-                assert sorted(_arr(T.item_order, T.n_items, ctypes.c_int64)) == list(range(T.n_items))
+            if T.col_pairs:
+                assert T.item_order and T.pos_row and T.tiles_per_col % 2 == 0
             assert T.col_table and T.col_table % 16 == 0         # scratch for the column tables
             if T.col_table_ready:
                 # the caller ran the pre-pass (sdp_column_table) on this J
@@ -429,8 +428,16 @@ class FakeLib(object):
         n_units = (T.n_states + 31) // 32 if tiled else T.n_states
         if column:
             # one band of whole rows: n_states, tiles_per_col and item_begin are the band's
-            assert T.n_states % T.n_cols == 0 and T.tiles_per_col == (T.n_states // T.n_cols + 31) // 32
+            assert T.n_states % T.n_cols == 0
             n_units = T.n_cols * T.tiles_per_col
+            row_pos = None
+            if T.pos_row:
+                # two rows per lane: positions are not rows (pos_row: position -> row, -1 padding)
+                pr = _arr(T.pos_row, T.tiles_per_col * 32, ctypes.c_int32)
+                row_pos = {int(r): p_ for p_, r in enumerate(pr) if r >= 0}
+                assert sorted(row_pos) == list(range(T.n_states // T.n_cols))
+            else:
+                assert T.tiles_per_col == (T.n_states // T.n_cols + 31) // 32
         ib = _arr(T.item_begin, n_units + 1, ctypes.c_int64)
         top = int(ib[-1]) * width
         pv = _arr(part_val, top, ctypes.c_double)
@@ -442,6 +449,8 @@ class FakeLib(object):
             unit, lane = (i // 32, i % 32) if tiled else (i, 0)
             if column:
                 row, c = divmod(i, T.n_cols)
+                if row_pos is not None:
+                    row = row_pos[row]
                 unit, lane = c * T.tiles_per_col + row // 32, row % 32
             for k in range(ib[unit], ib[unit + 1]):
                 kk = k * width + lane
@@ -458,9 +467,11 @@ class FakeLib(object):
         (1-l0)*R[q0][w] + l0*R[q0+1][w] with q0 = cell_u / stride0"""
         W, Tc = T.W, T.tiles_per_col          # (tiles per column of the FIRST band)
         seg = _arr(T.seg_begin, T.n_segs + 1, ctypes.c_int64)
-        run_end = _arr(T.run_end, T.n_items, ctypes.c_int64)
-        # positions -> items (SdpTables.item_order), identity when absent
-        order = _arr(T.item_order, T.n_items, ctypes.c_int64) if T.item_order else np.arange(T.n_items)
+        n_work = int(seg[-1])           # (positions of the walking order covered by this launch)
+        run_end = _arr(T.run_end, n_work, ctypes.c_int64)
+        # positions -> items (SdpTables.item_order), identity when absent; with two rows per lane
+        # the order lists the items of the first tile of every pair, item.g_base = the partner
+        order = _arr(T.item_order, n_work, ctypes.c_int64) if T.item_order else np.arange(T.n_items)
         rows, stride0 = int(orders[0]), int(strides[0])
         P = W | 1
         done = np.zeros(len(items), dtype=bool)
@@ -483,12 +494,24 @@ class FakeLib(object):
                         bb = rec(base + strides[k], k + 1)
                         return (1 - lw[k - 1]) * a + lw[k - 1] * bb
                     R[np.arange(rows) * P + w] = rec(np.arange(rows, dtype=np.int64) * stride0 + cw, 1)
-                for n_it in (int(order[pos]) for pos in range(i, e)):
+                todo = []
+                for pos in range(i, e):
+                    a = int(order[pos])
+                    todo.append(a)
+                    if T.col_pairs:
+                        b_ = int(items[a]["g_base"])
+                        assert int(items[a]["state"]) % 2 == 0
+                        if b_ >= 0:
+                            assert (int(items[b_]["state"]) == int(items[a]["state"]) + 1
+                                    and items[b_]["u_begin"] == items[a]["u_begin"]
+                                    and items[b_]["u_count"] == items[a]["u_count"])
+                            todo.append(b_)
+                for n_it in todo:
                     it = items[n_it]
                     assert int(it["Upad"]) == col and not done[n_it]
                     done[n_it] = True
                     cnt, ub, eb, tix = int(it["u_count"]), int(it["u_begin"]), int(it["entry_base"]), int(it["state"])
-                    assert int(it["g_base"]) == eb
+                    assert T.col_pairs or int(it["g_base"]) == eb
                     cu = _arr(T.cell + 4 * eb, cnt * 32, ctypes.c_int32).astype(np.int64).reshape(cnt, 32)
                     lu = _arr(T.lam + 8 * eb, cnt * 32, ctypes.c_double).reshape(cnt, 32)
                     Gv = _arr(T.g + 8 * eb, cnt * 32, ctypes.c_double).reshape(cnt, 32)
@@ -509,7 +532,9 @@ class FakeLib(object):
                             j = int(np.argmax(nan)) if nan.any() else int(np.argmin(a))
                             pv[n_it * 32 + lane], pi[n_it * 32 + lane] = a[j], ub + j
                 i = e
-        assert done[int(seg[0]):int(seg[-1])].all()
+        # every item the covered positions stand for was processed (with pairs: partners too)
+        covered = [int(order[pos]) for pos in range(int(seg[0]), int(seg[-1]))]
+        assert done[covered].all() and (T.col_pairs or done.sum() == len(covered))
 
     def sdp_policy_eval(self, gref, W, g_per_w, p, cell, lam, lam_plane, g, n_states, state_begin,
                         n_grid, J_a, J_b, n_iter, rel_dp, ref_index, hist, stream):

@@ -367,7 +367,7 @@ def test_column_order_and_row_aligned_bounds():
     """layout CF walks a slab of whole rows band by band, column by column, every column
     of a band padded to whole tiles of 32 rows; slab boundaries are moved to whole rows"""
     from stodynprog_b200.engine import column_order, row_aligned, item_run_ends, column_segments
-    order, valid, tiles, tile_begin, tile_col = column_order(70 * 5, 5)
+    order, valid, tiles, tile_begin, tile_col, _ = column_order(70 * 5, 5)
     assert tiles == [3] and tile_begin == [0, 15] and len(order) == 5 * 96 and valid.sum() == 350
     assert sorted(order[valid]) == list(range(350))              # every state exactly once
     assert list(tile_col) == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4]
@@ -376,11 +376,11 @@ def test_column_order_and_row_aligned_bounds():
     for c in range(5):
         assert list(o[c, :70]) == [r * 5 + c for r in range(70)]   # lane <-> row of the column
         assert np.all(o[c, 70:] == 69 * 5 + c) and not v[c, 70:].any() and v[c, :70].all()
-    order, valid, tiles, tile_begin, tile_col = column_order(64 * 3, 3)
+    order, valid, tiles, tile_begin, tile_col, _ = column_order(64 * 3, 3)
     assert tiles == [2] and valid.all() and len(order) == 192
     # two bands: rows 0..39 (2 tiles per column, 24 padding lanes) and 40..69 (1 tile, 2 padding lanes)
-    order, valid, tiles, tile_begin, tile_col = column_order(70 * 5, 5, [0, 40, 70])
-    assert tiles == [2, 1] and tile_begin == [0, 10, 15] and len(order) == 32 * 15
+    order, valid, tiles, tile_begin, tile_col, pos_row = column_order(70 * 5, 5, [0, 40, 70])
+    assert pos_row is None and tiles == [2, 1] and tile_begin == [0, 10, 15] and len(order) == 32 * 15
     assert sorted(order[valid]) == list(range(350))
     assert list(tile_col) == [0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 0, 1, 2, 3, 4]
     assert list(order[:40]) == [r * 5 for r in range(40)] and not valid[40:64].any()
@@ -388,6 +388,22 @@ def test_column_order_and_row_aligned_bounds():
     assert list(band1[2, :30]) == [r * 5 + 2 for r in range(40, 70)]
     with pytest.raises(AssertionError):
         column_order(70 * 5, 5, [0, 40, 60])
+    # two rows per lane: rows r, r+1 share a lane where pair_ok[r]; a lone row gets a padding
+    # position beside it; every band is padded to whole PAIRS of tiles (64 positions)
+    from stodynprog_b200.engine import pair_positions
+    ok = np.ones(69, dtype=bool)
+    ok[[4, 9, 10]] = False                     # rows 4|5, 9|10, 10|11 must not share a lane
+    pr = pair_positions(0, 40, ok)
+    assert list(pr[:14]) == [0, 1, 2, 3, 4, -1, 5, 6, 7, 8, 9, -1, 10, -1] and len(pr) == 64
+    assert sorted(pr[pr >= 0]) == list(range(40)) and np.all(pr[0::2] >= 0) == (pr[0::2] >= 0).all()
+    for a, b in zip(pr[0::2], pr[1::2]):
+        assert b == -1 or (b == a + 1 and ok[a])
+    order, valid, tiles, tile_begin, tile_col, pos_row = column_order(70 * 5, 5, [0, 40, 70], ok)
+    assert tiles == [2, 2] and tile_begin == [0, 10, 20] and len(order) == 64 * 10
+    assert sorted(order[valid]) == list(range(350)) and len(pos_row) == 2
+    assert list(pos_row[0]) == list(pr) and sorted(pos_row[1][pos_row[1] >= 0]) == list(range(30))
+    band1 = order[320:].reshape(5, 64)
+    assert np.array_equal(band1[3][pos_row[1] >= 0], (40 + pos_row[1][pos_row[1] >= 0]) * 5 + 3)
     assert list(item_run_ends([3, 3, 3, 4, 9, 9])) == [3, 3, 3, 4, 6, 6]
     assert list(item_run_ends([])) == [] and list(item_run_ends([7])) == [1]
     seg = column_segments(np.array([10, 10, 10, 10, 30, 10]), 3)

@@ -905,16 +905,20 @@ def test_column_hoist_is_bit_identical(product, backend, which):
     ref = _column_case(_Api(product, backend, "state_minor", "auto", "on"), which)
     ref.column_hoist = "off"
     col = _column_case(_Api(product, backend, "state_minor", "auto", "on"), which)
-    col.column_hoist = "on"
+    col.column_hoist, col.column_pairs = "on", "off"        # one row per lane
+    col2 = _column_case(_Api(product, backend, "state_minor", "auto", "on"), which)
+    col2.column_hoist, col2.column_pairs = "on", "on"       # two rows per lane
     J0 = np.random.default_rng(11).standard_normal(ref._state_grid_shape)
     for sweep in range(3):
         Jr, polr = ref.value_iteration(J0, report_time=False)
         Jc, polc = col.value_iteration(J0, report_time=False)
-        Tr, Tc = ref.last_tables, col.last_tables
+        Jc2, polc2 = col2.value_iteration(J0, report_time=False)
+        Tr, Tc, Tc2 = ref.last_tables, col.last_tables, col2.last_tables
         assert Tr.layout_name == "state_minor_factored" and Tc.layout_name == "column_factored"
-        assert Tc.n_backups_local == Tr.n_backups_local and Tc.u_mask == 1
-        assert _same_bits(Jr, Jc), sweep
-        assert np.array_equal(polr, polc, equal_nan=True), sweep
+        assert Tc2.layout_name == "column_factored" and Tc2.pairs and not Tc.pairs
+        assert Tc.n_backups_local == Tr.n_backups_local == Tc2.n_backups_local and Tc.u_mask == 1
+        assert _same_bits(Jr, Jc) and _same_bits(Jr, Jc2), sweep
+        assert np.array_equal(polr, polc, equal_nan=True) and np.array_equal(polr, polc2, equal_nan=True), sweep
         J0 = Jr.copy()
         if sweep == 1:                          # special values travel through the table too
             J0.reshape(-1)[::7] = np.nan
@@ -935,6 +939,9 @@ def test_column_hoist_is_bit_identical(product, backend, which):
                 J2, pol2 = col.value_iteration(J0, report_time=False)
                 assert _same_bits(Jr, J2), (threads, ub, pf, pre)
                 assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf, pre)
+                if pre == 2:            # (two rows per lane copies its table with the TMA engine only)
+                    J3, pol3 = col2.value_iteration(J0, report_time=False)
+                    assert _same_bits(Jr, J3) and np.array_equal(polr, pol3, equal_nan=True), (threads, "pairs")
         finally:
             lib.sdp_set_option(b"col_threads", 768)
             lib.sdp_set_option(b"col_ub", 2)
@@ -1065,7 +1072,8 @@ def test_column_hoist_band_launch_plan(product, monkeypatch):
     tb0 = T.bands["tile_begin"]
     for b, ch in enumerate(plan):
         seg = ch["keep"].numpy()
-        i0, i1 = int(T.item_begin_host[tb0[b]]), int(T.item_begin_host[tb0[b + 1]])
+        # (positions of the work list: every item, or - two rows per lane - the first tile's of each pair)
+        i0, i1 = (int(np.searchsorted(T.work_host, T.item_begin_host[tb0[k]])) for k in (b, b + 1))
         assert seg[0] == i0 and seg[-1] == i1 and np.all(np.diff(seg) >= 0) and i1 > i0
         assert ch["tab_p"].col_table_ready == 1 and ch["tab_p"].n_segs == len(seg) - 1
         assert ch["tab_f"].n_states == ch["s1"] - ch["s0"] and ch["tab_f"].tiles_per_col == T.bands["tiles"][b]
