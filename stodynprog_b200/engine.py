@@ -31,8 +31,13 @@ COLUMN_HOIST_DEFAULT = os.environ.get("SDP_COLUMN_HOIST", "1") != "0"
 # against 0.233 ms per sweep for 1/8 of the grid, 0.61 against 0.65 ms for 1/2.  "auto" cuts
 # by columns whenever layout CF applies and every rank gets at least 4 columns.
 SLAB_AXIS_DEFAULT = os.environ.get("SDP_SLAB_AXIS", "auto")
-# solver.column_pairs = "auto": layout CF with two rows per lane (3 shared-memory reads for 2 backups)
-COLUMN_PAIRS_DEFAULT = os.environ.get("SDP_COLUMN_PAIRS", "1") != "0"
+# solver.column_pairs = "auto": layout CF with two rows per lane (3 shared-memory reads for 2
+# backups instead of 4).  OFF by default: measured on config #5 (profiles/r2_emu_variants_pairs.txt)
+# 1.58-1.67 ms per sweep against 1.15 ms with one row per lane.  The reads saved come back as bank
+# conflicts: a half-warp's 16 lanes then span up to 32 table rows, and no placement of the rows in
+# the 16 eight-byte bank pairs serves both the stride-2 pattern of the interior of the grid and the
+# stride <= 1 patterns of the clipped control boxes without collisions.
+COLUMN_PAIRS_DEFAULT = os.environ.get("SDP_COLUMN_PAIRS", "0") != "0"
 
 
 def _torch():
@@ -1651,15 +1656,16 @@ class Engine(object):
                                              ctypes.c_void_p(argmin.data_ptr() + 4 * s0), stream)
             _cabi.check(rc, "sdp_sweep_finalize")
 
-    def sweep_local(self, T, J_prev, events=None):
+    def sweep_local(self, T, J_prev, events=None, J_out=None):
         """Enqueue K1 on this rank's slab.  J_prev: device fp64 [n_grid].
-        Results land in T.J_out / T.argmin (slab-local).  `events`: optional
+        Results land in `J_out` (default T.J_out) / T.argmin (slab-local).  `events`: optional
         (start, end) torch.cuda.Event pair recorded around the streaming kernel
         alone (bench roofline)."""
+        J_out = T.J_out if J_out is None else J_out
         if events is None and not T.column:
             rc = self.lib.sdp_sweep(ctypes.byref(T.grid), ctypes.byref(T.c_tables), self._ptr(J_prev),
                                     self._ptr(T.part_val), self._ptr(T.part_idx),
-                                    self._ptr(T.J_out), self._ptr(T.argmin), self.stream)
+                                    self._ptr(J_out), self._ptr(T.argmin), self.stream)
             _cabi.check(rc, "sdp_sweep")
             return
         if events is not None:
@@ -1670,7 +1676,7 @@ class Engine(object):
         _cabi.check(rc, "sdp_sweep_partials")
         if events is not None:
             events[1].record(self.torch_stream)
-        self._finalize(T, T.J_out, T.argmin)
+        self._finalize(T, J_out, T.argmin)
 
     # Device-resident iterations (solve_value_iteration, the bench loop) may leave the flag wait
     # of a sweep's exchange to the NEXT sweep, whose first kernel then starts with it
@@ -1742,9 +1748,12 @@ class Engine(object):
                 _cabi.check(rc, "sdp_p2p_wait")
         else:
             self._argmin_in_px = False
-            self.sweep_local(T, J_prev, events)
             if self.coll.world == 1:
-                J_new.copy_(T.J_out[:n])
+                self.sweep_local(T, J_prev, events, J_out=J_new)     # (one rank: straight into J_new)
+            else:
+                self.sweep_local(T, J_prev, events)
+            if self.coll.world == 1:
+                pass
             elif T.col_bounds is not None:
                 self.coll.all_gather_indexed(T.J_out[:n], T.gather_maxc, T.gather_index, out=J_new)
             else:
