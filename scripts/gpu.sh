@@ -60,6 +60,7 @@ for STEP in "$@"; do
           -k regex:'k_sweep|k_column_table|k_combine' --launch-skip ${NCU_SKIP:-2} -c ${NCU_COUNT:-4} -f \
           -o $OUT/${TAG}_ncu_$W python scripts/ncu_target.py $TGT > $OUT/${TAG}_ncu_$W.log 2>&1
       ncu -i $OUT/${TAG}_ncu_$W.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/${TAG}_ncu_$W.txt
+      [ -z "${KEEP_REP:-}" ] && rm -f $OUT/${TAG}_ncu_$W.ncu-rep     # (gpurun brings back at most 64 MiB)
       env $ENVS timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
           --log-file $OUT/${TAG}_launches_$W.csv python scripts/ncu_target.py $TGT >> $OUT/${TAG}_ncu_$W.log 2>&1
       grep "== kernel\|gpu__time_duration\|dram__bytes_read.sum \|wavefronts.avg.pct\|fp64_cycles_active.avg.pct_of_peak_sustained_elapsed\|issue_active" $OUT/${TAG}_ncu_$W.txt | head -40 ;;

@@ -686,6 +686,26 @@ class Engine(object):
             outs.append(t.reshape(a.shape))
         return outs
 
+    def to_device_concat(self, records, parts):
+        """a structured record array + a LIST of fp64 arrays -> one page-locked buffer -> one
+        asynchronous H2D copy; returns (records as device bytes, the parts concatenated without gaps
+        as one device fp64 tensor).  Each part is copied once, straight into the upload buffer."""
+        torch = _torch()
+        rec = np.ascontiguousarray(records).view(np.uint8).reshape(-1)
+        n_parts = int(sum(a.size for a in parts))
+        off = (rec.nbytes + 15) // 16 * 16
+        total = off + 8 * n_parts
+        host = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=self._cuda)
+        hn = host.numpy()
+        hn[:rec.nbytes] = rec
+        dst = hn[off:off + 8 * n_parts].view(np.float64)
+        pos = 0
+        for a in parts:
+            dst[pos:pos + a.size] = a.reshape(-1)
+            pos += a.size
+        buf = host.to(self.device, non_blocking=True) if self._cuda else host
+        return buf[:rec.nbytes], buf[off:off + 8 * n_parts].view(torch.float64)
+
     def sync(self):
         if self._cuda:
             _torch().cuda.synchronize(self.device)
@@ -1273,7 +1293,8 @@ class Engine(object):
                 def flush(desc, staging):
                     if u_mask:
                         tb.check_factorable(desc, d, u_mask)
-                    desc_dev, stag_dev = self.to_device_packed([desc, staging])
+                    desc_dev, stag_dev = self.to_device_concat(desc, staging)
+                    n_staging = int(stag_dev.numel())
                     ns = len(desc)
                     first = done[0]
                     if tiled:
@@ -1322,7 +1343,7 @@ class Engine(object):
 
                     launch(self._ptr(desc_dev), self._ptr(stag_dev), self._ptr(T.g))
                     # (`keep`: the device arrays the launch closure points into)
-                    flushes.append(dict(desc=desc, n_staging=len(staging), stag_dev=stag_dev, launch=launch,
+                    flushes.append(dict(desc=desc, n_staging=n_staging, stag_dev=stag_dev, launch=launch,
                                         first=first, keep=(desc_dev, tile_off_dev, tile_g_off_dev, tile_U_dev)
                                         if tiled else (desc_dev,)) if keep_staging else None)
                     done[0] += ns

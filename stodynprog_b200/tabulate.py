@@ -207,7 +207,9 @@ class _ChunkWriter(object):
     def flush(self):
         if not self.n_states:
             return
-        staging = np.concatenate(self.arrays) if self.arrays else np.zeros(1)
+        # (the staged arrays travel as a list: the caller copies each straight into its
+        # page-locked upload buffer instead of concatenating first)
+        staging = self.arrays if self.arrays else [np.zeros(1)]
         desc = np.concatenate(self.descs)
         self.flush_fn(desc, staging)
         self.reset()
