@@ -1065,6 +1065,7 @@ struct Tuning {
     int col_pf;        // layout CF: groups of col_ub controls in flight per lane (1|2)
     int col_dynamic;   // layout CF: warps take the items of a column first come first served (1) or round-robin (0)
     int col_prepass;   // layout CF: column tables from the coalesced pre-pass, copied by vector loads (1) or by the TMA engine (2); 0: gathered by every CTA
+    int pdl;           // programmatic dependent launch of pre-pass / column sweep / combine (1) or plain launches (0)
     int dbg_exchange;  // TIMING EXPERIMENTS ONLY (wrong results): 1 = no stores to remote ranks, 2 = no system fence, 4 = relaxed flag stores
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -1107,6 +1108,7 @@ static Tuning& tuning() {
         x.col_prepass = clampi(env_int("SDP_COL_PREPASS", 2), 0, 2);
         x.col_dynamic = env_int("SDP_COL_DYNAMIC", 1) != 0;
         x.dbg_exchange = 0;
+        x.pdl = env_int("SDP_PDL", 1) != 0;
         return x;
     }();
     return t;
@@ -1131,6 +1133,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "col_prepass")) t.col_prepass = clampi(value, 0, 2);
     else if (!strcmp(name, "col_dynamic")) t.col_dynamic = value != 0;
     else if (!strcmp(name, "dbg_exchange")) t.dbg_exchange = value;
+    else if (!strcmp(name, "pdl")) t.pdl = value != 0;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -1823,6 +1826,28 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned 
 // computes with lanes along the columns - the w-parts of neighbouring columns point at
 // neighbouring cells, so the gathers of a warp are a few lines instead of 32 - into a
 // shared-memory tile, then writes each column's run of rows contiguously.
+// Programmatic dependent launch (sm_90+): the kernel may be scheduled while its predecessor in the
+// stream drains; it calls cudaGridDependencySynchronize() (griddepcontrol.wait) before touching
+// anything the predecessor wrote.  Hides the launch latency at the 3 kernel boundaries of a sweep
+// (pre-pass -> sweep -> combine), which weighs on the 0.2 ms sweeps of an 8-GPU run.
+// tuning().pdl = 0 launches the plain way.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t shm, cudaStream_t st,
+                              Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = shm;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tuning().pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // set by sdp_sweep_partials_after for the duration of the call: the exchange whose flag wait
 // the first kernel that reads J_prev must perform (consumed by launch_column_table)
 static thread_local const PeersDev* g_wait_peers = nullptr;
@@ -1838,6 +1863,7 @@ k_column_table(GridT<double> G, SdpTables T, const double* __restrict__ Jprev, i
     constexpr int NW = D - 1;
     constexpr int TR = SDP_CT_ROWS;
     extern __shared__ __align__(16) unsigned char tsm[];
+    cudaGridDependencySynchronize();       // (programmatic dependent launch: the previous kernel's writes)
     if (WAIT) {
         if (threadIdx.x < PW.world) wait_flag(PW.flags[PW.rank] + threadIdx.x, *PW.epoch, timeout_ns);
         __syncthreads();
@@ -1899,12 +1925,12 @@ static int launch_column_table(const GridT<double>& G, const SdpTables& T, const
         // the flag wait of the previous exchange rides in this kernel (sdp_sweep_partials_after)
         const PeersDev P2 = *g_wait_peers;
         g_wait_peers = nullptr;
-        k_column_table<D, true><<<grid, 256, tshm, st>>>(
-            G, T, Jprev, pitch, P2, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL);
+        launch_pdl(k_column_table<D, true>, grid, dim3(256), tshm, st,
+                   G, T, Jprev, pitch, P2, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL);
     } else {
         PeersDev none;
         memset(&none, 0, sizeof(none));
-        k_column_table<D, false><<<grid, 256, tshm, st>>>(G, T, Jprev, pitch, none, 0ULL);
+        launch_pdl(k_column_table<D, false>, grid, dim3(256), tshm, st, G, T, Jprev, pitch, none, 0ULL);
     }
     SDP_LAUNCH_CHECK();
     return SDP_OK;
@@ -1930,6 +1956,7 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
         mbar_init(smem_u32(&tbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    cudaGridDependencySynchronize();       // (programmatic dependent launch: the pre-pass's column tables)
     __syncthreads();
     const int W = T.W;
     const int P = W | 1;        // odd row pitch: adjacent rows never share a bank pair
@@ -2114,11 +2141,11 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
     const double inv0 = 1.0 / (double)G.stride[0];
     const int dynamic = (T.col_launch_hint & 0xffff) ? !((T.col_launch_hint >> 16) & 1) : tuning().col_dynamic;
     if (T.W == WM)
-        k_sweep_fact_column<D, WM, UB, PF, true, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
-            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, dynamic);
+        launch_pdl(k_sweep_fact_column<D, WM, UB, PF, true, MAXT>, dim3((unsigned)T.n_segs), dim3(threads), shm, st,
+                   G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, dynamic);
     else
-        k_sweep_fact_column<D, WM, UB, PF, false, MAXT><<<(unsigned)T.n_segs, threads, shm, st>>>(
-            G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, dynamic);
+        launch_pdl(k_sweep_fact_column<D, WM, UB, PF, false, MAXT>, dim3((unsigned)T.n_segs), dim3(threads), shm, st,
+                   G, T, Jprev, part_val, part_idx, inv0, pv, pitch, prepass, dynamic);
     note_kernel("%sk_sweep_fact_column<%d,%d,%d,%d,%s,%d> [%d CTAs x %d threads]",
                 (prepass && !T.col_table_ready) ? "k_column_table + " : "", D, WM, UB, PF,
                 T.W == WM ? "true" : "false", MAXT, (int)T.n_segs, threads);
@@ -2707,6 +2734,7 @@ k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
     __shared__ int i_sh[32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ty = blockIdx.x / col_blocks;                 // tile (32 rows) of the band
+    cudaGridDependencySynchronize();       // (programmatic dependent launch: the sweep's partial minima)
     const int c0 = (blockIdx.x - ty * col_blocks) * 32;
     if (n_rows > 0) {
         const int c = c0 + warp;
@@ -2759,9 +2787,9 @@ static void launch_combine_column(const SdpTables& T, const double* part_val, co
     const int col_blocks = T.n_cols > 0 ? (T.n_cols + 31) / 32 : 1;
     unsigned blocks = (unsigned)col_blocks * (unsigned)(T.pos_row ? T.tiles_per_col : (n_rows + 31) / 32);
     if (blocks == 0 || n_rows == 0) blocks = 1;       // (an empty shard still publishes its epoch)
-    k_combine_column<<<blocks, 1024, 0, st>>>(n_rows, T.n_cols, T.tiles_per_col, col_blocks, T.item_begin,
-                                              part_val, part_idx, J_out, argmin_out, P, j_offset, j_pitch,
-                                              tuning().dbg_exchange, T.pos_row);
+    launch_pdl(k_combine_column, dim3(blocks), dim3(1024), 0, st, n_rows, T.n_cols, T.tiles_per_col, col_blocks,
+               T.item_begin, part_val, part_idx, J_out, argmin_out, P, j_offset, j_pitch,
+               tuning().dbg_exchange, T.pos_row);
 }
 
 static void launch_combine_column_local(const SdpTables& T, const double* part_val, const int32_t* part_idx,
