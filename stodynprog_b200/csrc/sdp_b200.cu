@@ -1859,9 +1859,8 @@ static thread_local const PeersDev* g_wait_peers = nullptr;
 template <int D, bool WAIT>
 __global__ void __launch_bounds__(256)
 k_column_table(GridT<double> G, SdpTables T, const double* __restrict__ Jprev, int64_t pitch,
-               PeersDev PW, unsigned long long timeout_ns) {
+               PeersDev PW, unsigned long long timeout_ns, int TR) {
     constexpr int NW = D - 1;
-    constexpr int TR = SDP_CT_ROWS;
     extern __shared__ __align__(16) unsigned char tsm[];
     cudaGridDependencySynchronize();       // (programmatic dependent launch: the previous kernel's writes)
     if (WAIT) {
@@ -1885,6 +1884,8 @@ k_column_table(GridT<double> G, SdpTables T, const double* __restrict__ Jprev, i
         for (int j = 0; j < NW; ++j) lw_s[(j * 32 + lc) * W + w] = __ldg(T.lam_w + (int64_t)j * T.lam_w_plane + f);
     }
     __syncthreads();
+    // (independent iterations: unrolled so that the gathers of several elements are in flight)
+#pragma unroll 6
     for (int k = threadIdx.x; k < TR * W * 32; k += blockDim.x) {
         const int lc = k & 31;
         const int rw = k >> 5;
@@ -1918,19 +1919,24 @@ template <int D>
 static int launch_column_table(const GridT<double>& G, const SdpTables& T, const double* Jprev, cudaStream_t st) {
     constexpr int NW = D - 1;
     const int P = T.W | 1;
-    const size_t tshm = (size_t)32 * (SDP_CT_ROWS * P + 1) * 8 + (size_t)NW * 32 * T.W * 8 + (size_t)32 * T.W * 4;
-    dim3 grid((unsigned)((T.n_cols + 31) / 32), (unsigned)((G.order[0] + SDP_CT_ROWS - 1) / SDP_CT_ROWS));
+    // rows per CTA: 16, fewer when the shard has so few columns that 16 would leave SMs idle
+    // (the 62 columns of one rank of eight: 250 CTAs of 16 rows, 1 000 of 4)
+    int TR = SDP_CT_ROWS;
+    const int64_t col_blocks = (T.n_cols + 31) / 32;
+    while (TR > 4 && col_blocks * ((G.order[0] + TR - 1) / TR) < 148 * 6) TR >>= 1;
+    const size_t tshm = (size_t)32 * (TR * P + 1) * 8 + (size_t)NW * 32 * T.W * 8 + (size_t)32 * T.W * 4;
+    dim3 grid((unsigned)col_blocks, (unsigned)((G.order[0] + TR - 1) / TR));
     const int64_t pitch = T.col_pairs ? SDP_COLUMN_PITCH2(G.order[0], T.W) : SDP_COLUMN_PITCH(G.order[0], T.W);
     if (g_wait_peers) {
         // the flag wait of the previous exchange rides in this kernel (sdp_sweep_partials_after)
         const PeersDev P2 = *g_wait_peers;
         g_wait_peers = nullptr;
         launch_pdl(k_column_table<D, true>, grid, dim3(256), tshm, st,
-                   G, T, Jprev, pitch, P2, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL);
+                   G, T, Jprev, pitch, P2, (unsigned long long)tuning().p2p_timeout_s * 1000000000ULL, TR);
     } else {
         PeersDev none;
         memset(&none, 0, sizeof(none));
-        launch_pdl(k_column_table<D, false>, grid, dim3(256), tshm, st, G, T, Jprev, pitch, none, 0ULL);
+        launch_pdl(k_column_table<D, false>, grid, dim3(256), tshm, st, G, T, Jprev, pitch, none, 0ULL, TR);
     }
     SDP_LAUNCH_CHECK();
     return SDP_OK;
