@@ -1,27 +1,35 @@
 #!/usr/bin/env python
 """bench.py - Bellman backups/s of the sweep hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload large|ar1|pv]
 
 A "step" is one full Bellman sweep (value_iteration's hot path) over the
 configured state grid.  Workload: BASELINE.json configs[4], the storage-AR1
 problem scaled to 2000 x 500 states x <=256 controls x 9 perturbation nodes
-(1 848 240 000 admissible backups per sweep, 38.6 GB of tables), sharded over
+(1 848 240 000 admissible backups per sweep, 38.6 GB of dense tables), sharded over
 the N GPUs (strong scaling: total work fixed).  One JSON line on stdout.
 
-  value      whole-job backups/s, tables and J resident in HBM, CUDA events on
-             the launching stream, barrier + synchronize on both sides, max over ranks
+  value      whole-job backups/s of a device-resident value iteration, tables and J in
+             HBM, CUDA events on the launching stream, barrier + synchronize on both sides,
+             max over ranks
   e2e        the same metric through the public API with HOST arrays:
-             DPSolver.value_iteration(J_host) -> (J_host, pol_host), i.e. H2D of J,
-             sweep, D2H of J and argmin, host mapping argmin -> control values
-  roofline   HBM: algorithmic bytes (4 + 8d + 8/W per backup) of the
-             streaming kernel / its own CUDA-event duration, vs MEASURED_PEAKS.json
+             DPSolver.value_iteration(J_host) -> (J_host, pol_host)
+  verified   parity of THIS run, outside the timed regions: 1 000 seeded random states of one
+             more sweep - through the timed device path and through value_iteration - against
+             the oracle port of the reference's per-state loop
+  roofline   a utilisation of the unit that bounds the streaming kernel (named by the library,
+             sdp_last_kernel): shared-memory bytes over 128 B/clk/SM for layout CF, streamed /
+             algorithmic table bytes over the measured HBM bandwidth otherwise; the dense-
+             equivalent rate of SURVEY.md 8d is reported beside it as `dense_equivalent`
   cpu_baseline  the oracle port of the reference's numpy/Cython loop, 1 core (the
              reference is single-threaded), on a bounded random sample of states
 
---impl reference times the reference's CPU path (oracle port; its interpolation
-runs through the reference's own compiled Cython routine when oracle/_ref is
-present) on bounded samples of the same workload and prints the same line.
+--impl reference times the UNMODIFIED reference's own per-state backup
+(stodynprog.DPSolver._value_at_state_vect, from the verbatim copy staged under the git-ignored
+oracle/_ref/py with its Cython routine compiled from its own source) on bounded samples of the
+same workload, 1 core, and prints the same line (kind "reference"; the oracle port when the
+staged copy is absent).
+--workload pv: BASELINE configs[1], the time-dependent recursion (see run_pv).
 """
 import argparse
 import json

@@ -62,6 +62,30 @@ def check_column_layout(sdp, wl, rank):
     return bool(ok)
 
 
+def check_tiny_grid_and_late_peer(sdp, wl, rank):
+    """the 10 states of the inventory problem (config #1) over all the ranks: some ranks hold one
+    state, with eight ranks some hold NONE (an empty shard still has to publish its epoch), and
+    one rank arrives a second late at every other sweep (its peers wait on their flags); against
+    the golden fixture of the unmodified reference"""
+    import time
+    from conftest import golden, rel_err
+    G = golden("inventory.npz")
+    prob = wl.inventory(sdp)
+    J, ok = prob.J0, True
+    for k in range(6):
+        if k % 2 == 1 and rank == dist.get_world_size() - 1:
+            time.sleep(1.0)
+        J, u = prob.solver.value_iteration(J, report_time=False)
+        ok &= np.array_equal(u, G["pol"][k]) and rel_err(J, G["J"][k]) <= 1e-10
+    T = prob.solver.last_tables
+    sizes = [None] * dist.get_world_size()
+    dist.all_gather_object(sizes, int(T.n_states))
+    if rank == 0:
+        print("[inventory, 10 states] states per rank %s, late peer tolerated: %s" % (sizes, "OK" if ok else "FAILED"),
+              flush=True)
+    return bool(ok)
+
+
 def check_shared_results(sdp, wl, rank):
     """host results through the shared page-locked segment (hostshare.py): every array handed
     out keeps its values while it is alive - five sweeps whose results are all KEPT (the ring has
@@ -242,6 +266,7 @@ def main():
         ok &= rel_err(Js, G["vi_J2"]) <= 1e-10 and abs(info["residuals"][-1] - r_expected) <= 1e-9 * r_expected
     ok &= check_column_layout(sdp, wl, rank)
     ok &= check_shared_results(sdp, wl, rank)
+    ok &= check_tiny_grid_and_late_peer(sdp, wl, rank)
     if os.environ.get("SDP_CHECK_BENCH_GRID"):
         ok &= check_bench_grid(sdp, wl, rank)
     flag = torch.tensor([1 if ok else 0], device="cuda")
