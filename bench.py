@@ -481,6 +481,9 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
+        if rank == 0 and os.environ.get("SDP_SHARED_TIMING") and getattr(eng, "last_shared_timing", None):
+            sys.stderr.write("shared-results call, host ms per stage [slots, upload, sweep, results, cache check, "
+                             "gpu wait, barrier]: %s\n" % ["%.3f" % (1e3 * x) for x in eng.last_shared_timing])
         nb_J = 8 * n_grid
         nb_pol = 8 * n_grid * len(sv.sys.control)
         copying = world if mode == "all" else 1       # ranks that move host data

@@ -764,10 +764,12 @@ class Engine(object):
         own PCIe link.  Returns (J, pol, J_ref) as views of the slot (None, None, J_ref when
         `want_results` is False), or None when no slot is free (the caller takes the private-
         copy path; same decision on every rank)."""
+        import time
         torch = _torch()
         world, rank = self.coll.world, self.coll.rank
         n_grid, nc = hs.n_grid, hs.nc
         px = self.peer_exchange(n_grid)
+        tm = [time.perf_counter()]
         # 1. where is the input, which slot takes the output (rank 0's array decides)
         src = -2
         if rank == 0:
@@ -786,6 +788,7 @@ class Engine(object):
         if out is None:
             return None
         J_src = hs.stage_J() if src < 0 else hs.slot_J(src)
+        tm.append(time.perf_counter())
         # 2. upload 1/N, hand it to the peers
         J_prev, J_new = self.J_pair(n_grid)
         self.begin_call(n_grid)
@@ -796,9 +799,11 @@ class Engine(object):
             if r != rank:
                 px.peer_view(r, k)[a:b].copy_(J_prev[a:b], non_blocking=True)
         px.barrier()
+        tm.append(time.perf_counter())
         # 3. the sweep; J_new and the argmin are complete on every rank after the flag wait
         ref_out = torch.zeros(1, dtype=torch.float64, device=self.device) if rel_ref_index is not None else None
         self.sweep(T, J_prev, J_new, rel_ref_index=rel_ref_index, ref_out=ref_out)
+        tm.append(time.perf_counter())
         # 4. 1/N of the results -> the shared slot
         pol = torch.empty((b - a, max(nc, 1)), dtype=torch.float64, device=self.device)
         if nc and b > a:
@@ -815,10 +820,17 @@ class Engine(object):
         if ref_out is not None:
             ref_host = self.host_result_buffer((1,), torch.float64)
             ref_host.copy_(ref_out, non_blocking=True)
+        tm.append(time.perf_counter())
         if while_waiting is not None:
             while_waiting()
+        tm.append(time.perf_counter())
         self.torch_stream.synchronize() if self._cuda else None
+        tm.append(time.perf_counter())
         hs.barrier()
+        tm.append(time.perf_counter())
+        # host-side seconds: [agree on slots, enqueue upload + hand-over, enqueue sweep, enqueue result
+        # copies, cache check, wait for the GPU, host barrier] (diagnostics, bench --shared-timing)
+        self.last_shared_timing = [b_ - a_ for a_, b_ in zip(tm[:-1], tm[1:])]
         J_ref = float(ref_host[0]) if ref_host is not None else None
         if not want_results:
             return None, None, J_ref
