@@ -367,6 +367,11 @@ int sdp_p2p_wait(const SdpPeers* peers, void* stream);
 int sdp_sweep_partials_after(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
                              double* part_val, int32_t* part_idx, const SdpPeers* wait_for,
                              void* stream);
+/* Hand a piece of J to the peers: src[offset .. offset+n) (this rank's device copy) is stored at the
+ * same indices of every OTHER rank's peers->J buffer, then the epoch is published as by
+ * sdp_sweep_finalize_p2p (follow with sdp_p2p_wait; every rank calls it, n may be 0).  Used when
+ * every rank uploads 1/N of the next sweep's input from host memory shared by the ranks. */
+int sdp_p2p_broadcast(const double* src, int64_t offset, int64_t n, const SdpPeers* peers, void* stream);
 /* Stream-ordered barrier over the ranks: epoch += 1, publish, wait. */
 int sdp_p2p_barrier(const SdpPeers* peers, void* stream);
 

@@ -69,7 +69,7 @@ for STEP in "$@"; do
         L=$OUT/${TAG}_sanitizer_${TOOL}_n$N.log
         if [ "$N" -gt 1 ]; then
           PORT=$((PORT+1))
-          ( time timeout 1200 compute-sanitizer --tool $TOOL --target-processes all --error-exitcode 9 \
+          ( time timeout 1200 compute-sanitizer --tool $TOOL --target-processes all --report-api-errors no --error-exitcode 9 \
               $TR --master-port $PORT scripts/sanitizer_target.py ) > $L 2>&1
         else
           ( time timeout 1200 compute-sanitizer --tool $TOOL --error-exitcode 9 python scripts/sanitizer_target.py ) > $L 2>&1

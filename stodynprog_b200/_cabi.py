@@ -145,6 +145,7 @@ SIGNATURES = {
     "sdp_sweep_partials_after": (ctypes.c_int, [_gp, ctypes.POINTER(SdpTables), _vp, _vp, _vp,
                                                 ctypes.POINTER(SdpPeers), _vp]),
     "sdp_p2p_barrier": (ctypes.c_int, [ctypes.POINTER(SdpPeers), _vp]),
+    "sdp_p2p_broadcast": (ctypes.c_int, [_vp, _i64, _i64, ctypes.POINTER(SdpPeers), _vp]),
     "sdp_policy_eval": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
                                        _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
     "sdp_policy_eval_p2p": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,

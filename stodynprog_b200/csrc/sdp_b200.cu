@@ -2887,6 +2887,35 @@ extern "C" int sdp_p2p_wait(const SdpPeers* peers, void* stream) {
     return SDP_OK;
 }
 
+// n values of src (this rank's copy, device) starting at `offset` -> the same place of every
+// OTHER rank's J buffer, then the epoch (follow with sdp_p2p_wait): the hand-over of an uploaded
+// piece of J to the peers in one launch
+__global__ void __launch_bounds__(256)
+k_p2p_broadcast(const double* __restrict__ src, int64_t offset, int64_t n, PeersDev P) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = src[offset + i];
+#pragma unroll
+        for (int q = 0; q < SDP_MAX_PEERS; ++q)
+            if (q < P.world && q != P.rank) P.J[q][offset + i] = v;
+    }
+    publish_epoch(P);
+}
+
+extern "C" int sdp_p2p_broadcast(const double* src, int64_t offset, int64_t n, const SdpPeers* peers, void* stream) {
+    PeersDev P;
+    int rc = make_peers(peers, &P, "sdp_p2p_broadcast");
+    if (rc) return rc;
+    if (offset < 0 || n < 0 || (n > 0 && !src)) return fail(SDP_EINVAL, "%s", "sdp_p2p_broadcast: bad arguments");
+    for (int r = 0; r < P.world; ++r)
+        if (!P.J[r]) return fail(SDP_EINVAL, "%s", "sdp_p2p_broadcast: NULL J buffer");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks < 1) blocks = 1;            // (an empty piece still publishes the epoch)
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_p2p_broadcast<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, offset, n, P);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
 extern "C" int sdp_sweep_partials_after(const SdpGrid* grid, const SdpTables* tab, const double* J_prev,
                                         double* part_val, int32_t* part_idx, const SdpPeers* wait_for,
                                         void* stream) {

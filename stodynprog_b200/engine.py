@@ -790,15 +790,17 @@ class Engine(object):
         J_src = hs.stage_J() if src < 0 else hs.slot_J(src)
         tm.append(time.perf_counter())
         # 2. upload 1/N, hand it to the peers
+        # (no begin_call barrier: every rank passed the host barrier above after synchronising its
+        # previous call, so nobody still touches the J buffers)
         J_prev, J_new = self.J_pair(n_grid)
-        self.begin_call(n_grid)
+        self.flush_exchange()
         a, b = n_grid * rank // world, n_grid * (rank + 1) // world
         k = px.index_of(J_prev)
         J_prev[a:b].copy_(J_src[a:b], non_blocking=True)
-        for r in range(world):
-            if r != rank:
-                px.peer_view(r, k)[a:b].copy_(J_prev[a:b], non_blocking=True)
-        px.barrier()
+        rc = self.lib.sdp_p2p_broadcast(self._ptr(J_prev), a, b - a, ctypes.byref(px.peers_J_only[k]), self.stream)
+        _cabi.check(rc, "sdp_p2p_broadcast")
+        rc = self.lib.sdp_p2p_wait(ctypes.byref(px.peers_J_only[k]), self.stream)
+        _cabi.check(rc, "sdp_p2p_wait")
         tm.append(time.perf_counter())
         # 3. the sweep; J_new and the argmin are complete on every rank after the flag wait
         ref_out = torch.zeros(1, dtype=torch.float64, device=self.device) if rel_ref_index is not None else None
