@@ -953,6 +953,63 @@ class Engine(object):
     SCAN_PROCS = int(os.environ.get("SDP_SCAN_PROCS", "1"))
     SCAN_PARALLEL_MIN_STATES = 200 * 1000
 
+    def _scan_boxes(self, solver, t_k, state_grid, n_grid, mode):
+        """Pass 1 of a table build: the admissible box and control-grid sizes of every state of the
+        grid.  Every rank scans an equal share (one vectorised call; else one call per distinct
+        box; else per state, optionally on forked workers), the host table is replicated.
+        Returns (HostStateTable of the whole grid, this rank's state tuples if they were made)."""
+        sys = solver.sys
+        coll = self.coll
+        world, rank = coll.world, coll.rank
+        nb_control = len(sys.control)
+        eq = [n_grid * r // world for r in range(world + 1)]
+        mine = None
+        # the scan used to be by far the longest host stage: the last one is kept, so that a second
+        # layout of the same problem (dense after factored, a re-cut of the slabs) does not repeat
+        # it; DPSolver.clear_tables() drops it
+        scan_key = (t_k, id(sys.control_box), repr(sorted(sys.params.items())) if sys.params else "",
+                    tuple(float(c) for c in solver.control_steps),
+                    tuple(g.tobytes() for g in state_grid), world)
+        host_full = None
+        if self._scan_cache is not None and self._scan_cache[0] == scan_key:
+            host_full = self._scan_cache[1]
+            # the box function may read globals / closure cells that changed since the scan
+            # (the reference calls it afresh in every sweep): re-check three states
+            probe = sorted({0, n_grid // 2, n_grid - 1})
+            now = tb.scan_control_boxes(sys, solver.control_steps,
+                                        [tb.state_tuples_at(state_grid, i, i + 1)[0] for i in probe], t_k)
+            if not (np.array_equal(now.lo.view(np.int64), host_full.lo[probe].view(np.int64))
+                    and np.array_equal(now.hi.view(np.int64), host_full.hi[probe].view(np.int64))
+                    and np.array_equal(now.npts, host_full.npts[probe])):
+                host_full = None
+        if host_full is None:
+            part = None
+            if mode != "per_state":
+                # one vectorised control_box call, trusted only if sample states agree
+                # bit-for-bit with the reference's per-state calls
+                part = tb.scan_control_boxes_batched(sys, solver.control_steps, state_grid,
+                                                     eq[rank], eq[rank + 1], t_k)
+            if part is None and mode != "per_state":
+                # box functions that read only some of the state variables (the storage
+                # examples): one call per distinct box, checked on sample states
+                part = tb.scan_control_boxes_by_axes(sys, solver.control_steps, state_grid,
+                                                     eq[rank], eq[rank + 1], t_k)
+            if part is None and world == 1 and self.SCAN_PROCS > 1 and n_grid >= self.SCAN_PARALLEL_MIN_STATES:
+                # box functions that do not vectorise (np.max((a, b)) on scalars, as in the
+                # reference's examples): one call per state, on several host cores
+                part = tb.scan_control_boxes_parallel(sys, solver.control_steps, state_grid,
+                                                      eq[rank], eq[rank + 1], t_k, self.SCAN_PROCS)
+            if part is None:
+                mine = tb.state_tuples(state_grid, eq[rank], eq[rank + 1])
+                part = tb.scan_control_boxes(sys, solver.control_steps, mine, t_k)
+            parts = coll.all_gather_object((part.lo, part.hi, part.npts))
+            host_full = tb.HostStateTable(n_grid, nb_control)
+            host_full.lo = np.concatenate([p[0] for p in parts], axis=0)
+            host_full.hi = np.concatenate([p[1] for p in parts], axis=0)
+            host_full.npts = np.concatenate([p[2] for p in parts], axis=0)
+            self._scan_cache = (scan_key, host_full)
+        return host_full, mine
+
     def build_sweep_tables(self, solver, t_k=None, reuse=None):
         """Tabulate the user's callables over this rank's shard and build the tables on the
         device (see _build_sweep_tables).  With several ranks and slab_axis "auto" the grid is
@@ -996,56 +1053,11 @@ class Engine(object):
         world, rank = coll.world, coll.rank
         dev = self.device
 
-        # pass 1: control boxes. Every rank scans an equal share, then the full
-        # host table is replicated (it is needed to map argmin -> control values).
-        eq = [n_grid * r // world for r in range(world + 1)]
+        # pass 1: control boxes (replicated host table, needed to map argmin -> control values)
         mode = getattr(solver, "tabulate", "auto")
-        mine = None
         nb_control = len(sys.control)
-        # the scan is by far the longest host stage (one Python call per state): the last
-        # one is kept, so that a second layout of the same problem (dense after factored,
-        # a re-cut of the slabs) does not repeat it; DPSolver.clear_tables() drops it
-        scan_key = (t_k, id(sys.control_box), repr(sorted(sys.params.items())) if sys.params else "",
-                    tuple(float(c) for c in solver.control_steps),
-                    tuple(g.tobytes() for g in state_grid), world)
-        host_full = None
-        if self._scan_cache is not None and self._scan_cache[0] == scan_key:
-            host_full = self._scan_cache[1]
-            # the box function may read globals / closure cells that changed since the scan
-            # (the reference calls it afresh in every sweep): re-check three states
-            probe = sorted({0, n_grid // 2, n_grid - 1})
-            now = tb.scan_control_boxes(sys, solver.control_steps,
-                                        [tb.state_tuples_at(state_grid, i, i + 1)[0] for i in probe], t_k)
-            if not (np.array_equal(now.lo.view(np.int64), host_full.lo[probe].view(np.int64))
-                    and np.array_equal(now.hi.view(np.int64), host_full.hi[probe].view(np.int64))
-                    and np.array_equal(now.npts, host_full.npts[probe])):
-                host_full = None
-        if host_full is None:
-            part = None
-            if mode != "per_state":
-                # one vectorised control_box call, trusted only if sample states agree
-                # bit-for-bit with the reference's per-state calls
-                part = tb.scan_control_boxes_batched(sys, solver.control_steps, state_grid,
-                                                     eq[rank], eq[rank + 1], t_k)
-            if part is None and mode != "per_state":
-                # box functions that read only some of the state variables (the storage
-                # examples): one call per distinct box, checked on sample states
-                part = tb.scan_control_boxes_by_axes(sys, solver.control_steps, state_grid,
-                                                     eq[rank], eq[rank + 1], t_k)
-            if part is None and world == 1 and self.SCAN_PROCS > 1 and n_grid >= self.SCAN_PARALLEL_MIN_STATES:
-                # box functions that do not vectorise (np.max((a, b)) on scalars, as in the
-                # reference's examples): one call per state, on several host cores
-                part = tb.scan_control_boxes_parallel(sys, solver.control_steps, state_grid,
-                                                      eq[rank], eq[rank + 1], t_k, self.SCAN_PROCS)
-            if part is None:
-                mine = tb.state_tuples(state_grid, eq[rank], eq[rank + 1])
-                part = tb.scan_control_boxes(sys, solver.control_steps, mine, t_k)
-            parts = coll.all_gather_object((part.lo, part.hi, part.npts))
-            host_full = tb.HostStateTable(n_grid, nb_control)
-            host_full.lo = np.concatenate([p[0] for p in parts], axis=0)
-            host_full.hi = np.concatenate([p[1] for p in parts], axis=0)
-            host_full.npts = np.concatenate([p[2] for p in parts], axis=0)
-            self._scan_cache = (scan_key, host_full)
+        eq = [n_grid * r // world for r in range(world + 1)]
+        host_full, mine = self._scan_boxes(solver, t_k, state_grid, n_grid, mode)
         U_all = host_full.U.astype(np.int64)
         if U_all.max(initial=0) >= 2 ** 31 - 4:
             raise ValueError("more than 2^31 control combinations for one state")
