@@ -1315,6 +1315,7 @@ class Engine(object):
                 ensure("g", max(g_len, 4), torch.float64)
                 done = [0]      # states flushed so far (chunks arrive in order)
                 del flushes[:], chunk_record[:]
+                chunk_grids = {}
 
                 def flush(desc, staging):
                     if u_mask:
@@ -1385,7 +1386,9 @@ class Engine(object):
                     tb.tabulate_states_batched(sys, state_grid, sb, se, host, w_grid, t_k, entry_off,
                                                g_off, Upad, g_per_w, flush, align=align,
                                                verify=1 if prev_mode == "batched" else 8,
-                                               grid_cache=self._grid_cache if t_k is not None else None,
+                                               # (chunks of a column-ordered grid repeat the same rows of
+                                               # control grids: kept for the duration of this build)
+                                               grid_cache=self._grid_cache if t_k is not None else chunk_grids,
                                                flat_index=flat_eff, valid=valid,
                                                record=chunk_record if keep_staging else None)
                 else:

@@ -69,6 +69,13 @@ class HostShare(object):
         self.size = (self._off_slot[-1] + jb + pb + 4095) // 4096 * 4096
         name = None
         if self.rank == 0:
+            # (a tmpfs smaller than the segment would only fail at the first page fault, with SIGBUS)
+            st = os.statvfs("/dev/shm")
+            if st.f_bavail * st.f_frsize < self.size + (64 << 20):
+                name = ""
+        if coll.all_gather_object(name)[0] == "":
+            raise RuntimeError("/dev/shm is too small for %d MB of shared result slots" % (self.size >> 20))
+        if self.rank == 0:
             name = "/dev/shm/sdp_b200_%d_%x" % (os.getpid(), int(time.time() * 1e6) & 0xffffffff)
             fd = os.open(name, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
             os.ftruncate(fd, self.size)
