@@ -1478,6 +1478,19 @@ class Engine(object):
                 chunk = pick_item_chunk(unit_U, 128 if not tiled else 32,
                                         **({"target": sm_count * 16 * 48} if col else {}))
             T.item_chunk = chunk
+            if col and not pairs and self.COLUMN_TAIL_FRACTION > 0 and chunk >= 32:
+                # layout CF: the warps of a CTA meet at a barrier at the end of every (band, column)
+                # run of tiles and wait for the one that took the last item; the last tiles of every
+                # run are cut into runs of half the length, handed out last, so that the wait is
+                # half an item shorter (it weighs on the short sweeps of a multi-GPU shard)
+                bt, tb0 = T.bands["tiles"], T.bands["tile_begin"]
+                chunk_arr = np.full(len(unit_U), chunk, dtype=np.int64)
+                for b, tpc in enumerate(bt):
+                    tail = int(round(tpc * self.COLUMN_TAIL_FRACTION))
+                    if tail > 0:
+                        t_in = np.arange(tb0[b + 1] - tb0[b]) % tpc
+                        chunk_arr[tb0[b]:tb0[b + 1]][t_in >= tpc - tail] = chunk // 2
+                chunk = chunk_arr
             if tiled:
                 per_entry = Wf * 32
                 g_unit_off = tile_off if (T.g_per_w or u_mask) else tile_g_off
@@ -1598,6 +1611,8 @@ class Engine(object):
         return T
 
     COLUMN_SEGS_PER_SM = int(os.environ.get("SDP_COLUMN_SEGS_PER_SM", "1"))
+    # share of the tiles at the end of every (band, column) run whose work items are half as long
+    COLUMN_TAIL_FRACTION = float(os.environ.get("SDP_COLUMN_TAIL_FRACTION", "0"))
     # launch shape of a band's sweep (SdpTables.col_launch_hint): 640 threads, round-robin - measured
     # on config #5 with ~10 column pieces per CTA (profiles/r2_emu_variants_bands.txt): 1.256 ms
     # against 1.346 ms for the 768-thread first-come-first-served shape that is best (1.146 against
