@@ -2029,41 +2029,17 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
 
         // the warps share the items of the column: round-robin, or (dynamic) first come first
         // served - the items differ in length and a column piece may hold only a few of them
-        // Software pipeline over the items: a warp takes its NEXT item while it still works on the
-        // current one - the item record and the lane's control count travel behind the current
-        // item's arithmetic, and the first rows of the next item's u-part are pulled into L2 -
-        // instead of paying the two dependent memory latencies at the head of every item
-        // (5.5 % of the stall samples of config #5 sat there, twice that on a shard of an 8-GPU run).
-        int round = 0;
-        auto take = [&](int rnd) -> int64_t {
-            int k = rnd * nwarps + warp;
+        for (int round = 0;; ++round) {
+            int k = round * nwarps + warp;
             if (dynamic) {
                 if (lane == 0) k = atomicAdd(&next_item, 1);
                 k = __shfl_sync(0xffffffffu, k, 0);
             }
-            return i + k;
-        };
-        int64_t pos = take(round);
-        bool have = pos < e;
-        int64_t item_id = 0;
-        SdpItem it = {};
-        int Us = 0;
-        if (have) {
-            item_id = T.item_order ? T.item_order[pos] : pos;
-            it = T.items[item_id];
-            Us = T.U[(int64_t)it.state * 32 + lane];      // by position; 0 on padding lanes
-        }
-        while (have) {
-            const int64_t pos_n = take(++round);
-            const bool have_n = pos_n < e;
-            int64_t id_n = 0;
-            SdpItem it_n = {};
-            int Us_n = 0;
-            if (have_n) {
-                id_n = T.item_order ? T.item_order[pos_n] : pos_n;
-                it_n = T.items[id_n];
-                Us_n = T.U[(int64_t)it_n.state * 32 + lane];
-            }
+            const int64_t pos = i + k;
+            if (pos >= e) break;
+            const int64_t item_id = T.item_order ? T.item_order[pos] : pos;
+            const SdpItem it = T.items[item_id];
+            const int Us = T.U[(int64_t)it.state * 32 + lane];      // by position; 0 on padding lanes
             const int32_t* __restrict__ cup = T.cell + it.entry_base + lane;
             const double* __restrict__ lup = T.lam + it.entry_base + lane;
             const double* __restrict__ gp = T.g + it.g_base + lane;
@@ -2084,15 +2060,6 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
                     g_n[s][b] = __ldcs(gp + o);
                     l_n[s][b] = __ldcs(lup + o);
                 }
-            if (have_n) {
-                // (the next item's first two rows of the u-part: one line of cells, two of weights / costs)
-                const int64_t o1 = (int64_t)min(1, it_n.u_count - 1) * 32;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(T.cell + it_n.entry_base + o1 + lane));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(T.lam + it_n.entry_base + lane));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(T.lam + it_n.entry_base + o1 + lane));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(T.g + it_n.g_base + lane));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(T.g + it_n.g_base + o1 + lane));
-            }
             for (int uu0 = 0; uu0 < it.u_count; uu0 += UB * PF) {
 #pragma unroll
                 for (int s = 0; s < PF; ++s) {
@@ -2147,10 +2114,6 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
             }
             part_val[item_id * 32 + lane] = best_v;
             part_idx[item_id * 32 + lane] = best_i;
-            have = have_n;
-            item_id = id_n;
-            it = it_n;
-            Us = Us_n;
         }
         i = e;
     }
