@@ -44,6 +44,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))      # workloads.py: the benchmark problem definitions
 
 METRIC = "bellman_backups_per_sec"
 UNIT = "backups/s"
@@ -122,7 +124,7 @@ def workload_config(name, dims, W):
 
 
 def make_problem(api, args, **solver_kw):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     if args.workload == "ar1":
         return wl.storage_ar1(api, **solver_kw), "howto storage-AR1 41x61 (BASELINE configs[2])"
     prob = wl.storage_ar1_large(api, n_E=args.n_E, n_P=args.n_P, **solver_kw)
@@ -627,7 +629,8 @@ def run_pv(args):
     import io
     import torch
     import stodynprog_b200 as sdp
-    from stodynprog_b200 import workloads as wl, _cabi
+    import workloads as wl
+    from stodynprog_b200 import _cabi
     from stodynprog_b200 import build as product_build
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -685,7 +688,7 @@ def measure_config3(sdp, peak, peak_src, sm_count, sm_mhz, steps=50, warmup=5):
     backups per sweep): the grid the north star's 60 % roofline target is quoted on.
     Reported for the default (factored) tables and for the dense tables."""
     import torch
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     out = {"workload": "howto storage-AR1 41x61 x 4001..8001 controls x 9 nodes"}
     for compress in ("auto", "off"):
         prob = wl.storage_ar1(sdp)

@@ -263,7 +263,7 @@ class PortSolver(object):
 
 
 class _PortAPI(object):
-    """`api` object for stodynprog_b200.workloads factories"""
+    """`api` object for the tests/workloads.py factories"""
 
     def __init__(self, interp="c"):
         from stodynprog_b200.sysdesc import SysDescription

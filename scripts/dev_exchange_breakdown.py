@@ -12,6 +12,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 os.environ.setdefault("SDP_P2P_TIMEOUT_S", "60")
@@ -19,7 +20,8 @@ rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import stodynprog_b200 as sdp  # noqa: E402
-from stodynprog_b200 import workloads as wl, _cabi  # noqa: E402
+import workloads as wl  # noqa: E402
+from stodynprog_b200 import _cabi  # noqa: E402
 
 sv = wl.storage_ar1_large(sdp).solver
 eng = sv.engine

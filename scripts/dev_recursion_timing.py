@@ -11,8 +11,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import stodynprog_b200 as sdp  # noqa: E402
-from stodynprog_b200 import workloads as wl  # noqa: E402
+import workloads as wl  # noqa: E402
 from oracle.ref_port import port_api  # noqa: E402
 
 

@@ -11,8 +11,10 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import stodynprog_b200 as sdp  # noqa: E402
-from stodynprog_b200 import workloads as wl, _cabi  # noqa: E402
+import workloads as wl  # noqa: E402
+from stodynprog_b200 import _cabi  # noqa: E402
 from stodynprog_b200.engine import partition_by_weight  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8

@@ -9,9 +9,10 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import stodynprog_b200 as sdp  # noqa: E402
-from stodynprog_b200 import workloads as wl  # noqa: E402
+import workloads as wl  # noqa: E402
 from dev_timing import time_sweeps  # noqa: E402
 
 for compress in ("auto", "off"):

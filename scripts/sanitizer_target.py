@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 import stodynprog_b200 as sdp  # noqa: E402
-from stodynprog_b200 import workloads as wl  # noqa: E402
+import workloads as wl  # noqa: E402
 from stodynprog_b200.engine import Engine  # noqa: E402
 from oracle.ref_port import port_api  # noqa: E402
 

@@ -6,7 +6,7 @@ Run in the build container only (needs /root/reference):
 The reference is imported from where it lies through oracle/ref_loader.py
 (environment shims only, no source change) with its Cython routine compiled by
 oracle/build_ref.py.  Problem definitions come from
-stodynprog_b200/workloads.py, instantiated against the reference's own
+tests/workloads.py, instantiated against the reference's own
 SysDescription / DPSolver classes.  Outputs (.npz, compressed) are committed;
 the GPU box has no /root/reference and only reads the fixtures.
 
@@ -38,7 +38,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle.ref_loader import load_reference, load_reference_cython  # noqa: E402
-from stodynprog_b200 import workloads as wl  # noqa: E402
+import workloads as wl  # noqa: E402
 sys.path.insert(0, HERE)
 from make_golden_cases import column_cases  # noqa: E402
 

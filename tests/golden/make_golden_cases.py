@@ -4,7 +4,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from stodynprog_b200 import workloads as wl  # noqa: E402
+import workloads as wl  # noqa: E402
 
 
 def column_cases(api, **kw):

@@ -203,7 +203,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import stodynprog_b200 as sdp
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from conftest import golden, rel_err
     G = golden("storage_ar1.npz")
     layouts = ["control_minor", "state_minor"]

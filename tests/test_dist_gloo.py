@@ -47,7 +47,7 @@ def _worker(rank, world, port, out_dir, layout):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import stodynprog_b200 as sdp
-        from stodynprog_b200 import workloads as wl
+        import workloads as wl
         from fake_lib import FakeLib
         prob, sv, J0 = _problem(sdp, wl, FakeLib(), layout)
         J1, pol1 = sv.value_iteration(J0, report_time=False)
@@ -89,7 +89,7 @@ def test_sharded_sweep_world2_matches_single_process(tmp_path, layout):
     # single-process run of the same thing
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import stodynprog_b200 as sdp
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from fake_lib import FakeLib
     prob, sv, J0 = _problem(sdp, wl, FakeLib(), layout)
     J1, pol1 = sv.value_iteration(J0, report_time=False)

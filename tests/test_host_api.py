@@ -125,7 +125,7 @@ class TestSysDescription:
 
 # --- DPSolver host logic -------------------------------------------------------
 def test_discretize_and_reference_state():
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     sv = wl.storage_ar1(sdp).solver
     assert sv._state_grid_shape == (41, 61)
     assert sv._state_ref_ind == (20, 30)
@@ -140,7 +140,7 @@ def test_discretize_and_reference_state():
 
 
 def test_discrete_pmf_must_sum_to_one():
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     sv = wl.inventory(sdp).solver
     assert list(sv.perturb_proba[0]) == [0.2, 0.4, 0.3, 0.1]
     with pytest.raises(AssertionError):
@@ -148,7 +148,7 @@ def test_discrete_pmf_must_sum_to_one():
 
 
 def test_control_grids_match_port(port):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     import itertools
     a = wl.storage_ar1(sdp).solver
     b = wl.storage_ar1(port).solver
@@ -268,7 +268,7 @@ def test_pick_item_chunk():
 
 
 def test_interp_on_state_errors():
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     sv = wl.storage_ar1(sdp, n_E=5, n_P=6).solver
     with pytest.raises(ValueError) as e:
         sv.interp_on_state(np.zeros((6, 5)))
@@ -282,7 +282,7 @@ def test_interp_on_state_errors():
 
 def test_print_summary_matches_notebook(capsys):
     """examples/howto storage-AR1.ipynb cell 8 output"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     sv = wl.storage_ar1(sdp).solver
     sv.print_summary()
     out = capsys.readouterr().out
@@ -418,7 +418,8 @@ def test_parallel_control_box_scan(monkeypatch):
     """the per-state control_box scan on forked workers: same boxes and grid sizes, bit for
     bit; None (serial scan takes over) when a worker fails; used by the table build of large
     single-rank grids"""
-    from stodynprog_b200 import tabulate as tb, workloads as wl
+    import workloads as wl
+    from stodynprog_b200 import tabulate as tb
     from stodynprog_b200.engine import Engine
     from fake_lib import FakeLib
     sv = wl.storage_ar1(sdp, n_E=23, n_P=7, steps=(0.3, 0.1), _test_lib=FakeLib()).solver
@@ -458,7 +459,7 @@ def test_control_box_scan_by_axes():
     vectorisable) are scanned once per distinct box and checked on sample states: same table,
     bit for bit; a box that reads every axis, or one whose dependence hides from the probe but not
     from the check, gives None (per-state scan)"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from fake_lib import FakeLib
     sv = wl.storage_ar1(sdp, n_E=90, n_P=70, steps=(0.3, 0.1), _test_lib=FakeLib()).solver
     n = 90 * 70
@@ -494,7 +495,7 @@ def test_control_box_scan_by_axes():
 def test_batched_tabulation_checks_every_chunk():
     """a cost that is not element-wise over the state axis in ONE region of the state space only
     must be caught although the first chunk verifies: the batched mode is abandoned"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from fake_lib import FakeLib
     prob = wl.storage_ar1(sdp, n_E=64, n_P=8, steps=(0.5, 0.1), _test_lib=FakeLib())
     sv = prob.solver
@@ -528,7 +529,7 @@ def test_cached_tables_follow_the_callables(port):
     """The reference calls dyn / cost / control_box afresh in every sweep, so a change of a
     global or closure variable they read takes effect at once (its doc/example_inventory.py cost
     reads h, p, c).  Cached tables are re-validated on probe states and rebuilt."""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from fake_lib import FakeLib
     price = [1.0]
 
@@ -587,7 +588,7 @@ def test_host_interpolation_routine_is_bit_exact(product, d):
 def test_no_cpu_fallback(product):
     """without a GPU the product refuses to run; without the library it says so"""
     import torch
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     if not torch.cuda.is_available():
         sv = wl.inventory(sdp).solver
         with pytest.raises(_cabi.SdpLibraryError):

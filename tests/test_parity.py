@@ -187,7 +187,7 @@ def test_MultilinearInterpolator_R2R2(product):
 
 @gpu
 def test_interp_on_state_broadcast(product, port):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     prob = wl.storage_ar1(product, n_E=11, n_P=13)
     ora = wl.storage_ar1(port, n_E=11, n_P=13)
     A = np.random.default_rng(3).standard_normal((11, 13))
@@ -205,7 +205,7 @@ def test_interp_on_state_broadcast(product, port):
 # config #1: inventory (doc/example_inventory.rst:217-239 + reference run)
 # ---------------------------------------------------------------------------
 def test_inventory_golden(api):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     G = golden("inventory.npz")
     prob = wl.inventory(api)
     J = prob.J0
@@ -224,7 +224,7 @@ def test_inventory_golden(api):
 # ---------------------------------------------------------------------------
 def test_pv_storage_bellman_recursion_vs_port(api, port):
     """short horizon, coarse control step (the model backend is slow)"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     prob = wl.pv_storage(api, horizon=30)
     prob.solver.control_steps = (.01,)
     J, pol = prob.solver.bellman_recursion(30, prob.J_fin, report_time=False)
@@ -242,7 +242,7 @@ def test_recursion_fast_path_and_its_refusals(api, port):
     once and the sweeps run back to back (Engine.recursion_fast) - same J and policies, bit for
     bit, as the instant-by-instant path; dynamics or admissible controls that do depend on
     the instant are detected and take the instant-by-instant path (and match the port)"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     out = {}
     for mode in ("auto", "per_instant"):
         prob = wl.pv_storage(api, horizon=12)
@@ -278,7 +278,7 @@ def test_recursion_fast_path_and_its_refusals(api, port):
 
 @gpu
 def test_pv_storage_full_horizon_golden(cuda_api):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     G = golden("pv_storage.npz")
     prob = wl.pv_storage(cuda_api)
     J, pol = prob.solver.bellman_recursion(prob.horizon, prob.J_fin, report_time=False)
@@ -292,7 +292,7 @@ def test_pv_storage_full_horizon_golden(cuda_api):
 # ---------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def ar1(cuda_api):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     return wl.storage_ar1(cuda_api)
 
 
@@ -344,7 +344,7 @@ def test_storage_ar1_policy_iteration_golden(ar1, capsys):
 def test_storage_ar1_random_J_vs_port(ar1, port):
     """non-trivial J (no ties): argmin index and J against the numpy port on a
     subset of states, plus exact agreement with the ordered-sum C oracle."""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     ora = wl.storage_ar1(port)
     J0 = np.random.default_rng(0).standard_normal((41, 61))
     J, pol = ar1.solver.value_iteration(J0, report_time=False)
@@ -369,7 +369,7 @@ def test_storage_ar1_sup_norm_and_device_loop(ar1):
 
 def test_item_chunking_invariance(api):
     """splitting a state's controls into runs must not change anything"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     J0 = np.random.default_rng(5).standard_normal((9, 11))
     res = []
     for chunk in (64, 512, 100000):
@@ -383,7 +383,7 @@ def test_item_chunking_invariance(api):
 # config #4: SEAREV (3-D)
 # ---------------------------------------------------------------------------
 def _searev_small(api, **kw):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     prob = wl.searev(api, n_E=7, n_S=11, n_A=11, **kw)
     prob.solver.control_steps = (.01,)
     return prob
@@ -621,7 +621,7 @@ def test_abi_rejects_bad_arguments(eng):
 @pytest.mark.parametrize("layout", ["control_minor", "state_minor"])
 @pytest.mark.parametrize("which", ["storage_ar1", "searev", "toy_w", "curtail"])
 def test_batched_tabulation_is_bit_identical(product, backend, layout, which):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     tabs = []
     for mode in ("per_state", "batched"):
         api = _Api(product, backend, layout, mode, "off")
@@ -751,7 +751,7 @@ FACTOR_CASES = {
 
 
 def _factor_case(api, which):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     if which == "storage_ar1":
         return wl.storage_ar1(api, n_E=9, n_P=11, steps=(0.01, 0.1)).solver
     if which == "searev":
@@ -802,7 +802,8 @@ def test_factored_tables_and_sweep_equal_dense(product, backend, layout, which):
 def test_hoisted_inner_interpolation_is_bit_identical(product, which):
     """AF kernel with and without the per-item table of inner interpolations; the
     constant-W kernel with all slots live (W = 3, 5, 9) and with idle slots (W = 2, 4, 7)"""
-    from stodynprog_b200 import _cabi, workloads as wl
+    import workloads as wl
+    from stodynprog_b200 import _cabi
     api = _Api(product, "cuda", "control_minor", "auto", "on")
     if which.startswith("storage_ar1_w"):
         sv = wl.storage_ar1(api, n_E=9, n_P=11, n_w=int(which[-1]), steps=(0.01, 0.1)).solver
@@ -862,7 +863,7 @@ def _coupled_w_system(api, n0=40, **kw):
 
 
 def _column_case(api, which):
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     if which.startswith("ar1_w"):
         # 70 rows: 3 tiles per column, the last one with 26 padding lanes; control step 0.5 =
         # 3.5 grid rows; W = 9, 5, 3 fill the unrolled slots, W = 7, 4, 2 leave idle ones
@@ -954,7 +955,7 @@ def test_column_hoist_is_bit_identical(product, backend, which):
 def test_column_hoist_solvers_and_chunking(product, backend):
     """the other drivers on top of layout CF: relative DP, policy iteration, the
     device-resident loop; explicit work-item lengths"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     out = []
     for colmode, chunk in (("off", None), ("on", None), ("on", 4), ("on", 512)):
         api = _Api(product, backend, "state_minor", "auto", "on")
@@ -1012,7 +1013,7 @@ def test_column_cases_golden(product, backend, colmode, capsys):
 def test_column_hoist_row_bands(product, backend, which, monkeypatch):
     """layout CF with the rows cut into several bands (tiles ordered band by band, one
     combine launch per band): same J and policies, bit for bit, as one band and as BF"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from stodynprog_b200.engine import Engine
     out = {}
     for bands in ("off", "1", "3", "5"):
@@ -1046,7 +1047,7 @@ def test_column_hoist_band_launch_plan(product, monkeypatch):
     union must equal the one-launch sweep"""
     import ctypes
     import torch
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from stodynprog_b200.engine import Engine
     monkeypatch.setattr(Engine, "COLUMN_BANDS", "3")
     api = _Api(product, "model", "state_minor", "auto", "on")
@@ -1162,7 +1163,7 @@ def test_unfactorable_systems_fall_back_to_dense(product):
     with pytest.raises(ValueError):
         sv.sweep_tables()
     # deterministic and 1-D systems have nothing to factor
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     api = _Api(product, "model", "control_minor", "auto", "auto")
     assert not wl.inventory(api).solver.sweep_tables().factored
 
@@ -1216,7 +1217,7 @@ def test_searev_full_policy_iteration_golden(cuda_api, capsys):
     policy_iteration(pol_lin, 1000, 5, rel_dp=True) on the 31x61x61 grid (5 argmin
     sweeps over 2.2 G backups + 6000 fixed-policy backups of the whole grid).  The
     fixture is the unmodified reference's output, bit-identical to the shipped file."""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     G = golden("searev_full.npz")
     assert bool(G["matches_shipped_npy"])
     prob = wl.searev(cuda_api)
@@ -1261,7 +1262,7 @@ def test_large_grid_sampled_against_port(cuda_api, port):
     """2000 x 125 slice of config #5 (layout B, batched tabulation): 300 random
     states checked against the numpy port; min over controls <= any fixed control;
     idempotence of the table cache."""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     n_E, n_P = 2000, 125
     prob = wl.storage_ar1_large(cuda_api, n_E=n_E, n_P=n_P)
     ora = wl.storage_ar1_large(port, n_E=n_E, n_P=n_P)
@@ -1291,7 +1292,7 @@ def test_device_argument_is_honoured(product, port):
     GPU 1 (the C ABI launches on the current device, so the engine makes its device current
     around every entry point); the caller's current device is left alone"""
     import torch
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     torch.cuda.set_device(0)
@@ -1316,7 +1317,7 @@ def test_config5_full_size_against_port(cuda_api, port):
     `value_iteration` (results streamed band by band, Engine.sweep_to_host) and the
     device-resident loop (Engine.sweep), 1 000 seeded random states against the oracle port
     (stodynprog.py:639-691): policies exact, J within 1e-10."""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     prob = wl.storage_ar1_large(cuda_api)
     ora = wl.storage_ar1_large(port).solver
     sv = prob.solver
@@ -1346,7 +1347,7 @@ def test_column_layout_against_port_by_W(cuda_api, port, n_w):
     """layout CF against the oracle port on every state, for the node counts that take the
     3-, 5- and 9-slot instantiations of the column kernel exactly (FULL) and partly (W = 4:
     slot masking)"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     kw = dict(n_E=70, n_P=6, n_w=n_w, steps=(0.3, 0.1))
     sv = wl.storage_ar1(cuda_api, **kw).solver
     sv.table_layout, sv.column_hoist = "state_minor", "on"
@@ -1366,7 +1367,8 @@ def test_layout_B_kernel_variants_are_bit_identical(product):
     """straight LDG, TMA-fed ring (several ring shapes) and software-pipelined
     kernels of the state-minor layout, and both lane widths of layout A, must
     produce identical J and argmin"""
-    from stodynprog_b200 import workloads as wl, _cabi
+    import workloads as wl
+    from stodynprog_b200 import _cabi
     lib = _cabi.load_library()
 
     def opt(**kw):
@@ -1406,7 +1408,7 @@ def test_overlapped_result_copy_is_bit_identical(product, layout, compress):
     """value_iteration's large-sweep path (runs of the slab swept on alternating streams,
     results copied to the host while later runs compute) must return exactly what the
     plain path returns"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from stodynprog_b200.engine import Engine
     api = _Api(product, "cuda", layout, compress=compress)
     for prob in (wl.storage_ar1(api, n_E=40, n_P=37, steps=(0.05, 0.1), item_chunk=48),
@@ -1454,7 +1456,7 @@ def test_column_hoist_overlapped_result_copy(product, bands, monkeypatch):
     once, every band is swept by its own launch (its own CTA segments over the band's
     items) on alternating streams, combined and copied to the host while the next bands
     compute - same J and policies as the plain path and as layout BF"""
-    from stodynprog_b200 import workloads as wl
+    import workloads as wl
     from stodynprog_b200.engine import Engine
     monkeypatch.setattr(Engine, "COLUMN_BANDS", bands)
     res = {}
