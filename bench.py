@@ -411,6 +411,10 @@ def run_ours(args):
     sv.column_hoist = args.column_hoist
     if args.item_chunk:
         sv._item_chunk = args.item_chunk
+    # table build: dyn/cost evaluated chunk by chunk on several host threads (DPSolver.host_threads,
+    # an opt-in: the reference calls them on the calling thread); the box's cores shared by the ranks
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    sv.host_threads = max(1, min(16, ncpu // world)) if args.host_threads == "auto" else int(args.host_threads)
     eng = sv.engine
     t0 = time.perf_counter()
     T = sv.sweep_tables()
@@ -588,7 +592,8 @@ def run_ours(args):
             "plan": {"backups_per_sweep": total_backups, "table_layout": T.layout_name,
                      "row_bands": (T.bands["rows"] if T.column else None),
                      "shard_axis": (None if world == 1 else "columns" if T.col_bounds is not None else "rows"),
-                     "tabulate_mode": T.tabulate_mode, "item_chunk": T.item_chunk,
+                     "tabulate_mode": T.tabulate_mode, "host_threads": int(sv.host_threads),
+                     "item_chunk": T.item_chunk,
                      "table_gb_per_gpu": T.device_bytes / 1e9,
                      "parallelism": "state shards x%d, %s" % (
                          world, "one rank" if world == 1 else
@@ -597,6 +602,10 @@ def run_ours(args):
                           else "NCCL all-gather of J per sweep"))},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "clocks": clocks, "setup_seconds": float(setup[0]),
+            # rank 0's build, seconds per stage: scan of the control boxes, layout decisions,
+            # dyn/cost evaluation + staging copies + uploads + K0 launches (pipelined), work list,
+            # and the wait for the device work still in flight at the end
+            "setup_split": T.setup_split,
         }
         if verified is not None:
             line["verified"] = verified
@@ -725,6 +734,8 @@ def main():
                     help="factored (x,u)+(x,w) tables (auto: whenever the system allows)")
     ap.add_argument("--column-hoist", dest="column_hoist", default="auto", choices=["auto", "on", "off"],
                     help="layout CF, one inner-interpolation table per grid column (auto: SDP_COLUMN_HOIST)")
+    ap.add_argument("--host-threads", dest="host_threads", default="auto",
+                    help="host threads of the table build (auto = cores / ranks, at most 16; 1 = calling thread only)")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-layout sub-measurement")
     ap.add_argument("--item-chunk", dest="item_chunk", type=int, default=0)
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=None,

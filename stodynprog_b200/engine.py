@@ -17,271 +17,19 @@ import numpy as np
 
 from . import _cabi
 from . import tabulate as tb
+from .tablebuild import (                                        # noqa: F401  (re-exported)
+    COLUMN_HOIST_DEFAULT, SLAB_AXIS_DEFAULT, COLUMN_PAIRS_DEFAULT, ITEMS_TARGET,
+    BuildPlan, ShardBuild, SweepTables, fill_c_tables, partition_by_weight, rebalance_bounds,
+    make_items, pick_item_chunk, host_threads, pair_positions, column_order, item_run_ends,
+    column_segments, row_aligned, ColumnHoistRefused, _ColumnsNotApplicable)
 
 __all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "rebalance_bounds",
            "column_order", "column_segments", "row_aligned"]
-
-# solver.column_hoist = "auto" uses layout CF (column-shared hoist) whenever it applies unless
-# SDP_COLUMN_HOIST=0; "on" / "off" on the solver override it.  Measured on config #5, one B200
-# (profiles/r1_column_tuning.txt): 1.21 ms per sweep against 2.83 ms for layout BF.
-COLUMN_HOIST_DEFAULT = os.environ.get("SDP_COLUMN_HOIST", "1") != "0"
-# solver.slab_axis = "auto": how a grid in layout CF is cut over several ranks ("auto" | "rows" |
-# "columns").  By columns every rank tabulates and loads the tables of its own columns only;
-# measured on config #5 (profiles/r2_shard_emulation.txt, one rank's streaming kernel): 0.179 ms
-# against 0.233 ms per sweep for 1/8 of the grid, 0.61 against 0.65 ms for 1/2.  "auto" cuts
-# by columns whenever layout CF applies and every rank gets at least 4 columns.
-SLAB_AXIS_DEFAULT = os.environ.get("SDP_SLAB_AXIS", "auto")
-# solver.column_pairs = "auto": layout CF with two rows per lane (3 shared-memory reads for 2
-# backups instead of 4).  OFF by default: measured on config #5 (profiles/r2_emu_variants_pairs.txt)
-# 1.58-1.67 ms per sweep against 1.15 ms with one row per lane.  The reads saved come back as bank
-# conflicts: a half-warp's 16 lanes then span up to 32 table rows, and no placement of the rows in
-# the 16 eight-byte bank pairs serves both the stride-2 pattern of the interior of the grid and the
-# stride <= 1 patterns of the clipped control boxes without collisions.
-COLUMN_PAIRS_DEFAULT = os.environ.get("SDP_COLUMN_PAIRS", "0") != "0"
 
 
 def _torch():
     import torch
     return torch
-
-
-def partition_by_weight(weights, world):
-    """Cut range(len(weights)) into `world` contiguous slabs of nearly equal
-    total weight.  Returns the world+1 boundaries (monotone, first 0, last n)."""
-    w = np.asarray(weights, dtype=np.float64)
-    n = len(w)
-    bounds = [0]
-    if n == 0:
-        return [0] * (world + 1)
-    csum = np.cumsum(w)
-    total = csum[-1]
-    for r in range(1, world):
-        target = total * r / world
-        b = int(np.searchsorted(csum, target, side="left")) + 1
-        # pick the nearer of the two candidate cuts
-        if b - 1 > bounds[-1] and abs(csum[b - 2] - target) <= abs(csum[b - 1] - target):
-            b -= 1
-        b = min(max(b, bounds[-1]), n)
-        bounds.append(b)
-    bounds.append(n)
-    return bounds
-
-
-def rebalance_bounds(U_all, bounds, times, tolerance=1.03):
-    """Re-cut contiguous slabs from measured slab times: the weight U(x)+1 of every
-    state is scaled by its slab's time per unit weight (a piecewise-constant cost
-    density), then the grid is cut into slabs of equal estimated time.  Returns the
-    new boundaries, or None if the slabs are balanced within `tolerance` (slowest /
-    mean), a time is missing, or nothing would move."""
-    t = np.asarray(times, dtype=float)
-    world = len(t)
-    old = [int(b) for b in bounds]
-    if world < 2 or not np.all(t > 0) or t.max() <= tolerance * t.mean():
-        return None
-    w = np.asarray(U_all, dtype=np.float64) + 1.0
-    for r in range(world):
-        sl = slice(old[r], old[r + 1])
-        tot = w[sl].sum()
-        if tot > 0:
-            w[sl] *= t[r] / tot
-    new = [int(b) for b in partition_by_weight(w, world)]
-    return None if new == old else new
-
-
-def make_items(unit_U, chunk, unit_off, per_entry, g_unit_off, g_per_entry, Upad):
-    """Work-item table (SdpItem records) + first item of every unit.
-
-    A unit (a state in layout A, a tile of 32 states in layout B) with unit_U controls is
-    cut into ceil(unit_U / chunk) runs of EQUAL length (a multiple of 4, at most `chunk`):
-    140 controls with chunk 128 become 72 + 68, not 128 + 12 - a short run costs a warp
-    the same prologue (item, w-part, first row) as a long one.  Control u of a unit sits
-    `u * per_entry` table entries after `unit_off[unit]` (g: `u * g_per_entry` after
-    `g_unit_off[unit]`); `Upad` is layout A's row pitch per unit (None for layout B)."""
-    unit_U = np.asarray(unit_U, dtype=np.int64)
-    units = len(unit_U)
-    n_it = (unit_U + chunk - 1) // chunk
-    per_unit = (((unit_U + np.maximum(n_it, 1) - 1) // np.maximum(n_it, 1)) + 3) // 4 * 4
-    item_begin = np.zeros(units + 1, dtype=np.int64)
-    np.cumsum(n_it, out=item_begin[1:])
-    n_items = int(item_begin[-1])
-    st = np.repeat(np.arange(units, dtype=np.int64), n_it)
-    kk = np.arange(n_items, dtype=np.int64) - item_begin[st]
-    per = per_unit[st]
-    items = np.zeros(n_items, dtype=_cabi.ITEM_DTYPE)
-    items["u_begin"] = kk * per
-    items["u_count"] = np.minimum(per, unit_U[st] - kk * per)
-    items["state"] = st
-    assert n_items == 0 or int(items["u_count"].min()) >= 1
-    items["entry_base"] = np.asarray(unit_off)[st] + kk * per * per_entry
-    items["g_base"] = np.asarray(g_unit_off)[st] + kk * per * g_per_entry
-    items["Upad"] = 0 if Upad is None else np.asarray(Upad)[st]
-    return items, item_begin
-
-
-def fill_c_tables(T):
-    """the SdpTables record (include/sdp_b200.h) of a SweepTables"""
-    c = _cabi.SdpTables()
-    c.cell = T.cell.data_ptr()
-    c.lam = T.lam.data_ptr()
-    c.lam_plane = T.lam_plane
-    c.g = T.g.data_ptr()
-    c.g_per_w = T.g_per_w
-    c.W = T.W
-    c.expect = T.expect
-    if T.u_mask:
-        c.layout = _cabi.LAYOUT_STATE_MINOR_FACTORED if T.tiled else _cabi.LAYOUT_CONTROL_MINOR_FACTORED
-        if T.column:
-            c.layout = _cabi.LAYOUT_COLUMN_FACTORED
-            c.n_cols, c.tiles_per_col = T.n_cols, T.tiles_per_col
-            c.seg_begin, c.n_segs = T.seg_begin.data_ptr(), T.n_segs
-            c.col_table = T.col_table.data_ptr()
-            c.col_table_ready = 0
-            if T.item_order is not None:
-                # several bands: the whole-list launch walks the bands of a column back to back
-                c.item_order = T.item_order.data_ptr()
-                c.run_end = T.run_end_ord.data_ptr()
-            else:
-                c.run_end = T.run_end.data_ptr()
-            if getattr(T, "pairs", False):
-                c.col_pairs = 1
-                c.pos_row = T.pos_row.data_ptr()
-        c.u_mask = T.u_mask
-        c.cell_w = T.cell_w.data_ptr()
-        c.lam_w = T.lam_w.data_ptr()
-        c.lam_w_plane = T.lam_w_plane
-    else:
-        c.layout = _cabi.LAYOUT_STATE_MINOR if T.tiled else _cabi.LAYOUT_CONTROL_MINOR
-    c.p = T.p.data_ptr()
-    c.p_host = T.p_host.ctypes.data
-    c.items = T.items.data_ptr()
-    c.n_items = T.n_items
-    c.item_begin = T.item_begin.data_ptr()
-    c.n_states = T.n_states
-    c.U = T.U_dev.data_ptr()
-    return c
-
-
-# Work items (warps) wanted per sweep launch.  A B200 keeps 148 SMs x 12..24 warps of these
-# kernels resident, so a slab of a multi-GPU run (config #5 cut in 8: ~4 000 tiles of ~200
-# controls) is only 2-3 waves of equally long items and its time is quantised by whole waves:
-# measured per slab (profiles/r1_slab_chunks.txt) 0.373..0.449 ms with one item per tile,
-# 0.384..0.390 ms with runs of <= 64 controls (about 9 waves) - 13 % on the slowest slab,
-# which is the one the whole sweep waits for.  Runs are cut evenly (see the item table), so
-# shorter runs cost nothing measurable on a grid that is already long (2.843 vs 2.853 ms).
-ITEMS_TARGET = 148 * 96
-
-
-def pick_item_chunk(unit_U, min_chunk, max_chunk=512, target=ITEMS_TARGET):
-    """largest power-of-two-scaled chunk in [min_chunk, max_chunk] giving at least
-    `target` work items for units with `unit_U` controls each"""
-    unit_U = np.asarray(unit_U, dtype=np.int64)
-    chunk = max_chunk
-    while chunk > min_chunk and int(((unit_U + chunk - 1) // chunk).sum()) < target:
-        chunk //= 2
-    return max(chunk, min_chunk)
-
-
-class _ColumnsNotApplicable(Exception):
-    """the cut by columns was chosen by "auto" but layout CF turned out not to apply to the
-    built tables: build_sweep_tables starts again with slabs of rows"""
-
-
-class ColumnHoistRefused(Exception):
-    """layout CF was demanded (column_hoist = 'on') for tables whose (x,w) part varies
-    along a column of the grid"""
-
-
-def pair_positions(r0, r1, pair_ok):
-    """Positions of the rows [r0, r1) of a band for the two-rows-per-lane sweep: rows r, r+1 with
-    pair_ok[r] share a lane (positions 2j, 2j+1), any other row gets a lane of its own with a
-    padding position (-1) beside it; padded with -1 to a multiple of 64 (whole pairs of tiles).
-    Returns the int64 array position -> row."""
-    out = []
-    r = r0
-    while r < r1:
-        if r + 1 < r1 and pair_ok[r]:
-            out += [r, r + 1]
-            r += 2
-        else:
-            out += [r, -1]
-            r += 1
-    out += [-1] * (-len(out) % 64)
-    return np.asarray(out, dtype=np.int64)
-
-
-def column_order(n_states, n_cols, band_rows=None, pair_ok=None):
-    """Position order of layout CF for a slab of whole rows of state axis 0.
-
-    The slab's local states are i = row*n_cols + col (C-order).  Layout CF walks them
-    band by band (`band_rows`: row boundaries [0, ..., n_rows]; default one band), inside a
-    band column by column, every column of a band padded to whole tiles of 32 rows.
-    Returns (order, valid, band_tiles, band_tile_begin, tile_col, pos_row):
-      order[p]  local state at position p (a padding position repeats the last row of
-                its column in the band), valid[p] False on padding positions;
-      band_tiles[b] tiles per column in band b; band_tile_begin[b] its first tile;
-      tile_col[t] the column of tile t;
-      pos_row   None, or - `pair_ok` given: two rows per lane, see pair_positions - per band the
-                int64 array position (of every column) -> row of the band (row - r0), -1 = padding."""
-    n_rows = n_states // n_cols
-    assert n_rows * n_cols == n_states and n_rows >= 1
-    if band_rows is None:
-        band_rows = [0, n_rows]
-    band_rows = [int(r) for r in band_rows]
-    assert band_rows[0] == 0 and band_rows[-1] == n_rows and all(a < b for a, b in zip(band_rows, band_rows[1:]))
-    cols = np.arange(n_cols, dtype=np.int64)
-    orders, valids, band_tiles, band_tile_begin, tile_col, pos_row = [], [], [], [0], [], []
-    for r0, r1 in zip(band_rows[:-1], band_rows[1:]):
-        if pair_ok is None:
-            tpc = (r1 - r0 + 31) // 32
-            row = r0 + np.arange(32 * tpc, dtype=np.int64)
-            valid_row = row < r1
-            row = np.minimum(row, r1 - 1)
-        else:
-            pr = pair_positions(r0, r1, pair_ok)
-            tpc = len(pr) // 32
-            valid_row = pr >= 0
-            # (a padding position repeats the nearest real row before it: any real state does)
-            row = np.maximum.accumulate(np.where(valid_row, pr, r0))
-            pos_row.append(np.where(valid_row, pr - r0, -1))
-        orders.append((row[None, :] * n_cols + cols[:, None]).reshape(-1))
-        valids.append(np.broadcast_to(valid_row[None, :], (n_cols, len(row))).reshape(-1))
-        band_tiles.append(tpc)
-        band_tile_begin.append(band_tile_begin[-1] + n_cols * tpc)
-        tile_col.append(np.repeat(cols, tpc))
-    return (np.concatenate(orders), np.concatenate(valids), band_tiles, band_tile_begin,
-            np.concatenate(tile_col), pos_row if pair_ok is not None else None)
-
-
-def item_run_ends(run_key):
-    """run_end[i] = index one past the last item of the run of equal consecutive keys
-    containing item i (layout CF: the items of one band and column)"""
-    key = np.asarray(run_key)
-    n = len(key)
-    if n == 0:
-        return np.zeros(0, dtype=np.int64)
-    ends = np.concatenate([np.flatnonzero(key[1:] != key[:-1]) + 1, [n]]).astype(np.int64)
-    return ends[np.searchsorted(ends, np.arange(n), side="right")]
-
-
-def column_segments(item_u_count, n_ctas):
-    """Layout CF: cut the item list (ordered by tile, hence by column) into at most
-    `n_ctas` contiguous runs of equal weight, one per CTA - one CTA per SM, since the
-    column table fills its shared memory - so that a CTA meets few column changes.
-    Weight of an item: its controls plus a fixed cost.  Returns int64 [n_segs + 1]."""
-    n_items = len(item_u_count)
-    n_segs = max(1, min(int(n_ctas), n_items))
-    seg = partition_by_weight(np.asarray(item_u_count, dtype=np.float64) + 2.0, n_segs)
-    return np.asarray(seg, dtype=np.int64)
-
-
-def row_aligned(bounds, n_cols):
-    """slab boundaries moved to the nearest multiple of n_cols (whole rows of axis 0),
-    kept monotone"""
-    out = [int(bounds[0])]
-    for b in bounds[1:-1]:
-        out.append(max(out[-1], int(round(float(b) / n_cols)) * n_cols))
-    out.append(int(bounds[-1]))
-    return [min(b, out[-1]) for b in out]
 
 
 class _DeviceBoundLib(object):
@@ -477,95 +225,6 @@ class PeerExchange(object):
         _cabi.check(rc, "sdp_p2p_barrier")
 
 
-class SweepTables(object):
-    """Dense (cell, lam, g) tables of one slab of states, resident in HBM,
-    plus the host-side control discretisation needed to turn argmin indices
-    back into control values."""
-
-    def __init__(self):
-        self.grid = None           # _cabi.SdpGrid
-        self.d = 0
-        self.W = 1
-        self.expect = 1
-        self.g_per_w = 0
-        self.bounds = None         # slab boundaries over ranks (world+1)
-        self.state_begin = 0
-        self.n_states = 0
-        self.host_full = None      # HostStateTable of ALL states (replicated)
-        self.cell = self.lam = self.g = self.p = None
-        self.p_host = None
-        self.items = self.item_begin = None
-        self.part_val = self.part_idx = None
-        self.J_out = self.argmin = None
-        self.lam_plane = 0
-        self.n_items = 0
-        self.n_entries = 0
-        self.n_backups_local = 0   # admissible (x,u,w) triples in this slab
-        self.n_backups_total = 0
-        self.c_tables = None       # _cabi.SdpTables
-        self.tiled = False         # layout B (state-minor) when True
-        self.u_mask = 0            # factored layouts: coordinates of the (x,u) part; 0 = dense
-        self.cell_w = self.lam_w = None
-        self.lam_w_plane = 0
-        self.U_dev = None
-        self.tabulate_mode = None
-        self.setup_seconds = 0.0
-        self.item_chunk = 0        # controls per work item used for these tables
-        self.item_begin_host = self.unit_U_host = None
-        self.chunk_plan = None     # see Engine._chunk_plan
-        # layout CF (column-shared hoist): BF tables over column-major tiles, see column_order()
-        self.column = False
-        self.n_cols = self.tiles_per_col = 0
-        self.seg_begin = None      # device int64 [n_segs+1]: item range of every CTA
-        self.n_segs = 0
-        self.item_u_count_host = None
-        self.col_table = None      # device fp64 scratch: the column tables of the current sweep
-        self.run_end = None        # device int64 [n_items]: end of every item's (band, column) run
-        self.pairs = False         # layout CF with two rows per lane (SdpTables.col_pairs)
-        self.pos_row = self.work_dev = self.work_host = None
-        self.item_order = None     # several bands: device int64 [n_items], items column by column (all bands)
-        self.run_end_ord = None    # ... and the end of every position's column run in that order
-        self.bands = None          # dict(rows, tiles, tile_begin, tile_col), see column_order
-        self.band_views = None     # per band: (SdpTables view for the combine pass, first state, states)
-        self.sm_count = 148
-        # grid sharded by COLUMNS (layout CF, solver.slab_axis = "columns"): this rank holds the
-        # columns [col_bounds[rank], col_bounds[rank+1]) of every row; local state row*n_cols + lc
-        self.col_bounds = None
-        self.gather_index = None   # device int64 [n_grid]: see Collective.all_gather_indexed
-        self.gather_maxc = 0
-        self.slab_times_ms = None  # measured per-rank sweep times (several ranks, see _measured_bounds)
-        self.slab_recut = False    # True when those times moved the slab boundaries
-
-    @property
-    def algorithmic_bytes_per_backup(self):
-        """4 + 8 d + 8 kappa  """
-        kappa = 1.0 if self.g_per_w else 1.0 / self.W
-        return 4.0 + 8.0 * self.d + 8.0 * kappa
-
-    @property
-    def factored(self):
-        return self.u_mask != 0
-
-    @property
-    def layout_name(self):
-        if self.column:
-            return "column_factored"
-        return ("state_minor" if self.tiled else "control_minor") + ("_factored" if self.u_mask else "")
-
-    @property
-    def device_bytes(self):
-        n = 0
-        for t in (self.cell, self.lam, self.g, self.items, self.item_begin, self.cell_w, self.lam_w):
-            if t is not None:
-                n += t.numel() * t.element_size()
-        return n
-
-    @property
-    def streamed_bytes_per_backup(self):
-        """bytes of table the sweep kernel actually reads per admissible (x,u,w)"""
-        return self.device_bytes / max(self.n_backups_local, 1)
-
-
 class PolicyTables(object):
     """[w][n_states] planes for the fixed-policy backup (eval_policy)."""
 
@@ -686,10 +345,11 @@ class Engine(object):
             outs.append(t.reshape(a.shape))
         return outs
 
-    def to_device_concat(self, records, parts):
+    def to_device_concat(self, records, parts, threads=1):
         """a structured record array + a LIST of fp64 arrays -> one page-locked buffer -> one
         asynchronous H2D copy; returns (records as device bytes, the parts concatenated without gaps
-        as one device fp64 tensor).  Each part is copied once, straight into the upload buffer."""
+        as one device fp64 tensor).  Each part is copied once, straight into the upload buffer
+        (`threads` > 1: the large parts by that many host threads side by side)."""
         torch = _torch()
         rec = np.ascontiguousarray(records).view(np.uint8).reshape(-1)
         n_parts = int(sum(a.size for a in parts))
@@ -699,10 +359,23 @@ class Engine(object):
         hn = host.numpy()
         hn[:rec.nbytes] = rec
         dst = hn[off:off + 8 * n_parts].view(np.float64)
-        pos = 0
+        pos, jobs = 0, []
         for a in parts:
-            dst[pos:pos + a.size] = a.reshape(-1)
+            jobs.append((pos, a.reshape(-1)))
             pos += a.size
+
+        def copy(job):
+            dst[job[0]:job[0] + job[1].size] = job[1]
+
+        big = [j for j in jobs if j[1].size >= (1 << 17)]
+        if threads > 1 and len(big) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            if getattr(self, "_copy_pool", None) is None or self._copy_pool._max_workers != threads:
+                self._copy_pool = ThreadPoolExecutor(max_workers=threads, thread_name_prefix="sdp-stage")
+            list(self._copy_pool.map(copy, big))
+            jobs = [j for j in jobs if j[1].size < (1 << 17)]
+        for j in jobs:
+            copy(j)
         buf = host.to(self.device, non_blocking=True) if self._cuda else host
         return buf[:rec.nbytes], buf[off:off + 8 * n_parts].view(torch.float64)
 
@@ -1012,603 +685,16 @@ class Engine(object):
 
     def build_sweep_tables(self, solver, t_k=None, reuse=None):
         """Tabulate the user's callables over this rank's shard and build the tables on the
-        device (see _build_sweep_tables).  With several ranks and slab_axis "auto" the grid is
-        cut by columns when layout CF is expected to apply; if the built tables refuse it (same
-        decision on every rank), the build starts again with slabs of rows."""
+        device: `tablebuild.BuildPlan` (scan of the control boxes, cut over the ranks) and
+        `tablebuild.ShardBuild` (layout, tabulation with its fall-backs, work list).  `reuse`: a
+        SweepTables whose device buffers are recycled when the sizes match (time-dependent
+        recursion).  With several ranks and slab_axis "auto" the grid is cut by columns when
+        layout CF is expected to apply; if the built tables refuse it (same decision on every
+        rank), the build starts again with slabs of rows."""
         try:
-            return self._build_sweep_tables(solver, t_k, reuse, None)
+            return BuildPlan(self, solver, t_k).run(reuse)
         except _ColumnsNotApplicable:
-            return self._build_sweep_tables(solver, t_k, None, "rows")
-
-    def _build_sweep_tables(self, solver, t_k, reuse, forced_axis):
-        """Tabulate the user's callables over this rank's slab and build the dense
-        tables on the device.  `reuse`: a SweepTables whose device buffers are
-        recycled when the sizes match (time-dependent recursion).
-
-        Solver knobs read here:
-          solver.table_layout   : "auto" | "control_minor" (A) | "state_minor" (B)
-          solver.table_compress : "auto" | "off" | "on"  (factored (x,u) + (x,w) tables)
-          solver.tabulate       : "auto" | "per_state" | "batched"
-        """
-        import time
-        torch = _torch()
-        t0 = time.perf_counter()
-        sys = solver.sys
-        state_grid = [np.asarray(g, dtype=float) for g in solver.state_grid]
-        d = len(state_grid)
-        grid = _cabi.make_grid(state_grid)
-        for ax in state_grid:
-            if len(ax) < 2:
-                raise ValueError("every state variable needs at least 2 grid points "
-                                 "(the reference's interpolation reads out of bounds and "
-                                 "divides 0/0 on a 1-point axis, SURVEY.md App. A.2)")
-        n_grid = int(np.prod([len(ax) for ax in state_grid]))
-        # several perturbations (a TODO of the reference, stodynprog.py:666,679-683): their product
-        # grid is flattened in C order into one axis of W nodes (tabulate.perturb_layout)
-        nb_perturb = len(solver.perturb_grid)
-        W = tb.perturb_layout(solver.perturb_grid)[2]
-        if W > 4096:
-            raise ValueError("the product perturbation grid has %d nodes; at most 4096 are supported" % W)
-        coll = self.coll
-        world, rank = coll.world, coll.rank
-        dev = self.device
-
-        # pass 1: control boxes (replicated host table, needed to map argmin -> control values)
-        mode = getattr(solver, "tabulate", "auto")
-        nb_control = len(sys.control)
-        eq = [n_grid * r // world for r in range(world + 1)]
-        host_full, mine = self._scan_boxes(solver, t_k, state_grid, n_grid, mode)
-        U_all = host_full.U.astype(np.int64)
-        if U_all.max(initial=0) >= 2 ** 31 - 4:
-            raise ValueError("more than 2^31 control combinations for one state")
-
-        # layout CF (column-shared hoist, include/sdp_b200.h): wanted by solver.column_hoist,
-        # possible when the column table fits shared memory; needs slabs of whole rows of
-        # state axis 0, a factored split with u_mask == 1 and a w-part that is the same for
-        # all the states of a column (checked on the built tables, see build_for)
-        n_rows0 = len(state_grid[0])
-        n_cols = n_grid // n_rows0
-        col_mode = getattr(solver, "column_hoist", "auto")
-        if col_mode not in ("auto", "on", "off"):
-            raise ValueError("column_hoist must be 'auto', 'on' or 'off'")
-        col_wanted = col_mode == "on" or (col_mode == "auto" and COLUMN_HOIST_DEFAULT)
-        col_candidate = bool(
-            col_wanted and d in (2, 3) and nb_perturb >= 1 and 1 < W <= _cabi.FACTORED_MAX_W_REG
-            and 8 * _cabi.column_pitch(n_rows0, W) <= _cabi.COLUMN_MAX_SMEM_BYTES
-            and getattr(solver, "table_layout", "auto") in ("auto", "state_minor")
-            and getattr(solver, "table_compress", "auto") != "off"
-            and n_rows0 >= 32 * world and nb_control <= _cabi.SDP_MAX_C)
-        col_refused = [False]       # set when the built w-part turns out to vary along a column
-        # layout CF with two rows per lane (SdpTables.col_pairs): solver.column_pairs / SDP_COLUMN_PAIRS
-        pair_mode = getattr(solver, "column_pairs", "auto")
-        if pair_mode not in ("auto", "on", "off"):
-            raise ValueError("column_pairs must be 'auto', 'on' or 'off'")
-        pairs = bool(col_candidate and (pair_mode == "on" or (pair_mode == "auto" and COLUMN_PAIRS_DEFAULT))
-                     and 8 * _cabi.column_pitch(n_rows0, W, pairs=True) <= _cabi.COLUMN_MAX_SMEM_BYTES)
-        # several ranks: slabs of whole rows of axis 0 ("rows"), or - layout CF only - whole
-        # columns ("columns": every rank then tabulates and loads the tables of its own columns
-        # only, so the per-column costs divide by the number of ranks)
-        slab_axis = getattr(solver, "slab_axis", "auto")
-        if slab_axis not in ("auto", "rows", "columns"):
-            raise ValueError("slab_axis must be 'auto', 'rows' or 'columns'")
-        if slab_axis == "auto":
-            slab_axis = SLAB_AXIS_DEFAULT
-        axis_auto = slab_axis == "auto" or forced_axis is not None
-        if forced_axis is not None:
-            slab_axis = forced_axis
-        elif slab_axis == "auto":
-            slab_axis = "columns" if (col_candidate and n_cols >= 4 * world) else "rows"
-        by_columns = world > 1 and slab_axis == "columns"
-        # developer experiments (scripts/dev_shard_emulation.py): the tables of ONE column shard
-        # [c0, c1) of the grid on a single rank, as a rank of a multi-GPU run would hold them
-        col_override = getattr(solver, "_col_override", None) if world == 1 else None
-        if col_override is not None:
-            by_columns = True
-        if by_columns and not (col_candidate and n_cols >= world):
-            raise ValueError("slab_axis='columns' needs layout CF (column_hoist) and at least one "
-                             "grid column per rank")
-
-        def build_for(bounds, reuse):
-            """tables of this rank's slab: states [bounds[rank], bounds[rank+1]) of the C-order
-            grid, or (by_columns) the columns [bounds[rank], bounds[rank+1]) of every row"""
-            if by_columns:
-                c0, c1 = bounds[rank], bounds[rank + 1]
-                # local state row*(c1-c0) + lc  <->  grid state row*n_cols + c0 + lc
-                glob = (np.arange(n_rows0, dtype=np.int64)[:, None] * n_cols
-                        + np.arange(c0, c1, dtype=np.int64)[None, :]).reshape(-1)
-                sb, se, n = 0, n_grid, len(glob)
-                n_cols_loc = c1 - c0
-            else:
-                sb, se = bounds[rank], bounds[rank + 1]
-                n = se - sb
-                glob = slice(sb, se)
-                n_cols_loc = n_cols
-            host = tb.HostStateTable(n, nb_control)
-            host.lo, host.hi, host.npts = host_full.lo[glob], host_full.hi[glob], host_full.npts[glob]
-            U = U_all[glob]
-
-            # table layout (see include/sdp_b200.h): lane <-> control (A) when states
-            # have many controls, lane <-> state (B) when there are many states with
-            # few controls each
-            layout = getattr(solver, "table_layout", "auto")
-            if layout == "auto":
-                mean_U = float(U.mean()) if n else 0.0
-                layout = "state_minor" if (n >= 32 * 1024 and mean_U <= 1024) else "control_minor"
-            tiled = layout == "state_minor"
-            w_grid = [np.asarray(g) for g in solver.perturb_grid]
-
-            # factored ("broadcast-compressed") tables when every next-state coordinate
-            # depends on (x,u) only or on (x,w) only and g does not depend on w; probed on
-            # the slab's state with most controls, then checked on every staged chunk
-            compress = getattr(solver, "table_compress", "auto")
-            u_mask = 0
-            w_cap = _cabi.FACTORED_MAX_W_REG if tiled else _cabi.FACTORED_MAX_W_SMEM
-            if (compress != "off" and n > 0 and nb_perturb >= 1 and 1 < W <= w_cap and d in (2, 3)
-                    and nb_control <= _cabi.SDP_MAX_C):
-                i_probe = int(np.argmax(U))
-                # (host row i_probe is grid state glob[i_probe] when the shard is whole columns)
-                g_probe = int(glob[i_probe]) if by_columns else sb + i_probe
-                x_probe = tb.state_tuples_at(state_grid, g_probe, g_probe + 1)[0]
-                u_mask = tb.probe_factor_mask(sys, x_probe, host, i_probe, w_grid, t_k) or 0
-            if compress == "on" and not u_mask:
-                raise ValueError("table_compress='on' but the system's dyn/cost do not have the "
-                                 "(x,u) + (x,w) structure (or d, W are outside the supported range)")
-            if world > 1:
-                # all ranks must agree (they run the same kernels on the same layout)
-                u_mask = min(coll.all_gather_object(u_mask))
-            column = bool(col_candidate and not col_refused[0] and tiled and u_mask == 1 and n > 0
-                          and (by_columns or (sb % n_cols == 0 and se % n_cols == 0)))
-            if world > 1:
-                column = bool(min(coll.all_gather_object(column)))
-            if by_columns and not column:
-                if axis_auto:
-                    raise _ColumnsNotApplicable()
-                raise ValueError("slab_axis='columns' but layout CF does not apply to these tables")
-            if col_mode == "on" and not column:
-                raise ValueError("column_hoist='on' but layout CF does not apply: it needs the "
-                                 "state-minor layout, a factored (x,u)+(x,w) split with state axis 0 "
-                                 "alone following the control, at most 9 perturbation nodes, a w-part "
-                                 "that does not depend on axis 0, and order[0]*(W|1)*8 bytes of "
-                                 "shared memory")
-            pos = {}
-
-            def positions(col):
-                """(n_eff, U_eff, host_eff, flat_eff, valid, bands): the slab's states in table
-                order - C-order, or for layout CF band by band, column by column, with padding
-                (column_order)"""
-                if col not in pos:
-                    if not col:
-                        pos[col] = (n, U, host, None, None, None)
-                    else:
-                        bands = self._column_bands(U.reshape(n // n_cols_loc, n_cols_loc).sum(axis=1), W)
-                        pair_ok = None
-                        if pairs:
-                            # rows that may share a lane: neighbours on axis 0 with the same control
-                            # grid sizes in every column (their backups then read overlapping table
-                            # rows); a speed hint only - the kernel handles any pair
-                            npts_rc = host.npts.reshape(n // n_cols_loc, n_cols_loc * max(nb_control, 1))
-                            pair_ok = np.all(npts_rc[1:] == npts_rc[:-1], axis=1)
-                        order, valid, band_tiles, band_tile_begin, tile_col, pos_row = \
-                            column_order(n, n_cols_loc, bands, pair_ok)
-                        h = tb.HostStateTable(len(order), nb_control)
-                        h.lo, h.hi, h.npts = host.lo[order], host.hi[order], host.npts[order]
-                        flat = glob[order] if by_columns else sb + order
-                        pos[col] = (len(order), np.where(valid, U[order], 0), h, flat, valid,
-                                    dict(rows=bands, tiles=band_tiles, tile_begin=band_tile_begin,
-                                         tile_col=tile_col, pos_row=pos_row))
-                return pos[col]
-
-            def sizes(u_mask, col):
-                """entry offsets of the layout: dense tables have W entries per control,
-                factored tables one"""
-                Wf = 1 if u_mask else W
-                n, U = positions(col)[:2]
-                if tiled:
-                    n_tiles = (n + 31) // 32
-                    Upad_t = np.zeros(n_tiles * 32, dtype=np.int64)
-                    Upad_t[:n] = U
-                    tile_U = Upad_t.reshape(n_tiles, 32).max(axis=1)
-                    if col and pairs:
-                        # the two tiles of a pair are swept by one warp: same number of controls
-                        tile_U = np.repeat(tile_U.reshape(-1, 2).max(axis=1), 2)
-                    tile_off = np.zeros(n_tiles + 1, dtype=np.int64)
-                    np.cumsum(tile_U * Wf * 32, out=tile_off[1:])
-                    return (n_tiles, tile_U, tile_off, int(tile_off[-1]), np.zeros(n + 1, dtype=np.int64),
-                            np.zeros(n, dtype=np.int64))
-                Upad = (U + 3) // 4 * 4
-                entry_off = np.zeros(n + 1, dtype=np.int64)
-                np.cumsum(Wf * Upad, out=entry_off[1:])
-                return 0, None, None, int(entry_off[-1]), entry_off, Upad
-
-            prev_mode = reuse.tabulate_mode if reuse is not None else None
-            T = reuse if (reuse is not None and reuse.W == W and reuse.d == d and reuse.tiled == tiled) \
-                else SweepTables()
-            T.grid, T.d, T.W = grid, d, W
-            T.tiled = tiled
-            T.expect = 1 if nb_perturb >= 1 else 0
-            T.bounds, T.state_begin, T.n_states = bounds, sb, n
-            T.col_bounds = None
-            if by_columns and col_override is not None:
-                T.bounds, T.state_begin, T.col_bounds = None, 0, [int(b) for b in bounds]
-            elif by_columns:
-                # the exchange goes by grid position, not by slab: T.bounds stays None
-                T.bounds, T.state_begin, T.col_bounds = None, 0, [int(b) for b in bounds]
-                widths = np.diff(np.asarray(bounds, dtype=np.int64))
-                T.gather_maxc = int(widths.max()) * n_rows0
-                cols = np.arange(n_cols, dtype=np.int64)
-                owner = np.searchsorted(np.asarray(bounds[1:], dtype=np.int64), cols, side="right")
-                lc = cols - np.asarray(bounds, dtype=np.int64)[owner]
-                rows = np.arange(n_rows0, dtype=np.int64)[:, None]
-                idx = owner[None, :] * T.gather_maxc + rows * widths[owner][None, :] + lc[None, :]
-                T.gather_index = self.to_device(idx.reshape(-1))
-            T.host_full = host_full
-            T.n_backups_local = int(U.sum()) * W
-            T.n_backups_total = int(U_all.sum()) * W
-            # host copy of the probabilities, kept alive with the tables (SdpTables.p_host)
-            T.p_host = tb.joint_proba(solver.perturb_proba) if nb_perturb >= 1 else np.ones(1)
-            # (one packed upload for the small per-table arrays)
-            small = [T.p_host]
-            if nb_control:
-                small += [host_full.lo.reshape(-1), host_full.hi.reshape(-1),
-                          host_full.npts.astype(np.int32).reshape(-1)]
-            small = self.to_device_packed(small)
-            T.p = small[0]
-            # replicated control discretisation, for the argmin -> control value kernel
-            T.lo_dev, T.hi_dev, T.npts_dev = (small[1], small[2], small[3]) if nb_control else (None, None, None)
-            T.nb_control = nb_control
-            T.tabulate_mode = None
-
-            def ensure(name, numel, dtype):
-                """(re)allocate T.<name> only when the size changes (time-dependent
-                recursions rebuild same-sized tables at every instant)"""
-                t = getattr(T, name)
-                if t is None or t.numel() != numel or t.dtype != dtype:
-                    setattr(T, name, None)        # release before allocating the new size
-                    setattr(T, name, torch.empty(numel, dtype=dtype, device=dev))
-
-            keep_staging = bool(getattr(solver, "_keep_staging", False))
-            flushes, chunk_record = [], []
-
-            def build(g_per_w, batched, u_mask, col):
-                L = {"u_mask": u_mask}
-                n, U, host, flat_eff, valid, _ = positions(col)
-                n_tiles, tile_U, tile_off, n_entries, entry_off, Upad = sizes(u_mask, col)
-                lam_plane = (n_entries + 3) // 4 * 4
-                n_u = bin(u_mask).count("1")
-                L.update(n_tiles=n_tiles, tile_U=tile_U, tile_off=tile_off, n_entries=n_entries,
-                         entry_off=entry_off, Upad=Upad, lam_plane=lam_plane)
-                ensure("cell", max(lam_plane, 4), torch.int32)
-                ensure("lam", max(lam_plane, 4) * (n_u if u_mask else d), torch.float64)
-                if u_mask:
-                    n_wp = (n_tiles * 32 if tiled else n) * W
-                    lam_w_plane = (n_wp + 3) // 4 * 4
-                    ensure("cell_w", max(lam_w_plane, 4), torch.int32)
-                    ensure("lam_w", max(lam_w_plane, 4) * (d - n_u), torch.float64)
-                else:
-                    T.cell_w = T.lam_w = None
-                    lam_w_plane = 0
-                L["lam_w_plane"] = lam_w_plane
-                tile_g_off = None
-                if u_mask:
-                    # one g per (x,u) entry, indexed like the u-part
-                    g_off, g_len = entry_off, n_entries
-                    tile_g_off = tile_off
-                elif tiled:
-                    if g_per_w:
-                        tile_g_off = tile_off
-                    else:
-                        tile_g_off = np.zeros(n_tiles + 1, dtype=np.int64)
-                        np.cumsum(tile_U * 32, out=tile_g_off[1:])
-                    g_off = np.zeros(n + 1, dtype=np.int64)
-                    g_len = int(tile_g_off[-1])
-                else:
-                    if g_per_w:
-                        g_off = entry_off
-                    else:
-                        g_off = np.zeros(n + 1, dtype=np.int64)
-                        np.cumsum(Upad, out=g_off[1:])
-                    g_len = int(g_off[-1])
-                if tiled:
-                    tile_off_dev, tile_g_off_dev, tile_U_dev = self.to_device_packed(
-                        [tile_off, tile_g_off, tile_U.astype(np.int32)])
-                L.update(g_off=g_off, tile_g_off=tile_g_off)
-                ensure("g", max(g_len, 4), torch.float64)
-                done = [0]      # states flushed so far (chunks arrive in order)
-                del flushes[:], chunk_record[:]
-                chunk_grids = {}
-
-                def flush(desc, staging):
-                    if u_mask:
-                        tb.check_factorable(desc, d, u_mask)
-                    desc_dev, stag_dev = self.to_device_concat(desc, staging)
-                    n_staging = int(stag_dev.numel())
-                    ns = len(desc)
-                    first = done[0]
-                    if tiled:
-                        assert first % 32 == 0
-                        t_first = first // 32
-                        nt = (ns + 31) // 32
-                        t_off = ctypes.c_void_p(tile_off_dev.data_ptr() + 8 * t_first)
-                        t_U = ctypes.c_void_p(tile_U_dev.data_ptr() + 4 * t_first)
-                        t_Umax = int(tile_U[t_first:t_first + nt].max())
-                    max_Upad = int(desc["Upad"].max()) if not tiled else 0
-
-                    def launch(desc_ptr, stag_ptr, g_ptr):
-                        """K0 on this chunk: `desc_ptr` / `stag_ptr` the chunk's descriptors and
-                        staged outputs, `g_ptr` the stage-cost table to fill (a recursion whose
-                        dynamics ignore the instant calls it again per instant with the
-                        descriptors pointing at that instant's cost)"""
-                        if tiled and u_mask:
-                            w0 = t_first * W * 32
-                            rc = self.lib.sdp_build_tables_factored_tiled(
-                                ctypes.byref(grid), W, u_mask, ns, desc_ptr, stag_ptr,
-                                nt, t_off, t_U, t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane,
-                                g_ptr, ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
-                                ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
-                            _cabi.check(rc, "sdp_build_tables_factored_tiled")
-                        elif tiled:
-                            rc = self.lib.sdp_build_tables_tiled(
-                                ctypes.byref(grid), W, g_per_w, ns, desc_ptr, stag_ptr,
-                                nt, t_off, ctypes.c_void_p(tile_g_off_dev.data_ptr() + 8 * t_first), t_U,
-                                t_Umax, self._ptr(T.cell), self._ptr(T.lam), lam_plane, g_ptr,
-                                self.stream)
-                            _cabi.check(rc, "sdp_build_tables_tiled")
-                        elif u_mask:
-                            w0 = first * W
-                            rc = self.lib.sdp_build_tables_factored(
-                                ctypes.byref(grid), W, u_mask, ns, desc_ptr, stag_ptr,
-                                self._ptr(T.cell), self._ptr(T.lam), lam_plane, g_ptr,
-                                max_Upad, ctypes.c_void_p(T.cell_w.data_ptr() + 4 * w0),
-                                ctypes.c_void_p(T.lam_w.data_ptr() + 8 * w0), lam_w_plane, self.stream)
-                            _cabi.check(rc, "sdp_build_tables_factored")
-                        else:
-                            rc = self.lib.sdp_build_tables(ctypes.byref(grid), W, g_per_w, ns,
-                                                           desc_ptr, stag_ptr,
-                                                           self._ptr(T.cell), self._ptr(T.lam), lam_plane,
-                                                           g_ptr, max_Upad, self.stream)
-                            _cabi.check(rc, "sdp_build_tables")
-
-                    launch(self._ptr(desc_dev), self._ptr(stag_dev), self._ptr(T.g))
-                    # (`keep`: the device arrays the launch closure points into)
-                    flushes.append(dict(desc=desc, n_staging=n_staging, stag_dev=stag_dev, launch=launch,
-                                        first=first, keep=(desc_dev, tile_off_dev, tile_g_off_dev, tile_U_dev)
-                                        if tiled else (desc_dev,)) if keep_staging else None)
-                    done[0] += ns
-                    # the staging tensors are freed by torch's caching allocator in
-                    # stream order, so no synchronisation is needed here
-
-                align = 32 if tiled else 1
-                if batched:
-                    # time-dependent recursion: the callables are the same at every instant, so
-                    # the full bit-for-bit check of the batched evaluation is made at the first
-                    # instant and a one-state check afterwards; unchanged control boxes reuse
-                    # the chunk's control grids
-                    tb.tabulate_states_batched(sys, state_grid, sb, se, host, w_grid, t_k, entry_off,
-                                               g_off, Upad, g_per_w, flush, align=align,
-                                               verify=1 if prev_mode == "batched" else 8,
-                                               # (chunks of a column-ordered grid repeat the same rows of
-                                               # control grids: kept for the duration of this build)
-                                               grid_cache=self._grid_cache if t_k is not None else chunk_grids,
-                                               flat_index=flat_eff, valid=valid,
-                                               record=chunk_record if keep_staging else None)
-                else:
-                    states = mine if (mine is not None and (sb, se) == (eq[rank], eq[rank + 1])) else \
-                        tb.state_tuples(state_grid, sb, se)
-                    if col:
-                        states = [states[i] for i in flat_eff - sb]      # (by_columns: sb = 0, all states)
-                    tb.tabulate_states(sys, states, host, w_grid, t_k, entry_off, g_off, Upad,
-                                       g_per_w, flush, align=align, valid=valid)
-                return L
-
-            # mode / layout resolution: batched evaluation is tried first in "auto"
-            # mode and abandoned if it fails or is not bit-identical to the
-            # reference's per-state calls on the sample states; factored tables are
-            # abandoned for dense ones as soon as one chunk does not fit the split
-            g_per_w = T.g_per_w if (reuse is T and not u_mask) else 0
-            batched = mode in ("auto", "batched")
-            L = None
-            while L is None:
-                try:
-                    col = column and u_mask == 1
-                    built = build(g_per_w, batched, u_mask, col)
-                    T.tabulate_mode = "batched" if batched else "per_state"
-                    if col:
-                        # the hoisted table is shared by a column only if the (x,w) part of its
-                        # states is the same; checked bit for bit on the built tables
-                        ok = self._column_w_part_ok(T, W, n_cols_loc, positions(True)[5], positions(True)[4],
-                                                    built["lam_w_plane"])
-                        if world > 1:
-                            ok = bool(min(coll.all_gather_object(ok)))
-                        if not ok:
-                            if by_columns and axis_auto and col_mode != "on":
-                                raise _ColumnsNotApplicable()
-                            if col_mode == "on" or by_columns:
-                                raise ColumnHoistRefused("column_hoist='on' but the (x,w) part of the "
-                                                         "next state depends on state axis 0")
-                            col_refused[0] = True
-                            column = False
-                            built = None         # rebuild in C-order (layout BF)
-                    L = built
-                except tb.NotFactorable:
-                    if compress == "on" or world > 1:
-                        # (with several ranks a silent per-rank fallback would desynchronise the layouts)
-                        raise ValueError("dyn/cost outputs do not keep the (x,u) + (x,w) structure "
-                                         "seen on the probe state; use solver.table_compress = 'off'")
-                    u_mask = 0
-                except tb.GDependsOnW:
-                    if g_per_w:
-                        raise
-                    if u_mask:
-                        u_mask = 0
-                    else:
-                        g_per_w = 1      # the cost depends on w: dense g table
-                except tb.BatchedMismatch:
-                    if mode != "auto":
-                        raise
-                    batched = False      # not bit-identical to per-state calls
-                except ColumnHoistRefused as e:
-                    raise ValueError(str(e))
-                except _ColumnsNotApplicable:
-                    raise
-                except Exception:
-                    if not (batched and mode == "auto"):
-                        raise
-                    batched = False      # callables not vectorisable over states
-            T.u_mask = u_mask
-            T.g_per_w = g_per_w
-            col = column and u_mask == 1
-            T.column = col
-            T.bands = positions(True)[5] if col else None
-            T.n_cols, T.tiles_per_col = (n_cols_loc, T.bands["tiles"][0]) if col else (0, 0)
-            U_eff = positions(col)[1]
-            n_tiles, tile_U, tile_off = L["n_tiles"], L["tile_U"], L["tile_off"]
-            entry_off, Upad, g_off, tile_g_off = L["entry_off"], L["Upad"], L["g_off"], L["tile_g_off"]
-            lam_plane = L["lam_plane"]
-            T.n_entries, T.lam_plane, T.lam_w_plane = L["n_entries"], lam_plane, L["lam_w_plane"]
-            Wf = 1 if u_mask else W     # table entries per control
-
-            # work items: one warp per run of at most `item_chunk` controls
-            unit_U = tile_U if tiled else U
-            chunk = self.item_chunk
-            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count if self._cuda else 148
-            if self.item_chunk_auto:
-                # layout A walks 128 controls per warp iteration, layout B one; layout CF has one
-                # CTA per SM whose 16 warps share the items of a few column pieces: several
-                # rounds of items per piece keep the warps of a CTA level
-                chunk = pick_item_chunk(unit_U, 128 if not tiled else 32,
-                                        **({"target": sm_count * 16 * 48} if col else {}))
-            T.item_chunk = chunk
-            if col and not pairs and self.COLUMN_TAIL_FRACTION > 0 and chunk >= 32:
-                # layout CF: the warps of a CTA meet at a barrier at the end of every (band, column)
-                # run of tiles and wait for the one that took the last item; the last tiles of every
-                # run are cut into runs of half the length, handed out last, so that the wait is
-                # half an item shorter (it weighs on the short sweeps of a multi-GPU shard)
-                bt, tb0 = T.bands["tiles"], T.bands["tile_begin"]
-                chunk_arr = np.full(len(unit_U), chunk, dtype=np.int64)
-                for b, tpc in enumerate(bt):
-                    tail = int(round(tpc * self.COLUMN_TAIL_FRACTION))
-                    if tail > 0:
-                        t_in = np.arange(tb0[b + 1] - tb0[b]) % tpc
-                        chunk_arr[tb0[b]:tb0[b + 1]][t_in >= tpc - tail] = chunk // 2
-                chunk = chunk_arr
-            if tiled:
-                per_entry = Wf * 32
-                g_unit_off = tile_off if (T.g_per_w or u_mask) else tile_g_off
-                # (layout CF: the Upad field of an item carries the column of its tile)
-                items, item_begin = make_items(unit_U, chunk, tile_off, per_entry, g_unit_off,
-                                               per_entry if (T.g_per_w or u_mask) else 32,
-                                               T.bands["tile_col"] if col else None)
-            else:
-                items, item_begin = make_items(unit_U, chunk, entry_off, 1, g_off, 1, Upad)
-            n_items = len(items)
-            T.n_items = n_items
-            T.item_begin_host = item_begin
-            T.unit_U_host = np.asarray(unit_U, dtype=np.int64)
-            T.chunk_plan = None
-            up = [items if n_items else np.zeros(1, dtype=_cabi.ITEM_DTYPE), item_begin,
-                  U_eff.astype(np.int32) if len(U_eff) else np.zeros(1, dtype=np.int32)]
-            T.item_u_count_host = items["u_count"].copy() if col else None
-            T.item_order = T.run_end_ord = T.pos_row = None
-            T.pairs = bool(col and pairs)
-            T.work_host = None
-            if col:
-                T.sm_count = sm_count
-                # items of one band and column are consecutive (tiles are ordered that way)
-                n_bands = len(T.bands["tiles"])
-                tile_band = np.repeat(np.arange(n_bands), np.diff(T.bands["tile_begin"]))
-                st_of_item = items["state"].astype(np.int64)
-                item_col = T.bands["tile_col"][st_of_item]
-                # the WORK list: what a warp takes - every item, or (two rows per lane) the items of
-                # the first tile of every pair, each carrying the index of the same run of controls
-                # in the second tile (item.g_base; the two tiles are cut alike)
-                work = np.arange(n_items, dtype=np.int64)
-                if T.pairs:
-                    n_it = np.diff(item_begin)[st_of_item]
-                    first = (st_of_item % 2) == 0        # (tiles per column and band are even)
-                    items["g_base"] = np.where(first, work + n_it, -1)
-                    work = work[first]
-                T.work_host = work
-                w_band, w_col, w_cnt = tile_band[st_of_item][work], item_col[work], T.item_u_count_host[work]
-                if n_bands > 1 or T.pairs:
-                    # the launch over the whole list (device-resident sweeps) walks the work column
-                    # by column, the bands of a column back to back: one table load per column
-                    by_col = np.argsort(w_col * n_bands + w_band, kind="stable")
-                    order = work[by_col]
-                    up.append(column_segments(w_cnt[by_col], sm_count * self.COLUMN_SEGS_PER_SM))
-                    up.append(item_run_ends(w_band * n_cols_loc + w_col))      # (natural order, per band)
-                    up += [order, item_run_ends(w_col[by_col])]
-                else:
-                    up.append(column_segments(w_cnt, sm_count * self.COLUMN_SEGS_PER_SM))
-                    up.append(item_run_ends(w_band * n_cols_loc + w_col))
-                T.n_segs = len(up[3]) - 1
-                if T.pairs:
-                    up += [work, np.concatenate(T.bands["pos_row"]).astype(np.int32)]
-                up[0] = items            # (g_base now holds the partners)
-            else:
-                T.n_segs, T.seg_begin, T.run_end = 0, None, None
-            up = self.to_device_packed(up)
-            T.items, T.item_begin, T.U_dev = up[0], up[1], up[2]
-            if col:
-                T.seg_begin, T.run_end = up[3], up[4]
-                if n_bands > 1 or T.pairs:
-                    T.item_order, T.run_end_ord = up[5], up[6]
-                T.work_dev = None
-                if T.pairs:
-                    T.work_dev, T.pos_row = up[-2], up[-1]
-                ensure("col_table", n_cols_loc * _cabi.column_pitch(n_rows0, W, T.pairs), torch.float64)
-            else:
-                T.col_table = None
-            T.band_views = None
-            n_part = max(n_items, 1) * (32 if tiled else 1)
-            T.part_val = torch.empty(n_part, dtype=torch.float64, device=dev)
-            T.part_idx = torch.empty(n_part, dtype=torch.int32, device=dev)
-            T.J_out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
-            T.argmin = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-            T.c_tables = fill_c_tables(T)
-            # (kept for Engine.recursion_fast: one chunk, one flush, batched evaluation)
-            T.build_record = None
-            if keep_staging and T.tabulate_mode == "batched" and len(flushes) == 1 and len(chunk_record) == 1 \
-                    and not col:
-                T.build_record = dict(flushes[0], host=host, w_grid=w_grid, **chunk_record[0])
-            return T
-
-        # slabs balanced by admissible controls ...
-        if col_override is not None:
-            bounds = [int(col_override[0]), int(col_override[1])]
-        elif by_columns:
-            # whole columns per rank, cut by the admissible controls of the columns
-            col_w = (U_all + 1).reshape(n_rows0, n_cols).sum(axis=0)
-            bounds = [int(b) for b in partition_by_weight(col_w, world)]
-        elif world > 1 and col_candidate:
-            # whole rows of axis 0 per rank (layout CF); a row is 1/n_rows0 of the grid
-            row_w = (U_all + 1).reshape(n_rows0, n_cols).sum(axis=1)
-            bounds = [int(b) * n_cols for b in partition_by_weight(row_w, world)]
-        else:
-            bounds = partition_by_weight(U_all + 1, world) if world > 1 else [0, n_grid]
-        override = getattr(solver, "_slab_override", None)
-        if override is not None and world == 1:
-            # developer experiments (scripts/dev_slab_chunks.py): the tables of ONE slab of
-            # the grid, as a rank of a multi-GPU run would hold them; only the streaming
-            # kernel can be run on such tables (J_out covers the slab, not the grid)
-            bounds = [int(override[0]), int(override[1])]
-        T = build_for(bounds, reuse)
-        # ... then, with several ranks, by the measured cost of a backup in each slab
-        balance = getattr(solver, "slab_balance", "auto")
-        # (layout CF cuts whole rows of axis 0 and keeps the cut by admissible controls unless
-        # the measured re-cut is asked for explicitly)
-        if world > 1 and self._cuda and balance != "controls" and not by_columns and \
-                (balance == "measured" or (T.n_backups_total >= self.REBALANCE_MIN_BACKUPS and not T.column)):
-            new_bounds = self._measured_bounds(T, U_all)
-            if new_bounds is not None and T.column:
-                new_bounds = row_aligned(new_bounds, n_cols)
-                if new_bounds == [int(b) for b in T.bounds]:
-                    new_bounds = None
-            if new_bounds is not None:
-                T = build_for(new_bounds, T)
-                T.slab_recut = True
-        self.sync()
-        T.setup_seconds = time.perf_counter() - t0
-        return T
+            return BuildPlan(self, solver, t_k, forced_axis="rows").run(None)
 
     COLUMN_SEGS_PER_SM = int(os.environ.get("SDP_COLUMN_SEGS_PER_SM", "1"))
     # share of the tiles at the end of every (band, column) run whose work items are half as long

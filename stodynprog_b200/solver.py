@@ -23,6 +23,8 @@ state grid over the GPUs of one box.
 import itertools
 from datetime import datetime
 
+import os
+
 import numpy as np
 
 from . import tabulate as tb
@@ -56,6 +58,11 @@ class DPSolver(object):
         # table layout and host tabulation mode (see Engine.build_sweep_tables)
         self.table_layout = "auto"    # "auto" | "control_minor" | "state_minor"
         self.tabulate = "auto"        # "auto" | "per_state" | "batched"
+        # batched tabulation: host threads that evaluate dyn/cost on chunks of states.  1 (the
+        # default, or SDP_HOST_THREADS) calls them on the calling thread only, as the reference does;
+        # more is an opt-in for callables that are thread-safe (pure numpy code is): "auto" = the
+        # cores this process may run on, at most 16.  Same calls, same tables either way.
+        self.host_threads = os.environ.get("SDP_HOST_THREADS", "1")
         # "auto": keep the tables as a (x,u) part + a (x,w) part whenever dyn/cost
         # have that structure (every reference example does); "off": always dense
         self.table_compress = "auto"  # "auto" | "off" | "on"

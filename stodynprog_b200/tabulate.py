@@ -635,7 +635,7 @@ def _eval_state_chunk(sys, state_cols, lo, hi, npts, w_args, t_k, W, grid_cache=
 def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid, t_k, entry_off,
                             g_off, Upad, g_per_w, flush_fn, chunk_states=4096,
                             max_doubles=16 << 20, align=1, verify=8, grid_cache=None,
-                            flat_index=None, valid=None, record=None):
+                            flat_index=None, valid=None, record=None, threads=1):
     """Second pass, batched mode: one dyn/cost call per chunk of states.
     `verify` sample states of EVERY chunk are re-evaluated per state, the
     reference's way, and compared bit-for-bit; a mismatch raises
@@ -644,7 +644,12 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
     them explicitly instead (layout CF walks the grid column by column), with
     `host_tab`, `entry_off`, ... indexed by position in that list, and `valid`
     marking the real states (False: a padding position that repeats a real state and
-    gets U = 0)."""
+    gets U = 0).
+    `threads` > 1 (DPSolver.host_threads, opt-in): the chunks are evaluated - and checked - on that
+    many host threads (numpy releases the interpreter lock inside its loops) while the calling
+    thread stages and uploads them in order.  Same calls, same arguments, same tables; the
+    reference calls dyn/cost on the calling thread only, so callables that are not thread-safe
+    must keep the default of 1."""
     d = len(sys.state)
     nb_control = len(sys.control)
     if nb_control > _cabi.SDP_MAX_C:
@@ -654,7 +659,9 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
     writer = _ChunkWriter(d, flush_fn, max_doubles, align)
     n = end - begin if flat_index is None else len(flat_index)
     chunk_states = max(align, chunk_states // align * align)
-    for b0 in range(0, n, chunk_states):
+
+    def evaluate(b0):
+        """the user's callables on one chunk (and its check): independent of every other chunk"""
         b1 = min(b0 + chunk_states, n)
         S = b1 - b0
         flat = np.arange(begin + b0, begin + b1) if flat_index is None else flat_index[b0:b1]
@@ -670,6 +677,10 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
             # np.where / clipping may differ: each is checked on its own sample states
             _verify_chunk(sys, cols, host_tab, b0, outs, w_args, t_k, W, min(verify, S),
                           None if valid is None else valid[b0:b1], w_shape)
+        return b1, cols, npts, outs
+
+    for b0, (b1, cols, npts, outs) in _in_order(evaluate, range(0, n, chunk_states), threads):
+        S = b1 - b0
         recs = np.zeros(S, dtype=_cabi.STATE_DESC_DTYPE)
         recs["npts"] = 1
         recs["npts"][:, :nb_control] = npts
@@ -692,6 +703,32 @@ def tabulate_states_batched(sys, state_grid, begin, end, host_tab, perturb_grid,
             record.append(dict(cols=cols, outs=outs, g_base=int(base), b0=b0, b1=b1))
         writer.add_descs(recs)
     writer.flush()
+
+
+def _in_order(fn, keys, threads=1, ahead=2):
+    """yield (key, fn(key)) in the order of `keys`; with threads > 1 up to ahead*threads calls
+    run on worker threads ahead of the consumer.  An exception of a call surfaces, at its turn, in
+    the consumer; calls not yet started are then dropped."""
+    keys = list(keys)
+    if threads <= 1 or len(keys) <= 1:
+        for k in keys:
+            yield k, fn(k)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    window = max(2, ahead * threads)
+    pool = ThreadPoolExecutor(max_workers=threads, thread_name_prefix="sdp-tabulate")
+    pending = []
+    try:
+        nxt = 0
+        for k in keys:
+            while nxt < len(keys) and len(pending) < window:
+                pending.append(pool.submit(fn, keys[nxt]))
+                nxt += 1
+            yield k, pending.pop(0).result()
+    finally:
+        for f in pending:
+            f.cancel()
+        pool.shutdown(wait=True)
 
 
 class BatchedMismatch(Exception):

@@ -525,6 +525,63 @@ def test_batched_tabulation_checks_every_chunk():
     assert seen and T.tabulate_mode == "per_state"
 
 
+@pytest.mark.parametrize("layout", ["auto", "control_minor"])
+def test_host_threads_give_the_same_tables(layout):
+    """DPSolver.host_threads: chunks evaluated on worker threads, staged in order by the caller:
+    the same tables, bit for bit, the calls really made off the calling thread, and a chunk that
+    fails its check still ends the batched mode"""
+    import threading
+    import workloads as wl
+    from fake_lib import FakeLib
+    real = tb.tabulate_states_batched
+
+    def small_chunks(*a, **k):
+        k["chunk_states"] = 96
+        return real(*a, **k)
+
+    def tables(threads, cost_wrapper=None):
+        prob = wl.storage_ar1(sdp, n_E=70, n_P=33, steps=(0.3, 0.1), _test_lib=FakeLib())
+        sv = prob.solver
+        sv.table_layout = layout
+        sv.host_threads = threads
+        if cost_wrapper:
+            sv.sys._cost = cost_wrapper(sv.sys.cost)
+        tb.tabulate_states_batched = small_chunks
+        try:
+            return sv.sweep_tables(), sv
+        finally:
+            tb.tabulate_states_batched = real
+
+    names = set()
+
+    def noting(cost):
+        def f(*a):
+            if np.ndim(a[0]) > 0:
+                names.add(threading.current_thread().name)
+            return cost(*a)
+        return f
+    (T1, sv1), (T4, sv4) = tables(1), tables(4, noting)
+    assert T1.tabulate_mode == T4.tabulate_mode == "batched"
+    assert any(n.startswith("sdp-tabulate") for n in names)
+    assert T1.n_entries == T4.n_entries
+    for name in ("cell", "lam", "g"):       # (the allocations end in uninitialised padding)
+        a, b = getattr(T1, name).numpy()[:T1.n_entries], getattr(T4, name).numpy()[:T1.n_entries]
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), name
+    J0 = np.random.default_rng(3).standard_normal(sv1._state_grid_shape)
+    (J1, p1), (J4, p4) = sv1.value_iteration(J0), sv4.value_iteration(J0)
+    assert np.array_equal(J1.view(np.int64), J4.view(np.int64)) and np.array_equal(p1, p4)
+    assert tables("auto")[0].tabulate_mode == "batched"
+
+    def sneaky(cost):
+        def f(E, *a):
+            g = cost(E, *a)
+            return g + 1e-3 * np.mean(E) if (np.ndim(E) > 0 and np.max(E) > 9.) else g
+        return f
+    assert tables(4, sneaky)[0].tabulate_mode == "per_state"
+    with pytest.raises(ValueError):
+        tables(0)
+
+
 def test_cached_tables_follow_the_callables(port):
     """The reference calls dyn / cost / control_box afresh in every sweep, so a change of a
     global or closure variable they read takes effect at once (its doc/example_inventory.py cost

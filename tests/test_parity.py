@@ -1118,7 +1118,7 @@ def test_column_bands_choice(product, monkeypatch):
 def test_column_hoist_is_refused_when_it_does_not_apply(product):
     """a w-part that varies along a column is detected on the built tables: "auto" falls
     back to layout BF (same results), "on" raises; so do grids or layouts CF cannot take"""
-    import stodynprog_b200.engine as engine_mod
+    import stodynprog_b200.tablebuild as engine_mod
     ref = _coupled_w_system(_Api(product, "model", "state_minor", "auto", "on"))
     ref.column_hoist = "off"
     auto = _coupled_w_system(_Api(product, "model", "state_minor", "auto", "on"))
