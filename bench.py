@@ -591,6 +591,11 @@ def run_ours(args):
             "config": workload_config(name, dims, T.W),
             "plan": {"backups_per_sweep": total_backups, "table_layout": T.layout_name,
                      "row_bands": (T.bands["rows"] if T.column else None),
+                     # (the e2e path sweeps the columns in pieces, each on its way to the host
+                     # while the next ones are swept)
+                     "column_pieces": ([[ch["c0"], ch["c1"]] for ch in eng._chunk_plan(T)]
+                                       if (T.column and world == 1 and eng.can_overlap_results(T)
+                                           and len(T.bands["tiles"]) == 1) else None),
                      "shard_axis": (None if world == 1 else "columns" if T.col_bounds is not None else "rows"),
                      "tabulate_mode": T.tabulate_mode, "host_threads": int(sv.host_threads),
                      "item_chunk": T.item_chunk,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SDP_ABI_VERSION 7
+#define SDP_ABI_VERSION 8
 #define SDP_MAX_D 4 /* the reference dispatches d = 1..4 (multilinear_cython.pyx:36-47) */
 
 /* error codes */
@@ -418,6 +418,29 @@ int sdp_policy_eval_p2p(const SdpGrid* grid, int32_t W, int32_t g_per_w, const d
  * (or the centre point (lo+hi)/2 when npts == 1). */
 int sdp_policy_values(int64_t n, int32_t nc, const double* lo, const double* hi,
                       const int32_t* npts, const int32_t* argmin, double* pol, void* stream);
+
+/* One rank, layout CF, results handed out by COLUMN pieces (the host path of value_iteration:
+ * a piece is swept, combined and on its way to the host while the next pieces compute).  `tab` is a
+ * view of the tables on the columns [col_begin, col_begin + tab->n_cols) of a grid of glob_cols
+ * columns: item_begin starts at the first tile of col_begin, one band of rows.  The per-state
+ * combine of sdp_sweep_finalize for those columns; J_out / argmin_out are WHOLE-GRID arrays in
+ * grid order (state row*glob_cols + col).  nc > 0: the argmin is also mapped to control values
+ * as by sdp_policy_values (lo / hi / npts / pol: whole-grid [state][nc]) - the
+ * `u_grids[i].flatten()[ind_opt[i]]` of stodynprog.py:686-689 fused into the combine.
+ * beside_sweep != 0: a later piece is being swept on another stream meanwhile; the launch then uses
+ * CTAs of 128 threads x 32 registers, which fit next to a resident CTA of the streaming kernel (one
+ * per SM, 768 threads x 80 registers), so the combine does not wait for an SM to drain. */
+int sdp_sweep_finalize_cols(const SdpTables* tab, const double* part_val, const int32_t* part_idx,
+                            double* J_out, int32_t* argmin_out, int64_t glob_cols, int64_t col_begin,
+                            int32_t nc, const double* lo, const double* hi, const int32_t* npts,
+                            double* pol, int32_t beside_sweep, void* stream);
+
+/* `height` rows of `width` bytes from src (row pitch spitch bytes) to dst (row pitch dpitch),
+ * asynchronously on the stream; either side device or page-locked host memory.  Puts a column
+ * piece of a result where it belongs in the caller's C-order host array (the reference returns
+ * J_k and pol_k as C-order arrays over the state grid, stodynprog.py:496-499). */
+int sdp_memcpy_2d(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width,
+                  int64_t height, void* stream);
 
 /* Relative-DP normalisation: ref_out[0] = J[ref_index]; J[i] -= ref_out[0]
  * (stodynprog.py:523-525, :760-762).  J: device [n]. */

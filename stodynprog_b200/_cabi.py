@@ -12,7 +12,7 @@ import numpy as np
 
 SDP_MAX_D = 4
 SDP_MAX_C = 4
-SDP_ABI_VERSION = 7
+SDP_ABI_VERSION = 8
 LAYOUT_CONTROL_MINOR = 0   # "A": [state][w][u]
 LAYOUT_STATE_MINOR = 1     # "B": [tile of 32 states][u][w][lane]
 LAYOUT_CONTROL_MINOR_FACTORED = 2   # "AF": (x,u) part [state][Upad] + (x,w) part [state][W]
@@ -151,6 +151,9 @@ SIGNATURES = {
     "sdp_policy_eval_p2p": (ctypes.c_int, [_gp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64,
                                            _vp, ctypes.POINTER(SdpPeers), _vp, _vp, _vp, _vp, _vp]),
     "sdp_policy_values": (ctypes.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sdp_sweep_finalize_cols": (ctypes.c_int, [ctypes.POINTER(SdpTables), _vp, _vp, _vp, _vp, _i64, _i64,
+                                               _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "sdp_memcpy_2d": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "sdp_rel_shift": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "sdp_supnorm_diff": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "sdp_interp": (ctypes.c_int, [_gp, _i64, _vp, _i64, _vp, _vp, _vp]),

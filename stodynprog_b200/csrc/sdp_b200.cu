@@ -1066,6 +1066,8 @@ struct Tuning {
     int col_dynamic;   // layout CF: warps take the items of a column first come first served (1) or round-robin (0)
     int col_prepass;   // layout CF: column tables from the coalesced pre-pass, copied by vector loads (1) or by the TMA engine (2); 0: gathered by every CTA
     int pdl;           // programmatic dependent launch of pre-pass / column sweep / combine (1) or plain launches (0)
+    int small_combine; // sdp_sweep_finalize_cols: the 128-thread combine that fits next to a streaming CTA (1) or the 1024-thread one (0)
+    int carveout;      // layout CF: streaming kernel and small combine ask for the largest shared-memory carve-out (1) or leave it to the driver (0)
     int dbg_exchange;  // TIMING EXPERIMENTS ONLY (wrong results): 1 = no stores to remote ranks, 2 = no system fence, 4 = relaxed flag stores
 };
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -1109,6 +1111,8 @@ static Tuning& tuning() {
         x.col_dynamic = env_int("SDP_COL_DYNAMIC", 1) != 0;
         x.dbg_exchange = 0;
         x.pdl = env_int("SDP_PDL", 1) != 0;
+        x.small_combine = env_int("SDP_SMALL_COMBINE", 1) != 0;
+        x.carveout = env_int("SDP_CARVEOUT", 1) != 0;
         return x;
     }();
     return t;
@@ -1134,6 +1138,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "col_dynamic")) t.col_dynamic = value != 0;
     else if (!strcmp(name, "dbg_exchange")) t.dbg_exchange = value;
     else if (!strcmp(name, "pdl")) t.pdl = value != 0;
+    else if (!strcmp(name, "small_combine")) t.small_combine = value != 0;
     else return fail(SDP_EINVAL, "sdp_set_option: unknown option %s", name);
     return SDP_OK;
 }
@@ -2138,6 +2143,15 @@ static int launch_fact_column_k(const GridT<double>& G, const SdpTables& T, cons
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, false, MAXT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        // the largest shared-memory carve-out (the kernel streams with evict-first loads: 2 % L1 hit
+        // rate): k_combine_column_small asks for the same one, so that one of its CTAs can join a
+        // resident CTA of this kernel without the SM draining to change its configuration
+        if (e == cudaSuccess && tuning().carveout)
+            e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, true, MAXT>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess && tuning().carveout)
+            e = cudaFuncSetAttribute(k_sweep_fact_column<D, WM, UB, PF, false, MAXT>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return fail(SDP_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = shm;
     }
@@ -2730,12 +2744,35 @@ __global__ void k_p2p_barrier(PeersDev P, unsigned long long timeout_ns) {
 // contiguous bytes into the local buffer, or into every rank's buffer over NVLink).
 // State (row, col) of the band goes to J[j_offset + row * j_pitch + col] and to
 // argmin_out[row * n_cols + col].  P.world == 0: local store into J_out, no epoch.
+// value of control axis c at index idx of a grid of m points on [a, b]: the reference's
+// np.linspace arithmetic (stodynprog.py:458, numpy's linspace: step = delta/div, y = idx*step + a,
+// last point forced to b; one point: the middle)
+__device__ __forceinline__ double control_axis_value(int m, int idx, double a, double b) {
+    if (m == 1) return div_(add_(a, b), 2.0);
+    if (idx == m - 1) return b;
+    const double div = (double)(m - 1);
+    const double delta = sub_(b, a);
+    const double step = div_(delta, div);
+    if (step == 0.0) return add_(mul_(div_((double)idx, div), delta), a);
+    return add_(mul_((double)idx, step), a);
+}
+
+// optional tail of the CF combine: the argmin of every state mapped to control VALUES (K3 fused;
+// lo / hi / npts / pol indexed by grid state like J_out).  nc == 0: off.
+struct PolMap {
+    int nc;
+    const double* lo;
+    const double* hi;
+    const int32_t* npts;
+    double* pol;
+};
+
 __global__ void __launch_bounds__(1024)
 k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
                  const int64_t* __restrict__ item_begin, const double* __restrict__ part_val,
                  const int32_t* __restrict__ part_idx, double* __restrict__ J_out,
                  int32_t* __restrict__ argmin_out, PeersDev P, int64_t j_offset, int64_t j_pitch, int dbg,
-                 const int32_t* __restrict__ pos_row) {
+                 const int32_t* __restrict__ pos_row, int64_t a_offset, int64_t a_pitch, PolMap M) {
     __shared__ double v_sh[32][33];
     __shared__ int i_sh[32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2763,10 +2800,20 @@ k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
         const int r = pos_row ? pos_row[ty * 32 + warp] : ty * 32 + warp, c = c0 + lane;
         if (r >= 0 && r < n_rows && c < n_cols) {
             const double bv = v_sh[warp][lane];
-            argmin_out[(int64_t)r * n_cols + c] = i_sh[warp][lane];
+            argmin_out[a_offset + (int64_t)r * a_pitch + c] = i_sh[warp][lane];
             const int64_t g = j_offset + (int64_t)r * j_pitch + c;
             if (P.world == 0) {
                 J_out[g] = bv;
+                if (M.nc > 0) {
+                    // (same arithmetic as k_policy_values)
+                    long long rem = i_sh[warp][lane];
+                    for (int k = M.nc - 1; k >= 0; --k) {
+                        const int m = M.npts[g * M.nc + k];
+                        const int idx = (int)(rem % m);
+                        rem /= m;
+                        M.pol[g * M.nc + k] = control_axis_value(m, idx, M.lo[g * M.nc + k], M.hi[g * M.nc + k]);
+                    }
+                }
             } else {
 #pragma unroll
                 for (int q = 0; q < SDP_MAX_PEERS; ++q)
@@ -2788,14 +2835,19 @@ k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
 // launch of the above for one band of layout CF
 static void launch_combine_column(const SdpTables& T, const double* part_val, const int32_t* part_idx,
                                   double* J_out, int32_t* argmin_out, const PeersDev& P,
-                                  int64_t j_offset, int64_t j_pitch, cudaStream_t st) {
+                                  int64_t j_offset, int64_t j_pitch, cudaStream_t st,
+                                  int64_t a_offset = 0, int64_t a_pitch = -1, const PolMap* map = nullptr) {
+    PolMap M;
+    memset(&M, 0, sizeof(M));
+    if (map) M = *map;
+    if (a_pitch < 0) a_pitch = T.n_cols;       // (the argmin stays local: state r*n_cols + c of the shard)
     const int n_rows = T.n_cols > 0 ? (int)(T.n_states / T.n_cols) : 0;
     const int col_blocks = T.n_cols > 0 ? (T.n_cols + 31) / 32 : 1;
     unsigned blocks = (unsigned)col_blocks * (unsigned)(T.pos_row ? T.tiles_per_col : (n_rows + 31) / 32);
     if (blocks == 0 || n_rows == 0) blocks = 1;       // (an empty shard still publishes its epoch)
     launch_pdl(k_combine_column, dim3(blocks), dim3(1024), 0, st, n_rows, T.n_cols, T.tiles_per_col, col_blocks,
                T.item_begin, part_val, part_idx, J_out, argmin_out, P, j_offset, j_pitch,
-               tuning().dbg_exchange, T.pos_row);
+               tuning().dbg_exchange, T.pos_row, a_offset, a_pitch, M);
 }
 
 static void launch_combine_column_local(const SdpTables& T, const double* part_val, const int32_t* part_idx,
@@ -2875,6 +2927,141 @@ extern "C" int sdp_sweep_finalize_p2p_cols(const SdpTables* tab, const double* p
     // (an empty shard still launches one CTA: the epoch must advance on every rank)
     launch_combine_column(T, part_val, part_idx, nullptr, argmin_out, P, col_begin, glob_cols, st);
     SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+// The CF combine for the host path of one rank (sdp_sweep_finalize_cols): same tile of 32 rows x
+// 32 columns transposed through shared memory as k_combine_column, but 128 threads and at most 32
+// registers per thread, so that a CTA fits NEXT TO a resident CTA of the streaming kernel (768
+// threads x 80 registers leave 4 096 registers per SM): the combine of one column piece then runs
+// while the next piece is being swept on another stream, instead of waiting for an SM to drain,
+// and the piece's results leave for the host that much earlier.  Maps the argmin to control
+// values in the same pass (K3 fused).
+__global__ void __launch_bounds__(128, 16)
+k_combine_column_small(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
+                       const int64_t* __restrict__ item_begin, const double* __restrict__ part_val,
+                       const int32_t* __restrict__ part_idx, double* __restrict__ J_out,
+                       int32_t* __restrict__ argmin_out, int64_t offset, int64_t pitch,
+                       const int32_t* __restrict__ pos_row, PolMap M) {
+    __shared__ double v_sh[32][33];
+    __shared__ int i_sh[32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ty = blockIdx.x / col_blocks;                 // tile (32 rows) of the band
+    const int c0 = (blockIdx.x - ty * col_blocks) * 32;
+    // (few warps next to a busy streaming CTA: what counts is loads in flight - the item ranges of
+    // the warp's 8 columns are fetched by 8 lanes at once, the partial minima 4 items at a time)
+    long long b0 = 0, b1 = 0;
+    if (lane < 8 && c0 + warp + 4 * lane < n_cols) {
+        const int64_t tile = (int64_t)(c0 + warp + 4 * lane) * tiles_per_col + ty;
+        b0 = item_begin[tile];
+        b1 = item_begin[tile + 1];
+    }
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const long long k0 = __shfl_sync(0xffffffffu, b0, j), k1 = __shfl_sync(0xffffffffu, b1, j);
+        const int lc = warp + 4 * j;
+        if (c0 + lc >= n_cols) break;
+        double bv = CUDART_INF;
+        int bi = INT_MAX;
+        for (long long k = k0; k < k1; k += 4) {
+            double v[4];
+            int ix[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long kk = (k + u < k1) ? k + u : k1 - 1;
+                v[u] = part_val[kk * 32 + lane];
+                ix[u] = part_idx[kk * 32 + lane];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k + u < k1 && better(v[u], ix[u], bv, bi)) { bv = v[u]; bi = ix[u]; }
+        }
+        v_sh[lane][lc] = bv;
+        i_sh[lane][lc] = bi;
+    }
+    __syncthreads();
+    const int c = c0 + lane;
+    if (c >= n_cols) return;
+    const int nc = M.nc;
+    const double* __restrict__ lo = M.lo;
+    const double* __restrict__ hi = M.hi;
+    const int32_t* __restrict__ npts = M.npts;
+    double* __restrict__ pol = M.pol;
+#pragma unroll 2
+    for (int lr = warp; lr < 32; lr += 4) {
+        const int r = pos_row ? pos_row[ty * 32 + lr] : ty * 32 + lr;
+        if (r < 0 || r >= n_rows) continue;
+        const int64_t g = offset + (int64_t)r * pitch + c;
+        const int bi = i_sh[lr][lane];
+        J_out[g] = v_sh[lr][lane];
+        argmin_out[g] = bi;
+        unsigned rem = (unsigned)bi;          // (a flat index below 2^31)
+        for (int k = nc - 1; k >= 0; --k) {
+            const int m = npts[g * nc + k];
+            const double a = lo[g * nc + k], b = hi[g * nc + k];
+            const int idx = (int)(rem % (unsigned)m);
+            rem /= (unsigned)m;
+            pol[g * nc + k] = control_axis_value(m, idx, a, b);
+        }
+    }
+}
+
+// One rank, layout CF, results streamed by COLUMN pieces: the combine of the columns
+// [col_begin, col_begin + tab->n_cols) of a grid of glob_cols columns (tab: a view whose item_begin
+// starts at the first tile of col_begin).  J_out / argmin_out are whole-grid arrays in grid order;
+// with nc > 0 the argmin is also mapped to control values (lo / hi / npts / pol whole-grid, [state][nc]).
+// beside_sweep != 0: another piece is being swept meanwhile - launch the 128-thread variant whose CTAs
+// fit next to the resident streaming CTAs; 0: the GPU is free, the 1024-thread variant is quicker.
+extern "C" int sdp_sweep_finalize_cols(const SdpTables* tab, const double* part_val, const int32_t* part_idx,
+                                       double* J_out, int32_t* argmin_out, int64_t glob_cols, int64_t col_begin,
+                                       int32_t nc, const double* lo, const double* hi, const int32_t* npts,
+                                       double* pol, int32_t beside_sweep, void* stream) {
+    if (!tab) return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_cols: tables is NULL");
+    const SdpTables& T = *tab;
+    int rc = check_tables(T, "sdp_sweep_finalize_cols");
+    if (rc) return rc;
+    if (!is_column(T)) return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_cols: the tables are not in layout CF");
+    if (T.n_states == 0) return SDP_OK;
+    if ((rc = check_column_band(T, "sdp_sweep_finalize_cols"))) return rc;
+    if (col_begin < 0 || glob_cols < col_begin + T.n_cols || !part_val || !part_idx || !J_out || !argmin_out ||
+        nc < 0 || (nc > 0 && (!lo || !hi || !npts || !pol)))
+        return fail(SDP_EINVAL, "%s", "sdp_sweep_finalize_cols: bad arguments");
+    PeersDev none;
+    memset(&none, 0, sizeof(none));
+    PolMap M;
+    M.nc = nc; M.lo = lo; M.hi = hi; M.npts = npts; M.pol = pol;
+    const int n_rows = (int)(T.n_states / T.n_cols);
+    const int col_blocks = (T.n_cols + 31) / 32;
+    const unsigned blocks = (unsigned)col_blocks * (unsigned)(T.pos_row ? T.tiles_per_col : (n_rows + 31) / 32);
+    static bool carve_set = false;
+    if (!carve_set && tuning().carveout) {
+        cudaFuncSetAttribute(k_combine_column_small, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
+    if (beside_sweep && tuning().small_combine)
+        k_combine_column_small<<<blocks, 128, 0, (cudaStream_t)stream>>>(
+            n_rows, T.n_cols, T.tiles_per_col, col_blocks, T.item_begin, part_val, part_idx, J_out, argmin_out,
+            col_begin, glob_cols, T.pos_row, M);
+    else
+        launch_combine_column(T, part_val, part_idx, J_out, argmin_out, none, col_begin, glob_cols,
+                              (cudaStream_t)stream, col_begin, glob_cols, &M);
+    SDP_LAUNCH_CHECK();
+    return SDP_OK;
+}
+
+// `height` rows of `width` bytes from src (pitch spitch) to dst (pitch dpitch), asynchronously on
+// the stream; either side may be device or page-locked host memory (the column pieces of a result
+// go to their place in the caller's C-order host arrays this way)
+extern "C" int sdp_memcpy_2d(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width,
+                             int64_t height, void* stream) {
+    if (width < 0 || height < 0 || dpitch < width || spitch < width)
+        return fail(SDP_EINVAL, "%s", "sdp_memcpy_2d: bad sizes");
+    if (width == 0 || height == 0) return SDP_OK;
+    if (!dst || !src) return fail(SDP_EINVAL, "%s", "sdp_memcpy_2d: NULL pointer");
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height,
+                                      cudaMemcpyDefault, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(SDP_ECUDA, "sdp_memcpy_2d: %s", cudaGetErrorString(e));
     return SDP_OK;
 }
 
@@ -3180,20 +3367,7 @@ k_policy_values(int64_t n, int nc, const double* __restrict__ lo, const double* 
         const int m = npts[i * nc + c];
         const int idx = (int)(rem % m);
         rem /= m;
-        const double a = lo[i * nc + c], b = hi[i * nc + c];
-        double y;
-        if (m == 1) {
-            y = div_(add_(a, b), 2.0);
-        } else if (idx == m - 1) {
-            y = b;
-        } else {
-            const double div = (double)(m - 1);
-            const double delta = sub_(b, a);
-            const double step = div_(delta, div);
-            if (step == 0.0) y = add_(mul_(div_((double)idx, div), delta), a);
-            else y = add_(mul_((double)idx, step), a);
-        }
-        pol[i * nc + c] = y;
+        pol[i * nc + c] = control_axis_value(m, idx, lo[i * nc + c], hi[i * nc + c]);
     }
 }
 

@@ -738,14 +738,22 @@ class Engine(object):
                     return False
         return True
 
-    # layout CF on one rank: the rows are cut into bands of decreasing size so that the
-    # results of a band can travel to the host while the next bands are swept (sweep_to_host)
-    # Measured on config #5 (profiles/r1_column_tuning.txt), ms per device-resident sweep /
-    # ms per value_iteration call with host arrays: 1 band 1.21 / 1.93, 3 bands (45 / 25 /
-    # 30 % of the controls) 1.29 / 1.75, 5 bands (45 / 25 / 15 / 10 / 5 %) 1.75 / 1.72 - a
-    # small band gives a CTA only a round or two of items per column table.
-    COLUMN_BANDS = os.environ.get("SDP_COLUMN_BANDS", "auto")    # "auto" | number of bands
-    COLUMN_BAND_FRACTIONS = (0.45, 0.25, 0.30)
+    # layout CF on one rank, results for the host: the grid is swept in a few PIECES OF COLUMNS (see
+    # _chunk_plan / sweep_to_host), each combined, mapped to control values and sent to its place
+    # in the caller's arrays (2-D copies) while the next pieces are swept.  A piece of columns
+    # costs a CTA no extra column table, unlike a band of ROWS, which costs every CTA a table load
+    # and a drained barrier per (band, column) it meets: measured on config #5
+    # (profiles/r1_column_tuning.txt, r2_emu_variants_bands.txt) the three row bands of round 1
+    # took 1.256 ms per sweep against 1.146 ms for one band.  Row bands remain available
+    # (SDP_COLUMN_BANDS = number of bands) and take the per-band path below.
+    COLUMN_BANDS = os.environ.get("SDP_COLUMN_BANDS", "auto")    # "auto" (one band) | number of row bands
+    # shares of the columns (by admissible controls) of the pieces, in sweep order: the copy of a
+    # piece hides behind the pieces after it, the last piece's copy behind nothing
+    COLUMN_PIECES = tuple(float(x) for x in os.environ.get("SDP_COLUMN_PIECES", "0.3,0.3,0.3,0.1").split(","))
+    # ... with the cuts moved to the nearest multiple of the CTA count when that is within a third
+    # of a piece: every CTA then sweeps WHOLE columns of the piece (a CTA that starts or ends a
+    # piece in the middle of a column pays an extra column table and barrier, ~10 us)
+    COLUMN_PIECES_ALIGN = os.environ.get("SDP_COLUMN_PIECES_ALIGN", "1") != "0"
 
     def _column_bands(self, row_weight, W):
         """row boundaries of the bands of layout CF for a slab whose rows weigh `row_weight`
@@ -756,14 +764,10 @@ class Engine(object):
         if self.coll.world > 1:
             return one               # the fused combine + exchange publishes one epoch per sweep
         if mode == "auto":
-            big = (self._cuda and self.coll.world == 1
-                   and float(np.sum(row_weight)) * W >= self.OVERLAP_MIN_BACKUPS
-                   and os.environ.get("SDP_OVERLAP", "1") != "0")
-            fractions = self.COLUMN_BAND_FRACTIONS if big else (1.0,)
-        else:
-            k = max(1, int(mode))
-            fractions = self.OVERLAP_FRACTIONS[:k - 1] + (1.0,) if k <= len(self.OVERLAP_FRACTIONS) \
-                else tuple([1.0 / k] * k)
+            return one               # results leave by pieces of columns (_column_piece_plan)
+        k = max(1, int(mode))
+        fractions = self.OVERLAP_FRACTIONS[:k - 1] + (1.0,) if k <= len(self.OVERLAP_FRACTIONS) \
+            else tuple([1.0 / k] * k)
         if len(fractions) == 1 or n_rows < 64 * len(fractions):
             return one
         csum = np.cumsum(np.asarray(row_weight, dtype=np.float64))
@@ -932,8 +936,8 @@ class Engine(object):
     OVERLAP_FRACTIONS = (0.45, 0.25, 0.15, 0.10, 0.05)
 
     def can_overlap_results(self, T):
-        if T.column and len(T.bands["tiles"]) < 2:
-            return False             # layout CF streams its results band by band
+        if T.column and len(T.bands["tiles"]) < 2 and (T.n_cols < 2 or T.col_bounds is not None):
+            return False             # layout CF streams its results by pieces of columns (or row bands)
         return (self._cuda and self.coll.world == 1 and T.n_items >= self.OVERLAP_MIN_ITEMS
                 and T.n_backups_local >= self.OVERLAP_MIN_BACKUPS
                 and os.environ.get("SDP_OVERLAP", "1") != "0")
@@ -944,6 +948,9 @@ class Engine(object):
         same tables: shifted item / item_begin pointers), so that its results can
         travel to the host while the next run computes"""
         if T.chunk_plan is not None:
+            return T.chunk_plan
+        if T.column and len(T.bands["tiles"]) == 1:
+            T.chunk_plan = self._column_piece_plan(T)
             return T.chunk_plan
         if T.column:
             # one run per band: its own CTA segments over the band's items (absolute item
@@ -998,6 +1005,64 @@ class Engine(object):
         T.chunk_plan = plan
         return plan
 
+    def _column_piece_plan(self, T):
+        """layout CF, one band: the columns cut into a few pieces of decreasing weight
+        (COLUMN_PIECES).  The items of a column are consecutive, so a piece is a range of the
+        work list with its own CTA segments (absolute positions; the column tables are tabulated
+        once before the first piece) and a view of the tables on its columns for the combine."""
+        tpc = int(T.bands["tiles"][0])
+        n_cols = T.n_cols
+        n_rows = T.n_states // n_cols
+        first_item = T.item_begin_host[np.arange(n_cols + 1, dtype=np.int64) * tpc]      # per column
+        csum = np.concatenate([[0], np.cumsum(T.item_u_count_host, dtype=np.float64)])[first_item]
+        cuts, acc = [0], 0.0
+        for f in self.COLUMN_PIECES[:-1]:
+            acc += f
+            c = int(np.searchsorted(csum, acc * csum[-1], side="left"))
+            n_ctas = T.sm_count * self.COLUMN_SEGS_PER_SM
+            if self.COLUMN_PIECES_ALIGN and n_cols >= 2 * n_ctas:
+                a = cuts[-1] + max(1, int(round((c - cuts[-1]) / float(n_ctas)))) * n_ctas
+                if abs(a - c) * 3 <= max(c - cuts[-1], 1):
+                    c = a
+            if cuts[-1] < c < n_cols:
+                cuts.append(c)
+        cuts.append(n_cols)
+        plan = []
+        for c0, c1 in zip(cuts[:-1], cuts[1:]):
+            # (positions of the work list - every item, or with two rows per lane the items of the
+            # first tile of every pair - that belong to the piece)
+            i0, i1 = (int(np.searchsorted(T.work_host, first_item[c])) for c in (c0, c1))
+            seg = i0 + column_segments(T.item_u_count_host[T.work_host[i0:i1]],
+                                       T.sm_count * self.COLUMN_SEGS_PER_SM)
+            seg_dev = self.to_device_packed([seg])[0]
+            cp = _cabi.SdpTables.from_buffer_copy(T.c_tables)
+            cp.seg_begin, cp.n_segs, cp.col_table_ready = seg_dev.data_ptr(), len(seg) - 1, 1
+            cp.item_order = T.work_dev.data_ptr() if T.work_dev is not None else 0
+            cp.run_end = T.run_end.data_ptr()
+            view = _cabi.SdpTables.from_buffer_copy(T.c_tables)
+            view.item_begin = T.c_tables.item_begin + 8 * c0 * tpc
+            view.n_cols = c1 - c0
+            view.n_states = n_rows * (c1 - c0)
+            plan.append(dict(kind="cols", tab_p=cp, tab_f=view, c0=c0, c1=c1, n_rows=n_rows, keep=seg_dev,
+                             pv=ctypes.c_void_p(T.part_val.data_ptr()),
+                             pi=ctypes.c_void_p(T.part_idx.data_ptr())))
+        return plan
+
+    def _columns_to_host(self, T, ch, J_new, pol, J_pin, pol_pin):
+        """on the copy stream: the columns [c0, c1) of J and of the policy (device, grid order) into
+        the same columns of the C-order host arrays - one 2-D copy each"""
+        nc, n_cols, c0, c1, n_rows = T.nb_control, T.n_cols, ch["c0"], ch["c1"], ch["n_rows"]
+        cs = ctypes.c_void_p(self._copy.cuda_stream)
+        rc = self.lib.sdp_memcpy_2d(ctypes.c_void_p(J_pin.data_ptr() + 8 * c0), 8 * n_cols,
+                                    ctypes.c_void_p(J_new.data_ptr() + 8 * c0), 8 * n_cols,
+                                    8 * (c1 - c0), n_rows, cs)
+        _cabi.check(rc, "sdp_memcpy_2d")
+        if nc:
+            rc = self.lib.sdp_memcpy_2d(ctypes.c_void_p(pol_pin.data_ptr() + 8 * nc * c0), 8 * nc * n_cols,
+                                        ctypes.c_void_p(pol.data_ptr() + 8 * nc * c0), 8 * nc * n_cols,
+                                        8 * nc * (c1 - c0), n_rows, cs)
+            _cabi.check(rc, "sdp_memcpy_2d")
+
     def sweep_to_host(self, T, J_prev, J_new, while_waiting=None):
         """One sweep of a single-rank slab, returning (J, pol) as host arrays in
         page-locked memory.  The slab is swept in a few runs on two alternating
@@ -1012,6 +1077,15 @@ class Engine(object):
             self._side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
             self._copy = torch.cuda.Stream(dev)
         main = torch.cuda.current_stream(dev)
+        # developer timeline (scripts/dev_e2e_timeline.py): a list that receives (label, event)
+        trace = getattr(self, "_trace", None)
+
+        def mark(label, stream):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                trace.append((label, e))
+        mark("J on the device", main)
         pol = torch.empty((n, nc), dtype=torch.float64, device=dev)
         J_pin = self.host_result_buffer((n,), torch.float64)
         pol_pin = self.host_result_buffer((n, nc), torch.float64)
@@ -1021,14 +1095,42 @@ class Engine(object):
             _cabi.check(rc, "sdp_column_table")
         ev0 = torch.cuda.Event()
         ev0.record(main)
-        for k, ch in enumerate(self._chunk_plan(T)):
+        mark("column tables", main)
+        plan = self._chunk_plan(T)
+        after = None
+        for k, ch in enumerate(plan):
             st = self._side[k % 2]
             sp = ctypes.c_void_p(st.cuda_stream)
             st.wait_event(ev0)
-            s0, s1 = ch["s0"], ch["s1"]
+            if after is not None:
+                st.wait_event(after)       # (the last piece of columns starts after the combine before it)
+                after = None
             rc = self.lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(ch["tab_p"]),
                                              self._ptr(J_prev), ch["pv"], ch["pi"], sp)
             _cabi.check(rc, "sdp_sweep_partials")
+            mark("run %d swept" % k, st)
+            if ch.get("kind") == "cols":
+                # the combine of a piece runs beside the sweep of the next one (small CTAs that fit
+                # next to the resident streaming CTAs; it takes ~180 us that way, hidden) - except the
+                # last two: the results of the last-but-one piece would leave too late, so its
+                # combine (15 us on the free GPU) goes BEFORE the last sweep, and nothing runs
+                # beside the last combine
+                beside = k + 2 < len(plan)
+                ev = torch.cuda.Event()
+                rc = self.lib.sdp_sweep_finalize_cols(
+                    ctypes.byref(ch["tab_f"]), self._ptr(T.part_val), self._ptr(T.part_idx), self._ptr(J_new),
+                    self._ptr(T.argmin), T.n_cols, ch["c0"], nc, self._ptr(T.lo_dev), self._ptr(T.hi_dev),
+                    self._ptr(T.npts_dev), self._ptr(pol) if nc else ctypes.c_void_p(0), int(beside), sp)
+                _cabi.check(rc, "sdp_sweep_finalize_cols")
+                ev.record(st)
+                if k + 2 == len(plan):
+                    after = ev
+                mark("run %d combined + mapped" % k, st)
+                self._copy.wait_event(ev)
+                self._columns_to_host(T, ch, J_new, pol, J_pin, pol_pin)
+                mark("run %d on the host" % k, self._copy)
+                continue
+            s0, s1 = ch["s0"], ch["s1"]
             rc = self.lib.sdp_sweep_finalize(ctypes.byref(ch["tab_f"]), self._ptr(T.part_val),
                                              self._ptr(T.part_idx),
                                              ctypes.c_void_p(J_new.data_ptr() + 8 * s0),
@@ -1044,18 +1146,21 @@ class Engine(object):
                 _cabi.check(rc, "sdp_policy_values")
             ev = torch.cuda.Event()
             ev.record(st)
+            mark("run %d combined + mapped" % k, st)
             self._copy.wait_event(ev)
             with torch.cuda.stream(self._copy):
                 J_pin[s0:s1].copy_(J_new[s0:s1], non_blocking=True)
                 if nc:
                     pol_pin[s0:s1].copy_(pol[s0:s1], non_blocking=True)
+            mark("run %d on the host" % k, self._copy)
         done = torch.cuda.Event()
         done.record(self._copy)
         main.wait_event(done)
         if while_waiting is not None:
             while_waiting()          # host work hidden behind the sweep (the GPU is busy)
+        out = self.result_array(J_pin), self.result_array(pol_pin)      # (wrapped while the GPU works)
         done.synchronize()
-        return self.result_array(J_pin), self.result_array(pol_pin)
+        return out
 
     def gather_argmin(self, T):
         """full-grid int32 argmin (device) of the last sweep.  With the peer-memory exchange every

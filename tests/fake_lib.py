@@ -460,6 +460,46 @@ class FakeLib(object):
         self.launches += 1
         return 0
 
+    def sdp_sweep_finalize_cols(self, tref, part_val, part_idx, J_out, argmin_out, glob_cols, col_begin,
+                                nc, lo, hi, npts, pol, beside_sweep, stream):
+        """the combine of a view on the columns [col_begin, col_begin + n_cols): results in grid
+        order into whole-grid arrays; nc > 0: the control values too"""
+        T = tref._obj
+        assert T.layout == _cabi.LAYOUT_COLUMN_FACTORED and T.n_states % T.n_cols == 0
+        assert 0 <= col_begin and col_begin + T.n_cols <= glob_cols
+        n_rows = T.n_states // T.n_cols
+        J_loc = np.zeros(T.n_states)
+        a_loc = np.zeros(T.n_states, dtype=np.int32)
+        rc = self.sdp_sweep_finalize(tref, part_val, part_idx, ctypes.c_void_p(J_loc.ctypes.data),
+                                     ctypes.c_void_p(a_loc.ctypes.data), stream)
+        if rc:
+            return rc
+        n_all = n_rows * glob_cols
+        Jo = _arr(J_out, n_all, ctypes.c_double).reshape(n_rows, glob_cols)
+        ao = _arr(argmin_out, n_all, ctypes.c_int32).reshape(n_rows, glob_cols)
+        Jo[:, col_begin:col_begin + T.n_cols] = J_loc.reshape(n_rows, T.n_cols)
+        ao[:, col_begin:col_begin + T.n_cols] = a_loc.reshape(n_rows, T.n_cols)
+        if nc > 0:
+            g = (np.arange(n_rows)[:, None] * glob_cols + col_begin + np.arange(T.n_cols)[None, :]).reshape(-1)
+            LO = _arr(lo, n_all * nc, ctypes.c_double).reshape(n_all, nc)[g].copy()
+            HI = _arr(hi, n_all * nc, ctypes.c_double).reshape(n_all, nc)[g].copy()
+            NP = _arr(npts, n_all * nc, ctypes.c_int32).reshape(n_all, nc)[g].copy()
+            out = np.zeros((len(g), nc))
+            self.sdp_policy_values(len(g), nc, ctypes.c_void_p(LO.ctypes.data), ctypes.c_void_p(HI.ctypes.data),
+                                   ctypes.c_void_p(NP.ctypes.data), ctypes.c_void_p(a_loc.ctypes.data),
+                                   ctypes.c_void_p(out.ctypes.data), stream)
+            _arr(pol, n_all * nc, ctypes.c_double).reshape(n_all, nc)[g] = out
+        return 0
+
+    def sdp_memcpy_2d(self, dst, dpitch, src, spitch, width, height, stream):
+        assert dpitch >= width and spitch >= width
+        if width and height:
+            S = _arr(src, (height - 1) * spitch + width, ctypes.c_uint8)
+            D = _arr(dst, (height - 1) * dpitch + width, ctypes.c_uint8)
+            for r in range(height):
+                D[r * dpitch:r * dpitch + width] = S[r * spitch:r * spitch + width]
+        return 0
+
     def _column_partials(self, T, d, J, strides, orders, items, p, pv, pi, Us):
         """layout CF the way k_sweep_fact_column does it: one CTA per segment of the item
         list; at every column change the table R[row][w] = inner interpolation over the axes

@@ -1093,6 +1093,72 @@ def test_column_hoist_band_launch_plan(product, monkeypatch):
     assert torch.equal(J_again.view(torch.int64), J_ref.view(torch.int64))
 
 
+def test_column_piece_launch_plan(product, monkeypatch):
+    """the launch sequence of value_iteration's large-sweep path for layout CF with one band,
+    replayed on the numpy model: pre-pass once, then per PIECE OF COLUMNS one streaming launch over
+    the piece's own CTA segments, one combine launch on the piece's view that also maps the argmin
+    to control values, and 2-D copies of the piece's columns into the C-order result arrays - the
+    union must equal the one-launch sweep followed by sdp_policy_values"""
+    import ctypes
+    import torch
+    import workloads as wl
+    from stodynprog_b200.engine import Engine
+    monkeypatch.setattr(Engine, "COLUMN_PIECES", (0.4, 0.3, 0.2, 0.1))
+    api = _Api(product, "model", "state_minor", "auto", "on")
+    sv = wl.storage_ar1(api, n_E=70, n_P=11, n_w=3, steps=(1.0, 0.1)).solver
+    sv.column_hoist = "on"
+    T = sv.sweep_tables()
+    eng = sv.engine
+    n_rows, n_cols, nc = 70, 11, 2
+    n_grid = n_rows * n_cols
+    assert T.column and len(T.bands["tiles"]) == 1 and T.n_cols == n_cols
+    J = torch.from_numpy(np.random.default_rng(3).standard_normal(n_grid))
+    J_ref = torch.empty(n_grid, dtype=torch.float64)
+    eng.sweep(T, J, J_ref)
+    argmin_ref = T.argmin[:n_grid].clone()
+    pol_ref = eng.policy_values(T, argmin_ref)
+    plan = eng._chunk_plan(T)
+    assert plan is eng._chunk_plan(T) and len(plan) == 4
+    assert [ch["c0"] for ch in plan][0] == 0 and [ch["c1"] for ch in plan][-1] == n_cols
+    assert all(a["c1"] == b["c0"] and a["c0"] < a["c1"] for a, b in zip(plan, plan[1:]))
+    widths = [ch["c1"] - ch["c0"] for ch in plan]
+    assert widths[0] == max(widths) and sum(widths) == n_cols
+    T.part_val.fill_(float("nan"))
+    T.argmin.fill_(-7)
+    J_new = torch.full((n_grid,), float("nan"), dtype=torch.float64)
+    pol = torch.full((n_grid, nc), float("nan"), dtype=torch.float64)
+    J_host = torch.full((n_grid,), float("nan"), dtype=torch.float64)
+    pol_host = torch.full((n_grid, nc), float("nan"), dtype=torch.float64)
+    eng._copy = type("S", (), {"cuda_stream": 0})()
+    lib = eng.lib
+    assert lib.sdp_column_table(ctypes.byref(T.grid), ctypes.byref(T.c_tables), eng._ptr(J), eng.stream) == 0
+    tpc = T.bands["tiles"][0]
+    for ch in plan:
+        seg = ch["keep"].numpy()
+        i0, i1 = (int(T.item_begin_host[c * tpc]) for c in (ch["c0"], ch["c1"]))
+        assert seg[0] == i0 and seg[-1] == i1 and np.all(np.diff(seg) >= 0) and i1 > i0
+        assert ch["tab_p"].col_table_ready == 1 and ch["tab_p"].n_segs == len(seg) - 1
+        assert ch["tab_f"].n_cols == ch["c1"] - ch["c0"] and ch["tab_f"].n_states == n_rows * ch["tab_f"].n_cols
+        assert lib.sdp_sweep_partials(ctypes.byref(T.grid), ctypes.byref(ch["tab_p"]), eng._ptr(J), ch["pv"],
+                                      ch["pi"], eng.stream) == 0
+        assert lib.sdp_sweep_finalize_cols(
+            ctypes.byref(ch["tab_f"]), eng._ptr(T.part_val), eng._ptr(T.part_idx), eng._ptr(J_new),
+            eng._ptr(T.argmin), n_cols, ch["c0"], nc, eng._ptr(T.lo_dev), eng._ptr(T.hi_dev),
+            eng._ptr(T.npts_dev), eng._ptr(pol), int(ch is not plan[-1]), eng.stream) == 0
+        eng._columns_to_host(T, ch, J_new, pol, J_host, pol_host)
+    for got in (J_new, J_host):
+        assert torch.equal(got.view(torch.int64), J_ref.view(torch.int64))
+    for got in (pol, pol_host):
+        assert torch.equal(got.view(torch.int64), pol_ref.reshape(n_grid, nc).view(torch.int64))
+    assert torch.equal(T.argmin[:n_grid], argmin_ref)
+    # fewer columns than pieces: as many pieces as there are columns to cut
+    sv2 = wl.storage_ar1(api, n_E=40, n_P=2, n_w=3, steps=(1.0, 0.1)).solver
+    sv2.column_hoist = "on"
+    T2 = sv2.sweep_tables()
+    p2 = sv2.engine._chunk_plan(T2)
+    assert [(ch["c0"], ch["c1"]) for ch in p2] == [(0, 1), (1, 2)]
+
+
 def test_column_bands_choice(product, monkeypatch):
     """row bands of layout CF: none on several ranks or small slabs, whole tiles of 32 rows,
     cut by the controls of the rows"""
@@ -1103,7 +1169,7 @@ def test_column_bands_choice(product, monkeypatch):
     monkeypatch.setattr(Engine, "COLUMN_BANDS", "1")
     assert eng._column_bands(w, 9) == [0, 2000]
     monkeypatch.setattr(Engine, "COLUMN_BANDS", "auto")
-    assert eng._column_bands(w, 9) == [0, 2000]            # no GPU: nothing to overlap
+    assert eng._column_bands(w, 9) == [0, 2000]            # results leave by pieces of columns
     monkeypatch.setattr(Engine, "COLUMN_BANDS", "3")
     assert eng._column_bands(w, 9) == [0, 928, 1408, 2000]
     assert eng._column_bands(np.r_[np.full(1000, 100.0), np.full(1000, 300.0)], 9) == [0, 1280, 1600, 2000]
@@ -1313,8 +1379,8 @@ def test_device_argument_is_honoured(product, port):
 @gpu
 def test_config5_full_size_against_port(cuda_api, port):
     """BASELINE configs[4] at FULL size - 2000 x 500 states x 129..256 controls x 9 nodes,
-    1 848 240 000 backups per sweep - through the default tables (layout CF, three row bands):
-    `value_iteration` (results streamed band by band, Engine.sweep_to_host) and the
+    1 848 240 000 backups per sweep - through the default tables (layout CF, one band):
+    `value_iteration` (results streamed by pieces of columns, Engine.sweep_to_host) and the
     device-resident loop (Engine.sweep), 1 000 seeded random states against the oracle port
     (stodynprog.py:639-691): policies exact, J within 1e-10."""
     import workloads as wl
@@ -1326,7 +1392,8 @@ def test_config5_full_size_against_port(cuda_api, port):
     J0 = np.random.default_rng(3).standard_normal(dims)
     J, pol = sv.value_iteration(J0, report_time=False)
     T = sv.last_tables
-    assert T.layout_name == "column_factored" and len(T.bands["tiles"]) == 3
+    assert T.layout_name == "column_factored" and len(T.bands["tiles"]) == 1
+    assert sv.engine.can_overlap_results(T) and len(sv.engine._chunk_plan(T)) == 4
     assert T.n_backups_total == 1848240000
     Js, pols, info = sv.solve_value_iteration(J_zero=J0, max_iter=1)
     assert np.array_equal(J.view(np.int64), Js.view(np.int64)) and np.array_equal(pol, pols)
@@ -1447,6 +1514,51 @@ def test_overlapped_result_copy_is_bit_identical(product, layout, compress):
                 Engine.PINNED_RESULT_BUDGET = budget
         finally:
             Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = saved
+
+
+@gpu
+@pytest.mark.parametrize("case", ["plain", "W4", "pairs", "uneven", "small_off"])
+def test_column_pieces_overlapped_result_copy(product, case, monkeypatch):
+    """layout CF (one band), large-sweep path of value_iteration: the column tables are tabulated
+    once, every piece of columns is swept by its own launch on alternating streams, combined and
+    mapped to control values by one launch (the 128-thread combine that fits next to a streaming
+    CTA, or the 1024-thread one) and copied to its columns of the host arrays (2-D copies) while
+    the next pieces compute - same J and policies as the plain path and as layout BF"""
+    import workloads as wl
+    from stodynprog_b200 import _cabi
+    from stodynprog_b200.engine import Engine
+    monkeypatch.setattr(Engine, "COLUMN_PIECES", (0.2, 0.5, 0.3) if case == "uneven" else (0.5, 0.25, 0.15, 0.1))
+    lib = _cabi.load_library()
+    lib.sdp_set_option(b"small_combine", 0 if case == "small_off" else 1)
+    try:
+        res = {}
+        for colmode in ("off", "on"):
+            api = _Api(product, "cuda", "state_minor", "auto", "on")
+            sv = wl.storage_ar1(api, n_E=400, n_P=37, n_w=4 if case == "W4" else 9, steps=(0.5, 0.1)).solver
+            sv.column_hoist = colmode
+            sv.column_pairs = "on" if case == "pairs" else "off"
+            J0 = np.random.default_rng(9).standard_normal(sv._state_grid_shape)
+            monkeypatch.setattr(Engine, "OVERLAP_MIN_BACKUPS", 1 << 62)
+            monkeypatch.setattr(Engine, "OVERLAP_MIN_ITEMS", 1 << 62)
+            J_a, pol_a = sv.value_iteration(J0, report_time=False)
+            T = sv.last_tables
+            assert not sv.engine.can_overlap_results(T) and T.column == (colmode == "on")
+            monkeypatch.setattr(Engine, "OVERLAP_MIN_BACKUPS", 0)
+            monkeypatch.setattr(Engine, "OVERLAP_MIN_ITEMS", 0)
+            assert sv.engine.can_overlap_results(T)
+            if T.column:
+                plan = sv.engine._chunk_plan(T)
+                assert len(T.bands["tiles"]) == 1 and len(plan) == len(Engine.COLUMN_PIECES)
+                assert all(ch["kind"] == "cols" for ch in plan) and T.pairs == (case == "pairs")
+            for _ in range(3):
+                J_b, pol_b = sv.value_iteration(J0, report_time=False)
+                assert np.array_equal(J_a, J_b) and np.array_equal(pol_a, pol_b)
+            J_c, pol_c = sv.value_iteration(J_b, report_time=False)       # page-locked input, second sweep
+            res[colmode] = (J_a, pol_a, J_c, pol_c)
+        for a, b in zip(res["off"], res["on"]):
+            assert np.array_equal(a.view(np.int64), b.view(np.int64))
+    finally:
+        lib.sdp_set_option(b"small_combine", 1)
 
 
 @gpu
