@@ -1107,7 +1107,7 @@ static Tuning& tuning() {
         x.col_threads = clampi(env_int("SDP_COL_THREADS", 768), 128, 768) / 32 * 32;
         x.col_ub = env_int("SDP_COL_UB", 2) == 1 ? 1 : 2;
         x.col_pf = env_int("SDP_COL_PF", 2) == 1 ? 1 : 2;
-        x.col_prepass = clampi(env_int("SDP_COL_PREPASS", 2), 0, 2);
+        x.col_prepass = clampi(env_int("SDP_COL_PREPASS", 3), 0, 3);
         x.col_dynamic = env_int("SDP_COL_DYNAMIC", 1) != 0;
         x.dbg_exchange = 0;
         x.pdl = env_int("SDP_PDL", 1) != 0;
@@ -1134,7 +1134,7 @@ extern "C" int sdp_set_option(const char* name, int value) {
     else if (!strcmp(name, "col_threads")) t.col_threads = clampi(value, 128, 768) / 32 * 32;
     else if (!strcmp(name, "col_ub")) t.col_ub = (value == 1) ? 1 : 2;
     else if (!strcmp(name, "col_pf")) t.col_pf = (value == 1) ? 1 : 2;
-    else if (!strcmp(name, "col_prepass")) t.col_prepass = clampi(value, 0, 2);
+    else if (!strcmp(name, "col_prepass")) t.col_prepass = clampi(value, 0, 3);
     else if (!strcmp(name, "col_dynamic")) t.col_dynamic = value != 0;
     else if (!strcmp(name, "dbg_exchange")) t.dbg_exchange = value;
     else if (!strcmp(name, "pdl")) t.pdl = value != 0;
@@ -1957,7 +1957,7 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
                     double inv_stride0, PVals PV, int64_t pitch, int prepass, int dynamic) {
     constexpr int NW = D - 1;
     extern __shared__ __align__(128) unsigned char csm[];
-    __shared__ int next_item;                           // dynamic hand-out of the items of a column
+    __shared__ int next_item[2];                        // dynamic hand-out of the items of a column (two, used in turn)
     double* R_sh = reinterpret_cast<double*>(csm);      // [order[0]][P] + slack = `pitch` doubles
     __shared__ int cw_sh[WM];
     __shared__ double lw_sh[NW][WM];
@@ -1966,6 +1966,7 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&tbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        next_item[0] = next_item[1] = 0;
     }
     cudaGridDependencySynchronize();       // (programmatic dependent launch: the pre-pass's column tables)
     __syncthreads();
@@ -1977,6 +1978,7 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
 
     int64_t i = T.seg_begin[blockIdx.x];
     const int64_t seg_end = T.seg_begin[blockIdx.x + 1];
+    int turn = 0;                    // which of the two item counters this column run uses
     while (i < seg_end) {
         // (positions i index the item list directly, or through T.item_order: the bands of a
         // column back to back, so that a device-resident sweep loads each column's table once)
@@ -1984,10 +1986,15 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
         const int64_t run_end = T.run_end[i];     // end of the run of positions sharing this table
         const int64_t e = run_end < seg_end ? run_end : seg_end;
         __syncthreads();                 // the previous column's readers are done with R
-        if (threadIdx.x == 0) next_item = 0;
-        if (prepass == 2) {
+        // (the counter of the NEXT run is cleared now: nobody touches it during this run)
+        if (threadIdx.x == 0) next_item[turn ^ 1] = 0;
+        // prepass 2: the table arrives by bulk copy while the warps already take their first item
+        // and issue its first loads from the (x,u) stream; each thread waits on the copy's barrier
+        // just before its first read of the table (`have_table`)
+        bool have_table = prepass < 2;
+        if (prepass >= 2) {
             // the column's table, tabulated by k_column_table, is one contiguous block: one
-            // thread hands it to the TMA engine in <= 32 KB pieces, everybody waits on the barrier
+            // thread hands it to the TMA engine in <= 32 KB pieces
             if (threadIdx.x == 0) {
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(T.col_table + (int64_t)col * pitch);
                 const uint32_t bytes = (uint32_t)(pitch * 8);
@@ -1996,8 +2003,10 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
                 for (uint32_t o = 0; o < bytes; o += 32768u)
                     bulk_g2s(smem_u32(csm + o), src + o, min(32768u, bytes - o), bar);
             }
-            mbar_wait(smem_u32(&tbar), tphase);
-            tphase ^= 1u;
+            if (prepass == 2) {          // (3: the wait moves behind the first item's loads)
+                mbar_wait(smem_u32(&tbar), tphase);
+                have_table = true;
+            }
         } else if (prepass) {
             const double2* __restrict__ src = reinterpret_cast<const double2*>(T.col_table + (int64_t)col * pitch);
             double2* dst = reinterpret_cast<double2*>(R_sh);
@@ -2030,14 +2039,14 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
                 R_sh[r * P + w] = Lerp<double, D, 1>::eval(Jprev, r * stride0 + cw_sh[w], G.stride, lam);
             }
         }
-        __syncthreads();
+        if (prepass < 2) __syncthreads();
 
         // the warps share the items of the column: round-robin, or (dynamic) first come first
         // served - the items differ in length and a column piece may hold only a few of them
         for (int round = 0;; ++round) {
             int k = round * nwarps + warp;
             if (dynamic) {
-                if (lane == 0) k = atomicAdd(&next_item, 1);
+                if (lane == 0) k = atomicAdd(&next_item[turn], 1);
                 k = __shfl_sync(0xffffffffu, k, 0);
             }
             const int64_t pos = i + k;
@@ -2065,6 +2074,10 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
                     g_n[s][b] = __ldcs(gp + o);
                     l_n[s][b] = __ldcs(lup + o);
                 }
+            if (!have_table) {           // (warp-uniform; first item of the run only)
+                mbar_wait(smem_u32(&tbar), tphase);
+                have_table = true;
+            }
             for (int uu0 = 0; uu0 < it.u_count; uu0 += UB * PF) {
 #pragma unroll
                 for (int s = 0; s < PF; ++s) {
@@ -2120,6 +2133,13 @@ k_sweep_fact_column(GridT<double> G, SdpTables T, const double* __restrict__ Jpr
             part_val[item_id * 32 + lane] = best_v;
             part_idx[item_id * 32 + lane] = best_i;
         }
+        if (prepass >= 2) {
+            // a warp that got no item of this run still observes the copy's completion: thread 0
+            // re-arms the barrier for the next table only after every thread has seen this phase
+            if (!have_table) mbar_wait(smem_u32(&tbar), tphase);
+            tphase ^= 1u;
+        }
+        turn ^= 1;
         i = e;
     }
 }
@@ -2408,8 +2428,8 @@ template <int D>
 static int launch_fact_column(const GridT<double>& G, const SdpTables& T, const double* Jprev,
                               double* part_val, int32_t* part_idx, cudaStream_t st) {
     if (T.col_pairs) {
-        if (tuning().col_prepass != 2)
-            return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF with col_pairs needs col_prepass = 2");
+        if (tuning().col_prepass < 2)
+            return fail(SDP_EINVAL, "%s", "sdp_sweep: layout CF with col_pairs needs col_prepass >= 2");
         if (T.W <= 3) return launch_fact_column2_w<D, 3>(G, T, Jprev, part_val, part_idx, st);
         if (T.W <= 5) return launch_fact_column2_w<D, 5>(G, T, Jprev, part_val, part_idx, st);
         return launch_fact_column2_w<D, 9>(G, T, Jprev, part_val, part_idx, st);

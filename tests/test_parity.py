@@ -931,7 +931,8 @@ def test_column_hoist_is_bit_identical(product, backend, which):
             Jr, polr = ref.value_iteration(J0, report_time=False)
             for threads, ub, pf, pre in ((128, 1, 1, 1), (256, 2, 1, 0), (512, 1, 2, 0), (96, 2, 2, 2),
                                          (160, 1, 2, 1), (640, 2, 1, 2), (640, 2, 2, 1), (768, 2, 1, 2),
-                                         (768, 1, 2, 0), (704, 1, 1, 2)):
+                                         (768, 1, 2, 0), (704, 1, 1, 2), (768, 2, 1, 3), (640, 1, 2, 3),
+                                         (64, 2, 2, 3)):
                 lib.sdp_set_option(b"col_threads", threads)
                 lib.sdp_set_option(b"col_ub", ub)
                 lib.sdp_set_option(b"col_pf", pf)
@@ -940,14 +941,14 @@ def test_column_hoist_is_bit_identical(product, backend, which):
                 J2, pol2 = col.value_iteration(J0, report_time=False)
                 assert _same_bits(Jr, J2), (threads, ub, pf, pre)
                 assert np.array_equal(polr, pol2, equal_nan=True), (threads, ub, pf, pre)
-                if pre == 2:            # (two rows per lane copies its table with the TMA engine only)
+                if pre >= 2:            # (two rows per lane copies its table with the TMA engine only)
                     J3, pol3 = col2.value_iteration(J0, report_time=False)
                     assert _same_bits(Jr, J3) and np.array_equal(polr, pol3, equal_nan=True), (threads, "pairs")
         finally:
             lib.sdp_set_option(b"col_threads", 768)
             lib.sdp_set_option(b"col_ub", 2)
             lib.sdp_set_option(b"col_pf", 2)
-            lib.sdp_set_option(b"col_prepass", 2)
+            lib.sdp_set_option(b"col_prepass", 3)
             lib.sdp_set_option(b"col_dynamic", 1)
 
 
