@@ -60,6 +60,17 @@ if world == 1:
     sv.table_layout, sv.column_hoist = "state_minor", "on"
     check("column CF, three bands, W = 3", sv, so, np.random.default_rng(2).standard_normal((330, 3)), 1)
     Engine.COLUMN_BANDS = "auto"
+    # the host path of large sweeps: pieces of columns on alternating streams, combine + control
+    # values in one launch (the small variant beside the next sweep, the wide one at the end),
+    # 2-D copies into the result arrays
+    saved = Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS
+    Engine.OVERLAP_MIN_BACKUPS = Engine.OVERLAP_MIN_ITEMS = 0
+    kw = dict(n_E=100, n_P=37, n_w=9, steps=(0.5, 0.1))
+    sv, so = wl.storage_ar1(sdp, **kw).solver, wl.storage_ar1(port, **kw).solver
+    sv.table_layout, sv.column_hoist = "state_minor", "on"
+    check("column CF, pieces of columns", sv, so, np.random.default_rng(6).standard_normal((100, 37)))
+    assert sv.engine.can_overlap_results(sv.last_tables) and len(sv.engine._chunk_plan(sv.last_tables)) == 4
+    Engine.OVERLAP_MIN_BACKUPS, Engine.OVERLAP_MIN_ITEMS = saved
     prob, ora = wl.searev(sdp, n_E=7, n_S=9, n_A=9), wl.searev(port, n_E=7, n_S=9, n_A=9)
     prob.solver.control_steps = ora.solver.control_steps = (.05,)
     check("SEAREV 3-D, AF", prob.solver, ora.solver, np.zeros((7, 9, 9)), 1)
