@@ -2805,10 +2805,20 @@ k_combine_column(int n_rows, int n_cols, int tiles_per_col, int col_blocks,
             const int64_t tile = (int64_t)c * tiles_per_col + ty;
             double bv = CUDART_INF;
             int bi = INT_MAX;
-            for (int64_t k = item_begin[tile]; k < item_begin[tile + 1]; ++k) {
-                const double v = part_val[k * 32 + lane];
-                const int ix = part_idx[k * 32 + lane];
-                if (better(v, ix, bv, bi)) { bv = v; bi = ix; }
+            // (the partial minima of four items in flight at a time, compared in item order)
+            const int64_t k1 = item_begin[tile + 1];
+            for (int64_t k = item_begin[tile]; k < k1; k += 4) {
+                double v[4];
+                int ix[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t kk = (k + u < k1) ? k + u : k1 - 1;
+                    v[u] = part_val[kk * 32 + lane];
+                    ix[u] = part_idx[kk * 32 + lane];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k + u < k1 && better(v[u], ix[u], bv, bi)) { bv = v[u]; bi = ix[u]; }
             }
             v_sh[lane][warp] = bv;
             i_sh[lane][warp] = bi;
