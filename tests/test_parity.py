@@ -614,6 +614,50 @@ def test_abi_rejects_bad_arguments(eng):
         _cabi.check(rc, "sdp_cell_setup")
 
 
+@gpu
+def test_memcpy_2d_and_finalize_cols_through_the_abi(eng, cuda_api):
+    """sdp_memcpy_2d: a column range of a C-order device array into the same columns of a
+    page-locked host array, nothing else touched; argument checks of the two entry points of the
+    column-piece path"""
+    import torch
+    import workloads as wl
+    from stodynprog_b200 import _cabi
+    lib = eng.lib
+    rows, cols = 37, 23
+    src = torch.arange(rows * cols, dtype=torch.float64, device=eng.device)
+    dst = torch.full((rows * cols,), -1.0, dtype=torch.float64).pin_memory()
+    c0, c1 = 5, 14
+    rc = lib.sdp_memcpy_2d(ctypes.c_void_p(dst.data_ptr() + 8 * c0), 8 * cols,
+                           ctypes.c_void_p(src.data_ptr() + 8 * c0), 8 * cols, 8 * (c1 - c0), rows, eng.stream)
+    _cabi.check(rc, "sdp_memcpy_2d")
+    eng.sync()
+    want = np.full((rows, cols), -1.0)
+    want[:, c0:c1] = np.arange(rows * cols, dtype=float).reshape(rows, cols)[:, c0:c1]
+    assert np.array_equal(dst.numpy().reshape(rows, cols), want)
+    assert lib.sdp_memcpy_2d(eng._ptr(dst), 8, eng._ptr(src), 8 * cols, 16, rows, eng.stream) == -1
+    assert b"sdp_memcpy_2d" in lib.sdp_last_error()
+    assert lib.sdp_memcpy_2d(None, 8 * cols, eng._ptr(src), 8 * cols, 8, rows, eng.stream) == -1
+    assert lib.sdp_memcpy_2d(eng._ptr(dst), 8 * cols, eng._ptr(src), 8 * cols, 0, rows, eng.stream) == 0
+    # finalize_cols: tables that are not in layout CF, a column range outside the grid, missing policy arrays
+    sv = wl.storage_ar1(cuda_api, n_E=70, n_P=6, n_w=9, steps=(0.3, 0.1)).solver
+    sv.table_layout, sv.column_hoist = "state_minor", "off"
+    T = sv.sweep_tables()
+    args = (eng._ptr(T.part_val), eng._ptr(T.part_idx), eng._ptr(T.J_out), eng._ptr(T.argmin))
+    assert lib.sdp_sweep_finalize_cols(ctypes.byref(T.c_tables), *args, 6, 0, 0, None, None, None, None, 0,
+                                       eng.stream) == -1
+    assert b"layout CF" in lib.sdp_last_error()
+    sv = wl.storage_ar1(cuda_api, n_E=70, n_P=6, n_w=9, steps=(0.3, 0.1)).solver
+    sv.table_layout, sv.column_hoist = "state_minor", "on"
+    T = sv.sweep_tables()
+    assert T.column
+    args = (eng._ptr(T.part_val), eng._ptr(T.part_idx), eng._ptr(T.J_out), eng._ptr(T.argmin))
+    assert lib.sdp_sweep_finalize_cols(ctypes.byref(T.c_tables), *args, 5, 0, 0, None, None, None, None, 0,
+                                       eng.stream) == -1          # 6 columns do not fit a grid of 5
+    assert lib.sdp_sweep_finalize_cols(ctypes.byref(T.c_tables), *args, 6, 0, 2, None, None, None, None, 0,
+                                       eng.stream) == -1          # nc > 0 without lo / hi / npts / pol
+    assert b"sdp_sweep_finalize_cols" in lib.sdp_last_error()
+
+
 # ---------------------------------------------------------------------------
 # host tabulation: one call per chunk of states == one call per state
 # ---------------------------------------------------------------------------
