@@ -9,6 +9,8 @@
 #   emu[:N,N]        scripts/dev_shard_emulation.py (shards of an N-GPU run timed on one GPU)
 #   ncu:WHICH        ncu --set full of the streaming kernel of WHICH in {large,ar1}, + launch list
 #   sanitize         compute-sanitizer memcheck / racecheck on small grids
+#   timeline[:VARS]  where the time of one value_iteration call goes (per variant of environment settings)
+#   emuopts:OPTS     streaming-kernel time on one GPU and on one shard of eight per set of library options
 #   py:SCRIPT[:ARGS] any script under scripts/
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
@@ -77,6 +79,24 @@ for STEP in "$@"; do
         echo "exit: $?" >> $L
         grep -v "Warning\|warn" $L | tail -25
       done ;;
+    timeline)
+      # timeline[:ENV=V;ENV=V ...]  the e2e timeline of value_iteration (scripts/dev_e2e_timeline.py) once
+      # per variant (environment settings separated by ';', variants by spaces), e.g.
+      #   timeline:SDP_COLUMN_PIECES=0.3,0.3,0.3,0.1+SDP_SMALL_COMBINE=0
+      : > $OUT/${TAG}_e2e_timeline.txt
+      for V in ${ARGS:-DEFAULT=1}; do
+        echo "== $V" >> $OUT/${TAG}_e2e_timeline.txt
+        env $(echo "$V" | tr ';' ' ') timeout 200 python scripts/dev_e2e_timeline.py >> $OUT/${TAG}_e2e_timeline.txt 2>&1
+      done
+      cat $OUT/${TAG}_e2e_timeline.txt ;;
+    emuopts)
+      # emuopts:OPT=V,OPT=V[+OPT=V ...]  one-GPU and 1/8-shard kernel times (columns) per set of library options
+      : > $OUT/${TAG}_emu_options.txt
+      for V in $ARGS; do
+        echo "== $V" >> $OUT/${TAG}_emu_options.txt
+        OPTS=$V AXES=columns timeout 300 python scripts/dev_shard_emulation.py 8 2>&1 | grep "^N=" >> $OUT/${TAG}_emu_options.txt
+      done
+      cat $OUT/${TAG}_emu_options.txt ;;
     py)
       S=${ARGS%% *}; A=""; [ "$ARGS" != "$S" ] && A=${ARGS#* }
       ( time run_py scripts/$S $A ) > $OUT/${TAG}_$(basename $S .py).txt 2>&1
