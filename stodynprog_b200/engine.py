@@ -1065,11 +1065,14 @@ class Engine(object):
 
     def sweep_to_host(self, T, J_prev, J_new, while_waiting=None):
         """One sweep of a single-rank slab, returning (J, pol) as host arrays in
-        page-locked memory.  The slab is swept in a few runs on two alternating
-        streams (so that the tail of one run is filled by the next); as soon as a run
-        is combined and its argmin mapped to control values (K3), a copy stream sends
-        that run's J and policy to the host while the following runs still compute.
-        Same kernels on sub-ranges of the same tables: bit-identical to `sweep`."""
+        page-locked memory.  The slab is swept in a few runs (`_chunk_plan`: ranges of
+        states, row bands of layout CF, or - layout CF with one band, the default - pieces
+        of columns) on two alternating streams (so that the tail of one run is filled by
+        the next); as soon as a run is combined and its argmin mapped to control values
+        (K3; one launch does both for a piece of columns), a copy stream sends that run's
+        J and policy to their place in the host arrays while the following runs still
+        compute.  Same kernels on sub-ranges of the same tables: bit-identical to `sweep`.
+        (stodynprog.py:496-499,517-521: J_k and pol_k are C-order arrays over the grid.)"""
         torch = _torch()
         dev = self.device
         n, nc = T.n_states, T.nb_control
