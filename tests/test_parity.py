@@ -1600,6 +1600,17 @@ def test_column_pieces_overlapped_result_copy(product, case, monkeypatch):
                 assert np.array_equal(J_a, J_b) and np.array_equal(pol_a, pol_b)
             J_c, pol_c = sv.value_iteration(J_b, report_time=False)       # page-locked input, second sweep
             res[colmode] = (J_a, pol_a, J_c, pol_c)
+            if T.column and case == "plain":
+                # page-locked result budget exhausted: the 2-D copies land in pageable memory, same values
+                import torch
+                budget = Engine.PINNED_RESULT_BUDGET
+                try:
+                    Engine.PINNED_RESULT_BUDGET = 0
+                    J_e, pol_e = sv.value_iteration(np.array(J_b), report_time=False)
+                    assert not torch.from_numpy(J_e).is_pinned()
+                    assert np.array_equal(J_e, J_c) and np.array_equal(pol_e, pol_c)
+                finally:
+                    Engine.PINNED_RESULT_BUDGET = budget
         for a, b in zip(res["off"], res["on"]):
             assert np.array_equal(a.view(np.int64), b.view(np.int64))
     finally:
