@@ -21,7 +21,7 @@ from .tablebuild import (                                        # noqa: F401  (
     COLUMN_HOIST_DEFAULT, SLAB_AXIS_DEFAULT, COLUMN_PAIRS_DEFAULT, ITEMS_TARGET,
     BuildPlan, ShardBuild, SweepTables, fill_c_tables, partition_by_weight, rebalance_bounds,
     make_items, pick_item_chunk, host_threads, pair_positions, column_order, item_run_ends,
-    column_segments, row_aligned, ColumnHoistRefused, _ColumnsNotApplicable)
+    column_segments, column_piece_cuts, row_aligned, ColumnHoistRefused, _ColumnsNotApplicable)
 
 __all__ = ["Engine", "SweepTables", "PolicyTables", "partition_by_weight", "rebalance_bounds",
            "column_order", "column_segments", "row_aligned"]
@@ -750,9 +750,7 @@ class Engine(object):
     # shares of the columns (by admissible controls) of the pieces, in sweep order: the copy of a
     # piece hides behind the pieces after it, the last piece's copy behind nothing
     COLUMN_PIECES = tuple(float(x) for x in os.environ.get("SDP_COLUMN_PIECES", "0.3,0.3,0.3,0.1").split(","))
-    # ... with the cuts moved to the nearest multiple of the CTA count when that is within a third
-    # of a piece: every CTA then sweeps WHOLE columns of the piece (a CTA that starts or ends a
-    # piece in the middle of a column pays an extra column table and barrier, ~10 us)
+    # ... with the cuts moved to multiples of the CTA count where that is close (column_piece_cuts)
     COLUMN_PIECES_ALIGN = os.environ.get("SDP_COLUMN_PIECES_ALIGN", "1") != "0"
 
     def _column_bands(self, row_weight, W):
@@ -1015,18 +1013,8 @@ class Engine(object):
         n_rows = T.n_states // n_cols
         first_item = T.item_begin_host[np.arange(n_cols + 1, dtype=np.int64) * tpc]      # per column
         csum = np.concatenate([[0], np.cumsum(T.item_u_count_host, dtype=np.float64)])[first_item]
-        cuts, acc = [0], 0.0
-        for f in self.COLUMN_PIECES[:-1]:
-            acc += f
-            c = int(np.searchsorted(csum, acc * csum[-1], side="left"))
-            n_ctas = T.sm_count * self.COLUMN_SEGS_PER_SM
-            if self.COLUMN_PIECES_ALIGN and n_cols >= 2 * n_ctas:
-                a = cuts[-1] + max(1, int(round((c - cuts[-1]) / float(n_ctas)))) * n_ctas
-                if abs(a - c) * 3 <= max(c - cuts[-1], 1):
-                    c = a
-            if cuts[-1] < c < n_cols:
-                cuts.append(c)
-        cuts.append(n_cols)
+        cuts = column_piece_cuts(csum, self.COLUMN_PIECES,
+                                 T.sm_count * self.COLUMN_SEGS_PER_SM if self.COLUMN_PIECES_ALIGN else 0)
         plan = []
         for c0, c1 in zip(cuts[:-1], cuts[1:]):
             # (positions of the work list - every item, or with two rows per lane the items of the

@@ -253,6 +253,29 @@ def column_segments(item_u_count, n_ctas):
     return np.asarray(seg, dtype=np.int64)
 
 
+def column_piece_cuts(col_csum, fractions, n_ctas=0):
+    """Layout CF, results handed out by pieces of columns: the column boundaries [0, ..., n_cols] of
+    the pieces.  `col_csum[c]` = weight of the columns before c (n_cols + 1 values); piece k takes
+    the share fractions[k] of the total weight (the last one the rest).  With n_ctas > 0 and at least
+    2 * n_ctas columns a cut moves to the nearest multiple of n_ctas columns past the previous cut
+    when that is within a third of the piece: every CTA then sweeps WHOLE columns of the piece
+    (a CTA that starts or ends a piece in the middle of a column pays an extra column table and
+    barrier, ~10 us).  Cuts that would leave an empty piece are dropped."""
+    col_csum = np.asarray(col_csum, dtype=np.float64)
+    n_cols = len(col_csum) - 1
+    cuts, acc = [0], 0.0
+    for f in fractions[:-1]:
+        acc += f
+        c = int(np.searchsorted(col_csum, acc * col_csum[-1], side="left"))
+        if n_ctas > 0 and n_cols >= 2 * n_ctas:
+            a = cuts[-1] + max(1, int(round((c - cuts[-1]) / float(n_ctas)))) * n_ctas
+            if abs(a - c) * 3 <= max(c - cuts[-1], 1):
+                c = a
+        if cuts[-1] < c < n_cols:
+            cuts.append(c)
+    return cuts + [n_cols]
+
+
 def row_aligned(bounds, n_cols):
     """slab boundaries moved to the nearest multiple of n_cols (whole rows of axis 0),
     kept monotone"""

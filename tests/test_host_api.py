@@ -255,6 +255,31 @@ def test_make_items_cuts_units_into_equal_runs():
     assert list(items["u_count"]) == [72, 68] and list(items["Upad"]) == [140, 140]
 
 
+def test_column_piece_cuts():
+    """pieces of columns for the host results of layout CF: a partition of the columns in sweep
+    order, never an empty piece, cuts on multiples of the CTA count where that is close"""
+    from hypothesis import given, settings, strategies as st
+    from stodynprog_b200.tablebuild import column_piece_cuts
+    # config #5 on a B200: 500 equal columns, 148 CTAs
+    even = np.arange(501, dtype=float)
+    assert column_piece_cuts(even, (0.3, 0.3, 0.3, 0.1), 148) == [0, 148, 296, 444, 500]
+    assert column_piece_cuts(even, (0.5, 0.25, 0.15, 0.1), 148) == [0, 296, 375, 450, 500]
+    assert column_piece_cuts(even, (0.5, 0.25, 0.15, 0.1), 0) == [0, 250, 375, 450, 500]
+    assert column_piece_cuts(even[:3], (0.3, 0.3, 0.3, 0.1), 148) == [0, 1, 2]
+    assert column_piece_cuts(even[:2], (0.5, 0.5), 148) == [0, 1]
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.floats(0.0, 50.0), min_size=1, max_size=700),
+           st.lists(st.floats(0.01, 1.0), min_size=1, max_size=6), st.integers(0, 200))
+    def prop(weights, fractions, n_ctas):
+        csum = np.concatenate([[0.0], np.cumsum(weights)])
+        cuts = column_piece_cuts(csum, tuple(fractions), n_ctas)
+        assert cuts[0] == 0 and cuts[-1] == len(weights)
+        assert all(a < b for a, b in zip(cuts, cuts[1:]))
+        assert len(cuts) - 1 <= len(fractions)
+    prop()
+
+
 def test_pick_item_chunk():
     from stodynprog_b200.engine import pick_item_chunk, ITEMS_TARGET
     # plenty of units: keep the long runs
